@@ -1,0 +1,191 @@
+"""Pins oracle/tdvc_oracle.py to vectors produced by the REAL reference (oracle/gen_golden.py).
+
+CPU only.  fp64 oracle vs fp64 reference output: 1e-9 (max-abs-normalised)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import golden, golden_shapes, relerr, stats
+from oracle import tdvc_oracle as O
+from oracle.cases import CASES, HP_STAGE1, HP_STAGE2_1, HP_STAGE2_2, rand_like
+from oracle.params import make_batch, make_state_dict
+
+TOL = 1e-9
+
+
+def _sd(g, seed, grad=True):
+    sd = make_state_dict(golden_shapes(g), seed=seed, dtype=torch.float64)
+    if grad:
+        for v in sd.values():
+            v.requires_grad_(True)
+    return sd
+
+
+def _check_grads(g, sd, tol=TOL, prefix="grad/", sprefix="gstat/"):
+    n_full = 0
+    for k, v in sd.items():
+        gr = v.grad if v.grad is not None else torch.zeros_like(v)
+        if prefix + k in g.files:
+            assert relerr(gr, g[prefix + k]) < tol, k
+            n_full += 1
+        ref = g[sprefix + k]
+        got = stats(gr)
+        assert abs(got[2] - ref[2]) <= tol * max(ref[2], 1e-30) * 10 + 1e-300, (k, got, ref)
+        assert abs(got[0] - ref[0]) <= tol * max(ref[1], 1e-30) * 10 + 1e-300, (k, got, ref)
+    return n_full
+
+
+@pytest.mark.parametrize("name", ["g_tiny", "g_full"])
+def test_generator(name):
+    g = golden(name)
+    cfg = CASES[name]
+    sd = _sd(g, cfg["seed"])
+    b = make_batch(cfg["B"], cfg["T"], cfg["nspk"], seed=cfg["seed"] + 1, frames_div=int(np.prod(cfg["ratios"])))
+    c_tgt = F.one_hot(b["label_tgt"], cfg["nspk"]).double()
+    y, subs, emb = O.generator(sd, b["signal_real"], c_tgt, b["c_f0_conv"], cfg["ratios"])
+    assert relerr(y, g["y"]) < TOL
+    assert relerr(emb, g["emb"]) < TOL
+    for i, s in enumerate(subs):
+        assert relerr(s, g[f"subs/{i}"]) < TOL
+    loss = (y * rand_like(y, 11)).sum() + sum((s * rand_like(s, 12 + i)).sum() for i, s in enumerate(subs)) \
+        + (emb * rand_like(emb, 20)).sum()
+    assert abs(loss.item() - float(g["loss"])) < 1e-9 * max(1.0, abs(float(g["loss"])))
+    loss.backward()
+    assert _check_grads(g, sd) > 0
+
+
+@pytest.mark.parametrize("name,kind", [("d_tiny", "cmb"), ("msd_tiny", "msd"), ("d_full", "cmb")])
+def test_discriminator(name, kind):
+    g = golden(name)
+    cfg = CASES["d_full" if name == "d_full" else "d_tiny"]
+    sd = _sd(g, cfg["seed"])
+    b = make_batch(cfg["B"], cfg["T"], cfg["nspk"], seed=cfg["seed"] + 1, frames_div=320)
+    x = b["signal_real"].clone().requires_grad_(True)
+    kw = dict(num_disc=cfg["num_disc"], num_layers=cfg["d_layers"])
+    if kind == "cmb":
+        subs = [(rand_like(torch.empty(cfg["B"], 1, cfg["T"] // 4), 31) * 0.1).requires_grad_(True),
+                (rand_like(torch.empty(cfg["B"], 1, cfg["T"] // 2), 32) * 0.1).requires_grad_(True)]
+        outs, feats = O.cmb_discriminator(sd, x, b["label_src"], subs, **kw)
+    else:
+        subs = []
+        outs, feats = O.multiscale_discriminator(sd, x, b["label_src"], **kw)
+    for i, o in enumerate(outs):
+        assert relerr(o, g[f"outs/{i}"]) < TOL
+    loss = sum(((o - 1) ** 2).mean() for o in outs)
+    for i, fl in enumerate(feats):
+        for j, f in enumerate(fl):
+            ref = g[f"fstat/{i}.{j}"]
+            assert abs(stats(f)[2] - ref[2]) < TOL * ref[2] * 10
+            if f"feat/{i}.{j}" in g.files:
+                assert relerr(f, g[f"feat/{i}.{j}"]) < TOL
+            loss = loss + (f * rand_like(f, 100 + 10 * i + j)).mean()
+    loss.backward()
+    _check_grads(g, sd)
+    assert relerr(x.grad, g["dx"]) < TOL
+    for i, s in enumerate(subs):
+        assert relerr(s.grad, g[f"dsubs/{i}"]) < TOL
+
+
+def test_cin():
+    g = golden("cin")
+    C, ncond, B, T = 12, 7, 3, 50
+    shapes = {"embedding.weight": (2 * C, ncond), "embedding.bias": (2 * C,),
+              "embedding_conv.weight": (2 * C, ncond + 1, 5), "embedding_conv.bias": (2 * C,)}
+    assert list(shapes) == [str(k) for k in g["cin_keys"]]
+    sd = {("m." + k): v.requires_grad_(True) for k, v in make_state_dict(shapes, seed=5).items()}
+    x = (rand_like(torch.empty(B, C, T), 41) * 2 + 0.3).requires_grad_(True)
+    c2 = rand_like(torch.empty(B, ncond), 42).requires_grad_(True)
+    c3 = rand_like(torch.empty(B, ncond + 1, T), 43).requires_grad_(True)
+    y2 = O.cond_instance_norm(sd, "m", x, c2)
+    assert relerr(y2, g["y2"]) < TOL
+    (y2 * rand_like(y2, 44)).sum().backward()
+    assert relerr(x.grad, g["dx2"]) < TOL and relerr(c2.grad, g["dc2"]) < TOL
+    for k in ("embedding.weight", "embedding.bias"):
+        assert relerr(sd["m." + k].grad, g["g2/" + k]) < TOL
+    x.grad = None
+    y3 = O.cond_instance_norm(sd, "m", x, c3)
+    assert relerr(y3, g["y3"]) < TOL
+    (y3 * rand_like(y3, 45)).sum().backward()
+    assert relerr(x.grad, g["dx3"]) < TOL and relerr(c3.grad, g["dc3"]) < TOL
+    # CINResnetBlock
+    keys = [str(k) for k in g["blk_keys"]]
+    bshapes = {}
+    for k in keys:
+        if k.startswith("block.0.") or k.startswith("block.3."):
+            bshapes[k] = shapes[k.split(".", 2)[2]]
+        elif k == "block.2.weight":
+            bshapes[k] = (C, C, 7)
+        elif k.endswith(".weight"):
+            bshapes[k] = (C, C, 1)
+        else:
+            bshapes[k] = (C,)
+    bsd = {("b." + k): v.requires_grad_(True) for k, v in make_state_dict(bshapes, seed=6).items()}
+    xb = rand_like(torch.empty(B, C, T), 46).requires_grad_(True)
+    yb = O.cin_resnet_block(bsd, "b", xb, c2.detach(), dilation=3, kernel_size=7)
+    assert relerr(yb, g["yb"]) < TOL
+    (yb * rand_like(yb, 47)).sum().backward()
+    assert relerr(xb.grad, g["dxb"]) < TOL
+    for k in keys:
+        if "gb/" + k in g.files:
+            assert relerr(bsd["b." + k].grad, g["gb/" + k]) < TOL, k
+
+
+def test_losses():
+    g = golden("losses")
+    B, T = 3, 8960
+    a = (rand_like(torch.empty(B, 1, T), 51) * 0.1).requires_grad_(True)
+    r = rand_like(torch.empty(B, 1, T), 52) * 0.1
+    mel = O.mel_loss(a, r)
+    assert abs(mel.item() - float(g["mel"])) < 1e-9 * abs(float(g["mel"]))
+    mel.backward()
+    assert relerr(a.grad, g["dmel"]) < 1e-8
+    X = F.normalize(rand_like(torch.empty(B, 16, 28), 53), dim=1).requires_grad_(True)
+    Y = F.normalize(rand_like(torch.empty(B, 16, 28), 54), dim=1).requires_grad_(True)
+    con = O.contrastive_loss(X, Y, torch.as_tensor(g["raw0"]).long(), torch.as_tensor(g["raw1"]).long())
+    assert abs(con.item() - float(g["con"])) < 1e-9 * abs(float(g["con"]))
+    con.backward()
+    assert relerr(X.grad, g["dX"]) < TOL and relerr(Y.grad, g["dY"]) < TOL
+    fs = [[rand_like(torch.empty(2, 4, 30), 60 + i * 3 + j) for j in range(3)] for i in range(2)]
+    fr = [[rand_like(torch.empty(2, 4, 30), 80 + i * 3 + j) for j in range(3)] for i in range(2)]
+    assert abs(O.feat_loss(fs, fr).item() - float(g["feat"])) < 1e-12
+
+
+@pytest.mark.parametrize("name,hp,case", [("step_tiny_s1", HP_STAGE1, "step_tiny"),
+                                          ("step_tiny_s21", HP_STAGE2_1, "step_tiny"),
+                                          ("step_tiny_s22", HP_STAGE2_2, "step_tiny"),
+                                          ("step_full_s1", HP_STAGE1, "step_full")])
+def test_train_step(name, hp, case):
+    """One G+D iteration (train.py:259-491) against the reference's own modules driven by
+    oracle/gen_golden.py:ref_step."""
+    from oracle.step import oracle_step
+    g = golden(name)
+    cfg = CASES[case]
+    out = oracle_step(cfg, hp, dtype=torch.float64)
+    for k in ("d_loss_real", "d_loss_fake", "g_adv", "g_idt", "g_cont", "g_rec", "g_loss"):
+        ref = float(np.asarray(g[k]).reshape(-1)[0])
+        got = float(out[k])
+        assert abs(got - ref) <= 1e-9 * max(1.0, abs(ref)), (k, got, ref)
+    assert relerr(out["fake"], g["fake"]) < TOL
+    for which in ("D", "G"):
+        for k, gr in out[which + "_grad"].items():
+            ref = g[f"{which}_grad/{k}"]
+            got = stats(gr)
+            assert abs(got[2] - ref[2]) <= 1e-8 * max(ref[2], 1e-30) + 1e-300, (which, k, got, ref)
+
+
+@pytest.mark.parametrize("gname,case,which", [("g_tiny", "g_tiny", "G"), ("g_full", "g_full", "G"),
+                                               ("d_tiny", "d_tiny", "D"), ("d_full", "d_full", "D")])
+def test_state_dict_layout(gname, case, which):
+    """The analytic key/shape tables (oracle/step.py) equal the reference modules' state_dict()."""
+    from oracle.step import discriminator_shapes, generator_shapes
+    g = golden(gname)
+    ref = golden_shapes(g)
+    mine = generator_shapes(CASES[case]) if which == "G" else discriminator_shapes(CASES[case])
+    assert set(ref) == set(mine)
+    for k in ref:
+        assert tuple(ref[k]) == tuple(mine[k]), k
+    if case == "g_full":
+        assert len(ref) == 743
+    if case == "d_full":
+        assert len(ref) == 60
