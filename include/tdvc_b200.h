@@ -1,0 +1,164 @@
+/* tdvc_b200.h -- C ABI of libtdvc_b200.so: the sm_100a kernels behind td-vc-gan's
+ * Generator / ConditionalInstanceNorm / Discriminator / GAN-loss hot path.
+ *
+ * The reference (vicpc00/td-vc-gan) has NO FFI of its own: it is pure PyTorch and every
+ * arithmetic op below is an ATen call made from its nn.Modules.  Each entry point therefore
+ * cites the reference call site (file:line, relative to the reference root) whose ATen op it
+ * replaces; the Python host (td-vc-gan_b200/tdvc/ops.py) binds them with ctypes and wraps them
+ * in torch.autograd.Functions, see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers to DEVICE memory, sizes as int/int64, `stream` is a cudaStream_t passed
+ *     as void*; no torch types.  The caller allocates every output and workspace.
+ *   - activations are NCW, contiguous, fp32 (layout of the reference's tensors).
+ *   - every function returns 0 on success, a negative tdvc_status otherwise;
+ *     tdvc_last_error() gives a thread-local message.  Nothing synchronises the device.
+ *   - no hidden global state except lazily cached function attributes / driver entry points.
+ */
+#ifndef TDVC_B200_H
+#define TDVC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum tdvc_status { TDVC_OK = 0, TDVC_ERR_ARG = -1, TDVC_ERR_CUDA = -2, TDVC_ERR_UNSUPPORTED = -3 };
+enum tdvc_pad_mode { TDVC_PAD_ZEROS = 0, TDVC_PAD_REFLECT = 1 };
+enum tdvc_act { TDVC_ACT_NONE = 0, TDVC_ACT_LRELU = 1, TDVC_ACT_TANH = 2 };
+
+/* Geometry of one Conv1d / ConvTranspose1d call.  For Conv1d: x[B,Cin,Tin] -> y[B,Cout,Tout],
+ * weight [Cout, Cin/groups, K].  For ConvTranspose1d: x[B,Cin,Tin] -> y[B,Cout,Tout], weight
+ * [Cin, Cout, K] (groups must be 1). */
+typedef struct tdvc_conv_geom {
+  int32_t B, Cin, Tin, Cout, Tout, K;
+  int32_t stride, pad, dilation, groups;
+  int32_t pad_mode;   /* tdvc_pad_mode; reflect only for Conv1d */
+  float in_slope;     /* LeakyReLU slope applied to x as it is read (1.0f = identity): the
+                         nn.LeakyReLU that precedes every conv in model/generator.py */
+  int32_t out_act;    /* tdvc_act applied after bias (+residual) */
+  float out_slope;    /* slope for TDVC_ACT_LRELU */
+} tdvc_conv_geom;
+
+const char* tdvc_last_error(void);
+int tdvc_version(void);
+/* 1 if the current device is sm_100 (tcgen05/TMEM/TMA paths usable), 0 otherwise, <0 on error */
+int tdvc_device_is_sm100(void);
+
+/* ---- weight norm: torch.nn.utils.weight_norm (util/__init__.py:16-20, model/generator.py:14,
+ *      model/discriminator.py:11): w[r,:] = g[r] * v[r,:] / ||v[r,:]||_2, rows = dim 0. */
+int tdvc_weight_norm_fwd(const float* v, const float* g, float* w, float* inv_norm /*[rows]*/,
+                         int rows, int cols, void* stream);
+int tdvc_weight_norm_bwd(const float* dw, const float* v, const float* g, const float* inv_norm,
+                         float* dv, float* dg, int rows, int cols, void* stream);
+
+/* ---- Conv1d (model/generator.py:75-92,146-156,214-249,299-347; model/discriminator.py:17-38;
+ *      depthwise Kaiser FIR F.conv1d at model/generator.py:165-168, model/discriminator.py:100-102).
+ *      fwd: y = act(conv(lrelu_in(pad(x)), w) + bias + residual).  bias/residual may be NULL.      */
+int tdvc_conv1d_fwd(const tdvc_conv_geom* g, const float* x, const float* w, const float* bias,
+                    const float* residual, float* y, void* stream);
+/* dx = d/dx of the above given dy = dL/d(pre-activation output).  `x` is needed only when
+ * in_slope != 1 (sign mask); `ws` is a workspace of tdvc_conv1d_bwd_data_ws(g) floats (reflect
+ * padding or strided polyphase staging), may be NULL when that returns 0. */
+int64_t tdvc_conv1d_bwd_data_ws(const tdvc_conv_geom* g);
+int tdvc_conv1d_bwd_data(const tdvc_conv_geom* g, const float* dy, const float* w, const float* x,
+                         float* dx, float* ws, void* stream);
+/* dw (same layout as w, OVERWRITTEN) and dbias (may be NULL) */
+int tdvc_conv1d_bwd_weight(const tdvc_conv_geom* g, const float* dy, const float* x, float* dw,
+                           float* dbias, void* stream);
+
+/* ---- ConvTranspose1d (model/generator.py:311-315).  No fused input activation (in_slope must be 1). */
+int tdvc_conv_transpose1d_fwd(const tdvc_conv_geom* g, const float* x, const float* w,
+                              const float* bias, float* y, void* stream);
+int tdvc_conv_transpose1d_bwd_data(const tdvc_conv_geom* g, const float* dy, const float* w,
+                                   float* dx, void* stream);
+int tdvc_conv_transpose1d_bwd_weight(const tdvc_conv_geom* g, const float* dy, const float* x,
+                                     float* dw, float* dbias, void* stream);
+
+/* ---- elementwise pieces of FiLMResnetBlock / MRFBlock / Discriminator
+ *      (model/generator.py:96-111,186-194; model/discriminator.py:20,31,38) */
+int tdvc_leaky_relu_fwd(const float* x, float* y, int64_t n, float slope, void* stream);
+/* dz = dy * act'(.) evaluated from the activation OUTPUT y (lrelu: sign(y); tanh: 1-y^2) */
+int tdvc_act_bwd_from_output(const float* dy, const float* y, float* dz, int64_t n, int act,
+                             float slope, void* stream);
+/* FiLM: y = h*(1+gamma)+beta with gb = [B, 2C, T] holding gamma (first C) then beta */
+int tdvc_film_fwd(const float* h, const float* gb, float* y, int B, int C, int T, void* stream);
+int tdvc_film_bwd(const float* dy, const float* h, const float* gb, float* dh, float* dgb,
+                  int B, int C, int T, void* stream);
+/* y = alpha * (a + b + c); b, c may be NULL */
+int tdvc_add3_scale(const float* a, const float* b, const float* c, float* y, int64_t n,
+                    float alpha, void* stream);
+/* F.normalize(x, dim=1) on [B,C,T] (model/generator.py:271), eps 1e-12 */
+int tdvc_l2norm_fwd(const float* x, float* y, float* inv /*[B,T]*/, int B, int C, int T, void* stream);
+int tdvc_l2norm_bwd(const float* dy, const float* y, const float* inv, float* dx, int B, int C, int T,
+                    void* stream);
+/* c_first != 0: cat([c.unsqueeze(2).repeat(1,1,T), e], dim=1) (model/generator.py:387-399);
+ * c_first == 0: cat([e, c...], dim=1) (model/generator.py:260-261,380-381).  out [B, Cc+Ce, T] */
+int tdvc_cond_concat_fwd(const float* c /*[B,Cc]*/, const float* e /*[B,Ce,T]*/, float* out,
+                         int B, int Cc, int Ce, int T, int c_first, void* stream);
+/* dc[b,cc] = sum_t dout[b,cc,t] ; de = the e rows of dout (de may be NULL). */
+int tdvc_cond_concat_bwd(const float* dout, float* dc, float* de, int B, int Cc, int Ce, int T,
+                         int c_first, void* stream);
+
+/* ---- instance norm / conditional instance norm (model/conditional_instance_norm.py:4-19;
+ *      nn.InstanceNorm1d(affine=False): biased variance over T, eps).  gb may be NULL (plain
+ *      instance norm) or [B,2C,Tg] with Tg in {1, T} (Linear- or Conv-produced gamma|beta).
+ *      y = (1+gamma)*xhat + beta, optionally followed by LeakyReLU(out_slope) (1.0 = none).     */
+int tdvc_instnorm_stats(const float* x, float* mean, float* rstd, int BC, int T, float eps, void* stream);
+int tdvc_cin_apply_fwd(const float* x, const float* mean, const float* rstd, const float* gb, int Tg,
+                       float* y, int B, int C, int T, float out_slope, void* stream);
+/* dy -> dx, dgb (dgb may be NULL when gb is NULL).  y_act is the forward output (only read when
+ * out_slope != 1). */
+int tdvc_cin_apply_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
+                       const float* gb, int Tg, const float* y_act, float* dx, float* dgb,
+                       int B, int C, int T, float out_slope, void* stream);
+
+/* ---- AvgPool1d(4, 2, 1, count_include_pad=False) (model/discriminator.py:63,72) */
+int tdvc_avgpool4s2_fwd(const float* x, float* y, int BC, int Tin, int Tout, void* stream);
+int tdvc_avgpool4s2_bwd(const float* dy, float* dx, int BC, int Tin, int Tout, void* stream);
+
+/* ---- x.gather(1, label) (model/discriminator.py:49-51): y[b,0,t] = x[b,label[b],t] */
+int tdvc_select_channel_fwd(const float* x, const int64_t* label, float* y, int B, int C, int T, void* stream);
+int tdvc_select_channel_bwd(const float* dy, const int64_t* label, float* dx /*zero-filled here*/,
+                            int B, int C, int T, void* stream);
+
+/* ---- losses (train.py:273-281,327-331 LSGAN F.mse_loss; util/losses.py:55-68 F.l1_loss).
+ *      out_sum += scale * sum(...) (caller zeroes out_sum; scale carries 1/N and any lambda). */
+int tdvc_sq_err_const_sum(const float* a, float target, float scale, float* out_sum, int64_t n, void* stream);
+/* da = gscale[0] * 2*scale*(a-target) */
+int tdvc_sq_err_const_bwd(const float* a, float target, float scale, const float* gscale, float* da,
+                          int64_t n, void* stream);
+int tdvc_abs_diff_sum(const float* a, const float* b, float scale, float* out_sum, int64_t n, void* stream);
+/* da = gscale[0] * scale * sign(a-b) */
+int tdvc_abs_diff_bwd(const float* a, const float* b, float scale, const float* gscale, float* da,
+                      int64_t n, void* stream);
+
+/* ---- fused multi-tensor AdamW (torch.optim.AdamW at train.py:188-189): one launch for a whole
+ *      parameter list.  ptr tables are DEVICE arrays of n_tensors pointers / sizes.             */
+int tdvc_adamw_multi(float* const* params, const float* const* grads, float* const* exp_avg,
+                     float* const* exp_avg_sq, const int64_t* sizes, int n_tensors, int64_t max_size,
+                     float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                     float grad_scale, void* stream);
+
+/* ---- bf16 tensor-core path (tcgen05 / TMEM / TMA), dense stride-1 Conv1d as implicit GEMM.
+ *      pack: x[B,C,T] fp32 NCW -> xp[B, Tp, Cp] bf16 channels-last with LeakyReLU(in_slope) and
+ *      `halo` samples of reflect/zero padding on each side (Tp = T + 2*halo, Cp = C rounded up to
+ *      8, zero filled).  */
+int tdvc_pack_cl_bf16(const float* x, void* xp, int B, int C, int T, int Cp, int halo, int pad_mode,
+                      float in_slope, void* stream);
+/* w[Cout,Cin,K] fp32 -> wp[K, Coutp, Cinp] bf16 (zero padded); transpose_flip!=0 produces the
+ * dgrad operand wp[K, Cinp, Coutp] with taps reversed. */
+int tdvc_pack_weight_bf16(const float* w, void* wp, int Cout, int Cin, int K, int Coutp, int Cinp,
+                          int transpose_flip, void* stream);
+/* y[B,Cout,Tout] fp32 NCW = epilogue( sum_k sum_ci xp[b, t + k*dilation + off, ci] * wp[k, co, ci] )
+ * epilogue: + bias[co] ; FiLM  y*(1+gb[b,co,t]) + gb[b,Cout+co,t] when gb != NULL ; + residual ; act. */
+int tdvc_conv1d_tc_fwd(const void* xp, const void* wp, const float* bias, const float* gb,
+                       const float* residual, float* y, int B, int Cinp, int Tp, int Cout, int Coutp,
+                       int Tout, int K, int dilation, int t_off, int out_act, float out_slope,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TDVC_B200_H */

@@ -1,0 +1,60 @@
+// Shared helpers for libtdvc_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/tdvc_b200.h"
+
+namespace tdvc {
+
+void set_error(const char* fmt, ...);
+
+#define TDVC_CHECK_ARG(cond)                                                        \
+  do {                                                                              \
+    if (!(cond)) {                                                                  \
+      tdvc::set_error("%s:%d: bad argument: %s", __FILE__, __LINE__, #cond);        \
+      return TDVC_ERR_ARG;                                                          \
+    }                                                                               \
+  } while (0)
+
+#define TDVC_CUDA(expr)                                                             \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      tdvc::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return TDVC_ERR_CUDA;                                                         \
+    }                                                                               \
+  } while (0)
+
+#define TDVC_LAUNCH_CHECK() TDVC_CUDA(cudaGetLastError())
+
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum; every thread gets the result.  `sm` must hold >= 33 floats.
+__device__ __forceinline__ float block_sum(float v, float* sm) {
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sm[wid] = v;
+  __syncthreads();
+  float r = (threadIdx.x < nw) ? sm[threadIdx.x] : 0.f;
+  if (wid == 0) {
+    r = warp_sum(r);
+    if (lane == 0) sm[32] = r;
+  }
+  __syncthreads();
+  return sm[32];
+}
+
+// number of SMs of the current device (cached)
+int num_sms();
+
+}  // namespace tdvc

@@ -1,0 +1,630 @@
+// fp32 CUDA-core Conv1d / ConvTranspose1d kernels (the exact-parity path, rel 1e-5 vs the reference).
+//
+// Three kernels cover every convolution of td-vc-gan's Generator and Discriminators
+// (model/generator.py:75-92,146-168,214-249,299-347; model/discriminator.py:17-38,100-102):
+//   conv_fwd_k   : direct conv, NCW, any stride/dilation/groups, zero or reflect padding, fused input
+//                  LeakyReLU, bias, residual, output activation.  Also used (weight strides swapped,
+//                  taps flipped) as the stride-1 dgrad and as ConvTranspose1d's dgrad.
+//   conv_tr_k    : transposed ("scatter as gather", polyphase) conv: strided dgrad and ConvTranspose1d fwd.
+//   conv_wgrad_k : weight gradient as an implicit-im2col outer-product reduction over (b, t) with
+//                  register accumulation and one atomicAdd per output per CTA.
+// All are shared-memory tiled, coalesced along time, bank-conflict free for stride 1.
+#include <algorithm>
+#include "common.cuh"
+
+namespace tdvc {
+
+struct FwdP {
+  int B, Cin, Tin, Cout, Tout, K, stride, pad, dil, groups;
+  int pad_mode, out_act;
+  float in_slope, out_slope;
+  int cin_g, cout_g;
+  long long w_sco, w_sci, w_sk;
+  int w_flip;
+  int ci_chunk, span;
+};
+
+__device__ __forceinline__ float fetch_padded(const float* __restrict__ row, int gt, int T, int pad_mode,
+                                              float slope) {
+  if (gt < 0) {
+    if (pad_mode != TDVC_PAD_REFLECT) return 0.f;
+    gt = -gt;
+    if (gt >= T) return 0.f;
+  } else if (gt >= T) {
+    if (pad_mode != TDVC_PAD_REFLECT) return 0.f;
+    gt = 2 * (T - 1) - gt;
+    if (gt < 0) return 0.f;
+  }
+  float v = __ldg(row + gt);
+  return v > 0.f ? v : v * slope;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+  if (act == TDVC_ACT_LRELU) return v > 0.f ? v : v * slope;
+  if (act == TDVC_ACT_TANH) return tanhf(v);
+  return v;
+}
+
+// weight tile in shared memory: row r = (ci,k), COB output channels.  Vector (float4) readers use an
+// XOR swizzle on 4-channel groups so the transposing store (consecutive r per lane) is at worst 4-way
+// conflicted; scalar readers use a +1 padded pitch.
+template <int CO_T, int COB>
+__device__ __forceinline__ int ws_index(int r, int co) {
+  if constexpr (CO_T % 4 == 0) {
+    constexpr int M = COB / 4 - 1;
+    return r * COB + ((((co >> 2) ^ (r & M)) << 2) | (co & 3));
+  } else {
+    return r * (COB + 1) + co;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward: each thread owns CO_T output channels x 4 time steps (time interleaved by TX so that a
+// warp reads consecutive shared-memory words).  block = 256 threads = TX (time) x TY (channels).
+template <int CO_T, int TX>
+__global__ void __launch_bounds__(256) conv_fwd_k(FwdP p, const float* __restrict__ x, const float* __restrict__ w,
+                                                   const float* __restrict__ bias, const float* __restrict__ res,
+                                                   float* __restrict__ y) {
+  constexpr int TY = 256 / TX, TT = TX * 4, COB = TY * CO_T;
+  extern __shared__ float sm[];
+  float* xs = sm;
+  float* ws = sm + (((size_t)p.ci_chunk * p.span + 3) & ~(size_t)3);
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  const int t0 = blockIdx.x * TT;
+  const int tiles_per_group = (p.cout_g + COB - 1) / COB;
+  const int grp = blockIdx.y / tiles_per_group;
+  const int co0 = (blockIdx.y % tiles_per_group) * COB;
+  const int b = blockIdx.z;
+  float acc[CO_T][4];
+#pragma unroll
+  for (int c = 0; c < CO_T; ++c)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[c][j] = 0.f;
+  const float* xb = x + ((long long)b * p.Cin + (long long)grp * p.cin_g) * p.Tin;
+  const int gt0 = t0 * p.stride - p.pad;
+  const bool row_active = (co0 + ty * CO_T) < p.cout_g;
+  const int xstep = TX * p.stride;
+
+  for (int c0 = 0; c0 < p.cin_g; c0 += p.ci_chunk) {
+    const int nci = min(p.ci_chunk, p.cin_g - c0);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nci * p.span; idx += 256) {
+      int ci = idx / p.span, i = idx - ci * p.span;
+      xs[idx] = fetch_padded(xb + (long long)(c0 + ci) * p.Tin, gt0 + i, p.Tin, p.pad_mode, p.in_slope);
+    }
+    const int nwk = nci * p.K;
+    for (int idx = threadIdx.x; idx < COB * nwk; idx += 256) {
+      int co = idx / nwk, r = idx - co * nwk;
+      int ci = r / p.K, k = r - ci * p.K;
+      float v = 0.f;
+      if (co0 + co < p.cout_g) {
+        int kk = p.w_flip ? p.K - 1 - k : k;
+        v = __ldg(w + (long long)(grp * p.cout_g + co0 + co) * p.w_sco + (long long)(c0 + ci) * p.w_sci +
+                  (long long)kk * p.w_sk);
+      }
+      ws[ws_index<CO_T, COB>(r, co)] = v;
+    }
+    __syncthreads();
+    if (row_active) {
+      for (int ci = 0; ci < nci; ++ci) {
+        const float* xr = xs + ci * p.span + tx * p.stride;
+        for (int k = 0; k < p.K; ++k) {
+          const float* xk = xr + k * p.dil;
+          float xv0 = xk[0], xv1 = xk[xstep], xv2 = xk[2 * xstep], xv3 = xk[3 * xstep];
+          const int r = ci * p.K + k;
+          float wv[CO_T];
+          if constexpr (CO_T % 4 == 0) {
+#pragma unroll
+            for (int c = 0; c < CO_T; c += 4) {
+              float4 t4 = *reinterpret_cast<const float4*>(ws + ws_index<CO_T, COB>(r, ty * CO_T + c));
+              wv[c] = t4.x; wv[c + 1] = t4.y; wv[c + 2] = t4.z; wv[c + 3] = t4.w;
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < CO_T; ++c) wv[c] = ws[ws_index<CO_T, COB>(r, ty * CO_T + c)];
+          }
+#pragma unroll
+          for (int c = 0; c < CO_T; ++c) {
+            acc[c][0] = fmaf(wv[c], xv0, acc[c][0]);
+            acc[c][1] = fmaf(wv[c], xv1, acc[c][1]);
+            acc[c][2] = fmaf(wv[c], xv2, acc[c][2]);
+            acc[c][3] = fmaf(wv[c], xv3, acc[c][3]);
+          }
+        }
+      }
+    }
+  }
+  if (!row_active) return;
+#pragma unroll
+  for (int c = 0; c < CO_T; ++c) {
+    int co = co0 + ty * CO_T + c;
+    if (co >= p.cout_g) break;
+    int cog = grp * p.cout_g + co;
+    float bv = bias ? __ldg(bias + cog) : 0.f;
+    long long base = ((long long)b * p.Cout + cog) * p.Tout;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int t = t0 + tx + j * TX;
+      if (t < p.Tout) {
+        float v = acc[c][j] + bv;
+        if (res) v += __ldg(res + base + t);
+        y[base + t] = apply_act(v, p.out_act, p.out_slope);
+      }
+    }
+  }
+}
+
+template <int CO_T, int TX>
+static int launch_fwd_t(FwdP p, const float* x, const float* w, const float* bias, const float* res, float* y,
+                        cudaStream_t st) {
+  constexpr int TY = 256 / TX, TT = TX * 4, COB = TY * CO_T;
+  p.span = (TT - 1) * p.stride + (p.K - 1) * p.dil + 1;
+  const size_t budget = 64 * 1024;
+  constexpr int WPITCH = (CO_T % 4 == 0) ? COB : COB + 1;
+  size_t per_ci = ((size_t)p.span + (size_t)p.K * WPITCH) * sizeof(float);
+  int chunk = (int)((budget - 16) / per_ci);
+  if (chunk < 1) chunk = 1;
+  if (chunk > p.cin_g) chunk = p.cin_g;
+  if (chunk > 32) chunk = 32;
+  p.ci_chunk = chunk;
+  size_t smem = per_ci * chunk + 16;
+  TDVC_CHECK_ARG(smem <= 200 * 1024);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    TDVC_CUDA(cudaFuncSetAttribute(conv_fwd_k<CO_T, TX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = 200 * 1024;
+  }
+  dim3 grid(cdiv(p.Tout, TT), p.groups * cdiv(p.cout_g, COB), p.B);
+  TDVC_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535);
+  conv_fwd_k<CO_T, TX><<<grid, 256, smem, st>>>(p, x, w, bias, res, y);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+static int launch_fwd(FwdP p, const float* x, const float* w, const float* bias, const float* res, float* y,
+                      cudaStream_t st) {
+  if (p.B == 0 || p.Tout <= 0) return TDVC_OK;
+  const bool small_t = p.Tout <= 48;
+  const int ty = small_t ? 32 : 8;
+  int co_t = 8;
+  if (ty * 1 >= p.cout_g) co_t = 1;
+  else if (ty * 2 >= p.cout_g) co_t = 2;
+  else if (ty * 4 >= p.cout_g) co_t = 4;
+#define TDVC_FWD_CASE(C, X) return launch_fwd_t<C, X>(p, x, w, bias, res, y, st)
+  if (small_t) {
+    switch (co_t) { case 1: TDVC_FWD_CASE(1, 8); case 2: TDVC_FWD_CASE(2, 8); case 4: TDVC_FWD_CASE(4, 8); default: TDVC_FWD_CASE(8, 8); }
+  } else {
+    switch (co_t) { case 1: TDVC_FWD_CASE(1, 32); case 2: TDVC_FWD_CASE(2, 32); case 4: TDVC_FWD_CASE(4, 32); default: TDVC_FWD_CASE(8, 32); }
+  }
+#undef TDVC_FWD_CASE
+}
+
+static int check_geom(const tdvc_conv_geom* g, bool transpose) {
+  TDVC_CHECK_ARG(g != nullptr);
+  TDVC_CHECK_ARG(g->B >= 0 && g->Cin > 0 && g->Cout > 0 && g->Tin > 0 && g->Tout > 0 && g->K > 0);
+  TDVC_CHECK_ARG(g->stride > 0 && g->dilation > 0 && g->pad >= 0 && g->groups > 0);
+  TDVC_CHECK_ARG(g->Cin % g->groups == 0 && g->Cout % g->groups == 0);
+  if (!transpose) {
+    long long tout = ((long long)g->Tin + 2LL * g->pad - (long long)g->dilation * (g->K - 1) - 1) / g->stride + 1;
+    TDVC_CHECK_ARG(tout == g->Tout);
+    if (g->pad_mode == TDVC_PAD_REFLECT) TDVC_CHECK_ARG(g->pad < g->Tin);
+  } else {
+    TDVC_CHECK_ARG(g->groups == 1 && g->dilation == 1 && g->pad_mode == TDVC_PAD_ZEROS && g->in_slope == 1.0f);
+    long long tout_min = ((long long)g->Tin - 1) * g->stride - 2LL * g->pad + (g->K - 1) + 1;
+    TDVC_CHECK_ARG(g->Tout >= tout_min && g->Tout < tout_min + g->stride);  // output_padding < stride
+  }
+  return TDVC_OK;
+}
+
+static FwdP fwd_params(const tdvc_conv_geom* g) {
+  FwdP p{};
+  p.B = g->B; p.Cin = g->Cin; p.Tin = g->Tin; p.Cout = g->Cout; p.Tout = g->Tout; p.K = g->K;
+  p.stride = g->stride; p.pad = g->pad; p.dil = g->dilation; p.groups = g->groups;
+  p.pad_mode = g->pad_mode; p.out_act = g->out_act; p.in_slope = g->in_slope; p.out_slope = g->out_slope;
+  p.cin_g = g->Cin / g->groups; p.cout_g = g->Cout / g->groups;
+  p.w_sco = (long long)p.cin_g * g->K; p.w_sci = g->K; p.w_sk = 1; p.w_flip = 0;
+  return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// transposed conv:  out[b, oc, i] = sum_{ic,k} in[b, ic, t] * w[ic, oc_in_group, k],  t*stride = i + peff - k*dil
+struct TrP {
+  int B, Cin, Tin, Cout, Tout, K, stride, peff, dil, groups;  // "in"/"out" are this kernel's operands
+  int in_g, out_g, ic_chunk, qlen;
+};
+
+template <int OC_T>
+__global__ void __launch_bounds__(256) conv_tr_k(TrP p, const float* __restrict__ in, const float* __restrict__ w,
+                                                  const float* __restrict__ bias, float* __restrict__ out) {
+  constexpr int TU = 128, TY = 2, OB = TY * OC_T;
+  extern __shared__ float sm[];
+  float* ins = sm;                                   // [ic_chunk][qlen]
+  float* ws = sm + (size_t)p.ic_chunk * p.qlen;      // [ic_chunk][K][OB]
+  const int tx = threadIdx.x % TU, ty = threadIdx.x / TU;
+  const int u0 = blockIdx.x * TU;
+  const int tiles_per_group = (p.out_g + OB - 1) / OB;
+  const int grp = blockIdx.y / tiles_per_group;
+  const int oc0 = (blockIdx.y % tiles_per_group) * OB;
+  const int b = blockIdx.z;
+  // first input sample any output of this tile can touch (floor division, may be negative)
+  int num = u0 + p.peff - (p.K - 1) * p.dil;
+  const int t_min = (num >= 0) ? num / p.stride : -((-num + p.stride - 1) / p.stride);
+  const int i = u0 + tx;
+  const int base = i + p.peff;  // >= 0
+  float acc[OC_T];
+#pragma unroll
+  for (int c = 0; c < OC_T; ++c) acc[c] = 0.f;
+  const float* inb = in + ((long long)b * p.Cin + (long long)grp * p.in_g) * p.Tin;
+  const bool row_active = (oc0 + ty * OC_T) < p.out_g;
+
+  for (int c0 = 0; c0 < p.in_g; c0 += p.ic_chunk) {
+    const int nic = min(p.ic_chunk, p.in_g - c0);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nic * p.qlen; idx += 256) {
+      int ic = idx / p.qlen, q = idx - ic * p.qlen;
+      int t = t_min + q;
+      ins[idx] = (t >= 0 && t < p.Tin) ? __ldg(inb + (long long)(c0 + ic) * p.Tin + t) : 0.f;
+    }
+    const int nko = p.K * p.out_g;  // contiguous run per input channel in global memory
+    for (int idx = threadIdx.x; idx < nic * p.K * OB; idx += 256) {
+      int ob = idx % OB, r = idx / OB;
+      int k = r % p.K, ic = r / p.K;
+      float v = 0.f;
+      if (oc0 + ob < p.out_g)
+        v = __ldg(w + (long long)(grp * p.in_g + c0 + ic) * nko + (long long)(oc0 + ob) * p.K + k);
+      ws[idx] = v;
+    }
+    __syncthreads();
+    if (row_active && i < p.Tout) {
+      if (p.dil == 1) {
+        const int phase = base % p.stride;
+        const int q0 = base / p.stride - t_min;  // index of t for k = phase
+        for (int ic = 0; ic < nic; ++ic) {
+          const float* ir = ins + ic * p.qlen;
+          const float* wr = ws + (size_t)ic * p.K * OB + ty * OC_T;
+          int q = q0;
+          for (int k = phase; k < p.K; k += p.stride, --q) {
+            float xv = ir[q];  // zero outside [0,Tin)
+#pragma unroll
+            for (int c = 0; c < OC_T; ++c) acc[c] = fmaf(xv, wr[k * OB + c], acc[c]);
+          }
+        }
+      } else {
+        for (int ic = 0; ic < nic; ++ic) {
+          const float* ir = ins + ic * p.qlen;
+          const float* wr = ws + (size_t)ic * p.K * OB + ty * OC_T;
+          for (int k = 0; k < p.K; ++k) {
+            int r = base - k * p.dil;
+            if (r < 0 || (r % p.stride) != 0) continue;
+            float xv = ir[r / p.stride - t_min];
+#pragma unroll
+            for (int c = 0; c < OC_T; ++c) acc[c] = fmaf(xv, wr[k * OB + c], acc[c]);
+          }
+        }
+      }
+    }
+  }
+  if (!row_active || i >= p.Tout) return;
+#pragma unroll
+  for (int c = 0; c < OC_T; ++c) {
+    int oc = oc0 + ty * OC_T + c;
+    if (oc >= p.out_g) break;
+    int ocg = grp * p.out_g + oc;
+    float v = acc[c] + (bias ? __ldg(bias + ocg) : 0.f);
+    out[((long long)b * p.Cout + ocg) * p.Tout + i] = v;
+  }
+}
+
+template <int OC_T>
+static int launch_tr_t(TrP p, const float* in, const float* w, const float* bias, float* out, cudaStream_t st) {
+  constexpr int TU = 128, OB = 2 * OC_T;
+  p.qlen = (TU - 1 + (p.K - 1) * p.dil) / p.stride + 3;
+  size_t per_ic = ((size_t)p.qlen + (size_t)p.K * OB) * sizeof(float);
+  int chunk = (int)((48 * 1024) / per_ic);
+  if (chunk < 1) chunk = 1;
+  if (chunk > p.in_g) chunk = p.in_g;
+  p.ic_chunk = chunk;
+  size_t smem = per_ic * chunk;
+  TDVC_CHECK_ARG(smem <= 48 * 1024);
+  dim3 grid(cdiv(p.Tout, TU), p.groups * cdiv(p.out_g, OB), p.B);
+  TDVC_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535);
+  conv_tr_k<OC_T><<<grid, 256, smem, st>>>(p, in, w, bias, out);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+static int launch_tr(TrP p, const float* in, const float* w, const float* bias, float* out, cudaStream_t st) {
+  if (p.B == 0 || p.Tout <= 0) return TDVC_OK;
+  if (p.out_g <= 2) return launch_tr_t<1>(p, in, w, bias, out, st);
+  if (p.out_g <= 4) return launch_tr_t<2>(p, in, w, bias, out, st);
+  if (p.out_g <= 8) return launch_tr_t<4>(p, in, w, bias, out, st);
+  return launch_tr_t<8>(p, in, w, bias, out, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// reflect fold + input-activation mask:  dx[t] = mask(x[t]) * (stage[p+t] + mirrored halo terms)
+__global__ void pad_act_bwd_k(const float* __restrict__ stage, const float* __restrict__ x, float* __restrict__ dx,
+                              long long rows, int T, int p, int reflect, float slope) {
+  long long n = rows * T;
+  int Ts = T + 2 * p;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long r = idx / T;
+    int t = (int)(idx - r * T);
+    const float* s = stage + r * Ts;
+    float v = s[p + t];
+    if (reflect) {
+      if (t >= 1 && t <= p) v += s[p - t];
+      int m = 2 * (T - 1) - t;  // mirrored position in unpadded coordinates, lives in the right halo
+      if (m >= T && m < T + p) v += s[p + m];
+    }
+    if (slope != 1.0f && x[idx] <= 0.f) v *= slope;
+    dx[idx] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad:  out[ca, (cb,k)] = sum_{b,t} A[b, ca, t] * Bm[b, cb, t*stride + k*dil - pad]
+struct WgP {
+  int B, Ca, Ta, Cb, Tb, K, stride, pad, dil, groups;
+  int ca_g, cb_g, pad_mode;
+  float b_slope;
+  int jtot, rows, span, nchunk, zsplit;
+};
+
+template <int RC>
+__global__ void __launch_bounds__(256) conv_wgrad_k(WgP p, const float* __restrict__ A, const float* __restrict__ Bm,
+                                                     float* __restrict__ out) {
+  constexpr int TTW = 128, CAB = 16 * RC, JB = 64;
+  extern __shared__ float sm[];
+  float* a_s = sm;                  // [CAB][TTW]
+  float* bs = sm + CAB * TTW;       // [rows][span]
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int j0 = blockIdx.x * JB;
+  const int tiles_per_group = (p.ca_g + CAB - 1) / CAB;
+  const int grp = blockIdx.y / tiles_per_group;
+  const int ca0 = (blockIdx.y % tiles_per_group) * CAB;
+  const int cb_lo = j0 / p.K;
+  int off[4];
+  bool jok[4];
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    int j = j0 + tx + 16 * jj;
+    jok[jj] = j < p.jtot;
+    int cb = jok[jj] ? j / p.K : cb_lo;
+    int k = jok[jj] ? j - cb * p.K : 0;
+    off[jj] = (cb - cb_lo) * p.span + k * p.dil;
+  }
+  float acc[RC][4];
+#pragma unroll
+  for (int c = 0; c < RC; ++c)
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) acc[c][jj] = 0.f;
+  const int cb_hi = min((j0 + JB - 1) / p.K, p.cb_g - 1);
+  const int nrows = cb_hi - cb_lo + 1;
+  const int total = p.B * p.nchunk;
+  for (int item = blockIdx.z; item < total; item += p.zsplit) {
+    const int b = item / p.nchunk;
+    const int tb = (item - b * p.nchunk) * TTW;
+    const int nt = min(TTW, p.Ta - tb);
+    __syncthreads();
+    const float* Ab = A + ((long long)b * p.Ca + (long long)grp * p.ca_g + ca0) * p.Ta + tb;
+    for (int idx = threadIdx.x; idx < CAB * TTW; idx += 256) {
+      int ca = idx / TTW, t = idx - ca * TTW;
+      a_s[idx] = (ca0 + ca < p.ca_g && t < nt) ? __ldg(Ab + (long long)ca * p.Ta + t) : 0.f;
+    }
+    const float* Bb = Bm + ((long long)b * p.Cb + (long long)grp * p.cb_g + cb_lo) * p.Tb;
+    const int g0 = tb * p.stride - p.pad;
+    for (int idx = threadIdx.x; idx < nrows * p.span; idx += 256) {
+      int r = idx / p.span, i = idx - r * p.span;
+      bs[idx] = fetch_padded(Bb + (long long)r * p.Tb, g0 + i, p.Tb, p.pad_mode, p.b_slope);
+    }
+    __syncthreads();
+    const float* ar = a_s + ty * RC * TTW;
+    for (int t = 0; t < nt; ++t) {
+      float av[RC];
+#pragma unroll
+      for (int c = 0; c < RC; ++c) av[c] = ar[c * TTW + t];
+      const int ts = t * p.stride;
+      float b0 = bs[off[0] + ts], b1 = bs[off[1] + ts], b2 = bs[off[2] + ts], b3 = bs[off[3] + ts];
+#pragma unroll
+      for (int c = 0; c < RC; ++c) {
+        acc[c][0] = fmaf(av[c], b0, acc[c][0]);
+        acc[c][1] = fmaf(av[c], b1, acc[c][1]);
+        acc[c][2] = fmaf(av[c], b2, acc[c][2]);
+        acc[c][3] = fmaf(av[c], b3, acc[c][3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < RC; ++c) {
+    int ca = ca0 + ty * RC + c;
+    if (ca >= p.ca_g) continue;
+    float* orow = out + (long long)(grp * p.ca_g + ca) * p.jtot;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+      if (jok[jj]) atomicAdd(orow + j0 + tx + 16 * jj, acc[c][jj]);
+  }
+}
+
+template <int RC>
+static int launch_wgrad_t(WgP p, const float* A, const float* Bm, float* out, cudaStream_t st) {
+  constexpr int TTW = 128, CAB = 16 * RC, JB = 64;
+  p.jtot = p.cb_g * p.K;
+  p.span = (TTW - 1) * p.stride + (p.K - 1) * p.dil + 1;
+  p.rows = min(p.cb_g, (JB + p.K - 2) / p.K + 1);
+  p.nchunk = cdiv(p.Ta, TTW);
+  size_t smem = ((size_t)CAB * TTW + (size_t)p.rows * p.span) * sizeof(float);
+  TDVC_CHECK_ARG(smem <= 200 * 1024);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    TDVC_CUDA(cudaFuncSetAttribute(conv_wgrad_k<RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = 200 * 1024;
+  }
+  int gx = cdiv(p.jtot, JB), gy = p.groups * cdiv(p.ca_g, CAB);
+  long long total = (long long)p.B * p.nchunk;
+  long long want = (4LL * num_sms() + (long long)gx * gy - 1) / ((long long)gx * gy);
+  if (want < 1) want = 1;
+  if (want > total) want = total;
+  if (want > 65535) want = 65535;
+  p.zsplit = (int)want;
+  TDVC_CHECK_ARG(gy <= 65535);
+  dim3 grid(gx, gy, p.zsplit);
+  conv_wgrad_k<RC><<<grid, 256, smem, st>>>(p, A, Bm, out);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+static int launch_wgrad(WgP p, const float* A, const float* Bm, float* out, cudaStream_t st) {
+  TDVC_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)p.Ca * p.cb_g * p.K, st));
+  if (p.B == 0) return TDVC_OK;
+  if (p.ca_g <= 16) return launch_wgrad_t<1>(p, A, Bm, out, st);
+  return launch_wgrad_t<4>(p, A, Bm, out, st);
+}
+
+// per-channel sum over (b, t): bias gradient
+__global__ void channel_sum_k(const float* __restrict__ dy, float* __restrict__ db, int B, int C, int T, int zsplit) {
+  __shared__ float sm[33];
+  const int c = blockIdx.x;
+  float s = 0.f;
+  for (int b = blockIdx.y; b < B; b += zsplit) {
+    const float* r = dy + ((long long)b * C + c) * T;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) s += r[t];
+  }
+  s = block_sum(s, sm);
+  if (threadIdx.x == 0) atomicAdd(db + c, s);
+}
+
+static int launch_channel_sum(const float* dy, float* db, int B, int C, int T, cudaStream_t st) {
+  TDVC_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * C, st));
+  if (B == 0) return TDVC_OK;
+  int zs = min(B, max(1, (2 * num_sms()) / C));
+  channel_sum_k<<<dim3(C, zs), 256, 0, st>>>(dy, db, B, C, T, zs);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+}  // namespace tdvc
+
+using namespace tdvc;
+
+extern "C" int tdvc_conv1d_fwd(const tdvc_conv_geom* g, const float* x, const float* w, const float* bias,
+                               const float* residual, float* y, void* stream) {
+  int rc = check_geom(g, false);
+  if (rc) return rc;
+  TDVC_CHECK_ARG(x && w && y);
+  return launch_fwd(fwd_params(g), x, w, bias, residual, y, (cudaStream_t)stream);
+}
+
+static bool needs_stage(const tdvc_conv_geom* g) {
+  return (g->pad_mode == TDVC_PAD_REFLECT && g->pad > 0) || g->in_slope != 1.0f;
+}
+
+extern "C" int64_t tdvc_conv1d_bwd_data_ws(const tdvc_conv_geom* g) {
+  if (!g || !needs_stage(g)) return 0;
+  int ph = (g->pad_mode == TDVC_PAD_REFLECT) ? g->pad : 0;
+  return (int64_t)g->B * g->Cin * (g->Tin + 2 * ph);
+}
+
+extern "C" int tdvc_conv1d_bwd_data(const tdvc_conv_geom* g, const float* dy, const float* w, const float* x,
+                                    float* dx, float* ws, void* stream) {
+  int rc = check_geom(g, false);
+  if (rc) return rc;
+  TDVC_CHECK_ARG(dy && w && dx);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool stage = needs_stage(g);
+  const int ph = (g->pad_mode == TDVC_PAD_REFLECT) ? g->pad : 0;  // halo kept in the staging buffer
+  if (stage) TDVC_CHECK_ARG(ws != nullptr);
+  if (g->in_slope != 1.0f) TDVC_CHECK_ARG(x != nullptr);
+  float* target = stage ? ws : dx;
+  const int Lout = g->Tin + 2 * ph;
+  const int peff = g->pad - ph;
+  if (g->stride == 1 && g->groups == 1) {
+    // dgrad as a forward conv of dy with channel-swapped, tap-flipped weights
+    FwdP p{};
+    p.B = g->B; p.Cin = g->Cout; p.Tin = g->Tout; p.Cout = g->Cin; p.Tout = Lout; p.K = g->K;
+    p.stride = 1; p.dil = g->dilation; p.groups = 1; p.pad = (g->K - 1) * g->dilation - peff;
+    p.pad_mode = TDVC_PAD_ZEROS; p.out_act = TDVC_ACT_NONE; p.in_slope = 1.0f; p.out_slope = 1.0f;
+    p.cin_g = p.Cin; p.cout_g = p.Cout;
+    p.w_sco = g->K; p.w_sci = (long long)g->Cin * g->K; p.w_sk = 1; p.w_flip = 1;
+    TDVC_CHECK_ARG(p.pad >= 0);
+    rc = launch_fwd(p, dy, w, nullptr, nullptr, target, st);
+  } else {
+    TrP p{};
+    p.B = g->B; p.Cin = g->Cout; p.Tin = g->Tout; p.Cout = g->Cin; p.Tout = Lout; p.K = g->K;
+    p.stride = g->stride; p.peff = peff; p.dil = g->dilation; p.groups = g->groups;
+    p.in_g = g->Cout / g->groups; p.out_g = g->Cin / g->groups;
+    rc = launch_tr(p, dy, w, nullptr, target, st);
+  }
+  if (rc) return rc;
+  if (stage) {
+    long long rows = (long long)g->B * g->Cin;
+    long long n = rows * g->Tin;
+    int blocks = (int)std::min<long long>((n + 255) / 256, 8LL * num_sms());
+    if (blocks > 0) {
+      pad_act_bwd_k<<<blocks, 256, 0, st>>>(ws, x, dx, rows, g->Tin, ph, g->pad_mode == TDVC_PAD_REFLECT, g->in_slope);
+      TDVC_LAUNCH_CHECK();
+    }
+  }
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_conv1d_bwd_weight(const tdvc_conv_geom* g, const float* dy, const float* x, float* dw,
+                                      float* dbias, void* stream) {
+  int rc = check_geom(g, false);
+  if (rc) return rc;
+  TDVC_CHECK_ARG(dy && x && dw);
+  cudaStream_t st = (cudaStream_t)stream;
+  WgP p{};
+  p.B = g->B; p.Ca = g->Cout; p.Ta = g->Tout; p.Cb = g->Cin; p.Tb = g->Tin; p.K = g->K;
+  p.stride = g->stride; p.pad = g->pad; p.dil = g->dilation; p.groups = g->groups;
+  p.ca_g = g->Cout / g->groups; p.cb_g = g->Cin / g->groups; p.pad_mode = g->pad_mode; p.b_slope = g->in_slope;
+  rc = launch_wgrad(p, dy, x, dw, st);
+  if (rc) return rc;
+  if (dbias) return launch_channel_sum(dy, dbias, g->B, g->Cout, g->Tout, st);
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_conv_transpose1d_fwd(const tdvc_conv_geom* g, const float* x, const float* w, const float* bias,
+                                         float* y, void* stream) {
+  int rc = check_geom(g, true);
+  if (rc) return rc;
+  TDVC_CHECK_ARG(x && w && y);
+  TrP p{};
+  p.B = g->B; p.Cin = g->Cin; p.Tin = g->Tin; p.Cout = g->Cout; p.Tout = g->Tout; p.K = g->K;
+  p.stride = g->stride; p.peff = g->pad; p.dil = 1; p.groups = 1; p.in_g = g->Cin; p.out_g = g->Cout;
+  return launch_tr(p, x, w, bias, y, (cudaStream_t)stream);
+}
+
+extern "C" int tdvc_conv_transpose1d_bwd_data(const tdvc_conv_geom* g, const float* dy, const float* w, float* dx,
+                                              void* stream) {
+  int rc = check_geom(g, true);
+  if (rc) return rc;
+  TDVC_CHECK_ARG(dy && w && dx);
+  // dx[b,ci,t] = sum_{co,k} dy[b,co,t*s + k - p] * w[ci,co,k]: a strided forward conv of dy whose
+  // "output channels" are ci -- w[Cin,Cout,K] already has that layout.
+  FwdP p{};
+  p.B = g->B; p.Cin = g->Cout; p.Tin = g->Tout; p.Cout = g->Cin; p.Tout = g->Tin; p.K = g->K;
+  p.stride = g->stride; p.pad = g->pad; p.dil = 1; p.groups = 1;
+  p.pad_mode = TDVC_PAD_ZEROS; p.out_act = TDVC_ACT_NONE; p.in_slope = 1.0f; p.out_slope = 1.0f;
+  p.cin_g = p.Cin; p.cout_g = p.Cout;
+  p.w_sco = (long long)g->Cout * g->K; p.w_sci = g->K; p.w_sk = 1; p.w_flip = 0;
+  return launch_fwd(p, dy, w, nullptr, nullptr, dx, (cudaStream_t)stream);
+}
+
+extern "C" int tdvc_conv_transpose1d_bwd_weight(const tdvc_conv_geom* g, const float* dy, const float* x, float* dw,
+                                                float* dbias, void* stream) {
+  int rc = check_geom(g, true);
+  if (rc) return rc;
+  TDVC_CHECK_ARG(dy && x && dw);
+  cudaStream_t st = (cudaStream_t)stream;
+  // dw[ci,co,k] = sum_{b,t} x[b,ci,t] * dy[b,co,t*s + k - p]
+  WgP p{};
+  p.B = g->B; p.Ca = g->Cin; p.Ta = g->Tin; p.Cb = g->Cout; p.Tb = g->Tout; p.K = g->K;
+  p.stride = g->stride; p.pad = g->pad; p.dil = 1; p.groups = 1;
+  p.ca_g = g->Cin; p.cb_g = g->Cout; p.pad_mode = TDVC_PAD_ZEROS; p.b_slope = 1.0f;
+  rc = launch_wgrad(p, x, dy, dw, st);
+  if (rc) return rc;
+  if (dbias) return launch_channel_sum(dy, dbias, g->B, g->Cout, g->Tout, st);
+  return TDVC_OK;
+}

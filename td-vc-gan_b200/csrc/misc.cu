@@ -1,0 +1,238 @@
+// Pooling, label gather, loss reductions and the fused multi-tensor AdamW.
+//   AvgPool1d(4,2,1,count_include_pad=False): model/discriminator.py:63,72
+//   x.gather(1,label): model/discriminator.py:49-51
+//   LSGAN F.mse_loss: train.py:273-281,327-331 ; feature-matching F.l1_loss: util/losses.py:55-68
+//   torch.optim.AdamW: train.py:188-189
+#include <algorithm>
+#include "common.cuh"
+
+namespace tdvc {
+
+static inline int ew_blocks(long long n_items) {
+  long long b = (n_items + 255) / 256;
+  long long cap = 16LL * num_sms();
+  return (int)std::max<long long>(1, std::min(b, cap));
+}
+
+__global__ void avgpool_fwd_k(const float* __restrict__ x, float* __restrict__ y, long long rows, int Tin, int Tout) {
+  long long n = rows * Tout;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i / Tout;
+    int o = (int)(i - r * Tout);
+    int lo = max(2 * o - 1, 0), hi = min(2 * o + 2, Tin - 1);
+    const float* xr = x + r * Tin;
+    float s = 0.f;
+    for (int t = lo; t <= hi; ++t) s += xr[t];
+    y[i] = s / (float)(hi - lo + 1);
+  }
+}
+
+__global__ void avgpool_bwd_k(const float* __restrict__ dy, float* __restrict__ dx, long long rows, int Tin, int Tout) {
+  long long n = rows * Tin;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i / Tin;
+    int t = (int)(i - r * Tin);
+    // windows o with 2o-1 <= t <= 2o+2
+    int o_lo = max((t - 2 + 1) / 2, 0);
+    if (t - 2 < 0) o_lo = 0;
+    int o_hi = min((t + 1) / 2, Tout - 1);
+    float s = 0.f;
+    for (int o = o_lo; o <= o_hi; ++o) {
+      int lo = max(2 * o - 1, 0), hi = min(2 * o + 2, Tin - 1);
+      if (t >= lo && t <= hi) s += dy[r * Tout + o] / (float)(hi - lo + 1);
+    }
+    dx[i] = s;
+  }
+}
+
+__global__ void select_fwd_k(const float* __restrict__ x, const int64_t* __restrict__ label, float* __restrict__ y,
+                             int B, int C, int T) {
+  long long n = (long long)B * T;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int b = (int)(i / T);
+    int t = (int)(i - (long long)b * T);
+    long long l = label[b];
+    y[i] = (l >= 0 && l < C) ? x[((long long)b * C + l) * T + t] : 0.f;
+  }
+}
+
+__global__ void select_bwd_k(const float* __restrict__ dy, const int64_t* __restrict__ label, float* __restrict__ dx,
+                             int B, int C, int T) {
+  long long n = (long long)B * C * T;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    long long row = i / T;
+    int t = (int)(i - row * T);
+    int b = (int)(row / C), c = (int)(row - (long long)b * C);
+    dx[i] = (label[b] == c) ? dy[(long long)b * T + t] : 0.f;
+  }
+}
+
+__global__ void sq_err_const_sum_k(const float* __restrict__ a, float target, float scale, float* __restrict__ out,
+                                   long long n) {
+  __shared__ float sm[33];
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float d = a[i] - target;
+    s = fmaf(d, d, s);
+  }
+  s = block_sum(s, sm);
+  if (threadIdx.x == 0) atomicAdd(out, s * scale);
+}
+
+__global__ void sq_err_const_bwd_k(const float* __restrict__ a, float target, float scale,
+                                   const float* __restrict__ gscale, float* __restrict__ da, long long n) {
+  float g = 2.f * scale * gscale[0];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    da[i] = g * (a[i] - target);
+}
+
+__global__ void abs_diff_sum_k(const float* __restrict__ a, const float* __restrict__ b, float scale,
+                               float* __restrict__ out, long long n) {
+  __shared__ float sm[33];
+  float s = 0.f;
+  long long n4 = n >> 2;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const float4* a4 = reinterpret_cast<const float4*>(a);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+  for (long long i = i0; i < n4; i += stride) {
+    float4 u = a4[i], v = b4[i];
+    s += fabsf(u.x - v.x) + fabsf(u.y - v.y) + fabsf(u.z - v.z) + fabsf(u.w - v.w);
+  }
+  for (long long i = (n4 << 2) + i0; i < n; i += stride) s += fabsf(a[i] - b[i]);
+  s = block_sum(s, sm);
+  if (threadIdx.x == 0) atomicAdd(out, s * scale);
+}
+
+__global__ void abs_diff_bwd_k(const float* __restrict__ a, const float* __restrict__ b, float scale,
+                               const float* __restrict__ gscale, float* __restrict__ da, long long n) {
+  float g = scale * gscale[0];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float d = a[i] - b[i];
+    da[i] = d > 0.f ? g : (d < 0.f ? -g : 0.f);
+  }
+}
+
+// AdamW exactly as torch.optim.AdamW (decoupled decay, bias correction, eps outside the sqrt of v_hat):
+//   p *= 1 - lr*wd ; m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
+__global__ void adamw_multi_k(float* const* __restrict__ params, const float* const* __restrict__ grads,
+                              float* const* __restrict__ m1, float* const* __restrict__ m2,
+                              const int64_t* __restrict__ sizes, int chunks_per_tensor, float lr, float b1, float b2,
+                              float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
+  const int ti = blockIdx.x / chunks_per_tensor;
+  const int ch = blockIdx.x - ti * chunks_per_tensor;
+  const long long n = sizes[ti];
+  float* p = params[ti];
+  const float* g = grads[ti];
+  float* m = m1[ti];
+  float* v = m2[ti];
+  if (g == nullptr) return;
+  const float step_size = lr / bc1;
+  for (long long i = (long long)ch * blockDim.x + threadIdx.x; i < n; i += (long long)chunks_per_tensor * blockDim.x) {
+    float gi = g[i] * gscale;
+    float pi = p[i] * (1.f - lr * wd);
+    float mi = b1 * m[i] + (1.f - b1) * gi;
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - step_size * (mi / denom);
+  }
+}
+
+}  // namespace tdvc
+using namespace tdvc;
+
+extern "C" int tdvc_avgpool4s2_fwd(const float* x, float* y, int BC, int Tin, int Tout, void* stream) {
+  TDVC_CHECK_ARG(BC >= 0 && Tin > 0 && Tout == (Tin + 2 - 4) / 2 + 1 && x && y);
+  if (BC == 0) return TDVC_OK;
+  avgpool_fwd_k<<<ew_blocks((long long)BC * Tout), 256, 0, (cudaStream_t)stream>>>(x, y, BC, Tin, Tout);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_avgpool4s2_bwd(const float* dy, float* dx, int BC, int Tin, int Tout, void* stream) {
+  TDVC_CHECK_ARG(BC >= 0 && Tin > 0 && Tout == (Tin + 2 - 4) / 2 + 1 && dy && dx);
+  if (BC == 0) return TDVC_OK;
+  avgpool_bwd_k<<<ew_blocks((long long)BC * Tin), 256, 0, (cudaStream_t)stream>>>(dy, dx, BC, Tin, Tout);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_select_channel_fwd(const float* x, const int64_t* label, float* y, int B, int C, int T,
+                                       void* stream) {
+  TDVC_CHECK_ARG(B >= 0 && C > 0 && T > 0 && x && label && y);
+  if (B == 0) return TDVC_OK;
+  select_fwd_k<<<ew_blocks((long long)B * T), 256, 0, (cudaStream_t)stream>>>(x, label, y, B, C, T);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_select_channel_bwd(const float* dy, const int64_t* label, float* dx, int B, int C, int T,
+                                       void* stream) {
+  TDVC_CHECK_ARG(B >= 0 && C > 0 && T > 0 && dy && label && dx);
+  if (B == 0) return TDVC_OK;
+  select_bwd_k<<<ew_blocks((long long)B * C * T), 256, 0, (cudaStream_t)stream>>>(dy, label, dx, B, C, T);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_sq_err_const_sum(const float* a, float target, float scale, float* out_sum, int64_t n,
+                                     void* stream) {
+  TDVC_CHECK_ARG(n >= 0 && out_sum);
+  if (n == 0) return TDVC_OK;
+  TDVC_CHECK_ARG(a);
+  int blocks = (int)std::min<long long>((n + 1023) / 1024, 2LL * num_sms());
+  sq_err_const_sum_k<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, target, scale, out_sum, n);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_sq_err_const_bwd(const float* a, float target, float scale, const float* gscale, float* da,
+                                     int64_t n, void* stream) {
+  TDVC_CHECK_ARG(n >= 0);
+  if (n == 0) return TDVC_OK;
+  TDVC_CHECK_ARG(a && gscale && da);
+  sq_err_const_bwd_k<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(a, target, scale, gscale, da, n);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_abs_diff_sum(const float* a, const float* b, float scale, float* out_sum, int64_t n,
+                                 void* stream) {
+  TDVC_CHECK_ARG(n >= 0 && out_sum);
+  if (n == 0) return TDVC_OK;
+  TDVC_CHECK_ARG(a && b && ((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0));
+  int blocks = (int)std::min<long long>((n + 2047) / 2048, 4LL * num_sms());
+  abs_diff_sum_k<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, b, scale, out_sum, n);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_abs_diff_bwd(const float* a, const float* b, float scale, const float* gscale, float* da,
+                                 int64_t n, void* stream) {
+  TDVC_CHECK_ARG(n >= 0);
+  if (n == 0) return TDVC_OK;
+  TDVC_CHECK_ARG(a && b && gscale && da);
+  abs_diff_bwd_k<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(a, b, scale, gscale, da, n);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_adamw_multi(float* const* params, const float* const* grads, float* const* exp_avg,
+                                float* const* exp_avg_sq, const int64_t* sizes, int n_tensors, int64_t max_size,
+                                float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                                float grad_scale, void* stream) {
+  TDVC_CHECK_ARG(n_tensors >= 0 && step >= 1 && max_size >= 0);
+  if (n_tensors == 0 || max_size == 0) return TDVC_OK;
+  TDVC_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && sizes);
+  float bc1 = 1.f - powf(beta1, (float)step);
+  float bc2 = 1.f - powf(beta2, (float)step);
+  int chunks = (int)std::min<long long>((max_size + 256 * 8 - 1) / (256 * 8), 64);
+  if (chunks < 1) chunks = 1;
+  adamw_multi_k<<<n_tensors * chunks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, sizes, chunks,
+                                                                      lr, beta1, beta2, eps, weight_decay, bc1,
+                                                                      sqrtf(bc2), grad_scale);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}

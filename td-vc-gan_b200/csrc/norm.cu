@@ -1,0 +1,184 @@
+// Weight-norm and (conditional) instance-norm: HBM-bound row reductions with 128-bit loads and
+// warp-shuffle + shared-memory reductions.
+//   weight norm : util/__init__.py:16-20, model/generator.py:14, model/discriminator.py:11
+//   instance norm / CIN : model/conditional_instance_norm.py:4-19
+#include <algorithm>
+#include "common.cuh"
+
+namespace tdvc {
+
+// one block per row
+__global__ void wn_fwd_k(const float* __restrict__ v, const float* __restrict__ g, float* __restrict__ w,
+                         float* __restrict__ inv_norm, int cols) {
+  __shared__ float sm[33];
+  const int r = blockIdx.x;
+  const float* vr = v + (long long)r * cols;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) { float a = vr[i]; s = fmaf(a, a, s); }
+  s = block_sum(s, sm);
+  float inv = rsqrtf(s);
+  // one Newton step: rsqrtf is 2 ulp, the reference divides by an exactly rounded sqrt
+  inv = inv * (1.5f - 0.5f * s * inv * inv);
+  float scale = g[r] * inv;
+  float* wr = w + (long long)r * cols;
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) wr[i] = vr[i] * scale;
+  if (threadIdx.x == 0) inv_norm[r] = inv;
+}
+
+// w = g v / n :  dg = <dw, v>/n ;  dv = (g/n) (dw - v <dw,v>/n^2)
+__global__ void wn_bwd_k(const float* __restrict__ dw, const float* __restrict__ v, const float* __restrict__ g,
+                         const float* __restrict__ inv_norm, float* __restrict__ dv, float* __restrict__ dg, int cols) {
+  __shared__ float sm[33];
+  const int r = blockIdx.x;
+  const float* vr = v + (long long)r * cols;
+  const float* dr = dw + (long long)r * cols;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) s = fmaf(dr[i], vr[i], s);
+  s = block_sum(s, sm);
+  float inv = inv_norm[r];
+  float gi = g[r] * inv;
+  float c = s * inv * inv;
+  float* o = dv + (long long)r * cols;
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) o[i] = gi * (dr[i] - vr[i] * c);
+  if (threadIdx.x == 0) dg[r] = s * inv;
+}
+
+// per-(b,c) mean and 1/sqrt(var+eps) over T (biased variance, two-pass for fp32 accuracy)
+__global__ void instnorm_stats_k(const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ rstd, int T,
+                                 float eps) {
+  __shared__ float sm[33];
+  const long long r = blockIdx.x;
+  const float* xr = x + r * T;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < T; i += blockDim.x) s += xr[i];
+  s = block_sum(s, sm);
+  float m = s / (float)T;
+  float q = 0.f;
+  for (int i = threadIdx.x; i < T; i += blockDim.x) { float d = xr[i] - m; q = fmaf(d, d, q); }
+  q = block_sum(q, sm);
+  if (threadIdx.x == 0) {
+    mean[r] = m;
+    rstd[r] = 1.0f / sqrtf(q / (float)T + eps);
+  }
+}
+
+__global__ void cin_apply_fwd_k(const float* __restrict__ x, const float* __restrict__ mean,
+                                const float* __restrict__ rstd, const float* __restrict__ gb, int Tg,
+                                float* __restrict__ y, int B, int C, int T, float slope) {
+  long long n = (long long)B * C * T;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    long long row = i / T;
+    int t = (int)(i - row * T);
+    float xh = (x[i] - mean[row]) * rstd[row];
+    float v = xh;
+    if (gb) {
+      int b = (int)(row / C), c = (int)(row - (long long)b * C);
+      int tg = Tg == 1 ? 0 : t;
+      const float* gp = gb + ((long long)b * 2 * C) * Tg;
+      v = fmaf(1.f + gp[(long long)c * Tg + tg], xh, gp[(long long)(C + c) * Tg + tg]);
+    }
+    y[i] = lrelu(v, slope);
+  }
+}
+
+// one block per (b,c) row.  With dxh = dL/dxhat:  dx = rstd * (dxh - mean_t(dxh) - xhat * mean_t(dxh*xhat))
+__global__ void cin_apply_bwd_k(const float* __restrict__ dy, const float* __restrict__ x,
+                                const float* __restrict__ mean, const float* __restrict__ rstd,
+                                const float* __restrict__ gb, int Tg, const float* __restrict__ y_act,
+                                float* __restrict__ dx, float* __restrict__ dgb, int C, int T, float slope) {
+  __shared__ float sm[33];
+  const long long row = blockIdx.x;
+  const int b = (int)(row / C), c = (int)(row - (long long)b * C);
+  const float m = mean[row], rs = rstd[row];
+  const float* xr = x + row * T;
+  const float* dyr = dy + row * T;
+  const float* yr = y_act ? y_act + row * T : nullptr;
+  const float* gam = gb ? gb + ((long long)b * 2 * C + c) * Tg : nullptr;
+  float* dgam = dgb ? dgb + ((long long)b * 2 * C + c) * Tg : nullptr;
+  float* dbet = dgb ? dgb + ((long long)b * 2 * C + C + c) * Tg : nullptr;
+  float s1 = 0.f, s2 = 0.f, sg = 0.f, sb = 0.f;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    float g = dyr[t];
+    if (slope != 1.0f && yr[t] <= 0.f) g *= slope;
+    float xh = (xr[t] - m) * rs;
+    float dxh = g;
+    if (gam) {
+      int tg = Tg == 1 ? 0 : t;
+      dxh = g * (1.f + gam[tg]);
+      if (Tg == 1) { sg = fmaf(g, xh, sg); sb += g; }
+      else { dgam[t] = g * xh; dbet[t] = g; }
+    }
+    s1 += dxh;
+    s2 = fmaf(dxh, xh, s2);
+  }
+  s1 = block_sum(s1, sm);
+  s2 = block_sum(s2, sm);
+  if (gam && Tg == 1) {
+    sg = block_sum(sg, sm);
+    sb = block_sum(sb, sm);
+    if (threadIdx.x == 0) { dgam[0] = sg; dbet[0] = sb; }
+  }
+  const float m1 = s1 / (float)T, m2 = s2 / (float)T;
+  float* dxr = dx + row * T;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    float g = dyr[t];
+    if (slope != 1.0f && yr[t] <= 0.f) g *= slope;
+    float xh = (xr[t] - m) * rs;
+    float dxh = gam ? g * (1.f + gam[Tg == 1 ? 0 : t]) : g;
+    dxr[t] = rs * (dxh - m1 - xh * m2);
+  }
+}
+
+}  // namespace tdvc
+using namespace tdvc;
+
+extern "C" int tdvc_weight_norm_fwd(const float* v, const float* g, float* w, float* inv_norm, int rows, int cols,
+                                    void* stream) {
+  TDVC_CHECK_ARG(rows > 0 && cols > 0 && v && g && w && inv_norm);
+  int threads = cols >= 1024 ? 256 : (cols >= 128 ? 128 : 32);
+  wn_fwd_k<<<rows, threads, 0, (cudaStream_t)stream>>>(v, g, w, inv_norm, cols);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_weight_norm_bwd(const float* dw, const float* v, const float* g, const float* inv_norm, float* dv,
+                                    float* dg, int rows, int cols, void* stream) {
+  TDVC_CHECK_ARG(rows > 0 && cols > 0 && dw && v && g && inv_norm && dv && dg);
+  int threads = cols >= 1024 ? 256 : (cols >= 128 ? 128 : 32);
+  wn_bwd_k<<<rows, threads, 0, (cudaStream_t)stream>>>(dw, v, g, inv_norm, dv, dg, cols);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_instnorm_stats(const float* x, float* mean, float* rstd, int BC, int T, float eps, void* stream) {
+  TDVC_CHECK_ARG(BC >= 0 && T > 0 && x && mean && rstd);
+  if (BC == 0) return TDVC_OK;
+  instnorm_stats_k<<<BC, T >= 1024 ? 256 : 128, 0, (cudaStream_t)stream>>>(x, mean, rstd, T, eps);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_cin_apply_fwd(const float* x, const float* mean, const float* rstd, const float* gb, int Tg,
+                                  float* y, int B, int C, int T, float out_slope, void* stream) {
+  TDVC_CHECK_ARG(B >= 0 && C > 0 && T > 0 && x && mean && rstd && y);
+  TDVC_CHECK_ARG(gb == nullptr || Tg == 1 || Tg == T);
+  if (B == 0) return TDVC_OK;
+  long long n = (long long)B * C * T;
+  int blocks = (int)std::min<long long>((n + 255) / 256, 16LL * num_sms());
+  cin_apply_fwd_k<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, mean, rstd, gb, Tg, y, B, C, T, out_slope);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_cin_apply_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
+                                  const float* gb, int Tg, const float* y_act, float* dx, float* dgb, int B, int C,
+                                  int T, float out_slope, void* stream) {
+  TDVC_CHECK_ARG(B >= 0 && C > 0 && T > 0 && dy && x && mean && rstd && dx);
+  TDVC_CHECK_ARG(gb == nullptr || ((Tg == 1 || Tg == T) && dgb != nullptr));
+  TDVC_CHECK_ARG(out_slope == 1.0f || y_act != nullptr);
+  if (B == 0) return TDVC_OK;
+  cin_apply_bwd_k<<<B * C, T >= 1024 ? 256 : 128, 0, (cudaStream_t)stream>>>(dy, x, mean, rstd, gb, Tg, y_act, dx, dgb,
+                                                                             C, T, out_slope);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}

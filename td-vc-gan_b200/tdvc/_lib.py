@@ -1,0 +1,95 @@
+"""ctypes binding of libtdvc_b200.so (the C ABI declared in include/tdvc_b200.h).
+
+The library is built in-tree by build.sh / __graft_entry__.build().  There is no CPU or
+PyTorch fallback: if the shared object is missing, or a tensor is not on a CUDA device, the
+ops raise."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtdvc_b200.so")
+
+c_float_p = C.c_void_p  # device pointers travel as void*
+
+
+class ConvGeom(C.Structure):
+    """struct tdvc_conv_geom"""
+    _fields_ = [("B", C.c_int32), ("Cin", C.c_int32), ("Tin", C.c_int32), ("Cout", C.c_int32),
+                ("Tout", C.c_int32), ("K", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
+                ("dilation", C.c_int32), ("groups", C.c_int32), ("pad_mode", C.c_int32),
+                ("in_slope", C.c_float), ("out_act", C.c_int32), ("out_slope", C.c_float)]
+
+
+PAD_ZEROS, PAD_REFLECT = 0, 1
+ACT_NONE, ACT_LRELU, ACT_TANH = 0, 1, 2
+
+_P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_G = C.POINTER(ConvGeom)
+
+# name -> (restype, argtypes); mirrors include/tdvc_b200.h one to one (tests check every symbol)
+SIGNATURES = {
+    "tdvc_last_error": (C.c_char_p, []),
+    "tdvc_version": (_I, []),
+    "tdvc_device_is_sm100": (_I, []),
+    "tdvc_weight_norm_fwd": (_I, [_P, _P, _P, _P, _I, _I, _P]),
+    "tdvc_weight_norm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "tdvc_conv1d_fwd": (_I, [_G, _P, _P, _P, _P, _P, _P]),
+    "tdvc_conv1d_bwd_data_ws": (_L, [_G]),
+    "tdvc_conv1d_bwd_data": (_I, [_G, _P, _P, _P, _P, _P, _P]),
+    "tdvc_conv1d_bwd_weight": (_I, [_G, _P, _P, _P, _P, _P]),
+    "tdvc_conv_transpose1d_fwd": (_I, [_G, _P, _P, _P, _P, _P]),
+    "tdvc_conv_transpose1d_bwd_data": (_I, [_G, _P, _P, _P, _P]),
+    "tdvc_conv_transpose1d_bwd_weight": (_I, [_G, _P, _P, _P, _P, _P]),
+    "tdvc_leaky_relu_fwd": (_I, [_P, _P, _L, _F, _P]),
+    "tdvc_act_bwd_from_output": (_I, [_P, _P, _P, _L, _I, _F, _P]),
+    "tdvc_film_fwd": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "tdvc_film_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "tdvc_add3_scale": (_I, [_P, _P, _P, _P, _L, _F, _P]),
+    "tdvc_l2norm_fwd": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "tdvc_l2norm_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+    "tdvc_cond_concat_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "tdvc_cond_concat_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "tdvc_instnorm_stats": (_I, [_P, _P, _P, _I, _I, _F, _P]),
+    "tdvc_cin_apply_fwd": (_I, [_P, _P, _P, _P, _I, _P, _I, _I, _I, _F, _P]),
+    "tdvc_cin_apply_bwd": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _F, _P]),
+    "tdvc_avgpool4s2_fwd": (_I, [_P, _P, _I, _I, _I, _P]),
+    "tdvc_avgpool4s2_bwd": (_I, [_P, _P, _I, _I, _I, _P]),
+    "tdvc_select_channel_fwd": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "tdvc_select_channel_bwd": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "tdvc_sq_err_const_sum": (_I, [_P, _F, _F, _P, _L, _P]),
+    "tdvc_sq_err_const_bwd": (_I, [_P, _F, _F, _P, _P, _L, _P]),
+    "tdvc_abs_diff_sum": (_I, [_P, _P, _F, _P, _L, _P]),
+    "tdvc_abs_diff_bwd": (_I, [_P, _P, _F, _P, _P, _L, _P]),
+    "tdvc_adamw_multi": (_I, [_P, _P, _P, _P, _P, _I, _L, _F, _F, _F, _F, _F, _I, _F, _P]),
+    "tdvc_pack_cl_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _P]),
+    "tdvc_pack_weight_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "tdvc_conv1d_tc_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P]),
+}
+
+_lib = None
+
+
+def load():
+    """Loads (once) and returns the CDLL.  Raises RuntimeError when the extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"tdvc: {LIB_PATH} is missing -- build it with ./build.sh (or __graft_entry__.build()); "
+            "there is no CPU / PyTorch fallback for the hot path")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)      # AttributeError here = header / library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().tdvc_last_error()
+        raise RuntimeError(f"tdvc {what} failed ({rc}): {msg.decode() if msg else '?'}")

@@ -1,0 +1,539 @@
+"""torch.autograd.Functions over the C ABI (include/tdvc_b200.h).
+
+Each op mirrors one ATen call site of the reference (cited in the header) and keeps its
+argument meaning.  PyTorch is used for device memory, streams and autograd bookkeeping only:
+all arithmetic happens in libtdvc_b200.so.  Inputs must be CUDA tensors; fp32, NCW.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import ACT_LRELU, ACT_NONE, ACT_TANH, PAD_REFLECT, PAD_ZEROS, ConvGeom
+
+_ACT = {None: ACT_NONE, "none": ACT_NONE, "lrelu": ACT_LRELU, "tanh": ACT_TANH}
+
+# precision mode of the dense stride-1 convolutions: "fp32" (CUDA-core exact path, rel 1e-5 vs the
+# reference) or "bf16" (tcgen05 tensor-core path, bf16 operands / fp32 accumulate, rel 2e-2)
+_PRECISION = "fp32"
+
+
+def set_precision(mode: str):
+    global _PRECISION
+    if mode not in ("fp32", "bf16"):
+        raise ValueError(mode)
+    _PRECISION = mode
+
+
+def get_precision() -> str:
+    return _PRECISION
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _st():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _req(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("tdvc ops need CUDA tensors (there is no CPU fallback); got a "
+                               f"{t.device} tensor")
+        if t.dtype != torch.float32:
+            raise RuntimeError(f"tdvc ops are fp32 at the boundary; got {t.dtype}")
+
+
+def _c(t: Optional[torch.Tensor]):
+    return None if t is None else t.contiguous()
+
+
+def _geom(B, Cin, Tin, Cout, Tout, K, stride, pad, dilation, groups, pad_mode, in_slope, out_act, out_slope):
+    return ConvGeom(B, Cin, Tin, Cout, Tout, K, stride, pad, dilation, groups, pad_mode, float(in_slope),
+                    out_act, float(out_slope))
+
+
+# ----------------------------------------------------------------------------- weight norm
+
+class _WeightNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, v, g):
+        _req(v, g)
+        v, g = _c(v), _c(g)
+        rows = v.shape[0]
+        cols = v.numel() // rows
+        w = torch.empty_like(v)
+        inv = torch.empty(rows, device=v.device, dtype=torch.float32)
+        _lib.check(_lib.load().tdvc_weight_norm_fwd(_p(v), _p(g), _p(w), _p(inv), rows, cols, _st()), "weight_norm_fwd")
+        ctx.save_for_backward(v, g, inv)
+        return w
+
+    @staticmethod
+    def backward(ctx, dw):
+        v, g, inv = ctx.saved_tensors
+        dw = _c(dw)
+        rows = v.shape[0]
+        cols = v.numel() // rows
+        dv = torch.empty_like(v)
+        dg = torch.empty_like(g)
+        _lib.check(_lib.load().tdvc_weight_norm_bwd(_p(dw), _p(v), _p(g), _p(inv), _p(dv), _p(dg), rows, cols, _st()),
+                   "weight_norm_bwd")
+        return dv, dg
+
+
+def weight_norm(v: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+    """w = g * v / ||v|| (norm over all dims but 0) -- torch.nn.utils.weight_norm's per-forward recompute."""
+    return _WeightNorm.apply(v, g)
+
+
+# ----------------------------------------------------------------------------- conv1d
+
+class _Conv1d(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, bias, residual, stride, pad, dilation, groups, pad_mode, in_slope, out_act, out_slope):
+        _req(x, w, bias, residual)
+        x, w, bias, residual = _c(x), _c(w), _c(bias), _c(residual)
+        B, Cin, Tin = x.shape
+        Cout, cin_g, K = w.shape
+        if cin_g * groups != Cin:
+            raise RuntimeError(f"conv1d: weight {tuple(w.shape)} does not match input {tuple(x.shape)} groups={groups}")
+        Tout = (Tin + 2 * pad - dilation * (K - 1) - 1) // stride + 1
+        if Tout <= 0:
+            raise RuntimeError(f"conv1d: input length {Tin} too short for kernel {K} (dilation {dilation})")
+        if pad_mode == PAD_REFLECT and pad >= Tin:
+            raise RuntimeError(f"conv1d: reflect padding {pad} must be smaller than the input length {Tin}")
+        g = _geom(B, Cin, Tin, Cout, Tout, K, stride, pad, dilation, groups, pad_mode, in_slope, out_act, out_slope)
+        y = torch.empty(B, Cout, Tout, device=x.device, dtype=torch.float32)
+        if residual is not None and residual.shape != y.shape:
+            raise RuntimeError("conv1d: residual shape mismatch")
+        _lib.check(_lib.load().tdvc_conv1d_fwd(C.byref(g), _p(x), _p(w), _p(bias), _p(residual), _p(y), _st()), "conv1d_fwd")
+        ctx.geom = g
+        ctx.has_bias = bias is not None
+        ctx.has_res = residual is not None
+        ctx.save_for_backward(x, w, y if out_act != ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        g = ctx.geom
+        lib = _lib.load()
+        dy = _c(dy)
+        if g.out_act != ACT_NONE:
+            dz = torch.empty_like(dy)
+            _lib.check(lib.tdvc_act_bwd_from_output(_p(dy), _p(y), _p(dz), dy.numel(), g.out_act, g.out_slope, _st()),
+                       "act_bwd")
+            dy = dz
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            n_ws = lib.tdvc_conv1d_bwd_data_ws(C.byref(g))
+            ws = torch.empty(n_ws, device=x.device, dtype=torch.float32) if n_ws > 0 else None
+            _lib.check(lib.tdvc_conv1d_bwd_data(C.byref(g), _p(dy), _p(w), _p(x), _p(dx), _p(ws), _st()), "conv1d_bwd_data")
+        need_b = ctx.has_bias and ctx.needs_input_grad[2]
+        if ctx.needs_input_grad[1] or need_b:
+            dw = torch.empty_like(w)
+            db = torch.empty(g.Cout, device=x.device, dtype=torch.float32) if need_b else None
+            _lib.check(lib.tdvc_conv1d_bwd_weight(C.byref(g), _p(dy), _p(x), _p(dw), _p(db), _st()), "conv1d_bwd_weight")
+            if not ctx.needs_input_grad[1]:
+                dw = None
+        dres = dy if (ctx.has_res and ctx.needs_input_grad[3]) else None
+        return dx, dw, db, dres, None, None, None, None, None, None, None, None
+
+
+def conv1d(x, weight, bias=None, *, stride=1, padding=0, dilation=1, groups=1, reflect=False,
+           in_slope=1.0, out_act=None, out_slope=0.2, residual=None):
+    """act(conv1d(leaky_relu(pad(x), in_slope), weight) + bias + residual); nn.Conv1d semantics
+    (padding_mode 'zeros' or 'reflect')."""
+    return _Conv1d.apply(x, weight, bias, residual, int(stride), int(padding), int(dilation), int(groups),
+                         PAD_REFLECT if (reflect and padding > 0) else PAD_ZEROS, float(in_slope), _ACT[out_act],
+                         float(out_slope))
+
+
+def linear(x, weight, bias=None):
+    """F.linear on [B, Cin] as a length-1 convolution (Generator.embedding, CIN.embedding)."""
+    return conv1d(x.unsqueeze(2), weight.unsqueeze(2), bias).squeeze(2)
+
+
+# ----------------------------------------------------------------------------- conv transpose
+
+class _ConvTranspose1d(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, bias, stride, pad, output_padding):
+        _req(x, w, bias)
+        x, w, bias = _c(x), _c(w), _c(bias)
+        B, Cin, Tin = x.shape
+        Cin_w, Cout, K = w.shape
+        if Cin_w != Cin:
+            raise RuntimeError(f"conv_transpose1d: weight {tuple(w.shape)} does not match input {tuple(x.shape)}")
+        Tout = (Tin - 1) * stride - 2 * pad + (K - 1) + output_padding + 1
+        g = _geom(B, Cin, Tin, Cout, Tout, K, stride, pad, 1, 1, PAD_ZEROS, 1.0, ACT_NONE, 1.0)
+        y = torch.empty(B, Cout, Tout, device=x.device, dtype=torch.float32)
+        _lib.check(_lib.load().tdvc_conv_transpose1d_fwd(C.byref(g), _p(x), _p(w), _p(bias), _p(y), _st()),
+                   "conv_transpose1d_fwd")
+        ctx.geom = g
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        g = ctx.geom
+        lib = _lib.load()
+        dy = _c(dy)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            _lib.check(lib.tdvc_conv_transpose1d_bwd_data(C.byref(g), _p(dy), _p(w), _p(dx), _st()), "convT_bwd_data")
+        need_b = ctx.has_bias and ctx.needs_input_grad[2]
+        if ctx.needs_input_grad[1] or need_b:
+            dw = torch.empty_like(w)
+            db = torch.empty(g.Cout, device=x.device, dtype=torch.float32) if need_b else None
+            _lib.check(lib.tdvc_conv_transpose1d_bwd_weight(C.byref(g), _p(dy), _p(x), _p(dw), _p(db), _st()),
+                       "convT_bwd_weight")
+            if not ctx.needs_input_grad[1]:
+                dw = None
+        return dx, dw, db, None, None, None
+
+
+def conv_transpose1d(x, weight, bias=None, *, stride=1, padding=0, output_padding=0):
+    return _ConvTranspose1d.apply(x, weight, bias, int(stride), int(padding), int(output_padding))
+
+
+# ----------------------------------------------------------------------------- elementwise
+
+class _LeakyReLU(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, slope):
+        _req(x)
+        x = _c(x)
+        y = torch.empty_like(x)
+        _lib.check(_lib.load().tdvc_leaky_relu_fwd(_p(x), _p(y), x.numel(), slope, _st()), "leaky_relu")
+        ctx.slope = slope
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dy = _c(dy)
+        dx = torch.empty_like(dy)
+        _lib.check(_lib.load().tdvc_act_bwd_from_output(_p(dy), _p(y), _p(dx), dy.numel(), ACT_LRELU, ctx.slope, _st()),
+                   "leaky_relu_bwd")
+        return dx, None
+
+
+def leaky_relu(x, slope=0.2):
+    return _LeakyReLU.apply(x, float(slope))
+
+
+class _Film(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, gb):
+        _req(h, gb)
+        h, gb = _c(h), _c(gb)
+        B, Cc, T = h.shape
+        if gb.shape != (B, 2 * Cc, T):
+            raise RuntimeError(f"film: gamma/beta tensor {tuple(gb.shape)} does not match {tuple(h.shape)}")
+        y = torch.empty_like(h)
+        _lib.check(_lib.load().tdvc_film_fwd(_p(h), _p(gb), _p(y), B, Cc, T, _st()), "film_fwd")
+        ctx.save_for_backward(h, gb)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        h, gb = ctx.saved_tensors
+        dy = _c(dy)
+        B, Cc, T = h.shape
+        dh = torch.empty_like(h)
+        dgb = torch.empty_like(gb)
+        _lib.check(_lib.load().tdvc_film_bwd(_p(dy), _p(h), _p(gb), _p(dh), _p(dgb), B, Cc, T, _st()), "film_bwd")
+        return dh, dgb
+
+
+def film(h, gb):
+    """h*(1+gamma)+beta with (gamma, beta) = gb.chunk(2, dim=1)  (model/generator.py:104-107)."""
+    return _Film.apply(h, gb)
+
+
+class _Add3Scale(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, alpha, a, b, c):
+        _req(a, b, c)
+        a, b, c = _c(a), _c(b), _c(c)
+        y = torch.empty_like(a)
+        _lib.check(_lib.load().tdvc_add3_scale(_p(a), _p(b), _p(c), _p(y), a.numel(), alpha, _st()), "add3_scale")
+        ctx.alpha = alpha
+        ctx.n = 1 + (b is not None) + (c is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _c(dy)
+        d = torch.empty_like(dy)
+        _lib.check(_lib.load().tdvc_add3_scale(_p(dy), None, None, _p(d), dy.numel(), ctx.alpha, _st()), "add3_scale_bwd")
+        return (None, d) + tuple(d if i < ctx.n - 1 else None for i in range(2))
+
+
+def add_scale(a, b=None, c=None, alpha=1.0):
+    """alpha * (a + b + c)"""
+    return _Add3Scale.apply(float(alpha), a, b, c)
+
+
+class _L2Norm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        _req(x)
+        x = _c(x)
+        B, Cc, T = x.shape
+        y = torch.empty_like(x)
+        inv = torch.empty(B, T, device=x.device, dtype=torch.float32)
+        _lib.check(_lib.load().tdvc_l2norm_fwd(_p(x), _p(y), _p(inv), B, Cc, T, _st()), "l2norm_fwd")
+        ctx.save_for_backward(y, inv)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, inv = ctx.saved_tensors
+        dy = _c(dy)
+        B, Cc, T = y.shape
+        dx = torch.empty_like(y)
+        _lib.check(_lib.load().tdvc_l2norm_bwd(_p(dy), _p(y), _p(inv), _p(dx), B, Cc, T, _st()), "l2norm_bwd")
+        return dx
+
+
+def l2_normalize(x):
+    """F.normalize(x, dim=1) for [B, C, T]."""
+    return _L2Norm.apply(x)
+
+
+class _CondConcat(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, c, e, c_first):
+        _req(c, e)
+        c, e = _c(c), _c(e)
+        B, Cc = c.shape
+        Be, Ce, T = e.shape
+        if B != Be:
+            raise RuntimeError("cond_concat: batch mismatch")
+        out = torch.empty(B, Cc + Ce, T, device=e.device, dtype=torch.float32)
+        _lib.check(_lib.load().tdvc_cond_concat_fwd(_p(c), _p(e), _p(out), B, Cc, Ce, T, c_first, _st()), "cond_concat_fwd")
+        ctx.dims = (B, Cc, Ce, T, c_first)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, Cc, Ce, T, c_first = ctx.dims
+        dout = _c(dout)
+        dc = torch.empty(B, Cc, device=dout.device, dtype=torch.float32)
+        de = torch.empty(B, Ce, T, device=dout.device, dtype=torch.float32) if ctx.needs_input_grad[1] else None
+        _lib.check(_lib.load().tdvc_cond_concat_bwd(_p(dout), _p(dc), _p(de), B, Cc, Ce, T, c_first, _st()), "cond_concat_bwd")
+        return dc, de, None
+
+
+def cond_concat(c, e):
+    """torch.cat([c.unsqueeze(2).repeat(1, 1, T), e], dim=1)  (model/generator.py:387-399)."""
+    return _CondConcat.apply(c, e, 1)
+
+
+def cond_concat_front(x, c):
+    """torch.cat([x, c.unsqueeze(2).repeat(1, 1, T)], dim=1)  (model/generator.py:260-261,380-381)."""
+    return _CondConcat.apply(c, x, 0)
+
+
+def cat_channels_2d(a, b):
+    """torch.cat([a, b], dim=1) of two [B, C] speaker codes (model/generator.py:498; glue, not arithmetic)."""
+    return torch.cat([a, b], dim=1)
+
+
+# ----------------------------------------------------------------------------- instance norm / CIN
+
+class _CinApply(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gb, eps, out_slope):
+        _req(x, gb)
+        x, gb = _c(x), _c(gb)
+        B, Cc, T = x.shape
+        Tg = 1
+        if gb is not None:
+            if gb.dim() != 3 or gb.shape[0] != B or gb.shape[1] != 2 * Cc or gb.shape[2] not in (1, T):
+                raise RuntimeError(f"cin: gamma/beta tensor {tuple(gb.shape)} does not match {tuple(x.shape)}")
+            Tg = gb.shape[2]
+        lib = _lib.load()
+        mean = torch.empty(B * Cc, device=x.device, dtype=torch.float32)
+        rstd = torch.empty_like(mean)
+        _lib.check(lib.tdvc_instnorm_stats(_p(x), _p(mean), _p(rstd), B * Cc, T, eps, _st()), "instnorm_stats")
+        y = torch.empty_like(x)
+        _lib.check(lib.tdvc_cin_apply_fwd(_p(x), _p(mean), _p(rstd), _p(gb), Tg, _p(y), B, Cc, T, out_slope, _st()),
+                   "cin_apply_fwd")
+        ctx.out_slope, ctx.Tg = out_slope, Tg
+        ctx.save_for_backward(x, mean, rstd, gb, y if out_slope != 1.0 else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, rstd, gb, y = ctx.saved_tensors
+        dy = _c(dy)
+        B, Cc, T = x.shape
+        dx = torch.empty_like(x)
+        dgb = torch.empty_like(gb) if gb is not None else None
+        _lib.check(_lib.load().tdvc_cin_apply_bwd(_p(dy), _p(x), _p(mean), _p(rstd), _p(gb), ctx.Tg, _p(y), _p(dx),
+                                                  _p(dgb), B, Cc, T, ctx.out_slope, _st()), "cin_apply_bwd")
+        return dx, dgb, None, None
+
+
+def instance_norm(x, eps=1e-5, out_slope=1.0):
+    """nn.InstanceNorm1d(affine=False) (+ optional fused LeakyReLU)."""
+    return _CinApply.apply(x, None, float(eps), float(out_slope))
+
+
+def cond_instance_norm(x, gb, eps=1e-5, out_slope=1.0):
+    """(1 + gamma) * instance_norm(x) + beta with gb = [B, 2C, 1 or T]  (model/conditional_instance_norm.py:18-19)."""
+    return _CinApply.apply(x, gb, float(eps), float(out_slope))
+
+
+# ----------------------------------------------------------------------------- pooling / gather
+
+class _AvgPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        _req(x)
+        x = _c(x)
+        B, Cc, Tin = x.shape
+        Tout = (Tin + 2 - 4) // 2 + 1
+        y = torch.empty(B, Cc, Tout, device=x.device, dtype=torch.float32)
+        _lib.check(_lib.load().tdvc_avgpool4s2_fwd(_p(x), _p(y), B * Cc, Tin, Tout, _st()), "avgpool_fwd")
+        ctx.dims = (B, Cc, Tin, Tout)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, Cc, Tin, Tout = ctx.dims
+        dy = _c(dy)
+        dx = torch.empty(B, Cc, Tin, device=dy.device, dtype=torch.float32)
+        _lib.check(_lib.load().tdvc_avgpool4s2_bwd(_p(dy), _p(dx), B * Cc, Tin, Tout, _st()), "avgpool_bwd")
+        return dx
+
+
+def avg_pool_4_2_1(x):
+    """nn.AvgPool1d(kernel_size=4, stride=2, padding=1, count_include_pad=False)."""
+    return _AvgPool.apply(x)
+
+
+class _SelectChannel(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, label):
+        _req(x)
+        x = _c(x)
+        if not label.is_cuda or label.dtype != torch.int64:
+            raise RuntimeError("select_channel: label must be a CUDA int64 tensor")
+        label = label.contiguous()
+        B, Cc, T = x.shape
+        y = torch.empty(B, 1, T, device=x.device, dtype=torch.float32)
+        _lib.check(_lib.load().tdvc_select_channel_fwd(_p(x), _p(label), _p(y), B, Cc, T, _st()), "select_fwd")
+        ctx.dims = (B, Cc, T)
+        ctx.save_for_backward(label)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (label,) = ctx.saved_tensors
+        B, Cc, T = ctx.dims
+        dy = _c(dy)
+        dx = torch.empty(B, Cc, T, device=dy.device, dtype=torch.float32)
+        _lib.check(_lib.load().tdvc_select_channel_bwd(_p(dy), _p(label), _p(dx), B, Cc, T, _st()), "select_bwd")
+        return dx, None
+
+
+def select_channel(x, label):
+    """x.gather(1, label.view(-1,1,1).expand(-1,1,T))  (model/discriminator.py:49-51)."""
+    return _SelectChannel.apply(x, label)
+
+
+# ----------------------------------------------------------------------------- losses
+
+class _SqErrConstMean(torch.autograd.Function):
+    """sum_i weight_i * mean((a_i - target)^2) over a list of tensors: the LSGAN terms of
+    train.py:273-281,327-331 in one reduction buffer."""
+
+    @staticmethod
+    def forward(ctx, target, *tensors):
+        _req(*tensors)
+        tensors = [_c(t) for t in tensors]
+        out = torch.zeros(1, device=tensors[0].device, dtype=torch.float32)
+        lib = _lib.load()
+        for t in tensors:
+            _lib.check(lib.tdvc_sq_err_const_sum(_p(t), target, 1.0 / t.numel(), _p(out), t.numel(), _st()), "sq_err_sum")
+        ctx.target = target
+        ctx.save_for_backward(*tensors)
+        return out.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        tensors = ctx.saved_tensors
+        g = g.reshape(1).contiguous().float()
+        lib = _lib.load()
+        grads = []
+        for i, t in enumerate(tensors):
+            if not ctx.needs_input_grad[1 + i]:
+                grads.append(None)
+                continue
+            d = torch.empty_like(t)
+            _lib.check(lib.tdvc_sq_err_const_bwd(_p(t), ctx.target, 1.0 / t.numel(), _p(g), _p(d), t.numel(), _st()),
+                       "sq_err_bwd")
+            grads.append(d)
+        return (None, *grads)
+
+
+def mse_to_const_sum(tensors: Sequence[torch.Tensor], target: float) -> torch.Tensor:
+    """sum over tensors of F.mse_loss(t, full_like(t, target))."""
+    return _SqErrConstMean.apply(float(target), *tensors)
+
+
+class _L1MeanSum(torch.autograd.Function):
+    """sum_i mean(|a_i - b_i|), b detached: util/losses.py:55-68 (all 30 feature maps, one scalar)."""
+
+    @staticmethod
+    def forward(ctx, n, *tensors):
+        a, b = tensors[:n], tensors[n:]
+        _req(*a, *b)
+        a = [_c(t) for t in a]
+        b = [_c(t) for t in b]
+        out = torch.zeros(1, device=a[0].device, dtype=torch.float32)
+        lib = _lib.load()
+        for u, v in zip(a, b):
+            if u.shape != v.shape:
+                raise RuntimeError(f"l1 loss: shape mismatch {tuple(u.shape)} vs {tuple(v.shape)}")
+            _lib.check(lib.tdvc_abs_diff_sum(_p(u), _p(v), 1.0 / u.numel(), _p(out), u.numel(), _st()), "abs_diff_sum")
+        ctx.n = n
+        ctx.save_for_backward(*a, *b)
+        return out.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        n = ctx.n
+        a, b = ctx.saved_tensors[:n], ctx.saved_tensors[n:]
+        g = g.reshape(1).contiguous().float()
+        lib = _lib.load()
+        grads = []
+        for i, (u, v) in enumerate(zip(a, b)):
+            if not ctx.needs_input_grad[1 + i]:
+                grads.append(None)
+                continue
+            d = torch.empty_like(u)
+            _lib.check(lib.tdvc_abs_diff_bwd(_p(u), _p(v), 1.0 / u.numel(), _p(g), _p(d), u.numel(), _st()), "abs_diff_bwd")
+            grads.append(d)
+        return (None, *grads, *([None] * n))
+
+
+def l1_mean_sum(sig: Sequence[torch.Tensor], ref: Sequence[torch.Tensor]) -> torch.Tensor:
+    sig, ref = list(sig), [r.detach() for r in ref]
+    return _L1MeanSum.apply(len(sig), *sig, *ref)

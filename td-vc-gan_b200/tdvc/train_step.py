@@ -1,0 +1,132 @@
+"""One G+D training iteration, restating the loop body of the reference's train.py:209-511 on the tdvc
+modules.  `train.py` itself runs unchanged against the drop-in `model` / `util` packages;
+this class is the same computation packaged for benchmarking, CUDA-graph capture and data-parallel use
+(it skips work that provably cannot change any result, each case cited below)."""
+from __future__ import annotations
+
+import contextlib
+from typing import Optional
+
+import torch
+
+import util.losses as losses
+from tdvc import ops
+
+
+def label2onehot(labels: torch.Tensor, n_classes: int) -> torch.Tensor:
+    """train.py:39-44, built on the labels' device."""
+    out = torch.zeros(labels.shape[0], n_classes, device=labels.device, dtype=torch.float32)
+    out[torch.arange(labels.shape[0], device=labels.device), labels] = 1
+    return out
+
+
+@contextlib.contextmanager
+def frozen(module: torch.nn.Module):
+    """Temporarily stop producing weight gradients for `module` (its inputs still get gradients).  During the
+    G step the reference computes D's weight gradients and throws them away (optimizer_D.zero_grad() precedes,
+    optimizer_D.step() never follows: train.py:485-491)."""
+    flags = [p.requires_grad for p in module.parameters()]
+    for p in module.parameters():
+        p.requires_grad_(False)
+    try:
+        yield
+    finally:
+        for p, f in zip(module.parameters(), flags):
+            p.requires_grad_(f)
+
+
+class TrainStep:
+    def __init__(self, G, D, hp: dict, optimizer_G=None, optimizer_D=None, num_spk: Optional[int] = None,
+                 grad_hook=None):
+        """hp: the `train:` section of a config/*.yaml as a dict (lambda_*, no_conv, jitter_amp ...).
+        grad_hook(module_name, params) is called after each backward and before the optimiser step: the
+        data-parallel gradient all-reduce plugs in there."""
+        self.G, self.D, self.hp = G, D, hp
+        self.opt_G, self.opt_D = optimizer_G, optimizer_D
+        self.num_spk = num_spk if num_spk is not None else G.embedding.weight.shape[1]
+        self.grad_hook = grad_hook
+
+    # ---- D step: train.py:259-296
+    def d_step(self, batch) -> dict:
+        G, D = self.G, self.D
+        x = batch["signal_real"]
+        c_tgt = label2onehot(batch["label_tgt"], self.num_spk)
+        # The reference builds G's graph here and never back-propagates it through G's weights: the full-rate
+        # output is detached (train.py:269); the sub-scale heads are not, but the gradients they deposit in G
+        # are zeroed before G's own backward (train.py:485-486).  no_grad skips that dead graph.
+        with torch.no_grad():
+            fake, fake_subs = G(x, c_tgt, c_var=batch["c_f0_conv"], out_subsample=True)
+            real_subs = D.get_subsamples(x)
+        o_real, _ = D(x, batch["label_src"], real_subs)
+        o_fake, _ = D(fake, batch["label_tgt"], fake_subs)
+        d_real = ops.mse_to_const_sum(o_real, 1.0)
+        d_fake = ops.mse_to_const_sum(o_fake, 0.0)
+        d_loss = d_real + d_fake
+        if self.opt_D is not None:
+            self.opt_D.zero_grad(set_to_none=True)
+        d_loss.backward()
+        if self.grad_hook is not None:
+            self.grad_hook("D", list(D.parameters()))
+        if self.opt_D is not None:
+            self.opt_D.step()
+        return {"d_loss_real": d_real.detach(), "d_loss_fake": d_fake.detach(), "d_loss": d_loss.detach(),
+                "fake": fake}
+
+    # ---- G step: train.py:320-491 (lambda_f0 needs torchcrepe, lambda_latcls the latent classifier: both 0 here)
+    def g_step(self, batch, raw_draws=None) -> dict:
+        G, D, hp = self.G, self.D, self.hp
+        x = batch["signal_real"]
+        lab_s, lab_t = batch["label_src"], batch["label_tgt"]
+        c_src = label2onehot(lab_s, self.num_spk)
+        c_tgt = label2onehot(lab_t, self.num_spk)
+        out = {}
+        with frozen(D):
+            fake, fake_subs = G(x, c_tgt, c_var=batch["c_f0_conv"], out_subsample=True)
+            emb_real = G.content_embedding
+            o_fake, _ = D(fake, lab_t, fake_subs)
+            g_adv = ops.mse_to_const_sum(o_fake, 1.0)
+            f_real = None
+            if (hp["lambda_rec"] > 0 or hp["lambda_idt"] > 0) and hp["lambda_feat"] > 0:
+                with torch.no_grad():   # reference features are .detach()ed inside the loss (losses.py:63)
+                    _, f_real = D(x, lab_s, D.get_subsamples(x))
+            zero = torch.zeros((), device=x.device)
+            g_rec = zero
+            if (not hp["no_conv"]) and hp["lambda_rec"] > 0:
+                rec, rec_subs = G(fake.detach(), c_src, c_var=batch["c_f0_src"], out_subsample=True)
+                if hp["lambda_feat"] > 0:
+                    _, f_rec = D(rec, lab_s, rec_subs)
+                    g_rec = g_rec + hp["lambda_feat"] * losses.multiscale_feat_loss(f_rec, f_real, norm_p=1)
+                if hp["lambda_spec"] > 0:
+                    g_rec = g_rec + hp["lambda_spec"] * losses.multiscale_spec_loss(rec, x, [2048, 1024, 512])
+            g_idt = zero
+            if hp["lambda_idt"] > 0:
+                if not hp["no_conv"]:
+                    idt, idt_subs = G(x, c_src, c_var=batch["c_f0_src"], out_subsample=True)
+                else:
+                    idt, idt_subs = fake, fake_subs
+                if hp["lambda_feat"] > 0:
+                    _, f_idt = D(idt, lab_s, idt_subs)
+                    g_idt = g_idt + hp["lambda_feat"] * losses.multiscale_feat_loss(f_idt, f_real, norm_p=1)
+                if hp["lambda_spec"] > 0:
+                    g_idt = g_idt + hp["lambda_spec"] * losses.multiscale_spec_loss(idt, x, [2048, 1024, 512])
+            g_cont = zero
+            if hp["lambda_cont_emb"] > 0 and hp["lambda_corrupted"]:
+                emb_corr = G.encoder(batch["signal_corrupted"])
+                g_cont = g_cont + losses.contrastive_loss(emb_real, emb_corr, num_negatives=100, temp=0.1,
+                                                          _raw_draws=raw_draws)
+            g_loss = g_adv + hp["lambda_rec"] * g_rec + hp["lambda_idt"] * g_idt + hp["lambda_cont_emb"] * g_cont
+            if self.opt_G is not None:
+                self.opt_G.zero_grad(set_to_none=True)
+            g_loss.backward()
+        if self.grad_hook is not None:
+            self.grad_hook("G", list(G.parameters()))
+        if self.opt_G is not None:
+            self.opt_G.step()
+        out.update(g_adv=g_adv.detach(), g_rec=g_rec.detach(), g_idt=g_idt.detach(), g_cont=g_cont.detach(),
+                   g_loss=g_loss.detach(), fake=fake.detach())
+        return out
+
+    def step(self, batch, raw_draws=None) -> dict:
+        out = self.d_step(batch)
+        out.update(self.g_step(batch, raw_draws))
+        return out

@@ -1,0 +1,256 @@
+"""Per-kernel parity: every C-ABI op against a plain fp64 CPU PyTorch statement of the same ATen op the
+reference calls.  Tolerance for the fp32 path: 1e-5 max-abs-normalised (BASELINE.json north_star);
+reductions over >1e5 terms (weight gradients) 3e-5."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+TOL_W = 3e-5
+
+
+def dev(t):
+    return t.detach().float().cuda().requires_grad_(t.requires_grad)
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g, dtype=torch.float64) * scale
+
+
+CONV_CASES = [
+    # B, Cin, T, Cout, K, stride, pad, dil, groups, reflect, in_slope, out_act, bias, residual
+    (2, 16, 300, 16, 3, 1, 1, 1, 1, True, 0.2, None, True, False),        # FiLM conv k3 d1
+    (2, 16, 300, 16, 7, 1, 9, 3, 1, True, 0.2, None, True, False),        # k7 d3
+    (2, 8, 300, 8, 11, 1, 25, 5, 1, True, 0.2, None, True, True),         # k11 d5 (+residual)
+    (2, 24, 257, 24, 3, 1, 1, 1, 1, False, 1.0, None, True, False),       # cond_var.0 'same'
+    (2, 136, 130, 136, 3, 1, 1, 1, 1, False, 1.0, None, True, False),     # real cond width
+    (2, 136, 130, 32, 3, 1, 1, 1, 1, False, 0.2, None, True, False),      # cond_var.2
+    (3, 16, 128, 16, 1, 1, 0, 1, 1, False, 0.2, None, True, True),        # posconv 1x1 + residual
+    (2, 1, 500, 16, 7, 1, 3, 1, 1, True, 1.0, None, True, False),         # encoder.0
+    (2, 16, 500, 1, 7, 1, 3, 1, 1, True, 0.2, "tanh", True, False),       # output head + tanh
+    (2, 16, 512, 32, 4, 2, 1, 1, 1, False, 0.2, None, True, False),       # strided r=2
+    (2, 32, 480, 64, 16, 8, 4, 1, 1, False, 0.2, None, True, False),      # strided r=8
+    (2, 24, 400, 40, 20, 10, 5, 1, 1, False, 0.2, None, True, False),     # strided r=10
+    (2, 1, 600, 16, 15, 1, 7, 1, 1, True, 1.0, "lrelu", True, False),     # D layer 0
+    (2, 16, 600, 64, 41, 4, 20, 1, 4, False, 1.0, "lrelu", True, False),  # D grouped (4->16)
+    (2, 64, 150, 64, 41, 4, 20, 1, 16, False, 1.0, "lrelu", True, False), # D grouped (4->4)
+    (2, 64, 35, 64, 5, 1, 2, 1, 1, False, 1.0, "lrelu", True, False),     # D dense k5, short T
+    (2, 64, 9, 100, 3, 1, 1, 1, 1, False, 1.0, None, False, False),       # D output, no bias
+    (2, 8, 640, 8, 33, 2, 16, 1, 8, False, 1.0, None, False, False),      # depthwise Kaiser r=2
+    (2, 8, 800, 8, 161, 10, 80, 1, 8, False, 1.0, None, False, False),    # depthwise Kaiser r=10
+    (1, 1, 1000, 1, 129, 2, 64, 1, 1, False, 1.0, None, False, False),    # D band-split FIR
+    (2, 100, 1, 128, 1, 1, 0, 1, 1, False, 1.0, None, True, False),       # Linear as conv, T=1
+    (1, 3, 31, 5, 5, 1, 2, 1, 1, True, 0.2, None, True, False),           # ragged tiny
+    (2, 256, 28, 256, 7, 1, 3, 1, 1, False, 0.2, None, True, False),      # encoder.18 (T/320)
+    (2, 16, 1000, 16, 11, 1, 25, 5, 1, True, 0.2, None, True, False),     # multi-tile reflect both ends
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[str(i) for i in range(len(CONV_CASES))])
+def test_conv1d_fwd_bwd(case):
+    from tdvc import ops
+    B, Cin, T, Cout, K, s, p, d, g, reflect, in_slope, out_act, has_b, has_r = case
+    x = rnd(B, Cin, T, seed=1).requires_grad_(True)
+    w = rnd(Cout, Cin // g, K, seed=2, scale=(Cin // g * K) ** -0.5).requires_grad_(True)
+    b = rnd(Cout, seed=3, scale=0.1).requires_grad_(True) if has_b else None
+    xin = F.leaky_relu(x, in_slope) if in_slope != 1.0 else x
+    if reflect and p > 0:
+        y0 = F.conv1d(F.pad(xin, (p, p), mode="reflect"), w, b, stride=s, dilation=d, groups=g)
+    else:
+        y0 = F.conv1d(xin, w, b, stride=s, padding=p, dilation=d, groups=g)
+    r = rnd(*y0.shape, seed=4).requires_grad_(True) if has_r else None
+    if has_r:
+        y0 = y0 + r
+    yref = {"lrelu": lambda v: F.leaky_relu(v, 0.2), "tanh": torch.tanh, None: lambda v: v}[out_act](y0)
+    proj = rnd(*yref.shape, seed=5)
+    (yref * proj).sum().backward()
+
+    xd, wd = dev(x), dev(w)
+    bd = dev(b) if has_b else None
+    rd = dev(r) if has_r else None
+    y = ops.conv1d(xd, wd, bd, stride=s, padding=p, dilation=d, groups=g, reflect=reflect, in_slope=in_slope,
+                   out_act=out_act, out_slope=0.2, residual=rd)
+    assert relerr(y, yref) < TOL
+    (y * proj.float().cuda()).sum().backward()
+    assert relerr(xd.grad, x.grad) < TOL
+    assert relerr(wd.grad, w.grad) < TOL_W
+    if has_b:
+        assert relerr(bd.grad, b.grad) < TOL_W
+    if has_r:
+        assert relerr(rd.grad, r.grad) < TOL
+
+
+@pytest.mark.parametrize("B,Cin,T,Cout,r", [(2, 32, 28, 16, 10), (2, 16, 70, 8, 8), (2, 8, 300, 4, 2), (1, 5, 33, 3, 3)])
+def test_conv_transpose1d(B, Cin, T, Cout, r):
+    from tdvc import ops
+    K, p, op = 2 * r, r // 2 + r % 2, r % 2
+    x = rnd(B, Cin, T, seed=1).requires_grad_(True)
+    w = rnd(Cin, Cout, K, seed=2, scale=(Cin * 2) ** -0.5).requires_grad_(True)
+    b = rnd(Cout, seed=3, scale=0.1).requires_grad_(True)
+    yref = F.conv_transpose1d(x, w, b, stride=r, padding=p, output_padding=op)
+    proj = rnd(*yref.shape, seed=5)
+    (yref * proj).sum().backward()
+    xd, wd, bd = dev(x), dev(w), dev(b)
+    y = ops.conv_transpose1d(xd, wd, bd, stride=r, padding=p, output_padding=op)
+    assert relerr(y, yref) < TOL
+    (y * proj.float().cuda()).sum().backward()
+    assert relerr(xd.grad, x.grad) < TOL
+    assert relerr(wd.grad, w.grad) < TOL_W
+    assert relerr(bd.grad, b.grad) < TOL_W
+
+
+@pytest.mark.parametrize("shape", [(16, 1, 7), (136, 136, 3), (1024, 1024, 5), (64, 4, 41), (256, 128, 20)])
+def test_weight_norm(shape):
+    from tdvc import ops
+    v = rnd(*shape, seed=1).requires_grad_(True)
+    g = (rnd(shape[0], 1, 1, seed=2).abs() + 0.5).requires_grad_(True)
+    wref = v * (g / v.reshape(shape[0], -1).norm(dim=1).reshape(-1, 1, 1))
+    proj = rnd(*shape, seed=3)
+    (wref * proj).sum().backward()
+    vd, gd = dev(v), dev(g)
+    w = ops.weight_norm(vd, gd)
+    assert relerr(w, wref) < TOL
+    (w * proj.float().cuda()).sum().backward()
+    assert relerr(vd.grad, v.grad) < TOL
+    assert relerr(gd.grad, g.grad) < TOL
+
+
+def test_elementwise_family():
+    from tdvc import ops
+    B, C, T = 3, 10, 257
+    h = rnd(B, C, T, seed=1).requires_grad_(True)
+    gb = rnd(B, 2 * C, T, seed=2).requires_grad_(True)
+    gam, bet = gb.chunk(2, dim=1)
+    yref = h * (1 + gam) + bet
+    proj = rnd(B, C, T, seed=3)
+    (yref * proj).sum().backward()
+    hd, gbd = dev(h), dev(gb)
+    y = ops.film(hd, gbd)
+    assert relerr(y, yref) < TOL
+    (y * proj.float().cuda()).sum().backward()
+    assert relerr(hd.grad, h.grad) < TOL and relerr(gbd.grad, gb.grad) < TOL
+    # leaky relu (odd length exercises the vector tail)
+    x = rnd(5, 3, 1001, seed=4).requires_grad_(True)
+    F.leaky_relu(x, 0.2).mul(rnd(5, 3, 1001, seed=5)).sum().backward()
+    xd = dev(x)
+    yd = ops.leaky_relu(xd, 0.2)
+    assert relerr(yd, F.leaky_relu(x, 0.2)) < TOL
+    (yd * rnd(5, 3, 1001, seed=5).float().cuda()).sum().backward()
+    assert relerr(xd.grad, x.grad) < TOL
+    # (a+b+c)/3
+    a, b, c = (rnd(2, 4, 99, seed=s).requires_grad_(True) for s in (6, 7, 8))
+    ((a + b + c) / 3).mul(rnd(2, 4, 99, seed=9)).sum().backward()
+    ad, bd, cd = dev(a), dev(b), dev(c)
+    s3 = ops.add_scale(ad, bd, cd, alpha=1 / 3)
+    assert relerr(s3, (a + b + c) / 3) < TOL
+    (s3 * rnd(2, 4, 99, seed=9).float().cuda()).sum().backward()
+    for u, v in ((ad, a), (bd, b), (cd, c)):
+        assert relerr(u.grad, v.grad) < TOL
+    # F.normalize(dim=1)
+    z = rnd(3, 16, 28, seed=10).requires_grad_(True)
+    F.normalize(z, dim=1).mul(rnd(3, 16, 28, seed=11)).sum().backward()
+    zd = dev(z)
+    n = ops.l2_normalize(zd)
+    assert relerr(n, F.normalize(z, dim=1)) < TOL
+    (n * rnd(3, 16, 28, seed=11).float().cuda()).sum().backward()
+    assert relerr(zd.grad, z.grad) < TOL
+    # cond concat, both orders
+    cc = rnd(3, 5, seed=12).requires_grad_(True)
+    e = rnd(3, 4, 40, seed=13).requires_grad_(True)
+    for first in (True, False):
+        cc.grad = e.grad = None
+        rep = cc.unsqueeze(2).repeat(1, 1, 40)
+        ref = torch.cat([rep, e], 1) if first else torch.cat([e, rep], 1)
+        (ref * rnd(3, 9, 40, seed=14)).sum().backward()
+        ccd, ed = dev(cc), dev(e)
+        o = ops.cond_concat(ccd, ed) if first else ops.cond_concat_front(ed, ccd)
+        assert relerr(o, ref) < 1e-7
+        (o * rnd(3, 9, 40, seed=14).float().cuda()).sum().backward()
+        assert relerr(ccd.grad, cc.grad) < TOL and relerr(ed.grad, e.grad) < TOL
+
+
+@pytest.mark.parametrize("Tg", [None, 1, "T"])
+@pytest.mark.parametrize("slope", [1.0, 0.2])
+def test_instance_norm_and_cin(Tg, slope):
+    from tdvc import ops
+    B, C, T = 3, 12, 333
+    x = (rnd(B, C, T, seed=1) * 2 + 0.3).requires_grad_(True)
+    xh = F.instance_norm(x, eps=1e-5)
+    gb = None
+    if Tg is not None:
+        gb = rnd(B, 2 * C, 1 if Tg == 1 else T, seed=2).requires_grad_(True)
+        gam, bet = gb.chunk(2, dim=1)
+        xh = (1 + gam) * xh + bet
+    yref = F.leaky_relu(xh, slope) if slope != 1.0 else xh
+    proj = rnd(B, C, T, seed=3)
+    (yref * proj).sum().backward()
+    xd = dev(x)
+    gbd = dev(gb) if gb is not None else None
+    y = ops.cond_instance_norm(xd, gbd, 1e-5, slope) if gb is not None else ops.instance_norm(xd, 1e-5, slope)
+    assert relerr(y, yref) < TOL
+    (y * proj.float().cuda()).sum().backward()
+    assert relerr(xd.grad, x.grad) < 2e-5
+    if gb is not None:
+        assert relerr(gbd.grad, gb.grad) < TOL
+
+
+def test_pool_select_losses_adamw():
+    from tdvc import ops
+    from tdvc.optim import FusedAdamW
+    for T in (64, 65, 9):
+        x = rnd(2, 3, T, seed=1).requires_grad_(True)
+        ref = F.avg_pool1d(x, 4, 2, 1, count_include_pad=False)
+        (ref * rnd(*ref.shape, seed=2)).sum().backward()
+        xd = dev(x)
+        y = ops.avg_pool_4_2_1(xd)
+        assert relerr(y, ref) < TOL
+        (y * rnd(*ref.shape, seed=2).float().cuda()).sum().backward()
+        assert relerr(xd.grad, x.grad) < TOL
+    x = rnd(4, 10, 35, seed=3).requires_grad_(True)
+    lab = torch.tensor([3, 0, 9, 3])
+    ref = x.gather(1, lab.view(-1, 1, 1).expand(-1, 1, 35))
+    (ref * rnd(4, 1, 35, seed=4)).sum().backward()
+    xd = dev(x)
+    y = ops.select_channel(xd, lab.cuda())
+    assert relerr(y, ref) < 1e-7
+    (y * rnd(4, 1, 35, seed=4).float().cuda()).sum().backward()
+    assert relerr(xd.grad, x.grad) < 1e-7
+    # LSGAN sums
+    outs = [rnd(4, 1, n, seed=10 + n).requires_grad_(True) for n in (35, 18, 9, 9, 18)]
+    ref = sum(F.mse_loss(o, torch.ones_like(o)) for o in outs)
+    (ref * 1.7).backward()
+    od = [dev(o) for o in outs]
+    l = ops.mse_to_const_sum(od, 1.0)
+    assert abs(l.item() - ref.item()) < 1e-5 * abs(ref.item())
+    (l * 1.7).backward()
+    for a, b in zip(od, outs):
+        assert relerr(a.grad, b.grad) < TOL
+    # feature matching L1
+    sig = [rnd(2, 4, n, seed=20 + n).requires_grad_(True) for n in (1001, 64, 7)]
+    reff = [rnd(2, 4, n, seed=40 + n) for n in (1001, 64, 7)]
+    ref = sum(F.l1_loss(a, b) for a, b in zip(sig, reff))
+    ref.backward()
+    sd = [dev(s) for s in sig]
+    l = ops.l1_mean_sum(sd, [r.float().cuda() for r in reff])
+    assert abs(l.item() - ref.item()) < 1e-5 * abs(ref.item())
+    l.backward()
+    for a, b in zip(sd, sig):
+        assert relerr(a.grad, b.grad) < TOL
+    # AdamW vs torch.optim.AdamW, 3 steps
+    ps = [rnd(7, 5, seed=50).float(), rnd(1000, seed=51).float(), rnd(3, 1, 1, seed=52).float()]
+    ref_p = [torch.nn.Parameter(p.clone().double()) for p in ps]
+    my_p = [torch.nn.Parameter(p.clone().cuda()) for p in ps]
+    o_ref = torch.optim.AdamW(ref_p, 1e-2, (0.8, 0.99))
+    o_my = FusedAdamW(my_p, 1e-2, (0.8, 0.99))
+    for step in range(3):
+        for i, (a, b) in enumerate(zip(ref_p, my_p)):
+            gr = rnd(*a.shape, seed=60 + 10 * step + i)
+            a.grad = gr.clone()
+            b.grad = gr.float().cuda()
+        o_ref.step(); o_my.step()
+    for a, b in zip(ref_p, my_p):
+        assert relerr(b, a) < 1e-5

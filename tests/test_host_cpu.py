@@ -1,0 +1,189 @@
+"""CPU-side tests: checkpoint layout, constructor behaviour, C-ABI surface.  No kernels run here."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import golden, golden_shapes
+from oracle.cases import CASES
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def build_G(cfg):
+    from model.generator import Generator
+    return Generator(list(cfg["ratios"]), list(cfg["channels"]), 0, cfg["nspk"], cfg["cond_dim"], cfg["content_dim"],
+                     3, 0, "conv", norm_layer=(None, None, None), weight_norm=("weight_norm",) * 3,
+                     bot_cond="target", enc_cond=None, dec_cond="target", output_content_emb=True)
+
+
+def build_D(cfg, kind="cmb"):
+    from model.discriminator import CollaborativeMultibandDiscriminator, MultiscaleDiscriminator
+    cls = CollaborativeMultibandDiscriminator if kind == "cmb" else MultiscaleDiscriminator
+    return cls(cfg["num_disc"], cfg["nspk"], cfg["d_layers"], cfg["d_base"], 4, 4, 128, "target")
+
+
+@pytest.mark.parametrize("name", ["g_tiny", "g_full"])
+def test_generator_state_dict_matches_reference(name):
+    g = golden(name)
+    G = build_G(CASES[name])
+    sd = G.state_dict()
+    assert list(sd.keys()) == [str(k) for k in g["keys"]]          # same keys, same order
+    ref = golden_shapes(g)
+    for k, v in sd.items():
+        assert tuple(v.shape) == tuple(ref[k]), k
+    if name == "g_full":
+        assert len(sd) == 743
+        assert sum(p.numel() for p in G.parameters()) == 14630558
+
+
+@pytest.mark.parametrize("name,kind", [("d_tiny", "cmb"), ("msd_tiny", "msd"), ("d_full", "cmb")])
+def test_discriminator_state_dict_matches_reference(name, kind):
+    g = golden(name)
+    D = build_D(CASES["d_full" if name == "d_full" else "d_tiny"], kind)
+    sd = D.state_dict()
+    assert list(sd.keys()) == [str(k) for k in g["keys"]]
+    ref = golden_shapes(g)
+    for k, v in sd.items():
+        assert tuple(v.shape) == tuple(ref[k]), k
+    if name == "d_full":
+        assert len(sd) == 60
+        assert sum(p.numel() for p in D.parameters()) == 17836764
+    # non-persistent buffers are not in the checkpoint (model/discriminator.py:92)
+    assert not any("down_filter" in k for k in sd)
+
+
+def test_cin_state_dict():
+    from model.conditional_instance_norm import ConditionalInstanceNorm
+    from model.generator import CINResnetBlock
+    g = golden("cin")
+    assert list(ConditionalInstanceNorm(12, 7).state_dict().keys()) == [str(k) for k in g["cin_keys"]]
+    assert list(CINResnetBlock(12, 7, dilation=3, kernel_size=7).state_dict().keys()) == [str(k) for k in g["blk_keys"]]
+
+
+def test_strict_round_trip_and_no_caller_mutation():
+    cfg = CASES["g_tiny"]
+    chans = list(cfg["channels"])
+    ratios = list(cfg["ratios"])
+    G1 = build_G(cfg)
+    assert chans == list(cfg["channels"]) and ratios == list(cfg["ratios"])
+    G2 = build_G(cfg)
+    G2.load_state_dict(G1.state_dict(), strict=True)
+    for (k1, v1), (k2, v2) in zip(G1.state_dict().items(), G2.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2)
+    # weight_g starts at ||v|| (torch.nn.utils.weight_norm), ConvTranspose norms over in-channels
+    sd = G1.state_dict()
+    v, gg = sd["decoder.decoder.6.weight_v"], sd["decoder.decoder.6.weight_g"]
+    assert gg.shape == (v.shape[0], 1, 1)
+    assert torch.allclose(gg.flatten(), v.reshape(v.shape[0], -1).norm(dim=1))
+    # parameters are leaf nn.Parameters visible to an optimiser
+    assert all(p.is_leaf and p.requires_grad for p in G1.parameters())
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/model"), reason="reference checkout not present")
+def test_default_init_equals_reference_init():
+    """torch.manual_seed(s) + constructor gives the reference's initial weights (same RNG consumption)."""
+    code = r"""
+import sys, torch, warnings
+warnings.filterwarnings('ignore')
+sys.path.insert(0, sys.argv[1])
+from model.generator import Generator
+from model.discriminator import CollaborativeMultibandDiscriminator
+torch.manual_seed(7)
+G = Generator([4,4,2,2],[32,16,16,8,8],0,6,16,16,3,0,'conv',norm_layer=(None,None,None),weight_norm=('weight_norm',)*3,
+              bot_cond='target',enc_cond=None,dec_cond='target',output_content_emb=True)
+D = CollaborativeMultibandDiscriminator(3,6,3,4,4,4,128,'target')
+sd = {('G.'+k): v for k, v in G.state_dict().items()}
+sd.update({('D.'+k): v for k, v in D.state_dict().items()})
+torch.save(sd, sys.argv[2])
+"""
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        outs = []
+        for path in ("/root/reference", os.path.join(REPO, "td-vc-gan_b200")):
+            out = os.path.join(td, f"sd{len(outs)}.pt")
+            env = dict(os.environ, PYTHONPATH="")
+            subprocess.run([sys.executable, "-c", code, path, out], check=True, env=env, cwd=td)
+            outs.append(torch.load(out))
+    a, b = outs
+    assert list(a.keys()) == list(b.keys())
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(REPO, "include", "tdvc_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(tdvc_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_c_abi_exports_every_declared_symbol():
+    from tdvc import _lib
+    lib = _lib.load()        # raises if the .so was not built
+    syms = _declared_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/tdvc_b200.h but not exported"
+        assert s in _lib.SIGNATURES, f"{s} has no ctypes signature"
+    assert set(_lib.SIGNATURES) == set(syms)
+    assert lib.tdvc_version() >= 100
+    assert ctypes.sizeof(_lib.ConvGeom) == 14 * 4
+
+
+def test_ops_refuse_cpu_tensors():
+    """No CPU fallback: the product path fails loudly off-GPU."""
+    from tdvc import ops
+    x = torch.zeros(1, 2, 16)
+    w = torch.zeros(2, 2, 3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.conv1d(x, w)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.leaky_relu(x)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(REPO, "td-vc-gan_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(root, f)).read()
+                assert "oracle" not in src.replace("# oracle", ""), os.path.join(root, f)
+
+
+def test_util_helpers():
+    import util
+    from util.dsp import kaiser_filter
+    f = kaiser_filter(129, 0.5, 10)
+    assert f.shape == (129,) and abs(f.sum().item() - 1) < 1e-6 and torch.allclose(f, f.flip(0), atol=1e-7)
+    f2 = util.kaiser_filter(32, 0.5)
+    assert f2.shape == (1, 1, 33)
+    x = torch.arange(12.).view(2, 6)
+    r = util.roll_batches(x, torch.tensor([1, 2]), 1)
+    assert torch.equal(r[0], torch.roll(x[0], 1)) and torch.equal(r[1], torch.roll(x[1], 2))
+    with pytest.raises(Exception):
+        kaiser_filter(128, 0.5)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/util"), reason="reference checkout not present")
+def test_filters_equal_reference():
+    code = r"""
+import sys, torch
+sys.path.insert(0, sys.argv[1])
+import util
+from util.dsp import kaiser_filter
+torch.save([util.kaiser_filter(16*r, 1/r) for r in (2, 8, 10)] + [kaiser_filter(129, 0.5, 10)], sys.argv[2])
+"""
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        res = []
+        for path in ("/root/reference", os.path.join(REPO, "td-vc-gan_b200")):
+            out = os.path.join(td, f"f{len(res)}.pt")
+            subprocess.run([sys.executable, "-c", code, path, out], check=True, env=dict(os.environ, PYTHONPATH=""), cwd=td)
+            res.append(torch.load(out))
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
