@@ -43,6 +43,8 @@ typedef struct tdvc_conv_geom {
 
 const char* tdvc_last_error(void);
 int tdvc_version(void);
+/* kernels launched by this library in this process so far (bench.py reports the per-step delta) */
+int64_t tdvc_launch_count(void);
 /* 1 if the current device is sm_100 (tcgen05/TMEM/TMA paths usable), 0 otherwise, <0 on error */
 int tdvc_device_is_sm100(void);
 

@@ -26,7 +26,13 @@ void set_error(const char* fmt, ...);
     }                                                                               \
   } while (0)
 
-#define TDVC_LAUNCH_CHECK() TDVC_CUDA(cudaGetLastError())
+// every kernel launch in the library is followed by this macro: it also feeds tdvc_launch_count()
+extern unsigned long long g_launches;
+#define TDVC_LAUNCH_CHECK()            \
+  do {                                 \
+    ++tdvc::g_launches;                \
+    TDVC_CUDA(cudaGetLastError());     \
+  } while (0)
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

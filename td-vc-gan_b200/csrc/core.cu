@@ -5,6 +5,7 @@
 
 namespace tdvc {
 static thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -28,6 +29,7 @@ int num_sms() {
 
 extern "C" const char* tdvc_last_error(void) { return tdvc::g_err; }
 extern "C" int tdvc_version(void) { return 100; }
+extern "C" int64_t tdvc_launch_count(void) { return (int64_t)tdvc::g_launches; }
 extern "C" int tdvc_device_is_sm100(void) {
   int dev = 0, major = 0;
   TDVC_CUDA(cudaGetDevice(&dev));

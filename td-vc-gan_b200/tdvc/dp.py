@@ -1,0 +1,70 @@
+"""Batch-sharded data parallelism: one process per GPU, full G and D replicas, gradient mean over ranks.
+
+The reference is single-device; every op in the hot path is per-sample (InstanceNorm is
+per (b, c), there is no BatchNorm, losses are means), so averaging gradients over ranks that each hold B
+samples is numerically the large-batch step.  torch.distributed (NCCL over NVLink / NVSwitch) is the
+plumbing; gradients travel as one flat fp32 bucket per network so a step costs two all-reduces
+(71 MB for D, 59 MB for G) instead of ~800 small ones."""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+class GradAverager:
+    """grad_hook for tdvc.train_step.TrainStep: flattens the gradients of one network into a persistent
+    bucket, all-reduces it (AVG on NCCL, SUM then scale elsewhere) and scatters the result back."""
+
+    def __init__(self, group: Optional[dist.ProcessGroup] = None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._buckets = {}
+
+    def __call__(self, name: str, params: List[torch.nn.Parameter]):
+        if self.world == 1:
+            return
+        grads = [p.grad for p in params if p.grad is not None]
+        if not grads:
+            return
+        n = sum(g.numel() for g in grads)
+        flat = self._buckets.get(name)
+        if flat is None or flat.numel() != n or flat.device != grads[0].device:
+            flat = torch.empty(n, device=grads[0].device, dtype=grads[0].dtype)
+            self._buckets[name] = flat
+        views, off = [], 0
+        for g in grads:
+            views.append(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+        torch._foreach_copy_(views, grads)
+        if flat.is_cuda and dist.get_backend(self.group) == "nccl":
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            flat.div_(self.world)
+        torch._foreach_copy_(grads, views)
+
+
+def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None):
+    """Make every rank start from rank `src`'s weights (replicas are built with the same seed, this is a guard)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src, group=group)
+
+
+def shard_batch(batch: dict, rank: int, world: int) -> dict:
+    """Split a global batch along dim 0 into `world` equal shards and return shard `rank`."""
+    out = {}
+    for k, v in batch.items():
+        if torch.is_tensor(v):
+            if v.shape[0] % world:
+                raise ValueError(f"batch dimension {v.shape[0]} of {k} is not divisible by world size {world}")
+            n = v.shape[0] // world
+            out[k] = v[rank * n:(rank + 1) * n]
+        elif isinstance(v, (list, tuple)):
+            out[k] = [shard_batch({"x": t}, rank, world)["x"] if torch.is_tensor(t) else t for t in v]
+        else:
+            out[k] = v
+    return out

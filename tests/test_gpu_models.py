@@ -126,7 +126,10 @@ def test_cin_vs_golden():
     assert relerr(xb.grad, g["dxb"]) < 2e-5
     for k, p in blk.named_parameters():
         if "gb/" + k in g.files:
-            assert relerr(p.grad, g["gb/" + k]) < 5e-5, k
+            if np.abs(g["gb/" + k]).max() < 1e-10:      # analytically zero (bias feeding an instance norm)
+                assert p.grad.abs().max().item() < 1e-4, k
+            else:
+                assert relerr(p.grad, g["gb/" + k]) < 5e-5, k
 
 
 def test_losses_vs_golden():
