@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""Headline benchmark: one G+D training step of td-vc-gan (config/conv_enc-stage1.yaml as shipped:
+B=16/GPU, T=8960 samples @16 kHz, 100 speakers) on N B200s, in audio-seconds per second.
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (CUDA path)
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU cores
+
+Contract: W untimed warm-up steps, then exactly K steps between barrier + synchronize, CUDA events on the
+launching stream, max over ranks; rank 0 prints ONE JSON line.  See DESIGN.md "Measurement".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(REPO, "td-vc-gan_b200")
+for p in (PKG, REPO):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "train_audio_sec_per_sec"
+UNIT = "audio-s/s"
+SR = 16000
+# model + train sections of config/conv_enc-stage1.yaml (the reference's file does not travel to the GPU box)
+MODEL = dict(ratios=(10, 8, 2, 2), channels=(256, 128, 64, 32, 16), content_dim=128, cond_dim=128, nspk=100,
+             num_disc=3, d_layers=4, d_base=16)
+TRAIN = dict(no_conv=False, lambda_rec=0, lambda_idt=5, lambda_feat=2, lambda_spec=5, lambda_wave=0, lambda_latcls=0,
+             lambda_cont_emb=10, lambda_corrupted=1, lambda_converted=0, lambda_f0=0, jitter_amp=0,
+             batch_size=16, max_segment=8960, lr=1e-4, betas=(0.8, 0.99))
+# algorithmic FLOPs of one step at B=16 (fwd 1557 + bwd 2138 GF; analytic 2*MAC per conv)
+STEP_GFLOP_B16 = 3695.0
+
+
+def peaks():
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], tc_burst=p["bf16_tflops"], tc_sustained=p["bf16_tflops_sustained"], src="measured")
+    except Exception:
+        return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_models(device):
+    import torch
+    from model.discriminator import CollaborativeMultibandDiscriminator
+    from model.generator import Generator
+    torch.manual_seed(0)      # identical replicas on every rank
+    m = MODEL
+    G = Generator(list(m["ratios"]), list(m["channels"]), 0, m["nspk"], m["cond_dim"], m["content_dim"], 3, 0, "conv",
+                  norm_layer=(None, None, None), weight_norm=("weight_norm",) * 3, bot_cond="target", enc_cond=None,
+                  dec_cond="target", output_content_emb=True)
+    D = CollaborativeMultibandDiscriminator(m["num_disc"], m["nspk"], m["d_layers"], m["d_base"], 4, 4, 128, "target")
+    return G.to(device), D.to(device)
+
+
+def synth_batch(B, T, nspk, seed):
+    """SURVEY.md 8(d) synthetic batch (host tensors, fp32)."""
+    import math
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    t = torch.arange(T, dtype=torch.float32) / SR
+    f0 = torch.rand(B, 1, 1, generator=g) * 200 + 100
+    x = 0.05 * torch.sin(2 * math.pi * f0 * t) + 0.01 * torch.randn(B, 1, T, generator=g)
+    xc = x + 0.005 * torch.randn(B, 1, T, generator=g)
+    lab_s = torch.randint(0, nspk, (B,), generator=g)
+    perm = torch.randperm(B, generator=g)
+    lab_t, f0_t = lab_s[perm], f0[perm]
+
+    def excite(f):
+        ph = torch.rand(1, generator=g) * 2 * math.pi
+        return 0.1 * torch.sin(2 * math.pi * f * t + ph) + 0.003 * torch.randn(B, 1, T, generator=g)
+    return {"signal_real": x, "signal_corrupted": xc, "label_src": lab_s, "label_tgt": lab_t,
+            "c_f0_conv": excite(f0_t), "c_f0_src": excite(f0)}
+
+
+def to_device(batch, device, pinned=None):
+    import torch
+    out = {}
+    nbytes = 0
+    for k, v in batch.items():
+        src = pinned[k] if pinned is not None else v
+        out[k] = src.to(device, non_blocking=True)
+        nbytes += v.numel() * v.element_size()
+    return out, nbytes
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from tdvc import _lib, ops
+    from tdvc.dp import GradAverager, broadcast_parameters
+    from tdvc.optim import FusedAdamW
+    from tdvc.train_step import TrainStep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    ops.set_precision(args.precision)
+    B, T, nspk = TRAIN["batch_size"], TRAIN["max_segment"], MODEL["nspk"]
+    G, D = build_models(dev)
+    broadcast_parameters(G); broadcast_parameters(D)
+    oG = FusedAdamW(G.parameters(), TRAIN["lr"], TRAIN["betas"])
+    oD = FusedAdamW(D.parameters(), TRAIN["lr"], TRAIN["betas"])
+    hook = GradAverager() if world > 1 else None
+    ts = TrainStep(G, D, TRAIN, oG, oD, nspk, grad_hook=hook)
+    host = synth_batch(B, T, nspk, seed=1234 + rank)
+    pinned = {k: v.pin_memory() for k, v in host.items()}
+    resident, _ = to_device(host, dev)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    last = {}
+
+    def step_resident():
+        last.update(ts.step(resident))
+
+    h2d = [0]
+    d2h = [0]
+
+    def step_e2e():
+        batch, nb = to_device(host, dev, pinned)
+        out = ts.step(batch)
+        losses = torch.stack([out["d_loss"].reshape(()), out["g_loss"].reshape(())]).cpu()   # D2H read of the result
+        h2d[0], d2h[0] = nb, losses.numel() * losses.element_size()
+        last["host_losses"] = losses
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local) if rank == 0 else None
+    n0 = lib.tdvc_launch_count()
+    if sampler:
+        sampler.start()
+    ms = timed(step_resident, args.steps)
+    clocks = sampler.stop() if sampler else None
+    launches = (lib.tdvc_launch_count() - n0) / max(1, args.steps)
+    # end-to-end arm: host buffers in, loss scalars out, copies inside the timed region
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    audio_s = world * B * T / SR
+    value = audio_s * args.steps / (ms / 1e3)
+    e2e = audio_s * args.steps / (ms_e2e / 1e3)
+
+    out = None
+    if rank == 0:
+        pk = peaks()
+        roof = dominant_kernel_roofline(dev, B, T, pk, args)
+        out = {
+            "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp32" if args.precision == "fp32" else "bf16",
+            "data": "synthetic",
+            "config": {"workload": "conv_enc-stage1.yaml as shipped: one D step + one G step (G fwd x3, D fwd x5, "
+                                   "encoder(corrupted), LSGAN + feature-matching + mel + contrastive losses, both "
+                                   "backward passes, AdamW on G and D)",
+                       "batch_per_gpu": B, "segment_samples": T, "sample_rate": SR, "speakers": nspk,
+                       "lambda_f0": "0 (torchcrepe unavailable offline, SURVEY 8c)", "precision": args.precision,
+                       "l2": "no explicit flush: one step streams >6 GB of activations, far larger than the 126 MB L2",
+                       "parallelism": f"dp{world}", "step_gflop_algorithmic": STEP_GFLOP_B16 * world},
+            "clocks": clocks,
+            "e2e": {"value": round(e2e, 3), "unit": UNIT, "h2d_bytes_per_step": h2d[0], "d2h_bytes_per_step": d2h[0],
+                    "ms_per_step": round(ms_e2e / args.steps, 3)},
+            "gpu_launches": int(round(launches)),
+            "step_tflops_algorithmic": round(STEP_GFLOP_B16 * world / (ms / args.steps), 3),
+            "roofline": roof,
+            "losses": {k: float(v) for k, v in last.items() if k in ("d_loss", "g_loss")},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(steps=1, warmup=0, budget_s=30.0)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if out is not None:
+        print(json.dumps(out), flush=True)
+
+
+def dominant_kernel_roofline(dev, B, T, pk, args):
+    """The kernel that carries most of the step's FLOPs: FiLM `cond_var.0` (136->136, k=3, 'same') at the full-rate
+    decoder stage (143 of 465 GF of a G forward).  Timed alone with CUDA events on the current
+    stream, inputs 78 MB + outputs 78 MB per launch and 9 distinct weight sets cycled (L2 mostly cold for
+    activations).  achieved = algorithmic FLOPs / launch time vs the measured dense bf16 tensor-core peak."""
+    import torch
+    from tdvc import ops
+    C = MODEL["cond_dim"] + 8
+    n_sets = 9
+    xs = [torch.randn(B, C, T, device=dev) for _ in range(3)]
+    ws = [torch.randn(C, C, 3, device=dev) * 0.05 for _ in range(n_sets)]
+    bs = [torch.zeros(C, device=dev) for _ in range(n_sets)]
+    with torch.no_grad():
+        for i in range(3):
+            ops.conv1d(xs[i % 3], ws[i], bs[i], padding=1)
+        torch.cuda.synchronize()
+        reps = 18
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(reps):
+            ops.conv1d(xs[i % 3], ws[i % n_sets], bs[i % n_sets], padding=1)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    flops = 2.0 * B * T * C * C * 3
+    ach = flops / (ms * 1e-3) / 1e12
+    peak = pk["tc_burst"]
+    kname = "conv_fwd_k<8,32> (fp32 CUDA cores)" if args.precision == "fp32" else "conv_tc_fwd_k (tcgen05 bf16)"
+    return {"bound": "tensor", "achieved": round(ach, 3), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 5),
+            "traffic": None, "kernel": kname, "shape": f"B={B} Cin={C} Cout={C} K=3 T={T}",
+            "flops_per_launch": flops, "ms_per_launch": round(ms, 4),
+            "peak_source": f"MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone), {pk['src']}"}
+
+
+def cpu_baseline(steps, warmup, budget_s=30.0):
+    """The reference algorithm (CPU oracle port, fp32, all host threads) on a bounded sample of the same
+    workload: full G+D steps (forward, both backward passes, torch AdamW updates) at the largest batch
+    B in {16, 8, 4, 2} whose estimated cost fits `budget_s` seconds per step; audio-s/s = B*0.56 s / step time."""
+    import torch
+    from oracle.step import make_models, oracle_step, step_batch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    hp = dict(TRAIN)
+    hp["faithful_waste"] = True      # the reference back-propagates the sub-scale heads into G in the D step
+
+    def setup(Bs):
+        cfg = dict(MODEL, B=Bs, T=TRAIN["max_segment"], seed=6)
+        sdG, sdD = make_models(cfg, torch.float32)
+        for v in list(sdG.values()) + list(sdD.values()):
+            v.requires_grad_(True)
+        oG = torch.optim.AdamW(list(sdG.values()), TRAIN["lr"], TRAIN["betas"])
+        oD = torch.optim.AdamW(list(sdD.values()), TRAIN["lr"], TRAIN["betas"])
+        return cfg, sdG, sdD, oG, oD, step_batch(cfg, hp, torch.float32)
+
+    def one(state):
+        cfg, sdG, sdD, oG, oD, batch = state
+        out = oracle_step(cfg, hp, torch.float32, sdG, sdD, batch)
+        for k, v in sdD.items():
+            v.grad = out["D_grad"][k]
+        for k, v in sdG.items():
+            v.grad = out["G_grad"][k]
+        oD.step(); oG.step()
+
+    st = setup(2)
+    t0 = time.perf_counter()
+    one(st)                                   # probe (also warms the thread pool / allocator)
+    t2 = time.perf_counter() - t0
+    Bs = 2
+    for cand in (16, 8, 4):
+        if t2 * cand / 2 * 0.7 <= budget_s:   # larger batches amortise better than linearly
+            Bs = cand
+            break
+    if Bs != 2:
+        st = setup(Bs)
+    for _ in range(warmup):
+        one(st)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one(st)
+    dt = (time.perf_counter() - t0) / steps
+    v = Bs * TRAIN["max_segment"] / SR / dt
+    return {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{steps} full G+D step(s) (fwd, both bwd, AdamW) at B={Bs} of 16, T=8960, fp32, "
+                      f"{warmup} warm-up after a B=2 probe; {dt:.2f} s/step",
+            "s_per_step": round(dt, 3), "batch": Bs}
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU implementation of the path (oracle port; the reference itself is
+    pure Python/PyTorch and cannot travel to the GPU box) on the host cores, same metric and config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    warm = min(args.warmup, 1)
+    cb = cpu_baseline(steps=steps, warmup=warm, budget_s=max(4.0, 150.0 / (steps + warm)))
+    sample_B = cb["batch"]
+    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": 0,
+           "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": round(cb["s_per_step"] * 1e3, 1),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+           "config": {"workload": f"conv_enc-stage1.yaml as shipped, one G+D step; bounded sample B={sample_B} of 16 per step",
+                      "batch_per_gpu": sample_B, "segment_samples": TRAIN["max_segment"], "sample_rate": SR,
+                      "speakers": MODEL["nspk"]},
+           "cpu_baseline": cb,
+           "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("TDVC_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

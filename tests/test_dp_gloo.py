@@ -28,7 +28,10 @@ def _worker(rank, world, port, q):
     avg("net", params)   # idempotent on already-averaged grads, reuses the bucket
     full = {"x": torch.arange(8.).view(4, 2), "lab": torch.arange(4), "neg": [torch.arange(12).view(4, 3)], "k": 3}
     sh = shard_batch(full, rank, world)
-    q.put((rank, w0, [p.grad.clone() for p in params], sh))
+    # plain lists: tensors would travel by fd-sharing and this process exits before the parent reads them
+    sh_l = {k: (v.tolist() if torch.is_tensor(v) else [t.tolist() for t in v] if isinstance(v, list) else v)
+            for k, v in sh.items()}
+    q.put((rank, w0.tolist(), [p.grad.tolist() for p in params], sh_l))
     dist.destroy_process_group()
 
 
@@ -44,10 +47,12 @@ def test_grad_average_and_shard_two_ranks():
         p.join(timeout=60)
         assert p.exitcode == 0
     (_, w_a, g_a, s_a), (_, w_b, g_b, s_b) = res
-    assert torch.equal(w_a, w_b)                               # broadcast made the replicas identical
+    assert w_a == w_b                                          # broadcast made the replicas identical
     for i, (ga, gb) in enumerate(zip(g_a, g_b)):
-        assert torch.allclose(ga, torch.full_like(ga, 1.5 * (i + 1)))   # mean of (1, 2) * (i+1)
-        assert torch.equal(ga, gb)
-    assert torch.equal(s_a["x"], torch.arange(8.).view(4, 2)[:2]) and torch.equal(s_b["x"], torch.arange(8.).view(4, 2)[2:])
-    assert torch.equal(s_b["lab"], torch.tensor([2, 3])) and s_a["k"] == 3
-    assert torch.equal(s_b["neg"][0], torch.arange(12).view(4, 3)[2:])
+        ga_t = torch.tensor(ga)
+        assert torch.allclose(ga_t, torch.full_like(ga_t, 1.5 * (i + 1)))   # mean of (1, 2) * (i+1)
+        assert ga == gb
+    full = torch.arange(8.).view(4, 2)
+    assert s_a["x"] == full[:2].tolist() and s_b["x"] == full[2:].tolist()
+    assert s_b["lab"] == [2, 3] and s_a["k"] == 3
+    assert s_b["neg"][0] == torch.arange(12).view(4, 3)[2:].tolist()
