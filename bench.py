@@ -211,6 +211,12 @@ def run_ours(args):
     ms = timed(step_resident, args.steps)
     clocks = sampler.stop() if sampler else None
     launches = (lib.tdvc_launch_count() - n0) / max(1, args.steps)
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_mode": True, "ms_per_step": ms / args.steps, "gpu_launches": launches}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     # end-to-end arm: host buffers in, loss scalars out, copies inside the timed region
     step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
@@ -369,11 +375,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("TDVC_PRECISION", "fp32"), choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="profiling aid (ncu): honour --warmup as given, skip the e2e / roofline / cpu legs; "
+                         "numbers printed in this mode are not bench values")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
     else:
-        if args.warmup < 3:
+        if args.warmup < 3 and not args.profile:
             args.warmup = 3
         run_ours(args)
 

@@ -66,6 +66,13 @@ int tdvc_conv1d_fwd(const tdvc_conv_geom* g, const float* x, const float* w, con
 int64_t tdvc_conv1d_bwd_data_ws(const tdvc_conv_geom* g);
 int tdvc_conv1d_bwd_data(const tdvc_conv_geom* g, const float* dy, const float* w, const float* x,
                          float* dx, float* ws, void* stream);
+/* dbias[c] = sum_{b,t} dy[b,c,t] (OVERWRITTEN) */
+int tdvc_bias_grad(const float* dy, float* dbias, int B, int C, int T, void* stream);
+/* second half of bwd_data on its own (used after a tensor-core dgrad): folds the `halo` reflected samples of
+ * stage[rows, T+2*halo] back and applies the input-LeakyReLU mask from x:  dx[rows, T]. x may be NULL when
+ * in_slope == 1. */
+int tdvc_pad_act_bwd(const float* stage, const float* x, float* dx, int64_t rows, int T, int halo, int reflect,
+                     float in_slope, void* stream);
 /* dw (same layout as w, OVERWRITTEN) and dbias (may be NULL) */
 int tdvc_conv1d_bwd_weight(const tdvc_conv_geom* g, const float* dy, const float* x, float* dw,
                            float* dbias, void* stream);
@@ -159,6 +166,11 @@ int tdvc_conv1d_tc_fwd(const void* xp, const void* wp, const float* bias, const 
                        const float* residual, float* y, int B, int Cinp, int Tp, int Cout, int Coutp,
                        int Tout, int K, int dilation, int t_off, int out_act, float out_slope,
                        void* stream);
+
+/* weight gradient of the same conv on tcgen05: dw[Cout,Cin,K] (OVERWRITTEN, fp32) from the packed bf16 operands
+ * dyp[B,Tout,Cdp] and xp[B,Tp,Cp]; xp row read for output step t and tap k is t + k*dilation + t_off. */
+int tdvc_conv1d_tc_wgrad(const void* dyp, const void* xp, float* dw, int B, int Cdp, int Tout, int Cp, int Tp,
+                         int Cout, int Cin, int K, int dilation, int t_off, void* stream);
 
 #ifdef __cplusplus
 }

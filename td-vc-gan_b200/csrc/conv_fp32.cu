@@ -569,6 +569,23 @@ extern "C" int tdvc_conv1d_bwd_data(const tdvc_conv_geom* g, const float* dy, co
   return TDVC_OK;
 }
 
+extern "C" int tdvc_bias_grad(const float* dy, float* dbias, int B, int C, int T, void* stream) {
+  TDVC_CHECK_ARG(dy && dbias && B >= 0 && C > 0 && T > 0);
+  return launch_channel_sum(dy, dbias, B, C, T, (cudaStream_t)stream);
+}
+
+extern "C" int tdvc_pad_act_bwd(const float* stage, const float* x, float* dx, int64_t rows, int T, int halo, int reflect,
+                                float in_slope, void* stream) {
+  TDVC_CHECK_ARG(stage && dx && rows >= 0 && T > 0 && halo >= 0);
+  TDVC_CHECK_ARG(in_slope == 1.0f || x != nullptr);
+  long long n = (long long)rows * T;
+  if (n == 0) return TDVC_OK;
+  int blocks = (int)std::min<long long>((n + 255) / 256, 8LL * num_sms());
+  pad_act_bwd_k<<<blocks, 256, 0, (cudaStream_t)stream>>>(stage, x, dx, rows, T, halo, reflect, in_slope);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
 extern "C" int tdvc_conv1d_bwd_weight(const tdvc_conv_geom* g, const float* dy, const float* x, float* dw,
                                       float* dbias, void* stream) {
   int rc = check_geom(g, false);

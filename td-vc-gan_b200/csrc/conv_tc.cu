@@ -1,9 +1,567 @@
-// placeholder until the tcgen05 path lands (replaced below in this round)
+// bf16 tensor-core path for the dense stride-1 convolutions (FiLM cond_var.0 / cond_var.2, conv.1,
+// posconv, the discriminator's 1024x1024 k5 layer and their data gradients): implicit GEMM on
+// tcgen05.mma with the accumulator in TMEM and both operands brought in by TMA.
+//
+//   D[t, co] = sum_{tap} sum_{ci} A_tap[t, ci] * W_tap[co, ci]
+//     A_tap = rows (t0 + tap*dilation + t_off ...) of the channels-last bf16 activation copy xp[B, Tp, Cp]
+//             -> one 3-D TMA box {64 ch, 128 t, 1 b} per (tap, 64-channel chunk), K-major, SWIZZLE_128B;
+//                the conv's zero padding is TMA out-of-bounds fill, reflect padding is materialised by
+//                the pack kernel in the halo rows.
+//     W_tap = wp[tap, co, ci] bf16 -> box {64 ch, BN co, 1 tap}, K-major, SWIZZLE_128B.
+//   M = 128 time steps (TMEM lanes), N = BN <= 256 output channels (TMEM columns), K = 16 per MMA.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..5 = epilogue (tcgen05.ld -> bias / FiLM / residual / activation -> coalesced NCW fp32 stores:
+// a TMEM lane is a time step, so for a fixed channel a warp writes 32 consecutive floats).
+// One output tile per CTA; several CTAs per SM overlap one tile's epilogue with another's main loop.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <algorithm>
 #include "common.cuh"
-extern "C" int tdvc_pack_cl_bf16(const float*, void*, int, int, int, int, int, int, float, void*) {
-  tdvc::set_error("tcgen05 path not built"); return TDVC_ERR_UNSUPPORTED; }
-extern "C" int tdvc_pack_weight_bf16(const float*, void*, int, int, int, int, int, int, void*) {
-  tdvc::set_error("tcgen05 path not built"); return TDVC_ERR_UNSUPPORTED; }
-extern "C" int tdvc_conv1d_tc_fwd(const void*, const void*, const float*, const float*, const float*, float*, int, int,
-                                  int, int, int, int, int, int, int, int, float, void*) {
-  tdvc::set_error("tcgen05 path not built"); return TDVC_ERR_UNSUPPORTED; }
+
+namespace tdvc {
+
+// ------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 128-byte rows,
+// 8-row (1024 B) swizzle atoms stacked along M/N -> SBO = 1024 B; LBO unused (1); version 1; layout 2.
+__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+struct TcP {
+  int B, Tout, Cout, K, dil, t_off;
+  int nchunk, last_nk16, BN, stages, tmem_cols;
+  int out_act;
+  float out_slope;
+  const float* bias;
+  const float* gb;
+  const float* res;
+  float* y;
+};
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
+constexpr int TC_THREADS = 192;
+
+__global__ void __launch_bounds__(TC_THREADS) conv_tc_fwd_k(const __grid_constant__ CUtensorMap map_a,
+                                                            const __grid_constant__ CUtensorMap map_b, TcP p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B atoms need 1024-B alignment
+  const int b_bytes = p.BN * TC_BK * 2;
+  const int stage_bytes = TC_A_BYTES + b_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tmem_full_bar = empty_bar + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t0 = blockIdx.x * TC_BM;
+  const int n0 = blockIdx.y * p.BN;
+  const int b = blockIdx.z;
+  const int iters = p.K * p.nchunk;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------- TMA producer
+    if (lane == 0) {
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        const int tap = it / p.nchunk, ck = it - tap * p.nchunk;
+        uint8_t* sa = smem + (size_t)s * stage_bytes;
+        mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+        tma_load_3d(sa, &map_a, &full_bar[s], ck * TC_BK, t0 + tap * p.dil + p.t_off, b);
+        tma_load_3d(sa + TC_A_BYTES, &map_b, &full_bar[s], ck * TC_BK, n0, tap);
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer (one elected thread)
+    // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7, 10), both K-major, N>>3 at 17, M>>4 at 24
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % p.stages;
+      const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const int ck = it % p.nchunk;
+        const int nk = (ck == p.nchunk - 1) ? p.last_nk16 : (TC_BK / 16);
+        const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint64_t da = make_sw128_kmajor_desc(a_addr);
+        const uint64_t db = make_sw128_kmajor_desc(a_addr + TC_A_BYTES);
+        for (int k = 0; k < nk; ++k) {
+          // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+          umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);                 // frees the smem stage when these MMAs retire
+        if (it == iters - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---------------- epilogue: warps 2..5, TMEM lane quadrant = warp % 4
+    const int q = warp & 3;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int t = t0 + q * 32 + lane;
+    const bool t_ok = t < p.Tout;
+    const long long row_base = (long long)b * p.Cout * p.Tout + t;
+    for (int c0 = 0; c0 < p.BN; c0 += 16) {
+      if (n0 + c0 >= p.Cout) break;     // warp-uniform
+      float v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      if (t_ok) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int co = n0 + c0 + j;
+          if (co < p.Cout) {
+            float o = v[j];
+            if (p.bias) o += __ldg(p.bias + co);
+            const long long idx = row_base + (long long)co * p.Tout;
+            if (p.gb) {
+              const long long gi = (long long)b * 2 * p.Cout * p.Tout + (long long)co * p.Tout + t;
+              o = fmaf(o, 1.f + __ldg(p.gb + gi), __ldg(p.gb + gi + (long long)p.Cout * p.Tout));
+            }
+            if (p.res) o += __ldg(p.res + idx);
+            if (p.out_act == TDVC_ACT_LRELU) o = o > 0.f ? o : o * p.out_slope;
+            else if (p.out_act == TDVC_ACT_TANH) o = tanhf(o);
+            p.y[idx] = o;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------ wgrad
+// dW[co, ci, tap] = sum_{b,t} dy[b,t,co] * xa[b, t + tap*dil + t_off, ci]   as a GEMM with M = co, N = ci, K = time.
+// Both operands are the channels-last bf16 copies that forward / dgrad already use, read as MN-major
+// (channel-contiguous) SWIZZLE_128B tiles: box {64 ch, 64 t}.  One TMEM accumulator per tap (KT taps x NT
+// columns <= 512).  A CTA walks a strided subset of the (batch, 64-step time chunk) units, accumulating in
+// TMEM, then adds its partial sums into dW with fp32 atomics.
+struct WgTcP {
+  int B, Tout, Cout, Cin, K, dil, t_off;
+  int KT, NT, nb, ntap_groups, n_ntiles, stages, tmem_cols, nchunk_t, units, splits;
+  float* dw;
+};
+
+constexpr int WG_BOX_BYTES = 64 * 64 * 2;   // 64 time rows x 64 channels bf16
+
+// MN-major SWIZZLE_128B descriptor: 64-channel (128 B) rows, 8-row K atoms 1024 B apart (SBO), 64-channel MN
+// atoms `lbo` bytes apart (LBO).
+__device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(TC_THREADS) conv_tc_wgrad_k(const __grid_constant__ CUtensorMap map_a,
+                                                              const __grid_constant__ CUtensorMap map_b, WgTcP p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int a_bytes = 2 * WG_BOX_BYTES;
+  const int b_tap_bytes = p.nb * WG_BOX_BYTES;
+  const int stage_bytes = a_bytes + p.KT * b_tap_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tmem_full_bar = empty_bar + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // blockIdx.y enumerates (m tile, tap group, n tile)
+  int yy = blockIdx.y;
+  const int nt_i = yy % p.n_ntiles; yy /= p.n_ntiles;
+  const int tg = yy % p.ntap_groups;
+  const int mt = yy / p.ntap_groups;
+  const int co0 = mt * 128, n0 = nt_i * p.NT, tap0 = tg * p.KT;
+  const int ntaps = min(p.KT, p.K - tap0);
+  const int split = blockIdx.x;
+  const int my_units = (p.units - split + p.splits - 1) / p.splits;   // units split, split+splits, ...
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (my_units > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        for (int it = 0; it < my_units; ++it) {
+          const int u = split + it * p.splits;
+          const int b = u / p.nchunk_t, tc = (u - b * p.nchunk_t) * 64;
+          const int s = it % p.stages;
+          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* sa = smem + (size_t)s * stage_bytes;
+          mbar_expect_tx(&full_bar[s], (uint32_t)(a_bytes + ntaps * b_tap_bytes));
+          tma_load_3d(sa, &map_a, &full_bar[s], co0, tc, b);
+          tma_load_3d(sa + WG_BOX_BYTES, &map_a, &full_bar[s], co0 + 64, tc, b);
+          for (int tp = 0; tp < ntaps; ++tp)
+            for (int j = 0; j < p.nb; ++j)
+              tma_load_3d(sa + a_bytes + tp * b_tap_bytes + j * WG_BOX_BYTES, &map_b, &full_bar[s], n0 + 64 * j,
+                          tc + (tap0 + tp) * p.dil + p.t_off, b);
+        }
+      }
+    } else if (warp == 1) {
+      // D=f32, A=B=bf16, both MN-major (bits 15, 16), N = NT, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      for (int it = 0; it < my_units; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+          for (int tp = 0; tp < ntaps; ++tp) {
+            const uint32_t b_addr = a_addr + a_bytes + tp * b_tap_bytes;
+            for (int k = 0; k < 4; ++k) {      // 64 time rows per stage = 4 x K16; 16 rows = 2048 B
+              const uint64_t da = make_sw128_mnmajor_desc(a_addr + k * 2048, WG_BOX_BYTES);
+              const uint64_t db = make_sw128_mnmajor_desc(b_addr + k * 2048, WG_BOX_BYTES);
+              umma_bf16(tmem_base + (uint32_t)(tp * p.NT), da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[s]);
+          if (it == my_units - 1) umma_commit(tmem_full_bar);
+        }
+        __syncwarp();
+      }
+    } else {
+      const int q = warp & 3;
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+      const int co = co0 + q * 32 + lane;
+      const bool co_ok = co < p.Cout;
+      for (int tp = 0; tp < ntaps; ++tp) {
+        for (int c0 = 0; c0 < p.NT; c0 += 16) {
+          if (n0 + c0 >= p.Cin) break;
+          float v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tp * p.NT + c0), v);
+          if (co_ok) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int ci = n0 + c0 + j;
+              if (ci < p.Cin) atomicAdd(p.dw + ((long long)co * p.Cin + ci) * p.K + tap0 + tp, v[j]);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------ pack kernels
+// x[B,C,T] fp32 NCW -> xp[B,Tp,Cp] bf16 channels-last, LeakyReLU(in_slope), halo rows reflect- or zero-filled.
+__global__ void pack_cl_bf16_k(const float* __restrict__ x, __nv_bfloat16* __restrict__ xp, int C, int T, int Cp, int Tp,
+                               int halo, int pad_mode, float slope) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int tp0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  // read: threadIdx.x along time (coalesced), threadIdx.y strides channels
+  for (int cy = threadIdx.y; cy < 32; cy += blockDim.y) {
+    int c = c0 + cy, tp = tp0 + threadIdx.x;
+    float v = 0.f;
+    if (c < C && tp < Tp) {
+      int u = tp - halo;
+      bool ok = true;
+      if (u < 0) { if (pad_mode == TDVC_PAD_REFLECT) { u = -u; ok = u < T; } else ok = false; }
+      else if (u >= T) { if (pad_mode == TDVC_PAD_REFLECT) { u = 2 * (T - 1) - u; ok = u >= 0; } else ok = false; }
+      if (ok) {
+        v = __ldg(x + ((long long)b * C + c) * T + u);
+        v = v > 0.f ? v : v * slope;
+      }
+    }
+    tile[cy][threadIdx.x] = v;
+  }
+  __syncthreads();
+  // write: threadIdx.x along channels (contiguous in xp)
+  for (int ty = threadIdx.y; ty < 32; ty += blockDim.y) {
+    int tp = tp0 + ty, c = c0 + threadIdx.x;
+    if (tp < Tp && c < Cp) xp[((long long)b * Tp + tp) * Cp + c] = __float2bfloat16(tile[threadIdx.x][ty]);
+  }
+}
+
+__global__ void pack_weight_bf16_k(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int Cout, int Cin, int K,
+                                   int Rp, int Qp, int transpose_flip) {
+  // output [K][Rp][Qp]; plain: R = co, Q = ci; transpose_flip: R = ci, Q = co, tap reversed
+  long long n = (long long)K * Rp * Qp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int qq = (int)(i % Qp);
+    long long r2 = i / Qp;
+    int rr = (int)(r2 % Rp);
+    int k = (int)(r2 / Rp);
+    int co = transpose_flip ? qq : rr, ci = transpose_flip ? rr : qq;
+    int ks = transpose_flip ? K - 1 - k : k;
+    float v = (co < Cout && ci < Cin) ? w[((long long)co * Cin + ci) * K + ks] : 0.f;
+    wp[i] = __float2bfloat16(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)sym;
+  }
+  return fn;
+}
+
+static int make_map_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0, uint32_t box1) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return TDVC_ERR_CUDA; }
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
+  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return TDVC_ERR_CUDA; }
+  return TDVC_OK;
+}
+
+}  // namespace tdvc
+using namespace tdvc;
+
+extern "C" int tdvc_pack_cl_bf16(const float* x, void* xp, int B, int C, int T, int Cp, int halo, int pad_mode,
+                                 float in_slope, void* stream) {
+  TDVC_CHECK_ARG(B >= 0 && C > 0 && T > 0 && Cp >= C && Cp % 8 == 0 && halo >= 0 && x && xp);
+  if (pad_mode == TDVC_PAD_REFLECT) TDVC_CHECK_ARG(halo < T);
+  if (B == 0) return TDVC_OK;
+  int Tp = T + 2 * halo;
+  dim3 grid(cdiv(Tp, 32), cdiv(Cp, 32), B);
+  TDVC_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535);
+  pack_cl_bf16_k<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)xp, C, T, Cp, Tp, halo, pad_mode, in_slope);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_pack_weight_bf16(const float* w, void* wp, int Cout, int Cin, int K, int Coutp, int Cinp,
+                                     int transpose_flip, void* stream) {
+  TDVC_CHECK_ARG(Cout > 0 && Cin > 0 && K > 0 && Coutp >= Cout && Cinp >= Cin && w && wp);
+  int Rp = transpose_flip ? Cinp : Coutp, Qp = transpose_flip ? Coutp : Cinp;
+  long long n = (long long)K * Rp * Qp;
+  int blocks = (int)std::min<long long>((n + 255) / 256, 8LL * num_sms());
+  pack_weight_bf16_k<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)wp, Cout, Cin, K, Rp, Qp, transpose_flip);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_conv1d_tc_fwd(const void* xp, const void* wp, const float* bias, const float* gb, const float* residual,
+                                  float* y, int B, int Cinp, int Tp, int Cout, int Coutp, int Tout, int K, int dilation,
+                                  int t_off, int out_act, float out_slope, void* stream) {
+  TDVC_CHECK_ARG(xp && wp && y && B >= 0 && Cinp > 0 && Cinp % 8 == 0 && Tp > 0 && Cout > 0 && Coutp >= Cout &&
+                 Coutp % 16 == 0 && Tout > 0 && K > 0 && dilation > 0);
+  TDVC_CHECK_ARG(((uintptr_t)xp % 16 == 0) && ((uintptr_t)wp % 16 == 0));
+  if (B == 0) return TDVC_OK;
+  TcP p{};
+  p.B = B; p.Tout = Tout; p.Cout = Cout; p.K = K; p.dil = dilation; p.t_off = t_off;
+  p.nchunk = cdiv(Cinp, TC_BK);
+  int rem = Cinp - (p.nchunk - 1) * TC_BK;
+  p.last_nk16 = cdiv(rem, 16);
+  // N tile: whole (padded) Cout when it fits one MMA, else 256/128-wide tiles
+  p.BN = Coutp <= 256 ? Coutp : (Coutp % 256 == 0 ? 256 : 128);
+  TDVC_CHECK_ARG(Coutp % p.BN == 0);
+  int cols = 32;
+  while (cols < p.BN) cols <<= 1;
+  p.tmem_cols = cols;
+  const int stage_bytes = TC_A_BYTES + p.BN * TC_BK * 2;
+  int stages = (int)((196 * 1024) / stage_bytes);
+  stages = std::min(stages, 6);
+  stages = std::min(stages, K * p.nchunk);
+  if (p.BN <= 128) stages = std::min(stages, 4);   // keep 2+ CTAs per SM resident for small-N layers
+  stages = std::max(stages, 1);
+  p.stages = stages;
+  p.out_act = out_act; p.out_slope = out_slope; p.bias = bias; p.gb = gb; p.res = residual; p.y = y;
+  size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    TDVC_CUDA(cudaFuncSetAttribute(conv_tc_fwd_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  CUtensorMap map_a, map_b;
+  int rc = make_map_3d(&map_a, xp, (uint64_t)Cinp, (uint64_t)Tp, (uint64_t)B, TC_BK, TC_BM);
+  if (rc) return rc;
+  rc = make_map_3d(&map_b, wp, (uint64_t)Cinp, (uint64_t)Coutp, (uint64_t)K, TC_BK, (uint32_t)p.BN);
+  if (rc) return rc;
+  dim3 grid(cdiv(Tout, TC_BM), Coutp / p.BN, B);
+  TDVC_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535);
+  conv_tc_fwd_k<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+// dw[Cout,Cin,K] (OVERWRITTEN) from the packed operands: dyp[B,Tout,Cdp] and xp[B,Tp,Cp] (both bf16 channels-last;
+// xp row = t + tap*dilation + t_off).
+extern "C" int tdvc_conv1d_tc_wgrad(const void* dyp, const void* xp, float* dw, int B, int Cdp, int Tout, int Cp, int Tp,
+                                    int Cout, int Cin, int K, int dilation, int t_off, void* stream) {
+  TDVC_CHECK_ARG(dyp && xp && dw && B >= 0 && Cdp % 8 == 0 && Cp % 8 == 0 && Cdp >= Cout && Cp >= Cin && Tout > 0 && Tp > 0 &&
+                 K > 0 && dilation > 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  TDVC_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * Cin * K, st));
+  if (B == 0) return TDVC_OK;
+  WgTcP p{};
+  p.B = B; p.Tout = Tout; p.Cout = Cout; p.Cin = Cin; p.K = K; p.dil = dilation; p.t_off = t_off; p.dw = dw;
+  const int N16 = ((Cin + 15) / 16) * 16;
+  int NT = 16;
+  // choose the widest N tile such that all taps (or as many as possible) fit the 512 TMEM columns
+  int best_nt = 16, best_cost = 1 << 30;
+  for (int cand = std::min(N16, 256); cand >= 16; cand -= 16) {
+    int kt = std::min(K, 512 / cand);
+    if (kt < 1) continue;
+    int groups = cdiv(K, kt), ntiles = cdiv(N16, cand);
+    int cost = groups * ntiles;            // A-tile re-reads: fewer (tap group x n tile) pairs is better
+    if (cost < best_cost) { best_cost = cost; best_nt = cand; }
+  }
+  NT = best_nt;
+  p.NT = NT;
+  p.KT = std::min(K, 512 / NT);
+  p.ntap_groups = cdiv(K, p.KT);
+  p.n_ntiles = cdiv(N16, NT);
+  p.nb = cdiv(NT, 64);
+  int cols = 32;
+  while (cols < p.KT * NT) cols <<= 1;
+  p.tmem_cols = cols;
+  const int stage_bytes = 2 * WG_BOX_BYTES + p.KT * p.nb * WG_BOX_BYTES;
+  p.nchunk_t = cdiv(Tout, 64);
+  p.units = B * p.nchunk_t;
+  int stages = std::min(4, (int)((200 * 1024) / stage_bytes));
+  TDVC_CHECK_ARG(stages >= 1);
+  stages = std::min(stages, std::max(1, p.units));
+  p.stages = stages;
+  const int m_tiles = cdiv(Cout, 128);
+  const int gy = m_tiles * p.ntap_groups * p.n_ntiles;
+  int splits = std::max(1, (2 * num_sms()) / gy);
+  splits = std::min(splits, p.units);
+  p.splits = splits;
+  size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    TDVC_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  CUtensorMap map_a, map_b;
+  int rc = make_map_3d(&map_a, dyp, (uint64_t)Cdp, (uint64_t)Tout, (uint64_t)B, 64, 64);
+  if (rc) return rc;
+  rc = make_map_3d(&map_b, xp, (uint64_t)Cp, (uint64_t)Tp, (uint64_t)B, 64, 64);
+  if (rc) return rc;
+  TDVC_CHECK_ARG(gy <= 65535);
+  conv_tc_wgrad_k<<<dim3(splits, gy), TC_THREADS, smem, st>>>(map_a, map_b, p);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}

@@ -39,6 +39,8 @@ SIGNATURES = {
     "tdvc_conv1d_fwd": (_I, [_G, _P, _P, _P, _P, _P, _P]),
     "tdvc_conv1d_bwd_data_ws": (_L, [_G]),
     "tdvc_conv1d_bwd_data": (_I, [_G, _P, _P, _P, _P, _P, _P]),
+    "tdvc_bias_grad": (_I, [_P, _P, _I, _I, _I, _P]),
+    "tdvc_pad_act_bwd": (_I, [_P, _P, _P, _L, _I, _I, _I, _F, _P]),
     "tdvc_conv1d_bwd_weight": (_I, [_G, _P, _P, _P, _P, _P]),
     "tdvc_conv_transpose1d_fwd": (_I, [_G, _P, _P, _P, _P, _P]),
     "tdvc_conv_transpose1d_bwd_data": (_I, [_G, _P, _P, _P, _P]),
@@ -66,6 +68,7 @@ SIGNATURES = {
     "tdvc_adamw_multi": (_I, [_P, _P, _P, _P, _P, _I, _L, _F, _F, _F, _F, _F, _I, _F, _P]),
     "tdvc_pack_cl_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _P]),
     "tdvc_pack_weight_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "tdvc_conv1d_tc_wgrad": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "tdvc_conv1d_tc_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P]),
 }
 

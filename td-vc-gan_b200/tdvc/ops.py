@@ -152,6 +152,10 @@ def conv1d(x, weight, bias=None, *, stride=1, padding=0, dilation=1, groups=1, r
            in_slope=1.0, out_act=None, out_slope=0.2, residual=None):
     """act(conv1d(leaky_relu(pad(x), in_slope), weight) + bias + residual); nn.Conv1d semantics
     (padding_mode 'zeros' or 'reflect')."""
+    if _PRECISION == "bf16" and tc_eligible(x.shape[1], weight.shape[0], int(stride), int(groups)):
+        return _Conv1dTC.apply(x, weight, bias, residual, int(padding), int(dilation),
+                               PAD_REFLECT if (reflect and padding > 0) else PAD_ZEROS, float(in_slope), _ACT[out_act],
+                               float(out_slope))
     return _Conv1d.apply(x, weight, bias, residual, int(stride), int(padding), int(dilation), int(groups),
                          PAD_REFLECT if (reflect and padding > 0) else PAD_ZEROS, float(in_slope), _ACT[out_act],
                          float(out_slope))
@@ -537,3 +541,150 @@ class _L1MeanSum(torch.autograd.Function):
 def l1_mean_sum(sig: Sequence[torch.Tensor], ref: Sequence[torch.Tensor]) -> torch.Tensor:
     sig, ref = list(sig), [r.detach() for r in ref]
     return _L1MeanSum.apply(len(sig), *sig, *ref)
+
+
+# ----------------------------------------------------------------------------- bf16 tensor-core conv path
+
+def _ceil(a, m):
+    return (a + m - 1) // m * m
+
+
+def _cp(c):
+    """channel padding of a packed (channels-last bf16) operand: the TMA box is 64 channels wide."""
+    return 64 if c <= 64 else _ceil(c, 8)
+
+
+def tc_eligible(Cin, Cout, stride, groups) -> bool:
+    """Dense stride-1 convs with enough channels to fill an MMA tile go to tcgen05 in bf16 mode."""
+    if stride != 1 or groups != 1 or Cin < 16 or Cout < 16:
+        return False
+    coutp = _ceil(Cout, 16)
+    return coutp <= 256 or coutp % 128 == 0
+
+
+class _PackCache:
+    """The FiLM conditioning tensor feeds 9 cond_var.0 convs per stage: pack it once.  Entries hold a reference
+    to the source tensor, so its storage cannot be recycled while the entry is alive."""
+
+    def __init__(self, size=6):
+        self.size, self.items = size, []
+
+    def get(self, key, src):
+        for k, s, v in self.items:
+            if k == key and s.data_ptr() == src.data_ptr() and s._version == src._version:
+                return v
+        return None
+
+    def put(self, key, src, val):
+        self.items.insert(0, (key, src, val))
+        del self.items[self.size:]
+
+    def clear(self):
+        self.items = []
+
+
+_pack_cache = _PackCache()
+
+
+def _pack_act(x, Cp, halo, pad_mode, slope, cache=True):
+    B, Cc, T = x.shape
+    key = (tuple(x.shape), Cp, halo, pad_mode, slope)
+    if cache:
+        hit = _pack_cache.get(key, x)
+        if hit is not None:
+            return hit
+    xp = torch.empty(B, T + 2 * halo, Cp, device=x.device, dtype=torch.bfloat16)
+    _lib.check(_lib.load().tdvc_pack_cl_bf16(_p(x), _p(xp), B, Cc, T, Cp, halo, pad_mode, slope, _st()), "pack_cl_bf16")
+    if cache:
+        _pack_cache.put(key, x, xp)
+    return xp
+
+
+def _pack_w(w, rows_p, cols_p, transpose_flip):
+    Cout, Cin, K = w.shape
+    wp = torch.empty(K, rows_p, cols_p, device=w.device, dtype=torch.bfloat16)
+    coutp, cinp = (cols_p, rows_p) if transpose_flip else (rows_p, cols_p)
+    _lib.check(_lib.load().tdvc_pack_weight_bf16(_p(w), _p(wp), Cout, Cin, K, coutp, cinp, int(transpose_flip), _st()),
+               "pack_weight_bf16")
+    return wp
+
+
+class _Conv1dTC(torch.autograd.Function):
+    """Same contract as _Conv1d for stride 1 / groups 1, computed with bf16 operands and fp32 accumulation on the
+    tcgen05 implicit-GEMM kernels (forward, data gradient and weight gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, residual, pad, dilation, pad_mode, in_slope, out_act, out_slope):
+        _req(x, w, bias, residual)
+        x, w, bias, residual = _c(x), _c(w), _c(bias), _c(residual)
+        B, Cin, Tin = x.shape
+        Cout, cin_w, K = w.shape
+        if cin_w != Cin:
+            raise RuntimeError(f"conv1d: weight {tuple(w.shape)} does not match input {tuple(x.shape)}")
+        Tout = Tin + 2 * pad - dilation * (K - 1)
+        if Tout <= 0:
+            raise RuntimeError(f"conv1d: input length {Tin} too short for kernel {K} (dilation {dilation})")
+        if pad_mode == PAD_REFLECT and pad >= Tin:
+            raise RuntimeError(f"conv1d: reflect padding {pad} must be smaller than the input length {Tin}")
+        lib = _lib.load()
+        Cp, Coutp = _cp(Cin), _ceil(Cout, 16)
+        halo = pad if pad_mode == PAD_REFLECT else 0          # zero padding is TMA out-of-bounds fill
+        xp = _pack_act(x, Cp, halo, pad_mode, in_slope)
+        wp = _pack_w(w, Coutp, Cp, False)
+        y = torch.empty(B, Cout, Tout, device=x.device, dtype=torch.float32)
+        if residual is not None and residual.shape != y.shape:
+            raise RuntimeError("conv1d: residual shape mismatch")
+        _lib.check(lib.tdvc_conv1d_tc_fwd(_p(xp), _p(wp), _p(bias), None, _p(residual), _p(y), B, Cp, Tin + 2 * halo, Cout,
+                                          Coutp, Tout, K, dilation, halo - pad, out_act, out_slope, _st()), "conv1d_tc_fwd")
+        ctx.cfg = (pad, dilation, pad_mode, in_slope, out_act, out_slope)
+        ctx.has_bias, ctx.has_res = bias is not None, residual is not None
+        ctx.save_for_backward(x, w, y if out_act != ACT_NONE else None, xp)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y, xp = ctx.saved_tensors
+        pad, dilation, pad_mode, in_slope, out_act, out_slope = ctx.cfg
+        lib = _lib.load()
+        dy = _c(dy)
+        B, Cin, Tin = x.shape
+        Cout, _, K = w.shape
+        Tout = dy.shape[2]
+        if out_act != ACT_NONE:
+            dz = torch.empty_like(dy)
+            _lib.check(lib.tdvc_act_bwd_from_output(_p(dy), _p(y), _p(dz), dy.numel(), out_act, out_slope, _st()), "act_bwd")
+            dy = dz
+        dx = dw = db = None
+        need_b = ctx.has_bias and ctx.needs_input_grad[2]
+        Cdp = _cp(Cout)
+        dyp = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            dyp = _pack_act(dy, Cdp, 0, PAD_ZEROS, 1.0, cache=False)     # shared by dgrad and wgrad
+        if ctx.needs_input_grad[0]:
+            # dgrad = the same implicit GEMM on dy with channel-swapped, tap-flipped weights
+            ph = pad if pad_mode == PAD_REFLECT else 0            # reflect halo kept in the staging buffer
+            Lout = Tin + 2 * ph
+            zpad = (K - 1) * dilation - (pad - ph)                # zero padding of dy in the equivalent forward conv
+            Cinp16 = _ceil(Cin, 16)
+            wtp = _pack_w(w, Cinp16, Cdp, True)
+            need_stage = ph > 0 or in_slope != 1.0
+            stage = torch.empty(B, Cin, Lout, device=x.device, dtype=torch.float32)
+            _lib.check(lib.tdvc_conv1d_tc_fwd(_p(dyp), _p(wtp), None, None, None, _p(stage), B, Cdp, Tout, Cin, Cinp16, Lout,
+                                              K, dilation, -zpad, ACT_NONE, 1.0, _st()), "conv1d_tc_dgrad")
+            if need_stage:
+                dx = torch.empty_like(x)
+                _lib.check(lib.tdvc_pad_act_bwd(_p(stage), _p(x), _p(dx), B * Cin, Tin, ph, int(pad_mode == PAD_REFLECT),
+                                                in_slope, _st()), "pad_act_bwd")
+            else:
+                dx = stage
+        if ctx.needs_input_grad[1]:
+            # wgrad on tcgen05 from the two packed operands (time is the GEMM K dimension)
+            halo = pad if pad_mode == PAD_REFLECT else 0
+            dw = torch.empty_like(w)
+            _lib.check(lib.tdvc_conv1d_tc_wgrad(_p(dyp), _p(xp), _p(dw), B, Cdp, Tout, xp.shape[2], xp.shape[1], Cout, Cin,
+                                                K, dilation, halo - pad, _st()), "conv1d_tc_wgrad")
+        if need_b:
+            db = torch.empty(Cout, device=x.device, dtype=torch.float32)
+            _lib.check(lib.tdvc_bias_grad(_p(dy), _p(db), B, Cout, Tout, _st()), "bias_grad")
+        dres = dy if (ctx.has_res and ctx.needs_input_grad[3]) else None
+        return dx, dw, db, dres, None, None, None, None, None, None
