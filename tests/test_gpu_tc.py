@@ -59,7 +59,6 @@ def test_conv1d_tc(case):
         y0 = y0 + r
     yref = F.leaky_relu(y0, 0.2) if out_act == "lrelu" else y0
     proj = rnd(*yref.shape, seed=5)
-    (yref * proj).sum().backward()
     xd, wd, bd = dev(x), dev(w), dev(b)
     rd = dev(r) if has_r else None
     assert ops.tc_eligible(Cin, Cout, 1, 1)
@@ -68,6 +67,14 @@ def test_conv1d_tc(case):
     torch.cuda.synchronize()
     e = relerr(y, yref)
     assert e < 1e-2, e
+    if out_act == "lrelu":
+        # the gradient of a LeakyReLU output depends on the SIGN of the pre-activation: where |y0| is below the bf16
+        # rounding error the device and the fp64 reference legitimately pick different branches, so the reference
+        # gradient is taken with the device's branch choice (that is the function the device differentiates)
+        mask = torch.where(y.detach().double().cpu() > 0, 1.0, 0.2)
+        (y0 * mask * proj).sum().backward()
+    else:
+        (yref * proj).sum().backward()
     (y * proj.float().cuda()).sum().backward()
     torch.cuda.synchronize()
     assert relerr(xd.grad, x.grad) < 1e-2
@@ -96,3 +103,83 @@ def test_pack_kernels_exact():
     ref = torch.zeros(3, 32, 64, dtype=torch.bfloat16)
     ref[:, :20, :24] = w.flip(2).permute(2, 1, 0).to(torch.bfloat16)
     assert torch.equal(wt, ref)
+
+
+def _build_and_load(cfg):
+    from oracle.params import make_state_dict
+    from test_host_cpu import build_D, build_G
+    G, D = build_G(cfg), build_D(cfg)
+    for m, seed in ((G, cfg["seed"]), (D, cfg["seed"] + 100)):
+        shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        m.load_state_dict(make_state_dict(shapes, seed=seed, dtype=torch.float32), strict=True)
+        m.cuda()
+    return G, D
+
+
+def test_generator_and_discriminator_bf16_vs_golden():
+    """Full-size Generator / Discriminator forward in bf16 mode against the fp64 reference vectors: 2e-2."""
+    import numpy as np
+    from helpers import golden
+    from oracle.cases import CASES, rand_like
+    from oracle.params import make_batch, make_state_dict
+    from test_host_cpu import build_D, build_G
+    g = golden("g_full")
+    cfg = CASES["g_full"]
+    G = build_G(cfg)
+    shapes = {k: tuple(v.shape) for k, v in G.state_dict().items()}
+    G.load_state_dict(make_state_dict(shapes, seed=cfg["seed"], dtype=torch.float32), strict=True)
+    G.cuda()
+    b = make_batch(cfg["B"], cfg["T"], cfg["nspk"], seed=cfg["seed"] + 1, frames_div=320)
+    c_tgt = F.one_hot(b["label_tgt"], cfg["nspk"]).float().cuda()
+    y, subs = G(b["signal_real"].float().cuda(), c_tgt, c_var=b["c_f0_conv"].float().cuda(), out_subsample=True)
+    assert relerr(y, g["y"]) < 2e-2
+    assert relerr(G.content_embedding, g["emb"]) < 2e-2
+    for i, s in enumerate(subs):
+        assert relerr(s, g[f"subs/{i}"]) < 2e-2
+    gd = golden("d_full")
+    cfg = CASES["d_full"]
+    D = build_D(cfg)
+    shapes = {k: tuple(v.shape) for k, v in D.state_dict().items()}
+    D.load_state_dict(make_state_dict(shapes, seed=cfg["seed"], dtype=torch.float32), strict=True)
+    D.cuda()
+    b = make_batch(cfg["B"], cfg["T"], cfg["nspk"], seed=cfg["seed"] + 1, frames_div=320)
+    subs = [rand_like(torch.empty(cfg["B"], 1, cfg["T"] // 4), 31).float().cuda() * 0.1,
+            rand_like(torch.empty(cfg["B"], 1, cfg["T"] // 2), 32).float().cuda() * 0.1]
+    outs, feats = D(b["signal_real"].float().cuda(), b["label_src"].cuda(), subs)
+    for i, o in enumerate(outs):
+        assert relerr(o, gd[f"outs/{i}"]) < 2e-2
+
+
+def test_train_step_bf16_losses_vs_golden():
+    """One full-size G+D step in bf16 mode: every loss scalar within 2e-2 of the fp64 reference, gradient norms
+    of 90 % of the tensors within 5e-2 (sign flips at LeakyReLU / L1 kinks dominate the rest)."""
+    import numpy as np
+    from helpers import golden, stats
+    from oracle.cases import CASES, HP_STAGE1
+    from oracle.params import make_batch
+    from tdvc.train_step import TrainStep
+    g = golden("step_full_s1")
+    cfg, hp = CASES["step_full"], HP_STAGE1
+    G, D = _build_and_load(cfg)
+    b = make_batch(cfg["B"], cfg["T"], cfg["nspk"], seed=cfg["seed"] + 1, frames_div=320, permute=True)
+    bd = {k: ((v.float() if v.is_floating_point() else v).cuda() if torch.is_tensor(v) else v) for k, v in b.items()}
+    ts = TrainStep(G, D, hp, None, None, cfg["nspk"])
+    out = ts.d_step(bd)
+    dgrad = {k: p.grad.clone() for k, p in D.named_parameters()}
+    D.zero_grad(); G.zero_grad()
+    out.update(ts.g_step(bd, raw_draws=b["neg_idx"]))
+    for k in ("d_loss_real", "d_loss_fake", "g_adv", "g_idt", "g_cont", "g_loss"):
+        ref = float(np.asarray(g[k]).reshape(-1)[0])
+        assert abs(float(out[k]) - ref) <= 2e-2 * max(1.0, abs(ref)), (k, float(out[k]), ref)
+    assert relerr(out["fake"], g["fake"]) < 2e-2
+    errs = []
+    for k, gr in dgrad.items():
+        ref = g[f"D_grad/{k}"]
+        if ref[2] > 1e-12:
+            errs.append(abs(stats(gr)[2] - ref[2]) / ref[2])
+    for k, p in G.named_parameters():
+        ref = g[f"G_grad/{k}"]
+        if ref[2] > 1e-12 and p.grad is not None:
+            errs.append(abs(stats(p.grad)[2] - ref[2]) / ref[2])
+    errs = np.sort(np.array(errs))
+    assert errs[int(0.9 * len(errs))] < 5e-2, errs[int(0.9 * len(errs))]
