@@ -17,6 +17,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace tdvc {
@@ -106,15 +107,20 @@ struct TcP {
   const float* gb;
   const float* res;
   float* y;
+  int debug;   // TDVC_TC_DEBUG (development only): 1 = no epilogue stores, 2 = no main loop, 4 = no tmem loads
 };
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 192;       // wgrad kernel: TMA warp, MMA warp, 4 epilogue warps
+constexpr int TC_FWD_THREADS = 320;   // forward kernel: TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quadrant)
 
-__global__ void __launch_bounds__(TC_THREADS) conv_tc_fwd_k(const __grid_constant__ CUtensorMap map_a,
-                                                            const __grid_constant__ CUtensorMap map_b, TcP p) {
+// ACT: tdvc_act of the epilogue; EPI: 0 = bias only, 1 = + residual, 2 = FiLM (+ residual when p.res)
+template <int ACT, int EPI>
+__global__ void __launch_bounds__(TC_FWD_THREADS) conv_tc_fwd_k(const __grid_constant__ CUtensorMap map_a,
+                                                                const __grid_constant__ CUtensorMap map_b, TcP p) {
+  __shared__ float bias_s[256];      // bias of this N tile (zeros when absent)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B atoms need 1024-B alignment
   const int b_bytes = p.BN * TC_BK * 2;
@@ -127,8 +133,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_fwd_k(const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t0 = blockIdx.x * TC_BM;
   const int n0 = blockIdx.y * p.BN;
+  for (int i = threadIdx.x; i < p.BN; i += TC_FWD_THREADS)
+    bias_s[i] = (p.bias && n0 + i < p.Cout) ? __ldg(p.bias + n0 + i) : 0.f;
   const int b = blockIdx.z;
-  const int iters = p.K * p.nchunk;
+  const int iters = (p.debug & 2) ? 0 : p.K * p.nchunk;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -140,11 +148,11 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_fwd_k(const __grid_constan
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  if (warp == 1 && !(p.debug & 16)) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = (p.debug & 16) ? 0u : *tmem_slot;
 
   if (warp == 0) {
     // ---------------- TMA producer
@@ -184,42 +192,55 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_fwd_k(const __grid_constan
       }
       __syncwarp();
     }
-  } else {
-    // ---------------- epilogue: warps 2..5, TMEM lane quadrant = warp % 4
+  } else if (!(p.debug & 8)) {
+    // ---------------- epilogue: warps 2..9; TMEM lane quadrant = warp % 4, the two warps of a quadrant split
+    // the 16-column chunks (even / odd).  A lane is a time step: for a fixed channel the warp stores 32
+    // consecutive floats (one 128-byte line).
     const int q = warp & 3;
-    mbar_wait(tmem_full_bar, 0);
+    const int half = (warp - 2) >> 2;
+    if (iters > 0) mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const int t = t0 + q * 32 + lane;
     const bool t_ok = t < p.Tout;
-    const long long row_base = (long long)b * p.Cout * p.Tout + t;
-    for (int c0 = 0; c0 < p.BN; c0 += 16) {
-      if (n0 + c0 >= p.Cout) break;     // warp-uniform
+    const long long ct = p.Tout;
+    const int nvalid = min(p.BN, p.Cout - n0);          // columns of this tile that are real channels
+    for (int c0 = half * 16; c0 < nvalid; c0 += 32) {
       float v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      if (p.debug & 4) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = (float)(c0 + j);
+      } else {
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      }
       if (t_ok) {
+        const long long base = ((long long)b * p.Cout + n0 + c0) * ct + t;
+        float* yp = p.y + base;
+        const float* rp = p.res + base;                                   // only dereferenced when EPI asks for it
+        const float* gp = p.gb + ((long long)b * 2 * p.Cout + n0 + c0) * ct + t;
+        const long long beta_off = (long long)p.Cout * ct;
+        const int nj = min(16, nvalid - c0);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const int co = n0 + c0 + j;
-          if (co < p.Cout) {
-            float o = v[j];
-            if (p.bias) o += __ldg(p.bias + co);
-            const long long idx = row_base + (long long)co * p.Tout;
-            if (p.gb) {
-              const long long gi = (long long)b * 2 * p.Cout * p.Tout + (long long)co * p.Tout + t;
-              o = fmaf(o, 1.f + __ldg(p.gb + gi), __ldg(p.gb + gi + (long long)p.Cout * p.Tout));
+          if (j < nj) {
+            float o = v[j] + bias_s[c0 + j];
+            if (EPI == 2) {
+              o = fmaf(o, 1.f + __ldg(gp), __ldg(gp + beta_off));
+              if (p.res) o += __ldg(rp);
+            } else if (EPI == 1) {
+              o += __ldg(rp);
             }
-            if (p.res) o += __ldg(p.res + idx);
-            if (p.out_act == TDVC_ACT_LRELU) o = o > 0.f ? o : o * p.out_slope;
-            else if (p.out_act == TDVC_ACT_TANH) o = tanhf(o);
-            p.y[idx] = o;
+            if (ACT == TDVC_ACT_LRELU) o = o > 0.f ? o : o * p.out_slope;
+            else if (ACT == TDVC_ACT_TANH) o = tanhf(o);
+            if (!(p.debug & 1)) *yp = o;
           }
+          yp += ct; rp += ct; gp += ct;
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if (warp == 1 && !(p.debug & 16)) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------ wgrad
@@ -481,18 +502,32 @@ extern "C" int tdvc_conv1d_tc_fwd(const void* xp, const void* wp, const float* b
   while (cols < p.BN) cols <<= 1;
   p.tmem_cols = cols;
   const int stage_bytes = TC_A_BYTES + p.BN * TC_BK * 2;
-  int stages = (int)((196 * 1024) / stage_bytes);
+  // ~100 KB of pipeline per CTA so that two CTAs share an SM: one tile's epilogue overlaps the other's main loop
+  int stages = (int)((100 * 1024) / stage_bytes);
+  stages = std::max(stages, 2);
   stages = std::min(stages, 6);
   stages = std::min(stages, K * p.nchunk);
-  if (p.BN <= 128) stages = std::min(stages, 4);   // keep 2+ CTAs per SM resident for small-N layers
   stages = std::max(stages, 1);
   p.stages = stages;
   p.out_act = out_act; p.out_slope = out_slope; p.bias = bias; p.gb = gb; p.res = residual; p.y = y;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("TDVC_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.debug = dbg;
+  }
   size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
-  static bool configured = false;
-  if (!configured) {
-    TDVC_CUDA(cudaFuncSetAttribute(conv_tc_fwd_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, TcP);
+  static const KernelFn table[3][3] = {
+      {conv_tc_fwd_k<0, 0>, conv_tc_fwd_k<0, 1>, conv_tc_fwd_k<0, 2>},
+      {conv_tc_fwd_k<1, 0>, conv_tc_fwd_k<1, 1>, conv_tc_fwd_k<1, 2>},
+      {conv_tc_fwd_k<2, 0>, conv_tc_fwd_k<2, 1>, conv_tc_fwd_k<2, 2>}};
+  TDVC_CHECK_ARG(out_act >= 0 && out_act <= 2);
+  const int epi = gb ? 2 : (residual ? 1 : 0);
+  KernelFn kern = table[out_act][epi];
+  static bool configured[3][3] = {};
+  if (!configured[out_act][epi]) {
+    TDVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured[out_act][epi] = true;
   }
   CUtensorMap map_a, map_b;
   int rc = make_map_3d(&map_a, xp, (uint64_t)Cinp, (uint64_t)Tp, (uint64_t)B, TC_BK, TC_BM);
@@ -501,7 +536,7 @@ extern "C" int tdvc_conv1d_tc_fwd(const void* xp, const void* wp, const float* b
   if (rc) return rc;
   dim3 grid(cdiv(Tout, TC_BM), Coutp / p.BN, B);
   TDVC_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535);
-  conv_tc_fwd_k<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
+  kern<<<grid, TC_FWD_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
