@@ -155,7 +155,8 @@ int tdvc_adamw_multi(float* const* params, const float* const* grads, float* con
  *      `halo` samples of reflect/zero padding on each side (Tp = T + 2*halo, Cp = C rounded up to
  *      8, zero filled).  */
 int tdvc_pack_cl_bf16(const float* x, void* xp, int B, int C, int T, int Cp, int halo, int pad_mode,
-                      float in_slope, void* stream);
+                      float in_slope, float* chan_sum /* optional [C]: sum over (b,t) of x, OVERWRITTEN: the bias
+                      gradient falls out of packing dL/dy */, void* stream);
 /* w[Cout,Cin,K] fp32 -> wp[K, Coutp, Cinp] bf16 (zero padded); transpose_flip!=0 produces the
  * dgrad operand wp[K, Cinp, Coutp] with taps reversed. */
 int tdvc_pack_weight_bf16(const float* w, void* wp, int Cout, int Cin, int K, int Coutp, int Cinp,
@@ -168,9 +169,11 @@ int tdvc_conv1d_tc_fwd(const void* xp, const void* wp, const float* bias, const 
                        void* stream);
 
 /* weight gradient of the same conv on tcgen05: dw[Cout,Cin,K] (OVERWRITTEN, fp32) from the packed bf16 operands
- * dyp[B,Tout,Cdp] and xp[B,Tp,Cp]; xp row read for output step t and tap k is t + k*dilation + t_off. */
-int tdvc_conv1d_tc_wgrad(const void* dyp, const void* xp, float* dw, int B, int Cdp, int Tout, int Cp, int Tp,
-                         int Cout, int Cin, int K, int dilation, int t_off, void* stream);
+ * dyp[B,Tout,Cdp] and xp[B,Tp,Cp]; xp row read for output step t and tap k is t + k*dilation + t_off.
+ * ws: workspace of tdvc_conv1d_tc_wgrad_ws(Cout, Cin, K) floats (split-K partial sums, [K][Coutp][Cinp]). */
+int64_t tdvc_conv1d_tc_wgrad_ws(int Cout, int Cin, int K);
+int tdvc_conv1d_tc_wgrad(const void* dyp, const void* xp, float* dw, float* ws, int B, int Cdp, int Tout, int Cp,
+                         int Tp, int Cout, int Cin, int K, int dilation, int t_off, void* stream);
 
 #ifdef __cplusplus
 }

@@ -186,10 +186,15 @@ static int launch_fwd(FwdP p, const float* x, const float* w, const float* bias,
   if (p.B == 0 || p.Tout <= 0) return TDVC_OK;
   const bool small_t = p.Tout <= 48;
   const int ty = small_t ? 32 : 8;
+  const int tt = small_t ? 32 : 128;
   int co_t = 8;
   if (ty * 1 >= p.cout_g) co_t = 1;
   else if (ty * 2 >= p.cout_g) co_t = 2;
   else if (ty * 4 >= p.cout_g) co_t = 4;
+  // short sequences (T/320 stage, discriminator tails) would otherwise launch a handful of CTAs: trade
+  // per-thread register tiling for enough CTAs to cover the 148 SMs
+  auto n_ctas = [&](int c) { return (long long)cdiv(p.Tout, tt) * p.groups * cdiv(p.cout_g, ty * c) * p.B; };
+  while (co_t > 1 && n_ctas(co_t) < num_sms()) co_t >>= 1;
 #define TDVC_FWD_CASE(C, X) return launch_fwd_t<C, X>(p, x, w, bias, res, y, st)
   if (small_t) {
     switch (co_t) { case 1: TDVC_FWD_CASE(1, 8); case 2: TDVC_FWD_CASE(2, 8); case 4: TDVC_FWD_CASE(4, 8); default: TDVC_FWD_CASE(8, 8); }
@@ -335,10 +340,15 @@ static int launch_tr_t(TrP p, const float* in, const float* w, const float* bias
 
 static int launch_tr(TrP p, const float* in, const float* w, const float* bias, float* out, cudaStream_t st) {
   if (p.B == 0 || p.Tout <= 0) return TDVC_OK;
-  if (p.out_g <= 2) return launch_tr_t<1>(p, in, w, bias, out, st);
-  if (p.out_g <= 4) return launch_tr_t<2>(p, in, w, bias, out, st);
-  if (p.out_g <= 8) return launch_tr_t<4>(p, in, w, bias, out, st);
-  return launch_tr_t<8>(p, in, w, bias, out, st);
+  int oc_t = p.out_g <= 2 ? 1 : (p.out_g <= 4 ? 2 : (p.out_g <= 8 ? 4 : 8));
+  auto n_ctas = [&](int c) { return (long long)cdiv(p.Tout, 128) * p.groups * cdiv(p.out_g, 2 * c) * p.B; };
+  while (oc_t > 1 && n_ctas(oc_t) < 2 * num_sms()) oc_t >>= 1;
+  switch (oc_t) {
+    case 1: return launch_tr_t<1>(p, in, w, bias, out, st);
+    case 2: return launch_tr_t<2>(p, in, w, bias, out, st);
+    case 4: return launch_tr_t<4>(p, in, w, bias, out, st);
+    default: return launch_tr_t<8>(p, in, w, bias, out, st);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

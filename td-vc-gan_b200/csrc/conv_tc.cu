@@ -244,15 +244,17 @@ __global__ void __launch_bounds__(TC_FWD_THREADS) conv_tc_fwd_k(const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------ wgrad
-// dW[co, ci, tap] = sum_{b,t} dy[b,t,co] * xa[b, t + tap*dil + t_off, ci]   as a GEMM with M = co, N = ci, K = time.
+// dW[co, ci, tap] = sum_{b,t} xa[b, t + tap*dil + t_off, ci] * dy[b, t, co]  as a GEMM with M = ci, N = co, K = time.
 // Both operands are the channels-last bf16 copies that forward / dgrad already use, read as MN-major
 // (channel-contiguous) SWIZZLE_128B tiles: box {64 ch, 64 t}.  One TMEM accumulator per tap (KT taps x NT
-// columns <= 512).  A CTA walks a strided subset of the (batch, 64-step time chunk) units, accumulating in
-// TMEM, then adds its partial sums into dW with fp32 atomics.
+// columns <= 512).  A CTA walks a strided subset of the (batch, 64-step time chunk) units accumulating in TMEM,
+// then adds its partial tile into ws[tap][co][ci] with fp32 reductions: a TMEM lane is a ci, so each warp-level
+// RED covers 32 consecutive floats (one line).  wgrad_finalize_k transposes ws into the [Cout][Cin][K] layout.
 struct WgTcP {
   int B, Tout, Cout, Cin, K, dil, t_off;
   int KT, NT, nb, ntap_groups, n_ntiles, stages, tmem_cols, nchunk_t, units, splits;
-  float* dw;
+  int Mp, Np;     // padded ci / co extents of the workspace
+  float* ws;
 };
 
 constexpr int WG_BOX_BYTES = 64 * 64 * 2;   // 64 time rows x 64 channels bf16
@@ -269,13 +271,13 @@ __device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr, 
   return d;
 }
 
-__global__ void __launch_bounds__(TC_THREADS) conv_tc_wgrad_k(const __grid_constant__ CUtensorMap map_a,
-                                                              const __grid_constant__ CUtensorMap map_b, WgTcP p) {
+__global__ void __launch_bounds__(TC_THREADS) conv_tc_wgrad_k(const __grid_constant__ CUtensorMap map_x,
+                                                              const __grid_constant__ CUtensorMap map_dy, WgTcP p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const int a_bytes = 2 * WG_BOX_BYTES;
-  const int b_tap_bytes = p.nb * WG_BOX_BYTES;
-  const int stage_bytes = a_bytes + p.KT * b_tap_bytes;
+  const int a_tap_bytes = 2 * WG_BOX_BYTES;           // 128 ci x 64 t
+  const int b_bytes = p.nb * WG_BOX_BYTES;            // NT co x 64 t
+  const int stage_bytes = p.KT * a_tap_bytes + b_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full_bar = empty_bar + p.stages;
@@ -287,14 +289,14 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_wgrad_k(const __grid_const
   const int nt_i = yy % p.n_ntiles; yy /= p.n_ntiles;
   const int tg = yy % p.ntap_groups;
   const int mt = yy / p.ntap_groups;
-  const int co0 = mt * 128, n0 = nt_i * p.NT, tap0 = tg * p.KT;
+  const int ci0 = mt * 128, n0 = nt_i * p.NT, tap0 = tg * p.KT;
   const int ntaps = min(p.KT, p.K - tap0);
   const int split = blockIdx.x;
   const int my_units = (p.units - split + p.splits - 1) / p.splits;   // units split, split+splits, ...
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dy) : "memory");
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -318,13 +320,14 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_wgrad_k(const __grid_const
           const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
           mbar_wait(&empty_bar[s], ph ^ 1u);
           uint8_t* sa = smem + (size_t)s * stage_bytes;
-          mbar_expect_tx(&full_bar[s], (uint32_t)(a_bytes + ntaps * b_tap_bytes));
-          tma_load_3d(sa, &map_a, &full_bar[s], co0, tc, b);
-          tma_load_3d(sa + WG_BOX_BYTES, &map_a, &full_bar[s], co0 + 64, tc, b);
-          for (int tp = 0; tp < ntaps; ++tp)
-            for (int j = 0; j < p.nb; ++j)
-              tma_load_3d(sa + a_bytes + tp * b_tap_bytes + j * WG_BOX_BYTES, &map_b, &full_bar[s], n0 + 64 * j,
-                          tc + (tap0 + tp) * p.dil + p.t_off, b);
+          mbar_expect_tx(&full_bar[s], (uint32_t)(ntaps * a_tap_bytes + b_bytes));
+          for (int tp = 0; tp < ntaps; ++tp) {
+            const int tx = tc + (tap0 + tp) * p.dil + p.t_off;
+            tma_load_3d(sa + tp * a_tap_bytes, &map_x, &full_bar[s], ci0, tx, b);
+            tma_load_3d(sa + tp * a_tap_bytes + WG_BOX_BYTES, &map_x, &full_bar[s], ci0 + 64, tx, b);
+          }
+          for (int j = 0; j < p.nb; ++j)
+            tma_load_3d(sa + p.KT * a_tap_bytes + j * WG_BOX_BYTES, &map_dy, &full_bar[s], n0 + 64 * j, tc, b);
         }
       }
     } else if (warp == 1) {
@@ -337,9 +340,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_wgrad_k(const __grid_const
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t s_addr = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t b_addr = s_addr + p.KT * a_tap_bytes;
           for (int tp = 0; tp < ntaps; ++tp) {
-            const uint32_t b_addr = a_addr + a_bytes + tp * b_tap_bytes;
+            const uint32_t a_addr = s_addr + tp * a_tap_bytes;
             for (int k = 0; k < 4; ++k) {      // 64 time rows per stage = 4 x K16; 16 rows = 2048 B
               const uint64_t da = make_sw128_mnmajor_desc(a_addr + k * 2048, WG_BOX_BYTES);
               const uint64_t db = make_sw128_mnmajor_desc(b_addr + k * 2048, WG_BOX_BYTES);
@@ -355,19 +359,19 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_wgrad_k(const __grid_const
       const int q = warp & 3;
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
-      const int co = co0 + q * 32 + lane;
-      const bool co_ok = co < p.Cout;
+      const int ci = ci0 + q * 32 + lane;
+      const bool row_ok = ci < p.Cin;
+      const int nvalid = min(p.NT, p.Cout - n0);
       for (int tp = 0; tp < ntaps; ++tp) {
-        for (int c0 = 0; c0 < p.NT; c0 += 16) {
-          if (n0 + c0 >= p.Cin) break;
+        float* wrow = p.ws + ((long long)(tap0 + tp) * p.Np + n0) * p.Mp + ci;
+        for (int c0 = 0; c0 < nvalid; c0 += 16) {
           float v[16];
           tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tp * p.NT + c0), v);
-          if (co_ok) {
+          if (row_ok) {
+            const int nj = min(16, nvalid - c0);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int ci = n0 + c0 + j;
-              if (ci < p.Cin) atomicAdd(p.dw + ((long long)co * p.Cin + ci) * p.K + tap0 + tp, v[j]);
-            }
+            for (int j = 0; j < 16; ++j)
+              if (j < nj) atomicAdd(wrow + (long long)(c0 + j) * p.Mp, v[j]);
           }
         }
       }
@@ -378,34 +382,67 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_wgrad_k(const __grid_const
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+// dw[co][ci][k] = ws[k][co][ci]
+__global__ void wgrad_finalize_k(const float* __restrict__ ws, float* __restrict__ dw, int Cout, int Cin, int K, int Np,
+                                 int Mp) {
+  long long n = (long long)Cout * Cin * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int k = (int)(i % K);
+    long long r = i / K;
+    int ci = (int)(r % Cin), co = (int)(r / Cin);
+    dw[i] = ws[((long long)k * Np + co) * Mp + ci];
+  }
+}
+
 // ------------------------------------------------------------------------------------------ pack kernels
 // x[B,C,T] fp32 NCW -> xp[B,Tp,Cp] bf16 channels-last, LeakyReLU(in_slope), halo rows reflect- or zero-filled.
+constexpr int PACK_STRIP = 8;   // 32-step time tiles per CTA
+
 __global__ void pack_cl_bf16_k(const float* __restrict__ x, __nv_bfloat16* __restrict__ xp, int C, int T, int Cp, int Tp,
-                               int halo, int pad_mode, float slope) {
+                               int halo, int pad_mode, float slope, float* __restrict__ chan_sum) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
-  const int tp0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  // read: threadIdx.x along time (coalesced), threadIdx.y strides channels
-  for (int cy = threadIdx.y; cy < 32; cy += blockDim.y) {
-    int c = c0 + cy, tp = tp0 + threadIdx.x;
-    float v = 0.f;
-    if (c < C && tp < Tp) {
-      int u = tp - halo;
-      bool ok = true;
-      if (u < 0) { if (pad_mode == TDVC_PAD_REFLECT) { u = -u; ok = u < T; } else ok = false; }
-      else if (u >= T) { if (pad_mode == TDVC_PAD_REFLECT) { u = 2 * (T - 1) - u; ok = u >= 0; } else ok = false; }
-      if (ok) {
-        v = __ldg(x + ((long long)b * C + c) * T + u);
-        v = v > 0.f ? v : v * slope;
+  const int c0 = blockIdx.y * 32;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};     // per-channel partial sums of this warp's 4 channel rows
+  for (int st = 0; st < PACK_STRIP; ++st) {
+    const int tp0 = (blockIdx.x * PACK_STRIP + st) * 32;
+    if (tp0 >= Tp) break;
+    // read: threadIdx.x along time (coalesced), threadIdx.y strides channels
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int cy = threadIdx.y + 8 * r;
+      const int c = c0 + cy, tp = tp0 + threadIdx.x;
+      float v = 0.f;
+      if (c < C && tp < Tp) {
+        int u = tp - halo;
+        bool ok = true;
+        if (u < 0) { if (pad_mode == TDVC_PAD_REFLECT) { u = -u; ok = u < T; } else ok = false; }
+        else if (u >= T) { if (pad_mode == TDVC_PAD_REFLECT) { u = 2 * (T - 1) - u; ok = u >= 0; } else ok = false; }
+        if (ok) {
+          v = __ldg(x + ((long long)b * C + c) * T + u);
+          if (tp >= halo && tp < halo + T) acc[r] += v;      // each source sample counted once
+          v = v > 0.f ? v : v * slope;
+        }
       }
+      tile[cy][threadIdx.x] = v;
     }
-    tile[cy][threadIdx.x] = v;
+    __syncthreads();
+    // write: threadIdx.x along channels (contiguous in xp)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int ty = threadIdx.y + 8 * r;
+      const int tp = tp0 + ty, c = c0 + threadIdx.x;
+      if (tp < Tp && c < Cp) xp[((long long)b * Tp + tp) * Cp + c] = __float2bfloat16(tile[threadIdx.x][ty]);
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  // write: threadIdx.x along channels (contiguous in xp)
-  for (int ty = threadIdx.y; ty < 32; ty += blockDim.y) {
-    int tp = tp0 + ty, c = c0 + threadIdx.x;
-    if (tp < Tp && c < Cp) xp[((long long)b * Tp + tp) * Cp + c] = __float2bfloat16(tile[threadIdx.x][ty]);
+  if (chan_sum) {      // per-channel sum of the fp32 source (the bias gradient when x is dL/dy)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float sres = warp_sum(acc[r]);
+      const int c = c0 + threadIdx.y + 8 * r;
+      if (threadIdx.x == 0 && c < C) atomicAdd(chan_sum + c, sres);
+    }
   }
 }
 
@@ -460,14 +497,15 @@ static int make_map_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d
 using namespace tdvc;
 
 extern "C" int tdvc_pack_cl_bf16(const float* x, void* xp, int B, int C, int T, int Cp, int halo, int pad_mode,
-                                 float in_slope, void* stream) {
+                                 float in_slope, float* chan_sum, void* stream) {
   TDVC_CHECK_ARG(B >= 0 && C > 0 && T > 0 && Cp >= C && Cp % 8 == 0 && halo >= 0 && x && xp);
   if (pad_mode == TDVC_PAD_REFLECT) TDVC_CHECK_ARG(halo < T);
+  if (chan_sum) TDVC_CUDA(cudaMemsetAsync(chan_sum, 0, sizeof(float) * C, (cudaStream_t)stream));
   if (B == 0) return TDVC_OK;
   int Tp = T + 2 * halo;
-  dim3 grid(cdiv(Tp, 32), cdiv(Cp, 32), B);
+  dim3 grid(cdiv(Tp, 32 * PACK_STRIP), cdiv(Cp, 32), B);
   TDVC_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535);
-  pack_cl_bf16_k<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)xp, C, T, Cp, Tp, halo, pad_mode, in_slope);
+  pack_cl_bf16_k<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)xp, C, T, Cp, Tp, halo, pad_mode, in_slope, chan_sum);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
@@ -541,47 +579,57 @@ extern "C" int tdvc_conv1d_tc_fwd(const void* xp, const void* wp, const float* b
   return TDVC_OK;
 }
 
+// workspace (floats) for tdvc_conv1d_tc_wgrad
+extern "C" int64_t tdvc_conv1d_tc_wgrad_ws(int Cout, int Cin, int K) {
+  const long long Mp = (long long)((Cin + 127) / 128) * 128, Np = (long long)((Cout + 15) / 16) * 16;
+  return (int64_t)K * Np * Mp;
+}
+
 // dw[Cout,Cin,K] (OVERWRITTEN) from the packed operands: dyp[B,Tout,Cdp] and xp[B,Tp,Cp] (both bf16 channels-last;
 // xp row = t + tap*dilation + t_off).
-extern "C" int tdvc_conv1d_tc_wgrad(const void* dyp, const void* xp, float* dw, int B, int Cdp, int Tout, int Cp, int Tp,
-                                    int Cout, int Cin, int K, int dilation, int t_off, void* stream) {
-  TDVC_CHECK_ARG(dyp && xp && dw && B >= 0 && Cdp % 8 == 0 && Cp % 8 == 0 && Cdp >= Cout && Cp >= Cin && Tout > 0 && Tp > 0 &&
-                 K > 0 && dilation > 0);
+extern "C" int tdvc_conv1d_tc_wgrad(const void* dyp, const void* xp, float* dw, float* ws, int B, int Cdp, int Tout, int Cp,
+                                    int Tp, int Cout, int Cin, int K, int dilation, int t_off, void* stream) {
+  TDVC_CHECK_ARG(dyp && xp && dw && ws && B >= 0 && Cdp % 8 == 0 && Cp % 8 == 0 && Cdp >= Cout && Cp >= Cin && Tout > 0 &&
+                 Tp > 0 && K > 0 && dilation > 0);
   cudaStream_t st = (cudaStream_t)stream;
-  TDVC_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * Cin * K, st));
-  if (B == 0) return TDVC_OK;
   WgTcP p{};
-  p.B = B; p.Tout = Tout; p.Cout = Cout; p.Cin = Cin; p.K = K; p.dil = dilation; p.t_off = t_off; p.dw = dw;
-  const int N16 = ((Cin + 15) / 16) * 16;
-  int NT = 16;
-  // choose the widest N tile such that all taps (or as many as possible) fit the 512 TMEM columns
+  p.B = B; p.Tout = Tout; p.Cout = Cout; p.Cin = Cin; p.K = K; p.dil = dilation; p.t_off = t_off; p.ws = ws;
+  p.Mp = ((Cin + 127) / 128) * 128;
+  p.Np = ((Cout + 15) / 16) * 16;
+  TDVC_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * (size_t)K * p.Np * p.Mp, st));
+  if (B == 0) { TDVC_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * Cin * K, st)); return TDVC_OK; }
+  const int N16 = p.Np;
+  // widest co tile such that as many taps as possible share the 512 TMEM columns (fewer re-reads of the operands)
   int best_nt = 16, best_cost = 1 << 30;
   for (int cand = std::min(N16, 256); cand >= 16; cand -= 16) {
     int kt = std::min(K, 512 / cand);
     if (kt < 1) continue;
-    int groups = cdiv(K, kt), ntiles = cdiv(N16, cand);
-    int cost = groups * ntiles;            // A-tile re-reads: fewer (tap group x n tile) pairs is better
+    // per-stage shared memory must leave room for at least 2 stages
+    long long stage = (long long)kt * 2 * WG_BOX_BYTES + (long long)cdiv(cand, 64) * WG_BOX_BYTES;
+    if (2 * stage > 200 * 1024) continue;
+    int cost = cdiv(K, kt) * cdiv(N16, cand);
     if (cost < best_cost) { best_cost = cost; best_nt = cand; }
   }
-  NT = best_nt;
-  p.NT = NT;
-  p.KT = std::min(K, 512 / NT);
+  p.NT = best_nt;
+  p.KT = std::min(K, 512 / p.NT);
+  while (p.KT > 1 && 2LL * ((long long)p.KT * 2 * WG_BOX_BYTES + (long long)cdiv(p.NT, 64) * WG_BOX_BYTES) > 200 * 1024) --p.KT;
   p.ntap_groups = cdiv(K, p.KT);
-  p.n_ntiles = cdiv(N16, NT);
-  p.nb = cdiv(NT, 64);
+  p.n_ntiles = cdiv(N16, p.NT);
+  p.nb = cdiv(p.NT, 64);
   int cols = 32;
-  while (cols < p.KT * NT) cols <<= 1;
+  while (cols < p.KT * p.NT) cols <<= 1;
+  TDVC_CHECK_ARG(cols <= 512);
   p.tmem_cols = cols;
-  const int stage_bytes = 2 * WG_BOX_BYTES + p.KT * p.nb * WG_BOX_BYTES;
+  const int stage_bytes = p.KT * 2 * WG_BOX_BYTES + p.nb * WG_BOX_BYTES;
   p.nchunk_t = cdiv(Tout, 64);
   p.units = B * p.nchunk_t;
   int stages = std::min(4, (int)((200 * 1024) / stage_bytes));
   TDVC_CHECK_ARG(stages >= 1);
   stages = std::min(stages, std::max(1, p.units));
   p.stages = stages;
-  const int m_tiles = cdiv(Cout, 128);
+  const int m_tiles = p.Mp / 128;
   const int gy = m_tiles * p.ntap_groups * p.n_ntiles;
-  int splits = std::max(1, (2 * num_sms()) / gy);
+  int splits = std::max(1, num_sms() / gy);
   splits = std::min(splits, p.units);
   p.splits = splits;
   size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
@@ -590,13 +638,17 @@ extern "C" int tdvc_conv1d_tc_wgrad(const void* dyp, const void* xp, float* dw, 
     TDVC_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  CUtensorMap map_a, map_b;
-  int rc = make_map_3d(&map_a, dyp, (uint64_t)Cdp, (uint64_t)Tout, (uint64_t)B, 64, 64);
+  CUtensorMap map_x, map_dy;
+  int rc = make_map_3d(&map_x, xp, (uint64_t)Cp, (uint64_t)Tp, (uint64_t)B, 64, 64);
   if (rc) return rc;
-  rc = make_map_3d(&map_b, xp, (uint64_t)Cp, (uint64_t)Tp, (uint64_t)B, 64, 64);
+  rc = make_map_3d(&map_dy, dyp, (uint64_t)Cdp, (uint64_t)Tout, (uint64_t)B, 64, 64);
   if (rc) return rc;
   TDVC_CHECK_ARG(gy <= 65535);
-  conv_tc_wgrad_k<<<dim3(splits, gy), TC_THREADS, smem, st>>>(map_a, map_b, p);
+  conv_tc_wgrad_k<<<dim3(splits, gy), TC_THREADS, smem, st>>>(map_x, map_dy, p);
+  TDVC_LAUNCH_CHECK();
+  long long n = (long long)Cout * Cin * K;
+  int blocks = (int)std::min<long long>((n + 255) / 256, 4LL * num_sms());
+  wgrad_finalize_k<<<blocks, 256, 0, st>>>(ws, dw, Cout, Cin, K, p.Np, p.Mp);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }

@@ -586,7 +586,7 @@ class _PackCache:
 _pack_cache = _PackCache()
 
 
-def _pack_act(x, Cp, halo, pad_mode, slope, cache=True):
+def _pack_act(x, Cp, halo, pad_mode, slope, cache=True, chan_sum=None):
     B, Cc, T = x.shape
     key = (tuple(x.shape), Cp, halo, pad_mode, slope)
     if cache:
@@ -594,7 +594,8 @@ def _pack_act(x, Cp, halo, pad_mode, slope, cache=True):
         if hit is not None:
             return hit
     xp = torch.empty(B, T + 2 * halo, Cp, device=x.device, dtype=torch.bfloat16)
-    _lib.check(_lib.load().tdvc_pack_cl_bf16(_p(x), _p(xp), B, Cc, T, Cp, halo, pad_mode, slope, _st()), "pack_cl_bf16")
+    _lib.check(_lib.load().tdvc_pack_cl_bf16(_p(x), _p(xp), B, Cc, T, Cp, halo, pad_mode, slope, _p(chan_sum), _st()),
+               "pack_cl_bf16")
     if cache:
         _pack_cache.put(key, x, xp)
     return xp
@@ -659,7 +660,11 @@ class _Conv1dTC(torch.autograd.Function):
         Cdp = _cp(Cout)
         dyp = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
-            dyp = _pack_act(dy, Cdp, 0, PAD_ZEROS, 1.0, cache=False)     # shared by dgrad and wgrad
+            # one pass over dL/dy: bf16 channels-last copy shared by dgrad and wgrad + the bias gradient
+            if need_b:
+                db = torch.empty(Cout, device=x.device, dtype=torch.float32)
+            dyp = _pack_act(dy, Cdp, 0, PAD_ZEROS, 1.0, cache=False, chan_sum=db)
+            need_b = False
         if ctx.needs_input_grad[0]:
             # dgrad = the same implicit GEMM on dy with channel-swapped, tap-flipped weights
             ph = pad if pad_mode == PAD_REFLECT else 0            # reflect halo kept in the staging buffer
@@ -681,8 +686,9 @@ class _Conv1dTC(torch.autograd.Function):
             # wgrad on tcgen05 from the two packed operands (time is the GEMM K dimension)
             halo = pad if pad_mode == PAD_REFLECT else 0
             dw = torch.empty_like(w)
-            _lib.check(lib.tdvc_conv1d_tc_wgrad(_p(dyp), _p(xp), _p(dw), B, Cdp, Tout, xp.shape[2], xp.shape[1], Cout, Cin,
-                                                K, dilation, halo - pad, _st()), "conv1d_tc_wgrad")
+            ws = torch.empty(lib.tdvc_conv1d_tc_wgrad_ws(Cout, Cin, K), device=x.device, dtype=torch.float32)
+            _lib.check(lib.tdvc_conv1d_tc_wgrad(_p(dyp), _p(xp), _p(dw), _p(ws), B, Cdp, Tout, xp.shape[2], xp.shape[1],
+                                                Cout, Cin, K, dilation, halo - pad, _st()), "conv1d_tc_wgrad")
         if need_b:
             db = torch.empty(Cout, device=x.device, dtype=torch.float32)
             _lib.check(lib.tdvc_bias_grad(_p(dy), _p(db), B, Cout, Tout, _st()), "bias_grad")
