@@ -144,7 +144,7 @@ def run_ours(args):
     from tdvc import _lib, ops
     from tdvc.dp import GradAverager, broadcast_parameters
     from tdvc.optim import FusedAdamW
-    from tdvc.train_step import TrainStep
+    from tdvc.train_step import GraphedTrainStep, TrainStep
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -188,19 +188,37 @@ def run_ours(args):
         return float(ms.item())
 
     last = {}
-
-    def step_resident():
-        last.update(ts.step(resident))
-
     h2d = [0]
     d2h = [0]
+    nbytes_in = sum(v.numel() * v.element_size() for v in host.values())
+    if args.graph:
+        # the whole step (both backward passes, all-reduce, optimisers) is one CUDA graph; eager warm-up inside
+        n0 = lib.tdvc_launch_count()
+        graphed = GraphedTrainStep(ts, resident, warmup=2)
+        n_cap = lib.tdvc_launch_count() - n0
+        launches_per_step = n_cap / 3.0          # 2 eager warm-up steps + 1 captured step
 
-    def step_e2e():
-        batch, nb = to_device(host, dev, pinned)
-        out = ts.step(batch)
-        losses = torch.stack([out["d_loss"].reshape(()), out["g_loss"].reshape(())]).cpu()   # D2H read of the result
-        h2d[0], d2h[0] = nb, losses.numel() * losses.element_size()
-        last["host_losses"] = losses
+        def step_resident():
+            last.update(graphed.step())
+
+        def step_e2e():
+            graphed.load(pinned)                                  # H2D of this step's inputs (pinned host memory)
+            out = graphed.step()
+            losses = torch.stack([out["d_loss"].reshape(()), out["g_loss"].reshape(())]).cpu()   # D2H of the result
+            h2d[0], d2h[0] = nbytes_in, losses.numel() * losses.element_size()
+            last["host_losses"] = losses
+    else:
+        launches_per_step = None
+
+        def step_resident():
+            last.update(ts.step(resident))
+
+        def step_e2e():
+            batch, nb = to_device(host, dev, pinned)
+            out = ts.step(batch)
+            losses = torch.stack([out["d_loss"].reshape(()), out["g_loss"].reshape(())]).cpu()
+            h2d[0], d2h[0] = nb, losses.numel() * losses.element_size()
+            last["host_losses"] = losses
 
     for _ in range(args.warmup):
         step_resident()
@@ -210,7 +228,7 @@ def run_ours(args):
         sampler.start()
     ms = timed(step_resident, args.steps)
     clocks = sampler.stop() if sampler else None
-    launches = (lib.tdvc_launch_count() - n0) / max(1, args.steps)
+    launches = launches_per_step if launches_per_step is not None else (lib.tdvc_launch_count() - n0) / max(1, args.steps)
     if args.profile:
         if rank == 0:
             print(json.dumps({"profile_mode": True, "ms_per_step": ms / args.steps, "gpu_launches": launches}))
@@ -240,7 +258,8 @@ def run_ours(args):
                        "batch_per_gpu": B, "segment_samples": T, "sample_rate": SR, "speakers": nspk,
                        "lambda_f0": "0 (torchcrepe unavailable offline, SURVEY 8c)", "precision": args.precision,
                        "l2": "no explicit flush: one step streams >6 GB of activations, far larger than the 126 MB L2",
-                       "parallelism": f"dp{world}", "step_gflop_algorithmic": STEP_GFLOP_B16 * world},
+                       "parallelism": f"dp{world}", "step_gflop_algorithmic": STEP_GFLOP_B16 * world,
+                       "cuda_graph": bool(args.graph)},
             "clocks": clocks,
             "e2e": {"value": round(e2e, 3), "unit": UNIT, "h2d_bytes_per_step": h2d[0], "d2h_bytes_per_step": d2h[0],
                     "ms_per_step": round(ms_e2e / args.steps, 3)},
@@ -373,8 +392,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("TDVC_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("TDVC_PRECISION", "bf16"), choices=["fp32", "bf16"],
+                    help="bf16 = tcgen05 tensor-core path (2e-2 parity, the headline); fp32 = exact CUDA-core path (1e-5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", dest="graph", action="store_false",
+                    help="launch every kernel from Python each step instead of replaying one CUDA graph")
     ap.add_argument("--profile", action="store_true",
                     help="profiling aid (ncu): honour --warmup as given, skip the e2e / roofline / cpu legs; "
                          "numbers printed in this mode are not bench values")

@@ -148,7 +148,8 @@ int tdvc_abs_diff_bwd(const float* a, const float* b, float scale, const float* 
 int tdvc_adamw_multi(float* const* params, const float* const* grads, float* const* exp_avg,
                      float* const* exp_avg_sq, const int64_t* sizes, int n_tensors, int64_t max_size,
                      float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                     float grad_scale, void* stream);
+                     float grad_scale, float* step_dev /* optional device step counter: incremented, then used
+                     for the bias corrections instead of `step` (CUDA-graph replay) */, void* stream);
 
 /* ---- bf16 tensor-core path (tcgen05 / TMEM / TMA), dense stride-1 Conv1d as implicit GEMM.
  *      pack: x[B,C,T] fp32 NCW -> xp[B, Tp, Cp] bf16 channels-last with LeakyReLU(in_slope) and

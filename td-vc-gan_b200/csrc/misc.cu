@@ -118,7 +118,13 @@ __global__ void abs_diff_bwd_k(const float* __restrict__ a, const float* __restr
 __global__ void adamw_multi_k(float* const* __restrict__ params, const float* const* __restrict__ grads,
                               float* const* __restrict__ m1, float* const* __restrict__ m2,
                               const int64_t* __restrict__ sizes, int chunks_per_tensor, float lr, float b1, float b2,
-                              float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
+                              float eps, float wd, float bc1, float bc2_sqrt, float gscale,
+                              const float* __restrict__ step_dev) {
+  if (step_dev) {      // step counter lives on the device (CUDA-graph replays must advance it)
+    const float st = *step_dev;
+    bc1 = 1.f - powf(b1, st);
+    bc2_sqrt = sqrtf(1.f - powf(b2, st));
+  }
   const int ti = blockIdx.x / chunks_per_tensor;
   const int ch = blockIdx.x - ti * chunks_per_tensor;
   const long long n = sizes[ti];
@@ -139,6 +145,8 @@ __global__ void adamw_multi_k(float* const* __restrict__ params, const float* co
     p[i] = pi - step_size * (mi / denom);
   }
 }
+
+__global__ void step_inc_k(float* step) { *step += 1.f; }
 
 }  // namespace tdvc
 using namespace tdvc;
@@ -222,17 +230,21 @@ extern "C" int tdvc_abs_diff_bwd(const float* a, const float* b, float scale, co
 extern "C" int tdvc_adamw_multi(float* const* params, const float* const* grads, float* const* exp_avg,
                                 float* const* exp_avg_sq, const int64_t* sizes, int n_tensors, int64_t max_size,
                                 float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                                float grad_scale, void* stream) {
-  TDVC_CHECK_ARG(n_tensors >= 0 && step >= 1 && max_size >= 0);
+                                float grad_scale, float* step_dev, void* stream) {
+  TDVC_CHECK_ARG(n_tensors >= 0 && (step >= 1 || step_dev) && max_size >= 0);
   if (n_tensors == 0 || max_size == 0) return TDVC_OK;
   TDVC_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && sizes);
-  float bc1 = 1.f - powf(beta1, (float)step);
-  float bc2 = 1.f - powf(beta2, (float)step);
+  float bc1 = 1.f - powf(beta1, (float)std::max(step, 1));
+  float bc2 = 1.f - powf(beta2, (float)std::max(step, 1));
+  if (step_dev) {
+    step_inc_k<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+    TDVC_LAUNCH_CHECK();
+  }
   int chunks = (int)std::min<long long>((max_size + 256 * 8 - 1) / (256 * 8), 64);
   if (chunks < 1) chunks = 1;
   adamw_multi_k<<<n_tensors * chunks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, sizes, chunks,
                                                                       lr, beta1, beta2, eps, weight_decay, bc1,
-                                                                      sqrtf(bc2), grad_scale);
+                                                                      sqrtf(bc2), grad_scale, step_dev);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }

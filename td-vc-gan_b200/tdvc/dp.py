@@ -22,6 +22,16 @@ class GradAverager:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._buckets = {}
 
+    def reduce_flat(self, flat: torch.Tensor):
+        """Average one persistent flat gradient bucket in place (FusedAdamW.bank())."""
+        if self.world == 1:
+            return
+        if flat.is_cuda and dist.get_backend(self.group) == "nccl":
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            flat.div_(self.world)
+
     def __call__(self, name: str, params: List[torch.nn.Parameter]):
         if self.world == 1:
             return

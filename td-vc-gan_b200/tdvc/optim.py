@@ -1,5 +1,12 @@
 """Fused multi-tensor AdamW: one kernel launch for a whole parameter list (reference uses
-torch.optim.AdamW(params, lr, betas) at train.py:188-189; defaults eps=1e-8, weight_decay=1e-2)."""
+torch.optim.AdamW(params, lr, betas) at train.py:188-189; defaults eps=1e-8, weight_decay=1e-2).
+
+Two ways to feed it gradients:
+  * default: reads each p.grad in place (pointer tables are rebuilt when a gradient tensor moves);
+  * `use_grad_bank()`: gradients are first gathered into one persistent flat fp32 buffer per parameter group
+    (a single multi-tensor copy).  The bank has a fixed address, so the step is CUDA-graph capturable, and it is
+    the bucket the data-parallel all-reduce operates on (`bank(i)`), between `gather_grads()` and `step()`.
+The step counter is kept on the device so graph replays advance the bias correction."""
 from __future__ import annotations
 
 import ctypes as C
@@ -14,25 +21,71 @@ class FusedAdamW(torch.optim.Optimizer):
         defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
         self._tables = {}
+        self._banks = None
+        self._gathered = False
 
-    def _table(self, gi, params):
-        """Device pointer tables for one param group; rebuilt only when a pointer changed."""
-        key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in params)
-        cached = self._tables.get(gi)
-        if cached is not None and cached["key"] == key:
-            return cached
-        dev = params[0].device
+    # ------------------------------------------------------------------ grad bank
+    def use_grad_bank(self):
+        if self._banks is not None:
+            return self
+        self._banks = []
+        for group in self.param_groups:
+            ps = [p for p in group["params"] if p.requires_grad]
+            n = sum(p.numel() for p in ps)
+            flat = torch.zeros(n, device=ps[0].device, dtype=torch.float32)
+            views, off = [], 0
+            for p in ps:
+                views.append(flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+            self._banks.append(dict(params=ps, flat=flat, views=views))
+        return self
+
+    def bank(self, gi=0) -> torch.Tensor:
+        return self._banks[gi]["flat"]
+
+    @torch.no_grad()
+    def gather_grads(self):
+        """Copy every p.grad into the bank (zeros where a parameter received no gradient)."""
+        for b in self._banks:
+            src, dst = [], []
+            missing = [v for p, v in zip(b["params"], b["views"]) if p.grad is None]
+            for p, v in zip(b["params"], b["views"]):
+                if p.grad is not None:
+                    src.append(p.grad)
+                    dst.append(v)
+            if missing:
+                torch._foreach_zero_(missing)
+            if src:
+                torch._foreach_copy_(dst, src)
+        self._gathered = True
+
+    # ------------------------------------------------------------------ tables
+    def _ensure_state(self, params):
         for p in params:
             st = self.state[p]
             if "exp_avg" not in st:
                 st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                 st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-        mk = lambda vals: torch.tensor(vals, dtype=torch.int64).to(dev, non_blocking=False)
+
+    def _table(self, gi, params, grads):
+        key = tuple((p.data_ptr(), g.data_ptr()) for p, g in zip(params, grads))
+        cached = self._tables.get(gi)
+        if cached is not None and cached["key"] == key:
+            return cached
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("FusedAdamW: pointer tables must exist before CUDA-graph capture "
+                               "(call use_grad_bank() and run one eager step first)")
+        dev = params[0].device
+        self._ensure_state(params)
+        mk = lambda vals: torch.tensor(vals, dtype=torch.int64).to(dev)
         tab = dict(key=key,
-                   p=mk([p.data_ptr() for p in params]), g=mk([p.grad.data_ptr() for p in params]),
+                   p=mk([p.data_ptr() for p in params]), g=mk([g.data_ptr() for g in grads]),
                    m=mk([self.state[p]["exp_avg"].data_ptr() for p in params]),
                    v=mk([self.state[p]["exp_avg_sq"].data_ptr() for p in params]),
-                   n=mk([p.numel() for p in params]), max_n=max(p.numel() for p in params), count=len(params))
+                   n=mk([p.numel() for p in params]), max_n=max(p.numel() for p in params), count=len(params),
+                   step=torch.zeros(1, device=dev, dtype=torch.float32))
+        if cached is not None:
+            tab["step"] = cached["step"]
         self._tables[gi] = tab
         return tab
 
@@ -43,19 +96,25 @@ class FusedAdamW(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         lib = _lib.load()
+        if self._banks is not None and not self._gathered:
+            self.gather_grads()
+        self._gathered = False
         for gi, group in enumerate(self.param_groups):
-            params = [p for p in group["params"] if p.grad is not None]
+            if self._banks is not None:
+                params, grads = self._banks[gi]["params"], self._banks[gi]["views"]
+            else:
+                params = [p for p in group["params"] if p.grad is not None]
+                grads = [p.grad for p in params]
             if not params:
                 continue
-            for p in params:
-                if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.grad.is_contiguous()):
+            for p, g in zip(params, grads):
+                if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and g.is_contiguous()):
                     raise RuntimeError("FusedAdamW needs contiguous fp32 CUDA parameters and gradients")
-            group["step"] = group.get("step", 0) + 1
-            tab = self._table(gi, params)
+            tab = self._table(gi, params, grads)
             b1, b2 = group["betas"]
             st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
             vp = lambda t: C.c_void_p(t.data_ptr())
             _lib.check(lib.tdvc_adamw_multi(vp(tab["p"]), vp(tab["g"]), vp(tab["m"]), vp(tab["v"]), vp(tab["n"]),
                                             tab["count"], tab["max_n"], group["lr"], b1, b2, group["eps"],
-                                            group["weight_decay"], group["step"], float(grad_scale), st), "adamw_multi")
+                                            group["weight_decay"], 0, float(grad_scale), vp(tab["step"]), st), "adamw_multi")
         return loss

@@ -46,6 +46,20 @@ class TrainStep:
         self.num_spk = num_spk if num_spk is not None else G.embedding.weight.shape[1]
         self.grad_hook = grad_hook
 
+    def _reduce_and_step(self, name, module, opt):
+        """(data-parallel gradient mean) + optimiser update.  With a FusedAdamW grad bank the all-reduce runs on
+        the optimiser's flat bucket, otherwise on the parameters' .grad tensors."""
+        banked = opt is not None and getattr(opt, "_banks", None) is not None
+        if banked:
+            opt.gather_grads()
+            if self.grad_hook is not None:
+                for gi in range(len(opt._banks)):
+                    self.grad_hook.reduce_flat(opt.bank(gi))
+        elif self.grad_hook is not None:
+            self.grad_hook(name, list(module.parameters()))
+        if opt is not None:
+            opt.step()
+
     # ---- D step: train.py:259-296
     def d_step(self, batch) -> dict:
         G, D = self.G, self.D
@@ -65,10 +79,7 @@ class TrainStep:
         if self.opt_D is not None:
             self.opt_D.zero_grad(set_to_none=True)
         d_loss.backward()
-        if self.grad_hook is not None:
-            self.grad_hook("D", list(D.parameters()))
-        if self.opt_D is not None:
-            self.opt_D.step()
+        self._reduce_and_step("D", D, self.opt_D)
         return {"d_loss_real": d_real.detach(), "d_loss_fake": d_fake.detach(), "d_loss": d_loss.detach(),
                 "fake": fake}
 
@@ -118,10 +129,7 @@ class TrainStep:
             if self.opt_G is not None:
                 self.opt_G.zero_grad(set_to_none=True)
             g_loss.backward()
-        if self.grad_hook is not None:
-            self.grad_hook("G", list(G.parameters()))
-        if self.opt_G is not None:
-            self.opt_G.step()
+        self._reduce_and_step("G", G, self.opt_G)
         out.update(g_adv=g_adv.detach(), g_rec=g_rec.detach(), g_idt=g_idt.detach(), g_cont=g_cont.detach(),
                    g_loss=g_loss.detach(), fake=fake.detach())
         return out
@@ -130,3 +138,41 @@ class TrainStep:
         out = self.d_step(batch)
         out.update(self.g_step(batch, raw_draws))
         return out
+
+
+class GraphedTrainStep:
+    """The whole G+D iteration captured once into a CUDA graph and replayed: the step issues ~8000 kernel
+    launches from Python, which costs more host time than the GPU needs to run them.  Inputs are copied into
+    static tensors; outputs are static tensors overwritten by every replay.  Needs optimisers with a grad bank
+    (fixed gradient addresses) -- FusedAdamW.use_grad_bank()."""
+
+    def __init__(self, ts: TrainStep, example_batch: dict, warmup: int = 3):
+        from tdvc import ops
+        self.ts = ts
+        for opt in (ts.opt_G, ts.opt_D):
+            if opt is not None and hasattr(opt, "use_grad_bank"):
+                opt.use_grad_bank()
+        self.static = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in example_batch.items()}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                ts.step(self.static)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        ops._pack_cache.clear()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = ts.step(self.static)
+        ops._pack_cache.clear()
+
+    def load(self, batch: dict, non_blocking: bool = True):
+        for k, v in batch.items():
+            if torch.is_tensor(v):
+                self.static[k].copy_(v, non_blocking=non_blocking)
+
+    def step(self, batch: Optional[dict] = None) -> dict:
+        if batch is not None:
+            self.load(batch)
+        self.graph.replay()
+        return self.out

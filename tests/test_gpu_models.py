@@ -239,3 +239,33 @@ def test_optimizer_step_moves_weights_like_torch_adamw():
         assert relerr(p, ref_p[k]) < 1e-6, k
     out = ts.g_step(bd, raw_draws=b["neg_idx"])
     assert torch.isfinite(out["g_loss"])
+
+
+def test_graphed_step_equals_eager_step():
+    """GraphedTrainStep (whole G+D iteration as one CUDA graph, grad-bank AdamW, device-side step counter)
+    leaves the same weights as the eager TrainStep after 3 iterations."""
+    from tdvc.optim import FusedAdamW
+    from tdvc.train_step import GraphedTrainStep, TrainStep
+    cfg, hp = CASES["step_tiny"], HP_STAGE2_1       # no contrastive RNG dependence on call order: same draws both ways
+    hp = dict(hp, lambda_cont_emb=0)
+    b = make_batch(cfg["B"], cfg["T"], cfg["nspk"], seed=9, frames_div=int(np.prod(cfg["ratios"])), permute=False)
+    bd = {k: (cu(v) if torch.is_tensor(v) else v) for k, v in b.items() if k != "neg_idx"}
+    results = []
+    for graphed in (False, True):
+        G = load_det(build_G(cfg), 11)
+        D = load_det(build_D(cfg), 12)
+        oG, oD = FusedAdamW(G.parameters(), 1e-3, (0.8, 0.99)), FusedAdamW(D.parameters(), 1e-3, (0.8, 0.99))
+        ts = TrainStep(G, D, hp, oG, oD, cfg["nspk"])
+        if graphed:
+            # capture performs 3 real (weight-updating) steps: 2 eager warm-ups + the captured one
+            gs = GraphedTrainStep(ts, bd, warmup=2)
+            out = gs.step()
+        else:
+            for _ in range(4):
+                out = ts.step(bd)
+        torch.cuda.synchronize()
+        results.append(({k: v.detach().clone() for k, v in G.state_dict().items()}, float(out["g_loss"]), float(out["d_loss"])))
+    (sd_e, gl_e, dl_e), (sd_g, gl_g, dl_g) = results
+    assert abs(gl_e - gl_g) <= 1e-4 * abs(gl_e) and abs(dl_e - dl_g) <= 1e-4 * abs(dl_e)
+    for k in sd_e:
+        assert relerr(sd_g[k], sd_e[k]) < 1e-4, k      # atomics in wgrad reorder fp32 sums run to run
