@@ -155,13 +155,18 @@ int tdvc_adamw_multi(float* const* params, const float* const* grads, float* con
  *      pack: x[B,C,T] fp32 NCW -> xp[B, Tp, Cp] bf16 channels-last with LeakyReLU(in_slope) and
  *      `halo` samples of reflect/zero padding on each side (Tp = T + 2*halo, Cp = C rounded up to
  *      8, zero filled).  */
-int tdvc_pack_cl_bf16(const float* x, void* xp, int B, int C, int T, int Cp, int halo, int pad_mode,
-                      float in_slope, float* chan_sum /* optional [C]: sum over (b,t) of x, OVERWRITTEN: the bias
-                      gradient falls out of packing dL/dy */, void* stream);
+int tdvc_pack_cl_bf16(const float* x, void* xp, int B, int C, int T, int Cp /* row pitch of xp */, int halo,
+                      int pad_mode, float in_slope, float* chan_sum /* optional [C]: sum over (b,t) of x, OVERWRITTEN:
+                      the bias gradient falls out of packing dL/dy */, int c_off /* first channel written */,
+                      int Cw /* channels written (>= C, zero filled; <= 0: Cp - c_off) */,
+                      int ones_ch /* >= C: that channel is set to 1 on the T valid rows (bias gradient through
+                      the wgrad GEMM); -1: none */, void* stream);
 /* w[Cout,Cin,K] fp32 -> wp[K, Coutp, Cinp] bf16 (zero padded); transpose_flip!=0 produces the
  * dgrad operand wp[K, Cinp, Coutp] with taps reversed. */
 int tdvc_pack_weight_bf16(const float* w, void* wp, int Cout, int Cin, int K, int Coutp, int Cinp,
-                          int transpose_flip, void* stream);
+                          int transpose_flip, int R_total, int r_off, int Q_total, int q_off, void* stream);
+/* (R_total, r_off, Q_total, q_off): write the packed block at row r_off / column q_off of a larger
+ * wp[K][R_total][Q_total] holding several convs' weights (grouped launches); <= 0 totals mean "the block is all". */
 /* y[B,Cout,Tout] fp32 NCW = epilogue( sum_k sum_ci xp[b, t + k*dilation + off, ci] * wp[k, co, ci] )
  * epilogue: + bias[co] ; FiLM  y*(1+gb[b,co,t]) + gb[b,Cout+co,t] when gb != NULL ; + residual ; act. */
 int tdvc_conv1d_tc_fwd(const void* xp, const void* wp, const float* bias, const float* gb,
@@ -169,12 +174,32 @@ int tdvc_conv1d_tc_fwd(const void* xp, const void* wp, const float* bias, const 
                        int Tout, int K, int dilation, int t_off, int out_act, float out_slope,
                        void* stream);
 
+/* Grouped / packed-operand form of the same kernel.  All `groups` share the time geometry; group g reads input
+ * channels [a_ch_off + g*a_ch_stride, +Cinp_g) of xp[B,Tp,Cp_total], uses weight rows [g*Coutp_g, +Coutp_g) of
+ * wp[K][groups*Coutp_g][Cinp_g] and bias[g*bias_stride + n].  Output: fp32 NCW y[groups][B][Cout_g][Tout], or
+ * (out_packed) bf16 channels-last yp[B][tp_out][cp_out] at row t+out_halo, channel out_ch_off + g*out_ch_stride + n
+ * -- the operand layout of the next conv, so no pack pass.  maskp (optional): a packed activated tensor
+ * (row t+mask_halo, channel mask_ch_off + g*mask_ch_stride + n); where it is <= 0 the result is multiplied by
+ * mask_slope: the LeakyReLU derivative fused into a data-gradient conv (generator.py:89 cond_var[1]). */
+typedef struct tdvc_tc_conv {
+  const void* xp; const void* wp; const float* bias; const float* gb; const float* residual;
+  float* y; void* yp; const void* maskp;
+  int32_t B, Tp, Tout, K, dilation, t_off;
+  int32_t Cp_total, groups, a_ch_off, a_ch_stride, Cinp_g, Cout_g, Coutp_g, bias_stride;
+  int32_t out_act; float out_slope;
+  int32_t out_packed, tp_out, cp_out, out_halo, out_ch_off, out_ch_stride;
+  int32_t tm, cm, mask_halo, mask_ch_off, mask_ch_stride; float mask_slope;
+} tdvc_tc_conv;
+int tdvc_conv1d_tc_fwd_ex(const tdvc_tc_conv* c, void* stream);
+
 /* weight gradient of the same conv on tcgen05: dw[Cout,Cin,K] (OVERWRITTEN, fp32) from the packed bf16 operands
  * dyp[B,Tout,Cdp] and xp[B,Tp,Cp]; xp row read for output step t and tap k is t + k*dilation + t_off.
  * ws: workspace of tdvc_conv1d_tc_wgrad_ws(Cout, Cin, K) floats (split-K partial sums, [K][Coutp][Cinp]). */
 int64_t tdvc_conv1d_tc_wgrad_ws(int Cout, int Cin, int K);
 int tdvc_conv1d_tc_wgrad(const void* dyp, const void* xp, float* dw, float* ws, int B, int Cdp, int Tout, int Cp,
-                         int Tp, int Cout, int Cin, int K, int dilation, int t_off, void* stream);
+                         int Tp, int Cout, int Cin, int K, int dilation, int t_off,
+                         int x_ch_off /* first channel of the conv's input inside xp */,
+                         int dy_ch_off /* first channel of the conv's output inside dyp */, void* stream);
 
 #ifdef __cplusplus
 }

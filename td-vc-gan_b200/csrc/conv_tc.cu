@@ -99,7 +99,7 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
 }
 
 struct TcP {
-  int B, Tout, Cout, K, dil, t_off;
+  int B, Tout, Cout, K, dil, t_off;          // Cout = valid output channels per group
   int nchunk, last_nk16, BN, stages, tmem_cols;
   int out_act;
   float out_slope;
@@ -108,6 +108,13 @@ struct TcP {
   const float* res;
   float* y;
   int debug;   // TDVC_TC_DEBUG (development only): 1 = no epilogue stores, 2 = no main loop, 4 = no tmem loads
+  // grouped / packed extensions (tdvc_conv1d_tc_fwd_ex)
+  int tiles_per_group, coutp_g, a_ch_off, a_ch_stride, bias_stride;
+  __nv_bfloat16* yp;                          // OUT == 1: packed bf16 channels-last output [B, tp_out, cp_out]
+  int tp_out, cp_out, out_halo, out_ch_off, out_ch_stride;
+  const __nv_bfloat16* maskp;                 // MASK == 1: packed activated tensor whose sign gates the result
+  int tm, cm, mask_halo, mask_ch_off, mask_ch_stride;
+  float mask_slope;
 };
 
 constexpr int TC_BM = 128;
@@ -116,8 +123,10 @@ constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
 constexpr int TC_THREADS = 192;       // wgrad kernel: TMA warp, MMA warp, 4 epilogue warps
 constexpr int TC_FWD_THREADS = 320;   // forward kernel: TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quadrant)
 
-// ACT: tdvc_act of the epilogue; EPI: 0 = bias only, 1 = + residual, 2 = FiLM (+ residual when p.res)
-template <int ACT, int EPI>
+// ACT: tdvc_act of the epilogue; EPI: 0 = bias only, 1 = + residual, 2 = FiLM (+ residual when p.res);
+// OUT: 0 = fp32 NCW [groups][B][Cout][T], 1 = bf16 channels-last (the next conv's operand, no pack pass);
+// MASK: 1 = multiply by the LeakyReLU derivative taken from the sign of a packed activated tensor (dgrad).
+template <int ACT, int EPI, int OUT, int MASK>
 __global__ void __launch_bounds__(TC_FWD_THREADS) conv_tc_fwd_k(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_b, TcP p) {
   __shared__ float bias_s[256];      // bias of this N tile (zeros when absent)
@@ -132,9 +141,10 @@ __global__ void __launch_bounds__(TC_FWD_THREADS) conv_tc_fwd_k(const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t0 = blockIdx.x * TC_BM;
-  const int n0 = blockIdx.y * p.BN;
+  const int grp = blockIdx.y / p.tiles_per_group;
+  const int n0 = (blockIdx.y - grp * p.tiles_per_group) * p.BN;       // channel offset inside the group
   for (int i = threadIdx.x; i < p.BN; i += TC_FWD_THREADS)
-    bias_s[i] = (p.bias && n0 + i < p.Cout) ? __ldg(p.bias + n0 + i) : 0.f;
+    bias_s[i] = (p.bias && n0 + i < p.Cout) ? __ldg(p.bias + grp * p.bias_stride + n0 + i) : 0.f;
   const int b = blockIdx.z;
   const int iters = (p.debug & 2) ? 0 : p.K * p.nchunk;
 
@@ -164,8 +174,8 @@ __global__ void __launch_bounds__(TC_FWD_THREADS) conv_tc_fwd_k(const __grid_con
         const int tap = it / p.nchunk, ck = it - tap * p.nchunk;
         uint8_t* sa = smem + (size_t)s * stage_bytes;
         mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
-        tma_load_3d(sa, &map_a, &full_bar[s], ck * TC_BK, t0 + tap * p.dil + p.t_off, b);
-        tma_load_3d(sa + TC_A_BYTES, &map_b, &full_bar[s], ck * TC_BK, n0, tap);
+        tma_load_3d(sa, &map_a, &full_bar[s], p.a_ch_off + grp * p.a_ch_stride + ck * TC_BK, t0 + tap * p.dil + p.t_off, b);
+        tma_load_3d(sa + TC_A_BYTES, &map_b, &full_bar[s], ck * TC_BK, grp * p.coutp_g + n0, tap);
       }
     }
   } else if (warp == 1) {
@@ -213,27 +223,64 @@ __global__ void __launch_bounds__(TC_FWD_THREADS) conv_tc_fwd_k(const __grid_con
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
       }
       if (t_ok) {
-        const long long base = ((long long)b * p.Cout + n0 + c0) * ct + t;
-        float* yp = p.y + base;
-        const float* rp = p.res + base;                                   // only dereferenced when EPI asks for it
-        const float* gp = p.gb + ((long long)b * 2 * p.Cout + n0 + c0) * ct + t;
-        const long long beta_off = (long long)p.Cout * ct;
         const int nj = min(16, nvalid - c0);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          if (j < nj) {
-            float o = v[j] + bias_s[c0 + j];
-            if (EPI == 2) {
-              o = fmaf(o, 1.f + __ldg(gp), __ldg(gp + beta_off));
-              if (p.res) o += __ldg(rp);
-            } else if (EPI == 1) {
-              o += __ldg(rp);
-            }
-            if (ACT == TDVC_ACT_LRELU) o = o > 0.f ? o : o * p.out_slope;
-            else if (ACT == TDVC_ACT_TANH) o = tanhf(o);
-            if (!(p.debug & 1)) *yp = o;
+        for (int j = 0; j < 16; ++j) v[j] += bias_s[c0 + j];
+        if (MASK) {
+          const __nv_bfloat16* mp = p.maskp + ((long long)b * p.tm + t + p.mask_halo) * p.cm + p.mask_ch_off +
+                                    grp * p.mask_ch_stride + n0 + c0;
+          uint4 m0 = __ldg(reinterpret_cast<const uint4*>(mp));
+          uint4 m1 = __ldg(reinterpret_cast<const uint4*>(mp) + 1);
+          const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            // bf16 sign/zero test on the raw bits: value <= 0  <=>  sign bit set or magnitude zero
+            const uint32_t h = (j & 1) ? (mw[j >> 1] >> 16) : (mw[j >> 1] & 0xFFFFu);
+            if ((h & 0x8000u) || (h & 0x7FFFu) == 0) v[j] *= p.mask_slope;
           }
-          yp += ct; rp += ct; gp += ct;
+        }
+        if (OUT == 0) {
+          const long long base = (((long long)grp * p.B + b) * p.Cout + n0 + c0) * ct + t;
+          float* yp = p.y + base;
+          const float* rp = p.res + base;                                   // only dereferenced when EPI asks for it
+          const float* gp = p.gb + ((long long)b * 2 * p.Cout + n0 + c0) * ct + t;
+          const long long beta_off = (long long)p.Cout * ct;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (j < nj) {
+              float o = v[j];
+              if (EPI == 2) {
+                o = fmaf(o, 1.f + __ldg(gp), __ldg(gp + beta_off));
+                if (p.res) o += __ldg(rp);
+              } else if (EPI == 1) {
+                o += __ldg(rp);
+              }
+              if (ACT == TDVC_ACT_LRELU) o = o > 0.f ? o : o * p.out_slope;
+              else if (ACT == TDVC_ACT_TANH) o = tanhf(o);
+              if (!(p.debug & 1)) *yp = o;
+            }
+            yp += ct; rp += ct; gp += ct;
+          }
+        } else {
+          // packed output: this thread owns 16 consecutive channels of one time step = 32 contiguous bytes
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float o = v[j];
+            if (ACT == TDVC_ACT_LRELU) o = o > 0.f ? o : o * p.out_slope;
+            v[j] = (j < nj) ? o : 0.f;
+          }
+          __nv_bfloat16* op = p.yp + ((long long)b * p.tp_out + t + p.out_halo) * p.cp_out + p.out_ch_off +
+                              grp * p.out_ch_stride + n0 + c0;
+          uint32_t w[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            w[j] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          if (!(p.debug & 1)) {
+            reinterpret_cast<uint4*>(op)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            reinterpret_cast<uint4*>(op)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+          }
         }
       }
     }
@@ -254,6 +301,7 @@ struct WgTcP {
   int B, Tout, Cout, Cin, K, dil, t_off;
   int KT, NT, nb, ntap_groups, n_ntiles, stages, tmem_cols, nchunk_t, units, splits;
   int Mp, Np;     // padded ci / co extents of the workspace
+  int x_ch_off, dy_ch_off;   // first channel of this conv's slice inside the packed operands
   float* ws;
 };
 
@@ -323,11 +371,11 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_wgrad_k(const __grid_const
           mbar_expect_tx(&full_bar[s], (uint32_t)(ntaps * a_tap_bytes + b_bytes));
           for (int tp = 0; tp < ntaps; ++tp) {
             const int tx = tc + (tap0 + tp) * p.dil + p.t_off;
-            tma_load_3d(sa + tp * a_tap_bytes, &map_x, &full_bar[s], ci0, tx, b);
-            tma_load_3d(sa + tp * a_tap_bytes + WG_BOX_BYTES, &map_x, &full_bar[s], ci0 + 64, tx, b);
+            tma_load_3d(sa + tp * a_tap_bytes, &map_x, &full_bar[s], p.x_ch_off + ci0, tx, b);
+            tma_load_3d(sa + tp * a_tap_bytes + WG_BOX_BYTES, &map_x, &full_bar[s], p.x_ch_off + ci0 + 64, tx, b);
           }
           for (int j = 0; j < p.nb; ++j)
-            tma_load_3d(sa + p.KT * a_tap_bytes + j * WG_BOX_BYTES, &map_dy, &full_bar[s], n0 + 64 * j, tc, b);
+            tma_load_3d(sa + p.KT * a_tap_bytes + j * WG_BOX_BYTES, &map_dy, &full_bar[s], p.dy_ch_off + n0 + 64 * j, tc, b);
         }
       }
     } else if (warp == 1) {
@@ -399,7 +447,8 @@ __global__ void wgrad_finalize_k(const float* __restrict__ ws, float* __restrict
 constexpr int PACK_STRIP = 8;   // 32-step time tiles per CTA
 
 __global__ void pack_cl_bf16_k(const float* __restrict__ x, __nv_bfloat16* __restrict__ xp, int C, int T, int Cp, int Tp,
-                               int halo, int pad_mode, float slope, float* __restrict__ chan_sum) {
+                               int halo, int pad_mode, float slope, float* __restrict__ chan_sum, int c_off, int Cw,
+                               int ones_ch) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int c0 = blockIdx.y * 32;
@@ -432,7 +481,11 @@ __global__ void pack_cl_bf16_k(const float* __restrict__ x, __nv_bfloat16* __res
     for (int r = 0; r < 4; ++r) {
       const int ty = threadIdx.y + 8 * r;
       const int tp = tp0 + ty, c = c0 + threadIdx.x;
-      if (tp < Tp && c < Cp) xp[((long long)b * Tp + tp) * Cp + c] = __float2bfloat16(tile[threadIdx.x][ty]);
+      if (tp < Tp && c < Cw) {
+        float o = tile[threadIdx.x][ty];
+        if (c == ones_ch) o = (tp >= halo && tp < halo + T) ? 1.f : 0.f;   // constant-one channel: bias grad via wgrad
+        xp[((long long)b * Tp + tp) * Cp + c_off + c] = __float2bfloat16(o);
+      }
     }
     __syncthreads();
   }
@@ -447,8 +500,9 @@ __global__ void pack_cl_bf16_k(const float* __restrict__ x, __nv_bfloat16* __res
 }
 
 __global__ void pack_weight_bf16_k(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int Cout, int Cin, int K,
-                                   int Rp, int Qp, int transpose_flip) {
-  // output [K][Rp][Qp]; plain: R = co, Q = ci; transpose_flip: R = ci, Q = co, tap reversed
+                                   int Rp, int Qp, int transpose_flip, int R_total, int r_off, int Q_total, int q_off) {
+  // writes the [K][Rp][Qp] block at (r_off, q_off) of wp[K][R_total][Q_total]
+  // plain: R = co, Q = ci; transpose_flip: R = ci, Q = co, taps reversed
   long long n = (long long)K * Rp * Qp;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     int qq = (int)(i % Qp);
@@ -458,7 +512,7 @@ __global__ void pack_weight_bf16_k(const float* __restrict__ w, __nv_bfloat16* _
     int co = transpose_flip ? qq : rr, ci = transpose_flip ? rr : qq;
     int ks = transpose_flip ? K - 1 - k : k;
     float v = (co < Cout && ci < Cin) ? w[((long long)co * Cin + ci) * K + ks] : 0.f;
-    wp[i] = __float2bfloat16(v);
+    wp[((long long)k * R_total + r_off + rr) * Q_total + q_off + qq] = __float2bfloat16(v);
   }
 }
 
@@ -497,45 +551,73 @@ static int make_map_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d
 using namespace tdvc;
 
 extern "C" int tdvc_pack_cl_bf16(const float* x, void* xp, int B, int C, int T, int Cp, int halo, int pad_mode,
-                                 float in_slope, float* chan_sum, void* stream) {
-  TDVC_CHECK_ARG(B >= 0 && C > 0 && T > 0 && Cp >= C && Cp % 8 == 0 && halo >= 0 && x && xp);
+                                 float in_slope, float* chan_sum, int c_off, int Cw, int ones_ch, void* stream) {
+  if (Cw <= 0) Cw = Cp - c_off;
+  TDVC_CHECK_ARG(B >= 0 && C > 0 && T > 0 && Cw >= C && c_off >= 0 && c_off + Cw <= Cp && Cp % 8 == 0 && halo >= 0 && x && xp);
+  TDVC_CHECK_ARG(ones_ch < 0 || (ones_ch >= C && ones_ch < Cw));
   if (pad_mode == TDVC_PAD_REFLECT) TDVC_CHECK_ARG(halo < T);
   if (chan_sum) TDVC_CUDA(cudaMemsetAsync(chan_sum, 0, sizeof(float) * C, (cudaStream_t)stream));
   if (B == 0) return TDVC_OK;
   int Tp = T + 2 * halo;
-  dim3 grid(cdiv(Tp, 32 * PACK_STRIP), cdiv(Cp, 32), B);
+  dim3 grid(cdiv(Tp, 32 * PACK_STRIP), cdiv(Cw, 32), B);
   TDVC_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535);
-  pack_cl_bf16_k<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)xp, C, T, Cp, Tp, halo, pad_mode, in_slope, chan_sum);
+  pack_cl_bf16_k<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)xp, C, T, Cp, Tp, halo, pad_mode, in_slope, chan_sum, c_off, Cw,
+                                                                   ones_ch);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
 
 extern "C" int tdvc_pack_weight_bf16(const float* w, void* wp, int Cout, int Cin, int K, int Coutp, int Cinp,
-                                     int transpose_flip, void* stream) {
+                                     int transpose_flip, int R_total, int r_off, int Q_total, int q_off, void* stream) {
   TDVC_CHECK_ARG(Cout > 0 && Cin > 0 && K > 0 && Coutp >= Cout && Cinp >= Cin && w && wp);
   int Rp = transpose_flip ? Cinp : Coutp, Qp = transpose_flip ? Coutp : Cinp;
+  if (R_total <= 0) { R_total = Rp; r_off = 0; }
+  if (Q_total <= 0) { Q_total = Qp; q_off = 0; }
+  TDVC_CHECK_ARG(r_off >= 0 && q_off >= 0 && r_off + Rp <= R_total && q_off + Qp <= Q_total);
   long long n = (long long)K * Rp * Qp;
   int blocks = (int)std::min<long long>((n + 255) / 256, 8LL * num_sms());
-  pack_weight_bf16_k<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)wp, Cout, Cin, K, Rp, Qp, transpose_flip);
+  pack_weight_bf16_k<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)wp, Cout, Cin, K, Rp, Qp, transpose_flip, R_total,
+                                                                       r_off, Q_total, q_off);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
 
-extern "C" int tdvc_conv1d_tc_fwd(const void* xp, const void* wp, const float* bias, const float* gb, const float* residual,
-                                  float* y, int B, int Cinp, int Tp, int Cout, int Coutp, int Tout, int K, int dilation,
-                                  int t_off, int out_act, float out_slope, void* stream) {
-  TDVC_CHECK_ARG(xp && wp && y && B >= 0 && Cinp > 0 && Cinp % 8 == 0 && Tp > 0 && Cout > 0 && Coutp >= Cout &&
-                 Coutp % 16 == 0 && Tout > 0 && K > 0 && dilation > 0);
-  TDVC_CHECK_ARG(((uintptr_t)xp % 16 == 0) && ((uintptr_t)wp % 16 == 0));
-  if (B == 0) return TDVC_OK;
+extern "C" int tdvc_conv1d_tc_fwd_ex(const tdvc_tc_conv* c, void* stream) {
+  TDVC_CHECK_ARG(c && c->xp && c->wp && c->B >= 0 && c->Tp > 0 && c->Tout > 0 && c->K > 0 && c->dilation > 0);
+  TDVC_CHECK_ARG(c->groups >= 1 && c->Cp_total % 8 == 0 && c->Cinp_g % 8 == 0 && c->Cinp_g > 0);
+  TDVC_CHECK_ARG(c->Cout_g > 0 && c->Coutp_g >= c->Cout_g && c->Coutp_g % 16 == 0);
+  TDVC_CHECK_ARG(((uintptr_t)c->xp % 16 == 0) && ((uintptr_t)c->wp % 16 == 0));
+  TDVC_CHECK_ARG(c->a_ch_off % 8 == 0 && c->a_ch_stride % 8 == 0);
+  TDVC_CHECK_ARG(c->out_act >= 0 && c->out_act <= 2);
+  if (c->out_packed) {
+    TDVC_CHECK_ARG(c->yp && c->cp_out % 8 == 0 && c->out_ch_off % 16 == 0 && c->out_ch_stride % 16 == 0 &&
+                   ((uintptr_t)c->yp % 16 == 0) && c->out_act != TDVC_ACT_TANH && !c->gb && !c->residual);
+    // every 16-channel chunk a thread stores must lie inside the row
+    TDVC_CHECK_ARG(c->out_ch_off + (c->groups - 1) * c->out_ch_stride + c->Coutp_g <= c->cp_out);
+  } else {
+    TDVC_CHECK_ARG(c->y != nullptr);
+    if (c->groups > 1) TDVC_CHECK_ARG(!c->gb && !c->residual);
+  }
+  if (c->maskp) {
+    TDVC_CHECK_ARG(c->cm % 8 == 0 && c->mask_ch_off % 16 == 0 && c->mask_ch_stride % 16 == 0 && ((uintptr_t)c->maskp % 16 == 0));
+    TDVC_CHECK_ARG(c->mask_ch_off + (c->groups - 1) * c->mask_ch_stride + c->Coutp_g <= c->cm);
+    TDVC_CHECK_ARG(!c->gb && !c->residual && c->out_act == TDVC_ACT_NONE);
+  }
+  if (c->B == 0) return TDVC_OK;
   TcP p{};
-  p.B = B; p.Tout = Tout; p.Cout = Cout; p.K = K; p.dil = dilation; p.t_off = t_off;
-  p.nchunk = cdiv(Cinp, TC_BK);
-  int rem = Cinp - (p.nchunk - 1) * TC_BK;
+  p.B = c->B; p.Tout = c->Tout; p.Cout = c->Cout_g; p.K = c->K; p.dil = c->dilation; p.t_off = c->t_off;
+  p.nchunk = cdiv(c->Cinp_g, TC_BK);
+  int rem = c->Cinp_g - (p.nchunk - 1) * TC_BK;
   p.last_nk16 = cdiv(rem, 16);
-  // N tile: whole (padded) Cout when it fits one MMA, else 256/128-wide tiles
-  p.BN = Coutp <= 256 ? Coutp : (Coutp % 256 == 0 ? 256 : 128);
-  TDVC_CHECK_ARG(Coutp % p.BN == 0);
+  // N tile: the widest multiple of 16 up to 256 that divides the padded per-group width
+  int bn = 0;
+  for (int cand = std::min(c->Coutp_g, 256); cand >= 16; cand -= 16)
+    if (c->Coutp_g % cand == 0) { bn = cand; break; }
+  TDVC_CHECK_ARG(bn >= 16);
+  p.BN = bn;
+  p.tiles_per_group = c->Coutp_g / bn;
+  p.coutp_g = c->Coutp_g;
+  p.a_ch_off = c->a_ch_off; p.a_ch_stride = c->a_ch_stride; p.bias_stride = c->bias_stride;
   int cols = 32;
   while (cols < p.BN) cols <<= 1;
   p.tmem_cols = cols;
@@ -544,10 +626,14 @@ extern "C" int tdvc_conv1d_tc_fwd(const void* xp, const void* wp, const float* b
   int stages = (int)((100 * 1024) / stage_bytes);
   stages = std::max(stages, 2);
   stages = std::min(stages, 6);
-  stages = std::min(stages, K * p.nchunk);
+  stages = std::min(stages, c->K * p.nchunk);
   stages = std::max(stages, 1);
   p.stages = stages;
-  p.out_act = out_act; p.out_slope = out_slope; p.bias = bias; p.gb = gb; p.res = residual; p.y = y;
+  p.out_act = c->out_act; p.out_slope = c->out_slope; p.bias = c->bias; p.gb = c->gb; p.res = c->residual; p.y = c->y;
+  p.yp = (__nv_bfloat16*)c->yp; p.tp_out = c->tp_out; p.cp_out = c->cp_out; p.out_halo = c->out_halo;
+  p.out_ch_off = c->out_ch_off; p.out_ch_stride = c->out_ch_stride;
+  p.maskp = (const __nv_bfloat16*)c->maskp; p.tm = c->tm; p.cm = c->cm; p.mask_halo = c->mask_halo;
+  p.mask_ch_off = c->mask_ch_off; p.mask_ch_stride = c->mask_ch_stride; p.mask_slope = c->mask_slope;
   {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("TDVC_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
@@ -555,28 +641,46 @@ extern "C" int tdvc_conv1d_tc_fwd(const void* xp, const void* wp, const float* b
   }
   size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, TcP);
-  static const KernelFn table[3][3] = {
-      {conv_tc_fwd_k<0, 0>, conv_tc_fwd_k<0, 1>, conv_tc_fwd_k<0, 2>},
-      {conv_tc_fwd_k<1, 0>, conv_tc_fwd_k<1, 1>, conv_tc_fwd_k<1, 2>},
-      {conv_tc_fwd_k<2, 0>, conv_tc_fwd_k<2, 1>, conv_tc_fwd_k<2, 2>}};
-  TDVC_CHECK_ARG(out_act >= 0 && out_act <= 2);
-  const int epi = gb ? 2 : (residual ? 1 : 0);
-  KernelFn kern = table[out_act][epi];
-  static bool configured[3][3] = {};
-  if (!configured[out_act][epi]) {
-    TDVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured[out_act][epi] = true;
+  KernelFn kern = nullptr;
+  const int epi = c->gb ? 2 : (c->residual ? 1 : 0);
+  const int act = c->out_act;
+  const bool mask = c->maskp != nullptr;
+  if (!c->out_packed && !mask) {
+    static const KernelFn table[3][3] = {
+        {conv_tc_fwd_k<0, 0, 0, 0>, conv_tc_fwd_k<0, 1, 0, 0>, conv_tc_fwd_k<0, 2, 0, 0>},
+        {conv_tc_fwd_k<1, 0, 0, 0>, conv_tc_fwd_k<1, 1, 0, 0>, conv_tc_fwd_k<1, 2, 0, 0>},
+        {conv_tc_fwd_k<2, 0, 0, 0>, conv_tc_fwd_k<2, 1, 0, 0>, conv_tc_fwd_k<2, 2, 0, 0>}};
+    kern = table[act][epi];
+  } else if (!c->out_packed && mask) {
+    kern = conv_tc_fwd_k<0, 0, 0, 1>;
+  } else if (c->out_packed && !mask) {
+    kern = act == TDVC_ACT_LRELU ? conv_tc_fwd_k<1, 0, 1, 0> : conv_tc_fwd_k<0, 0, 1, 0>;
+  } else {
+    kern = conv_tc_fwd_k<0, 0, 1, 1>;
   }
+  TDVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CUtensorMap map_a, map_b;
-  int rc = make_map_3d(&map_a, xp, (uint64_t)Cinp, (uint64_t)Tp, (uint64_t)B, TC_BK, TC_BM);
+  int rc = make_map_3d(&map_a, c->xp, (uint64_t)c->Cp_total, (uint64_t)c->Tp, (uint64_t)c->B, TC_BK, TC_BM);
   if (rc) return rc;
-  rc = make_map_3d(&map_b, wp, (uint64_t)Cinp, (uint64_t)Coutp, (uint64_t)K, TC_BK, (uint32_t)p.BN);
+  rc = make_map_3d(&map_b, c->wp, (uint64_t)c->Cinp_g, (uint64_t)c->groups * c->Coutp_g, (uint64_t)c->K, TC_BK, (uint32_t)p.BN);
   if (rc) return rc;
-  dim3 grid(cdiv(Tout, TC_BM), Coutp / p.BN, B);
+  dim3 grid(cdiv(c->Tout, TC_BM), c->groups * p.tiles_per_group, c->B);
   TDVC_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535);
   kern<<<grid, TC_FWD_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
+}
+
+extern "C" int tdvc_conv1d_tc_fwd(const void* xp, const void* wp, const float* bias, const float* gb, const float* residual,
+                                  float* y, int B, int Cinp, int Tp, int Cout, int Coutp, int Tout, int K, int dilation,
+                                  int t_off, int out_act, float out_slope, void* stream) {
+  tdvc_tc_conv c{};
+  c.xp = xp; c.wp = wp; c.bias = bias; c.gb = gb; c.residual = residual; c.y = y;
+  c.B = B; c.Tp = Tp; c.Tout = Tout; c.K = K; c.dilation = dilation; c.t_off = t_off;
+  c.Cp_total = Cinp; c.groups = 1; c.a_ch_off = 0; c.a_ch_stride = 0; c.Cinp_g = Cinp;
+  c.Cout_g = Cout; c.Coutp_g = Coutp; c.bias_stride = 0;
+  c.out_act = out_act; c.out_slope = out_slope;
+  return tdvc_conv1d_tc_fwd_ex(&c, stream);
 }
 
 // workspace (floats) for tdvc_conv1d_tc_wgrad
@@ -588,12 +692,14 @@ extern "C" int64_t tdvc_conv1d_tc_wgrad_ws(int Cout, int Cin, int K) {
 // dw[Cout,Cin,K] (OVERWRITTEN) from the packed operands: dyp[B,Tout,Cdp] and xp[B,Tp,Cp] (both bf16 channels-last;
 // xp row = t + tap*dilation + t_off).
 extern "C" int tdvc_conv1d_tc_wgrad(const void* dyp, const void* xp, float* dw, float* ws, int B, int Cdp, int Tout, int Cp,
-                                    int Tp, int Cout, int Cin, int K, int dilation, int t_off, void* stream) {
-  TDVC_CHECK_ARG(dyp && xp && dw && ws && B >= 0 && Cdp % 8 == 0 && Cp % 8 == 0 && Cdp >= Cout && Cp >= Cin && Tout > 0 &&
-                 Tp > 0 && K > 0 && dilation > 0);
+                                    int Tp, int Cout, int Cin, int K, int dilation, int t_off, int x_ch_off,
+                                    int dy_ch_off, void* stream) {
+  TDVC_CHECK_ARG(dyp && xp && dw && ws && B >= 0 && Cdp % 8 == 0 && Cp % 8 == 0 && dy_ch_off >= 0 && x_ch_off >= 0 &&
+                 Cdp >= dy_ch_off + Cout && Cp >= x_ch_off + Cin && Tout > 0 && Tp > 0 && K > 0 && dilation > 0);
   cudaStream_t st = (cudaStream_t)stream;
   WgTcP p{};
   p.B = B; p.Tout = Tout; p.Cout = Cout; p.Cin = Cin; p.K = K; p.dil = dilation; p.t_off = t_off; p.ws = ws;
+  p.x_ch_off = x_ch_off; p.dy_ch_off = dy_ch_off;
   p.Mp = ((Cin + 127) / 128) * 128;
   p.Np = ((Cout + 15) / 16) * 16;
   TDVC_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * (size_t)K * p.Np * p.Mp, st));

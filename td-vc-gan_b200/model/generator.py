@@ -165,9 +165,13 @@ class FiLMResnetBlock(nn.Module):
                 Conv1d(nc, n_channel * 2, kernel_size=3, padding='same', weight_norm=wn))
         self.shortcut = Identity()
 
-    def forward(self, x, c=None):
+    def forward(self, x, c=None, gb=None):
+        """`gb`: gamma|beta already computed for this block by the stage-level fused conditioning path
+        (MRFBlock.forward); otherwise cond_var runs here."""
         h = self.conv[1](x, in_slope=self.conv[0].negative_slope)
-        if c is not None:
+        if gb is not None:
+            h = ops.film(h, gb)
+        elif c is not None:
             if c.ndim == 2:
                 # the reference dereferences an attribute that is never defined here (generator.py:100)
                 raise AttributeError("'FiLMResnetBlock' object has no attribute 'cond'")
@@ -258,12 +262,32 @@ class MRFBlock(nn.Module):
                 self.blocks[i].append(FiLMResnetBlock(n_channel, n_cond_const, n_cond_var, dilation, kernel_size,
                                                       leaky_relu_slope, weight_norm))
 
+    def _fused_cond(self, c):
+        """All blocks' gamma|beta from one grouped tensor-core pass over c (bf16 mode), or None."""
+        if c is None or c.ndim != 3 or not self.has_cond:
+            return None
+        mods = [m for block in self.blocks for m in block]
+        cv0 = mods[0].cond_var[0]
+        if not ops.mrf_cond_path_eligible(c.shape[1], mods[0].cond_var[2].out_channels, c.shape[2]):
+            return None
+        if cv0.kernel_size != 3 or cv0.in_channels != c.shape[1]:
+            return None
+        wb = [(m.cond_var[0].effective_weight(), m.cond_var[0].bias, m.cond_var[2].effective_weight(), m.cond_var[2].bias)
+              for m in mods]
+        return ops.mrf_cond_path(c, wb, slope=mods[0].cond_var[1].negative_slope)
+
     def forward(self, x, c=None):
         outs = []
+        gbs = self._fused_cond(c)
+        i = 0
         for block in self.blocks:
             xs = x
             for mod in block:
-                xs = mod(xs, c)
+                if gbs is not None:
+                    xs = mod(xs, None, gb=gbs[i])
+                else:
+                    xs = mod(xs, c)
+                i += 1
             outs.append(xs)
         n = len(outs)
         if n <= 3:

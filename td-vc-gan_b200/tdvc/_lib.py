@@ -22,6 +22,18 @@ class ConvGeom(C.Structure):
                 ("in_slope", C.c_float), ("out_act", C.c_int32), ("out_slope", C.c_float)]
 
 
+class TcConv(C.Structure):
+    """struct tdvc_tc_conv"""
+    _fields_ = [("xp", C.c_void_p), ("wp", C.c_void_p), ("bias", C.c_void_p), ("gb", C.c_void_p),
+                ("residual", C.c_void_p), ("y", C.c_void_p), ("yp", C.c_void_p), ("maskp", C.c_void_p)] + \
+               [(n, C.c_int32) for n in ("B", "Tp", "Tout", "K", "dilation", "t_off", "Cp_total", "groups", "a_ch_off",
+                                         "a_ch_stride", "Cinp_g", "Cout_g", "Coutp_g", "bias_stride", "out_act")] + \
+               [("out_slope", C.c_float)] + \
+               [(n, C.c_int32) for n in ("out_packed", "tp_out", "cp_out", "out_halo", "out_ch_off", "out_ch_stride",
+                                         "tm", "cm", "mask_halo", "mask_ch_off", "mask_ch_stride")] + \
+               [("mask_slope", C.c_float)]
+
+
 PAD_ZEROS, PAD_REFLECT = 0, 1
 ACT_NONE, ACT_LRELU, ACT_TANH = 0, 1, 2
 
@@ -66,10 +78,11 @@ SIGNATURES = {
     "tdvc_abs_diff_sum": (_I, [_P, _P, _F, _P, _L, _P]),
     "tdvc_abs_diff_bwd": (_I, [_P, _P, _F, _P, _P, _L, _P]),
     "tdvc_adamw_multi": (_I, [_P, _P, _P, _P, _P, _I, _L, _F, _F, _F, _F, _F, _I, _F, _P, _P]),
-    "tdvc_pack_cl_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P]),
-    "tdvc_pack_weight_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "tdvc_pack_cl_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _I, _I, _I, _P]),
+    "tdvc_pack_weight_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "tdvc_conv1d_tc_wgrad_ws": (_L, [_I, _I, _I]),
-    "tdvc_conv1d_tc_wgrad": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "tdvc_conv1d_tc_wgrad": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "tdvc_conv1d_tc_fwd_ex": (_I, [C.POINTER(TcConv), _P]),
     "tdvc_conv1d_tc_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P]),
 }
 

@@ -594,8 +594,8 @@ def _pack_act(x, Cp, halo, pad_mode, slope, cache=True, chan_sum=None):
         if hit is not None:
             return hit
     xp = torch.empty(B, T + 2 * halo, Cp, device=x.device, dtype=torch.bfloat16)
-    _lib.check(_lib.load().tdvc_pack_cl_bf16(_p(x), _p(xp), B, Cc, T, Cp, halo, pad_mode, slope, _p(chan_sum), _st()),
-               "pack_cl_bf16")
+    _lib.check(_lib.load().tdvc_pack_cl_bf16(_p(x), _p(xp), B, Cc, T, Cp, halo, pad_mode, slope, _p(chan_sum), 0, 0, -1,
+                                             _st()), "pack_cl_bf16")
     if cache:
         _pack_cache.put(key, x, xp)
     return xp
@@ -605,8 +605,8 @@ def _pack_w(w, rows_p, cols_p, transpose_flip):
     Cout, Cin, K = w.shape
     wp = torch.empty(K, rows_p, cols_p, device=w.device, dtype=torch.bfloat16)
     coutp, cinp = (cols_p, rows_p) if transpose_flip else (rows_p, cols_p)
-    _lib.check(_lib.load().tdvc_pack_weight_bf16(_p(w), _p(wp), Cout, Cin, K, coutp, cinp, int(transpose_flip), _st()),
-               "pack_weight_bf16")
+    _lib.check(_lib.load().tdvc_pack_weight_bf16(_p(w), _p(wp), Cout, Cin, K, coutp, cinp, int(transpose_flip), 0, 0, 0, 0,
+                                                 _st()), "pack_weight_bf16")
     return wp
 
 
@@ -688,9 +688,152 @@ class _Conv1dTC(torch.autograd.Function):
             dw = torch.empty_like(w)
             ws = torch.empty(lib.tdvc_conv1d_tc_wgrad_ws(Cout, Cin, K), device=x.device, dtype=torch.float32)
             _lib.check(lib.tdvc_conv1d_tc_wgrad(_p(dyp), _p(xp), _p(dw), _p(ws), B, Cdp, Tout, xp.shape[2], xp.shape[1],
-                                                Cout, Cin, K, dilation, halo - pad, _st()), "conv1d_tc_wgrad")
+                                                Cout, Cin, K, dilation, halo - pad, 0, 0, _st()), "conv1d_tc_wgrad")
         if need_b:
             db = torch.empty(Cout, device=x.device, dtype=torch.float32)
             _lib.check(lib.tdvc_bias_grad(_p(dy), _p(db), B, Cout, Tout, _st()), "bias_grad")
         dres = dy if (ctx.has_res and ctx.needs_input_grad[3]) else None
         return dx, dw, db, dres, None, None, None, None, None, None
+
+
+# ----------------------------------------------------------------------------- fused FiLM conditioning path
+
+def _tc_conv(**kw):
+    c = _lib.TcConv()
+    for k, v in kw.items():
+        setattr(c, k, v.data_ptr() if torch.is_tensor(v) else v)
+    _lib.check(_lib.load().tdvc_conv1d_tc_fwd_ex(C.byref(c), _st()), "conv1d_tc_fwd_ex")
+
+
+class _MRFCondPath(torch.autograd.Function):
+    """(gamma|beta)_j = cond_var_j[2](leaky_relu(cond_var_j[0](c)))  for all n FiLM blocks of one MRF stage
+    (model/generator.py:85-92,102), which all read the same conditioning tensor c[B, Cc, T]:
+
+      forward   1 pack of c, ONE tcgen05 launch for the n `cond_var.0` convs (N = n*144) whose epilogue applies bias +
+                LeakyReLU and writes the next conv's bf16 channels-last operand directly, ONE grouped launch for the n
+                `cond_var.2` convs -> gb[n, B, 2C, T] fp32.
+      backward  n packs of dL/dgb (they also give cond_var.2's bias gradients), one grouped dgrad launch whose epilogue
+                applies the LeakyReLU mask and writes packed dL/dg1, n + 1 wgrad launches (the n `cond_var.0` weight
+                gradients are one GEMM; their bias gradients ride along through a constant-one input channel), and one
+                dgrad launch over the concatenated 1296 channels, which also sums the n blocks' contributions to dL/dc.
+    Intermediates never exist in fp32."""
+
+    @staticmethod
+    def forward(ctx, c, slope, *wb):
+        n = len(wb) // 4
+        w0s, b0s, w2s, b2s = wb[0::4], wb[1::4], wb[2::4], wb[3::4]
+        _req(c, *wb)
+        c = _c(c)
+        B, Cc, T = c.shape
+        K = w0s[0].shape[2]
+        C2 = w2s[0].shape[0]
+        if K != 3 or any(tuple(w.shape) != (Cc, Cc, 3) for w in w0s) or any(tuple(w.shape) != (C2, Cc, 3) for w in w2s):
+            raise RuntimeError("mrf_cond_path: unexpected cond_var geometry")
+        lib = _lib.load()
+        dev = c.device
+        Cg = _ceil(Cc + 1, 16)              # per-block channel pitch; channel Cc is the constant-one channel
+        C2p = _ceil(C2, 16)
+        # operands
+        cp = torch.empty(B, T, Cg, device=dev, dtype=torch.bfloat16)
+        _lib.check(lib.tdvc_pack_cl_bf16(_p(c), _p(cp), B, Cc, T, Cg, 0, PAD_ZEROS, 1.0, None, 0, Cg, Cc, _st()), "pack c")
+        w0p = torch.empty(K, n * Cg, Cg, device=dev, dtype=torch.bfloat16)
+        w2p = torch.empty(K, n * C2p, Cg, device=dev, dtype=torch.bfloat16)
+        b0p = torch.zeros(n * Cg, device=dev, dtype=torch.float32)
+        b2p = torch.zeros(n * C2p, device=dev, dtype=torch.float32)
+        for j in range(n):
+            w0, w2 = _c(w0s[j]), _c(w2s[j])
+            _lib.check(lib.tdvc_pack_weight_bf16(_p(w0), _p(w0p), Cc, Cc, K, Cg, Cg, 0, n * Cg, j * Cg, Cg, 0, _st()), "pack w0")
+            _lib.check(lib.tdvc_pack_weight_bf16(_p(w2), _p(w2p), C2, Cc, K, C2p, Cg, 0, n * C2p, j * C2p, Cg, 0, _st()), "pack w2")
+            if b0s[j] is not None:
+                b0p[j * Cg:j * Cg + Cc].copy_(b0s[j])
+            if b2s[j] is not None:
+                b2p[j * C2p:j * C2p + C2].copy_(b2s[j])
+        # all cond_var.0 convs: packed bf16 output g1p[B, T, n*Cg] = leaky_relu(conv + bias)
+        g1p = torch.empty(B, T, n * Cg, device=dev, dtype=torch.bfloat16)
+        _tc_conv(xp=cp, wp=w0p, bias=b0p, B=B, Tp=T, Tout=T, K=K, dilation=1, t_off=-1, Cp_total=Cg, groups=1,
+                 a_ch_off=0, a_ch_stride=0, Cinp_g=Cg, Cout_g=n * Cg, Coutp_g=n * Cg, bias_stride=0,
+                 out_act=ACT_LRELU, out_slope=slope, out_packed=1, yp=g1p, tp_out=T, cp_out=n * Cg, out_halo=0,
+                 out_ch_off=0, out_ch_stride=0)
+        # all cond_var.2 convs, grouped: gb[n, B, 2C, T]
+        gb = torch.empty(n, B, C2, T, device=dev, dtype=torch.float32)
+        _tc_conv(xp=g1p, wp=w2p, bias=b2p, y=gb, B=B, Tp=T, Tout=T, K=K, dilation=1, t_off=-1, Cp_total=n * Cg, groups=n,
+                 a_ch_off=0, a_ch_stride=Cg, Cinp_g=Cg, Cout_g=C2, Coutp_g=C2p, bias_stride=C2p, out_act=ACT_NONE,
+                 out_slope=1.0, out_packed=0)
+        ctx.dims = (n, B, Cc, T, K, C2, Cg, C2p, slope)
+        ctx.has_b0 = [b is not None for b in b0s]
+        ctx.has_b2 = [b is not None for b in b2s]
+        ctx.save_for_backward(cp, g1p, *[_c(w) for w in w0s], *[_c(w) for w in w2s])
+        return tuple(gb[j] for j in range(n))
+
+    @staticmethod
+    def backward(ctx, *dgb):
+        n, B, Cc, T, K, C2, Cg, C2p, slope = ctx.dims
+        saved = ctx.saved_tensors
+        cp, g1p = saved[0], saved[1]
+        w0s, w2s = saved[2:2 + n], saved[2 + n:2 + 2 * n]
+        lib = _lib.load()
+        dev = cp.device
+        # dL/dgb -> packed bf16 (+ cond_var.2 bias gradients)
+        dgbp = torch.empty(B, T, n * C2p, device=dev, dtype=torch.bfloat16)
+        db2 = torch.zeros(n, C2, device=dev, dtype=torch.float32)
+        for j in range(n):
+            if dgb[j] is None:
+                dgbp[:, :, j * C2p:(j + 1) * C2p].zero_()
+                continue
+            d = _c(dgb[j])
+            _lib.check(lib.tdvc_pack_cl_bf16(_p(d), _p(dgbp), B, C2, T, n * C2p, 0, PAD_ZEROS, 1.0, _p(db2[j]), j * C2p, C2p,
+                                             -1, _st()), "pack dgb")
+        # cond_var.2 weight gradients
+        dw2 = []
+        ws = torch.empty(max(lib.tdvc_conv1d_tc_wgrad_ws(C2, Cc, K), lib.tdvc_conv1d_tc_wgrad_ws(n * Cg, Cc + 1, K)),
+                         device=dev, dtype=torch.float32)
+        for j in range(n):
+            g = torch.empty(C2, Cc, K, device=dev, dtype=torch.float32)
+            _lib.check(lib.tdvc_conv1d_tc_wgrad(_p(dgbp), _p(g1p), _p(g), _p(ws), B, n * C2p, T, n * Cg, T, C2, Cc, K, 1, -1,
+                                                j * Cg, j * C2p, _st()), "wgrad cond_var.2")
+            dw2.append(g)
+        # dL/dg1 (packed, LeakyReLU mask applied in the epilogue): grouped dgrad of cond_var.2
+        w2tp = torch.empty(K, n * Cg, C2p, device=dev, dtype=torch.bfloat16)
+        w0tp = torch.empty(K, Cg, n * Cg, device=dev, dtype=torch.bfloat16)
+        for j in range(n):
+            _lib.check(lib.tdvc_pack_weight_bf16(_p(w2s[j]), _p(w2tp), C2, Cc, K, C2p, Cg, 1, n * Cg, j * Cg, C2p, 0, _st()),
+                       "pack w2^T")
+            _lib.check(lib.tdvc_pack_weight_bf16(_p(w0s[j]), _p(w0tp), Cc, Cc, K, Cg, Cg, 1, Cg, 0, n * Cg, j * Cg, _st()),
+                       "pack w0^T")
+        dg1p = torch.empty(B, T, n * Cg, device=dev, dtype=torch.bfloat16)
+        _tc_conv(xp=dgbp, wp=w2tp, B=B, Tp=T, Tout=T, K=K, dilation=1, t_off=-1, Cp_total=n * C2p, groups=n, a_ch_off=0,
+                 a_ch_stride=C2p, Cinp_g=C2p, Cout_g=Cg, Coutp_g=Cg, bias_stride=0, out_act=ACT_NONE, out_slope=1.0,
+                 out_packed=1, yp=dg1p, tp_out=T, cp_out=n * Cg, out_halo=0, out_ch_off=0, out_ch_stride=Cg,
+                 maskp=g1p, tm=T, cm=n * Cg, mask_halo=0, mask_ch_off=0, mask_ch_stride=Cg, mask_slope=slope)
+        # cond_var.0 weight (+ bias, through the constant-one channel of cp) gradients: one GEMM for all blocks
+        dw0_all = torch.empty(n * Cg, Cc + 1, K, device=dev, dtype=torch.float32)
+        _lib.check(lib.tdvc_conv1d_tc_wgrad(_p(dg1p), _p(cp), _p(dw0_all), _p(ws), B, n * Cg, T, Cg, T, n * Cg, Cc + 1, K, 1,
+                                            -1, 0, 0, _st()), "wgrad cond_var.0")
+        # dL/dc: one conv over the n*Cg concatenated channels (sums the blocks' contributions in the GEMM)
+        dc = None
+        if ctx.needs_input_grad[0]:
+            dc = torch.empty(B, Cc, T, device=dev, dtype=torch.float32)
+            _tc_conv(xp=dg1p, wp=w0tp, y=dc, B=B, Tp=T, Tout=T, K=K, dilation=1, t_off=-1, Cp_total=n * Cg, groups=1,
+                     a_ch_off=0, a_ch_stride=0, Cinp_g=n * Cg, Cout_g=Cc, Coutp_g=Cg, bias_stride=0, out_act=ACT_NONE,
+                     out_slope=1.0, out_packed=0)
+        grads = []
+        for j in range(n):
+            blk = dw0_all[j * Cg:j * Cg + Cc]
+            grads.append(blk[:, :Cc, :].contiguous())
+            grads.append(blk[:, Cc, (K - 1) // 2].contiguous() if ctx.has_b0[j] else None)
+            grads.append(dw2[j])
+            grads.append(db2[j] if ctx.has_b2[j] else None)
+        return (dc, None, *grads)
+
+
+def mrf_cond_path(c, blocks_wb, slope=0.2):
+    """blocks_wb: [(w0, b0, w2, b2), ...] effective (weight-normed) cond_var weights of the FiLM blocks sharing c.
+    Returns the list of gamma|beta tensors [B, 2C, T], one per block."""
+    flat = []
+    for w0, b0, w2, b2 in blocks_wb:
+        flat += [w0, b0, w2, b2]
+    return list(_MRFCondPath.apply(c, float(slope), *flat))
+
+
+def mrf_cond_path_eligible(Cc, C2, T) -> bool:
+    return _PRECISION == "bf16" and Cc >= 16 and C2 >= 16 and _ceil(C2, 16) <= 256

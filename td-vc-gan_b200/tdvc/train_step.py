@@ -16,8 +16,7 @@ from tdvc import ops
 def label2onehot(labels: torch.Tensor, n_classes: int) -> torch.Tensor:
     """train.py:39-44, built on the labels' device."""
     out = torch.zeros(labels.shape[0], n_classes, device=labels.device, dtype=torch.float32)
-    out[torch.arange(labels.shape[0], device=labels.device), labels] = 1
-    return out
+    return out.scatter_(1, labels.view(-1, 1), 1.0)      # scalar-valued scatter: no host tensor, graph-capturable
 
 
 @contextlib.contextmanager

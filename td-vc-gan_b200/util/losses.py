@@ -85,7 +85,7 @@ def contrastive_loss(sig_X, sig_Y, num_negatives=100, temp=1, _raw_draws=None):
             else:
                 idx = torch.randint(low=0, high=T - 1, size=(B, T, num_negatives), device=X.device)
             own = torch.arange(T, device=X.device).unsqueeze(-1).expand(-1, num_negatives)
-            idx[idx >= own] += 1
+            idx = idx + (idx >= own).to(idx.dtype)      # skip self; mask-free form (no host sync, graph-capturable)
             return X.unsqueeze(2).expand(-1, -1, T, -1).gather(3, idx.unsqueeze(1).expand(-1, Cc, -1, -1))
 
     def logits(X, Y, negs):

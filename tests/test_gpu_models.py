@@ -257,11 +257,11 @@ def test_graphed_step_equals_eager_step():
         oG, oD = FusedAdamW(G.parameters(), 1e-3, (0.8, 0.99)), FusedAdamW(D.parameters(), 1e-3, (0.8, 0.99))
         ts = TrainStep(G, D, hp, oG, oD, cfg["nspk"])
         if graphed:
-            # capture performs 3 real (weight-updating) steps: 2 eager warm-ups + the captured one
+            # 2 eager warm-up steps inside the constructor (capture itself executes nothing) + 1 replay
             gs = GraphedTrainStep(ts, bd, warmup=2)
             out = gs.step()
         else:
-            for _ in range(4):
+            for _ in range(3):
                 out = ts.step(bd)
         torch.cuda.synchronize()
         results.append(({k: v.detach().clone() for k, v in G.state_dict().items()}, float(out["g_loss"]), float(out["d_loss"])))
