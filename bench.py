@@ -278,36 +278,73 @@ def run_ours(args):
 
 
 def dominant_kernel_roofline(dev, B, T, pk, args):
-    """The kernel that carries most of the step's FLOPs: FiLM `cond_var.0` (136->136, k=3, 'same') at the full-rate
-    decoder stage (143 of 465 GF of a G forward).  Timed alone with CUDA events on the current
-    stream, inputs 78 MB + outputs 78 MB per launch and 9 distinct weight sets cycled (L2 mostly cold for
-    activations).  achieved = algorithmic FLOPs / launch time vs the measured dense bf16 tensor-core peak."""
+    """The launch that carries most of the step's FLOPs: the 9 FiLM `cond_var.0` convolutions (136->136, k=3,
+    'same') of the full-rate decoder stage (143 of 465 GF of a G forward).  bf16 mode runs them as
+    ONE tcgen05 launch (N = 9*144) writing the packed bf16 operand of cond_var.2; fp32 mode as 9 CUDA-core launches.
+    Timed alone, CUDA events around a CUDA-graph replay of `reps` launches on the capturing stream (so no host
+    launch gaps); operands 41 MB in, 371 MB out per launch (> L2).  achieved = algorithmic FLOPs / launch time
+    against the measured dense bf16 tensor-core burst peak."""
     import torch
     from tdvc import ops
-    C = MODEL["cond_dim"] + 8
-    n_sets = 9
-    xs = [torch.randn(B, C, T, device=dev) for _ in range(3)]
-    ws = [torch.randn(C, C, 3, device=dev) * 0.05 for _ in range(n_sets)]
-    bs = [torch.zeros(C, device=dev) for _ in range(n_sets)]
+    from tdvc._lib import ACT_LRELU
+    Cc, n, K = MODEL["cond_dim"] + 8, 9, 3
+    flops = 2.0 * B * T * Cc * Cc * K * n
+    reps = 5
+    side = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
     with torch.no_grad():
-        for i in range(3):
-            ops.conv1d(xs[i % 3], ws[i], bs[i], padding=1)
+        if args.precision == "bf16":
+            Cg = 144
+            cp = (torch.randn(B, T, Cg, device=dev) * 0.5).to(torch.bfloat16)
+            w0p = (torch.randn(K, n * Cg, Cg, device=dev) * 0.05).to(torch.bfloat16)
+            b0p = torch.zeros(n * Cg, device=dev)
+            outs = [torch.empty(B, T, n * Cg, device=dev, dtype=torch.bfloat16) for _ in range(2)]
+
+            def launch(i):
+                ops._tc_conv(xp=cp, wp=w0p, bias=b0p, B=B, Tp=T, Tout=T, K=K, dilation=1, t_off=-1, Cp_total=Cg, groups=1,
+                             a_ch_off=0, a_ch_stride=0, Cinp_g=Cg, Cout_g=n * Cg, Coutp_g=n * Cg, bias_stride=0,
+                             out_act=ACT_LRELU, out_slope=0.2, out_packed=1, yp=outs[i % 2], tp_out=T, cp_out=n * Cg,
+                             out_halo=0, out_ch_off=0, out_ch_stride=0)
+            kname = "conv_tc_fwd_k<ACT=lrelu,EPI=0,OUT=packed,MASK=0> (tcgen05 bf16, 9 cond_var.0 convs in one launch)"
+            launches_per_rep = 1
+        else:
+            x = torch.randn(B, Cc, T, device=dev)
+            ws = [torch.randn(Cc, Cc, K, device=dev) * 0.05 for _ in range(n)]
+            bs = torch.zeros(Cc, device=dev)
+
+            def launch(i):
+                for w in ws:
+                    ops.conv1d(x, w, bs, padding=1)
+            kname = "conv_fwd_k<8,32> (fp32 CUDA cores, 9 launches)"
+            launches_per_rep = n
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            launch(0)
+            side.synchronize()
+            with torch.cuda.graph(g, stream=side):
+                for i in range(reps):
+                    launch(i)
         torch.cuda.synchronize()
-        reps = 18
+        g.replay()
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(reps):
-            ops.conv1d(xs[i % 3], ws[i % n_sets], bs[i % n_sets], padding=1)
+        g.replay()
         e1.record()
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    flops = 2.0 * B * T * C * C * 3
     ach = flops / (ms * 1e-3) / 1e12
     peak = pk["tc_burst"]
-    kname = "conv_fwd_k<8,32> (fp32 CUDA cores)" if args.precision == "fp32" else "conv_tc_fwd_k (tcgen05 bf16)"
+    traffic = None
+    try:   # per-launch DRAM bytes of this kernel from the committed ncu --set full capture, if present
+        with open(os.path.join(REPO, "profiles", "r1_dominant_kernel_ncu.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        pass
     return {"bound": "tensor", "achieved": round(ach, 3), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 5),
-            "traffic": None, "kernel": kname, "shape": f"B={B} Cin={C} Cout={C} K=3 T={T}",
-            "flops_per_launch": flops, "ms_per_launch": round(ms, 4),
+            "traffic": traffic, "kernel": kname, "shape": f"B={B} T={T} Cin={Cc} Cout={n}x{Cc} K={K}",
+            "flops_per_launch": flops / launches_per_rep, "ms_per_launch": round(ms / launches_per_rep, 4),
+            "algorithmic_bytes_per_launch": B * T * (Cc * 2 + n * Cc * 2) if args.precision == "bf16" else None,
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone), {pk['src']}"}
 
 
@@ -387,6 +424,10 @@ def run_reference(args):
 
 
 def main():
+    # stdout carries exactly one JSON line: anything a library prints there (e.g. NCCL's version banner) goes to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -61,6 +61,11 @@ class TrainStep:
 
     # ---- D step: train.py:259-296
     def d_step(self, batch) -> dict:
+        out = self.d_forward_backward(batch)
+        self._reduce_and_step("D", self.D, self.opt_D)
+        return out
+
+    def d_forward_backward(self, batch) -> dict:
         G, D = self.G, self.D
         x = batch["signal_real"]
         c_tgt = label2onehot(batch["label_tgt"], self.num_spk)
@@ -78,12 +83,16 @@ class TrainStep:
         if self.opt_D is not None:
             self.opt_D.zero_grad(set_to_none=True)
         d_loss.backward()
-        self._reduce_and_step("D", D, self.opt_D)
         return {"d_loss_real": d_real.detach(), "d_loss_fake": d_fake.detach(), "d_loss": d_loss.detach(),
                 "fake": fake}
 
     # ---- G step: train.py:320-491 (lambda_f0 needs torchcrepe, lambda_latcls the latent classifier: both 0 here)
     def g_step(self, batch, raw_draws=None) -> dict:
+        out = self.g_forward_backward(batch, raw_draws)
+        self._reduce_and_step("G", self.G, self.opt_G)
+        return out
+
+    def g_forward_backward(self, batch, raw_draws=None) -> dict:
         G, D, hp = self.G, self.D, self.hp
         x = batch["signal_real"]
         lab_s, lab_t = batch["label_src"], batch["label_tgt"]
@@ -128,7 +137,6 @@ class TrainStep:
             if self.opt_G is not None:
                 self.opt_G.zero_grad(set_to_none=True)
             g_loss.backward()
-        self._reduce_and_step("G", G, self.opt_G)
         out.update(g_adv=g_adv.detach(), g_rec=g_rec.detach(), g_idt=g_idt.detach(), g_cont=g_cont.detach(),
                    g_loss=g_loss.detach(), fake=fake.detach())
         return out
@@ -140,10 +148,14 @@ class TrainStep:
 
 
 class GraphedTrainStep:
-    """The whole G+D iteration captured once into a CUDA graph and replayed: the step issues ~8000 kernel
-    launches from Python, which costs more host time than the GPU needs to run them.  Inputs are copied into
-    static tensors; outputs are static tensors overwritten by every replay.  Needs optimisers with a grad bank
-    (fixed gradient addresses) -- FusedAdamW.use_grad_bank()."""
+    """The G+D iteration captured into CUDA graphs and replayed: the step issues ~8000 kernel launches from
+    Python, which costs more host time than the GPU needs to run them.  Inputs are copied into static tensors;
+    outputs are static tensors overwritten by every replay.  Needs optimisers with a grad bank (fixed gradient
+    addresses) -- FusedAdamW.use_grad_bank().
+
+    Single GPU: one graph for the whole iteration.  Data parallel: three graphs with the two gradient all-reduces
+    issued eagerly between them on the same stream ([D fwd/bwd + gather] -> all-reduce(D bank) -> [AdamW(D) +
+    G fwd/bwd + gather] -> all-reduce(G bank) -> [AdamW(G)]), so NCCL never runs inside a capture."""
 
     def __init__(self, ts: TrainStep, example_batch: dict, warmup: int = 3):
         from tdvc import ops
@@ -152,6 +164,7 @@ class GraphedTrainStep:
             if opt is not None and hasattr(opt, "use_grad_bank"):
                 opt.use_grad_bank()
         self.static = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in example_batch.items()}
+        self.split = ts.grad_hook is not None and getattr(ts.grad_hook, "world", 1) > 1
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -160,9 +173,25 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         ops._pack_cache.clear()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.out = ts.step(self.static)
+        if not self.split:
+            self.graphs = [torch.cuda.CUDAGraph()]
+            with torch.cuda.graph(self.graphs[0]):
+                self.out = ts.step(self.static)
+        else:
+            g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                self.out = ts.d_forward_backward(self.static)
+                ts.opt_D.gather_grads()
+            ops._pack_cache.clear()
+            with torch.cuda.graph(g2, pool=g1.pool()):
+                ts.opt_D._gathered = True
+                ts.opt_D.step()
+                self.out.update(ts.g_forward_backward(self.static))
+                ts.opt_G.gather_grads()
+            with torch.cuda.graph(g3, pool=g1.pool()):
+                ts.opt_G._gathered = True
+                ts.opt_G.step()
+            self.graphs = [g1, g2, g3]
         ops._pack_cache.clear()
 
     def load(self, batch: dict, non_blocking: bool = True):
@@ -173,5 +202,15 @@ class GraphedTrainStep:
     def step(self, batch: Optional[dict] = None) -> dict:
         if batch is not None:
             self.load(batch)
-        self.graph.replay()
+        if not self.split:
+            self.graphs[0].replay()
+        else:
+            ts = self.ts
+            self.graphs[0].replay()
+            for gi in range(len(ts.opt_D._banks)):
+                ts.grad_hook.reduce_flat(ts.opt_D.bank(gi))
+            self.graphs[1].replay()
+            for gi in range(len(ts.opt_G._banks)):
+                ts.grad_hook.reduce_flat(ts.opt_G.bank(gi))
+            self.graphs[2].replay()
         return self.out
