@@ -268,6 +268,11 @@ def run_ours(args):
             "roofline": roof,
             "losses": {k: float(v) for k, v in last.items() if k in ("d_loss", "g_loss")},
         }
+        if world == 1:
+            try:
+                out["inference"] = inference_rtf(G, dev, args)
+            except Exception as e:      # never lose the headline line to the auxiliary measurement
+                out["inference"] = {"error": repr(e)[:200]}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(steps=1, warmup=0, budget_s=30.0)
     if world > 1:
@@ -346,6 +351,40 @@ def dominant_kernel_roofline(dev, B, T, pk, args):
             "flops_per_launch": flops / launches_per_rep, "ms_per_launch": round(ms / launches_per_rep, 4),
             "algorithmic_bytes_per_launch": B * T * (Cc * 2 + n * Cc * 2) if args.precision == "bf16" else None,
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone), {pk['src']}"}
+
+
+def inference_rtf(G, dev, args, B=16, seconds=4.0, reps=5):
+    """BASELINE config 5: batched `G(signal, c_tgt, c_var=excitation)` (generate_with_target.py:169) on synthetic
+    4 s utterances, forward only (no_grad), replayed from a CUDA graph.  RTF = wall time / audio seconds."""
+    import torch
+    T = int(seconds * SR)
+    host = synth_batch(B, T, MODEL["nspk"], seed=4321)
+    x, cv = host["signal_real"].to(dev), host["c_f0_conv"].to(dev)
+    c_tgt = torch.zeros(B, MODEL["nspk"], device=dev).scatter_(1, host["label_tgt"].to(dev).view(-1, 1), 1.0)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.no_grad():
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                G(x, c_tgt, c_var=cv)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g):
+            y = G(x, c_tgt, c_var=cv)
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    audio = B * seconds
+    return {"rtf": round(ms / 1e3 / audio, 7), "x_realtime": round(audio / (ms / 1e3), 1), "batch": B,
+            "utterance_s": seconds, "ms_per_batch": round(ms, 3), "finite": bool(torch.isfinite(y).all()),
+            "gflop_per_audio_s": 51.95, "tflops_algorithmic": round(51.95 * audio / ms, 2)}
 
 
 def cpu_baseline(steps, warmup, budget_s=30.0):

@@ -7,6 +7,7 @@ all arithmetic happens in libtdvc_b200.so.  Inputs must be CUDA tensors; fp32, N
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Optional, Sequence
 
 import torch
@@ -88,8 +89,45 @@ class _WeightNorm(torch.autograd.Function):
         return dv, dg
 
 
+class _StepCache:
+    """Inside `with ops.step_cache():` a weight that has not changed is normalised (and packed to bf16) once and
+    reused by every forward pass of the scope -- the generator runs 3-4 times per training iteration on the same
+    weights.  Reuse is through autograd (the cached tensor carries its grad_fn), so gradients from all passes
+    accumulate into one weight-norm backward.  Entries are keyed on the parameter versions and dropped at scope exit."""
+
+    def __init__(self):
+        self.depth = 0
+        self.wn = {}
+        self.wp = {}
+
+    def __enter__(self):
+        self.depth += 1
+        return self
+
+    def __exit__(self, *exc):
+        self.depth -= 1
+        if self.depth == 0:
+            self.wn.clear()
+            self.wp.clear()
+        return False
+
+
+_step_cache = _StepCache()
+
+
+def step_cache() -> _StepCache:
+    return _step_cache
+
+
 def weight_norm(v: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
     """w = g * v / ||v|| (norm over all dims but 0) -- torch.nn.utils.weight_norm's per-forward recompute."""
+    if _step_cache.depth > 0:
+        key = (v.data_ptr(), v._version, g.data_ptr(), g._version, torch.is_grad_enabled() and (v.requires_grad or g.requires_grad))
+        hit = _step_cache.wn.get(key)
+        if hit is None:
+            hit = _WeightNorm.apply(v, g)
+            _step_cache.wn[key] = hit
+        return hit
     return _WeightNorm.apply(v, g)
 
 
@@ -603,10 +641,18 @@ def _pack_act(x, Cp, halo, pad_mode, slope, cache=True, chan_sum=None):
 
 def _pack_w(w, rows_p, cols_p, transpose_flip):
     Cout, Cin, K = w.shape
+    key = None
+    if _step_cache.depth > 0:
+        key = (w.data_ptr(), w._version, tuple(w.shape), rows_p, cols_p, bool(transpose_flip))
+        hit = _step_cache.wp.get(key)
+        if hit is not None and hit[0]() is w:
+            return hit[1]
     wp = torch.empty(K, rows_p, cols_p, device=w.device, dtype=torch.bfloat16)
     coutp, cinp = (cols_p, rows_p) if transpose_flip else (rows_p, cols_p)
     _lib.check(_lib.load().tdvc_pack_weight_bf16(_p(w), _p(wp), Cout, Cin, K, coutp, cinp, int(transpose_flip), 0, 0, 0, 0,
                                                  _st()), "pack_weight_bf16")
+    if key is not None:
+        _step_cache.wp[key] = (weakref.ref(w), wp)
     return wp
 
 

@@ -66,6 +66,14 @@ class TrainStep:
         return out
 
     def d_forward_backward(self, batch) -> dict:
+        with ops.step_cache():
+            return self._d_forward_backward(batch)
+
+    def g_forward_backward(self, batch, raw_draws=None) -> dict:
+        with ops.step_cache():
+            return self._g_forward_backward(batch, raw_draws)
+
+    def _d_forward_backward(self, batch) -> dict:
         G, D = self.G, self.D
         x = batch["signal_real"]
         c_tgt = label2onehot(batch["label_tgt"], self.num_spk)
@@ -92,7 +100,7 @@ class TrainStep:
         self._reduce_and_step("G", self.G, self.opt_G)
         return out
 
-    def g_forward_backward(self, batch, raw_draws=None) -> dict:
+    def _g_forward_backward(self, batch, raw_draws=None) -> dict:
         G, D, hp = self.G, self.D, self.hp
         x = batch["signal_real"]
         lab_s, lab_t = batch["label_src"], batch["label_tgt"]
