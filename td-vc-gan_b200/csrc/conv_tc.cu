@@ -123,6 +123,86 @@ constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
 constexpr int TC_THREADS = 192;       // wgrad kernel: TMA warp, MMA warp, 4 epilogue warps
 constexpr int TC_FWD_THREADS = 320;   // forward kernel: TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quadrant)
 
+// Epilogue of one 128 x BN accumulator tile at TMEM address `acc` (lane quadrant q, column half `half`).
+template <int ACT, int EPI, int OUT, int MASK>
+__device__ __forceinline__ void tc_epilogue_tile(const TcP& p, const float* bias_s, uint32_t acc, int b, int t0, int grp,
+                                                 int n0, int q, int half, int lane) {
+    const int t = t0 + q * 32 + lane;
+    const bool t_ok = t < p.Tout;
+    const long long ct = p.Tout;
+    const int nvalid = min(p.BN, p.Cout - n0);          // columns of this tile that are real channels
+    for (int c0 = half * 16; c0 < nvalid; c0 += 32) {
+      float v[16];
+      if (p.debug & 4) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = (float)(c0 + j);
+      } else {
+        tmem_ld16(acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      }
+      if (t_ok) {
+        const int nj = min(16, nvalid - c0);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += bias_s[c0 + j];
+        if (MASK) {
+          const __nv_bfloat16* mp = p.maskp + ((long long)b * p.tm + t + p.mask_halo) * p.cm + p.mask_ch_off +
+                                    grp * p.mask_ch_stride + n0 + c0;
+          uint4 m0 = __ldg(reinterpret_cast<const uint4*>(mp));
+          uint4 m1 = __ldg(reinterpret_cast<const uint4*>(mp) + 1);
+          const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            // bf16 sign/zero test on the raw bits: value <= 0  <=>  sign bit set or magnitude zero
+            const uint32_t h = (j & 1) ? (mw[j >> 1] >> 16) : (mw[j >> 1] & 0xFFFFu);
+            if ((h & 0x8000u) || (h & 0x7FFFu) == 0) v[j] *= p.mask_slope;
+          }
+        }
+        if (OUT == 0) {
+          const long long base = (((long long)grp * p.B + b) * p.Cout + n0 + c0) * ct + t;
+          float* yp = p.y + base;
+          const float* rp = p.res + base;                                   // only dereferenced when EPI asks for it
+          const float* gp = p.gb + ((long long)b * 2 * p.Cout + n0 + c0) * ct + t;
+          const long long beta_off = (long long)p.Cout * ct;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (j < nj) {
+              float o = v[j];
+              if (EPI == 2) {
+                o = fmaf(o, 1.f + __ldg(gp), __ldg(gp + beta_off));
+                if (p.res) o += __ldg(rp);
+              } else if (EPI == 1) {
+                o += __ldg(rp);
+              }
+              if (ACT == TDVC_ACT_LRELU) o = o > 0.f ? o : o * p.out_slope;
+              else if (ACT == TDVC_ACT_TANH) o = tanhf(o);
+              if (!(p.debug & 1)) *yp = o;
+            }
+            yp += ct; rp += ct; gp += ct;
+          }
+        } else {
+          // packed output: this thread owns 16 consecutive channels of one time step = 32 contiguous bytes
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float o = v[j];
+            if (ACT == TDVC_ACT_LRELU) o = o > 0.f ? o : o * p.out_slope;
+            v[j] = (j < nj) ? o : 0.f;
+          }
+          __nv_bfloat16* op = p.yp + ((long long)b * p.tp_out + t + p.out_halo) * p.cp_out + p.out_ch_off +
+                              grp * p.out_ch_stride + n0 + c0;
+          uint32_t w[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            w[j] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          if (!(p.debug & 1)) {
+            reinterpret_cast<uint4*>(op)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            reinterpret_cast<uint4*>(op)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+          }
+        }
+      }
+    }
+}
+
 // ACT: tdvc_act of the epilogue; EPI: 0 = bias only, 1 = + residual, 2 = FiLM (+ residual when p.res);
 // OUT: 0 = fp32 NCW [groups][B][Cout][T], 1 = bf16 channels-last (the next conv's operand, no pack pass);
 // MASK: 1 = multiply by the LeakyReLU derivative taken from the sign of a packed activated tensor (dgrad).
@@ -210,84 +290,143 @@ __global__ void __launch_bounds__(TC_FWD_THREADS) conv_tc_fwd_k(const __grid_con
     const int half = (warp - 2) >> 2;
     if (iters > 0) mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    const int t = t0 + q * 32 + lane;
-    const bool t_ok = t < p.Tout;
-    const long long ct = p.Tout;
-    const int nvalid = min(p.BN, p.Cout - n0);          // columns of this tile that are real channels
-    for (int c0 = half * 16; c0 < nvalid; c0 += 32) {
-      float v[16];
-      if (p.debug & 4) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = (float)(c0 + j);
-      } else {
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      }
-      if (t_ok) {
-        const int nj = min(16, nvalid - c0);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] += bias_s[c0 + j];
-        if (MASK) {
-          const __nv_bfloat16* mp = p.maskp + ((long long)b * p.tm + t + p.mask_halo) * p.cm + p.mask_ch_off +
-                                    grp * p.mask_ch_stride + n0 + c0;
-          uint4 m0 = __ldg(reinterpret_cast<const uint4*>(mp));
-          uint4 m1 = __ldg(reinterpret_cast<const uint4*>(mp) + 1);
-          const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            // bf16 sign/zero test on the raw bits: value <= 0  <=>  sign bit set or magnitude zero
-            const uint32_t h = (j & 1) ? (mw[j >> 1] >> 16) : (mw[j >> 1] & 0xFFFFu);
-            if ((h & 0x8000u) || (h & 0x7FFFu) == 0) v[j] *= p.mask_slope;
-          }
-        }
-        if (OUT == 0) {
-          const long long base = (((long long)grp * p.B + b) * p.Cout + n0 + c0) * ct + t;
-          float* yp = p.y + base;
-          const float* rp = p.res + base;                                   // only dereferenced when EPI asks for it
-          const float* gp = p.gb + ((long long)b * 2 * p.Cout + n0 + c0) * ct + t;
-          const long long beta_off = (long long)p.Cout * ct;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (j < nj) {
-              float o = v[j];
-              if (EPI == 2) {
-                o = fmaf(o, 1.f + __ldg(gp), __ldg(gp + beta_off));
-                if (p.res) o += __ldg(rp);
-              } else if (EPI == 1) {
-                o += __ldg(rp);
-              }
-              if (ACT == TDVC_ACT_LRELU) o = o > 0.f ? o : o * p.out_slope;
-              else if (ACT == TDVC_ACT_TANH) o = tanhf(o);
-              if (!(p.debug & 1)) *yp = o;
-            }
-            yp += ct; rp += ct; gp += ct;
-          }
-        } else {
-          // packed output: this thread owns 16 consecutive channels of one time step = 32 contiguous bytes
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float o = v[j];
-            if (ACT == TDVC_ACT_LRELU) o = o > 0.f ? o : o * p.out_slope;
-            v[j] = (j < nj) ? o : 0.f;
-          }
-          __nv_bfloat16* op = p.yp + ((long long)b * p.tp_out + t + p.out_halo) * p.cp_out + p.out_ch_off +
-                              grp * p.out_ch_stride + n0 + c0;
-          uint32_t w[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-            w[j] = *reinterpret_cast<uint32_t*>(&h2);
-          }
-          if (!(p.debug & 1)) {
-            reinterpret_cast<uint4*>(op)[0] = make_uint4(w[0], w[1], w[2], w[3]);
-            reinterpret_cast<uint4*>(op)[1] = make_uint4(w[4], w[5], w[6], w[7]);
-          }
-        }
-      }
-    }
+    tc_epilogue_tile<ACT, EPI, OUT, MASK>(p, bias_s, tmem_base, b, t0, grp, n0, q, half, lane);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1 && !(p.debug & 16)) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------ weight-stationary forward
+// Persistent variant for convolutions whose whole weight tile set (K taps x Cin chunks x BN rows) fits in shared
+// memory next to a small activation ring -- FiLM cond_var.0 (9 x 18 KB) and most cond_var.2 / conv.1 layers:
+//   * a CTA owns one N tile and walks a strided list of 128-step time tiles: weights are fetched from L2 ONCE per
+//     CTA instead of once per tile (the non-persistent kernel re-reads 166 KB of weights per 128 x 144 tile);
+//   * the activation tile is loaded once per 64-channel chunk with its (K-1)*dilation halo rows; the K taps are
+//     row-shifted views of it (descriptor start address + tap*dilation*128 B, swizzle phase carried in the
+//     descriptor's base-offset field), so activations cross L2->SMEM once instead of K times;
+//   * two TMEM accumulators: the 8 epilogue warps drain tile i while the MMA warp computes tile i+1.
+struct WsP {
+  int n_mtiles, mtiles_per_b, rows_a, a_stage_bytes, w_tile_bytes, use_base_offset;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int ACT, int EPI, int OUT, int MASK>
+__global__ void __launch_bounds__(TC_FWD_THREADS, 1) conv_tc_ws_k(const __grid_constant__ CUtensorMap map_a,
+                                                                  const __grid_constant__ CUtensorMap map_b, TcP p, WsP w) {
+  __shared__ float bias_s[256];
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int n_wtiles = p.K * p.nchunk;
+  uint8_t* wsm = smem;                                            // [K][nchunk] tiles of BN x 128 B
+  uint8_t* ring = smem + (size_t)n_wtiles * w.w_tile_bytes;       // [stages] tiles of rows_a x 128 B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)p.stages * w.a_stage_bytes);
+  uint64_t* w_full = bars;
+  uint64_t* full_bar = bars + 1;
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tmem_full = empty_bar + p.stages;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = blockIdx.y / p.tiles_per_group;
+  const int n0 = (blockIdx.y - grp * p.tiles_per_group) * p.BN;
+  for (int i = threadIdx.x; i < p.BN; i += TC_FWD_THREADS)
+    bias_s[i] = (p.bias && n0 + i < p.Cout) ? __ldg(p.bias + grp * p.bias_stride + n0 + i) : 0.f;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    mbar_init(w_full, 1);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 8);          // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(w_full, (uint32_t)(n_wtiles * w.w_tile_bytes));
+      for (int tap = 0; tap < p.K; ++tap)
+        for (int ck = 0; ck < p.nchunk; ++ck)
+          tma_load_3d(wsm + (size_t)(tap * p.nchunk + ck) * w.w_tile_bytes, &map_b, w_full, ck * TC_BK,
+                      grp * p.coutp_g + n0, tap);
+      int it = 0;
+      for (int m = blockIdx.x; m < w.n_mtiles; m += gridDim.x) {
+        const int b = m / w.mtiles_per_b, t0 = (m - b * w.mtiles_per_b) * TC_BM;
+        for (int ck = 0; ck < p.nchunk; ++ck, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_expect_tx(&full_bar[s], (uint32_t)w.a_stage_bytes);
+          tma_load_3d(ring + (size_t)s * w.a_stage_bytes, &map_a, &full_bar[s], p.a_ch_off + grp * p.a_ch_stride + ck * TC_BK,
+                      t0 + p.t_off, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    mbar_wait(w_full, 0);
+    tc_fence_after();
+    int it = 0, i = 0;
+    for (int m = blockIdx.x; m < w.n_mtiles; m += gridDim.x, ++i) {
+      const int acc = i & 1;
+      mbar_wait(&tmem_empty[acc], ((uint32_t)(i >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      for (int ck = 0; ck < p.nchunk; ++ck, ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const int nk = (ck == p.nchunk - 1) ? p.last_nk16 : (TC_BK / 16);
+          const uint32_t ring_addr = smem_u32(ring + (size_t)s * w.a_stage_bytes);
+          for (int tap = 0; tap < p.K; ++tap) {
+            const uint32_t a_addr = ring_addr + (uint32_t)(tap * p.dil) * 128u;       // row-shifted view of the tile
+            uint64_t da = make_sw128_kmajor_desc(a_addr);
+            if (w.use_base_offset) da |= (uint64_t)((a_addr >> 7) & 7u) << 49;
+            const uint64_t db = make_sw128_kmajor_desc(smem_u32(wsm + (size_t)(tap * p.nchunk + ck) * w.w_tile_bytes));
+            for (int k = 0; k < nk; ++k)
+              umma_bf16(tmem_base + (uint32_t)(acc * p.BN), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                        (ck > 0 || tap > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+          if (ck == p.nchunk - 1) umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    int i = 0;
+    for (int m = blockIdx.x; m < w.n_mtiles; m += gridDim.x, ++i) {
+      const int b = m / w.mtiles_per_b, t0 = (m - b * w.mtiles_per_b) * TC_BM;
+      const int acc = i & 1;
+      mbar_wait(&tmem_full[acc], (uint32_t)(i >> 1) & 1u);
+      tc_fence_after();
+      tc_epilogue_tile<ACT, EPI, OUT, MASK>(p, bias_s, tmem_base + (uint32_t)(acc * p.BN), b, t0, grp, n0, q, half, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------ wgrad
@@ -639,12 +778,66 @@ extern "C" int tdvc_conv1d_tc_fwd_ex(const tdvc_tc_conv* c, void* stream) {
     if (dbg < 0) { const char* e = getenv("TDVC_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
     p.debug = dbg;
   }
-  size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
-  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, TcP);
-  KernelFn kern = nullptr;
   const int epi = c->gb ? 2 : (c->residual ? 1 : 0);
   const int act = c->out_act;
   const bool mask = c->maskp != nullptr;
+  // ---- weight-stationary persistent variant when the whole weight tile set fits next to an activation ring
+  {
+    static int ws_on = -1, ws_bo = -1;
+    if (ws_on < 0) { const char* e = getenv("TDVC_TC_WS"); ws_on = e ? atoi(e) : 1; }
+    if (ws_bo < 0) { const char* e = getenv("TDVC_TC_WS_BO"); ws_bo = e ? atoi(e) : 1; }
+    const int halo_rows = (c->K - 1) * c->dilation;
+    const int rows_a = ((TC_BM + halo_rows + 7) / 8) * 8;
+    const long long w_tile = (long long)p.BN * TC_BK * 2;
+    const long long w_bytes = (long long)c->K * p.nchunk * w_tile;
+    const long long a_stage = (long long)rows_a * TC_BK * 2;
+    const long long budget = 224LL * 1024 - 2048;
+    const int mtiles_per_b = cdiv(c->Tout, TC_BM);
+    const int n_mtiles = mtiles_per_b * c->B;
+    const int n_tiles_total = c->groups * p.tiles_per_group;
+    int ctas = std::max(1, num_sms() / n_tiles_total);
+    ctas = std::min(ctas, n_mtiles);
+    if (ws_on && rows_a <= 256 && w_bytes + 2 * a_stage <= budget && (n_mtiles >= 4 * ctas || ws_on == 2) && 2 * p.BN <= 512) {   // TDVC_TC_WS=2 forces it (tests)
+      WsP w{};
+      w.n_mtiles = n_mtiles; w.mtiles_per_b = mtiles_per_b; w.rows_a = rows_a; w.a_stage_bytes = (int)a_stage;
+      w.w_tile_bytes = (int)w_tile; w.use_base_offset = ws_bo;
+      int st = (int)std::min<long long>(4, (budget - w_bytes) / a_stage);
+      p.stages = st;
+      int cols2 = 32;
+      while (cols2 < 2 * p.BN) cols2 <<= 1;
+      p.tmem_cols = cols2;
+      size_t smem_ws = (size_t)w_bytes + (size_t)st * a_stage + (2 * st + 5) * sizeof(uint64_t) + 16 + 1024;
+      typedef void (*WsFn)(const CUtensorMap, const CUtensorMap, TcP, WsP);
+      WsFn kern = nullptr;
+      if (!c->out_packed && !mask) {
+        static const WsFn table[3][3] = {
+            {conv_tc_ws_k<0, 0, 0, 0>, conv_tc_ws_k<0, 1, 0, 0>, conv_tc_ws_k<0, 2, 0, 0>},
+            {conv_tc_ws_k<1, 0, 0, 0>, conv_tc_ws_k<1, 1, 0, 0>, conv_tc_ws_k<1, 2, 0, 0>},
+            {conv_tc_ws_k<2, 0, 0, 0>, conv_tc_ws_k<2, 1, 0, 0>, conv_tc_ws_k<2, 2, 0, 0>}};
+        kern = table[act][epi];
+      } else if (!c->out_packed && mask) {
+        kern = conv_tc_ws_k<0, 0, 0, 1>;
+      } else if (c->out_packed && !mask) {
+        kern = act == TDVC_ACT_LRELU ? conv_tc_ws_k<1, 0, 1, 0> : conv_tc_ws_k<0, 0, 1, 0>;
+      } else {
+        kern = conv_tc_ws_k<0, 0, 1, 1>;
+      }
+      TDVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+      CUtensorMap map_a, map_b;
+      int rc = make_map_3d(&map_a, c->xp, (uint64_t)c->Cp_total, (uint64_t)c->Tp, (uint64_t)c->B, TC_BK, (uint32_t)rows_a);
+      if (rc) return rc;
+      rc = make_map_3d(&map_b, c->wp, (uint64_t)c->Cinp_g, (uint64_t)c->groups * c->Coutp_g, (uint64_t)c->K, TC_BK, (uint32_t)p.BN);
+      if (rc) return rc;
+      dim3 grid(ctas, n_tiles_total, 1);
+      TDVC_CHECK_ARG(grid.y <= 65535);
+      kern<<<grid, TC_FWD_THREADS, smem_ws, (cudaStream_t)stream>>>(map_a, map_b, p, w);
+      TDVC_LAUNCH_CHECK();
+      return TDVC_OK;
+    }
+  }
+  size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, TcP);
+  KernelFn kern = nullptr;
   if (!c->out_packed && !mask) {
     static const KernelFn table[3][3] = {
         {conv_tc_fwd_k<0, 0, 0, 0>, conv_tc_fwd_k<0, 1, 0, 0>, conv_tc_fwd_k<0, 2, 0, 0>},
