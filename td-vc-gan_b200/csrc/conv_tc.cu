@@ -68,6 +68,21 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
       : "memory");
 }
+// same MMA with the descriptors given as (lo, hi) 32-bit halves: the issuing thread only does 32-bit adds on `lo`
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -141,8 +156,14 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcP& p, const float* bias
       }
       if (t_ok) {
         const int nj = min(16, nvalid - c0);
+        {
+          const float4* b4 = reinterpret_cast<const float4*>(bias_s + c0);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] += bias_s[c0 + j];
+          for (int j = 0; j < 4; ++j) {
+            const float4 bb = b4[j];
+            v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+          }
+        }
         if (MASK) {
           const __nv_bfloat16* mp = p.maskp + ((long long)b * p.tm + t + p.mask_halo) * p.cm + p.mask_ch_off +
                                     grp * p.mask_ch_stride + n0 + c0;
@@ -180,11 +201,14 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcP& p, const float* bias
           }
         } else {
           // packed output: this thread owns 16 consecutive channels of one time step = 32 contiguous bytes
+          if (ACT == TDVC_ACT_LRELU) {
+            const float sl = p.out_slope;       // 0 < slope < 1: leaky_relu(o) = max(o, slope * o)
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float o = v[j];
-            if (ACT == TDVC_ACT_LRELU) o = o > 0.f ? o : o * p.out_slope;
-            v[j] = (j < nj) ? o : 0.f;
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], v[j] * sl);
+          }
+          if (nj < 16) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = (j < nj) ? v[j] : 0.f;
           }
           __nv_bfloat16* op = p.yp + ((long long)b * p.tp_out + t + p.out_halo) * p.cp_out + p.out_ch_off +
                               grp * p.out_ch_stride + n0 + c0;
@@ -209,7 +233,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcP& p, const float* bias
 template <int ACT, int EPI, int OUT, int MASK>
 __global__ void __launch_bounds__(TC_FWD_THREADS) conv_tc_fwd_k(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_b, TcP p) {
-  __shared__ float bias_s[256];      // bias of this N tile (zeros when absent)
+  __shared__ __align__(16) float bias_s[256];      // bias of this N tile (zeros when absent)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B atoms need 1024-B alignment
   const int b_bytes = p.BN * TC_BK * 2;
@@ -307,27 +331,48 @@ __global__ void __launch_bounds__(TC_FWD_THREADS) conv_tc_fwd_k(const __grid_con
 //     descriptor's base-offset field), so activations cross L2->SMEM once instead of K times;
 //   * two TMEM accumulators: the 8 epilogue warps drain tile i while the MMA warp computes tile i+1.
 struct WsP {
-  int n_mtiles, mtiles_per_b, rows_a, a_stage_bytes, w_tile_bytes, use_base_offset;
+  int n_mtiles, mtiles_per_b, rows_a, a_stage_bytes, w_tile_bytes;
+  // narrow tail: when the reduction width leaves a 16-channel last chunk (144 = 64 + 64 + 16) that chunk travels as
+  // 32-byte rows (SWIZZLE_32B boxes, own small ring) instead of a zero-padded 128-byte one: 4x less shared memory
+  // for its weights and activations, which buys a deeper activation ring (the kernel is load-latency bound).
+  int narrow, n_full, an_stage_bytes, wn_tile_bytes, n_stages;
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// K-major SWIZZLE_32B descriptor: 32-byte rows (16 bf16), 8-row atoms 256 B apart.
+__device__ __forceinline__ uint64_t make_sw32_kmajor_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;
+  return d;
+}
+
 template <int ACT, int EPI, int OUT, int MASK>
 __global__ void __launch_bounds__(TC_FWD_THREADS, 1) conv_tc_ws_k(const __grid_constant__ CUtensorMap map_a,
-                                                                  const __grid_constant__ CUtensorMap map_b, TcP p, WsP w) {
-  __shared__ float bias_s[256];
+                                                                  const __grid_constant__ CUtensorMap map_b,
+                                                                  const __grid_constant__ CUtensorMap map_an,
+                                                                  const __grid_constant__ CUtensorMap map_bn, TcP p, WsP w) {
+  __shared__ __align__(16) float bias_s[256];
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const int n_wtiles = p.K * p.nchunk;
-  uint8_t* wsm = smem;                                            // [K][nchunk] tiles of BN x 128 B
-  uint8_t* ring = smem + (size_t)n_wtiles * w.w_tile_bytes;       // [stages] tiles of rows_a x 128 B
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)p.stages * w.a_stage_bytes);
+  const int nfull = w.n_full;                                      // 64-channel chunks
+  uint8_t* wsm = smem;                                             // [K][nfull] tiles of BN x 128 B
+  uint8_t* wsn = wsm + (size_t)p.K * nfull * w.w_tile_bytes;       // [K] tiles of BN x 32 B (narrow tail)
+  uint8_t* ring = wsn + (size_t)(w.narrow ? p.K : 0) * w.wn_tile_bytes;          // [stages] x rows_a x 128 B
+  uint8_t* ringn = ring + (size_t)p.stages * w.a_stage_bytes;                   // [n_stages] x rows_a x 32 B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ringn + (size_t)(w.narrow ? w.n_stages : 0) * w.an_stage_bytes);
   uint64_t* w_full = bars;
   uint64_t* full_bar = bars + 1;
   uint64_t* empty_bar = full_bar + p.stages;
-  uint64_t* tmem_full = empty_bar + p.stages;      // [2]
+  uint64_t* fulln_bar = empty_bar + p.stages;
+  uint64_t* emptyn_bar = fulln_bar + w.n_stages;
+  uint64_t* tmem_full = emptyn_bar + w.n_stages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;            // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -345,6 +390,10 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) conv_tc_ws_k(const __grid_c
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
+    for (int s = 0; s < w.n_stages; ++s) {
+      mbar_init(&fulln_bar[s], 1);
+      mbar_init(&emptyn_bar[s], 1);
+    }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], 8);          // one arrival per epilogue warp
@@ -356,24 +405,34 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) conv_tc_ws_k(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int a_ch0 = p.a_ch_off + grp * p.a_ch_stride;
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(w_full, (uint32_t)(n_wtiles * w.w_tile_bytes));
-      for (int tap = 0; tap < p.K; ++tap)
-        for (int ck = 0; ck < p.nchunk; ++ck)
-          tma_load_3d(wsm + (size_t)(tap * p.nchunk + ck) * w.w_tile_bytes, &map_b, w_full, ck * TC_BK,
-                      grp * p.coutp_g + n0, tap);
-      int it = 0;
+      mbar_expect_tx(w_full, (uint32_t)(p.K * nfull * w.w_tile_bytes + (w.narrow ? p.K * w.wn_tile_bytes : 0)));
+      for (int tap = 0; tap < p.K; ++tap) {
+        for (int ck = 0; ck < nfull; ++ck)
+          tma_load_3d(wsm + (size_t)(tap * nfull + ck) * w.w_tile_bytes, &map_b, w_full, ck * TC_BK, grp * p.coutp_g + n0, tap);
+        if (w.narrow)
+          tma_load_3d(wsn + (size_t)tap * w.wn_tile_bytes, &map_bn, w_full, nfull * TC_BK, grp * p.coutp_g + n0, tap);
+      }
+      int it = 0, itn = 0;
       for (int m = blockIdx.x; m < w.n_mtiles; m += gridDim.x) {
         const int b = m / w.mtiles_per_b, t0 = (m - b * w.mtiles_per_b) * TC_BM;
-        for (int ck = 0; ck < p.nchunk; ++ck, ++it) {
+        for (int ck = 0; ck < nfull; ++ck, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
           mbar_wait(&empty_bar[s], ph ^ 1u);
           mbar_expect_tx(&full_bar[s], (uint32_t)w.a_stage_bytes);
-          tma_load_3d(ring + (size_t)s * w.a_stage_bytes, &map_a, &full_bar[s], p.a_ch_off + grp * p.a_ch_stride + ck * TC_BK,
-                      t0 + p.t_off, b);
+          tma_load_3d(ring + (size_t)s * w.a_stage_bytes, &map_a, &full_bar[s], a_ch0 + ck * TC_BK, t0 + p.t_off, b);
+        }
+        if (w.narrow) {
+          const int s = itn % w.n_stages;
+          const uint32_t ph = (uint32_t)(itn / w.n_stages) & 1u;
+          mbar_wait(&emptyn_bar[s], ph ^ 1u);
+          mbar_expect_tx(&fulln_bar[s], (uint32_t)w.an_stage_bytes);
+          tma_load_3d(ringn + (size_t)s * w.an_stage_bytes, &map_an, &fulln_bar[s], a_ch0 + nfull * TC_BK, t0 + p.t_off, b);
+          ++itn;
         }
       }
     }
@@ -381,32 +440,69 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) conv_tc_ws_k(const __grid_c
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     mbar_wait(w_full, 0);
     tc_fence_after();
-    int it = 0, i = 0;
+    // descriptor constants (units of 16 bytes for the address field)
+    const uint64_t d128 = make_sw128_kmajor_desc(0), d32 = make_sw32_kmajor_desc(0);
+    const uint32_t hi128 = (uint32_t)(d128 >> 32), hi32 = (uint32_t)(d32 >> 32);
+    const uint32_t lo_flags128 = (uint32_t)d128, lo_flags32 = (uint32_t)d32;       // LBO field lives in the low word
+    const uint32_t a_lo0 = lo_flags128 | ((smem_u32(ring) & 0x3FFFF) >> 4);
+    const uint32_t b_lo0 = lo_flags128 | ((smem_u32(wsm) & 0x3FFFF) >> 4);
+    const uint32_t an_lo0 = lo_flags32 | ((smem_u32(ringn) & 0x3FFFF) >> 4);
+    const uint32_t bn_lo0 = lo_flags32 | ((smem_u32(wsn) & 0x3FFFF) >> 4);
+    const uint32_t a_stage16 = (uint32_t)w.a_stage_bytes >> 4, an_stage16 = (uint32_t)w.an_stage_bytes >> 4;
+    const uint32_t w_tile16 = (uint32_t)w.w_tile_bytes >> 4, wn_tile16 = (uint32_t)w.wn_tile_bytes >> 4;
+    const uint32_t w_tap16 = w_tile16 * (uint32_t)nfull;                 // next tap's tile of the same chunk
+    const uint32_t tap_step16 = (uint32_t)p.dil * 8u;                    // dil rows x 128 B
+    const uint32_t tapn_step16 = (uint32_t)p.dil * 2u;                   // dil rows x 32 B
+    int it = 0, itn = 0, i = 0;
     for (int m = blockIdx.x; m < w.n_mtiles; m += gridDim.x, ++i) {
       const int acc = i & 1;
+      const uint32_t d_addr = tmem_base + (uint32_t)(acc * p.BN);
       mbar_wait(&tmem_empty[acc], ((uint32_t)(i >> 1) & 1u) ^ 1u);
       tc_fence_after();
-      for (int ck = 0; ck < p.nchunk; ++ck, ++it) {
+      for (int ck = 0; ck < nfull; ++ck, ++it) {
         const int s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         if (lane == 0) {
-          const int nk = (ck == p.nchunk - 1) ? p.last_nk16 : (TC_BK / 16);
-          const uint32_t ring_addr = smem_u32(ring + (size_t)s * w.a_stage_bytes);
+          // the single issuing thread must spend < ~70 cycles per MMA (its execution time at N=144): descriptors are
+          // advanced with 32-bit adds on their low words only
+          const int nk = (!w.narrow && ck == nfull - 1) ? p.last_nk16 : (TC_BK / 16);
+          uint32_t a_lo = a_lo0 + (uint32_t)s * a_stage16;
+          uint32_t b_lo = b_lo0 + (uint32_t)ck * w_tile16;
           for (int tap = 0; tap < p.K; ++tap) {
-            const uint32_t a_addr = ring_addr + (uint32_t)(tap * p.dil) * 128u;       // row-shifted view of the tile
-            uint64_t da = make_sw128_kmajor_desc(a_addr);
-            if (w.use_base_offset) da |= (uint64_t)((a_addr >> 7) & 7u) << 49;
-            const uint64_t db = make_sw128_kmajor_desc(smem_u32(wsm + (size_t)(tap * p.nchunk + ck) * w.w_tile_bytes));
-            for (int k = 0; k < nk; ++k)
-              umma_bf16(tmem_base + (uint32_t)(acc * p.BN), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                        (ck > 0 || tap > 0 || k > 0) ? 1u : 0u);
+            // row-shifted view of the haloed tile: the 128B swizzle is a function of the absolute shared-memory
+            // address, so a start address moved by whole 128-byte rows needs no descriptor fix-up (verified on B200)
+            umma_bf16_lohi(d_addr, a_lo, hi128, b_lo, hi128, idesc, (ck > 0 || tap > 0) ? 1u : 0u);
+            if (nk > 1) umma_bf16_lohi(d_addr, a_lo + 2, hi128, b_lo + 2, hi128, idesc, 1u);
+            if (nk > 2) umma_bf16_lohi(d_addr, a_lo + 4, hi128, b_lo + 4, hi128, idesc, 1u);
+            if (nk > 3) umma_bf16_lohi(d_addr, a_lo + 6, hi128, b_lo + 6, hi128, idesc, 1u);
+            a_lo += tap_step16;
+            b_lo += w_tap16;
           }
           umma_commit(&empty_bar[s]);
-          if (ck == p.nchunk - 1) umma_commit(&tmem_full[acc]);
+          if (!w.narrow && ck == nfull - 1) umma_commit(&tmem_full[acc]);
         }
         __syncwarp();
+      }
+      if (w.narrow) {
+        const int s = itn % w.n_stages;
+        const uint32_t ph = (uint32_t)(itn / w.n_stages) & 1u;
+        mbar_wait(&fulln_bar[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          uint32_t a_lo = an_lo0 + (uint32_t)s * an_stage16;
+          uint32_t b_lo = bn_lo0;
+          for (int tap = 0; tap < p.K; ++tap) {
+            umma_bf16_lohi(d_addr, a_lo, hi32, b_lo, hi32, idesc, 1u);
+            a_lo += tapn_step16;
+            b_lo += wn_tile16;
+          }
+          umma_commit(&emptyn_bar[s]);
+          umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        ++itn;
       }
     }
   } else {
@@ -672,7 +768,8 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int make_map_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0, uint32_t box1) {
+static int make_map_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0, uint32_t box1,
+                       CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return TDVC_ERR_CUDA; }
   cuuint64_t dims[3] = {d0, d1, d2};
@@ -680,7 +777,7 @@ static int make_map_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d
   cuuint32_t box[3] = {box0, box1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return TDVC_ERR_CUDA; }
   return TDVC_OK;
@@ -783,31 +880,40 @@ extern "C" int tdvc_conv1d_tc_fwd_ex(const tdvc_tc_conv* c, void* stream) {
   const bool mask = c->maskp != nullptr;
   // ---- weight-stationary persistent variant when the whole weight tile set fits next to an activation ring
   {
-    static int ws_on = -1, ws_bo = -1;
+    static int ws_on = -1;
     if (ws_on < 0) { const char* e = getenv("TDVC_TC_WS"); ws_on = e ? atoi(e) : 1; }
-    if (ws_bo < 0) { const char* e = getenv("TDVC_TC_WS_BO"); ws_bo = e ? atoi(e) : 1; }
     const int halo_rows = (c->K - 1) * c->dilation;
     const int rows_a = ((TC_BM + halo_rows + 7) / 8) * 8;
-    const long long w_tile = (long long)p.BN * TC_BK * 2;
-    const long long w_bytes = (long long)c->K * p.nchunk * w_tile;
-    const long long a_stage = (long long)rows_a * TC_BK * 2;
+    const bool narrow = (c->Cinp_g % TC_BK) == 16 && c->Cinp_g > TC_BK;      // e.g. 144 = 64 + 64 + 16
+    const int n_full = narrow ? p.nchunk - 1 : p.nchunk;
+    const long long w_tile = (long long)p.BN * TC_BK * 2, wn_tile = (long long)p.BN * 32;
+    const long long w_bytes = (long long)c->K * n_full * w_tile + (narrow ? (long long)c->K * wn_tile : 0);
+    const long long a_stage = (long long)rows_a * TC_BK * 2, an_stage = (long long)rows_a * 32;
     const long long budget = 224LL * 1024 - 2048;
     const int mtiles_per_b = cdiv(c->Tout, TC_BM);
     const int n_mtiles = mtiles_per_b * c->B;
     const int n_tiles_total = c->groups * p.tiles_per_group;
     int ctas = std::max(1, num_sms() / n_tiles_total);
     ctas = std::min(ctas, n_mtiles);
-    if (ws_on && rows_a <= 256 && w_bytes + 2 * a_stage <= budget && (n_mtiles >= 4 * ctas || ws_on == 2) && 2 * p.BN <= 512) {   // TDVC_TC_WS=2 forces it (tests)
+    const int n_stages = narrow ? 3 : 0;
+    const long long fixed = w_bytes + n_stages * an_stage;
+    if (ws_on && rows_a <= 256 && fixed + 2 * a_stage <= budget && (n_mtiles >= 4 * ctas || ws_on == 2) && 2 * p.BN <= 512) {   // TDVC_TC_WS=2 forces it (tests)
       WsP w{};
       w.n_mtiles = n_mtiles; w.mtiles_per_b = mtiles_per_b; w.rows_a = rows_a; w.a_stage_bytes = (int)a_stage;
-      w.w_tile_bytes = (int)w_tile; w.use_base_offset = ws_bo;
-      int st = (int)std::min<long long>(4, (budget - w_bytes) / a_stage);
+      w.w_tile_bytes = (int)w_tile; w.narrow = narrow ? 1 : 0; w.n_full = n_full; w.an_stage_bytes = (int)an_stage;
+      w.wn_tile_bytes = (int)wn_tile; w.n_stages = n_stages;
+      int st = (int)std::min<long long>(8, (budget - fixed) / a_stage);
+      {
+        static int cap = -1;      // TDVC_TC_WS_STAGES: development knob (ring-depth sensitivity)
+        if (cap < 0) { const char* e = getenv("TDVC_TC_WS_STAGES"); cap = e ? atoi(e) : 0; }
+        if (cap >= 2) st = std::min(st, cap);
+      }
       p.stages = st;
       int cols2 = 32;
       while (cols2 < 2 * p.BN) cols2 <<= 1;
       p.tmem_cols = cols2;
-      size_t smem_ws = (size_t)w_bytes + (size_t)st * a_stage + (2 * st + 5) * sizeof(uint64_t) + 16 + 1024;
-      typedef void (*WsFn)(const CUtensorMap, const CUtensorMap, TcP, WsP);
+      size_t smem_ws = (size_t)fixed + (size_t)st * a_stage + (2 * st + 2 * n_stages + 5) * sizeof(uint64_t) + 16 + 1024;
+      typedef void (*WsFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, TcP, WsP);
       WsFn kern = nullptr;
       if (!c->out_packed && !mask) {
         static const WsFn table[3][3] = {
@@ -823,14 +929,24 @@ extern "C" int tdvc_conv1d_tc_fwd_ex(const tdvc_tc_conv* c, void* stream) {
         kern = conv_tc_ws_k<0, 0, 1, 1>;
       }
       TDVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-      CUtensorMap map_a, map_b;
+      CUtensorMap map_a, map_b, map_an, map_bn;
       int rc = make_map_3d(&map_a, c->xp, (uint64_t)c->Cp_total, (uint64_t)c->Tp, (uint64_t)c->B, TC_BK, (uint32_t)rows_a);
       if (rc) return rc;
       rc = make_map_3d(&map_b, c->wp, (uint64_t)c->Cinp_g, (uint64_t)c->groups * c->Coutp_g, (uint64_t)c->K, TC_BK, (uint32_t)p.BN);
       if (rc) return rc;
+      if (narrow) {
+        rc = make_map_3d(&map_an, c->xp, (uint64_t)c->Cp_total, (uint64_t)c->Tp, (uint64_t)c->B, 16, (uint32_t)rows_a,
+                         CU_TENSOR_MAP_SWIZZLE_32B);
+        if (rc) return rc;
+        rc = make_map_3d(&map_bn, c->wp, (uint64_t)c->Cinp_g, (uint64_t)c->groups * c->Coutp_g, (uint64_t)c->K, 16,
+                         (uint32_t)p.BN, CU_TENSOR_MAP_SWIZZLE_32B);
+        if (rc) return rc;
+      } else {
+        map_an = map_a; map_bn = map_b;
+      }
       dim3 grid(ctas, n_tiles_total, 1);
       TDVC_CHECK_ARG(grid.y <= 65535);
-      kern<<<grid, TC_FWD_THREADS, smem_ws, (cudaStream_t)stream>>>(map_a, map_b, p, w);
+      kern<<<grid, TC_FWD_THREADS, smem_ws, (cudaStream_t)stream>>>(map_a, map_b, map_an, map_bn, p, w);
       TDVC_LAUNCH_CHECK();
       return TDVC_OK;
     }
