@@ -136,7 +136,8 @@ constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
 constexpr int TC_THREADS = 192;       // wgrad kernel: TMA warp, MMA warp, 4 epilogue warps
-constexpr int TC_FWD_THREADS = 320;   // forward kernel: TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quadrant)
+constexpr int TC_EPI_WARPS = 16;      // forward kernels: epilogue warps (a multiple of 4: TC_EPI_WARPS / 4 per TMEM lane quadrant)
+constexpr int TC_FWD_THREADS = 64 + 32 * TC_EPI_WARPS;   // + TMA warp + MMA warp
 
 // Epilogue of one 128 x BN accumulator tile at TMEM address `acc` (lane quadrant q, column half `half`).
 template <int ACT, int EPI, int OUT, int MASK>
@@ -146,7 +147,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcP& p, const float* bias
     const bool t_ok = t < p.Tout;
     const long long ct = p.Tout;
     const int nvalid = min(p.BN, p.Cout - n0);          // columns of this tile that are real channels
-    for (int c0 = half * 16; c0 < nvalid; c0 += 32) {
+    for (int c0 = half * 16; c0 < nvalid; c0 += 16 * (TC_EPI_WARPS / 4)) {
       float v[16];
       if (p.debug & 4) {
 #pragma unroll
@@ -396,7 +397,7 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) conv_tc_ws_k(const __grid_c
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 8);          // one arrival per epilogue warp
+      mbar_init(&tmem_empty[a], TC_EPI_WARPS);          // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -514,7 +515,8 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) conv_tc_ws_k(const __grid_c
       const int acc = i & 1;
       mbar_wait(&tmem_full[acc], (uint32_t)(i >> 1) & 1u);
       tc_fence_after();
-      tc_epilogue_tile<ACT, EPI, OUT, MASK>(p, bias_s, tmem_base + (uint32_t)(acc * p.BN), b, t0, grp, n0, q, half, lane);
+      if (!(p.debug & 32))
+        tc_epilogue_tile<ACT, EPI, OUT, MASK>(p, bias_s, tmem_base + (uint32_t)(acc * p.BN), b, t0, grp, n0, q, half, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -679,58 +681,73 @@ __global__ void wgrad_finalize_k(const float* __restrict__ ws, float* __restrict
 
 // ------------------------------------------------------------------------------------------ pack kernels
 // x[B,C,T] fp32 NCW -> xp[B,Tp,Cp] bf16 channels-last, LeakyReLU(in_slope), halo rows reflect- or zero-filled.
-constexpr int PACK_STRIP = 8;   // 32-step time tiles per CTA
-
-__global__ void pack_cl_bf16_k(const float* __restrict__ x, __nv_bfloat16* __restrict__ xp, int C, int T, int Cp, int Tp,
-                               int halo, int pad_mode, float slope, float* __restrict__ chan_sum, int c_off, int Cw,
-                               int ones_ch) {
-  __shared__ float tile[32][33];
+// x[B,C,T] fp32 NCW -> xp[B,Tp,Cp] bf16 channels-last (channels [c_off, c_off+Cw)), LeakyReLU(slope), reflect / zero
+// halo rows.  A CTA moves a CH-channel x TL-step tile (CH*TL = 4096 elements whatever the channel count, so thin
+// tensors still put 16 independent loads per thread in flight): reads are 128-byte lines along time, writes are
+// bf16x2 per lane = 128-byte lines along channels, zero filled up to the 64-channel slice width.
+template <int CH>
+__global__ void __launch_bounds__(256) pack_cl_bf16_k(const float* __restrict__ x, __nv_bfloat16* __restrict__ xp, int C,
+                                                     int T, int Cp, int Tp, int halo, int pad_mode, float slope,
+                                                     float* __restrict__ chan_sum, int c_off, int Cw, int ones_ch) {
+  constexpr int TL = 4096 / CH;             // time steps per tile: 64 / 128 / 256
+  constexpr int RPW = CH / 8;               // channel rows per warp
+  constexpr int LPR = TL / 32;              // loads per row per lane
+  __shared__ float tile[CH][TL + 1];
   const int b = blockIdx.z;
-  const int c0 = blockIdx.y * 32;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};     // per-channel partial sums of this warp's 4 channel rows
-  for (int st = 0; st < PACK_STRIP; ++st) {
-    const int tp0 = (blockIdx.x * PACK_STRIP + st) * 32;
-    if (tp0 >= Tp) break;
-    // read: threadIdx.x along time (coalesced), threadIdx.y strides channels
+  const int c0 = blockIdx.y * 64;           // first channel of this CTA's 64-wide output slice ...
+  const int cin0 = c0 + (CH < 64 ? 0 : 0);  // ... and of the CH source channels it reads (CH < 64 only when C <= CH)
+  const int tp0 = blockIdx.x * TL;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  float vals[RPW][LPR];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int cy = threadIdx.y + 8 * r;
-      const int c = c0 + cy, tp = tp0 + threadIdx.x;
+  for (int r = 0; r < RPW; ++r) {
+    const int cy = wrp + 8 * r;
+    const int c = cin0 + cy;
+    const float* row = x + ((long long)b * C + c) * T;
+#pragma unroll
+    for (int l = 0; l < LPR; ++l) {
+      const int tp = tp0 + lane + 32 * l;
       float v = 0.f;
       if (c < C && tp < Tp) {
         int u = tp - halo;
         bool ok = true;
         if (u < 0) { if (pad_mode == TDVC_PAD_REFLECT) { u = -u; ok = u < T; } else ok = false; }
         else if (u >= T) { if (pad_mode == TDVC_PAD_REFLECT) { u = 2 * (T - 1) - u; ok = u >= 0; } else ok = false; }
-        if (ok) {
-          v = __ldg(x + ((long long)b * C + c) * T + u);
-          if (tp >= halo && tp < halo + T) acc[r] += v;      // each source sample counted once
-          v = v > 0.f ? v : v * slope;
-        }
+        if (ok) v = __ldg(row + u);
       }
-      tile[cy][threadIdx.x] = v;
+      vals[r][l] = v;
     }
-    __syncthreads();
-    // write: threadIdx.x along channels (contiguous in xp)
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int ty = threadIdx.y + 8 * r;
-      const int tp = tp0 + ty, c = c0 + threadIdx.x;
-      if (tp < Tp && c < Cw) {
-        float o = tile[threadIdx.x][ty];
-        if (c == ones_ch) o = (tp >= halo && tp < halo + T) ? 1.f : 0.f;   // constant-one channel: bias grad via wgrad
-        xp[((long long)b * Tp + tp) * Cp + c_off + c] = __float2bfloat16(o);
-      }
-    }
-    __syncthreads();
   }
-  if (chan_sum) {      // per-channel sum of the fp32 source (the bias gradient when x is dL/dy)
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      float sres = warp_sum(acc[r]);
-      const int c = c0 + threadIdx.y + 8 * r;
-      if (threadIdx.x == 0 && c < C) atomicAdd(chan_sum + c, sres);
+  for (int r = 0; r < RPW; ++r) {
+    const int cy = wrp + 8 * r;
+    float sum = 0.f;
+#pragma unroll
+    for (int l = 0; l < LPR; ++l) {
+      const int tp = tp0 + lane + 32 * l;
+      float v = vals[r][l];
+      if (tp >= halo && tp < halo + T) sum += v;          // each source sample counted once
+      tile[cy][lane + 32 * l] = v > 0.f ? v : v * slope;
     }
+    if (chan_sum) {      // per-channel sum of the fp32 source (the bias gradient when x is dL/dy)
+      sum = warp_sum(sum);
+      if (lane == 0 && cin0 + cy < C) atomicAdd(chan_sum + cin0 + cy, sum);
+    }
+  }
+  __syncthreads();
+  const int c = c0 + 2 * lane;                // this lane's channel pair inside the slice
+  if (c >= Cw) return;
+  for (int ty = wrp; ty < TL; ty += 8) {
+    const int tp = tp0 + ty;
+    if (tp >= Tp) break;
+    float o0 = (2 * lane < CH) ? tile[2 * lane < CH ? 2 * lane : 0][ty] : 0.f;
+    float o1 = (2 * lane + 1 < CH) ? tile[2 * lane + 1 < CH ? 2 * lane + 1 : 0][ty] : 0.f;
+    const bool valid_row = tp >= halo && tp < halo + T;
+    if (c == ones_ch) o0 = valid_row ? 1.f : 0.f;         // constant-one channel: bias grad via the wgrad GEMM
+    if (c + 1 == ones_ch) o1 = valid_row ? 1.f : 0.f;
+    __nv_bfloat16* dst = xp + ((long long)b * Tp + tp) * Cp + c_off + c;
+    if (c + 1 < Cw) *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(o0, o1);
+    else *dst = __float2bfloat16(o0);
   }
 }
 
@@ -795,10 +812,21 @@ extern "C" int tdvc_pack_cl_bf16(const float* x, void* xp, int B, int C, int T, 
   if (chan_sum) TDVC_CUDA(cudaMemsetAsync(chan_sum, 0, sizeof(float) * C, (cudaStream_t)stream));
   if (B == 0) return TDVC_OK;
   int Tp = T + 2 * halo;
-  dim3 grid(cdiv(Tp, 32 * PACK_STRIP), cdiv(Cw, 32), B);
-  TDVC_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535);
-  pack_cl_bf16_k<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)xp, C, T, Cp, Tp, halo, pad_mode, in_slope, chan_sum, c_off, Cw,
-                                                                   ones_ch);
+  TDVC_CHECK_ARG(Cw % 2 == 0 && c_off % 2 == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* o = (__nv_bfloat16*)xp;
+  // thin tensors: fewer channel rows, longer time tiles (same bytes in flight per CTA)
+  if (C <= 16 && Cw <= 64) {
+    dim3 grid(cdiv(Tp, 256), 1, B);
+    pack_cl_bf16_k<16><<<grid, 256, 0, st>>>(x, o, C, T, Cp, Tp, halo, pad_mode, in_slope, chan_sum, c_off, Cw, ones_ch);
+  } else if (C <= 32 && Cw <= 64) {
+    dim3 grid(cdiv(Tp, 128), 1, B);
+    pack_cl_bf16_k<32><<<grid, 256, 0, st>>>(x, o, C, T, Cp, Tp, halo, pad_mode, in_slope, chan_sum, c_off, Cw, ones_ch);
+  } else {
+    dim3 grid(cdiv(Tp, 64), cdiv(Cw, 64), B);
+    TDVC_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535);
+    pack_cl_bf16_k<64><<<grid, 256, 0, st>>>(x, o, C, T, Cp, Tp, halo, pad_mode, in_slope, chan_sum, c_off, Cw, ones_ch);
+  }
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
