@@ -157,6 +157,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     ops.set_precision(args.precision)
+    ops.set_branch_streams(args.branch_streams)
     B, T, nspk = TRAIN["batch_size"], TRAIN["max_segment"], MODEL["nspk"]
     G, D = build_models(dev)
     broadcast_parameters(G); broadcast_parameters(D)
@@ -477,6 +478,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="launch every kernel from Python each step instead of replaying one CUDA graph")
+    ap.add_argument("--branch-streams", type=int, default=int(os.environ.get("TDVC_BRANCH_STREAMS", "0")),
+                    help="1: run the 3 independent MRF branches on forked CUDA streams")
     ap.add_argument("--profile", action="store_true",
                     help="profiling aid (ncu): honour --warmup as given, skip the e2e / roofline / cpu legs; "
                          "numbers printed in this mode are not bench values")

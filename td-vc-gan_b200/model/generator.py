@@ -262,6 +262,45 @@ class MRFBlock(nn.Module):
                 self.blocks[i].append(FiLMResnetBlock(n_channel, n_cond_const, n_cond_var, dilation, kernel_size,
                                                       leaky_relu_slope, weight_norm))
 
+    def _branch(self, i, x, c, gbs):
+        """One kernel-size branch: its FiLM blocks in sequence."""
+        nd = len(self.blocks[i])
+        xs = x
+        for j, mod in enumerate(self.blocks[i]):
+            if gbs is not None:
+                xs = mod(xs, None, gb=gbs[i * nd + j])
+            else:
+                xs = mod(xs, c)
+        return xs
+
+    def _forward_branches_concurrent(self, x, c, gbs):
+        """The kernel-size branches are independent chains of small kernels: run them on forked CUDA streams (autograd
+        replays each node's backward on its forward stream, and a CUDA-graph capture records the fork/join), so the
+        GPU overlaps three latency-bound chains instead of idling between their launches."""
+        cur = torch.cuda.current_stream()
+        side = ops.branch_streams(x.device, len(self.blocks) - 1)
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        outs = [None] * len(self.blocks)
+        joins = []
+        for i in range(1, len(self.blocks)):
+            s = side[i - 1]
+            s.wait_event(fork)
+            with torch.cuda.stream(s):
+                outs[i] = self._branch(i, x, c, gbs)
+                ev = torch.cuda.Event()
+                ev.record(s)
+                joins.append(ev)
+            # tensors made on `cur` are read on `s` and vice versa: tell the caching allocator
+            for t in (x, c) + tuple(gbs or ()):
+                if t is not None:
+                    t.record_stream(s)
+            outs[i].record_stream(cur)
+        outs[0] = self._branch(0, x, c, gbs)
+        for ev in joins:
+            cur.wait_event(ev)
+        return outs
+
     def _fused_cond(self, c):
         """All blocks' gamma|beta from one grouped tensor-core pass over c (bf16 mode), or None."""
         if c is None or c.ndim != 3 or not self.has_cond:
@@ -277,18 +316,11 @@ class MRFBlock(nn.Module):
         return ops.mrf_cond_path(c, wb, slope=mods[0].cond_var[1].negative_slope)
 
     def forward(self, x, c=None):
-        outs = []
         gbs = self._fused_cond(c)
-        i = 0
-        for block in self.blocks:
-            xs = x
-            for mod in block:
-                if gbs is not None:
-                    xs = mod(xs, None, gb=gbs[i])
-                else:
-                    xs = mod(xs, c)
-                i += 1
-            outs.append(xs)
+        if ops.branch_streams_enabled() and x.is_cuda and len(self.blocks) > 1:
+            outs = self._forward_branches_concurrent(x, c, gbs)
+        else:
+            outs = [self._branch(i, x, c, gbs) for i in range(len(self.blocks))]
         n = len(outs)
         if n <= 3:
             return ops.add_scale(*outs, alpha=1.0 / n)

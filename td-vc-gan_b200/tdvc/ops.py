@@ -7,6 +7,7 @@ all arithmetic happens in libtdvc_b200.so.  Inputs must be CUDA tensors; fp32, N
 from __future__ import annotations
 
 import ctypes as C
+import os
 import weakref
 from typing import Optional, Sequence
 
@@ -33,6 +34,28 @@ def get_precision() -> str:
     return _PRECISION
 
 
+_BRANCH_STREAMS = os.environ.get("TDVC_BRANCH_STREAMS", "0") == "1"
+_branch_stream_pool = {}
+
+
+def branch_streams_enabled() -> bool:
+    return _BRANCH_STREAMS
+
+
+def set_branch_streams(on: bool):
+    """Run the independent kernel-size branches of every MRF block on forked CUDA streams."""
+    global _BRANCH_STREAMS
+    _BRANCH_STREAMS = bool(on)
+
+
+def branch_streams(device, n):
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    pool = _branch_stream_pool.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=device))
+    return pool[:n]
+
+
 def _p(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -53,7 +76,14 @@ def _req(*ts):
 
 
 def _c(t: Optional[torch.Tensor]):
-    return None if t is None else t.contiguous()
+    """contiguous(); with branch streams on, also tells the caching allocator that the tensor is read on the current
+    stream: tensors (activations forward, gradients backward) cross the forked MRF branch streams, and a block
+    freed by its allocating stream must not be recycled while another stream still reads it."""
+    if t is None:
+        return None
+    if _BRANCH_STREAMS and t.is_cuda:
+        t.record_stream(torch.cuda.current_stream())
+    return t.contiguous()
 
 
 def _geom(B, Cin, Tin, Cout, Tout, K, stride, pad, dilation, groups, pad_mode, in_slope, out_act, out_slope):
@@ -101,11 +131,13 @@ class _StepCache:
         self.wp = {}
 
     def __enter__(self):
-        self.depth += 1
+        if os.environ.get("TDVC_NO_STEP_CACHE") != "1":
+            self.depth += 1
         return self
 
     def __exit__(self, *exc):
-        self.depth -= 1
+        if os.environ.get("TDVC_NO_STEP_CACHE") != "1":
+            self.depth -= 1
         if self.depth == 0:
             self.wn.clear()
             self.wp.clear()
@@ -125,9 +157,12 @@ def weight_norm(v: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
         key = (v.data_ptr(), v._version, g.data_ptr(), g._version, torch.is_grad_enabled() and (v.requires_grad or g.requires_grad))
         hit = _step_cache.wn.get(key)
         if hit is None:
-            hit = _WeightNorm.apply(v, g)
+            hit = (_WeightNorm.apply(v, g), torch.cuda.current_stream().cuda_stream)
             _step_cache.wn[key] = hit
-        return hit
+        elif os.environ.get("TDVC_DEBUG_STREAMS") == "1" and hit[1] != torch.cuda.current_stream().cuda_stream:
+            print(f"[tdvc] weight {tuple(v.shape)} normalised on stream {hit[1]:#x}, reused on {torch.cuda.current_stream().cuda_stream:#x}",
+                  flush=True)
+        return hit[0]
     return _WeightNorm.apply(v, g)
 
 
