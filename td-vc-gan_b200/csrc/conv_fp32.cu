@@ -22,6 +22,7 @@ struct FwdP {
   long long w_sco, w_sci, w_sk;
   int w_flip;
   int ci_chunk, span;
+  int seg, span_p;   // strided convs keep the input tile de-interleaved by phase: element i -> (i % stride) * seg + i / stride
 };
 
 __device__ __forceinline__ float fetch_padded(const float* __restrict__ row, int gt, int T, int pad_mode,
@@ -68,7 +69,9 @@ __global__ void __launch_bounds__(256) conv_fwd_k(FwdP p, const float* __restric
   constexpr int TY = 256 / TX, TT = TX * 4, COB = TY * CO_T;
   extern __shared__ float sm[];
   float* xs = sm;
-  float* ws = sm + (((size_t)p.ci_chunk * p.span + 3) & ~(size_t)3);
+  float* ws = sm + (((size_t)p.ci_chunk * p.span_p + 3) & ~(size_t)3);
+  constexpr int WPITCH_K = (CO_T % 4 == 0) ? COB : COB + 1;
+  int* kofs = reinterpret_cast<int*>(ws + (size_t)p.ci_chunk * p.K * WPITCH_K);   // [K] tile offset of tap k
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   const int t0 = blockIdx.x * TT;
   const int tiles_per_group = (p.cout_g + COB - 1) / COB;
@@ -83,14 +86,21 @@ __global__ void __launch_bounds__(256) conv_fwd_k(FwdP p, const float* __restric
   const float* xb = x + ((long long)b * p.Cin + (long long)grp * p.cin_g) * p.Tin;
   const int gt0 = t0 * p.stride - p.pad;
   const bool row_active = (co0 + ty * CO_T) < p.cout_g;
-  const int xstep = TX * p.stride;
+  // With the tile stored phase-major, output step (tx + j*TX) and tap k read word  kofs[k] + tx + j*TX : consecutive
+  // lanes hit consecutive banks for any stride (a plain layout gives stride-way bank conflicts).
+  for (int k = threadIdx.x; k < p.K; k += 256) {
+    int e = k * p.dil;
+    kofs[k] = (e % p.stride) * p.seg + e / p.stride;
+  }
 
   for (int c0 = 0; c0 < p.cin_g; c0 += p.ci_chunk) {
     const int nci = min(p.ci_chunk, p.cin_g - c0);
     __syncthreads();
     for (int idx = threadIdx.x; idx < nci * p.span; idx += 256) {
       int ci = idx / p.span, i = idx - ci * p.span;
-      xs[idx] = fetch_padded(xb + (long long)(c0 + ci) * p.Tin, gt0 + i, p.Tin, p.pad_mode, p.in_slope);
+      float v = fetch_padded(xb + (long long)(c0 + ci) * p.Tin, gt0 + i, p.Tin, p.pad_mode, p.in_slope);
+      int pos = (p.stride == 1) ? i : (i % p.stride) * p.seg + i / p.stride;
+      xs[ci * p.span_p + pos] = v;
     }
     const int nwk = nci * p.K;
     for (int idx = threadIdx.x; idx < COB * nwk; idx += 256) {
@@ -107,10 +117,10 @@ __global__ void __launch_bounds__(256) conv_fwd_k(FwdP p, const float* __restric
     __syncthreads();
     if (row_active) {
       for (int ci = 0; ci < nci; ++ci) {
-        const float* xr = xs + ci * p.span + tx * p.stride;
+        const float* xr = xs + ci * p.span_p + tx;
         for (int k = 0; k < p.K; ++k) {
-          const float* xk = xr + k * p.dil;
-          float xv0 = xk[0], xv1 = xk[xstep], xv2 = xk[2 * xstep], xv3 = xk[3 * xstep];
+          const float* xk = xr + kofs[k];
+          float xv0 = xk[0], xv1 = xk[TX], xv2 = xk[2 * TX], xv3 = xk[3 * TX];
           const int r = ci * p.K + k;
           float wv[CO_T];
           if constexpr (CO_T % 4 == 0) {
@@ -159,15 +169,18 @@ static int launch_fwd_t(FwdP p, const float* x, const float* w, const float* bia
                         cudaStream_t st) {
   constexpr int TY = 256 / TX, TT = TX * 4, COB = TY * CO_T;
   p.span = (TT - 1) * p.stride + (p.K - 1) * p.dil + 1;
+  p.seg = (p.span + p.stride - 1) / p.stride;
+  p.span_p = p.seg * p.stride;
   const size_t budget = 64 * 1024;
   constexpr int WPITCH = (CO_T % 4 == 0) ? COB : COB + 1;
-  size_t per_ci = ((size_t)p.span + (size_t)p.K * WPITCH) * sizeof(float);
-  int chunk = (int)((budget - 16) / per_ci);
+  size_t per_ci = ((size_t)p.span_p + (size_t)p.K * WPITCH) * sizeof(float);
+  const size_t extra = 16 + (size_t)p.K * sizeof(int);
+  int chunk = (int)((budget - extra) / per_ci);
   if (chunk < 1) chunk = 1;
   if (chunk > p.cin_g) chunk = p.cin_g;
   if (chunk > 32) chunk = 32;
   p.ci_chunk = chunk;
-  size_t smem = per_ci * chunk + 16;
+  size_t smem = per_ci * chunk + extra;
   TDVC_CHECK_ARG(smem <= 200 * 1024);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
