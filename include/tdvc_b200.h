@@ -160,7 +160,9 @@ int tdvc_pack_cl_bf16(const float* x, void* xp, int B, int C, int T, int Cp /* r
                       the bias gradient falls out of packing dL/dy */, int c_off /* first channel written */,
                       int Cw /* channels written (>= C, zero filled; <= 0: Cp - c_off) */,
                       int ones_ch /* >= C: that channel is set to 1 on the T valid rows (bias gradient through
-                      the wgrad GEMM); -1: none */, void* stream);
+                      the wgrad GEMM); -1: none */,
+                      const float* film_gb /* optional [B,2C,T]: x*(1+gamma)+beta is applied before the LeakyReLU
+                      (FiLM + activation + pack in one pass, generator.py:104-108) */, void* stream);
 /* w[Cout,Cin,K] fp32 -> wp[K, Coutp, Cinp] bf16 (zero padded); transpose_flip!=0 produces the
  * dgrad operand wp[K, Cinp, Coutp] with taps reversed. */
 int tdvc_pack_weight_bf16(const float* w, void* wp, int Cout, int Cin, int K, int Coutp, int Cinp,

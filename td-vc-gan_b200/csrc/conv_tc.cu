@@ -688,7 +688,8 @@ __global__ void wgrad_finalize_k(const float* __restrict__ ws, float* __restrict
 template <int CH>
 __global__ void __launch_bounds__(256) pack_cl_bf16_k(const float* __restrict__ x, __nv_bfloat16* __restrict__ xp, int C,
                                                      int T, int Cp, int Tp, int halo, int pad_mode, float slope,
-                                                     float* __restrict__ chan_sum, int c_off, int Cw, int ones_ch) {
+                                                     float* __restrict__ chan_sum, int c_off, int Cw, int ones_ch,
+                                                     const float* __restrict__ film_gb) {
   constexpr int TL = 4096 / CH;             // time steps per tile: 64 / 128 / 256
   constexpr int RPW = CH / 8;               // channel rows per warp
   constexpr int LPR = TL / 32;              // loads per row per lane
@@ -713,7 +714,13 @@ __global__ void __launch_bounds__(256) pack_cl_bf16_k(const float* __restrict__ 
         bool ok = true;
         if (u < 0) { if (pad_mode == TDVC_PAD_REFLECT) { u = -u; ok = u < T; } else ok = false; }
         else if (u >= T) { if (pad_mode == TDVC_PAD_REFLECT) { u = 2 * (T - 1) - u; ok = u >= 0; } else ok = false; }
-        if (ok) v = __ldg(row + u);
+        if (ok) {
+          v = __ldg(row + u);
+          if (film_gb) {       // FiLM before the activation: h*(1+gamma)+beta, gb = [B, 2C, T]
+            const float* gp = film_gb + ((long long)b * 2 * C + c) * T + u;
+            v = fmaf(v, 1.f + __ldg(gp), __ldg(gp + (long long)C * T));
+          }
+        }
       }
       vals[r][l] = v;
     }
@@ -804,7 +811,8 @@ static int make_map_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d
 using namespace tdvc;
 
 extern "C" int tdvc_pack_cl_bf16(const float* x, void* xp, int B, int C, int T, int Cp, int halo, int pad_mode,
-                                 float in_slope, float* chan_sum, int c_off, int Cw, int ones_ch, void* stream) {
+                                 float in_slope, float* chan_sum, int c_off, int Cw, int ones_ch, const float* film_gb,
+                                 void* stream) {
   if (Cw <= 0) Cw = Cp - c_off;
   TDVC_CHECK_ARG(B >= 0 && C > 0 && T > 0 && Cw >= C && c_off >= 0 && c_off + Cw <= Cp && Cp % 8 == 0 && halo >= 0 && x && xp);
   TDVC_CHECK_ARG(ones_ch < 0 || (ones_ch >= C && ones_ch < Cw));
@@ -818,14 +826,17 @@ extern "C" int tdvc_pack_cl_bf16(const float* x, void* xp, int B, int C, int T, 
   // thin tensors: fewer channel rows, longer time tiles (same bytes in flight per CTA)
   if (C <= 16 && Cw <= 64) {
     dim3 grid(cdiv(Tp, 256), 1, B);
-    pack_cl_bf16_k<16><<<grid, 256, 0, st>>>(x, o, C, T, Cp, Tp, halo, pad_mode, in_slope, chan_sum, c_off, Cw, ones_ch);
+    pack_cl_bf16_k<16><<<grid, 256, 0, st>>>(x, o, C, T, Cp, Tp, halo, pad_mode, in_slope, chan_sum, c_off, Cw, ones_ch,
+                                             film_gb);
   } else if (C <= 32 && Cw <= 64) {
     dim3 grid(cdiv(Tp, 128), 1, B);
-    pack_cl_bf16_k<32><<<grid, 256, 0, st>>>(x, o, C, T, Cp, Tp, halo, pad_mode, in_slope, chan_sum, c_off, Cw, ones_ch);
+    pack_cl_bf16_k<32><<<grid, 256, 0, st>>>(x, o, C, T, Cp, Tp, halo, pad_mode, in_slope, chan_sum, c_off, Cw, ones_ch,
+                                             film_gb);
   } else {
     dim3 grid(cdiv(Tp, 64), cdiv(Cw, 64), B);
     TDVC_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535);
-    pack_cl_bf16_k<64><<<grid, 256, 0, st>>>(x, o, C, T, Cp, Tp, halo, pad_mode, in_slope, chan_sum, c_off, Cw, ones_ch);
+    pack_cl_bf16_k<64><<<grid, 256, 0, st>>>(x, o, C, T, Cp, Tp, halo, pad_mode, in_slope, chan_sum, c_off, Cw, ones_ch,
+                                             film_gb);
   }
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;

@@ -169,6 +169,13 @@ class FiLMResnetBlock(nn.Module):
         """`gb`: gamma|beta already computed for this block by the stage-level fused conditioning path
         (MRFBlock.forward); otherwise cond_var runs here."""
         h = self.conv[1](x, in_slope=self.conv[0].negative_slope)
+        pos = self.posconv[1]
+        if (c is None or c.ndim == 3) and x.is_cuda and ops.film_posconv_eligible(pos.in_channels) and pos.kernel_size == 1:
+            # bf16 mode: FiLM + LeakyReLU + pack in one pass, mask of the posconv dgrad in its epilogue
+            if gb is None and c is not None:
+                g = self.cond_var[0](c)
+                gb = self.cond_var[2](g, in_slope=self.cond_var[1].negative_slope)
+            return ops.film_posconv(h, gb, pos.effective_weight(), pos.bias, x, self.posconv[0].negative_slope)
         if gb is not None:
             h = ops.film(h, gb)
         elif c is not None:

@@ -668,7 +668,7 @@ def _pack_act(x, Cp, halo, pad_mode, slope, cache=True, chan_sum=None):
             return hit
     xp = torch.empty(B, T + 2 * halo, Cp, device=x.device, dtype=torch.bfloat16)
     _lib.check(_lib.load().tdvc_pack_cl_bf16(_p(x), _p(xp), B, Cc, T, Cp, halo, pad_mode, slope, _p(chan_sum), 0, 0, -1,
-                                             _st()), "pack_cl_bf16")
+                                             None, _st()), "pack_cl_bf16")
     if cache:
         _pack_cache.put(key, x, xp)
     return xp
@@ -816,7 +816,7 @@ class _MRFCondPath(torch.autograd.Function):
         C2p = _ceil(C2, 16)
         # operands
         cp = torch.empty(B, T, Cg, device=dev, dtype=torch.bfloat16)
-        _lib.check(lib.tdvc_pack_cl_bf16(_p(c), _p(cp), B, Cc, T, Cg, 0, PAD_ZEROS, 1.0, None, 0, Cg, Cc, _st()), "pack c")
+        _lib.check(lib.tdvc_pack_cl_bf16(_p(c), _p(cp), B, Cc, T, Cg, 0, PAD_ZEROS, 1.0, None, 0, Cg, Cc, None, _st()), "pack c")
         w0p = torch.empty(K, n * Cg, Cg, device=dev, dtype=torch.bfloat16)
         w2p = torch.empty(K, n * C2p, Cg, device=dev, dtype=torch.bfloat16)
         b0p = torch.zeros(n * Cg, device=dev, dtype=torch.float32)
@@ -863,7 +863,7 @@ class _MRFCondPath(torch.autograd.Function):
                 continue
             d = _c(dgb[j])
             _lib.check(lib.tdvc_pack_cl_bf16(_p(d), _p(dgbp), B, C2, T, n * C2p, 0, PAD_ZEROS, 1.0, _p(db2[j]), j * C2p, C2p,
-                                             -1, _st()), "pack dgb")
+                                             -1, None, _st()), "pack dgb")
         # cond_var.2 weight gradients
         dw2 = []
         ws = torch.empty(max(lib.tdvc_conv1d_tc_wgrad_ws(C2, Cc, K), lib.tdvc_conv1d_tc_wgrad_ws(n * Cg, Cc + 1, K)),
@@ -918,3 +918,84 @@ def mrf_cond_path(c, blocks_wb, slope=0.2):
 
 def mrf_cond_path_eligible(Cc, C2, T) -> bool:
     return _PRECISION == "bf16" and Cc >= 16 and C2 >= 16 and _ceil(C2, 16) <= 256
+
+
+# ----------------------------------------------------------------------------- fused FiLM + posconv
+
+class _FilmPosconvTC(torch.autograd.Function):
+    """out = conv1x1(leaky_relu(h0 * (1 + gamma) + beta)) + bias + x      (model/generator.py:104-109)
+
+    forward : ONE pass applies FiLM + LeakyReLU and writes the bf16 channels-last operand (no fp32 FiLM output, no
+              separate pack), then the tcgen05 1x1 conv with the residual add in its epilogue.
+    backward: dL/dout is packed once (also the bias gradient); the data-gradient conv applies the LeakyReLU mask in
+              its epilogue straight from the packed activation (no staging pass), the FiLM backward kernel yields
+              dL/dh0 and dL/d(gamma|beta)."""
+
+    @staticmethod
+    def forward(ctx, h0, gb, w, bias, x_res, slope):
+        _req(h0, gb, w, bias, x_res)
+        h0, gb, w, bias, x_res = _c(h0), _c(gb), _c(w), _c(bias), _c(x_res)
+        B, Cc, T = h0.shape
+        Cout = w.shape[0]
+        if w.shape[1] != Cc or w.shape[2] != 1:
+            raise RuntimeError("film_posconv: expects a 1x1 convolution")
+        if gb is not None and tuple(gb.shape) != (B, 2 * Cc, T):
+            raise RuntimeError(f"film: gamma/beta tensor {tuple(gb.shape)} does not match {tuple(h0.shape)}")
+        lib = _lib.load()
+        Cp, Coutp = _cp(Cc), _ceil(Cout, 16)
+        a1p = torch.empty(B, T, Cp, device=h0.device, dtype=torch.bfloat16)
+        _lib.check(lib.tdvc_pack_cl_bf16(_p(h0), _p(a1p), B, Cc, T, Cp, 0, PAD_ZEROS, slope, None, 0, 0, -1, _p(gb), _st()),
+                   "film_pack")
+        wp = _pack_w(w, Coutp, Cp, False)
+        y = torch.empty(B, Cout, T, device=h0.device, dtype=torch.float32)
+        _lib.check(lib.tdvc_conv1d_tc_fwd(_p(a1p), _p(wp), _p(bias), None, _p(x_res), _p(y), B, Cp, T, Cout, Coutp, T, 1, 1, 0,
+                                          ACT_NONE, 1.0, _st()), "posconv_tc_fwd")
+        ctx.slope = slope
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(h0, gb, w, a1p)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        h0, gb, w, a1p = ctx.saved_tensors
+        lib = _lib.load()
+        dy = _c(dy)
+        B, Cc, T = h0.shape
+        Cout = w.shape[0]
+        Cp = a1p.shape[2]
+        Cdp = _cp(Cout)
+        db = torch.empty(Cout, device=dy.device, dtype=torch.float32) if (ctx.has_bias and ctx.needs_input_grad[3]) else None
+        dyp = _pack_act(dy, Cdp, 0, PAD_ZEROS, 1.0, cache=False, chan_sum=db)
+        dw = None
+        if ctx.needs_input_grad[2]:
+            dw = torch.empty_like(w)
+            ws = torch.empty(lib.tdvc_conv1d_tc_wgrad_ws(Cout, Cc, 1), device=dy.device, dtype=torch.float32)
+            _lib.check(lib.tdvc_conv1d_tc_wgrad(_p(dyp), _p(a1p), _p(dw), _p(ws), B, Cdp, T, Cp, T, Cout, Cc, 1, 1, 0, 0, 0,
+                                                _st()), "posconv_tc_wgrad")
+        dh0 = dgb = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            Cinp16 = _ceil(Cc, 16)
+            wtp = _pack_w(w, Cinp16, Cdp, True)
+            dh1 = torch.empty(B, Cc, T, device=dy.device, dtype=torch.float32)
+            # LeakyReLU derivative from the sign of the packed activation, in the dgrad epilogue
+            _tc_conv(xp=dyp, wp=wtp, y=dh1, B=B, Tp=T, Tout=T, K=1, dilation=1, t_off=0, Cp_total=Cdp, groups=1, a_ch_off=0,
+                     a_ch_stride=0, Cinp_g=Cdp, Cout_g=Cc, Coutp_g=Cinp16, bias_stride=0, out_act=ACT_NONE, out_slope=1.0,
+                     out_packed=0, maskp=a1p, tm=T, cm=Cp, mask_halo=0, mask_ch_off=0, mask_ch_stride=0,
+                     mask_slope=ctx.slope)
+            if gb is not None:
+                dh0 = torch.empty_like(h0)
+                dgb = torch.empty_like(gb)
+                _lib.check(lib.tdvc_film_bwd(_p(dh1), _p(h0), _p(gb), _p(dh0), _p(dgb), B, Cc, T, _st()), "film_bwd")
+            else:
+                dh0 = dh1
+        dres = dy if ctx.needs_input_grad[4] else None
+        return dh0, dgb, dw, db, dres, None
+
+
+def film_posconv(h0, gb, weight, bias, x_res, slope=0.2):
+    return _FilmPosconvTC.apply(h0, gb, weight, bias, x_res, float(slope))
+
+
+def film_posconv_eligible(C) -> bool:
+    return (_PRECISION == "bf16" and C % 16 == 0 and tc_eligible(C, C, 1, 1)
+            and os.environ.get("TDVC_NO_FILM_FUSION") != "1")

@@ -219,3 +219,33 @@ def test_mrf_cond_path_fused(n, Cc, C, T, B):
     for blk_d, blk in zip(wd, ws):
         for td, t in zip(blk_d, blk):
             assert relerr(td.grad, t.grad) < 1e-2
+
+
+@pytest.mark.parametrize("C,T,B,with_gb", [(16, 300, 2, True), (64, 200, 2, True), (128, 130, 1, True), (32, 260, 2, False)])
+def test_film_posconv_fused(C, T, B, with_gb):
+    """FiLM + LeakyReLU + 1x1 conv + residual as one fused op (film_pack pass, tcgen05 conv, LeakyReLU mask in the
+    dgrad epilogue) against fp64 PyTorch, 1e-2."""
+    from tdvc import ops
+    h0 = rnd(B, C, T, seed=1).requires_grad_(True)
+    gb = (rnd(B, 2 * C, T, seed=2) * 0.5).requires_grad_(True) if with_gb else None
+    w = rnd(C, C, 1, seed=3, scale=C ** -0.5).requires_grad_(True)
+    b = rnd(C, seed=4, scale=0.1).requires_grad_(True)
+    x = rnd(B, C, T, seed=5).requires_grad_(True)
+    h1 = h0 * (1 + gb[:, :C]) + gb[:, C:] if with_gb else h0
+    ref = F.conv1d(F.leaky_relu(h1, 0.2), w, b) + x
+    proj = rnd(B, C, T, seed=6)
+    (ref * proj).sum().backward()
+    h0d, wd, bd, xd = dev(h0), dev(w), dev(b), dev(x)
+    gbd = dev(gb) if with_gb else None
+    assert ops.film_posconv_eligible(C)
+    y = ops.film_posconv(h0d, gbd, wd, bd, xd, 0.2)
+    torch.cuda.synchronize()
+    assert relerr(y, ref) < 1e-2
+    (y * proj.float().cuda()).sum().backward()
+    torch.cuda.synchronize()
+    assert relerr(h0d.grad, h0.grad) < 1e-2
+    assert relerr(wd.grad, w.grad) < 1e-2
+    assert relerr(bd.grad, b.grad) < 1e-2
+    assert relerr(xd.grad, x.grad) < 1e-6
+    if with_gb:
+        assert relerr(gbd.grad, gb.grad) < 1e-2
