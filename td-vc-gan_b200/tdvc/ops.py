@@ -355,8 +355,18 @@ class _Add3Scale(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         dy = _c(dy)
-        d = torch.empty_like(dy)
-        _lib.check(_lib.load().tdvc_add3_scale(_p(dy), None, None, _p(d), dy.numel(), ctx.alpha, _st()), "add3_scale_bwd")
+        lib = _lib.load()
+
+        def scaled():
+            d = torch.empty_like(dy)
+            _lib.check(lib.tdvc_add3_scale(_p(dy), None, None, _p(d), dy.numel(), ctx.alpha, _st()), "add3_scale_bwd")
+            return d
+        if _BRANCH_STREAMS:
+            # the summands' producers may live on different streams: autograd accumulates into a gradient in place once
+            # its CPU-side refcount drops to one, which would race with kernels another stream has only queued if the
+            # three branches were handed the same tensor -- give each its own
+            return (None,) + tuple(scaled() if i < ctx.n else None for i in range(3))
+        d = scaled()
         return (None, d) + tuple(d if i < ctx.n - 1 else None for i in range(2))
 
 
