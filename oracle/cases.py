@@ -25,6 +25,8 @@ _COMMON = dict(lambda_feat=2, lambda_spec=5, lambda_wave=0, lambda_latcls=0, lam
 HP_STAGE1 = dict(_COMMON, no_conv=False, lambda_rec=0, lambda_idt=5)
 HP_STAGE2_1 = dict(_COMMON, no_conv=True, lambda_rec=0, lambda_idt=20)
 HP_STAGE2_2 = dict(_COMMON, no_conv=False, lambda_rec=10, lambda_idt=1)
+# BASELINE.json config 2: conv_enc-stage2_1 with the latent classifier + gradient reversal switched on
+HP_LATCLS = dict(HP_STAGE2_1, lambda_latcls=1)
 
 
 def rand_like(t: torch.Tensor, tag: int, dtype=torch.float64) -> torch.Tensor:

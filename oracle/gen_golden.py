@@ -26,7 +26,7 @@ from model.discriminator import (CollaborativeMultibandDiscriminator,       # no
 from model.conditional_instance_norm import ConditionalInstanceNorm        # noqa: E402  (reference)
 import util.losses as ref_losses                                            # noqa: E402  (reference)
 from oracle.params import make_state_dict, make_batch                       # noqa: E402
-from oracle.cases import CASES, HP_STAGE1, HP_STAGE2_1, HP_STAGE2_2, rand_like  # noqa: E402
+from oracle.cases import CASES, HP_LATCLS, HP_STAGE1, HP_STAGE2_1, HP_STAGE2_2, rand_like  # noqa: E402
 
 OUT = os.path.join(REPO, "tests", "golden")
 os.makedirs(OUT, exist_ok=True)
@@ -187,7 +187,24 @@ def case_losses(name):
     save(name, mel=mel, dmel=a.grad, con=con, dX=X.grad, dY=Y.grad, raw0=raws[0], raw1=raws[1], feat=fl)
 
 
-def ref_step(G, D, b, hp, nspk):
+def case_latent_classifier(name):
+    """LatentClassifier + gradient reversal (model/latent_classifier.py:8-38, model/grad_rev.py:3-18)."""
+    from model.latent_classifier import LatentClassifier
+    nspk, cdim, B, T = 6, 16, 3, 28
+    m = LatentClassifier(nspk, cdim)
+    load(m, 9)
+    x = rand_like(torch.empty(B, cdim, T), 71).requires_grad_(True)
+    lab = torch.tensor([1, 4, 0])
+    out = m(x)
+    loss = F.cross_entropy(out, lab)
+    loss.backward()
+    full, st = grads_of(m, 20000)
+    save(name, out=out, loss=loss, dx=x.grad, grad=full, gstat=st,
+         keys=np.array(list(m.state_dict().keys())),
+         shapes=np.array([str(tuple(v.shape)) for v in m.state_dict().values()]))
+
+
+def ref_step(G, D, b, hp, nspk, C=None):
     """train.py:259-491 driven through the reference's own modules (lambda_f0 term = 0)."""
     x = b["signal_real"]
     c_src = F.one_hot(b["label_src"], nspk).double()
@@ -204,6 +221,13 @@ def ref_step(G, D, b, hp, nspk):
     (d_real + d_fake).backward()
     out["d_loss_real"], out["d_loss_fake"] = d_real.detach(), d_fake.detach()
     out["D_grad"] = grads_of(D, 0)[1]
+    if C is not None:      # latent classifier step, train.py:300-309
+        emb = G.content_embedding.clone()
+        c_loss = F.cross_entropy(C(emb.detach()), lab_s)
+        C.zero_grad()
+        c_loss.backward()
+        out["c_loss"] = c_loss.detach()
+        out["C_grad"] = grads_of(C, 0)[1]
     # G step (D weights NOT updated in between, so the fixture is optimiser-independent)
     fake, fake_subs = G(x, c_tgt, c_var=b["c_f0_conv"], out_subsample=True)
     emb_real = G.content_embedding.clone()
@@ -236,6 +260,10 @@ def ref_step(G, D, b, hp, nspk):
     finally:
         torch.randint = real_randint
     g_loss = g_adv + hp["lambda_rec"] * g_rec + hp["lambda_idt"] * g_idt + hp["lambda_cont_emb"] * g_cont
+    if C is not None and hp["lambda_latcls"] != 0:      # train.py:420-425 (through the gradient-reversal layer)
+        g_lat = F.cross_entropy(C(emb_real), lab_s)
+        out["g_latcls"] = g_lat.detach()
+        g_loss = g_loss + hp["lambda_latcls"] * g_lat
     D.zero_grad(); G.zero_grad()
     g_loss.backward()
     out.update(g_adv=g_adv.detach(), g_rec=g_rec.detach(), g_idt=g_idt.detach(), g_idt_feat=idt_feat.detach(),
@@ -248,9 +276,14 @@ def ref_step(G, D, b, hp, nspk):
 def case_step(name, cfg, hp):
     G, D = build_G(cfg), build_D(cfg)
     load(G, cfg["seed"]); load(D, cfg["seed"] + 100)
+    C = None
+    if hp["lambda_latcls"] != 0:
+        from model.latent_classifier import LatentClassifier
+        C = LatentClassifier(cfg["nspk"], cfg["content_dim"])
+        load(C, cfg["seed"] + 200)
     b = make_batch(cfg["B"], cfg["T"], cfg["nspk"], seed=cfg["seed"] + 1, frames_div=int(np.prod(cfg["ratios"])),
                    permute=not hp["no_conv"])
-    out = ref_step(G, D, b, hp, cfg["nspk"])
+    out = ref_step(G, D, b, hp, cfg["nspk"], C)
     save(name, **out)
 
 
@@ -262,9 +295,11 @@ if __name__ == "__main__":
     if want("msd_tiny"): case_discriminator("msd_tiny", CASES["d_tiny"], full_limit=20000, cls=MultiscaleDiscriminator)
     if want("cin"): case_cin("cin")
     if want("losses"): case_losses("losses")
+    if want("latcls"): case_latent_classifier("latcls")
     if want("g_full"): case_generator("g_full", CASES["g_full"], full_limit=4096)
     if want("d_full"): case_discriminator("d_full", CASES["d_full"], full_limit=4096)
     if want("step_tiny_s1"): case_step("step_tiny_s1", CASES["step_tiny"], HP_STAGE1)
     if want("step_tiny_s21"): case_step("step_tiny_s21", CASES["step_tiny"], HP_STAGE2_1)
     if want("step_tiny_s22"): case_step("step_tiny_s22", CASES["step_tiny"], HP_STAGE2_2)
+    if want("step_tiny_latcls"): case_step("step_tiny_latcls", CASES["step_tiny"], HP_LATCLS)
     if want("step_full_s1"): case_step("step_full_s1", CASES["step_full"], HP_STAGE1)

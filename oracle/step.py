@@ -95,6 +95,25 @@ def discriminator_shapes(cfg) -> dict:
     return S
 
 
+def latent_classifier_shapes(cfg) -> dict:
+    """Keys/shapes of LatentClassifier(nspk, content_dim), model/latent_classifier.py:8-32."""
+    S = {}
+    nf = cfg["content_dim"]
+    idx = 1
+    for _ in range(3):
+        prev, nf = nf, nf * 2
+        S[f"classifier.{idx}.bias"] = (nf,)
+        S[f"classifier.{idx}.weight_g"] = (nf, 1, 1)
+        S[f"classifier.{idx}.weight_v"] = (nf, prev, 21)
+        idx += 2
+    S[f"classifier.{idx}.bias"] = (nf,)
+    S[f"classifier.{idx}.weight_g"] = (nf, 1, 1)
+    S[f"classifier.{idx}.weight_v"] = (nf, nf, 5)
+    S[f"classifier.{idx + 2}.weight_g"] = (cfg["nspk"], 1, 1)
+    S[f"classifier.{idx + 2}.weight_v"] = (cfg["nspk"], nf, 3)
+    return S
+
+
 def make_models(cfg, dtype=torch.float64):
     sdG = make_state_dict(generator_shapes(cfg), seed=cfg["seed"], dtype=dtype)
     sdD = make_state_dict(discriminator_shapes(cfg), seed=cfg["seed"] + 100, dtype=dtype)
@@ -106,14 +125,16 @@ def step_batch(cfg, hp, dtype=torch.float64):
                       frames_div=int(np.prod(cfg["ratios"])), dtype=dtype, permute=not hp["no_conv"])
 
 
-def oracle_step(cfg, hp, dtype=torch.float64, sdG=None, sdD=None, batch=None) -> dict:
+def oracle_step(cfg, hp, dtype=torch.float64, sdG=None, sdD=None, batch=None, sdC=None) -> dict:
     """Runs the D-step and G-step losses and both backward passes.  Returns loss scalars,
-    'fake' and {'D_grad','G_grad'}: name -> grad tensor."""
+    'fake' and {'D_grad','G_grad'[,'C_grad']}: name -> grad tensor."""
     if sdG is None:
         sdG, sdD = make_models(cfg, dtype)
+    if sdC is None and hp.get("lambda_latcls", 0) != 0:
+        sdC = make_state_dict(latent_classifier_shapes(cfg), seed=cfg["seed"] + 200, dtype=dtype)
     if batch is None:
         batch = step_batch(cfg, hp, dtype)
-    for v in list(sdG.values()) + list(sdD.values()):
+    for v in list(sdG.values()) + list(sdD.values()) + list((sdC or {}).values()):
         v.requires_grad_(True)
         v.grad = None
     kw = dict(num_disc=cfg["num_disc"], num_layers=cfg["d_layers"])
@@ -122,9 +143,14 @@ def oracle_step(cfg, hp, dtype=torch.float64, sdG=None, sdD=None, batch=None) ->
     d["d_loss"].backward()
     out.update({k: v.detach() for k, v in d.items()})
     out["D_grad"] = {k: (v.grad.clone() if v.grad is not None else torch.zeros_like(v)) for k, v in sdD.items()}
-    for v in list(sdG.values()) + list(sdD.values()):
+    if sdC is not None:      # latent classifier step, train.py:300-309
+        c_loss = torch.nn.functional.cross_entropy(O.latent_classifier(sdC, d["emb"].detach()), batch["label_src"])
+        c_loss.backward()
+        out["c_loss"] = c_loss.detach()
+        out["C_grad"] = {k: v.grad.clone() for k, v in sdC.items()}
+    for v in list(sdG.values()) + list(sdD.values()) + list((sdC or {}).values()):
         v.grad = None
-    g = _g_step(sdG, sdD, batch, hp, cfg, kw)
+    g = _g_step(sdG, sdD, batch, hp, cfg, kw, sdC)
     g["g_loss"].backward()
     out.update({k: v.detach() for k, v in g.items()})
     out["G_grad"] = {k: (v.grad.clone() if v.grad is not None else torch.zeros_like(v)) for k, v in sdG.items()}
@@ -136,17 +162,17 @@ def _d_step(sdG, sdD, b, hp, cfg, kw):
     x = b["signal_real"]
     nspk = cfg["nspk"]
     c_tgt = O.one_hot(b["label_tgt"], nspk, x.dtype)
-    fake, fake_subs, _ = O.generator(sdG, x, c_tgt, b["c_f0_conv"], cfg["ratios"])
+    fake, fake_subs, emb = O.generator(sdG, x, c_tgt, b["c_f0_conv"], cfg["ratios"])
     o_real, _ = O.cmb_discriminator(sdD, x, b["label_src"], O.cmb_subsamples(x, cfg["num_disc"]), **kw)
     # reference passes the heads un-detached (train.py:269); the G grads that deposits are zeroed before
     # G's own backward (train.py:485-486) so detaching changes no result, only skips dead work.
     subs_in = fake_subs if hp.get("faithful_waste") else [s.detach() for s in fake_subs]
     o_fake, _ = O.cmb_discriminator(sdD, fake.detach(), b["label_tgt"], subs_in, **kw)
     d_real, d_fake = O.lsgan_d_loss(o_real, o_fake)
-    return {"d_loss_real": d_real, "d_loss_fake": d_fake, "d_loss": d_real + d_fake, "fake": fake}
+    return {"d_loss_real": d_real, "d_loss_fake": d_fake, "d_loss": d_real + d_fake, "fake": fake, "emb": emb}
 
 
-def _g_step(sdG, sdD, b, hp, cfg, kw):
+def _g_step(sdG, sdD, b, hp, cfg, kw, sdC=None):
     """train.py:320-480 (lambda_f0 = 0, lambda_latcls = 0, lambda_wave = 0 as shipped)."""
     x = b["signal_real"]
     nspk, ratios = cfg["nspk"], cfg["ratios"]
@@ -186,4 +212,7 @@ def _g_step(sdG, sdD, b, hp, cfg, kw):
     out.update(g_adv=g_adv, g_rec=g_rec, g_idt=g_idt, g_cont=g_cont)
     out["g_loss"] = (g_adv + hp["lambda_rec"] * g_rec + hp["lambda_idt"] * g_idt
                      + hp["lambda_cont_emb"] * g_cont)
+    if sdC is not None and hp.get("lambda_latcls", 0) != 0:      # train.py:420-425, through gradient reversal
+        out["g_latcls"] = torch.nn.functional.cross_entropy(O.latent_classifier(sdC, emb_real), lab_s)
+        out["g_loss"] = out["g_loss"] + hp["lambda_latcls"] * out["g_latcls"]
     return out

@@ -279,6 +279,32 @@ def multiscale_discriminator(sd: SD, x: torch.Tensor, label: torch.Tensor, *, nu
     return outs, feats
 
 
+def latent_classifier(sd: SD, x: torch.Tensor, *, num_layers: int = 3, down: int = 2) -> torch.Tensor:
+    """LatentClassifier.forward, model/latent_classifier.py:34-38: gradient reversal (identity forward,
+    model/grad_rev.py:5-10), 3 x (wn Conv k=21 s=2 p=10 + LeakyReLU), wn Conv k5, LeakyReLU, wn Conv k3 (no bias),
+    global average pool over time."""
+    x = GradRev.apply(x)
+    idx = 1
+    for _ in range(num_layers):
+        x = lrelu(conv(sd, f"classifier.{idx}", x, stride=down, padding=down * 5))
+        idx += 2
+    x = lrelu(conv(sd, f"classifier.{idx}", x, padding=2))
+    x = conv(sd, f"classifier.{idx + 2}", x, padding=1)
+    return x.mean(dim=2)
+
+
+class GradRev(torch.autograd.Function):
+    """model/grad_rev.py:3-10: identity forward, negated gradient."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return -g
+
+
 # ----------------------------------------------------------------------------- losses
 
 def lsgan_d_loss(outs_real: Sequence[torch.Tensor], outs_fake: Sequence[torch.Tensor]):

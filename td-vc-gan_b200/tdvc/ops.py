@@ -487,6 +487,37 @@ def cond_instance_norm(x, gb, eps=1e-5, out_slope=1.0):
     return _CinApply.apply(x, gb, float(eps), float(out_slope))
 
 
+class _TimeMean(torch.autograd.Function):
+    """x[B,C,T] -> mean over T: F.avg_pool1d(x, x.size(2)).squeeze(2) (model/latent_classifier.py:36).  Forward is the
+    row-mean half of the instance-norm statistics kernel, backward a broadcast."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _req(x)
+        x = _c(x)
+        B, Cc, T = x.shape
+        mean = torch.empty(B * Cc, device=x.device, dtype=torch.float32)
+        rstd = torch.empty_like(mean)
+        _lib.check(_lib.load().tdvc_instnorm_stats(_p(x), _p(mean), _p(rstd), B * Cc, T, 1.0, _st()), "time_mean")
+        ctx.dims = (B, Cc, T)
+        return mean.view(B, Cc)
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, Cc, T = ctx.dims
+        dy = _c(dy)
+        lib = _lib.load()
+        d = torch.empty_like(dy)
+        _lib.check(lib.tdvc_add3_scale(_p(dy), None, None, _p(d), dy.numel(), 1.0 / T, _st()), "time_mean_bwd scale")
+        dx = torch.empty(B, Cc, T, device=dy.device, dtype=torch.float32)
+        _lib.check(lib.tdvc_cond_concat_fwd(_p(d), None, _p(dx), B, Cc, 0, T, 1, _st()), "time_mean_bwd broadcast")
+        return dx
+
+
+def time_mean(x):
+    return _TimeMean.apply(x)
+
+
 # ----------------------------------------------------------------------------- pooling / gather
 
 class _AvgPool(torch.autograd.Function):

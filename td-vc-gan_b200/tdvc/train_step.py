@@ -36,12 +36,16 @@ def frozen(module: torch.nn.Module):
 
 class TrainStep:
     def __init__(self, G, D, hp: dict, optimizer_G=None, optimizer_D=None, num_spk: Optional[int] = None,
-                 grad_hook=None):
+                 grad_hook=None, C=None, optimizer_C=None):
         """hp: the `train:` section of a config/*.yaml as a dict (lambda_*, no_conv, jitter_amp ...).
         grad_hook(module_name, params) is called after each backward and before the optimiser step: the
         data-parallel gradient all-reduce plugs in there."""
         self.G, self.D, self.hp = G, D, hp
         self.opt_G, self.opt_D = optimizer_G, optimizer_D
+        # latent classifier (train.py:153-154,192): only when lambda_latcls != 0
+        self.C, self.opt_C = C, optimizer_C
+        if hp.get("lambda_latcls", 0) != 0 and C is None:
+            raise ValueError("lambda_latcls != 0 needs the LatentClassifier C")
         self.num_spk = num_spk if num_spk is not None else G.embedding.weight.shape[1]
         self.grad_hook = grad_hook
 
@@ -63,7 +67,20 @@ class TrainStep:
     def d_step(self, batch) -> dict:
         out = self.d_forward_backward(batch)
         self._reduce_and_step("D", self.D, self.opt_D)
+        if self.C is not None and self.hp.get("lambda_latcls", 0) != 0:
+            out.update(self.c_step(batch, out["emb_real"]))
         return out
+
+    def c_step(self, batch, emb_real) -> dict:
+        """Latent classifier update, train.py:300-309 (the embedding comes from the D-step generator pass and carries
+        no graph here, so only C receives gradients -- the reference zeroes what it deposits in G)."""
+        out_lat = self.C(emb_real.detach())
+        c_loss = torch.nn.functional.cross_entropy(out_lat, batch["label_src"])
+        if self.opt_C is not None:
+            self.opt_C.zero_grad(set_to_none=True)
+        c_loss.backward()
+        self._reduce_and_step("C", self.C, self.opt_C)
+        return {"c_loss": c_loss.detach()}
 
     def d_forward_backward(self, batch) -> dict:
         with ops.step_cache():
@@ -82,6 +99,7 @@ class TrainStep:
         # are zeroed before G's own backward (train.py:485-486).  no_grad skips that dead graph.
         with torch.no_grad():
             fake, fake_subs = G(x, c_tgt, c_var=batch["c_f0_conv"], out_subsample=True)
+            emb_real = getattr(G, "content_embedding", None)
             real_subs = D.get_subsamples(x)
         o_real, _ = D(x, batch["label_src"], real_subs)
         o_fake, _ = D(fake, batch["label_tgt"], fake_subs)
@@ -92,7 +110,7 @@ class TrainStep:
             self.opt_D.zero_grad(set_to_none=True)
         d_loss.backward()
         return {"d_loss_real": d_real.detach(), "d_loss_fake": d_fake.detach(), "d_loss": d_loss.detach(),
-                "fake": fake}
+                "fake": fake, "emb_real": emb_real}
 
     # ---- G step: train.py:320-491 (lambda_f0 needs torchcrepe, lambda_latcls the latent classifier: both 0 here)
     def g_step(self, batch, raw_draws=None) -> dict:
@@ -142,6 +160,13 @@ class TrainStep:
                 g_cont = g_cont + losses.contrastive_loss(emb_real, emb_corr, num_negatives=100, temp=0.1,
                                                           _raw_draws=raw_draws)
             g_loss = g_adv + hp["lambda_rec"] * g_rec + hp["lambda_idt"] * g_idt + hp["lambda_cont_emb"] * g_cont
+            if self.C is not None and hp.get("lambda_latcls", 0) != 0:
+                # train.py:420-425: speaker classification of the content embedding through the gradient-reversal
+                # layer; C's own weights are not updated by this loss (optimizer_C.step() is not called here)
+                with frozen(self.C):
+                    g_lat = torch.nn.functional.cross_entropy(self.C(emb_real), lab_s)
+                out["g_latcls"] = g_lat.detach()
+                g_loss = g_loss + hp["lambda_latcls"] * g_lat
             if self.opt_G is not None:
                 self.opt_G.zero_grad(set_to_none=True)
             g_loss.backward()

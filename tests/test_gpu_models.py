@@ -10,7 +10,7 @@ import torch
 import torch.nn.functional as F
 
 from helpers import golden, golden_shapes, relerr, stats
-from oracle.cases import CASES, HP_STAGE1, HP_STAGE2_1, HP_STAGE2_2, rand_like
+from oracle.cases import CASES, HP_LATCLS, HP_STAGE1, HP_STAGE2_1, HP_STAGE2_2, rand_like
 from oracle.params import make_batch, make_state_dict
 from test_host_cpu import build_D, build_G
 
@@ -161,9 +161,16 @@ def _run_step(cfg, hp):
     b = make_batch(cfg["B"], cfg["T"], cfg["nspk"], seed=cfg["seed"] + 1, frames_div=int(np.prod(cfg["ratios"])),
                    permute=not hp["no_conv"])
     bd = {k: (cu(v) if torch.is_tensor(v) else v) for k, v in b.items()}
-    ts = TrainStep(G, D, hp, None, None, cfg["nspk"])     # no optimiser: goldens were taken without a D update
+    C = None
+    if hp["lambda_latcls"] != 0:
+        from model.latent_classifier import LatentClassifier
+        C = load_det(LatentClassifier(cfg["nspk"], cfg["content_dim"]), cfg["seed"] + 200)
+    ts = TrainStep(G, D, hp, None, None, cfg["nspk"], C=C)     # no optimiser: goldens were taken without a D update
     out = ts.d_step(bd)
     out["D_grad"] = {k: p.grad.clone() for k, p in D.named_parameters()}
+    if C is not None:
+        out["C_grad"] = {k: p.grad.clone() for k, p in C.named_parameters()}
+        C.zero_grad()
     D.zero_grad(); G.zero_grad()
     out.update(ts.g_step(bd, raw_draws=b["neg_idx"]))
     out["G_grad"] = {k: (p.grad.clone() if p.grad is not None else torch.zeros_like(p)) for k, p in G.named_parameters()}
@@ -173,10 +180,14 @@ def _run_step(cfg, hp):
 @pytest.mark.parametrize("name,hp,case", [("step_tiny_s1", HP_STAGE1, "step_tiny"),
                                           ("step_tiny_s21", HP_STAGE2_1, "step_tiny"),
                                           ("step_tiny_s22", HP_STAGE2_2, "step_tiny"),
+                                          ("step_tiny_latcls", HP_LATCLS, "step_tiny"),
                                           ("step_full_s1", HP_STAGE1, "step_full")])
 def test_train_step_vs_golden(name, hp, case):
     g = golden(name)
     out = _run_step(CASES[case], hp)
+    if hp["lambda_latcls"] != 0:      # BASELINE config 2: latent classifier + gradient reversal
+        for k in ("c_loss", "g_latcls"):
+            assert abs(float(out[k]) - float(g[k])) <= 2e-5 * max(1.0, abs(float(g[k]))), k
     for k in ("d_loss_real", "d_loss_fake", "g_adv", "g_idt", "g_cont", "g_rec", "g_loss"):
         ref = float(np.asarray(g[k]).reshape(-1)[0])
         got = float(out[k])
@@ -186,7 +197,7 @@ def test_train_step_vs_golden(name, hp, case):
     # 4e-6, p99 1.4e-3, max 3.7e-3 (L1 / leaky-ReLU kinks, cancelling bias sums), so: 90 % of tensors within
     # 1e-4 and every tensor within 1e-2 of the fp64 reference norm.
     errs = []
-    for which in ("D", "G"):
+    for which in ("D", "G") + (("C",) if hp["lambda_latcls"] != 0 else ()):
         for k, gr in out[which + "_grad"].items():
             ref = g[f"{which}_grad/{k}"]
             if ref[2] < 1e-12:
@@ -269,3 +280,20 @@ def test_graphed_step_equals_eager_step():
     assert abs(gl_e - gl_g) <= 1e-4 * abs(gl_e) and abs(dl_e - dl_g) <= 1e-4 * abs(dl_e)
     for k in sd_e:
         assert relerr(sd_g[k], sd_e[k]) < 1e-4, k      # atomics in wgrad reorder fp32 sums run to run
+
+
+def test_latent_classifier_vs_golden():
+    """LatentClassifier + gradient-reversal layer on the tdvc kernels vs the reference."""
+    from model.latent_classifier import LatentClassifier
+    g = golden("latcls")
+    m = LatentClassifier(6, 16)
+    assert list(m.state_dict().keys()) == [str(k) for k in g["keys"]]
+    m = load_det(m, 9)
+    x = cu(rand_like(torch.empty(3, 16, 28), 71)).requires_grad_(True)
+    out = m(x)
+    assert relerr(out, g["out"]) < TOL
+    loss = F.cross_entropy(out, torch.tensor([1, 4, 0]).cuda())
+    assert abs(loss.item() - float(g["loss"])) < 1e-5
+    loss.backward()
+    assert relerr(x.grad, g["dx"]) < 2e-5
+    check_grads(m, g, 1e-4, 2e-5)

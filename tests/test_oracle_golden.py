@@ -8,7 +8,7 @@ import torch.nn.functional as F
 
 from helpers import golden, golden_shapes, relerr, stats
 from oracle import tdvc_oracle as O
-from oracle.cases import CASES, HP_STAGE1, HP_STAGE2_1, HP_STAGE2_2, rand_like
+from oracle.cases import CASES, HP_LATCLS, HP_STAGE1, HP_STAGE2_1, HP_STAGE2_2, rand_like
 from oracle.params import make_batch, make_state_dict
 
 TOL = 1e-9
@@ -154,6 +154,7 @@ def test_losses():
 @pytest.mark.parametrize("name,hp,case", [("step_tiny_s1", HP_STAGE1, "step_tiny"),
                                           ("step_tiny_s21", HP_STAGE2_1, "step_tiny"),
                                           ("step_tiny_s22", HP_STAGE2_2, "step_tiny"),
+                                          ("step_tiny_latcls", HP_LATCLS, "step_tiny"),
                                           ("step_full_s1", HP_STAGE1, "step_full")])
 def test_train_step(name, hp, case):
     """One G+D iteration (train.py:259-491) against the reference's own modules driven by
@@ -167,7 +168,10 @@ def test_train_step(name, hp, case):
         got = float(out[k])
         assert abs(got - ref) <= 1e-9 * max(1.0, abs(ref)), (k, got, ref)
     assert relerr(out["fake"], g["fake"]) < TOL
-    for which in ("D", "G"):
+    if hp["lambda_latcls"] != 0:
+        for k in ("c_loss", "g_latcls"):
+            assert abs(float(out[k]) - float(g[k])) <= 1e-9 * max(1.0, abs(float(g[k]))), k
+    for which in ("D", "G") + (("C",) if hp["lambda_latcls"] != 0 else ()):
         for k, gr in out[which + "_grad"].items():
             ref = g[f"{which}_grad/{k}"]
             got = stats(gr)
@@ -189,3 +193,18 @@ def test_state_dict_layout(gname, case, which):
         assert len(ref) == 743
     if case == "d_full":
         assert len(ref) == 60
+
+
+def test_latent_classifier():
+    """LatentClassifier + gradient reversal."""
+    g = golden("latcls")
+    sd = _sd(g, 9)
+    B, cdim, T = 3, 16, 28
+    x = rand_like(torch.empty(B, cdim, T), 71).requires_grad_(True)
+    out = O.latent_classifier(sd, x)
+    assert relerr(out, g["out"]) < TOL
+    loss = F.cross_entropy(out, torch.tensor([1, 4, 0]))
+    assert abs(loss.item() - float(g["loss"])) < 1e-10
+    loss.backward()
+    assert relerr(x.grad, g["dx"]) < TOL          # sign-reversed gradient
+    _check_grads(g, sd)
