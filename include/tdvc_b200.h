@@ -143,6 +143,13 @@ int tdvc_abs_diff_sum(const float* a, const float* b, float scale, float* out_su
 int tdvc_abs_diff_bwd(const float* a, const float* b, float scale, const float* gscale, float* da,
                       int64_t n, void* stream);
 
+/* ---- contrastive (InfoNCE) loss over content-embedding frames, util/losses.py:70-116: gather of in-utterance
+ *      negatives + cosine similarities + cross-entropy in one kernel.  One direction per call: anchors A, positives
+ *      P (both [B,C,T]), raw[B,T,N] = the reference's torch.randint(0, T-1) draws.  loss_sum[0] += scale * sum of
+ *      per-frame CE; dA / dP (optional, [B,C,T]) += scale * gradient.  Caller zeroes the accumulators. */
+int tdvc_contrastive_dir(const float* A, const float* P, const int64_t* raw, float* loss_sum, float* dA, float* dP,
+                         int B, int C, int T, int N, float scale, void* stream);
+
 /* ---- fused multi-tensor AdamW (torch.optim.AdamW at train.py:188-189): one launch for a whole
  *      parameter list.  ptr tables are DEVICE arrays of n_tensors pointers / sizes.             */
 int tdvc_adamw_multi(float* const* params, const float* const* grads, float* const* exp_avg,

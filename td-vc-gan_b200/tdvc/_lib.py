@@ -77,6 +77,7 @@ SIGNATURES = {
     "tdvc_sq_err_const_bwd": (_I, [_P, _F, _F, _P, _P, _L, _P]),
     "tdvc_abs_diff_sum": (_I, [_P, _P, _F, _P, _L, _P]),
     "tdvc_abs_diff_bwd": (_I, [_P, _P, _F, _P, _P, _L, _P]),
+    "tdvc_contrastive_dir": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
     "tdvc_adamw_multi": (_I, [_P, _P, _P, _P, _P, _I, _L, _F, _F, _F, _F, _F, _I, _F, _P, _P]),
     "tdvc_pack_cl_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _I, _I, _I, _P, _P]),
     "tdvc_pack_weight_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),

@@ -652,6 +652,53 @@ class _L1MeanSum(torch.autograd.Function):
         return (None, *grads, *([None] * n))
 
 
+class _Contrastive(torch.autograd.Function):
+    """util/losses.py:70-116 as one kernel per direction (value and unit gradients computed together)."""
+
+    @staticmethod
+    def forward(ctx, X, Y, raw_X, raw_Y):
+        _req(X, Y)
+        X, Y = _c(X), _c(Y)
+        B, Cc, T = X.shape
+        N = raw_X.shape[-1]
+        if Y.shape != X.shape or tuple(raw_X.shape) != (B, T, N) or tuple(raw_Y.shape) != (B, T, N):
+            raise RuntimeError("contrastive_loss: shape mismatch")
+        raw_X, raw_Y = raw_X.contiguous(), raw_Y.contiguous()
+        lib = _lib.load()
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        buf = torch.zeros(1 + (2 * X.numel() if need else 0), device=X.device, dtype=torch.float32)
+        loss = buf[:1]
+        dX = buf[1:1 + X.numel()].view_as(X) if need else None
+        dY = buf[1 + X.numel():].view_as(Y) if need else None
+        scale = 1.0 / (2 * B * T)
+        _lib.check(lib.tdvc_contrastive_dir(_p(X), _p(Y), _p(raw_X), _p(loss), _p(dX), _p(dY), B, Cc, T, N, scale, _st()),
+                   "contrastive X->Y")
+        _lib.check(lib.tdvc_contrastive_dir(_p(Y), _p(X), _p(raw_Y), _p(loss), _p(dY), _p(dX), B, Cc, T, N, scale, _st()),
+                   "contrastive Y->X")
+        if need:
+            ctx.save_for_backward(dX, dY)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        dX, dY = ctx.saved_tensors
+        g = float(1.0) if g is None else g
+        lib = _lib.load()
+        outs = []
+        for d, need in ((dX, ctx.needs_input_grad[0]), (dY, ctx.needs_input_grad[1])):
+            if not need:
+                outs.append(None)
+                continue
+            o = d * g        # scalar upstream gradient (a device tensor): one small elementwise op
+            outs.append(o)
+        return outs[0], outs[1], None, None
+
+
+def contrastive_loss(X, Y, raw_X, raw_Y):
+    """InfoNCE over frames with in-utterance negatives given by the raw randint draws [B,T,N] (int64)."""
+    return _Contrastive.apply(X, Y, raw_X, raw_Y)
+
+
 def l1_mean_sum(sig: Sequence[torch.Tensor], ref: Sequence[torch.Tensor]) -> torch.Tensor:
     sig, ref = list(sig), [r.detach() for r in ref]
     return _L1MeanSum.apply(len(sig), *sig, *ref)

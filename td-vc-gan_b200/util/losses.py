@@ -74,26 +74,12 @@ def multiscale_spec_loss(signal, ref, fft_sizes, spectype='both', return_separat
 def contrastive_loss(sig_X, sig_Y, num_negatives=100, temp=1, _raw_draws=None):
     """InfoNCE over time frames with in-utterance negatives (reference util/losses.py:70-116).  `temp` is
     accepted and, as in the reference, not applied (its inner call drops it).  `_raw_draws` (not in the
-    reference's signature) lets a test supply the two torch.randint draws so both sides share them."""
-    draws = list(_raw_draws) if _raw_draws is not None else None
-
-    def negatives(X):
-        B, Cc, T = X.shape
-        with torch.no_grad():
-            if draws is not None:
-                idx = draws.pop(0).to(X.device).clone()
-            else:
-                idx = torch.randint(low=0, high=T - 1, size=(B, T, num_negatives), device=X.device)
-            own = torch.arange(T, device=X.device).unsqueeze(-1).expand(-1, num_negatives)
-            idx = idx + (idx >= own).to(idx.dtype)      # skip self; mask-free form (no host sync, graph-capturable)
-            return X.unsqueeze(2).expand(-1, -1, T, -1).gather(3, idx.unsqueeze(1).expand(-1, Cc, -1, -1))
-
-    def logits(X, Y, negs):
-        cand = torch.cat([Y.unsqueeze(-1), negs], dim=-1)
-        return F.cosine_similarity(X.unsqueeze(-1), cand, dim=1)
-
-    negs_X = negatives(sig_X)
-    negs_Y = negatives(sig_Y)
-    lg = torch.cat((logits(sig_X, sig_Y, negs_X), logits(sig_Y, sig_X, negs_Y)), dim=0)
-    target = torch.zeros(lg.shape[:-1], dtype=torch.long, device=lg.device)
-    return F.cross_entropy(lg.transpose(1, 2), target)
+    reference's signature) lets a test supply the two torch.randint draws so both sides share them.
+    The gather + cosine + cross-entropy run as one tdvc kernel per direction; the random draws stay torch."""
+    B, Cc, T = sig_X.shape
+    if _raw_draws is not None:
+        raw_X, raw_Y = (d.to(sig_X.device) for d in _raw_draws)
+    else:
+        raw_X = torch.randint(low=0, high=T - 1, size=(B, T, num_negatives), device=sig_X.device)
+        raw_Y = torch.randint(low=0, high=T - 1, size=(B, T, num_negatives), device=sig_X.device)
+    return ops.contrastive_loss(sig_X, sig_Y, raw_X, raw_Y)
