@@ -187,6 +187,30 @@ def case_losses(name):
     save(name, mel=mel, dmel=a.grad, con=con, dX=X.grad, dY=Y.grad, raw0=raws[0], raw1=raws[1], feat=fl)
 
 
+def case_legacy_blocks(name):
+    """DecoderResnetBlock / TranformResnetBlock / ResnetBlock (model/generator.py:11-67): constructible legacy blocks that
+    no shipped config instantiates; pinned so the drop-in constructors stay honest."""
+    from model.generator import DecoderResnetBlock, TranformResnetBlock, ResnetBlock
+    import torch.nn as nn
+    C, B, T = 10, 2, 64
+    out = {}
+    for i, (tag, mk) in enumerate((("dec", lambda: DecoderResnetBlock(C, dilation=3)),
+                                   ("trf", lambda: TranformResnetBlock(C, dilation=1)),
+                                   ("res", lambda: ResnetBlock(C, dilation=3, weight_norm=nn.utils.weight_norm)))):
+        m = mk()
+        load(m, 20 + i)
+        x = rand_like(torch.empty(B, C, T), 81).requires_grad_(True)
+        y = m(x)
+        (y * rand_like(y, 82)).sum().backward()
+        out[tag + "_y"] = y
+        out[tag + "_dx"] = x.grad
+        out[tag + "_keys"] = np.array(list(m.state_dict().keys()))
+        out[tag + "_shapes"] = np.array([str(tuple(v.shape)) for v in m.state_dict().values()])
+        for k, p_ in m.named_parameters():
+            out[f"{tag}_grad/{k}"] = p_.grad.detach().double().numpy()
+    save(name, **out)
+
+
 def case_latent_classifier(name):
     """LatentClassifier + gradient reversal (model/latent_classifier.py:8-38, model/grad_rev.py:3-18)."""
     from model.latent_classifier import LatentClassifier
@@ -296,6 +320,7 @@ if __name__ == "__main__":
     if want("cin"): case_cin("cin")
     if want("losses"): case_losses("losses")
     if want("latcls"): case_latent_classifier("latcls")
+    if want("legacy"): case_legacy_blocks("legacy")
     if want("g_full"): case_generator("g_full", CASES["g_full"], full_limit=4096)
     if want("d_full"): case_discriminator("d_full", CASES["d_full"], full_limit=4096)
     if want("step_tiny_s1"): case_step("step_tiny_s1", CASES["step_tiny"], HP_STAGE1)

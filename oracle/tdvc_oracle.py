@@ -121,6 +121,29 @@ def cin_resnet_block(sd: SD, prefix: str, x: torch.Tensor, c: torch.Tensor, *, d
     return h + conv(sd, prefix + ".shortcut", x)
 
 
+# ----------------------------------------------------------------------------- legacy residual blocks
+
+def decoder_resnet_block(sd: SD, prefix: str, x: torch.Tensor, *, dilation: int = 1) -> torch.Tensor:
+    """DecoderResnetBlock.forward, model/generator.py:11-26 (k=3, reflect pad = dilation, wn 1x1 shortcut)."""
+    h = conv(sd, prefix + ".block.1", lrelu(x), dilation=dilation, padding=dilation, reflect=True)
+    h = conv(sd, prefix + ".block.3", lrelu(h))
+    return h + conv(sd, prefix + ".shortcut", x)
+
+
+def transform_resnet_block(sd: SD, prefix: str, x: torch.Tensor, *, dilation: int = 1) -> torch.Tensor:
+    """TranformResnetBlock.forward, model/generator.py:29-46 (relu-conv-norm order, InstanceNorm1d)."""
+    h = instance_norm(conv(sd, prefix + ".block.1", lrelu(x), dilation=dilation, padding=dilation, reflect=True))
+    h = instance_norm(conv(sd, prefix + ".block.4", lrelu(h)))
+    return h + conv(sd, prefix + ".shortcut", x)
+
+
+def resnet_block(sd: SD, prefix: str, x: torch.Tensor, *, dilation: int = 1) -> torch.Tensor:
+    """ResnetBlock.forward, model/generator.py:48-67 (norm-relu-conv, identity shortcut)."""
+    h = conv(sd, prefix + ".block.2", lrelu(instance_norm(x)), dilation=dilation, padding=dilation, reflect=True)
+    h = conv(sd, prefix + ".block.5", lrelu(instance_norm(h)))
+    return h + x
+
+
 # ----------------------------------------------------------------------------- generator blocks
 
 def film_block(sd: SD, prefix: str, x: torch.Tensor, c: Optional[torch.Tensor], *, kernel_size: int,

@@ -297,3 +297,27 @@ def test_latent_classifier_vs_golden():
     loss.backward()
     assert relerr(x.grad, g["dx"]) < 2e-5
     check_grads(m, g, 1e-4, 2e-5)
+
+
+def test_legacy_blocks_vs_golden():
+    """The constructible-but-unused residual blocks of model/generator.py:11-67 on the tdvc kernels."""
+    import torch.nn as nn
+    from model.generator import DecoderResnetBlock, ResnetBlock, TranformResnetBlock
+    g = golden("legacy")
+    mk = {"dec": lambda: DecoderResnetBlock(10, dilation=3), "trf": lambda: TranformResnetBlock(10, dilation=1),
+          "res": lambda: ResnetBlock(10, dilation=3, weight_norm=nn.utils.weight_norm)}
+    for i, (tag, f) in enumerate(mk.items()):
+        m = f()
+        assert list(m.state_dict().keys()) == [str(k) for k in g[tag + "_keys"]], tag
+        m = load_det(m, 20 + i)
+        x = cu(rand_like(torch.empty(2, 10, 64), 81)).requires_grad_(True)
+        y = m(x)
+        assert relerr(y, g[tag + "_y"]) < TOL, tag
+        (y * cu(rand_like(y, 82))).sum().backward()
+        assert relerr(x.grad, g[tag + "_dx"]) < 5e-5, tag
+        for k, p in m.named_parameters():
+            ref = g[f"{tag}_grad/{k}"]
+            if np.abs(ref).max() < 1e-10:          # bias in front of an instance norm: analytically zero
+                assert p.grad.abs().max().item() < 1e-4
+            else:
+                assert relerr(p.grad, ref) < 5e-5, (tag, k)

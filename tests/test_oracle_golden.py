@@ -208,3 +208,20 @@ def test_latent_classifier():
     loss.backward()
     assert relerr(x.grad, g["dx"]) < TOL          # sign-reversed gradient
     _check_grads(g, sd)
+
+
+def test_legacy_blocks():
+    """DecoderResnetBlock / TranformResnetBlock / ResnetBlock."""
+    import ast
+    g = golden("legacy")
+    fns = {"dec": (O.decoder_resnet_block, 3), "trf": (O.transform_resnet_block, 1), "res": (O.resnet_block, 3)}
+    for i, (tag, (fn, dil)) in enumerate(fns.items()):
+        shapes = {str(k): ast.literal_eval(str(s)) for k, s in zip(g[tag + "_keys"], g[tag + "_shapes"])}
+        sd = {("m." + k): v.requires_grad_(True) for k, v in make_state_dict(shapes, seed=20 + i).items()}
+        x = rand_like(torch.empty(2, 10, 64), 81).requires_grad_(True)
+        y = fn(sd, "m", x, dilation=dil)
+        assert relerr(y, g[tag + "_y"]) < TOL, tag
+        (y * rand_like(y, 82)).sum().backward()
+        assert relerr(x.grad, g[tag + "_dx"]) < TOL
+        for k in shapes:
+            assert relerr(sd["m." + k].grad, g[f"{tag}_grad/{k}"]) < 1e-8, (tag, k)
