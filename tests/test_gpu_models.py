@@ -319,5 +319,10 @@ def test_legacy_blocks_vs_golden():
             ref = g[f"{tag}_grad/{k}"]
             if np.abs(ref).max() < 1e-10:          # bias in front of an instance norm: analytically zero
                 assert p.grad.abs().max().item() < 1e-4
+            elif k.endswith("weight_g") and np.abs(ref).max() < 1e-2:
+                # weight_g in front of an instance norm: scale-invariant, the gradient is a near-total
+                # cancellation (|g| ~ 1e-3 against ~1e1 terms); judge it on the scale of its weight_v sibling
+                scale = float(np.linalg.norm(g[f"{tag}_grad/{k[:-1]}v"]))
+                assert (p.grad.detach().cpu().double().numpy() - ref).__abs__().max() < 5e-5 * scale, (tag, k)
             else:
                 assert relerr(p.grad, ref) < 5e-5, (tag, k)
