@@ -292,6 +292,7 @@ def dominant_kernel_roofline(dev, B, T, pk, args):
     against the measured dense bf16 tensor-core burst peak."""
     import torch
     from tdvc import ops
+    from tdvc import _lib
     from tdvc._lib import ACT_LRELU
     Cc, n, K = MODEL["cond_dim"] + 8, 9, 3
     flops = 2.0 * B * T * Cc * Cc * K * n
@@ -302,16 +303,30 @@ def dominant_kernel_roofline(dev, B, T, pk, args):
         if args.precision == "bf16":
             Cg = 144
             cp = (torch.randn(B, T, Cg, device=dev) * 0.5).to(torch.bfloat16)
-            w0p = (torch.randn(K, n * Cg, Cg, device=dev) * 0.05).to(torch.bfloat16)
-            b0p = torch.zeros(n * Cg, device=dev)
             outs = [torch.empty(B, T, n * Cg, device=dev, dtype=torch.bfloat16) for _ in range(2)]
+            if ops._STACKED_COND:
+                # what _MRFCondPath.forward launches: weights stacked densely (9 x 136 rows) as the M operand
+                R0 = (n - 1) * Cc + Cg
+                w0p = (torch.randn(K, R0, Cg, device=dev) * 0.05).to(torch.bfloat16)
+                b0p = torch.zeros(R0, device=dev)
+                lib = _lib.load()
 
-            def launch(i):
-                ops._tc_conv(xp=cp, wp=w0p, bias=b0p, B=B, Tp=T, Tout=T, K=K, dilation=1, t_off=-1, Cp_total=Cg, groups=1,
-                             a_ch_off=0, a_ch_stride=0, Cinp_g=Cg, Cout_g=n * Cg, Coutp_g=n * Cg, bias_stride=0,
-                             out_act=ACT_LRELU, out_slope=0.2, out_packed=1, yp=outs[i % 2], tp_out=T, cp_out=n * Cg,
-                             out_halo=0, out_ch_off=0, out_ch_stride=0)
-            kname = "conv_tc_fwd_k<ACT=lrelu,EPI=0,OUT=packed,MASK=0> (tcgen05 bf16, 9 cond_var.0 convs in one launch)"
+                def launch(i):
+                    _lib.check(lib.tdvc_conv1d_tc_fwd_stacked(cp.data_ptr(), w0p.data_ptr(), b0p.data_ptr(), outs[i % 2].data_ptr(),
+                                                              B, Cg, 0, Cg, T, T, K, 1, -1, R0, n, Cc, ACT_LRELU, 0.2, T, n * Cg,
+                                                              0, 0, Cg, ops._st()), "stacked")
+                kname = ("conv_tc_wt_k<ACT=lrelu> (tcgen05 bf16, M=128 stacked weight rows resident in smem, N=256 time steps; "
+                         "9 cond_var.0 convs in one launch)")
+            else:
+                w0p = (torch.randn(K, n * Cg, Cg, device=dev) * 0.05).to(torch.bfloat16)
+                b0p = torch.zeros(n * Cg, device=dev)
+
+                def launch(i):
+                    ops._tc_conv(xp=cp, wp=w0p, bias=b0p, B=B, Tp=T, Tout=T, K=K, dilation=1, t_off=-1, Cp_total=Cg, groups=1,
+                                 a_ch_off=0, a_ch_stride=0, Cinp_g=Cg, Cout_g=n * Cg, Coutp_g=n * Cg, bias_stride=0,
+                                 out_act=ACT_LRELU, out_slope=0.2, out_packed=1, yp=outs[i % 2], tp_out=T, cp_out=n * Cg,
+                                 out_halo=0, out_ch_off=0, out_ch_stride=0)
+                kname = "conv_tc_ws_k<ACT=lrelu,EPI=0,OUT=packed,MASK=0> (tcgen05 bf16, 9 cond_var.0 convs in one launch)"
             launches_per_rep = 1
         else:
             x = torch.randn(B, Cc, T, device=dev)

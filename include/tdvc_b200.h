@@ -201,6 +201,20 @@ typedef struct tdvc_tc_conv {
 } tdvc_tc_conv;
 int tdvc_conv1d_tc_fwd_ex(const tdvc_tc_conv* c, void* stream);
 
+/* Stacked-block form for n convs that read the SAME input -- the FiLM cond_var[0] convs of the 9 blocks of an MRF stage
+ * (generator.py:85-92,141-194).  The GEMM is turned round: the stacked weights are the M=128 tcgen05 operand (resident in
+ * shared memory), 256 time steps are N.  wp[K][R][Cinp] bf16 holds the blocks' rows densely, block j = rows
+ * [j*rows_per_block, +rows_per_block), R >= n_blocks*rows_per_block (rows beyond are never read); bias[n_blocks *
+ * rows_per_block] or NULL.  Input: channels [a_ch_off, +Cinp) of xp[B,Tp,Cp_total], row t + k*dilation + t_off
+ * (out-of-range rows read as zero).  Output, packed bf16 channels-last only (the next conv's operand):
+ * yp[b, t+out_halo, out_ch_off + j*out_ch_stride + r] = act(conv + bias) for row r of block j; the pad columns
+ * [rows_per_block, out_ch_stride) of every block are written as zeros.  out_act: TDVC_ACT_NONE / TDVC_ACT_LRELU.
+ * Needs Cinp >= 64 and K * 128 * Cinp * 2 bytes of weights + two activation stages within 227 KB of shared memory. */
+int tdvc_conv1d_tc_fwd_stacked(const void* xp, const void* wp, const float* bias, void* yp, int B, int Cp_total,
+                               int a_ch_off, int Cinp, int Tp, int Tout, int K, int dilation, int t_off, int R,
+                               int n_blocks, int rows_per_block, int out_act, float out_slope, int tp_out,
+                               int cp_out, int out_halo, int out_ch_off, int out_ch_stride, void* stream);
+
 /* weight gradient of the same conv on tcgen05: dw[Cout,Cin,K] (OVERWRITTEN, fp32) from the packed bf16 operands
  * dyp[B,Tout,Cdp] and xp[B,Tp,Cp]; xp row read for output step t and tap k is t + k*dilation + t_off.
  * ws: workspace of tdvc_conv1d_tc_wgrad_ws(Cout, Cin, K) floats (split-K partial sums, [K][Coutp][Cinp]). */

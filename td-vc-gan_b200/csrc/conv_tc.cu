@@ -113,6 +113,21 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
   return d;
 }
 
+// One lane of a converged warp (elect.sync).  Unlike `lane == 0`, the compiler knows the guarded region runs on exactly one
+// lane of a converged warp, so warp-uniform operands of tcgen05.mma / TMA go to uniform registers without the
+// elect-broadcast-retry loop it otherwise wraps around every such instruction (~100 cycles per MMA, measured).
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync _|px, 0xffffffff;\n\t"
+      "@px mov.s32 %0, 1;\n\t"
+      "}"
+      : "+r"(pred));
+  return pred;
+}
+
 struct TcP {
   int B, Tout, Cout, K, dil, t_off;          // Cout = valid output channels per group
   int nchunk, last_nk16, BN, stages, tmem_cols;
@@ -271,7 +286,7 @@ __global__ void __launch_bounds__(TC_FWD_THREADS) conv_tc_fwd_k(const __grid_con
 
   if (warp == 0) {
     // ---------------- TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       for (int it = 0; it < iters; ++it) {
         const int s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
@@ -292,7 +307,7 @@ __global__ void __launch_bounds__(TC_FWD_THREADS) conv_tc_fwd_k(const __grid_con
       const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
       mbar_wait(&full_bar[s], ph);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const int ck = it % p.nchunk;
         const int nk = (ck == p.nchunk - 1) ? p.last_nk16 : (TC_BK / 16);
         const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
@@ -409,7 +424,7 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) conv_tc_ws_k(const __grid_c
   const int a_ch0 = p.a_ch_off + grp * p.a_ch_stride;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(w_full, (uint32_t)(p.K * nfull * w.w_tile_bytes + (w.narrow ? p.K * w.wn_tile_bytes : 0)));
       for (int tap = 0; tap < p.K; ++tap) {
         for (int ck = 0; ck < nfull; ++ck)
@@ -465,7 +480,7 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) conv_tc_ws_k(const __grid_c
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           // the single issuing thread must spend < ~70 cycles per MMA (its execution time at N=144): descriptors are
           // advanced with 32-bit adds on their low words only
           const int nk = (!w.narrow && ck == nfull - 1) ? p.last_nk16 : (TC_BK / 16);
@@ -491,7 +506,7 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) conv_tc_ws_k(const __grid_c
         const uint32_t ph = (uint32_t)(itn / w.n_stages) & 1u;
         mbar_wait(&fulln_bar[s], ph);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           uint32_t a_lo = an_lo0 + (uint32_t)s * an_stage16;
           uint32_t b_lo = bn_lo0;
           for (int tap = 0; tap < p.K; ++tap) {
@@ -525,6 +540,369 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) conv_tc_ws_k(const __grid_c
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------ stacked-block forward
+// The GEMM turned round for convolutions whose output-channel dimension is the long one -- the n FiLM cond_var.0 convs of
+// an MRF stage read the same conditioning tensor, so their weights stack into one [n*136, 144*3] matrix:
+//   D[co, t] = sum_{tap} sum_{ci} W_tap[co, ci] * X[t + tap*dil + t_off, ci]
+//   A operand = weights, M = 128 stacked output channels (TMEM lanes), loaded once per CTA;
+//   B operand = the channels-last activation tile (time steps = TMEM columns), taps = row-shifted views.
+// Measured on B200: an SS-mode M=128 tcgen05.mma takes ~120 cycles for any N <= 144 (the A-operand read from shared
+// memory), so the time-as-M orientation tops out near 55 % of peak at N=144.  Two forms of the turned-round GEMM:
+//   TS = 0  weights resident in shared memory, N = 256 per MMA (the N at which an SS MMA reaches its 128-cycle floor);
+//           A + B operand reads are 96 B/cycle of shared-memory bandwidth, which the epilogue's staging tile competes for;
+//   TS = 1  weights resident in TENSOR MEMORY (K*Cin/2 <= 256 columns next to two 128-column accumulators, written once
+//           with tcgen05.st): the MMA reads only B from shared memory (64 B/cycle), N = 128 already runs at the tensor
+//           pipe's floor (A-in-TMEM floor = 128*N/256 cycles), and the 110 KB the weights occupied become ring stages.
+// The stacked rows are dense (no per-block padding), so 9 x 136 = 1224 rows are 10 M tiles instead of 11.  Ownership is
+// fixed -- CTA c keeps M tile c % m_tiles and walks time tiles c / m_tiles + i * ctas_per_m -- so the m_tiles CTAs that
+// need the same activation tile ask for it at the same moment (one HBM read, the rest L2 hits).  A TMEM lane is an output
+// channel: bias is one register; the packed channels-last output goes through a 1 KB per-warp staging tile so that global
+// stores are 16 bytes per lane (2- and 4-byte stores of 64-byte row segments ran 3-4x slower).
+struct WtP {
+  int n_ttiles, ttiles_per_b, m_tiles, ctas_per_m;
+  int nsplit, box_rows, a_stage_bytes, an_stage_bytes;      // activation stage = nsplit TMA boxes of box_rows rows
+  int narrow, n_full, n_stages, last_nk16;
+  int rows_total, rows_per_block;                           // dense stacked rows; block j = rows [j*rpb, (j+1)*rpb)
+  int vec;                                                  // 16-byte output stores through the per-warp staging tile
+  int R, cinp;                                              // TS: wp is [K][R][cinp]
+  const __nv_bfloat16* wp;
+};
+constexpr int WT_W_TILE = TC_BM * TC_BK * 2;      // 128 rows x 128 B
+constexpr int WT_WN_TILE = TC_BM * 32;            // 128 rows x 32 B (narrow tail)
+constexpr int WT_STG_BYTES = 16 * 32 * 2;         // per-warp output staging: 16 time steps x 32 channels bf16
+constexpr int WT_TS_WCOL = 256;                   // TS: first TMEM column of the weights (after two 128-column accumulators)
+
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem descriptor]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                             uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 db;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
+template <int ACT, int TS>
+__global__ void __launch_bounds__(TC_FWD_THREADS, 1) conv_tc_wt_k(const __grid_constant__ CUtensorMap map_x,
+                                                                  const __grid_constant__ CUtensorMap map_w,
+                                                                  const __grid_constant__ CUtensorMap map_xn,
+                                                                  const __grid_constant__ CUtensorMap map_wn, TcP p, WtP w) {
+  constexpr int BN = TS ? 128 : 256;                // time steps per tile = TMEM columns per accumulator
+  constexpr int NG = BN / 64;                       // 16-column groups per epilogue warp (4 column quarters x NG x 16)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int nfull = w.n_full;
+  uint8_t* wsm = smem;                                                        // SS: [K][nfull] tiles of 128 x 128 B
+  uint8_t* wsn = wsm + (TS ? 0 : (size_t)p.K * nfull * WT_W_TILE);            // SS: [K] tiles of 128 x 32 B
+  uint8_t* ring = wsn + (TS ? 0 : (size_t)(w.narrow ? p.K : 0) * WT_WN_TILE); // [stages] activation chunks, 128-B rows
+  uint8_t* ringn = ring + (size_t)p.stages * w.a_stage_bytes;                 // [n_stages] narrow chunks, 32-B rows
+  uint8_t* stage_out = ringn + (size_t)(w.narrow ? w.n_stages : 0) * w.an_stage_bytes;   // [TC_EPI_WARPS] x 1 KB (vec epilogue)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + (w.vec ? TC_EPI_WARPS * WT_STG_BYTES : 0));
+  uint64_t* w_full = bars;
+  uint64_t* full_bar = bars + 1;
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* fulln_bar = empty_bar + p.stages;
+  uint64_t* emptyn_bar = fulln_bar + w.n_stages;
+  uint64_t* tmem_full = emptyn_bar + w.n_stages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tile = blockIdx.x % w.m_tiles;
+  const int slot0 = blockIdx.x / w.m_tiles;
+  const int r0 = m_tile * TC_BM;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    if (!TS) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    mbar_init(w_full, 1);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < w.n_stages; ++s) {
+      mbar_init(&fulln_bar[s], 1);
+      mbar_init(&emptyn_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], TC_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (TS) {
+    // weights -> tensor memory, once: lane (= stacked row) x column (= two consecutive input channels of one tap).
+    // Warps 2..5 cover the four lane quadrants; each thread copies its own row, 16 channels (32 B) per tcgen05.st.
+    if (warp >= 2 && warp < 6) {
+      const int q = warp & 3;
+      const int r = r0 + q * 32 + lane;
+      const int kcols = w.cinp >> 1;                               // TMEM columns per tap
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)WT_TS_WCOL;
+      for (int tap = 0; tap < p.K; ++tap) {
+        const uint4* src = reinterpret_cast<const uint4*>(w.wp + ((long long)tap * w.R + r) * w.cinp);
+        for (int c8 = 0; c8 < (w.cinp >> 4); ++c8) {
+          uint32_t v[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+          if (r < w.rows_total) {
+            const uint4 lo = __ldg(src + 2 * c8), hi = __ldg(src + 2 * c8 + 1);
+            v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+          }
+          tmem_st8(tbase + (uint32_t)(tap * kcols + c8 * 8), v);
+        }
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+
+  if (warp == 0) {
+    if (elect_one()) {
+      if (!TS) {
+        mbar_expect_tx(w_full, (uint32_t)(p.K * nfull * WT_W_TILE + (w.narrow ? p.K * WT_WN_TILE : 0)));
+        for (int tap = 0; tap < p.K; ++tap) {
+          for (int ck = 0; ck < nfull; ++ck)
+            tma_load_3d(wsm + (size_t)(tap * nfull + ck) * WT_W_TILE, &map_w, w_full, ck * TC_BK, r0, tap);
+          if (w.narrow) tma_load_3d(wsn + (size_t)tap * WT_WN_TILE, &map_wn, w_full, nfull * TC_BK, r0, tap);
+        }
+      }
+      int it = 0, itn = 0;
+      for (int j = slot0; j < w.n_ttiles; j += w.ctas_per_m) {
+        const int b = j / w.ttiles_per_b, t0 = (j - b * w.ttiles_per_b) * BN + p.t_off;
+        if (!TS) {
+          // warm L2 with the tile after this one: the SS ring only looks one tile ahead, too short for an HBM miss
+          const int jn = j + w.ctas_per_m;
+          if (jn < w.n_ttiles && m_tile == 0 && !(p.debug & 64)) {
+            const int bn = jn / w.ttiles_per_b, tn = (jn - bn * w.ttiles_per_b) * BN + p.t_off;
+            for (int ck = 0; ck < nfull; ++ck)
+              for (int h = 0; h < w.nsplit; ++h) tma_prefetch_3d(&map_x, p.a_ch_off + ck * TC_BK, tn + h * w.box_rows, bn);
+            if (w.narrow)
+              for (int h = 0; h < w.nsplit; ++h) tma_prefetch_3d(&map_xn, p.a_ch_off + nfull * TC_BK, tn + h * w.box_rows, bn);
+          }
+        }
+        for (int ck = 0; ck < nfull; ++ck, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_expect_tx(&full_bar[s], (uint32_t)w.a_stage_bytes);
+          for (int h = 0; h < w.nsplit; ++h)
+            tma_load_3d(ring + (size_t)s * w.a_stage_bytes + (size_t)h * w.box_rows * 128, &map_x, &full_bar[s],
+                        p.a_ch_off + ck * TC_BK, t0 + h * w.box_rows, b);
+        }
+        if (w.narrow) {
+          const int s = itn % w.n_stages;
+          const uint32_t ph = (uint32_t)(itn / w.n_stages) & 1u;
+          mbar_wait(&emptyn_bar[s], ph ^ 1u);
+          mbar_expect_tx(&fulln_bar[s], (uint32_t)w.an_stage_bytes);
+          for (int h = 0; h < w.nsplit; ++h)
+            tma_load_3d(ringn + (size_t)s * w.an_stage_bytes + (size_t)h * w.box_rows * 32, &map_xn, &fulln_bar[s],
+                        p.a_ch_off + nfull * TC_BK, t0 + h * w.box_rows, b);
+          ++itn;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // M = 128 weight rows, N = BN time steps
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    if (!TS) {
+      mbar_wait(w_full, 0);
+      tc_fence_after();
+    }
+    const uint64_t d128 = make_sw128_kmajor_desc(0), d32 = make_sw32_kmajor_desc(0);
+    const uint32_t hi128 = (uint32_t)(d128 >> 32), hi32 = (uint32_t)(d32 >> 32);
+    const uint32_t lo_flags128 = (uint32_t)d128, lo_flags32 = (uint32_t)d32;
+    const uint32_t x_lo0 = lo_flags128 | ((smem_u32(ring) & 0x3FFFF) >> 4);
+    const uint32_t w_lo0 = lo_flags128 | ((smem_u32(wsm) & 0x3FFFF) >> 4);
+    const uint32_t xn_lo0 = lo_flags32 | ((smem_u32(ringn) & 0x3FFFF) >> 4);
+    const uint32_t wn_lo0 = lo_flags32 | ((smem_u32(wsn) & 0x3FFFF) >> 4);
+    const uint32_t a_stage16 = (uint32_t)w.a_stage_bytes >> 4, an_stage16 = (uint32_t)w.an_stage_bytes >> 4;
+    const uint32_t w_tile16 = (uint32_t)WT_W_TILE >> 4, wn_tile16 = (uint32_t)WT_WN_TILE >> 4;
+    const uint32_t w_tap16 = w_tile16 * (uint32_t)nfull;
+    const uint32_t tap_step16 = (uint32_t)p.dil * 8u;                    // dil rows x 128 B
+    const uint32_t tapn_step16 = (uint32_t)p.dil * 2u;                   // dil rows x 32 B
+    const uint32_t wt_base = tmem_base + (uint32_t)WT_TS_WCOL;           // TS: weights, lane 0
+    const uint32_t wt_tap = (uint32_t)(w.cinp >> 1);                     // TMEM columns per tap
+    int it = 0, itn = 0, i = 0;
+    for (int j = slot0; j < w.n_ttiles; j += w.ctas_per_m, ++i) {
+      const int acc = i & 1;
+      const uint32_t d_addr = tmem_base + (uint32_t)(acc * BN);
+      mbar_wait(&tmem_empty[acc], ((uint32_t)(i >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      for (int ck = 0; ck < nfull; ++ck, ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const int nk = (!w.narrow && ck == nfull - 1) ? w.last_nk16 : (TC_BK / 16);
+          uint32_t x_lo = x_lo0 + (uint32_t)s * a_stage16;
+          if (TS) {
+            uint32_t wa = wt_base + (uint32_t)(ck * (TC_BK / 2));          // 32 columns per 64-channel chunk
+            for (int tap = 0; tap < p.K; ++tap) {
+              umma_bf16_ts(d_addr, wa, x_lo, hi128, idesc, (ck > 0 || tap > 0) ? 1u : 0u);
+              if (nk > 1) umma_bf16_ts(d_addr, wa + 8, x_lo + 2, hi128, idesc, 1u);
+              if (nk > 2) umma_bf16_ts(d_addr, wa + 16, x_lo + 4, hi128, idesc, 1u);
+              if (nk > 3) umma_bf16_ts(d_addr, wa + 24, x_lo + 6, hi128, idesc, 1u);
+              x_lo += tap_step16;
+              wa += wt_tap;
+            }
+          } else {
+            uint32_t w_lo = w_lo0 + (uint32_t)ck * w_tile16;
+            for (int tap = 0; tap < p.K; ++tap) {
+              umma_bf16_lohi(d_addr, w_lo, hi128, x_lo, hi128, idesc, (ck > 0 || tap > 0) ? 1u : 0u);
+              if (nk > 1) umma_bf16_lohi(d_addr, w_lo + 2, hi128, x_lo + 2, hi128, idesc, 1u);
+              if (nk > 2) umma_bf16_lohi(d_addr, w_lo + 4, hi128, x_lo + 4, hi128, idesc, 1u);
+              if (nk > 3) umma_bf16_lohi(d_addr, w_lo + 6, hi128, x_lo + 6, hi128, idesc, 1u);
+              x_lo += tap_step16;
+              w_lo += w_tap16;
+            }
+          }
+          umma_commit(&empty_bar[s]);
+          if (!w.narrow && ck == nfull - 1) umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+      }
+      if (w.narrow) {
+        const int s = itn % w.n_stages;
+        const uint32_t ph = (uint32_t)(itn / w.n_stages) & 1u;
+        mbar_wait(&fulln_bar[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          uint32_t x_lo = xn_lo0 + (uint32_t)s * an_stage16;
+          if (TS) {
+            uint32_t wa = wt_base + (uint32_t)(nfull * (TC_BK / 2));
+            for (int tap = 0; tap < p.K; ++tap) {
+              umma_bf16_ts(d_addr, wa, x_lo, hi32, idesc, 1u);
+              x_lo += tapn_step16;
+              wa += wt_tap;
+            }
+          } else {
+            uint32_t w_lo = wn_lo0;
+            for (int tap = 0; tap < p.K; ++tap) {
+              umma_bf16_lohi(d_addr, w_lo, hi32, x_lo, hi32, idesc, 1u);
+              x_lo += tapn_step16;
+              w_lo += wn_tile16;
+            }
+          }
+          umma_commit(&emptyn_bar[s]);
+          umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        ++itn;
+      }
+    }
+  } else {
+    // epilogue: 16 warps; TMEM lane quadrant = warp % 4 (32 output channels), column quarter = (warp - 2) / 4
+    constexpr int CQ = BN / 4;                                // time steps per epilogue warp
+    const int q = warp & 3;
+    const int cq = (warp - 2) >> 2;
+    const int r = r0 + q * 32 + lane;                         // stacked row of this thread
+    const bool r_ok = r < w.rows_total;
+    const int blk = r / w.rows_per_block, ch = r - blk * w.rows_per_block;
+    const float bias_v = (r_ok && p.bias) ? __ldg(p.bias + r) : 0.f;
+    const int col = p.out_ch_off + blk * p.out_ch_stride + ch;
+    const int npad = (r_ok && ch == w.rows_per_block - 1) ? p.out_ch_stride - w.rows_per_block : 0;   // zero columns after a block
+    const float sl = p.out_slope;
+    const long long row_pitch = p.cp_out;
+    // vec epilogue: the warp's 32 channels x 16 steps go through a 1 KB shared-memory tile so that the global stores are
+    // 16 bytes per lane (8 consecutive channels of one time step) instead of 2: lane -> (time row lane/4 (+8), chunk lane%4)
+    __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(stage_out + (size_t)(warp - 2) * WT_STG_BYTES);
+    const int k8 = lane & 3, row8 = lane >> 2;
+    const int rk = r0 + q * 32 + 8 * k8;                      // first stacked row of this lane's 8-channel chunk
+    const bool rk_ok = rk < w.rows_total;
+    const int blk_k = rk / w.rows_per_block, ch_k = rk - blk_k * w.rows_per_block;
+    const int col_k = p.out_ch_off + blk_k * p.out_ch_stride + ch_k;
+    const int npad_k = (rk_ok && ch_k + 8 == w.rows_per_block) ? p.out_ch_stride - w.rows_per_block : 0;
+    int i = 0;
+    for (int j = slot0; j < w.n_ttiles; j += w.ctas_per_m, ++i) {
+      const int b = j / w.ttiles_per_b, t0 = (j - b * w.ttiles_per_b) * BN;
+      const int acc = i & 1;
+      mbar_wait(&tmem_full[acc], (uint32_t)(i >> 1) & 1u);
+      tc_fence_after();
+      if (!(p.debug & 32)) {
+        const uint32_t taddr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * CQ);
+        const int t_left = p.Tout - (t0 + cq * CQ);           // valid time steps from this warp's first column
+        if (w.vec) {
+          __nv_bfloat16* op = p.yp + ((long long)b * p.tp_out + t0 + cq * CQ + p.out_halo + row8) * row_pitch + col_k;
+#pragma unroll 1
+          for (int cc = 0; cc < NG; ++cc) {
+            float v[16];
+            tmem_ld16(taddr + (uint32_t)(cc * 16), v);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              float o = v[e] + bias_v;
+              if (ACT == TDVC_ACT_LRELU) o = fmaxf(o, o * sl);
+              stg[e * 32 + lane] = __float2bfloat16(o);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int row = row8 + 8 * h;
+              const uint4 val = *reinterpret_cast<const uint4*>(stg + row * 32 + 8 * k8);
+              if (rk_ok && cc * 16 + row < t_left && !(p.debug & 1)) {
+                __nv_bfloat16* o8 = op + (long long)(cc * 16 + 8 * h) * row_pitch;
+                *reinterpret_cast<uint4*>(o8) = val;
+                if (npad_k) {
+                  if (npad_k == 8) *reinterpret_cast<uint4*>(o8 + 8) = make_uint4(0u, 0u, 0u, 0u);
+                  else for (int z = 0; z < npad_k; ++z) o8[8 + z] = __float2bfloat16(0.f);
+                }
+              }
+            }
+            __syncwarp();
+          }
+        } else {
+          __nv_bfloat16* op = p.yp + ((long long)b * p.tp_out + t0 + cq * CQ + p.out_halo) * row_pitch + col;
+#pragma unroll 1
+          for (int cc = 0; cc < NG; ++cc) {
+            float v[16];
+            tmem_ld16(taddr + (uint32_t)(cc * 16), v);
+            if (r_ok && !(p.debug & 1)) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                if (cc * 16 + e < t_left) {
+                  float o = v[e] + bias_v;
+                  if (ACT == TDVC_ACT_LRELU) o = fmaxf(o, o * sl);
+                  op[0] = __float2bfloat16(o);
+                  for (int z = 1; z <= npad; ++z) op[z] = __float2bfloat16(0.f);
+                }
+                op += row_pitch;
+              }
+            } else {
+              op += 16 * row_pitch;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512u);
 }
 
 // ------------------------------------------------------------------------------------------ wgrad
@@ -597,7 +975,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_wgrad_k(const __grid_const
 
   if (my_units > 0) {
     if (warp == 0) {
-      if (lane == 0) {
+      if (elect_one()) {
         for (int it = 0; it < my_units; ++it) {
           const int u = split + it * p.splits;
           const int b = u / p.nchunk_t, tc = (u - b * p.nchunk_t) * 64;
@@ -624,7 +1002,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_wgrad_k(const __grid_const
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t s_addr = smem_u32(smem + (size_t)s * stage_bytes);
           const uint32_t b_addr = s_addr + p.KT * a_tap_bytes;
           for (int tp = 0; tp < ntaps; ++tp) {
@@ -1029,6 +1407,101 @@ extern "C" int tdvc_conv1d_tc_fwd(const void* xp, const void* wp, const float* b
   c.Cout_g = Cout; c.Coutp_g = Coutp; c.bias_stride = 0;
   c.out_act = out_act; c.out_slope = out_slope;
   return tdvc_conv1d_tc_fwd_ex(&c, stream);
+}
+
+extern "C" int tdvc_conv1d_tc_fwd_stacked(const void* xp, const void* wp, const float* bias, void* yp, int B, int Cp_total,
+                                          int a_ch_off, int Cinp, int Tp, int Tout, int K, int dilation, int t_off, int R,
+                                          int n_blocks, int rows_per_block, int out_act, float out_slope, int tp_out,
+                                          int cp_out, int out_halo, int out_ch_off, int out_ch_stride, void* stream) {
+  TDVC_CHECK_ARG(xp && wp && yp && B >= 0 && Tp > 0 && Tout > 0 && K > 0 && dilation > 0);
+  TDVC_CHECK_ARG(Cp_total % 8 == 0 && Cinp % 16 == 0 && Cinp >= TC_BK && a_ch_off % 8 == 0 && a_ch_off + Cinp <= Cp_total);
+  TDVC_CHECK_ARG(n_blocks > 0 && rows_per_block > 0 && (long long)n_blocks * rows_per_block <= R);
+  TDVC_CHECK_ARG(out_act == TDVC_ACT_NONE || out_act == TDVC_ACT_LRELU);
+  TDVC_CHECK_ARG(out_ch_stride >= rows_per_block && out_ch_off >= 0 && out_halo >= 0 &&
+                 out_ch_off + (long long)(n_blocks - 1) * out_ch_stride + out_ch_stride <= cp_out && tp_out >= Tout + out_halo);
+  TDVC_CHECK_ARG(((uintptr_t)xp % 16 == 0) && ((uintptr_t)wp % 16 == 0));
+  if (B == 0) return TDVC_OK;
+  TcP p{};
+  p.B = B; p.Tout = Tout; p.K = K; p.dil = dilation; p.t_off = t_off; p.a_ch_off = a_ch_off;
+  p.out_act = out_act; p.out_slope = out_slope; p.bias = bias;
+  p.yp = (__nv_bfloat16*)yp; p.tp_out = tp_out; p.cp_out = cp_out; p.out_halo = out_halo;
+  p.out_ch_off = out_ch_off; p.out_ch_stride = out_ch_stride;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("TDVC_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.debug = dbg;
+  }
+  WtP w{};
+  const int nchunk = cdiv(Cinp, TC_BK);
+  w.narrow = ((Cinp % TC_BK) == 16 && Cinp > TC_BK) ? 1 : 0;
+  w.n_full = w.narrow ? nchunk - 1 : nchunk;
+  w.last_nk16 = cdiv(Cinp - (nchunk - 1) * TC_BK, 16);
+  w.rows_total = n_blocks * rows_per_block; w.rows_per_block = rows_per_block;
+  w.R = R; w.cinp = Cinp; w.wp = (const __nv_bfloat16*)wp;
+  w.m_tiles = cdiv(w.rows_total, TC_BM);
+  TDVC_CHECK_ARG(w.m_tiles <= num_sms());
+  // TDVC_WT_TS=1: weights in tensor memory (when they fit next to two 128-column accumulators).  Off by default: measured
+  // on B200 at the cond_var.0 shape the N=128 TS form reaches 967 TFLOP/s in its main loop against 1278 for the N=256 SS
+  // form -- back-to-back MMAs into one accumulator do not run at the N/2-cycle floor at N=128 (profiles/README.md).
+  static int ts_on = -1;
+  if (ts_on < 0) { const char* e = getenv("TDVC_WT_TS"); ts_on = e ? atoi(e) : 0; }
+  const bool ts = ts_on && K * Cinp / 2 <= 512 - WT_TS_WCOL;
+  const int bn = ts ? 128 : 256;
+  w.ttiles_per_b = cdiv(Tout, bn);
+  w.n_ttiles = w.ttiles_per_b * B;
+  w.ctas_per_m = std::max(1, std::min(num_sms() / w.m_tiles, w.n_ttiles));
+  const int rows_needed = bn + (K - 1) * dilation;
+  w.nsplit = cdiv(rows_needed, 256);
+  w.box_rows = 8 * cdiv(cdiv(rows_needed, 8), w.nsplit);       // TMA boxes are <= 256 rows and whole 8-row swizzle atoms
+  TDVC_CHECK_ARG(w.box_rows <= 256);
+  w.a_stage_bytes = w.nsplit * w.box_rows * 128;
+  w.an_stage_bytes = w.nsplit * w.box_rows * 32;
+  // 16-byte stores need every 8-channel chunk of a warp to sit inside one block at a 16-byte aligned column
+  w.vec = (rows_per_block % 8 == 0 && out_ch_stride % 8 == 0 && out_ch_off % 8 == 0 && cp_out % 8 == 0 &&
+           (uintptr_t)yp % 16 == 0) ? 1 : 0;
+  const long long budget = 227LL * 1024 - 1024 - 512;
+  const long long w_smem = ts ? 0 : (long long)K * (w.n_full * WT_W_TILE + (w.narrow ? WT_WN_TILE : 0));
+  const long long stg = w.vec ? TC_EPI_WARPS * WT_STG_BYTES : 0;
+  // ring depth: whole tiles' worth of chunks, up to 4 tiles ahead (TS) / whatever is left beside the weights (SS)
+  int st, nst;
+  if (ts) {
+    const long long per_tile = (long long)w.n_full * w.a_stage_bytes + (w.narrow ? w.an_stage_bytes : 0);
+    int tiles = (int)std::min<long long>(4, (budget - stg) / per_tile);
+    if (tiles < 1) { set_error("conv1d_tc_fwd_stacked: one activation tile (%lld B) does not fit in shared memory", per_tile); return TDVC_ERR_ARG; }
+    st = std::max(2, tiles * w.n_full);
+    nst = w.narrow ? std::max(2, tiles) : 0;
+  } else {
+    nst = w.narrow ? 3 : 0;
+    st = (int)std::min<long long>(6, (budget - w_smem - stg - (long long)nst * w.an_stage_bytes) / w.a_stage_bytes);
+  }
+  w.n_stages = nst;
+  const long long fixed = w_smem + stg + (long long)nst * w.an_stage_bytes;
+  if (st < 2 || fixed + (long long)st * w.a_stage_bytes > budget) {
+    set_error("conv1d_tc_fwd_stacked: weights (%lld B) + two activation stages do not fit in shared memory", w_smem);
+    return TDVC_ERR_ARG;
+  }
+  p.stages = st;
+  const size_t smem = (size_t)fixed + (size_t)st * w.a_stage_bytes + (2 * st + 2 * nst + 5) * sizeof(uint64_t) + 16 + 1024;
+  typedef void (*WtFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, TcP, WtP);
+  static const WtFn table[2][2] = {{conv_tc_wt_k<0, 0>, conv_tc_wt_k<0, 1>}, {conv_tc_wt_k<1, 0>, conv_tc_wt_k<1, 1>}};
+  WtFn kern = table[out_act == TDVC_ACT_LRELU ? 1 : 0][ts ? 1 : 0];
+  TDVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CUtensorMap map_x, map_w, map_xn, map_wn;
+  int rc = make_map_3d(&map_x, xp, (uint64_t)Cp_total, (uint64_t)Tp, (uint64_t)B, TC_BK, (uint32_t)w.box_rows);
+  if (rc) return rc;
+  rc = make_map_3d(&map_w, wp, (uint64_t)Cinp, (uint64_t)R, (uint64_t)K, TC_BK, TC_BM);
+  if (rc) return rc;
+  if (w.narrow) {
+    rc = make_map_3d(&map_xn, xp, (uint64_t)Cp_total, (uint64_t)Tp, (uint64_t)B, 16, (uint32_t)w.box_rows, CU_TENSOR_MAP_SWIZZLE_32B);
+    if (rc) return rc;
+    rc = make_map_3d(&map_wn, wp, (uint64_t)Cinp, (uint64_t)R, (uint64_t)K, 16, TC_BM, CU_TENSOR_MAP_SWIZZLE_32B);
+    if (rc) return rc;
+  } else {
+    map_xn = map_x; map_wn = map_w;
+  }
+  kern<<<w.m_tiles * w.ctas_per_m, TC_FWD_THREADS, smem, (cudaStream_t)stream>>>(map_x, map_w, map_xn, map_wn, p, w);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
 }
 
 // workspace (floats) for tdvc_conv1d_tc_wgrad

@@ -874,6 +874,14 @@ def _tc_conv(**kw):
     _lib.check(_lib.load().tdvc_conv1d_tc_fwd_ex(C.byref(c), _st()), "conv1d_tc_fwd_ex")
 
 
+_STACKED_COND = os.environ.get("TDVC_TC_STACKED", "1") != "0"     # development switch: 0 = time-as-M kernel for cond_var.0
+
+
+def set_stacked_cond(on: bool) -> None:
+    global _STACKED_COND
+    _STACKED_COND = bool(on)
+
+
 class _MRFCondPath(torch.autograd.Function):
     """(gamma|beta)_j = cond_var_j[2](leaky_relu(cond_var_j[0](c)))  for all n FiLM blocks of one MRF stage
     (model/generator.py:85-92,102), which all read the same conditioning tensor c[B, Cc, T]:
@@ -905,24 +913,34 @@ class _MRFCondPath(torch.autograd.Function):
         # operands
         cp = torch.empty(B, T, Cg, device=dev, dtype=torch.bfloat16)
         _lib.check(lib.tdvc_pack_cl_bf16(_p(c), _p(cp), B, Cc, T, Cg, 0, PAD_ZEROS, 1.0, None, 0, Cg, Cc, None, _st()), "pack c")
-        w0p = torch.empty(K, n * Cg, Cg, device=dev, dtype=torch.bfloat16)
+        # cond_var.0 weights: stacked densely (pitch Cc, kernel with the weights as the M operand) when they fit, else at
+        # the padded pitch Cg of the time-as-M kernels.  Blocks are packed in order: block j+1 overwrites the Cg - Cc
+        # zero rows block j's pack wrote past its end.
+        stacked = _STACKED_COND and Cg >= 64 and K * 128 * Cg * 2 + 2 * (256 + 8 * K) * 128 + 3 * 272 * 32 <= 220 * 1024
+        pitch0 = Cc if stacked else Cg
+        R0 = (n - 1) * pitch0 + Cg
+        w0p = torch.empty(K, R0, Cg, device=dev, dtype=torch.bfloat16)
         w2p = torch.empty(K, n * C2p, Cg, device=dev, dtype=torch.bfloat16)
-        b0p = torch.zeros(n * Cg, device=dev, dtype=torch.float32)
+        b0p = torch.zeros(R0, device=dev, dtype=torch.float32)
         b2p = torch.zeros(n * C2p, device=dev, dtype=torch.float32)
         for j in range(n):
             w0, w2 = _c(w0s[j]), _c(w2s[j])
-            _lib.check(lib.tdvc_pack_weight_bf16(_p(w0), _p(w0p), Cc, Cc, K, Cg, Cg, 0, n * Cg, j * Cg, Cg, 0, _st()), "pack w0")
+            _lib.check(lib.tdvc_pack_weight_bf16(_p(w0), _p(w0p), Cc, Cc, K, Cg, Cg, 0, R0, j * pitch0, Cg, 0, _st()), "pack w0")
             _lib.check(lib.tdvc_pack_weight_bf16(_p(w2), _p(w2p), C2, Cc, K, C2p, Cg, 0, n * C2p, j * C2p, Cg, 0, _st()), "pack w2")
             if b0s[j] is not None:
-                b0p[j * Cg:j * Cg + Cc].copy_(b0s[j])
+                b0p[j * pitch0:j * pitch0 + Cc].copy_(b0s[j])
             if b2s[j] is not None:
                 b2p[j * C2p:j * C2p + C2].copy_(b2s[j])
         # all cond_var.0 convs: packed bf16 output g1p[B, T, n*Cg] = leaky_relu(conv + bias)
         g1p = torch.empty(B, T, n * Cg, device=dev, dtype=torch.bfloat16)
-        _tc_conv(xp=cp, wp=w0p, bias=b0p, B=B, Tp=T, Tout=T, K=K, dilation=1, t_off=-1, Cp_total=Cg, groups=1,
-                 a_ch_off=0, a_ch_stride=0, Cinp_g=Cg, Cout_g=n * Cg, Coutp_g=n * Cg, bias_stride=0,
-                 out_act=ACT_LRELU, out_slope=slope, out_packed=1, yp=g1p, tp_out=T, cp_out=n * Cg, out_halo=0,
-                 out_ch_off=0, out_ch_stride=0)
+        if stacked:
+            _lib.check(lib.tdvc_conv1d_tc_fwd_stacked(_p(cp), _p(w0p), _p(b0p), _p(g1p), B, Cg, 0, Cg, T, T, K, 1, -1, R0, n, Cc,
+                                                      ACT_LRELU, slope, T, n * Cg, 0, 0, Cg, _st()), "conv1d_tc_fwd_stacked")
+        else:
+            _tc_conv(xp=cp, wp=w0p, bias=b0p, B=B, Tp=T, Tout=T, K=K, dilation=1, t_off=-1, Cp_total=Cg, groups=1,
+                     a_ch_off=0, a_ch_stride=0, Cinp_g=Cg, Cout_g=n * Cg, Coutp_g=n * Cg, bias_stride=0,
+                     out_act=ACT_LRELU, out_slope=slope, out_packed=1, yp=g1p, tp_out=T, cp_out=n * Cg, out_halo=0,
+                     out_ch_off=0, out_ch_stride=0)
         # all cond_var.2 convs, grouped: gb[n, B, 2C, T]
         gb = torch.empty(n, B, C2, T, device=dev, dtype=torch.float32)
         _tc_conv(xp=g1p, wp=w2p, bias=b2p, y=gb, B=B, Tp=T, Tout=T, K=K, dilation=1, t_off=-1, Cp_total=n * Cg, groups=n,

@@ -249,3 +249,97 @@ def test_film_posconv_fused(C, T, B, with_gb):
     assert relerr(xd.grad, x.grad) < 1e-6
     if with_gb:
         assert relerr(gbd.grad, gb.grad) < 1e-2
+
+
+STACKED_CASES = [
+    # n blocks, rows per block (Cout of a block), Cin, T, B, K, dilation, pad, act
+    (9, 136, 136, 300, 2, 3, 1, 1, "lrelu"),     # the cond_var.0 stack: 1224 rows = 10 M tiles, 64+64+16 channel chunks
+    (9, 136, 136, 1024, 1, 3, 1, 1, "lrelu"),    # exact multiple of the 256-step tile, several tiles per CTA
+    (2, 72, 72, 515, 3, 3, 2, 2, None),          # 64+16 chunks, dilation 2, ragged T, rows straddle a block boundary
+    (3, 56, 100, 260, 2, 1, 1, 0, "lrelu"),      # k=1, 64+48 chunks (partial last chunk), Cout != Cin
+    (1, 200, 64, 700, 2, 5, 3, 6, None),         # one block, 2 M tiles, k5 d3
+    (4, 50, 64, 300, 2, 3, 1, 1, "lrelu"),       # block height not a multiple of 8: scalar-store epilogue
+]
+
+
+@pytest.mark.parametrize("case", STACKED_CASES, ids=[str(i) for i in range(len(STACKED_CASES))])
+def test_conv1d_tc_stacked(case):
+    """tdvc_conv1d_tc_fwd_stacked (weights as the M operand, N = 256 time steps) through the C ABI against fp64 conv of
+    the bf16-rounded operands: only fp32 accumulation order and the bf16 rounding of the output differ (2^-9 relative,
+    asserted at 6e-3 of the tensor's max).  Pad columns must come out as exact zeros and columns outside the blocks
+    must not be touched."""
+    import ctypes as C
+    from tdvc import _lib
+    n, rpb, Cin, T, B, K, dil, pad, act = case
+    lib = _lib.load()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    x = rnd(B, Cin, T, seed=1)
+    ws = [rnd(rpb, Cin, K, seed=10 + j, scale=(Cin * K) ** -0.5) for j in range(n)]
+    bs = [rnd(rpb, seed=30 + j, scale=0.1) for j in range(n)]
+    Cinp = -(-Cin // 16) * 16
+    pitch = -(-rpb // 16) * 16 + 16              # leave pad columns after every block
+    off = 16                                     # and untouched columns in front
+    xd = x.float().cuda().contiguous()
+    xp = torch.empty(B, T, Cinp, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.tdvc_pack_cl_bf16(xd.data_ptr(), xp.data_ptr(), B, Cin, T, Cinp, 0, _lib.PAD_ZEROS, 1.0, None, 0, Cinp, -1,
+                                     None, st), "pack")
+    rp = -(-rpb // 16) * 16
+    R = (n - 1) * rpb + rp
+    wp = torch.empty(K, R, Cinp, device="cuda", dtype=torch.bfloat16)
+    bias = torch.zeros(n * rpb, device="cuda")
+    for j in range(n):
+        wj = ws[j].float().cuda().contiguous()
+        _lib.check(lib.tdvc_pack_weight_bf16(wj.data_ptr(), wp.data_ptr(), rpb, Cin, K, rp, Cinp, 0, R, j * rpb, Cinp, 0, st),
+                   "pack w")
+        bias[j * rpb:(j + 1) * rpb] = bs[j].float().cuda()
+    Tout = T + 2 * pad - dil * (K - 1)
+    cp_out = off + n * pitch
+    yp = torch.full((B, Tout + 3, cp_out), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.tdvc_conv1d_tc_fwd_stacked(xp.data_ptr(), wp.data_ptr(), bias.data_ptr(), yp.data_ptr(), B, Cinp, 0, Cinp, T,
+                                              Tout, K, dil, -pad, R, n, rpb, _lib.ACT_LRELU if act else _lib.ACT_NONE, 0.2,
+                                              Tout + 3, cp_out, 2, off, pitch, st), "stacked")
+    torch.cuda.synchronize()
+    y = yp.double().cpu()
+    assert torch.isnan(y[:, :2]).all() and torch.isnan(y[:, Tout + 2:]).all()       # halo rows untouched
+    assert torch.isnan(y[:, :, :off]).all()                                          # leading columns untouched
+    xb = x.float().bfloat16().double()
+    for j in range(n):
+        ref = F.conv1d(xb, ws[j].float().bfloat16().double(), bs[j].float().double(), padding=pad, dilation=dil)
+        if act:
+            ref = F.leaky_relu(ref, 0.2)
+        got = y[:, 2:Tout + 2, off + j * pitch: off + j * pitch + rpb].transpose(1, 2)
+        assert relerr(got, ref) < 6e-3, j
+        assert (y[:, 2:Tout + 2, off + j * pitch + rpb: off + (j + 1) * pitch] == 0).all(), j
+
+
+def test_mrf_cond_path_stacked_matches_unstacked():
+    """The two kernels behind cond_var.0 (stacked weights-as-M vs time-as-M) give the same packed activations up to the
+    fp32 summation order: the fused path's outputs agree to 2e-3 at the headline channel count."""
+    from tdvc import ops
+    n, Cc, C, T, B = 9, 136, 32, 700, 2
+    cd = dev(rnd(B, Cc, T, seed=1))
+    wd = [tuple(dev(t) for t in (rnd(Cc, Cc, 3, seed=10 + j, scale=(3 * Cc) ** -0.5), rnd(Cc, seed=30 + j, scale=0.1),
+                                  rnd(2 * C, Cc, 3, seed=50 + j, scale=(3 * Cc) ** -0.5), rnd(2 * C, seed=70 + j, scale=0.1)))
+          for j in range(n)]
+    outs = {}
+    try:
+        for on in (True, False):
+            ops.set_stacked_cond(on)
+            with torch.no_grad():
+                outs[on] = [o.clone() for o in ops.mrf_cond_path(cd, wd, slope=0.2)]
+    finally:
+        ops.set_stacked_cond(True)
+    for a, b in zip(outs[True], outs[False]):
+        assert relerr(a, b) < 2e-3
+
+
+def test_conv1d_tc_stacked_weights_in_tmem():
+    """The TS form of the stacked kernel (weights in tensor memory, tcgen05.mma with the A operand from TMEM, N = 128) is
+    selected by an environment switch read once per process: run the stacked cases in a child process with it on."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, TDVC_WT_TS="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", __file__, "-k", "test_conv1d_tc_stacked and not tmem"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
