@@ -217,12 +217,14 @@ int tdvc_conv1d_tc_fwd_stacked(const void* xp, const void* wp, const float* bias
 
 /* weight gradient of the same conv on tcgen05: dw[Cout,Cin,K] (OVERWRITTEN, fp32) from the packed bf16 operands
  * dyp[B,Tout,Cdp] and xp[B,Tp,Cp]; xp row read for output step t and tap k is t + k*dilation + t_off.
- * ws: workspace of tdvc_conv1d_tc_wgrad_ws(Cout, Cin, K) floats (split-K partial sums, [K][Coutp][Cinp]). */
+ * ws: workspace of tdvc_conv1d_tc_wgrad_ws(Cout, Cin, K) floats (split-K partial sums, [K][Coutp][Cinp] + a bias row). */
 int64_t tdvc_conv1d_tc_wgrad_ws(int Cout, int Cin, int K);
 int tdvc_conv1d_tc_wgrad(const void* dyp, const void* xp, float* dw, float* ws, int B, int Cdp, int Tout, int Cp,
                          int Tp, int Cout, int Cin, int K, int dilation, int t_off,
                          int x_ch_off /* first channel of the conv's input inside xp */,
-                         int dy_ch_off /* first channel of the conv's output inside dyp */, void* stream);
+                         int dy_ch_off /* first channel of the conv's output inside dyp */,
+                         float* db /* optional: bias gradient [Cout] = sum over (b,t) of dL/dy, from the same GEMM */,
+                         void* stream);
 
 #ifdef __cplusplus
 }

@@ -34,6 +34,33 @@ extern unsigned long long g_launches;
     TDVC_CUDA(cudaGetLastError());     \
   } while (0)
 
+// Programmatic dependent launch.  The step is ~7000 short kernels replayed from a CUDA graph; between two dependent kernel
+// nodes the GPU otherwise idles for the whole launch latency.  Every kernel of the library is launched with
+// programmatic stream serialization and starts with pdl_prologue(): griddepcontrol.wait blocks until the preceding
+// grid has completed and its writes are visible (so nothing below it can observe stale data), and launch_dependents
+// then lets the NEXT kernel in the stream be scheduled -- its blocks take free SM slots and sit in their own
+// griddepcontrol.wait -- while this one runs.  TDVC_PDL=0 launches plainly (the prologue is then a no-op).
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<Args&&>(args)...);
+}
+
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }

@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(128) contrastive_k(const float* __restrict__ A
                                                      const int64_t* __restrict__ raw, float* __restrict__ loss_sum,
                                                      float* __restrict__ dA, float* __restrict__ dP, int C, int T, int N,
                                                      float scale) {
+  pdl_prologue();
   __shared__ float logit[CL_MAXN];
   __shared__ float vnorm[CL_MAXN];
   __shared__ int vidx[CL_MAXN];
@@ -101,7 +102,7 @@ extern "C" int tdvc_contrastive_dir(const float* A, const float* P, const int64_
   TDVC_CHECK_ARG(A && P && raw && loss_sum && B >= 0 && C > 0 && T > 1 && N > 0 && N + 1 <= CL_MAXN);
   TDVC_CHECK_ARG((dA == nullptr) == (dP == nullptr));
   if (B == 0) return TDVC_OK;
-  contrastive_k<<<B * T, 128, 0, (cudaStream_t)stream>>>(A, P, raw, loss_sum, dA, dP, C, T, N, scale);
+  tdvc::launch_k(contrastive_k, B * T, 128, 0, (cudaStream_t)stream, A, P, raw, loss_sum, dA, dP, C, T, N, scale);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }

@@ -66,6 +66,7 @@ template <int CO_T, int TX>
 __global__ void __launch_bounds__(256) conv_fwd_k(FwdP p, const float* __restrict__ x, const float* __restrict__ w,
                                                    const float* __restrict__ bias, const float* __restrict__ res,
                                                    float* __restrict__ y) {
+  pdl_prologue();
   constexpr int TY = 256 / TX, TT = TX * 4, COB = TY * CO_T;
   extern __shared__ float sm[];
   float* xs = sm;
@@ -189,7 +190,7 @@ static int launch_fwd_t(FwdP p, const float* x, const float* w, const float* bia
   }
   dim3 grid(cdiv(p.Tout, TT), p.groups * cdiv(p.cout_g, COB), p.B);
   TDVC_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535);
-  conv_fwd_k<CO_T, TX><<<grid, 256, smem, st>>>(p, x, w, bias, res, y);
+  tdvc::launch_k(conv_fwd_k<CO_T, TX>, grid, 256, smem, st, p, x, w, bias, res, y);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
@@ -254,6 +255,7 @@ struct TrP {
 template <int OC_T>
 __global__ void __launch_bounds__(256) conv_tr_k(TrP p, const float* __restrict__ in, const float* __restrict__ w,
                                                   const float* __restrict__ bias, float* __restrict__ out) {
+  pdl_prologue();
   constexpr int TU = 128, TY = 2, OB = TY * OC_T;
   extern __shared__ float sm[];
   float* ins = sm;                                   // [ic_chunk][qlen]
@@ -346,7 +348,7 @@ static int launch_tr_t(TrP p, const float* in, const float* w, const float* bias
   TDVC_CHECK_ARG(smem <= 48 * 1024);
   dim3 grid(cdiv(p.Tout, TU), p.groups * cdiv(p.out_g, OB), p.B);
   TDVC_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535);
-  conv_tr_k<OC_T><<<grid, 256, smem, st>>>(p, in, w, bias, out);
+  tdvc::launch_k(conv_tr_k<OC_T>, grid, 256, smem, st, p, in, w, bias, out);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
@@ -368,6 +370,7 @@ static int launch_tr(TrP p, const float* in, const float* w, const float* bias, 
 // reflect fold + input-activation mask:  dx[t] = mask(x[t]) * (stage[p+t] + mirrored halo terms)
 __global__ void pad_act_bwd_k(const float* __restrict__ stage, const float* __restrict__ x, float* __restrict__ dx,
                               long long rows, int T, int p, int reflect, float slope) {
+  pdl_prologue();
   long long n = rows * T;
   int Ts = T + 2 * p;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
@@ -398,6 +401,7 @@ struct WgP {
 template <int RC>
 __global__ void __launch_bounds__(256) conv_wgrad_k(WgP p, const float* __restrict__ A, const float* __restrict__ Bm,
                                                      float* __restrict__ out) {
+  pdl_prologue();
   constexpr int TTW = 128, CAB = 16 * RC, JB = 64;
   extern __shared__ float sm[];
   float* a_s = sm;                  // [CAB][TTW]
@@ -493,7 +497,7 @@ static int launch_wgrad_t(WgP p, const float* A, const float* Bm, float* out, cu
   p.zsplit = (int)want;
   TDVC_CHECK_ARG(gy <= 65535);
   dim3 grid(gx, gy, p.zsplit);
-  conv_wgrad_k<RC><<<grid, 256, smem, st>>>(p, A, Bm, out);
+  tdvc::launch_k(conv_wgrad_k<RC>, grid, 256, smem, st, p, A, Bm, out);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
@@ -507,6 +511,7 @@ static int launch_wgrad(WgP p, const float* A, const float* Bm, float* out, cuda
 
 // per-channel sum over (b, t): bias gradient
 __global__ void channel_sum_k(const float* __restrict__ dy, float* __restrict__ db, int B, int C, int T, int zsplit) {
+  pdl_prologue();
   __shared__ float sm[33];
   const int c = blockIdx.x;
   float s = 0.f;
@@ -522,7 +527,7 @@ static int launch_channel_sum(const float* dy, float* db, int B, int C, int T, c
   TDVC_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * C, st));
   if (B == 0) return TDVC_OK;
   int zs = min(B, max(1, (2 * num_sms()) / C));
-  channel_sum_k<<<dim3(C, zs), 256, 0, st>>>(dy, db, B, C, T, zs);
+  tdvc::launch_k(channel_sum_k, dim3(C, zs), 256, 0, st, dy, db, B, C, T, zs);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
@@ -585,7 +590,7 @@ extern "C" int tdvc_conv1d_bwd_data(const tdvc_conv_geom* g, const float* dy, co
     long long n = rows * g->Tin;
     int blocks = (int)std::min<long long>((n + 255) / 256, 8LL * num_sms());
     if (blocks > 0) {
-      pad_act_bwd_k<<<blocks, 256, 0, st>>>(ws, x, dx, rows, g->Tin, ph, g->pad_mode == TDVC_PAD_REFLECT, g->in_slope);
+      tdvc::launch_k(pad_act_bwd_k, blocks, 256, 0, st, ws, x, dx, rows, g->Tin, ph, g->pad_mode == TDVC_PAD_REFLECT, g->in_slope);
       TDVC_LAUNCH_CHECK();
     }
   }
@@ -604,7 +609,7 @@ extern "C" int tdvc_pad_act_bwd(const float* stage, const float* x, float* dx, i
   long long n = (long long)rows * T;
   if (n == 0) return TDVC_OK;
   int blocks = (int)std::min<long long>((n + 255) / 256, 8LL * num_sms());
-  pad_act_bwd_k<<<blocks, 256, 0, (cudaStream_t)stream>>>(stage, x, dx, rows, T, halo, reflect, in_slope);
+  tdvc::launch_k(pad_act_bwd_k, blocks, 256, 0, (cudaStream_t)stream, stage, x, dx, rows, T, halo, reflect, in_slope);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }

@@ -249,6 +249,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcP& p, const float* bias
 template <int ACT, int EPI, int OUT, int MASK>
 __global__ void __launch_bounds__(TC_FWD_THREADS) conv_tc_fwd_k(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_b, TcP p) {
+  pdl_prologue();
   __shared__ __align__(16) float bias_s[256];      // bias of this N tile (zeros when absent)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B atoms need 1024-B alignment
@@ -374,6 +375,7 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) conv_tc_ws_k(const __grid_c
                                                                   const __grid_constant__ CUtensorMap map_b,
                                                                   const __grid_constant__ CUtensorMap map_an,
                                                                   const __grid_constant__ CUtensorMap map_bn, TcP p, WsP w) {
+  pdl_prologue();
   __shared__ __align__(16) float bias_s[256];
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -603,6 +605,7 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) conv_tc_wt_k(const __grid_c
                                                                   const __grid_constant__ CUtensorMap map_w,
                                                                   const __grid_constant__ CUtensorMap map_xn,
                                                                   const __grid_constant__ CUtensorMap map_wn, TcP p, WtP w) {
+  pdl_prologue();
   constexpr int BN = TS ? 128 : 256;                // time steps per tile = TMEM columns per accumulator
   constexpr int NG = BN / 64;                       // 16-column groups per epilogue warp (4 column quarters x NG x 16)
   extern __shared__ uint8_t smem_raw[];
@@ -918,6 +921,7 @@ struct WgTcP {
   int Mp, Np;     // padded ci / co extents of the workspace
   int x_ch_off, dy_ch_off;   // first channel of this conv's slice inside the packed operands
   float* ws;
+  int bias;                  // also accumulate the bias gradient (column sums of dL/dy) into ws[K*Np*Mp + co]
 };
 
 constexpr int WG_BOX_BYTES = 64 * 64 * 2;   // 64 time rows x 64 channels bf16
@@ -936,12 +940,17 @@ __device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr, 
 
 __global__ void __launch_bounds__(TC_THREADS) conv_tc_wgrad_k(const __grid_constant__ CUtensorMap map_x,
                                                               const __grid_constant__ CUtensorMap map_dy, WgTcP p) {
+  pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int a_tap_bytes = 2 * WG_BOX_BYTES;           // 128 ci x 64 t
   const int b_bytes = p.nb * WG_BOX_BYTES;            // NT co x 64 t
   const int stage_bytes = p.KT * a_tap_bytes + b_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  // bias gradient = sum over (b, t) of dL/dy: one more "tap" whose A operand is a constant tile of ones, so the column
+  // sums come out of the same GEMM (every TMEM lane of accumulator KT holds them); only the CTAs of the first
+  // (ci tile, tap group) do it.  Replaces the atomics the dL/dy pack pass used to spend on it.
+  uint8_t* ones = smem + (size_t)p.stages * stage_bytes;                    // 128 x 64 bf16 (1024-B aligned), when p.bias
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ones + (p.bias ? a_tap_bytes : 0));
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full_bar = empty_bar + p.stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
@@ -956,6 +965,12 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_wgrad_k(const __grid_const
   const int ntaps = min(p.KT, p.K - tap0);
   const int split = blockIdx.x;
   const int my_units = (p.units - split + p.splits - 1) / p.splits;   // units split, split+splits, ...
+  const bool do_bias = p.bias && mt == 0 && tg == 0;
+  if (do_bias) {
+    uint32_t* o32 = reinterpret_cast<uint32_t*>(ones);
+    for (int i = threadIdx.x; i < a_tap_bytes / 4; i += TC_THREADS) o32[i] = 0x3F803F80u;      // bf16 1.0 pairs
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the MMA's reads
+  }
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
@@ -1013,6 +1028,14 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_wgrad_k(const __grid_const
               umma_bf16(tmem_base + (uint32_t)(tp * p.NT), da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
             }
           }
+          if (do_bias) {
+            const uint32_t o_addr = smem_u32(ones);
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t da = make_sw128_mnmajor_desc(o_addr + k * 2048, WG_BOX_BYTES);
+              const uint64_t db = make_sw128_mnmajor_desc(b_addr + k * 2048, WG_BOX_BYTES);
+              umma_bf16(tmem_base + (uint32_t)(p.KT * p.NT), da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            }
+          }
           umma_commit(&empty_bar[s]);
           if (it == my_units - 1) umma_commit(tmem_full_bar);
         }
@@ -1038,6 +1061,18 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_wgrad_k(const __grid_const
           }
         }
       }
+      if (do_bias && q == 0) {
+        // every lane of accumulator KT holds the column sums; lane j of the warp adds column c0 + j
+        float* brow = p.ws + (long long)p.K * p.Np * p.Mp + n0;
+        for (int c0 = 0; c0 < nvalid; c0 += 16) {
+          float v[16];
+          tmem_ld16(tmem_base + (uint32_t)(p.KT * p.NT + c0), v);
+          float mine = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) mine = (lane == j) ? v[j] : mine;
+          if (lane < min(16, nvalid - c0)) atomicAdd(brow + c0 + lane, mine);
+        }
+      }
     }
   }
   tc_fence_before();
@@ -1047,7 +1082,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_wgrad_k(const __grid_const
 
 // dw[co][ci][k] = ws[k][co][ci]
 __global__ void wgrad_finalize_k(const float* __restrict__ ws, float* __restrict__ dw, int Cout, int Cin, int K, int Np,
-                                 int Mp) {
+                                 int Mp, float* __restrict__ db) {
+  pdl_prologue();
   long long n = (long long)Cout * Cin * K;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     int k = (int)(i % K);
@@ -1055,6 +1091,8 @@ __global__ void wgrad_finalize_k(const float* __restrict__ ws, float* __restrict
     int ci = (int)(r % Cin), co = (int)(r / Cin);
     dw[i] = ws[((long long)k * Np + co) * Mp + ci];
   }
+  if (db && blockIdx.x == 0)
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) db[i] = ws[(long long)K * Np * Mp + i];
 }
 
 // ------------------------------------------------------------------------------------------ pack kernels
@@ -1068,6 +1106,7 @@ __global__ void __launch_bounds__(256) pack_cl_bf16_k(const float* __restrict__ 
                                                      int T, int Cp, int Tp, int halo, int pad_mode, float slope,
                                                      float* __restrict__ chan_sum, int c_off, int Cw, int ones_ch,
                                                      const float* __restrict__ film_gb) {
+  pdl_prologue();
   constexpr int TL = 4096 / CH;             // time steps per tile: 64 / 128 / 256
   constexpr int RPW = CH / 8;               // channel rows per warp
   constexpr int LPR = TL / 32;              // loads per row per lane
@@ -1138,6 +1177,7 @@ __global__ void __launch_bounds__(256) pack_cl_bf16_k(const float* __restrict__ 
 
 __global__ void pack_weight_bf16_k(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int Cout, int Cin, int K,
                                    int Rp, int Qp, int transpose_flip, int R_total, int r_off, int Q_total, int q_off) {
+  pdl_prologue();
   // writes the [K][Rp][Qp] block at (r_off, q_off) of wp[K][R_total][Q_total]
   // plain: R = co, Q = ci; transpose_flip: R = ci, Q = co, taps reversed
   long long n = (long long)K * Rp * Qp;
@@ -1204,16 +1244,16 @@ extern "C" int tdvc_pack_cl_bf16(const float* x, void* xp, int B, int C, int T, 
   // thin tensors: fewer channel rows, longer time tiles (same bytes in flight per CTA)
   if (C <= 16 && Cw <= 64) {
     dim3 grid(cdiv(Tp, 256), 1, B);
-    pack_cl_bf16_k<16><<<grid, 256, 0, st>>>(x, o, C, T, Cp, Tp, halo, pad_mode, in_slope, chan_sum, c_off, Cw, ones_ch,
+    tdvc::launch_k(pack_cl_bf16_k<16>, grid, 256, 0, st, x, o, C, T, Cp, Tp, halo, pad_mode, in_slope, chan_sum, c_off, Cw, ones_ch,
                                              film_gb);
   } else if (C <= 32 && Cw <= 64) {
     dim3 grid(cdiv(Tp, 128), 1, B);
-    pack_cl_bf16_k<32><<<grid, 256, 0, st>>>(x, o, C, T, Cp, Tp, halo, pad_mode, in_slope, chan_sum, c_off, Cw, ones_ch,
+    tdvc::launch_k(pack_cl_bf16_k<32>, grid, 256, 0, st, x, o, C, T, Cp, Tp, halo, pad_mode, in_slope, chan_sum, c_off, Cw, ones_ch,
                                              film_gb);
   } else {
     dim3 grid(cdiv(Tp, 64), cdiv(Cw, 64), B);
     TDVC_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535);
-    pack_cl_bf16_k<64><<<grid, 256, 0, st>>>(x, o, C, T, Cp, Tp, halo, pad_mode, in_slope, chan_sum, c_off, Cw, ones_ch,
+    tdvc::launch_k(pack_cl_bf16_k<64>, grid, 256, 0, st, x, o, C, T, Cp, Tp, halo, pad_mode, in_slope, chan_sum, c_off, Cw, ones_ch,
                                              film_gb);
   }
   TDVC_LAUNCH_CHECK();
@@ -1229,7 +1269,7 @@ extern "C" int tdvc_pack_weight_bf16(const float* w, void* wp, int Cout, int Cin
   TDVC_CHECK_ARG(r_off >= 0 && q_off >= 0 && r_off + Rp <= R_total && q_off + Qp <= Q_total);
   long long n = (long long)K * Rp * Qp;
   int blocks = (int)std::min<long long>((n + 255) / 256, 8LL * num_sms());
-  pack_weight_bf16_k<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)wp, Cout, Cin, K, Rp, Qp, transpose_flip, R_total,
+  tdvc::launch_k(pack_weight_bf16_k, blocks, 256, 0, (cudaStream_t)stream, w, (__nv_bfloat16*)wp, Cout, Cin, K, Rp, Qp, transpose_flip, R_total,
                                                                        r_off, Q_total, q_off);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
@@ -1363,7 +1403,7 @@ extern "C" int tdvc_conv1d_tc_fwd_ex(const tdvc_tc_conv* c, void* stream) {
       }
       dim3 grid(ctas, n_tiles_total, 1);
       TDVC_CHECK_ARG(grid.y <= 65535);
-      kern<<<grid, TC_FWD_THREADS, smem_ws, (cudaStream_t)stream>>>(map_a, map_b, map_an, map_bn, p, w);
+      tdvc::launch_k(kern, grid, TC_FWD_THREADS, smem_ws, (cudaStream_t)stream, map_a, map_b, map_an, map_bn, p, w);
       TDVC_LAUNCH_CHECK();
       return TDVC_OK;
     }
@@ -1392,7 +1432,7 @@ extern "C" int tdvc_conv1d_tc_fwd_ex(const tdvc_tc_conv* c, void* stream) {
   if (rc) return rc;
   dim3 grid(cdiv(c->Tout, TC_BM), c->groups * p.tiles_per_group, c->B);
   TDVC_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535);
-  kern<<<grid, TC_FWD_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
+  tdvc::launch_k(kern, grid, TC_FWD_THREADS, smem, (cudaStream_t)stream, map_a, map_b, p);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
@@ -1499,7 +1539,7 @@ extern "C" int tdvc_conv1d_tc_fwd_stacked(const void* xp, const void* wp, const 
   } else {
     map_xn = map_x; map_wn = map_w;
   }
-  kern<<<w.m_tiles * w.ctas_per_m, TC_FWD_THREADS, smem, (cudaStream_t)stream>>>(map_x, map_w, map_xn, map_wn, p, w);
+  tdvc::launch_k(kern, w.m_tiles * w.ctas_per_m, TC_FWD_THREADS, smem, (cudaStream_t)stream, map_x, map_w, map_xn, map_wn, p, w);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
@@ -1507,14 +1547,14 @@ extern "C" int tdvc_conv1d_tc_fwd_stacked(const void* xp, const void* wp, const 
 // workspace (floats) for tdvc_conv1d_tc_wgrad
 extern "C" int64_t tdvc_conv1d_tc_wgrad_ws(int Cout, int Cin, int K) {
   const long long Mp = (long long)((Cin + 127) / 128) * 128, Np = (long long)((Cout + 15) / 16) * 16;
-  return (int64_t)K * Np * Mp;
+  return (int64_t)K * Np * Mp + Np;      // + the bias-gradient row
 }
 
 // dw[Cout,Cin,K] (OVERWRITTEN) from the packed operands: dyp[B,Tout,Cdp] and xp[B,Tp,Cp] (both bf16 channels-last;
 // xp row = t + tap*dilation + t_off).
 extern "C" int tdvc_conv1d_tc_wgrad(const void* dyp, const void* xp, float* dw, float* ws, int B, int Cdp, int Tout, int Cp,
                                     int Tp, int Cout, int Cin, int K, int dilation, int t_off, int x_ch_off,
-                                    int dy_ch_off, void* stream) {
+                                    int dy_ch_off, float* db, void* stream) {
   TDVC_CHECK_ARG(dyp && xp && dw && ws && B >= 0 && Cdp % 8 == 0 && Cp % 8 == 0 && dy_ch_off >= 0 && x_ch_off >= 0 &&
                  Cdp >= dy_ch_off + Cout && Cp >= x_ch_off + Cin && Tout > 0 && Tp > 0 && K > 0 && dilation > 0);
   cudaStream_t st = (cudaStream_t)stream;
@@ -1523,13 +1563,19 @@ extern "C" int tdvc_conv1d_tc_wgrad(const void* dyp, const void* xp, float* dw, 
   p.x_ch_off = x_ch_off; p.dy_ch_off = dy_ch_off;
   p.Mp = ((Cin + 127) / 128) * 128;
   p.Np = ((Cout + 15) / 16) * 16;
-  TDVC_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * (size_t)K * p.Np * p.Mp, st));
-  if (B == 0) { TDVC_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * Cin * K, st)); return TDVC_OK; }
+  p.bias = db ? 1 : 0;
+  TDVC_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * ((size_t)K * p.Np * p.Mp + p.Np), st));
+  if (B == 0) {
+    TDVC_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * Cin * K, st));
+    if (db) TDVC_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)Cout, st));
+    return TDVC_OK;
+  }
+  const int xt = p.bias;     // accumulators beyond the taps
   const int N16 = p.Np;
   // widest co tile such that as many taps as possible share the 512 TMEM columns (fewer re-reads of the operands)
   int best_nt = 16, best_cost = 1 << 30;
   for (int cand = std::min(N16, 256); cand >= 16; cand -= 16) {
-    int kt = std::min(K, 512 / cand);
+    int kt = std::min(K, 512 / cand - xt);
     if (kt < 1) continue;
     // per-stage shared memory must leave room for at least 2 stages
     long long stage = (long long)kt * 2 * WG_BOX_BYTES + (long long)cdiv(cand, 64) * WG_BOX_BYTES;
@@ -1538,13 +1584,13 @@ extern "C" int tdvc_conv1d_tc_wgrad(const void* dyp, const void* xp, float* dw, 
     if (cost < best_cost) { best_cost = cost; best_nt = cand; }
   }
   p.NT = best_nt;
-  p.KT = std::min(K, 512 / p.NT);
+  p.KT = std::min(K, 512 / p.NT - xt);
   while (p.KT > 1 && 2LL * ((long long)p.KT * 2 * WG_BOX_BYTES + (long long)cdiv(p.NT, 64) * WG_BOX_BYTES) > 200 * 1024) --p.KT;
   p.ntap_groups = cdiv(K, p.KT);
   p.n_ntiles = cdiv(N16, p.NT);
   p.nb = cdiv(p.NT, 64);
   int cols = 32;
-  while (cols < p.KT * p.NT) cols <<= 1;
+  while (cols < (p.KT + xt) * p.NT) cols <<= 1;
   TDVC_CHECK_ARG(cols <= 512);
   p.tmem_cols = cols;
   const int stage_bytes = p.KT * 2 * WG_BOX_BYTES + p.nb * WG_BOX_BYTES;
@@ -1559,7 +1605,7 @@ extern "C" int tdvc_conv1d_tc_wgrad(const void* dyp, const void* xp, float* dw, 
   int splits = std::max(1, num_sms() / gy);
   splits = std::min(splits, p.units);
   p.splits = splits;
-  size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
+  size_t smem = (size_t)stages * stage_bytes + (p.bias ? 2 * WG_BOX_BYTES : 0) + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
   static bool configured = false;
   if (!configured) {
     TDVC_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1571,11 +1617,11 @@ extern "C" int tdvc_conv1d_tc_wgrad(const void* dyp, const void* xp, float* dw, 
   rc = make_map_3d(&map_dy, dyp, (uint64_t)Cdp, (uint64_t)Tout, (uint64_t)B, 64, 64);
   if (rc) return rc;
   TDVC_CHECK_ARG(gy <= 65535);
-  conv_tc_wgrad_k<<<dim3(splits, gy), TC_THREADS, smem, st>>>(map_x, map_dy, p);
+  tdvc::launch_k(conv_tc_wgrad_k, dim3(splits, gy), TC_THREADS, smem, st, map_x, map_dy, p);
   TDVC_LAUNCH_CHECK();
   long long n = (long long)Cout * Cin * K;
   int blocks = (int)std::min<long long>((n + 255) / 256, 4LL * num_sms());
-  wgrad_finalize_k<<<blocks, 256, 0, st>>>(ws, dw, Cout, Cin, K, p.Np, p.Mp);
+  tdvc::launch_k(wgrad_finalize_k, blocks, 256, 0, st, ws, dw, Cout, Cin, K, p.Np, p.Mp, db);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }

@@ -1,3 +1,4 @@
+#include <cstdlib>
 // Error reporting, device queries.
 #include <stdarg.h>
 #include <string.h>
@@ -24,6 +25,15 @@ int num_sms() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("TDVC_PDL");
+    on = e ? (atoi(e) != 0) : 1;
+  }
+  return on != 0;
 }
 }  // namespace tdvc
 

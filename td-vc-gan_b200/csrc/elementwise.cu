@@ -13,6 +13,7 @@ static inline int ew_blocks(long long n_items) {
 }
 
 __global__ void lrelu_fwd_k(const float* __restrict__ x, float* __restrict__ y, long long n, float slope) {
+  pdl_prologue();
   long long n4 = n >> 2;
   long long stride = (long long)gridDim.x * blockDim.x;
   long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -28,6 +29,7 @@ __global__ void lrelu_fwd_k(const float* __restrict__ x, float* __restrict__ y, 
 
 __global__ void act_bwd_k(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dz,
                           long long n, int act, float slope) {
+  pdl_prologue();
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     float g = dy[i], o = y[i];
@@ -39,6 +41,7 @@ __global__ void act_bwd_k(const float* __restrict__ dy, const float* __restrict_
 
 __global__ void film_fwd_k(const float* __restrict__ h, const float* __restrict__ gb, float* __restrict__ y, int B,
                            int C, int T) {
+  pdl_prologue();
   long long n = (long long)B * C * T;
   long long stride = (long long)gridDim.x * blockDim.x;
   long long CT = (long long)C * T;
@@ -51,6 +54,7 @@ __global__ void film_fwd_k(const float* __restrict__ h, const float* __restrict_
 
 __global__ void film_bwd_k(const float* __restrict__ dy, const float* __restrict__ h, const float* __restrict__ gb,
                            float* __restrict__ dh, float* __restrict__ dgb, int B, int C, int T) {
+  pdl_prologue();
   long long n = (long long)B * C * T;
   long long stride = (long long)gridDim.x * blockDim.x;
   long long CT = (long long)C * T;
@@ -66,6 +70,7 @@ __global__ void film_bwd_k(const float* __restrict__ dy, const float* __restrict
 
 __global__ void add3_scale_k(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
                              float* __restrict__ y, long long n, float alpha) {
+  pdl_prologue();
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     float v = a[i];
@@ -78,6 +83,7 @@ __global__ void add3_scale_k(const float* __restrict__ a, const float* __restric
 // F.normalize(dim=1): one thread per (b,t) column; consecutive threads -> consecutive t (coalesced per channel)
 __global__ void l2norm_fwd_k(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ inv, int B, int C,
                              int T) {
+  pdl_prologue();
   long long n = (long long)B * T;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     long long b = i / T;
@@ -95,6 +101,7 @@ __global__ void l2norm_fwd_k(const float* __restrict__ x, float* __restrict__ y,
 // y = x*r  =>  dx = r*(dy - y * sum_c(dy*y))   (the clamp branch has zero measure; same as ATen)
 __global__ void l2norm_bwd_k(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ inv,
                              float* __restrict__ dx, int B, int C, int T) {
+  pdl_prologue();
   long long n = (long long)B * T;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     long long b = i / T;
@@ -112,6 +119,7 @@ __global__ void l2norm_bwd_k(const float* __restrict__ dy, const float* __restri
 
 __global__ void cond_concat_fwd_k(const float* __restrict__ c, const float* __restrict__ e, float* __restrict__ out,
                                   int B, int Cc, int Ce, int T, int c_first) {
+  pdl_prologue();
   int Ct = Cc + Ce;
   long long n = (long long)B * Ct * T;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -127,6 +135,7 @@ __global__ void cond_concat_fwd_k(const float* __restrict__ c, const float* __re
 // one block per (b, channel) row of dout: time-sum for the constant channels, copy for the rest
 __global__ void cond_concat_bwd_k(const float* __restrict__ dout, float* __restrict__ dc, float* __restrict__ de, int B,
                                   int Cc, int Ce, int T, int c_first) {
+  pdl_prologue();
   __shared__ float sm[33];
   int Ct = Cc + Ce;
   int row = blockIdx.x;
@@ -152,7 +161,7 @@ extern "C" int tdvc_leaky_relu_fwd(const float* x, float* y, int64_t n, float sl
   TDVC_CHECK_ARG(n >= 0);
   if (n == 0) return TDVC_OK;
   TDVC_CHECK_ARG(x && y && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0));
-  lrelu_fwd_k<<<ew_blocks(n / 4 + 1), 256, 0, (cudaStream_t)stream>>>(x, y, n, slope);
+  tdvc::launch_k(lrelu_fwd_k, ew_blocks(n / 4 + 1), 256, 0, (cudaStream_t)stream, x, y, n, slope);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
@@ -162,7 +171,7 @@ extern "C" int tdvc_act_bwd_from_output(const float* dy, const float* y, float* 
   TDVC_CHECK_ARG(n >= 0);
   if (n == 0) return TDVC_OK;
   TDVC_CHECK_ARG(dy && y && dz);
-  act_bwd_k<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(dy, y, dz, n, act, slope);
+  tdvc::launch_k(act_bwd_k, ew_blocks(n), 256, 0, (cudaStream_t)stream, dy, y, dz, n, act, slope);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
@@ -170,7 +179,7 @@ extern "C" int tdvc_act_bwd_from_output(const float* dy, const float* y, float* 
 extern "C" int tdvc_film_fwd(const float* h, const float* gb, float* y, int B, int C, int T, void* stream) {
   TDVC_CHECK_ARG(B >= 0 && C > 0 && T > 0 && h && gb && y);
   if (B == 0) return TDVC_OK;
-  film_fwd_k<<<ew_blocks((long long)B * C * T), 256, 0, (cudaStream_t)stream>>>(h, gb, y, B, C, T);
+  tdvc::launch_k(film_fwd_k, ew_blocks((long long)B * C * T), 256, 0, (cudaStream_t)stream, h, gb, y, B, C, T);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
@@ -179,7 +188,7 @@ extern "C" int tdvc_film_bwd(const float* dy, const float* h, const float* gb, f
                              int T, void* stream) {
   TDVC_CHECK_ARG(B >= 0 && C > 0 && T > 0 && dy && h && gb && dh && dgb);
   if (B == 0) return TDVC_OK;
-  film_bwd_k<<<ew_blocks((long long)B * C * T), 256, 0, (cudaStream_t)stream>>>(dy, h, gb, dh, dgb, B, C, T);
+  tdvc::launch_k(film_bwd_k, ew_blocks((long long)B * C * T), 256, 0, (cudaStream_t)stream, dy, h, gb, dh, dgb, B, C, T);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
@@ -189,7 +198,7 @@ extern "C" int tdvc_add3_scale(const float* a, const float* b, const float* c, f
   TDVC_CHECK_ARG(n >= 0);
   if (n == 0) return TDVC_OK;
   TDVC_CHECK_ARG(a && y);
-  add3_scale_k<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(a, b, c, y, n, alpha);
+  tdvc::launch_k(add3_scale_k, ew_blocks(n), 256, 0, (cudaStream_t)stream, a, b, c, y, n, alpha);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
@@ -197,7 +206,7 @@ extern "C" int tdvc_add3_scale(const float* a, const float* b, const float* c, f
 extern "C" int tdvc_l2norm_fwd(const float* x, float* y, float* inv, int B, int C, int T, void* stream) {
   TDVC_CHECK_ARG(B >= 0 && C > 0 && T > 0 && x && y && inv);
   if (B == 0) return TDVC_OK;
-  l2norm_fwd_k<<<ew_blocks((long long)B * T), 256, 0, (cudaStream_t)stream>>>(x, y, inv, B, C, T);
+  tdvc::launch_k(l2norm_fwd_k, ew_blocks((long long)B * T), 256, 0, (cudaStream_t)stream, x, y, inv, B, C, T);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
@@ -206,7 +215,7 @@ extern "C" int tdvc_l2norm_bwd(const float* dy, const float* y, const float* inv
                                void* stream) {
   TDVC_CHECK_ARG(B >= 0 && C > 0 && T > 0 && dy && y && inv && dx);
   if (B == 0) return TDVC_OK;
-  l2norm_bwd_k<<<ew_blocks((long long)B * T), 256, 0, (cudaStream_t)stream>>>(dy, y, inv, dx, B, C, T);
+  tdvc::launch_k(l2norm_bwd_k, ew_blocks((long long)B * T), 256, 0, (cudaStream_t)stream, dy, y, inv, dx, B, C, T);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
@@ -216,7 +225,7 @@ extern "C" int tdvc_cond_concat_fwd(const float* c, const float* e, float* out, 
   TDVC_CHECK_ARG(B >= 0 && Cc >= 0 && Ce >= 0 && Cc + Ce > 0 && T > 0 && out);
   TDVC_CHECK_ARG((Cc == 0 || c) && (Ce == 0 || e));
   if (B == 0) return TDVC_OK;
-  cond_concat_fwd_k<<<ew_blocks((long long)B * (Cc + Ce) * T), 256, 0, (cudaStream_t)stream>>>(c, e, out, B, Cc, Ce, T, c_first);
+  tdvc::launch_k(cond_concat_fwd_k, ew_blocks((long long)B * (Cc + Ce) * T), 256, 0, (cudaStream_t)stream, c, e, out, B, Cc, Ce, T, c_first);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
@@ -226,7 +235,7 @@ extern "C" int tdvc_cond_concat_bwd(const float* dout, float* dc, float* de, int
   TDVC_CHECK_ARG(B >= 0 && Cc >= 0 && Ce >= 0 && Cc + Ce > 0 && T > 0 && dout);
   TDVC_CHECK_ARG(Cc == 0 || dc);
   if (B == 0) return TDVC_OK;
-  cond_concat_bwd_k<<<B * (Cc + Ce), 256, 0, (cudaStream_t)stream>>>(dout, dc, de, B, Cc, Ce, T, c_first);
+  tdvc::launch_k(cond_concat_bwd_k, B * (Cc + Ce), 256, 0, (cudaStream_t)stream, dout, dc, de, B, Cc, Ce, T, c_first);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }

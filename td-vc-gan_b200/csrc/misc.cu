@@ -15,6 +15,7 @@ static inline int ew_blocks(long long n_items) {
 }
 
 __global__ void avgpool_fwd_k(const float* __restrict__ x, float* __restrict__ y, long long rows, int Tin, int Tout) {
+  pdl_prologue();
   long long n = rows * Tout;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     long long r = i / Tout;
@@ -28,6 +29,7 @@ __global__ void avgpool_fwd_k(const float* __restrict__ x, float* __restrict__ y
 }
 
 __global__ void avgpool_bwd_k(const float* __restrict__ dy, float* __restrict__ dx, long long rows, int Tin, int Tout) {
+  pdl_prologue();
   long long n = rows * Tin;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     long long r = i / Tin;
@@ -47,6 +49,7 @@ __global__ void avgpool_bwd_k(const float* __restrict__ dy, float* __restrict__ 
 
 __global__ void select_fwd_k(const float* __restrict__ x, const int64_t* __restrict__ label, float* __restrict__ y,
                              int B, int C, int T) {
+  pdl_prologue();
   long long n = (long long)B * T;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     int b = (int)(i / T);
@@ -58,6 +61,7 @@ __global__ void select_fwd_k(const float* __restrict__ x, const int64_t* __restr
 
 __global__ void select_bwd_k(const float* __restrict__ dy, const int64_t* __restrict__ label, float* __restrict__ dx,
                              int B, int C, int T) {
+  pdl_prologue();
   long long n = (long long)B * C * T;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     long long row = i / T;
@@ -69,6 +73,7 @@ __global__ void select_bwd_k(const float* __restrict__ dy, const int64_t* __rest
 
 __global__ void sq_err_const_sum_k(const float* __restrict__ a, float target, float scale, float* __restrict__ out,
                                    long long n) {
+  pdl_prologue();
   __shared__ float sm[33];
   float s = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -81,6 +86,7 @@ __global__ void sq_err_const_sum_k(const float* __restrict__ a, float target, fl
 
 __global__ void sq_err_const_bwd_k(const float* __restrict__ a, float target, float scale,
                                    const float* __restrict__ gscale, float* __restrict__ da, long long n) {
+  pdl_prologue();
   float g = 2.f * scale * gscale[0];
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     da[i] = g * (a[i] - target);
@@ -88,6 +94,7 @@ __global__ void sq_err_const_bwd_k(const float* __restrict__ a, float target, fl
 
 __global__ void abs_diff_sum_k(const float* __restrict__ a, const float* __restrict__ b, float scale,
                                float* __restrict__ out, long long n) {
+  pdl_prologue();
   __shared__ float sm[33];
   float s = 0.f;
   long long n4 = n >> 2;
@@ -106,6 +113,7 @@ __global__ void abs_diff_sum_k(const float* __restrict__ a, const float* __restr
 
 __global__ void abs_diff_bwd_k(const float* __restrict__ a, const float* __restrict__ b, float scale,
                                const float* __restrict__ gscale, float* __restrict__ da, long long n) {
+  pdl_prologue();
   float g = scale * gscale[0];
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float d = a[i] - b[i];
@@ -120,6 +128,7 @@ __global__ void adamw_multi_k(float* const* __restrict__ params, const float* co
                               const int64_t* __restrict__ sizes, int chunks_per_tensor, float lr, float b1, float b2,
                               float eps, float wd, float bc1, float bc2_sqrt, float gscale,
                               const float* __restrict__ step_dev) {
+  pdl_prologue();
   if (step_dev) {      // step counter lives on the device (CUDA-graph replays must advance it)
     const float st = *step_dev;
     bc1 = 1.f - powf(b1, st);
@@ -146,7 +155,8 @@ __global__ void adamw_multi_k(float* const* __restrict__ params, const float* co
   }
 }
 
-__global__ void step_inc_k(float* step) { *step += 1.f; }
+__global__ void step_inc_k(float* step) {
+  pdl_prologue(); *step += 1.f; }
 
 }  // namespace tdvc
 using namespace tdvc;
@@ -154,7 +164,7 @@ using namespace tdvc;
 extern "C" int tdvc_avgpool4s2_fwd(const float* x, float* y, int BC, int Tin, int Tout, void* stream) {
   TDVC_CHECK_ARG(BC >= 0 && Tin > 0 && Tout == (Tin + 2 - 4) / 2 + 1 && x && y);
   if (BC == 0) return TDVC_OK;
-  avgpool_fwd_k<<<ew_blocks((long long)BC * Tout), 256, 0, (cudaStream_t)stream>>>(x, y, BC, Tin, Tout);
+  tdvc::launch_k(avgpool_fwd_k, ew_blocks((long long)BC * Tout), 256, 0, (cudaStream_t)stream, x, y, BC, Tin, Tout);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
@@ -162,7 +172,7 @@ extern "C" int tdvc_avgpool4s2_fwd(const float* x, float* y, int BC, int Tin, in
 extern "C" int tdvc_avgpool4s2_bwd(const float* dy, float* dx, int BC, int Tin, int Tout, void* stream) {
   TDVC_CHECK_ARG(BC >= 0 && Tin > 0 && Tout == (Tin + 2 - 4) / 2 + 1 && dy && dx);
   if (BC == 0) return TDVC_OK;
-  avgpool_bwd_k<<<ew_blocks((long long)BC * Tin), 256, 0, (cudaStream_t)stream>>>(dy, dx, BC, Tin, Tout);
+  tdvc::launch_k(avgpool_bwd_k, ew_blocks((long long)BC * Tin), 256, 0, (cudaStream_t)stream, dy, dx, BC, Tin, Tout);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
@@ -171,7 +181,7 @@ extern "C" int tdvc_select_channel_fwd(const float* x, const int64_t* label, flo
                                        void* stream) {
   TDVC_CHECK_ARG(B >= 0 && C > 0 && T > 0 && x && label && y);
   if (B == 0) return TDVC_OK;
-  select_fwd_k<<<ew_blocks((long long)B * T), 256, 0, (cudaStream_t)stream>>>(x, label, y, B, C, T);
+  tdvc::launch_k(select_fwd_k, ew_blocks((long long)B * T), 256, 0, (cudaStream_t)stream, x, label, y, B, C, T);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
@@ -180,7 +190,7 @@ extern "C" int tdvc_select_channel_bwd(const float* dy, const int64_t* label, fl
                                        void* stream) {
   TDVC_CHECK_ARG(B >= 0 && C > 0 && T > 0 && dy && label && dx);
   if (B == 0) return TDVC_OK;
-  select_bwd_k<<<ew_blocks((long long)B * C * T), 256, 0, (cudaStream_t)stream>>>(dy, label, dx, B, C, T);
+  tdvc::launch_k(select_bwd_k, ew_blocks((long long)B * C * T), 256, 0, (cudaStream_t)stream, dy, label, dx, B, C, T);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
@@ -191,7 +201,7 @@ extern "C" int tdvc_sq_err_const_sum(const float* a, float target, float scale, 
   if (n == 0) return TDVC_OK;
   TDVC_CHECK_ARG(a);
   int blocks = (int)std::min<long long>((n + 1023) / 1024, 2LL * num_sms());
-  sq_err_const_sum_k<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, target, scale, out_sum, n);
+  tdvc::launch_k(sq_err_const_sum_k, blocks, 256, 0, (cudaStream_t)stream, a, target, scale, out_sum, n);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
@@ -201,7 +211,7 @@ extern "C" int tdvc_sq_err_const_bwd(const float* a, float target, float scale, 
   TDVC_CHECK_ARG(n >= 0);
   if (n == 0) return TDVC_OK;
   TDVC_CHECK_ARG(a && gscale && da);
-  sq_err_const_bwd_k<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(a, target, scale, gscale, da, n);
+  tdvc::launch_k(sq_err_const_bwd_k, ew_blocks(n), 256, 0, (cudaStream_t)stream, a, target, scale, gscale, da, n);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
@@ -212,7 +222,7 @@ extern "C" int tdvc_abs_diff_sum(const float* a, const float* b, float scale, fl
   if (n == 0) return TDVC_OK;
   TDVC_CHECK_ARG(a && b && ((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0));
   int blocks = (int)std::min<long long>((n + 2047) / 2048, 4LL * num_sms());
-  abs_diff_sum_k<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, b, scale, out_sum, n);
+  tdvc::launch_k(abs_diff_sum_k, blocks, 256, 0, (cudaStream_t)stream, a, b, scale, out_sum, n);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
@@ -222,7 +232,7 @@ extern "C" int tdvc_abs_diff_bwd(const float* a, const float* b, float scale, co
   TDVC_CHECK_ARG(n >= 0);
   if (n == 0) return TDVC_OK;
   TDVC_CHECK_ARG(a && b && gscale && da);
-  abs_diff_bwd_k<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(a, b, scale, gscale, da, n);
+  tdvc::launch_k(abs_diff_bwd_k, ew_blocks(n), 256, 0, (cudaStream_t)stream, a, b, scale, gscale, da, n);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
@@ -237,12 +247,12 @@ extern "C" int tdvc_adamw_multi(float* const* params, const float* const* grads,
   float bc1 = 1.f - powf(beta1, (float)std::max(step, 1));
   float bc2 = 1.f - powf(beta2, (float)std::max(step, 1));
   if (step_dev) {
-    step_inc_k<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+    tdvc::launch_k(step_inc_k, 1, 1, 0, (cudaStream_t)stream, step_dev);
     TDVC_LAUNCH_CHECK();
   }
   int chunks = (int)std::min<long long>((max_size + 256 * 8 - 1) / (256 * 8), 64);
   if (chunks < 1) chunks = 1;
-  adamw_multi_k<<<n_tensors * chunks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, sizes, chunks,
+  tdvc::launch_k(adamw_multi_k, n_tensors * chunks, 256, 0, (cudaStream_t)stream, params, grads, exp_avg, exp_avg_sq, sizes, chunks,
                                                                       lr, beta1, beta2, eps, weight_decay, bc1,
                                                                       sqrtf(bc2), grad_scale, step_dev);
   TDVC_LAUNCH_CHECK();

@@ -10,6 +10,7 @@ namespace tdvc {
 // one block per row
 __global__ void wn_fwd_k(const float* __restrict__ v, const float* __restrict__ g, float* __restrict__ w,
                          float* __restrict__ inv_norm, int cols) {
+  pdl_prologue();
   __shared__ float sm[33];
   const int r = blockIdx.x;
   const float* vr = v + (long long)r * cols;
@@ -28,6 +29,7 @@ __global__ void wn_fwd_k(const float* __restrict__ v, const float* __restrict__ 
 // w = g v / n :  dg = <dw, v>/n ;  dv = (g/n) (dw - v <dw,v>/n^2)
 __global__ void wn_bwd_k(const float* __restrict__ dw, const float* __restrict__ v, const float* __restrict__ g,
                          const float* __restrict__ inv_norm, float* __restrict__ dv, float* __restrict__ dg, int cols) {
+  pdl_prologue();
   __shared__ float sm[33];
   const int r = blockIdx.x;
   const float* vr = v + (long long)r * cols;
@@ -46,6 +48,7 @@ __global__ void wn_bwd_k(const float* __restrict__ dw, const float* __restrict__
 // per-(b,c) mean and 1/sqrt(var+eps) over T (biased variance, two-pass for fp32 accuracy)
 __global__ void instnorm_stats_k(const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ rstd, int T,
                                  float eps) {
+  pdl_prologue();
   __shared__ float sm[33];
   const long long r = blockIdx.x;
   const float* xr = x + r * T;
@@ -65,6 +68,7 @@ __global__ void instnorm_stats_k(const float* __restrict__ x, float* __restrict_
 __global__ void cin_apply_fwd_k(const float* __restrict__ x, const float* __restrict__ mean,
                                 const float* __restrict__ rstd, const float* __restrict__ gb, int Tg,
                                 float* __restrict__ y, int B, int C, int T, float slope) {
+  pdl_prologue();
   long long n = (long long)B * C * T;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     long long row = i / T;
@@ -86,6 +90,7 @@ __global__ void cin_apply_bwd_k(const float* __restrict__ dy, const float* __res
                                 const float* __restrict__ mean, const float* __restrict__ rstd,
                                 const float* __restrict__ gb, int Tg, const float* __restrict__ y_act,
                                 float* __restrict__ dx, float* __restrict__ dgb, int C, int T, float slope) {
+  pdl_prologue();
   __shared__ float sm[33];
   const long long row = blockIdx.x;
   const int b = (int)(row / C), c = (int)(row - (long long)b * C);
@@ -136,7 +141,7 @@ extern "C" int tdvc_weight_norm_fwd(const float* v, const float* g, float* w, fl
                                     void* stream) {
   TDVC_CHECK_ARG(rows > 0 && cols > 0 && v && g && w && inv_norm);
   int threads = cols >= 1024 ? 256 : (cols >= 128 ? 128 : 32);
-  wn_fwd_k<<<rows, threads, 0, (cudaStream_t)stream>>>(v, g, w, inv_norm, cols);
+  tdvc::launch_k(wn_fwd_k, rows, threads, 0, (cudaStream_t)stream, v, g, w, inv_norm, cols);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
@@ -145,7 +150,7 @@ extern "C" int tdvc_weight_norm_bwd(const float* dw, const float* v, const float
                                     float* dg, int rows, int cols, void* stream) {
   TDVC_CHECK_ARG(rows > 0 && cols > 0 && dw && v && g && inv_norm && dv && dg);
   int threads = cols >= 1024 ? 256 : (cols >= 128 ? 128 : 32);
-  wn_bwd_k<<<rows, threads, 0, (cudaStream_t)stream>>>(dw, v, g, inv_norm, dv, dg, cols);
+  tdvc::launch_k(wn_bwd_k, rows, threads, 0, (cudaStream_t)stream, dw, v, g, inv_norm, dv, dg, cols);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
@@ -153,7 +158,7 @@ extern "C" int tdvc_weight_norm_bwd(const float* dw, const float* v, const float
 extern "C" int tdvc_instnorm_stats(const float* x, float* mean, float* rstd, int BC, int T, float eps, void* stream) {
   TDVC_CHECK_ARG(BC >= 0 && T > 0 && x && mean && rstd);
   if (BC == 0) return TDVC_OK;
-  instnorm_stats_k<<<BC, T >= 1024 ? 256 : 128, 0, (cudaStream_t)stream>>>(x, mean, rstd, T, eps);
+  tdvc::launch_k(instnorm_stats_k, BC, T >= 1024 ? 256 : 128, 0, (cudaStream_t)stream, x, mean, rstd, T, eps);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
@@ -165,7 +170,7 @@ extern "C" int tdvc_cin_apply_fwd(const float* x, const float* mean, const float
   if (B == 0) return TDVC_OK;
   long long n = (long long)B * C * T;
   int blocks = (int)std::min<long long>((n + 255) / 256, 16LL * num_sms());
-  cin_apply_fwd_k<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, mean, rstd, gb, Tg, y, B, C, T, out_slope);
+  tdvc::launch_k(cin_apply_fwd_k, blocks, 256, 0, (cudaStream_t)stream, x, mean, rstd, gb, Tg, y, B, C, T, out_slope);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
@@ -177,7 +182,7 @@ extern "C" int tdvc_cin_apply_bwd(const float* dy, const float* x, const float* 
   TDVC_CHECK_ARG(gb == nullptr || ((Tg == 1 || Tg == T) && dgb != nullptr));
   TDVC_CHECK_ARG(out_slope == 1.0f || y_act != nullptr);
   if (B == 0) return TDVC_OK;
-  cin_apply_bwd_k<<<B * C, T >= 1024 ? 256 : 128, 0, (cudaStream_t)stream>>>(dy, x, mean, rstd, gb, Tg, y_act, dx, dgb,
+  tdvc::launch_k(cin_apply_bwd_k, B * C, T >= 1024 ? 256 : 128, 0, (cudaStream_t)stream, dy, x, mean, rstd, gb, Tg, y_act, dx, dgb,
                                                                              C, T, out_slope);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;

@@ -82,7 +82,7 @@ SIGNATURES = {
     "tdvc_pack_cl_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _I, _I, _I, _P, _P]),
     "tdvc_pack_weight_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "tdvc_conv1d_tc_wgrad_ws": (_L, [_I, _I, _I]),
-    "tdvc_conv1d_tc_wgrad": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "tdvc_conv1d_tc_wgrad": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "tdvc_conv1d_tc_fwd_ex": (_I, [C.POINTER(TcConv), _P]),
     "tdvc_conv1d_tc_fwd_stacked": (_I, [_P, _P, _P, _P] + [_I] * 12 + [_I, _F] + [_I] * 5 + [_P]),
     "tdvc_conv1d_tc_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P]),

@@ -828,12 +828,14 @@ class _Conv1dTC(torch.autograd.Function):
         need_b = ctx.has_bias and ctx.needs_input_grad[2]
         Cdp = _cp(Cout)
         dyp = None
+        db_from_wgrad = need_b and ctx.needs_input_grad[1]      # the wgrad GEMM yields it through a tap of ones
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
-            # one pass over dL/dy: bf16 channels-last copy shared by dgrad and wgrad + the bias gradient
-            if need_b:
+            # one pass over dL/dy: bf16 channels-last copy shared by dgrad and wgrad (+ the bias gradient as column
+            # sums when no wgrad follows)
+            if need_b and not db_from_wgrad:
                 db = torch.empty(Cout, device=x.device, dtype=torch.float32)
+                need_b = False
             dyp = _pack_act(dy, Cdp, 0, PAD_ZEROS, 1.0, cache=False, chan_sum=db)
-            need_b = False
         if ctx.needs_input_grad[0]:
             # dgrad = the same implicit GEMM on dy with channel-swapped, tap-flipped weights
             ph = pad if pad_mode == PAD_REFLECT else 0            # reflect halo kept in the staging buffer
@@ -856,8 +858,12 @@ class _Conv1dTC(torch.autograd.Function):
             halo = pad if pad_mode == PAD_REFLECT else 0
             dw = torch.empty_like(w)
             ws = torch.empty(lib.tdvc_conv1d_tc_wgrad_ws(Cout, Cin, K), device=x.device, dtype=torch.float32)
+            if db_from_wgrad:
+                db = torch.empty(Cout, device=x.device, dtype=torch.float32)
+                need_b = False
             _lib.check(lib.tdvc_conv1d_tc_wgrad(_p(dyp), _p(xp), _p(dw), _p(ws), B, Cdp, Tout, xp.shape[2], xp.shape[1],
-                                                Cout, Cin, K, dilation, halo - pad, 0, 0, _st()), "conv1d_tc_wgrad")
+                                                Cout, Cin, K, dilation, halo - pad, 0, 0, _p(db) if db_from_wgrad else None,
+                                                _st()), "conv1d_tc_wgrad")
         if need_b:
             db = torch.empty(Cout, device=x.device, dtype=torch.float32)
             _lib.check(lib.tdvc_bias_grad(_p(dy), _p(db), B, Cout, Tout, _st()), "bias_grad")
@@ -960,15 +966,15 @@ class _MRFCondPath(torch.autograd.Function):
         w0s, w2s = saved[2:2 + n], saved[2 + n:2 + 2 * n]
         lib = _lib.load()
         dev = cp.device
-        # dL/dgb -> packed bf16 (+ cond_var.2 bias gradients)
+        # dL/dgb -> packed bf16 (cond_var.2's bias gradients come out of its wgrad GEMM below)
         dgbp = torch.empty(B, T, n * C2p, device=dev, dtype=torch.bfloat16)
-        db2 = torch.zeros(n, C2, device=dev, dtype=torch.float32)
+        db2 = torch.empty(n, C2, device=dev, dtype=torch.float32)
         for j in range(n):
             if dgb[j] is None:
                 dgbp[:, :, j * C2p:(j + 1) * C2p].zero_()
                 continue
             d = _c(dgb[j])
-            _lib.check(lib.tdvc_pack_cl_bf16(_p(d), _p(dgbp), B, C2, T, n * C2p, 0, PAD_ZEROS, 1.0, _p(db2[j]), j * C2p, C2p,
+            _lib.check(lib.tdvc_pack_cl_bf16(_p(d), _p(dgbp), B, C2, T, n * C2p, 0, PAD_ZEROS, 1.0, None, j * C2p, C2p,
                                              -1, None, _st()), "pack dgb")
         # cond_var.2 weight gradients
         dw2 = []
@@ -977,7 +983,7 @@ class _MRFCondPath(torch.autograd.Function):
         for j in range(n):
             g = torch.empty(C2, Cc, K, device=dev, dtype=torch.float32)
             _lib.check(lib.tdvc_conv1d_tc_wgrad(_p(dgbp), _p(g1p), _p(g), _p(ws), B, n * C2p, T, n * Cg, T, C2, Cc, K, 1, -1,
-                                                j * Cg, j * C2p, _st()), "wgrad cond_var.2")
+                                                j * Cg, j * C2p, _p(db2[j]), _st()), "wgrad cond_var.2")
             dw2.append(g)
         # dL/dg1 (packed, LeakyReLU mask applied in the epilogue): grouped dgrad of cond_var.2
         w2tp = torch.empty(K, n * Cg, C2p, device=dev, dtype=torch.bfloat16)
@@ -995,7 +1001,7 @@ class _MRFCondPath(torch.autograd.Function):
         # cond_var.0 weight (+ bias, through the constant-one channel of cp) gradients: one GEMM for all blocks
         dw0_all = torch.empty(n * Cg, Cc + 1, K, device=dev, dtype=torch.float32)
         _lib.check(lib.tdvc_conv1d_tc_wgrad(_p(dg1p), _p(cp), _p(dw0_all), _p(ws), B, n * Cg, T, Cg, T, n * Cg, Cc + 1, K, 1,
-                                            -1, 0, 0, _st()), "wgrad cond_var.0")
+                                            -1, 0, 0, None, _st()), "wgrad cond_var.0")
         # dL/dc: one conv over the n*Cg concatenated channels (sums the blocks' contributions in the GEMM)
         dc = None
         if ctx.needs_input_grad[0]:
@@ -1071,13 +1077,14 @@ class _FilmPosconvTC(torch.autograd.Function):
         Cp = a1p.shape[2]
         Cdp = _cp(Cout)
         db = torch.empty(Cout, device=dy.device, dtype=torch.float32) if (ctx.has_bias and ctx.needs_input_grad[3]) else None
-        dyp = _pack_act(dy, Cdp, 0, PAD_ZEROS, 1.0, cache=False, chan_sum=db)
+        db_from_wgrad = db is not None and ctx.needs_input_grad[2]      # the wgrad GEMM yields it through a tap of ones
+        dyp = _pack_act(dy, Cdp, 0, PAD_ZEROS, 1.0, cache=False, chan_sum=None if db_from_wgrad else db)
         dw = None
         if ctx.needs_input_grad[2]:
             dw = torch.empty_like(w)
             ws = torch.empty(lib.tdvc_conv1d_tc_wgrad_ws(Cout, Cc, 1), device=dy.device, dtype=torch.float32)
             _lib.check(lib.tdvc_conv1d_tc_wgrad(_p(dyp), _p(a1p), _p(dw), _p(ws), B, Cdp, T, Cp, T, Cout, Cc, 1, 1, 0, 0, 0,
-                                                _st()), "posconv_tc_wgrad")
+                                                _p(db) if db_from_wgrad else None, _st()), "posconv_tc_wgrad")
         dh0 = dgb = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             Cinp16 = _ceil(Cc, 16)
