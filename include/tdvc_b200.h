@@ -54,6 +54,11 @@ int tdvc_weight_norm_fwd(const float* v, const float* g, float* w, float* inv_no
                          int rows, int cols, void* stream);
 int tdvc_weight_norm_bwd(const float* dw, const float* v, const float* g, const float* inv_norm,
                          float* dv, float* dg, int rows, int cols, void* stream);
+/* the forward for MANY weights in one launch (every weight of G and D once per step instead of ~530 launches):
+ * table = device int64[n_weights][4] {v pointer, g pointer, offset of this w inside flat_w (floats), cols};
+ * row_start = device int32[n_weights + 1], first global row of each weight; inv norms go to flat_inv[global row]. */
+int tdvc_weight_norm_fwd_multi(const void* table, const void* row_start, int n_weights, int total_rows,
+                               float* flat_w, float* flat_inv, void* stream);
 
 /* ---- Conv1d (model/generator.py:75-92,146-156,214-249,299-347; model/discriminator.py:17-38;
  *      depthwise Kaiser FIR F.conv1d at model/generator.py:165-168, model/discriminator.py:100-102).
@@ -176,6 +181,10 @@ int tdvc_pack_weight_bf16(const float* w, void* wp, int Cout, int Cin, int K, in
                           int transpose_flip, int R_total, int r_off, int Q_total, int q_off, void* stream);
 /* (R_total, r_off, Q_total, q_off): write the packed block at row r_off / column q_off of a larger
  * wp[K][R_total][Q_total] holding several convs' weights (grouped launches); <= 0 totals mean "the block is all". */
+/* MANY weights in one launch: jobs = device int64[n_jobs][8] {offset of w inside flat_w (floats), offset of wp inside
+ * flat_wp (bf16 elements), Cout, Cin, K, Rp, Qp, transpose_flip}; job output layout [K][Rp][Qp] as above. */
+int tdvc_pack_weight_bf16_multi(const void* jobs, int n_jobs, int blocks_per_job, const float* flat_w, void* flat_wp,
+                                void* stream);
 /* y[B,Cout,Tout] fp32 NCW = epilogue( sum_k sum_ci xp[b, t + k*dilation + off, ci] * wp[k, co, ci] )
  * epilogue: + bias[co] ; FiLM  y*(1+gb[b,co,t]) + gb[b,Cout+co,t] when gb != NULL ; + residual ; act. */
 int tdvc_conv1d_tc_fwd(const void* xp, const void* wp, const float* bias, const float* gb,
@@ -224,6 +233,8 @@ int tdvc_conv1d_tc_wgrad(const void* dyp, const void* xp, float* dw, float* ws, 
                          int x_ch_off /* first channel of the conv's input inside xp */,
                          int dy_ch_off /* first channel of the conv's output inside dyp */,
                          float* db /* optional: bias gradient [Cout] = sum over (b,t) of dL/dy, from the same GEMM */,
+                         int ws_is_zero /* != 0: ws holds zeros on entry and is left zeroed on return (a persistent
+                                           workspace: no memset per call); 0: ws is scratch, cleared here */,
                          void* stream);
 
 #ifdef __cplusplus

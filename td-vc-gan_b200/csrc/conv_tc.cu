@@ -1095,6 +1095,28 @@ __global__ void wgrad_finalize_k(const float* __restrict__ ws, float* __restrict
     for (int i = threadIdx.x; i < Cout; i += blockDim.x) db[i] = ws[(long long)K * Np * Mp + i];
 }
 
+// same, and leaves the workspace zeroed again (only the entries read here were ever written): a persistent workspace
+// then needs no memset node per call
+__global__ void wgrad_finalize_zero_k(float* __restrict__ ws, float* __restrict__ dw, int Cout, int Cin, int K, int Np, int Mp,
+                                      float* __restrict__ db, int has_bias_row) {
+  pdl_prologue();
+  long long n = (long long)Cout * Cin * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int k = (int)(i % K);
+    long long r = i / K;
+    int ci = (int)(r % Cin), co = (int)(r / Cin);
+    float* src = ws + ((long long)k * Np + co) * Mp + ci;
+    dw[i] = *src;
+    *src = 0.f;
+  }
+  if (has_bias_row && blockIdx.x == 0)
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) {
+      float* src = ws + (long long)K * Np * Mp + i;
+      if (db) db[i] = *src;
+      *src = 0.f;
+    }
+}
+
 // ------------------------------------------------------------------------------------------ pack kernels
 // x[B,C,T] fp32 NCW -> xp[B,Tp,Cp] bf16 channels-last, LeakyReLU(in_slope), halo rows reflect- or zero-filled.
 // x[B,C,T] fp32 NCW -> xp[B,Tp,Cp] bf16 channels-last (channels [c_off, c_off+Cw)), LeakyReLU(slope), reflect / zero
@@ -1193,6 +1215,29 @@ __global__ void pack_weight_bf16_k(const float* __restrict__ w, __nv_bfloat16* _
   }
 }
 
+// Many weights in one launch: job[j] = {src offset in flat_w (floats), dst offset in flat_wp (bf16), Cout, Cin, K, Rp, Qp,
+// transpose_flip}; blockIdx.y = job, blockIdx.x strides over the job's K*Rp*Qp outputs (layout of pack_weight_bf16_k
+// with R_total = Rp, Q_total = Qp).
+__global__ void pack_weight_multi_k(const long long* __restrict__ jobs, const float* __restrict__ flat_w,
+                                    __nv_bfloat16* __restrict__ flat_wp) {
+  pdl_prologue();
+  const long long* e = jobs + 8LL * blockIdx.y;
+  const float* w = flat_w + e[0];
+  __nv_bfloat16* wp = flat_wp + e[1];
+  const int Cout = (int)e[2], Cin = (int)e[3], K = (int)e[4], Rp = (int)e[5], Qp = (int)e[6], flip = (int)e[7];
+  const long long n = (long long)K * Rp * Qp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int qq = (int)(i % Qp);
+    const long long r2 = i / Qp;
+    const int rr = (int)(r2 % Rp);
+    const int k = (int)(r2 / Rp);
+    const int co = flip ? qq : rr, ci = flip ? rr : qq;
+    const int ks = flip ? K - 1 - k : k;
+    const float v = (co < Cout && ci < Cin) ? w[((long long)co * Cin + ci) * K + ks] : 0.f;
+    wp[i] = __float2bfloat16(v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1271,6 +1316,15 @@ extern "C" int tdvc_pack_weight_bf16(const float* w, void* wp, int Cout, int Cin
   int blocks = (int)std::min<long long>((n + 255) / 256, 8LL * num_sms());
   tdvc::launch_k(pack_weight_bf16_k, blocks, 256, 0, (cudaStream_t)stream, w, (__nv_bfloat16*)wp, Cout, Cin, K, Rp, Qp, transpose_flip, R_total,
                                                                        r_off, Q_total, q_off);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_pack_weight_bf16_multi(const void* jobs, int n_jobs, int blocks_per_job, const float* flat_w, void* flat_wp,
+                                           void* stream) {
+  TDVC_CHECK_ARG(jobs && n_jobs > 0 && n_jobs <= 65535 && blocks_per_job > 0 && flat_w && flat_wp);
+  tdvc::launch_k(pack_weight_multi_k, dim3(blocks_per_job, n_jobs), 256, 0, (cudaStream_t)stream, (const long long*)jobs, flat_w,
+                 (__nv_bfloat16*)flat_wp);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
@@ -1554,7 +1608,7 @@ extern "C" int64_t tdvc_conv1d_tc_wgrad_ws(int Cout, int Cin, int K) {
 // xp row = t + tap*dilation + t_off).
 extern "C" int tdvc_conv1d_tc_wgrad(const void* dyp, const void* xp, float* dw, float* ws, int B, int Cdp, int Tout, int Cp,
                                     int Tp, int Cout, int Cin, int K, int dilation, int t_off, int x_ch_off,
-                                    int dy_ch_off, float* db, void* stream) {
+                                    int dy_ch_off, float* db, int ws_is_zero, void* stream) {
   TDVC_CHECK_ARG(dyp && xp && dw && ws && B >= 0 && Cdp % 8 == 0 && Cp % 8 == 0 && dy_ch_off >= 0 && x_ch_off >= 0 &&
                  Cdp >= dy_ch_off + Cout && Cp >= x_ch_off + Cin && Tout > 0 && Tp > 0 && K > 0 && dilation > 0);
   cudaStream_t st = (cudaStream_t)stream;
@@ -1564,7 +1618,7 @@ extern "C" int tdvc_conv1d_tc_wgrad(const void* dyp, const void* xp, float* dw, 
   p.Mp = ((Cin + 127) / 128) * 128;
   p.Np = ((Cout + 15) / 16) * 16;
   p.bias = db ? 1 : 0;
-  TDVC_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * ((size_t)K * p.Np * p.Mp + p.Np), st));
+  if (!ws_is_zero) TDVC_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * ((size_t)K * p.Np * p.Mp + p.Np), st));
   if (B == 0) {
     TDVC_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * Cin * K, st));
     if (db) TDVC_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)Cout, st));
@@ -1621,7 +1675,8 @@ extern "C" int tdvc_conv1d_tc_wgrad(const void* dyp, const void* xp, float* dw, 
   TDVC_LAUNCH_CHECK();
   long long n = (long long)Cout * Cin * K;
   int blocks = (int)std::min<long long>((n + 255) / 256, 4LL * num_sms());
-  tdvc::launch_k(wgrad_finalize_k, blocks, 256, 0, st, ws, dw, Cout, Cin, K, p.Np, p.Mp, db);
+  if (ws_is_zero) tdvc::launch_k(wgrad_finalize_zero_k, blocks, 256, 0, st, ws, dw, Cout, Cin, K, p.Np, p.Mp, db, p.bias);
+  else tdvc::launch_k(wgrad_finalize_k, blocks, 256, 0, st, ws, dw, Cout, Cin, K, p.Np, p.Mp, db);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }

@@ -26,6 +26,36 @@ __global__ void wn_fwd_k(const float* __restrict__ v, const float* __restrict__ 
   if (threadIdx.x == 0) inv_norm[r] = inv;
 }
 
+// The same for MANY weights in one launch (a step normalises ~270 weights; as separate launches that is ~530 graph nodes).
+// table[j] = {v, g, offset of w_j in flat_w (floats), cols}; row_start[j] = first global row of weight j (n + 1 entries);
+// one block per global row, inv_norm indexed by global row.
+__global__ void wn_fwd_multi_k(const long long* __restrict__ table, const int* __restrict__ row_start, int n,
+                               float* __restrict__ flat_w, float* __restrict__ flat_inv) {
+  pdl_prologue();
+  __shared__ float sm[33];
+  const int gr = blockIdx.x;
+  int lo = 0, hi = n - 1;                       // last j with row_start[j] <= gr
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(row_start + mid) <= gr) lo = mid; else hi = mid - 1;
+  }
+  const long long* e = table + 4LL * lo;
+  const float* v = reinterpret_cast<const float*>(e[0]);
+  const float* g = reinterpret_cast<const float*>(e[1]);
+  const int cols = (int)e[3];
+  const int r = gr - __ldg(row_start + lo);
+  const float* vr = v + (long long)r * cols;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) { float a = vr[i]; s = fmaf(a, a, s); }
+  s = block_sum(s, sm);
+  float inv = rsqrtf(s);
+  inv = inv * (1.5f - 0.5f * s * inv * inv);
+  const float scale = g[r] * inv;
+  float* wr = flat_w + e[2] + (long long)r * cols;
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) wr[i] = vr[i] * scale;
+  if (threadIdx.x == 0) flat_inv[gr] = inv;
+}
+
 // w = g v / n :  dg = <dw, v>/n ;  dv = (g/n) (dw - v <dw,v>/n^2)
 __global__ void wn_bwd_k(const float* __restrict__ dw, const float* __restrict__ v, const float* __restrict__ g,
                          const float* __restrict__ inv_norm, float* __restrict__ dv, float* __restrict__ dg, int cols) {
@@ -142,6 +172,15 @@ extern "C" int tdvc_weight_norm_fwd(const float* v, const float* g, float* w, fl
   TDVC_CHECK_ARG(rows > 0 && cols > 0 && v && g && w && inv_norm);
   int threads = cols >= 1024 ? 256 : (cols >= 128 ? 128 : 32);
   tdvc::launch_k(wn_fwd_k, rows, threads, 0, (cudaStream_t)stream, v, g, w, inv_norm, cols);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_weight_norm_fwd_multi(const void* table, const void* row_start, int n_weights, int total_rows,
+                                          float* flat_w, float* flat_inv, void* stream) {
+  TDVC_CHECK_ARG(table && row_start && n_weights > 0 && total_rows > 0 && flat_w && flat_inv);
+  tdvc::launch_k(wn_fwd_multi_k, total_rows, 128, 0, (cudaStream_t)stream, (const long long*)table, (const int*)row_start,
+                 n_weights, flat_w, flat_inv);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }

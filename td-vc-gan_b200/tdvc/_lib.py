@@ -48,6 +48,7 @@ SIGNATURES = {
     "tdvc_device_is_sm100": (_I, []),
     "tdvc_weight_norm_fwd": (_I, [_P, _P, _P, _P, _I, _I, _P]),
     "tdvc_weight_norm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "tdvc_weight_norm_fwd_multi": (_I, [_P, _P, _I, _I, _P, _P, _P]),
     "tdvc_conv1d_fwd": (_I, [_G, _P, _P, _P, _P, _P, _P]),
     "tdvc_conv1d_bwd_data_ws": (_L, [_G]),
     "tdvc_conv1d_bwd_data": (_I, [_G, _P, _P, _P, _P, _P, _P]),
@@ -82,7 +83,8 @@ SIGNATURES = {
     "tdvc_pack_cl_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _I, _I, _I, _P, _P]),
     "tdvc_pack_weight_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "tdvc_conv1d_tc_wgrad_ws": (_L, [_I, _I, _I]),
-    "tdvc_conv1d_tc_wgrad": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "tdvc_conv1d_tc_wgrad": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P]),
+    "tdvc_pack_weight_bf16_multi": (_I, [_P, _I, _I, _P, _P, _P]),
     "tdvc_conv1d_tc_fwd_ex": (_I, [C.POINTER(TcConv), _P]),
     "tdvc_conv1d_tc_fwd_stacked": (_I, [_P, _P, _P, _P] + [_I] * 12 + [_I, _F] + [_I] * 5 + [_P]),
     "tdvc_conv1d_tc_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P]),

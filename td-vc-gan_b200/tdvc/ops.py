@@ -97,12 +97,17 @@ class _WeightNorm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, v, g):
         _req(v, g)
-        v, g = _c(v), _c(g)
-        rows = v.shape[0]
-        cols = v.numel() // rows
-        w = torch.empty_like(v)
-        inv = torch.empty(rows, device=v.device, dtype=torch.float32)
-        _lib.check(_lib.load().tdvc_weight_norm_fwd(_p(v), _p(g), _p(w), _p(inv), rows, cols, _st()), "weight_norm_fwd")
+        pre = _step_cache.lookup_w(v, g)
+        if pre is not None:                      # normalised by the scope's batched launch
+            w, inv = pre
+        else:
+            v, g = _c(v), _c(g)
+            rows = v.shape[0]
+            cols = v.numel() // rows
+            w = torch.empty_like(v)
+            inv = torch.empty(rows, device=v.device, dtype=torch.float32)
+            _lib.check(_lib.load().tdvc_weight_norm_fwd(_p(v), _p(g), _p(w), _p(inv), rows, cols, _st()), "weight_norm_fwd")
+            _step_cache.note_w(v, g, w)
         ctx.save_for_backward(v, g, inv)
         return w
 
@@ -123,16 +128,31 @@ class _StepCache:
     """Inside `with ops.step_cache():` a weight that has not changed is normalised (and packed to bf16) once and
     reused by every forward pass of the scope -- the generator runs 3-4 times per training iteration on the same
     weights.  Reuse is through autograd (the cached tensor carries its grad_fn), so gradients from all passes
-    accumulate into one weight-norm backward.  Entries are keyed on the parameter versions and dropped at scope exit."""
+    accumulate into one weight-norm backward.  Entries are keyed on the parameter versions and dropped at scope exit.
+
+    Batching: the (v, g) pairs and the bf16 packs a scope asked for are remembered (the PLAN); from the next scope on,
+    entering the scope normalises every planned weight with ONE multi-tensor launch and packs every planned operand
+    with ONE more, instead of ~530 + ~380 small launches per step.  `_WeightNorm.forward` / `_pack_w` then pick their
+    result up from the flat buffers.  TDVC_NO_WN_BATCH=1 disables it."""
 
     def __init__(self):
         self.depth = 0
         self.wn = {}
         self.wp = {}
+        self.plan_w = []            # [(weakref v, weakref g)]
+        self.plan_w_idx = {}        # (v ptr, g ptr) -> index into plan_w
+        self.plan_p = []            # [(weight index, rows_p, cols_p, flip)]
+        self.plan_p_idx = {}
+        self.tables = None
+        self.pre_w = {}             # this scope: (v ptr, g ptr) -> (w, inv, v version, g version)
+        self.pre_p = {}             # this scope: (w ptr, rows_p, cols_p, flip) -> packed operand
+        self.cur_w = {}             # this scope: w ptr -> weight index
 
     def __enter__(self):
         if os.environ.get("TDVC_NO_STEP_CACHE") != "1":
             self.depth += 1
+            if self.depth == 1:
+                self._prelaunch()
         return self
 
     def __exit__(self, *exc):
@@ -141,7 +161,106 @@ class _StepCache:
         if self.depth == 0:
             self.wn.clear()
             self.wp.clear()
+            self.pre_w.clear()
+            self.pre_p.clear()
+            self.cur_w.clear()
         return False
+
+    # ---- plan bookkeeping
+    def note_w(self, v, g, w):
+        if self.depth == 0 or not (v.is_leaf and g.is_leaf):
+            return
+        key = (v.data_ptr(), g.data_ptr())
+        idx = self.plan_w_idx.get(key)
+        if idx is None:
+            idx = len(self.plan_w)
+            self.plan_w.append((weakref.ref(v), weakref.ref(g)))
+            self.plan_w_idx[key] = idx
+            self.tables = None
+        self.cur_w[w.data_ptr()] = idx
+
+    def note_p(self, w, rows_p, cols_p, flip):
+        idx = self.cur_w.get(w.data_ptr()) if self.depth > 0 else None
+        if idx is None:
+            return
+        key = (idx, rows_p, cols_p, bool(flip))
+        if key not in self.plan_p_idx:
+            self.plan_p_idx[key] = len(self.plan_p)
+            self.plan_p.append(key)
+            self.tables = None
+
+    def lookup_w(self, v, g):
+        if self.depth == 0:
+            return None
+        hit = self.pre_w.get((v.data_ptr(), g.data_ptr()))
+        if hit is None or hit[2] != v._version or hit[3] != g._version:
+            return None
+        return hit[0], hit[1]
+
+    def lookup_p(self, w, rows_p, cols_p, flip):
+        return self.pre_p.get((w.data_ptr(), rows_p, cols_p, bool(flip))) if self.depth > 0 else None
+
+    # ---- the batched launches
+    def _build_tables(self, live, dev):
+        al = lambda n, a: (n + a - 1) // a * a
+        rows, tab, w_off, off, r = [0], [], [], 0, 0
+        for v, g in live:
+            nr = v.shape[0]
+            cols = v.numel() // nr
+            tab += [v.data_ptr(), g.data_ptr(), off, cols]
+            w_off.append(off)
+            off += al(v.numel(), 64)
+            r += nr
+            rows.append(r)
+        jobs, p_off, poff = [], [], 0
+        for (idx, rows_p, cols_p, flip) in self.plan_p:
+            v = live[idx][0]
+            Cout, Cin, K = v.shape
+            jobs += [w_off[idx], poff, Cout, Cin, K, rows_p, cols_p, int(flip)]
+            p_off.append(poff)
+            poff += al(K * rows_p * cols_p, 64)
+        t = dict(sig=tuple(tab[0::4]) + tuple(tab[1::4]), dev=dev, n=len(live), total_rows=r, w_elems=off, p_elems=poff,
+                 w_off=w_off, row_start=rows, p_off=p_off,
+                 table=torch.tensor(tab, dtype=torch.int64).to(dev), rows_dev=torch.tensor(rows, dtype=torch.int32).to(dev),
+                 jobs=torch.tensor(jobs, dtype=torch.int64).to(dev) if jobs else None)
+        return t
+
+    def _prelaunch(self):
+        if not self.plan_w or os.environ.get("TDVC_NO_WN_BATCH") == "1" or branch_streams_enabled() or not torch.cuda.is_available():
+            return
+        live = [(rv(), rg()) for rv, rg in self.plan_w]
+        if any(v is None or g is None for v, g in live):          # a module went away: start the plan over
+            self.plan_w, self.plan_w_idx, self.plan_p, self.plan_p_idx, self.tables = [], {}, [], {}, None
+            return
+        dev = live[0][0].device
+        if any(v.device != dev or not v.is_contiguous() or not g.is_contiguous() for v, g in live):
+            return
+        sig = tuple(v.data_ptr() for v, _ in live) + tuple(g.data_ptr() for _, g in live)
+        if self.tables is None or self.tables["sig"] != sig or self.tables["dev"] != dev:
+            if torch.cuda.is_current_stream_capturing():
+                return                                           # host->device table upload is not capturable
+            self.tables = self._build_tables(live, dev)
+        t = self.tables
+        lib = _lib.load()
+        flat_w = torch.empty(t["w_elems"], device=dev, dtype=torch.float32)
+        flat_inv = torch.empty(t["total_rows"], device=dev, dtype=torch.float32)
+        _lib.check(lib.tdvc_weight_norm_fwd_multi(_p(t["table"]), _p(t["rows_dev"]), t["n"], t["total_rows"], _p(flat_w),
+                                                  _p(flat_inv), _st()), "weight_norm_fwd_multi")
+        ws = []
+        for j, (v, g) in enumerate(live):
+            w = flat_w[t["w_off"][j]:t["w_off"][j] + v.numel()].view_as(v)
+            inv = flat_inv[t["row_start"][j]:t["row_start"][j + 1]]
+            self.pre_w[(v.data_ptr(), g.data_ptr())] = (w, inv, v._version, g._version)
+            self.cur_w[w.data_ptr()] = j
+            ws.append(w)
+        if t["jobs"] is not None:
+            flat_wp = torch.empty(t["p_elems"], device=dev, dtype=torch.bfloat16)
+            _lib.check(lib.tdvc_pack_weight_bf16_multi(_p(t["jobs"]), len(self.plan_p), 8, _p(flat_w), _p(flat_wp), _st()),
+                       "pack_weight_bf16_multi")
+            for i, (idx, rows_p, cols_p, flip) in enumerate(self.plan_p):
+                K = live[idx][0].shape[2]
+                wp = flat_wp[t["p_off"][i]:t["p_off"][i] + K * rows_p * cols_p].view(K, rows_p, cols_p)
+                self.pre_p[(ws[idx].data_ptr(), rows_p, cols_p, flip)] = wp
 
 
 _step_cache = _StepCache()
@@ -766,10 +885,14 @@ def _pack_w(w, rows_p, cols_p, transpose_flip):
     Cout, Cin, K = w.shape
     key = None
     if _step_cache.depth > 0:
+        pre = _step_cache.lookup_p(w, rows_p, cols_p, transpose_flip)
+        if pre is not None:                        # packed by the scope's batched launch
+            return pre
         key = (w.data_ptr(), w._version, tuple(w.shape), rows_p, cols_p, bool(transpose_flip))
         hit = _step_cache.wp.get(key)
         if hit is not None and hit[0]() is w:
             return hit[1]
+        _step_cache.note_p(w, rows_p, cols_p, transpose_flip)
     wp = torch.empty(K, rows_p, cols_p, device=w.device, dtype=torch.bfloat16)
     coutp, cinp = (cols_p, rows_p) if transpose_flip else (rows_p, cols_p)
     _lib.check(_lib.load().tdvc_pack_weight_bf16(_p(w), _p(wp), Cout, Cin, K, coutp, cinp, int(transpose_flip), 0, 0, 0, 0,
@@ -777,6 +900,27 @@ def _pack_w(w, rows_p, cols_p, transpose_flip):
     if key is not None:
         _step_cache.wp[key] = (weakref.ref(w), wp)
     return wp
+
+
+# Persistent, always-zero split-K workspace of the tcgen05 wgrad: the kernel accumulates into it and its finalize pass
+# reads the result and writes the zeros back, so no memset node precedes each of the ~470 wgrad calls of a step.
+# One buffer per device (grow-only; superseded buffers are kept alive because captured graphs may still point at them).
+# With branch streams calls may overlap, so each call then gets its own scratch and clears it itself.
+_WGRAD_WS = {}
+_WGRAD_WS_RETIRED = []
+
+
+def _wgrad_ws(n_floats: int, dev):
+    """-> (workspace tensor, ws_is_zero flag for tdvc_conv1d_tc_wgrad)"""
+    if branch_streams_enabled():
+        return torch.empty(n_floats, device=dev, dtype=torch.float32), 0
+    buf = _WGRAD_WS.get(dev)
+    if buf is None or buf.numel() < n_floats:
+        if buf is not None:
+            _WGRAD_WS_RETIRED.append(buf)
+        buf = torch.zeros(max(n_floats, 1 << 20), device=dev, dtype=torch.float32)
+        _WGRAD_WS[dev] = buf
+    return buf, 1
 
 
 class _Conv1dTC(torch.autograd.Function):
@@ -857,13 +1001,13 @@ class _Conv1dTC(torch.autograd.Function):
             # wgrad on tcgen05 from the two packed operands (time is the GEMM K dimension)
             halo = pad if pad_mode == PAD_REFLECT else 0
             dw = torch.empty_like(w)
-            ws = torch.empty(lib.tdvc_conv1d_tc_wgrad_ws(Cout, Cin, K), device=x.device, dtype=torch.float32)
+            ws, wz = _wgrad_ws(lib.tdvc_conv1d_tc_wgrad_ws(Cout, Cin, K), x.device)
             if db_from_wgrad:
                 db = torch.empty(Cout, device=x.device, dtype=torch.float32)
                 need_b = False
             _lib.check(lib.tdvc_conv1d_tc_wgrad(_p(dyp), _p(xp), _p(dw), _p(ws), B, Cdp, Tout, xp.shape[2], xp.shape[1],
                                                 Cout, Cin, K, dilation, halo - pad, 0, 0, _p(db) if db_from_wgrad else None,
-                                                _st()), "conv1d_tc_wgrad")
+                                                wz, _st()), "conv1d_tc_wgrad")
         if need_b:
             db = torch.empty(Cout, device=x.device, dtype=torch.float32)
             _lib.check(lib.tdvc_bias_grad(_p(dy), _p(db), B, Cout, Tout, _st()), "bias_grad")
@@ -886,6 +1030,19 @@ _STACKED_COND = os.environ.get("TDVC_TC_STACKED", "1") != "0"     # development 
 def set_stacked_cond(on: bool) -> None:
     global _STACKED_COND
     _STACKED_COND = bool(on)
+
+
+def _step_cached(tag, tensors, make):
+    """make() once per step scope for this exact set of source tensors (identity + version); outside a scope, every call.
+    The entry keeps the sources alive so that their addresses cannot be recycled under the key."""
+    if _step_cache.depth == 0:
+        return make()
+    key = (tag,) + tuple((t.data_ptr(), t._version) if t is not None else None for t in tensors)
+    hit = _step_cache.wp.get(key)
+    if hit is None:
+        hit = (list(tensors), make())
+        _step_cache.wp[key] = hit
+    return hit[1]
 
 
 class _MRFCondPath(torch.autograd.Function):
@@ -925,18 +1082,23 @@ class _MRFCondPath(torch.autograd.Function):
         stacked = _STACKED_COND and Cg >= 64 and K * 128 * Cg * 2 + 2 * (256 + 8 * K) * 128 + 3 * 272 * 32 <= 220 * 1024
         pitch0 = Cc if stacked else Cg
         R0 = (n - 1) * pitch0 + Cg
-        w0p = torch.empty(K, R0, Cg, device=dev, dtype=torch.bfloat16)
-        w2p = torch.empty(K, n * C2p, Cg, device=dev, dtype=torch.bfloat16)
-        b0p = torch.zeros(R0, device=dev, dtype=torch.float32)
-        b2p = torch.zeros(n * C2p, device=dev, dtype=torch.float32)
-        for j in range(n):
-            w0, w2 = _c(w0s[j]), _c(w2s[j])
-            _lib.check(lib.tdvc_pack_weight_bf16(_p(w0), _p(w0p), Cc, Cc, K, Cg, Cg, 0, R0, j * pitch0, Cg, 0, _st()), "pack w0")
-            _lib.check(lib.tdvc_pack_weight_bf16(_p(w2), _p(w2p), C2, Cc, K, C2p, Cg, 0, n * C2p, j * C2p, Cg, 0, _st()), "pack w2")
-            if b0s[j] is not None:
-                b0p[j * pitch0:j * pitch0 + Cc].copy_(b0s[j])
-            if b2s[j] is not None:
-                b2p[j * C2p:j * C2p + C2].copy_(b2s[j])
+        def pack_fwd():
+            w0p = torch.empty(K, R0, Cg, device=dev, dtype=torch.bfloat16)
+            w2p = torch.empty(K, n * C2p, Cg, device=dev, dtype=torch.bfloat16)
+            b0p = torch.zeros(R0, device=dev, dtype=torch.float32)
+            b2p = torch.zeros(n * C2p, device=dev, dtype=torch.float32)
+            for j in range(n):
+                w0, w2 = _c(w0s[j]), _c(w2s[j])
+                _lib.check(lib.tdvc_pack_weight_bf16(_p(w0), _p(w0p), Cc, Cc, K, Cg, Cg, 0, R0, j * pitch0, Cg, 0, _st()), "pack w0")
+                _lib.check(lib.tdvc_pack_weight_bf16(_p(w2), _p(w2p), C2, Cc, K, C2p, Cg, 0, n * C2p, j * C2p, Cg, 0, _st()), "pack w2")
+                if b0s[j] is not None:
+                    b0p[j * pitch0:j * pitch0 + Cc].copy_(b0s[j])
+                if b2s[j] is not None:
+                    b2p[j * C2p:j * C2p + C2].copy_(b2s[j])
+            return w0p, w2p, b0p, b2p
+
+        # the generator runs several times per training iteration on the same weights: packed once per step scope
+        w0p, w2p, b0p, b2p = _step_cached(("cond_fwd", stacked), list(w0s) + list(w2s) + list(b0s) + list(b2s), pack_fwd)
         # all cond_var.0 convs: packed bf16 output g1p[B, T, n*Cg] = leaky_relu(conv + bias)
         g1p = torch.empty(B, T, n * Cg, device=dev, dtype=torch.bfloat16)
         if stacked:
@@ -978,21 +1140,24 @@ class _MRFCondPath(torch.autograd.Function):
                                              -1, None, _st()), "pack dgb")
         # cond_var.2 weight gradients
         dw2 = []
-        ws = torch.empty(max(lib.tdvc_conv1d_tc_wgrad_ws(C2, Cc, K), lib.tdvc_conv1d_tc_wgrad_ws(n * Cg, Cc + 1, K)),
-                         device=dev, dtype=torch.float32)
+        ws, wz = _wgrad_ws(max(lib.tdvc_conv1d_tc_wgrad_ws(C2, Cc, K), lib.tdvc_conv1d_tc_wgrad_ws(n * Cg, Cc + 1, K)), dev)
         for j in range(n):
             g = torch.empty(C2, Cc, K, device=dev, dtype=torch.float32)
             _lib.check(lib.tdvc_conv1d_tc_wgrad(_p(dgbp), _p(g1p), _p(g), _p(ws), B, n * C2p, T, n * Cg, T, C2, Cc, K, 1, -1,
-                                                j * Cg, j * C2p, _p(db2[j]), _st()), "wgrad cond_var.2")
+                                                j * Cg, j * C2p, _p(db2[j]), wz, _st()), "wgrad cond_var.2")
             dw2.append(g)
         # dL/dg1 (packed, LeakyReLU mask applied in the epilogue): grouped dgrad of cond_var.2
-        w2tp = torch.empty(K, n * Cg, C2p, device=dev, dtype=torch.bfloat16)
-        w0tp = torch.empty(K, Cg, n * Cg, device=dev, dtype=torch.bfloat16)
-        for j in range(n):
-            _lib.check(lib.tdvc_pack_weight_bf16(_p(w2s[j]), _p(w2tp), C2, Cc, K, C2p, Cg, 1, n * Cg, j * Cg, C2p, 0, _st()),
-                       "pack w2^T")
-            _lib.check(lib.tdvc_pack_weight_bf16(_p(w0s[j]), _p(w0tp), Cc, Cc, K, Cg, Cg, 1, Cg, 0, n * Cg, j * Cg, _st()),
-                       "pack w0^T")
+        def pack_bwd():
+            w2tp = torch.empty(K, n * Cg, C2p, device=dev, dtype=torch.bfloat16)
+            w0tp = torch.empty(K, Cg, n * Cg, device=dev, dtype=torch.bfloat16)
+            for j in range(n):
+                _lib.check(lib.tdvc_pack_weight_bf16(_p(w2s[j]), _p(w2tp), C2, Cc, K, C2p, Cg, 1, n * Cg, j * Cg, C2p, 0, _st()),
+                           "pack w2^T")
+                _lib.check(lib.tdvc_pack_weight_bf16(_p(w0s[j]), _p(w0tp), Cc, Cc, K, Cg, Cg, 1, Cg, 0, n * Cg, j * Cg, _st()),
+                           "pack w0^T")
+            return w2tp, w0tp
+
+        w2tp, w0tp = _step_cached(("cond_bwd",), list(w0s) + list(w2s), pack_bwd)
         dg1p = torch.empty(B, T, n * Cg, device=dev, dtype=torch.bfloat16)
         _tc_conv(xp=dgbp, wp=w2tp, B=B, Tp=T, Tout=T, K=K, dilation=1, t_off=-1, Cp_total=n * C2p, groups=n, a_ch_off=0,
                  a_ch_stride=C2p, Cinp_g=C2p, Cout_g=Cg, Coutp_g=Cg, bias_stride=0, out_act=ACT_NONE, out_slope=1.0,
@@ -1001,7 +1166,7 @@ class _MRFCondPath(torch.autograd.Function):
         # cond_var.0 weight (+ bias, through the constant-one channel of cp) gradients: one GEMM for all blocks
         dw0_all = torch.empty(n * Cg, Cc + 1, K, device=dev, dtype=torch.float32)
         _lib.check(lib.tdvc_conv1d_tc_wgrad(_p(dg1p), _p(cp), _p(dw0_all), _p(ws), B, n * Cg, T, Cg, T, n * Cg, Cc + 1, K, 1,
-                                            -1, 0, 0, None, _st()), "wgrad cond_var.0")
+                                            -1, 0, 0, None, wz, _st()), "wgrad cond_var.0")
         # dL/dc: one conv over the n*Cg concatenated channels (sums the blocks' contributions in the GEMM)
         dc = None
         if ctx.needs_input_grad[0]:
@@ -1082,9 +1247,9 @@ class _FilmPosconvTC(torch.autograd.Function):
         dw = None
         if ctx.needs_input_grad[2]:
             dw = torch.empty_like(w)
-            ws = torch.empty(lib.tdvc_conv1d_tc_wgrad_ws(Cout, Cc, 1), device=dy.device, dtype=torch.float32)
+            ws, wz = _wgrad_ws(lib.tdvc_conv1d_tc_wgrad_ws(Cout, Cc, 1), dy.device)
             _lib.check(lib.tdvc_conv1d_tc_wgrad(_p(dyp), _p(a1p), _p(dw), _p(ws), B, Cdp, T, Cp, T, Cout, Cc, 1, 1, 0, 0, 0,
-                                                _p(db) if db_from_wgrad else None, _st()), "posconv_tc_wgrad")
+                                                _p(db) if db_from_wgrad else None, wz, _st()), "posconv_tc_wgrad")
         dh0 = dgb = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             Cinp16 = _ceil(Cc, 16)
