@@ -132,6 +132,14 @@ int tdvc_cin_apply_bwd(const float* dy, const float* x, const float* mean, const
 int tdvc_avgpool4s2_fwd(const float* x, float* y, int BC, int Tin, int Tout, void* stream);
 int tdvc_avgpool4s2_bwd(const float* dy, float* dx, int BC, int Tin, int Tout, void* stream);
 
+/* ---- frame view of a signal for the strided (de)convolutions whose kernel is a whole number of strides -- the
+ *      encoder's downsampling Conv1d(k=2r, stride=r) and the decoder's ConvTranspose1d(k=2r, stride=r)
+ *      (model/generator.py:214-249, 299-347) run as stride-1 convolutions over frames of s samples:
+ *      out[b, p*C + c, q] = x[b, c, s*q + p - pad] (0 outside [0,T)), q < Tq;  depth_to_space is the inverse map
+ *      y[b, c, u] = in[b, p*C + c, q], s*q + p = u + pad (0 when q >= Tq), u < Tout.  Each is the other's gradient. */
+int tdvc_space_to_depth(const float* x, float* out, int B, int C, int T, int s, int pad, int Tq, void* stream);
+int tdvc_depth_to_space(const float* in, float* y, int B, int C, int Tq, int s, int pad, int Tout, void* stream);
+
 /* ---- x.gather(1, label) (model/discriminator.py:49-51): y[b,0,t] = x[b,label[b],t] */
 int tdvc_select_channel_fwd(const float* x, const int64_t* label, float* y, int B, int C, int T, void* stream);
 int tdvc_select_channel_bwd(const float* dy, const int64_t* label, float* dx /*zero-filled here*/,

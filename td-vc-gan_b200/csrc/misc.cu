@@ -158,6 +158,50 @@ __global__ void adamw_multi_k(float* const* __restrict__ params, const float* co
 __global__ void step_inc_k(float* step) {
   pdl_prologue(); *step += 1.f; }
 
+
+// ------------------------------------------------------------------------------------------ space <-> depth
+// A dense strided convolution whose kernel is a whole number of strides (the encoder's k = 2r, stride r downsamplers and,
+// transposed, the decoder's upsamplers: generator.py:214-249, 299-347) is a stride-1 convolution on the input viewed
+// as frames of `s` samples: xs[b, p*C + c, q] = x[b, c, s*q + p - pad] (zero outside [0, T)).  These two kernels are the
+// frame view and its inverse (each is the other's gradient); the convolution itself then runs on the tcgen05 path.
+constexpr int S2D_TT = 128;     // frames per block
+constexpr int S2D_MAX_S = 16;
+
+__global__ void __launch_bounds__(128) s2d_k(const float* __restrict__ x, float* __restrict__ out, int C, int T, int s, int pad,
+                                             int Tq) {
+  pdl_prologue();
+  __shared__ float sm[S2D_MAX_S * S2D_TT];
+  const int b = blockIdx.z, c = blockIdx.y, q0 = blockIdx.x * S2D_TT;
+  const float* xr = x + ((long long)b * C + c) * T;
+  const int u0 = s * q0 - pad, n = s * min(S2D_TT, Tq - q0);
+  for (int i = threadIdx.x; i < n; i += 128) {
+    const int u = u0 + i;
+    sm[i] = (u >= 0 && u < T) ? __ldg(xr + u) : 0.f;
+  }
+  __syncthreads();
+  const int q = q0 + threadIdx.x;
+  if (q < Tq)
+    for (int p = 0; p < s; ++p) out[((long long)b * s * C + (long long)p * C + c) * Tq + q] = sm[s * threadIdx.x + p];
+}
+
+// y[b, c, u] = in[b, p*C + c, q] with s*q + p = u + pad (zero when q >= Tq)
+__global__ void __launch_bounds__(128) d2s_k(const float* __restrict__ in, float* __restrict__ y, int C, int Tq, int s, int pad,
+                                             int Tout) {
+  pdl_prologue();
+  __shared__ float sm[S2D_MAX_S * S2D_TT];
+  const int b = blockIdx.z, c = blockIdx.y, q0 = blockIdx.x * S2D_TT;
+  const int q = q0 + threadIdx.x;
+  for (int p = 0; p < s; ++p)
+    sm[s * threadIdx.x + p] = (q < Tq) ? __ldg(in + ((long long)b * s * C + (long long)p * C + c) * Tq + q) : 0.f;
+  __syncthreads();
+  float* yr = y + ((long long)b * C + c) * Tout;
+  const int u0 = s * q0 - pad;
+  for (int i = threadIdx.x; i < s * S2D_TT; i += 128) {
+    const int u = u0 + i;
+    if (u >= 0 && u < Tout) yr[u] = sm[i];
+  }
+}
+
 }  // namespace tdvc
 using namespace tdvc;
 
@@ -255,6 +299,24 @@ extern "C" int tdvc_adamw_multi(float* const* params, const float* const* grads,
   tdvc::launch_k(adamw_multi_k, n_tensors * chunks, 256, 0, (cudaStream_t)stream, params, grads, exp_avg, exp_avg_sq, sizes, chunks,
                                                                       lr, beta1, beta2, eps, weight_decay, bc1,
                                                                       sqrtf(bc2), grad_scale, step_dev);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_space_to_depth(const float* x, float* out, int B, int C, int T, int s, int pad, int Tq, void* stream) {
+  TDVC_CHECK_ARG(x && out && B >= 0 && C > 0 && T > 0 && s >= 1 && s <= S2D_MAX_S && pad >= 0 && Tq > 0 && C <= 65535 && B <= 65535);
+  if (B == 0) return TDVC_OK;
+  tdvc::launch_k(s2d_k, dim3(cdiv(Tq, S2D_TT), C, B), 128, 0, (cudaStream_t)stream, x, out, C, T, s, pad, Tq);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_depth_to_space(const float* in, float* y, int B, int C, int Tq, int s, int pad, int Tout, void* stream) {
+  TDVC_CHECK_ARG(in && y && B >= 0 && C > 0 && Tq > 0 && s >= 1 && s <= S2D_MAX_S && pad >= 0 && Tout > 0 && C <= 65535 && B <= 65535);
+  if (B == 0) return TDVC_OK;
+  // every output sample must be covered by a block: frames up to (Tout - 1 + pad) / s
+  const int frames = std::max(Tq, (Tout - 1 + pad) / s + 1);
+  tdvc::launch_k(d2s_k, dim3(cdiv(frames, S2D_TT), C, B), 128, 0, (cudaStream_t)stream, in, y, C, Tq, s, pad, Tout);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }

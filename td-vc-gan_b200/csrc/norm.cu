@@ -45,8 +45,12 @@ __global__ void wn_fwd_multi_k(const long long* __restrict__ table, const int* _
   const int cols = (int)e[3];
   const int r = gr - __ldg(row_start + lo);
   const float* vr = v + (long long)r * cols;
+  // the partial sums are formed exactly as wn_fwd_k forms them for this row length (32 / 128 / 256 participating threads;
+  // the others add zeros), so the batched and the per-weight launch give bit-identical weights
+  const int nthr = cols >= 1024 ? 256 : (cols >= 128 ? 128 : 32);
   float s = 0.f;
-  for (int i = threadIdx.x; i < cols; i += blockDim.x) { float a = vr[i]; s = fmaf(a, a, s); }
+  if ((int)threadIdx.x < nthr)
+    for (int i = threadIdx.x; i < cols; i += nthr) { float a = vr[i]; s = fmaf(a, a, s); }
   s = block_sum(s, sm);
   float inv = rsqrtf(s);
   inv = inv * (1.5f - 0.5f * s * inv * inv);
@@ -179,7 +183,7 @@ extern "C" int tdvc_weight_norm_fwd(const float* v, const float* g, float* w, fl
 extern "C" int tdvc_weight_norm_fwd_multi(const void* table, const void* row_start, int n_weights, int total_rows,
                                           float* flat_w, float* flat_inv, void* stream) {
   TDVC_CHECK_ARG(table && row_start && n_weights > 0 && total_rows > 0 && flat_w && flat_inv);
-  tdvc::launch_k(wn_fwd_multi_k, total_rows, 128, 0, (cudaStream_t)stream, (const long long*)table, (const int*)row_start,
+  tdvc::launch_k(wn_fwd_multi_k, total_rows, 256, 0, (cudaStream_t)stream, (const long long*)table, (const int*)row_start,
                  n_weights, flat_w, flat_inv);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;

@@ -85,6 +85,8 @@ SIGNATURES = {
     "tdvc_conv1d_tc_wgrad_ws": (_L, [_I, _I, _I]),
     "tdvc_conv1d_tc_wgrad": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P]),
     "tdvc_pack_weight_bf16_multi": (_I, [_P, _I, _I, _P, _P, _P]),
+    "tdvc_space_to_depth": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "tdvc_depth_to_space": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "tdvc_conv1d_tc_fwd_ex": (_I, [C.POINTER(TcConv), _P]),
     "tdvc_conv1d_tc_fwd_stacked": (_I, [_P, _P, _P, _P] + [_I] * 12 + [_I, _F] + [_I] * 5 + [_P]),
     "tdvc_conv1d_tc_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P]),

@@ -219,7 +219,9 @@ class _StepCache:
             jobs += [w_off[idx], poff, Cout, Cin, K, rows_p, cols_p, int(flip)]
             p_off.append(poff)
             poff += al(K * rows_p * cols_p, 64)
+        max_job = max([jobs[8 * i + 4] * jobs[8 * i + 5] * jobs[8 * i + 6] for i in range(len(jobs) // 8)] or [1])
         t = dict(sig=tuple(tab[0::4]) + tuple(tab[1::4]), dev=dev, n=len(live), total_rows=r, w_elems=off, p_elems=poff,
+                 blocks_per_job=max(1, min(256, -(-max_job // (256 * 16)))),      # <= 16 outputs per thread in the largest job
                  w_off=w_off, row_start=rows, p_off=p_off,
                  table=torch.tensor(tab, dtype=torch.int64).to(dev), rows_dev=torch.tensor(rows, dtype=torch.int32).to(dev),
                  jobs=torch.tensor(jobs, dtype=torch.int64).to(dev) if jobs else None)
@@ -255,7 +257,8 @@ class _StepCache:
             ws.append(w)
         if t["jobs"] is not None:
             flat_wp = torch.empty(t["p_elems"], device=dev, dtype=torch.bfloat16)
-            _lib.check(lib.tdvc_pack_weight_bf16_multi(_p(t["jobs"]), len(self.plan_p), 8, _p(flat_w), _p(flat_wp), _st()),
+            _lib.check(lib.tdvc_pack_weight_bf16_multi(_p(t["jobs"]), len(self.plan_p), t["blocks_per_job"], _p(flat_w),
+                                                       _p(flat_wp), _st()),
                        "pack_weight_bf16_multi")
             for i, (idx, rows_p, cols_p, flip) in enumerate(self.plan_p):
                 K = live[idx][0].shape[2]
@@ -344,6 +347,11 @@ def conv1d(x, weight, bias=None, *, stride=1, padding=0, dilation=1, groups=1, r
            in_slope=1.0, out_act=None, out_slope=0.2, residual=None):
     """act(conv1d(leaky_relu(pad(x), in_slope), weight) + bias + residual); nn.Conv1d semantics
     (padding_mode 'zeros' or 'reflect')."""
+    if (_frame_conv_eligible(x.shape[1], weight.shape[0], weight.shape[2], int(stride), int(groups), int(dilation),
+                             bool(reflect and padding > 0))
+            and residual is None and tc_eligible(int(stride) * x.shape[1], weight.shape[0], 1, 1)
+            and x.shape[2] + 2 * int(padding) >= weight.shape[2]):
+        return _strided_conv_as_frames(x, weight, bias, int(stride), int(padding), in_slope, out_act, out_slope)
     if _PRECISION == "bf16" and tc_eligible(x.shape[1], weight.shape[0], int(stride), int(groups)):
         return _Conv1dTC.apply(x, weight, bias, residual, int(padding), int(dilation),
                                PAD_REFLECT if (reflect and padding > 0) else PAD_ZEROS, float(in_slope), _ACT[out_act],
@@ -401,6 +409,9 @@ class _ConvTranspose1d(torch.autograd.Function):
 
 
 def conv_transpose1d(x, weight, bias=None, *, stride=1, padding=0, output_padding=0):
+    if (_frame_conv_eligible(weight.shape[0], weight.shape[1], weight.shape[2], int(stride), 1, 1, False)
+            and int(output_padding) == 0 and tc_eligible(weight.shape[0], int(stride) * weight.shape[1], 1, 1)):
+        return _conv_transpose_as_frames(x, weight, bias, int(stride), int(padding))
     return _ConvTranspose1d.apply(x, weight, bias, int(stride), int(padding), int(output_padding))
 
 
@@ -1043,6 +1054,93 @@ def _step_cached(tag, tensors, make):
         hit = (list(tensors), make())
         _step_cache.wp[key] = hit
     return hit[1]
+
+
+# ----------------------------------------------------------------------------- strided convs as frame convolutions
+
+class _SpaceToDepth(torch.autograd.Function):
+    """xs[b, p*C + c, q] = x[b, c, s*q + p - pad] (zero outside the signal), q < Tq."""
+
+    @staticmethod
+    def forward(ctx, x, s, pad, Tq):
+        _req(x)
+        x = _c(x)
+        B, Cc, T = x.shape
+        out = torch.empty(B, s * Cc, Tq, device=x.device, dtype=torch.float32)
+        _lib.check(_lib.load().tdvc_space_to_depth(_p(x), _p(out), B, Cc, T, s, pad, Tq, _st()), "space_to_depth")
+        ctx.dims = (B, Cc, T, s, pad, Tq)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, Cc, T, s, pad, Tq = ctx.dims
+        dout = _c(dout)
+        dx = torch.empty(B, Cc, T, device=dout.device, dtype=torch.float32)
+        _lib.check(_lib.load().tdvc_depth_to_space(_p(dout), _p(dx), B, Cc, Tq, s, pad, T, _st()), "space_to_depth_bwd")
+        return dx, None, None, None
+
+
+class _DepthToSpace(torch.autograd.Function):
+    """y[b, c, u] = ys[b, p*C + c, q] with s*q + p = u + pad, u < Tout."""
+
+    @staticmethod
+    def forward(ctx, ys, s, pad, Tout):
+        _req(ys)
+        ys = _c(ys)
+        B, sC, Tq = ys.shape
+        Cc = sC // s
+        y = torch.empty(B, Cc, Tout, device=ys.device, dtype=torch.float32)
+        _lib.check(_lib.load().tdvc_depth_to_space(_p(ys), _p(y), B, Cc, Tq, s, pad, Tout, _st()), "depth_to_space")
+        ctx.dims = (B, Cc, Tq, s, pad, Tout)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, Cc, Tq, s, pad, Tout = ctx.dims
+        dy = _c(dy)
+        dys = torch.empty(B, s * Cc, Tq, device=dy.device, dtype=torch.float32)
+        _lib.check(_lib.load().tdvc_space_to_depth(_p(dy), _p(dys), B, Cc, Tout, s, pad, Tq, _st()), "depth_to_space_bwd")
+        return dys, None, None, None
+
+
+def _frame_conv_eligible(Cin, Cout, K, stride, groups, dilation, reflect) -> bool:
+    return (_PRECISION == "bf16" and _FRAME_CONV and 1 < stride <= 16 and groups == 1 and dilation == 1 and not reflect
+            and K % stride == 0 and K > stride)
+
+
+_FRAME_CONV = os.environ.get("TDVC_FRAME_CONV", "1") != "0"     # development switch: 0 = fp32 CUDA-core strided kernels
+
+
+def _strided_conv_as_frames(x, weight, bias, stride, padding, in_slope, out_act, out_slope):
+    """Conv1d(k = m*s, stride = s, zero padding) = stride-1 conv with m taps over frames of s samples:
+    y[t] = sum_j sum_(p,ci) xs[(p,ci), t + j] * w[co, ci, s*j + p].  The frame view costs one pass over x; the
+    convolution (forward, data and weight gradients) then runs on the tcgen05 path instead of the fp32 kernels."""
+    Cout, Cin, K = weight.shape
+    s, m = stride, K // stride
+    Tq = (x.shape[2] + 2 * padding) // s
+    xs = _SpaceToDepth.apply(x, s, padding, Tq)
+    w2 = _step_cached(("frames_w", s, torch.is_grad_enabled()), [weight],
+                      lambda: weight.view(Cout, Cin, m, s).permute(0, 3, 1, 2).reshape(Cout, s * Cin, m))
+    return _Conv1dTC.apply(xs, w2, bias, None, 0, 1, PAD_ZEROS, float(in_slope), _ACT[out_act], float(out_slope))
+
+
+def _conv_transpose_as_frames(x, weight, bias, stride, padding):
+    """ConvTranspose1d(k = m*s, stride = s): with u + pad = s*q + p, y[co, u] = sum_j sum_ci x[ci, q - j] * w[ci, co, s*j + p],
+    i.e. a stride-1 conv (m taps, padding m-1, taps reversed) producing s*Cout channels (p, co) per frame, then the
+    inverse frame view."""
+    Cin, Cout, K = weight.shape
+    s, m = stride, K // stride
+    Tout = (x.shape[2] - 1) * s - 2 * padding + K
+
+    def make():
+        w2 = weight.view(Cin, Cout, m, s).flip(2).permute(3, 1, 0, 2).reshape(s * Cout, Cin, m)
+        b2 = bias.repeat(s) if bias is not None else None
+        return w2, b2
+
+    w2, b2 = _step_cached(("frames_wt", s, torch.is_grad_enabled()), [weight, bias], make)
+    yq = _Conv1dTC.apply(x, w2, b2, None, m - 1, 1, PAD_ZEROS, 1.0, ACT_NONE, 1.0)
+    return _DepthToSpace.apply(yq, s, padding, Tout)
+
 
 
 class _MRFCondPath(torch.autograd.Function):

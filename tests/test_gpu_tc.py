@@ -343,3 +343,59 @@ def test_conv1d_tc_stacked_weights_in_tmem():
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", __file__, "-k", "test_conv1d_tc_stacked and not tmem"],
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+FRAME_CASES = [
+    # B, Cin, T, Cout, K, stride, pad     (the generator's down/up-sampling geometries, generator.py:214-249, 299-347)
+    (2, 128, 280, 256, 20, 10, 5),
+    (2, 64, 2240, 128, 16, 8, 4),
+    (2, 32, 448, 64, 4, 2, 1),
+    (3, 16, 301, 32, 4, 2, 1),          # (T + 2 pad) not a multiple of the stride: the incomplete last frame is unused
+    (2, 24, 100, 48, 9, 3, 4),          # three taps per frame
+]
+
+
+@pytest.mark.parametrize("case", FRAME_CASES, ids=[str(i) for i in range(len(FRAME_CASES))])
+def test_strided_conv_as_frames(case):
+    """Conv1d(k = m*stride) in bf16 mode = frame view + stride-1 tcgen05 conv; against fp64 PyTorch, 1e-2."""
+    from tdvc import ops
+    B, Cin, T, Cout, K, s, p = case
+    x = rnd(B, Cin, T, seed=1).requires_grad_(True)
+    w = rnd(Cout, Cin, K, seed=2, scale=(Cin * K) ** -0.5).requires_grad_(True)
+    b = rnd(Cout, seed=3, scale=0.1).requires_grad_(True)
+    ref = F.conv1d(F.leaky_relu(x, 0.2), w, b, stride=s, padding=p)
+    proj = rnd(*ref.shape, seed=5)
+    (ref * proj).sum().backward()
+    xd, wd, bd = dev(x), dev(w), dev(b)
+    assert ops._frame_conv_eligible(Cin, Cout, K, s, 1, 1, False)
+    y = ops.conv1d(xd, wd, bd, stride=s, padding=p, in_slope=0.2)
+    assert y.shape == ref.shape
+    assert relerr(y, ref) < 1e-2
+    (y * proj.float().cuda()).sum().backward()
+    torch.cuda.synchronize()
+    assert relerr(xd.grad, x.grad) < 1e-2
+    assert relerr(wd.grad, w.grad) < 1e-2
+    assert relerr(bd.grad, b.grad) < 1e-2
+
+
+@pytest.mark.parametrize("case", FRAME_CASES, ids=[str(i) for i in range(len(FRAME_CASES))])
+def test_conv_transpose_as_frames(case):
+    """ConvTranspose1d(k = m*stride) in bf16 mode = stride-1 tcgen05 conv to (phase, channel) frames + inverse frame view."""
+    from tdvc import ops
+    B, Cout, T, Cin, K, s, p = case                  # transposed: the wide side is the input
+    T = max(T // s, 5)
+    x = rnd(B, Cin, T, seed=1).requires_grad_(True)
+    w = rnd(Cin, Cout, K, seed=2, scale=(Cin * K / s) ** -0.5).requires_grad_(True)
+    b = rnd(Cout, seed=3, scale=0.1).requires_grad_(True)
+    ref = F.conv_transpose1d(x, w, b, stride=s, padding=p)
+    proj = rnd(*ref.shape, seed=5)
+    (ref * proj).sum().backward()
+    xd, wd, bd = dev(x), dev(w), dev(b)
+    y = ops.conv_transpose1d(xd, wd, bd, stride=s, padding=p)
+    assert y.shape == ref.shape
+    assert relerr(y, ref) < 1e-2
+    (y * proj.float().cuda()).sum().backward()
+    torch.cuda.synchronize()
+    assert relerr(xd.grad, x.grad) < 1e-2
+    assert relerr(wd.grad, w.grad) < 1e-2
+    assert relerr(bd.grad, b.grad) < 1e-2
