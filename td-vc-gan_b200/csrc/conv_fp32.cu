@@ -23,6 +23,8 @@ struct FwdP {
   int w_flip;
   int ci_chunk, span;
   int seg, span_p;   // strided convs keep the input tile de-interleaved by phase: element i -> (i % stride) * seg + i / stride
+  int gpb;           // groups per CTA: with few output channels per group (the discriminators' 4-in/4-out groups) a CTA's
+                     // channel rows span gpb consecutive groups instead of leaving most of its threads idle
 };
 
 __device__ __forceinline__ float fetch_padded(const float* __restrict__ row, int gt, int T, int pad_mode,
@@ -70,14 +72,16 @@ __global__ void __launch_bounds__(256) conv_fwd_k(FwdP p, const float* __restric
   constexpr int TY = 256 / TX, TT = TX * 4, COB = TY * CO_T;
   extern __shared__ float sm[];
   float* xs = sm;
-  float* ws = sm + (((size_t)p.ci_chunk * p.span_p + 3) & ~(size_t)3);
+  float* ws = sm + (((size_t)p.gpb * p.ci_chunk * p.span_p + 3) & ~(size_t)3);
   constexpr int WPITCH_K = (CO_T % 4 == 0) ? COB : COB + 1;
   int* kofs = reinterpret_cast<int*>(ws + (size_t)p.ci_chunk * p.K * WPITCH_K);   // [K] tile offset of tap k
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   const int t0 = blockIdx.x * TT;
   const int tiles_per_group = (p.cout_g + COB - 1) / COB;
-  const int grp = blockIdx.y / tiles_per_group;
-  const int co0 = (blockIdx.y % tiles_per_group) * COB;
+  const int grp = p.gpb > 1 ? blockIdx.y * p.gpb : blockIdx.y / tiles_per_group;     // first group of this CTA
+  const int co0 = p.gpb > 1 ? 0 : (blockIdx.y % tiles_per_group) * COB;
+  const int co_lim = p.gpb > 1 ? min(p.gpb, p.groups - grp) * p.cout_g : p.cout_g;   // channels (from grp's first) this CTA may own
+  const int g_local = p.gpb > 1 ? (ty * CO_T) / p.cout_g : 0;                        // this thread's group inside the bundle
   const int b = blockIdx.z;
   float acc[CO_T][4];
 #pragma unroll
@@ -86,7 +90,8 @@ __global__ void __launch_bounds__(256) conv_fwd_k(FwdP p, const float* __restric
     for (int j = 0; j < 4; ++j) acc[c][j] = 0.f;
   const float* xb = x + ((long long)b * p.Cin + (long long)grp * p.cin_g) * p.Tin;
   const int gt0 = t0 * p.stride - p.pad;
-  const bool row_active = (co0 + ty * CO_T) < p.cout_g;
+  const bool row_active = (co0 + ty * CO_T) < co_lim;
+  const int x_groups = p.gpb > 1 ? min(p.gpb, p.groups - grp) : 1;                   // input-channel groups in the tile
   // With the tile stored phase-major, output step (tx + j*TX) and tap k read word  kofs[k] + tx + j*TX : consecutive
   // lanes hit consecutive banks for any stride (a plain layout gives stride-way bank conflicts).
   for (int k = threadIdx.x; k < p.K; k += 256) {
@@ -97,7 +102,8 @@ __global__ void __launch_bounds__(256) conv_fwd_k(FwdP p, const float* __restric
   for (int c0 = 0; c0 < p.cin_g; c0 += p.ci_chunk) {
     const int nci = min(p.ci_chunk, p.cin_g - c0);
     __syncthreads();
-    for (int idx = threadIdx.x; idx < nci * p.span; idx += 256) {
+    // bundled groups (gpb > 1, then ci_chunk == cin_g): the tile holds the x_groups * cin_g input channels of the bundle
+    for (int idx = threadIdx.x; idx < x_groups * nci * p.span; idx += 256) {
       int ci = idx / p.span, i = idx - ci * p.span;
       float v = fetch_padded(xb + (long long)(c0 + ci) * p.Tin, gt0 + i, p.Tin, p.pad_mode, p.in_slope);
       int pos = (p.stride == 1) ? i : (i % p.stride) * p.seg + i / p.stride;
@@ -108,7 +114,7 @@ __global__ void __launch_bounds__(256) conv_fwd_k(FwdP p, const float* __restric
       int co = idx / nwk, r = idx - co * nwk;
       int ci = r / p.K, k = r - ci * p.K;
       float v = 0.f;
-      if (co0 + co < p.cout_g) {
+      if (co0 + co < co_lim) {
         int kk = p.w_flip ? p.K - 1 - k : k;
         v = __ldg(w + (long long)(grp * p.cout_g + co0 + co) * p.w_sco + (long long)(c0 + ci) * p.w_sci +
                   (long long)kk * p.w_sk);
@@ -118,7 +124,7 @@ __global__ void __launch_bounds__(256) conv_fwd_k(FwdP p, const float* __restric
     __syncthreads();
     if (row_active) {
       for (int ci = 0; ci < nci; ++ci) {
-        const float* xr = xs + ci * p.span_p + tx;
+        const float* xr = xs + (g_local * p.cin_g + ci) * p.span_p + tx;
         for (int k = 0; k < p.K; ++k) {
           const float* xk = xr + kofs[k];
           float xv0 = xk[0], xv1 = xk[TX], xv2 = xk[2 * TX], xv3 = xk[3 * TX];
@@ -149,7 +155,7 @@ __global__ void __launch_bounds__(256) conv_fwd_k(FwdP p, const float* __restric
 #pragma unroll
   for (int c = 0; c < CO_T; ++c) {
     int co = co0 + ty * CO_T + c;
-    if (co >= p.cout_g) break;
+    if (co >= co_lim) break;
     int cog = grp * p.cout_g + co;
     float bv = bias ? __ldg(bias + cog) : 0.f;
     long long base = ((long long)b * p.Cout + cog) * p.Tout;
@@ -182,13 +188,20 @@ static int launch_fwd_t(FwdP p, const float* x, const float* w, const float* bia
   if (chunk > 32) chunk = 32;
   p.ci_chunk = chunk;
   size_t smem = per_ci * chunk + extra;
+  // several groups per CTA when a group has fewer output channels than the CTA has channel rows
+  p.gpb = 1;
+  if (p.groups > 1 && p.cout_g < COB && COB % p.cout_g == 0 && p.cout_g % CO_T == 0 && chunk == p.cin_g) {
+    const int gpb = std::min(COB / p.cout_g, p.groups);
+    const size_t smem_b = ((size_t)gpb * p.cin_g * p.span_p + 4 + (size_t)p.cin_g * p.K * WPITCH) * sizeof(float) + extra;
+    if (gpb > 1 && smem_b <= budget) { p.gpb = gpb; smem = smem_b; }
+  }
   TDVC_CHECK_ARG(smem <= 200 * 1024);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     TDVC_CUDA(cudaFuncSetAttribute(conv_fwd_k<CO_T, TX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = 200 * 1024;
   }
-  dim3 grid(cdiv(p.Tout, TT), p.groups * cdiv(p.cout_g, COB), p.B);
+  dim3 grid(cdiv(p.Tout, TT), p.gpb > 1 ? cdiv(p.groups, p.gpb) : p.groups * cdiv(p.cout_g, COB), p.B);
   TDVC_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535);
   tdvc::launch_k(conv_fwd_k<CO_T, TX>, grid, 256, smem, st, p, x, w, bias, res, y);
   TDVC_LAUNCH_CHECK();
