@@ -832,7 +832,7 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) conv_tc_wt_k(const __grid_c
     // vec epilogue: the warp's 32 channels x 16 steps go through a 1 KB shared-memory tile so that the global stores are
     // 16 bytes per lane (8 consecutive channels of one time step) instead of 2: lane -> (time row lane/4 (+8), chunk lane%4)
     __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(stage_out + (size_t)(warp - 2) * WT_STG_BYTES);
-    const int k8 = lane & 3, row8 = lane >> 2;
+    const int k8 = lane & 3;
     const int rk = r0 + q * 32 + 8 * k8;                      // first stacked row of this lane's 8-channel chunk
     const bool rk_ok = rk < w.rows_total;
     const int blk_k = rk / w.rows_per_block, ch_k = rk - blk_k * w.rows_per_block;
@@ -848,29 +848,48 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) conv_tc_wt_k(const __grid_c
         const uint32_t taddr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * CQ);
         const int t_left = p.Tout - (t0 + cq * CQ);           // valid time steps from this warp's first column
         if (w.vec) {
-          __nv_bfloat16* op = p.yp + ((long long)b * p.tp_out + t0 + cq * CQ + p.out_halo + row8) * row_pitch + col_k;
+          // Staging tile [8 step pairs][32 channels] of 32-bit words: a lane stores its channel's (t, t+1) pair as one
+          // word (conflict-free, 8 stores per 16 steps); lane (m = lane / 4, k = lane % 4) then reads the 8 words of
+          // pair m, channels 8k..8k+7 and splits them into the two output rows t = 2m, 2m + 1 (16 bytes each).
+          // Odd m read their two 16-byte halves in the opposite order, which keeps the quarter-warp phases on 32 banks.
+          uint32_t* stg32 = reinterpret_cast<uint32_t*>(stg);
+          const int m = lane >> 2;
+          const int first = (m & 1) ? 4 : 0;
+          // TDVC_TC_DEBUG & 128 (development): all tiles write the same few rows -- same store instructions, no DRAM stream
+          const long long row0 = (p.debug & 128) ? (long long)(((j / w.ctas_per_m) & 1) * BN + cq * CQ + 2 * m)
+                                                 : ((long long)b * p.tp_out + t0 + cq * CQ + p.out_halo + 2 * m);
+          __nv_bfloat16* op = p.yp + row0 * row_pitch + col_k;
 #pragma unroll 1
           for (int cc = 0; cc < NG; ++cc) {
             float v[16];
             tmem_ld16(taddr + (uint32_t)(cc * 16), v);
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              float o = v[e] + bias_v;
-              if (ACT == TDVC_ACT_LRELU) o = fmaxf(o, o * sl);
-              stg[e * 32 + lane] = __float2bfloat16(o);
+            for (int e = 0; e < 8; ++e) {
+              float o0 = v[2 * e] + bias_v, o1 = v[2 * e + 1] + bias_v;
+              if (ACT == TDVC_ACT_LRELU) { o0 = fmaxf(o0, o0 * sl); o1 = fmaxf(o1, o1 * sl); }
+              const __nv_bfloat162 pr = __floats2bfloat162_rn(o0, o1);
+              stg32[e * 32 + lane] = *reinterpret_cast<const uint32_t*>(&pr);
             }
             __syncwarp();
+            const uint4 qa = *reinterpret_cast<const uint4*>(stg32 + m * 32 + 8 * k8 + first);
+            const uint4 qb = *reinterpret_cast<const uint4*>(stg32 + m * 32 + 8 * k8 + (4 - first));
+            const uint4 lo4 = first ? qb : qa, hi4 = first ? qa : qb;      // words of channels 8k..8k+3 / 8k+4..8k+7
+            const uint4 r0 = make_uint4(__byte_perm(lo4.x, lo4.y, 0x5410), __byte_perm(lo4.z, lo4.w, 0x5410),
+                                        __byte_perm(hi4.x, hi4.y, 0x5410), __byte_perm(hi4.z, hi4.w, 0x5410));   // step 2m
+            const uint4 r1 = make_uint4(__byte_perm(lo4.x, lo4.y, 0x7632), __byte_perm(lo4.z, lo4.w, 0x7632),
+                                        __byte_perm(hi4.x, hi4.y, 0x7632), __byte_perm(hi4.z, hi4.w, 0x7632));   // step 2m + 1
+            if (rk_ok && !(p.debug & 1)) {
+              __nv_bfloat16* o8 = op + (long long)(cc * 16) * row_pitch;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int row = row8 + 8 * h;
-              const uint4 val = *reinterpret_cast<const uint4*>(stg + row * 32 + 8 * k8);
-              if (rk_ok && cc * 16 + row < t_left && !(p.debug & 1)) {
-                __nv_bfloat16* o8 = op + (long long)(cc * 16 + 8 * h) * row_pitch;
-                *reinterpret_cast<uint4*>(o8) = val;
-                if (npad_k) {
-                  if (npad_k == 8) *reinterpret_cast<uint4*>(o8 + 8) = make_uint4(0u, 0u, 0u, 0u);
-                  else for (int z = 0; z < npad_k; ++z) o8[8 + z] = __float2bfloat16(0.f);
+              for (int h = 0; h < 2; ++h) {
+                if (cc * 16 + 2 * m + h < t_left) {
+                  *reinterpret_cast<uint4*>(o8) = h ? r1 : r0;
+                  if (npad_k) {
+                    if (npad_k == 8) *reinterpret_cast<uint4*>(o8 + 8) = make_uint4(0u, 0u, 0u, 0u);
+                    else for (int z = 0; z < npad_k; ++z) o8[8 + z] = __float2bfloat16(0.f);
+                  }
                 }
+                o8 += row_pitch;
               }
             }
             __syncwarp();
@@ -1408,7 +1427,9 @@ extern "C" int tdvc_conv1d_tc_fwd_ex(const tdvc_tc_conv* c, void* stream) {
     ctas = std::min(ctas, n_mtiles);
     const int n_stages = narrow ? 3 : 0;
     const long long fixed = w_bytes + n_stages * an_stage;
-    if (ws_on && rows_a <= 256 && fixed + 2 * a_stage <= budget && (n_mtiles >= 4 * ctas || ws_on == 2) && 2 * p.BN <= 512) {   // TDVC_TC_WS=2 forces it (tests)
+    static int min_tiles = -1;     // TDVC_TC_WS_MIN_TILES: time tiles per CTA from which the persistent kernel is used
+    if (min_tiles < 0) { const char* e = getenv("TDVC_TC_WS_MIN_TILES"); min_tiles = e ? std::max(1, atoi(e)) : 4; }
+    if (ws_on && rows_a <= 256 && fixed + 2 * a_stage <= budget && (n_mtiles >= min_tiles * ctas || ws_on == 2) && 2 * p.BN <= 512) {   // TDVC_TC_WS=2 forces it (tests)
       WsP w{};
       w.n_mtiles = n_mtiles; w.mtiles_per_b = mtiles_per_b; w.rows_a = rows_a; w.a_stage_bytes = (int)a_stage;
       w.w_tile_bytes = (int)w_tile; w.narrow = narrow ? 1 : 0; w.n_full = n_full; w.an_stage_bytes = (int)an_stage;

@@ -38,6 +38,7 @@ CONV_CASES = [
     (2, 1, 600, 16, 15, 1, 7, 1, 1, True, 1.0, "lrelu", True, False),     # D layer 0
     (2, 16, 600, 64, 41, 4, 20, 1, 4, False, 1.0, "lrelu", True, False),  # D grouped (4->16)
     (2, 64, 150, 64, 41, 4, 20, 1, 16, False, 1.0, "lrelu", True, False), # D grouped (4->4)
+    (2, 40, 150, 40, 41, 4, 20, 1, 10, False, 1.0, "lrelu", True, False), # 10 groups of 4->4: 8 + 2 groups per CTA bundle
     (2, 64, 35, 64, 5, 1, 2, 1, 1, False, 1.0, "lrelu", True, False),     # D dense k5, short T
     (2, 64, 9, 100, 3, 1, 1, 1, 1, False, 1.0, None, False, False),       # D output, no bias
     (2, 8, 640, 8, 33, 2, 16, 1, 8, False, 1.0, None, False, False),      # depthwise Kaiser r=2
