@@ -1,19 +1,23 @@
-// bf16 tensor-core path for the dense stride-1 convolutions (FiLM cond_var.0 / cond_var.2, conv.1,
-// posconv, the discriminator's 1024x1024 k5 layer and their data gradients): implicit GEMM on
-// tcgen05.mma with the accumulator in TMEM and both operands brought in by TMA.
+// bf16 tensor-core path for the dense convolutions (FiLM cond_var.0 / cond_var.2, conv.1, posconv, the
+// discriminator's 1024x1024 k5 layer, the frame-view strided / transposed convs, and all their data and weight
+// gradients): implicit GEMM on tcgen05.mma with the accumulator in TMEM and both operands brought in by TMA.
 //
+// Time-as-M kernels (conv_tc_fwd_k: one tile per CTA; conv_tc_ws_k: weight-stationary, persistent):
 //   D[t, co] = sum_{tap} sum_{ci} A_tap[t, ci] * W_tap[co, ci]
 //     A_tap = rows (t0 + tap*dilation + t_off ...) of the channels-last bf16 activation copy xp[B, Tp, Cp]
-//             -> one 3-D TMA box {64 ch, 128 t, 1 b} per (tap, 64-channel chunk), K-major, SWIZZLE_128B;
+//             -> 3-D TMA boxes {64 ch, 128 t (+ halo), 1 b} per 64-channel chunk, K-major, SWIZZLE_128B;
 //                the conv's zero padding is TMA out-of-bounds fill, reflect padding is materialised by
 //                the pack kernel in the halo rows.
 //     W_tap = wp[tap, co, ci] bf16 -> box {64 ch, BN co, 1 tap}, K-major, SWIZZLE_128B.
 //   M = 128 time steps (TMEM lanes), N = BN <= 256 output channels (TMEM columns), K = 16 per MMA.
+// Weights-as-M kernel (conv_tc_wt_k): the same sum with the roles swapped, M = 128 stacked output channels,
+//   N = 256 time steps -- see the comment above it.
+// Weight gradient (conv_tc_wgrad_k): M = ci, N = co, K = time, both operands MN-major views of the same packed tensors.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..5 = epilogue (tcgen05.ld -> bias / FiLM / residual / activation -> coalesced NCW fp32 stores:
-// a TMEM lane is a time step, so for a fixed channel a warp writes 32 consecutive floats).
-// One output tile per CTA; several CTAs per SM overlap one tile's epilogue with another's main loop.
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one lane chosen by elect.sync),
+// the remaining warps (16 in the forward kernels, 4 in wgrad) = epilogue: tcgen05.ld -> bias / FiLM / residual /
+// activation / LeakyReLU mask -> NCW fp32 stores (a TMEM lane is a time step: for a fixed channel a warp writes 32
+// consecutive floats) or the next conv's packed bf16 operand.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <algorithm>
