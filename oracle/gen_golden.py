@@ -311,9 +311,31 @@ def case_step(name, cfg, hp):
     save(name, **out)
 
 
+def case_host_utils(name):
+    """Host-side helpers of the path's callers: util.f0_to_excitation (util/__init__.py:22-50; consumes the
+    global torch RNG: start phase, noise, unvoiced noise -- so the seed is part of the fixture) and the Kaiser filters
+    (util/dsp.py:5-16, util/__init__.py kaiser_filter wrapper)."""
+    import util as ref_util
+    from util.dsp import kaiser_filter
+    g = torch.Generator().manual_seed(77)
+    f0 = 80.0 + 200.0 * torch.rand(2, 1, 15, generator=g)
+    f0[0, 0, 3:6] = 0.0                       # an unvoiced stretch
+    f0[1, 0, 10:] = 0.0
+    out = {}
+    for linear in (True, False):
+        torch.manual_seed(2024)
+        out[f"exc_linear{int(linear)}"] = ref_util.f0_to_excitation(f0.clone(), 64, sampling_rate=16000, linear=linear)
+    out["f0"] = f0
+    out["kaiser_129"] = kaiser_filter(129, 0.5, 10)
+    for r in (2, 8, 10):
+        out[f"kaiser_r{r}"] = ref_util.kaiser_filter(16 * r, 1 / r)
+    save(name, **{k: v.float().numpy() for k, v in out.items()})
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     def want(n): return not only or n in only
+    if want("host"): case_host_utils("host")
     if want("g_tiny"): case_generator("g_tiny", CASES["g_tiny"], full_limit=1 << 30)
     if want("d_tiny"): case_discriminator("d_tiny", CASES["d_tiny"], full_limit=20000)
     if want("msd_tiny"): case_discriminator("msd_tiny", CASES["d_tiny"], full_limit=20000, cls=MultiscaleDiscriminator)

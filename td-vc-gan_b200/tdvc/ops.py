@@ -505,6 +505,23 @@ def add_scale(a, b=None, c=None, alpha=1.0):
     return _Add3Scale.apply(float(alpha), a, b, c)
 
 
+class _GradReverse(torch.autograd.Function):
+    """Identity whose gradient is negated (the adversarial latent classifier's input, model/grad_rev.py:3-10: the
+    reference's backward hard-codes lamb = 1 whatever the layer was built with)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return add_scale(dy, alpha=-1.0)
+
+
+def grad_reverse(x):
+    return _GradReverse.apply(x)
+
+
 class _L2Norm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):

@@ -187,3 +187,21 @@ torch.save([util.kaiser_filter(16*r, 1/r) for r in (2, 8, 10)] + [kaiser_filter(
             res.append(torch.load(out))
     for a, b in zip(*res):
         assert torch.equal(a, b)
+
+
+def test_host_utils_vs_reference_golden():
+    """util.f0_to_excitation (same RNG draw order as the reference, so a seeded call is bit-identical) and the Kaiser
+    filter designs against tests/golden/host.npz, generated from the reference by oracle/gen_golden.py host."""
+    import numpy as np
+    import util
+    from util.dsp import kaiser_filter
+    g = np.load(os.path.join(REPO, "tests", "golden", "host.npz"))
+    f0 = torch.from_numpy(g["f0"])
+    for linear in (True, False):
+        torch.manual_seed(2024)
+        exc = util.f0_to_excitation(f0.clone(), 64, sampling_rate=16000, linear=linear)
+        assert exc.shape == (2, 1, 14 * 64)
+        assert np.array_equal(exc.numpy(), g[f"exc_linear{int(linear)}"]), linear
+    assert np.array_equal(kaiser_filter(129, 0.5, 10).numpy(), g["kaiser_129"])
+    for r in (2, 8, 10):
+        assert np.array_equal(util.kaiser_filter(16 * r, 1 / r).numpy(), g[f"kaiser_r{r}"])
