@@ -23,6 +23,8 @@ for p in (PKG, REPO):
         sys.path.insert(0, p)
 
 METRIC = "train_audio_sec_per_sec"
+WORKLOAD = ("conv_enc-stage1.yaml as shipped: one D step + one G step (G fwd x3, D fwd x5, encoder(corrupted), LSGAN + "
+            "feature-matching + mel + contrastive losses, both backward passes, AdamW on G and D)")
 UNIT = "audio-s/s"
 SR = 16000
 # model + train sections of config/conv_enc-stage1.yaml (the reference's file does not travel to the GPU box)
@@ -253,9 +255,7 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp32" if args.precision == "fp32" else "bf16",
             "data": "synthetic",
-            "config": {"workload": "conv_enc-stage1.yaml as shipped: one D step + one G step (G fwd x3, D fwd x5, "
-                                   "encoder(corrupted), LSGAN + feature-matching + mel + contrastive losses, both "
-                                   "backward passes, AdamW on G and D)",
+            "config": {"workload": WORKLOAD,
                        "batch_per_gpu": B, "segment_samples": T, "sample_rate": SR, "speakers": nspk,
                        "lambda_f0": "0 (torchcrepe unavailable offline, SURVEY 8c)", "precision": args.precision,
                        "l2": "no explicit flush: one step streams >6 GB of activations, far larger than the 126 MB L2",
@@ -466,12 +466,14 @@ def run_reference(args):
     warm = min(args.warmup, 1)
     cb = cpu_baseline(steps=steps, warmup=warm, budget_s=max(4.0, 150.0 / (steps + warm)))
     sample_B = cb["batch"]
-    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": 0,
+    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
            "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": round(cb["s_per_step"] * 1e3, 1),
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-           "config": {"workload": f"conv_enc-stage1.yaml as shipped, one G+D step; bounded sample B={sample_B} of 16 per step",
-                      "batch_per_gpu": sample_B, "segment_samples": TRAIN["max_segment"], "sample_rate": SR,
-                      "speakers": MODEL["nspk"]},
+           "config": {"workload": WORKLOAD, "batch_per_gpu": sample_B, "segment_samples": TRAIN["max_segment"],
+                      "sample_rate": SR, "speakers": MODEL["nspk"],
+                      "lambda_f0": "0 (torchcrepe unavailable offline, SURVEY 8c)", "precision": "fp32",
+                      "device": f"host CPU, {cb['cores']} threads (rank 0 only; the GPUs are not used by this arm)",
+                      "sample": f"each step is one full G+D iteration at B={sample_B} of 16"},
            "cpu_baseline": cb,
            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
