@@ -205,3 +205,28 @@ def test_host_utils_vs_reference_golden():
     assert np.array_equal(kaiser_filter(129, 0.5, 10).numpy(), g["kaiser_129"])
     for r in (2, 8, 10):
         assert np.array_equal(util.kaiser_filter(16 * r, 1 / r).numpy(), g[f"kaiser_r{r}"])
+
+
+def test_step_scope_batch_tables():
+    """Host logic of the batched weight-norm / operand-pack launches (tdvc.ops._StepCache._build_tables): the flat-buffer
+    offsets are aligned and disjoint, the row prefix sums match the weights, and every pack job points at its weight."""
+    import torch.nn as nn
+    from tdvc import ops
+    sc = ops._StepCache()
+    shapes = [(16, 1, 7), (32, 16, 4), (136, 136, 3), (5, 3, 1)]
+    live = [(nn.Parameter(torch.randn(*s)), nn.Parameter(torch.randn(s[0], 1, 1))) for s in shapes]
+    sc.plan_p = [(1, 32, 64, False), (2, 144, 144, False), (2, 144, 144, True)]
+    t = sc._build_tables(live, torch.device("cpu"))
+    assert t["n"] == 4 and t["total_rows"] == sum(s[0] for s in shapes)
+    assert t["row_start"] == [0, 16, 48, 184, 189]
+    ends = [o + v.numel() for o, (v, _) in zip(t["w_off"], live)]
+    assert all(o % 64 == 0 for o in t["w_off"]) and all(e <= o2 for e, o2 in zip(ends, t["w_off"][1:])) and ends[-1] <= t["w_elems"]
+    tab = t["table"].view(4, 4)
+    for j, (v, g) in enumerate(live):
+        assert tab[j].tolist() == [v.data_ptr(), g.data_ptr(), t["w_off"][j], v.numel() // v.shape[0]]
+    jobs = t["jobs"].view(3, 8)
+    assert jobs[0].tolist() == [t["w_off"][1], t["p_off"][0], 32, 16, 4, 32, 64, 0]
+    assert jobs[2].tolist() == [t["w_off"][2], t["p_off"][2], 136, 136, 3, 144, 144, 1]
+    sizes = [4 * 32 * 64, 3 * 144 * 144, 3 * 144 * 144]
+    assert all(o % 64 == 0 for o in t["p_off"]) and all(o + n <= o2 for o, n, o2 in zip(t["p_off"], sizes, t["p_off"][1:] + [t["p_elems"]]))
+    assert 1 <= t["blocks_per_job"] <= 256
