@@ -21,12 +21,15 @@ CASES = {
 # train sections of the shipped YAMLs (config/conv_enc-stage{1,2_1,2_2}.yaml:5-35); lambda_f0 forced to 0
 # (torchcrepe unavailable offline)
 _COMMON = dict(lambda_feat=2, lambda_spec=5, lambda_wave=0, lambda_latcls=0, lambda_cont_emb=10,
-               lambda_corrupted=1, lambda_converted=0, lambda_f0=0, jitter_amp=0)
+               lambda_corrupted=1, lambda_converted=0, lambda_f0=0, jitter_amp=0, grad_max_norm_D=None, grad_max_norm_G=None)
 HP_STAGE1 = dict(_COMMON, no_conv=False, lambda_rec=0, lambda_idt=5)
 HP_STAGE2_1 = dict(_COMMON, no_conv=True, lambda_rec=0, lambda_idt=20)
 HP_STAGE2_2 = dict(_COMMON, no_conv=False, lambda_rec=10, lambda_idt=1)
 # BASELINE.json config 2: conv_enc-stage2_1 with the latent classifier + gradient reversal switched on
 HP_LATCLS = dict(HP_STAGE2_1, lambda_latcls=1)
+# options no shipped YAML switches on, pinned so that they are not silently ignored: the waveform L1 term of
+# train.py:358-361,382-385 and clip_grad_norm_ on D and G (train.py:288-289,488-489); stored gradients are post-clip
+HP_WAVE_CLIP = dict(HP_STAGE2_2, lambda_wave=3.0, grad_max_norm_D=0.05, grad_max_norm_G=0.5)
 
 
 def rand_like(t: torch.Tensor, tag: int, dtype=torch.float64) -> torch.Tensor:

@@ -26,7 +26,7 @@ from model.discriminator import (CollaborativeMultibandDiscriminator,       # no
 from model.conditional_instance_norm import ConditionalInstanceNorm        # noqa: E402  (reference)
 import util.losses as ref_losses                                            # noqa: E402  (reference)
 from oracle.params import make_state_dict, make_batch                       # noqa: E402
-from oracle.cases import CASES, HP_LATCLS, HP_STAGE1, HP_STAGE2_1, HP_STAGE2_2, rand_like  # noqa: E402
+from oracle.cases import CASES, HP_LATCLS, HP_STAGE1, HP_STAGE2_1, HP_STAGE2_2, HP_WAVE_CLIP, rand_like  # noqa: E402
 
 OUT = os.path.join(REPO, "tests", "golden")
 os.makedirs(OUT, exist_ok=True)
@@ -243,6 +243,8 @@ def ref_step(G, D, b, hp, nspk, C=None):
     d_fake = sum(F.mse_loss(o, torch.zeros_like(o)) for o in o_fake)
     D.zero_grad()
     (d_real + d_fake).backward()
+    if hp.get("grad_max_norm_D") is not None:      # train.py:288-289
+        torch.nn.utils.clip_grad_norm_(D.parameters(), hp["grad_max_norm_D"])
     out["d_loss_real"], out["d_loss_fake"] = d_real.detach(), d_fake.detach()
     out["D_grad"] = grads_of(D, 0)[1]
     if C is not None:      # latent classifier step, train.py:300-309
@@ -266,6 +268,8 @@ def ref_step(G, D, b, hp, nspk, C=None):
         _, f_rec = D(rec, lab_s, rec_subs)
         g_rec = hp["lambda_feat"] * ref_losses.multiscale_feat_loss(f_rec, f_real) + \
             hp["lambda_spec"] * ref_losses.multiscale_spec_loss(rec, x, [2048, 1024, 512])
+        if hp["lambda_wave"] > 0:      # train.py:358-361
+            g_rec = g_rec + hp["lambda_wave"] * torch.mean(torch.abs(x - rec))
     if not hp["no_conv"]:
         idt, idt_subs = G(x, c_src, c_var=b["c_f0_src"], out_subsample=True)
     else:
@@ -275,6 +279,8 @@ def ref_step(G, D, b, hp, nspk, C=None):
     idt_spec = ref_losses.multiscale_spec_loss(idt, x, [2048, 1024, 512])
     ref_losses.get_melspec_transform = orig
     g_idt = hp["lambda_feat"] * idt_feat + hp["lambda_spec"] * idt_spec
+    if hp["lambda_wave"] > 0:          # train.py:382-385: the identity pass' wave term is added to g_loss_REC
+        g_rec = g_rec + hp["lambda_wave"] * torch.mean(torch.abs(x - idt))
     emb_corr = G.encoder(b["signal_corrupted"])
     it = iter([r.clone() for r in b["neg_idx"]])
     real_randint = torch.randint
@@ -290,6 +296,8 @@ def ref_step(G, D, b, hp, nspk, C=None):
         g_loss = g_loss + hp["lambda_latcls"] * g_lat
     D.zero_grad(); G.zero_grad()
     g_loss.backward()
+    if hp.get("grad_max_norm_G") is not None:      # train.py:488-489
+        torch.nn.utils.clip_grad_norm_(G.parameters(), hp["grad_max_norm_G"])
     out.update(g_adv=g_adv.detach(), g_rec=g_rec.detach(), g_idt=g_idt.detach(), g_idt_feat=idt_feat.detach(),
                g_idt_spec=idt_spec.detach(), g_cont=g_cont.detach(), g_loss=g_loss.detach())
     out["G_grad"] = grads_of(G, 0)[1]
@@ -349,4 +357,5 @@ if __name__ == "__main__":
     if want("step_tiny_s21"): case_step("step_tiny_s21", CASES["step_tiny"], HP_STAGE2_1)
     if want("step_tiny_s22"): case_step("step_tiny_s22", CASES["step_tiny"], HP_STAGE2_2)
     if want("step_tiny_latcls"): case_step("step_tiny_latcls", CASES["step_tiny"], HP_LATCLS)
+    if want("step_tiny_wave"): case_step("step_tiny_wave", CASES["step_tiny"], HP_WAVE_CLIP)
     if want("step_full_s1"): case_step("step_full_s1", CASES["step_full"], HP_STAGE1)

@@ -141,6 +141,8 @@ def oracle_step(cfg, hp, dtype=torch.float64, sdG=None, sdD=None, batch=None, sd
     out = {}
     d = _d_step(sdG, sdD, batch, hp, cfg, kw)
     d["d_loss"].backward()
+    if hp.get("grad_max_norm_D") is not None:      # train.py:288-289
+        torch.nn.utils.clip_grad_norm_(list(sdD.values()), hp["grad_max_norm_D"])
     out.update({k: v.detach() for k, v in d.items()})
     out["D_grad"] = {k: (v.grad.clone() if v.grad is not None else torch.zeros_like(v)) for k, v in sdD.items()}
     if sdC is not None:      # latent classifier step, train.py:300-309
@@ -152,6 +154,8 @@ def oracle_step(cfg, hp, dtype=torch.float64, sdG=None, sdD=None, batch=None, sd
         v.grad = None
     g = _g_step(sdG, sdD, batch, hp, cfg, kw, sdC)
     g["g_loss"].backward()
+    if hp.get("grad_max_norm_G") is not None:      # train.py:488-489
+        torch.nn.utils.clip_grad_norm_(list(sdG.values()), hp["grad_max_norm_G"])
     out.update({k: v.detach() for k, v in g.items()})
     out["G_grad"] = {k: (v.grad.clone() if v.grad is not None else torch.zeros_like(v)) for k, v in sdG.items()}
     return out
@@ -173,7 +177,7 @@ def _d_step(sdG, sdD, b, hp, cfg, kw):
 
 
 def _g_step(sdG, sdD, b, hp, cfg, kw, sdC=None):
-    """train.py:320-480 (lambda_f0 = 0, lambda_latcls = 0, lambda_wave = 0 as shipped)."""
+    """train.py:320-480 (lambda_f0 = 0)."""
     x = b["signal_real"]
     nspk, ratios = cfg["nspk"], cfg["ratios"]
     lab_s, lab_t = b["label_src"], b["label_tgt"]
@@ -194,6 +198,8 @@ def _g_step(sdG, sdD, b, hp, cfg, kw, sdC=None):
             g_rec = g_rec + hp["lambda_feat"] * O.feat_loss(f_rec, f_real)
         if hp["lambda_spec"] > 0:
             g_rec = g_rec + hp["lambda_spec"] * O.mel_loss(rec, x)
+        if hp.get("lambda_wave", 0) > 0:      # train.py:358-361
+            g_rec = g_rec + hp["lambda_wave"] * torch.mean(torch.abs(x - rec))
     g_idt = x.new_zeros(())
     if hp["lambda_idt"] > 0:
         if not hp["no_conv"]:
@@ -205,6 +211,8 @@ def _g_step(sdG, sdD, b, hp, cfg, kw, sdC=None):
             g_idt = g_idt + hp["lambda_feat"] * O.feat_loss(f_idt, f_real)
         if hp["lambda_spec"] > 0:
             g_idt = g_idt + hp["lambda_spec"] * O.mel_loss(idt, x)
+        if hp.get("lambda_wave", 0) > 0:      # train.py:382-385: added to g_loss_REC by the reference
+            g_rec = g_rec + hp["lambda_wave"] * torch.mean(torch.abs(x - idt))
     g_cont = x.new_zeros(())
     if hp["lambda_cont_emb"] > 0 and hp["lambda_corrupted"]:
         emb_corr = O.encoder(sdG, "encoder", b["signal_corrupted"], list(ratios)[::-1])

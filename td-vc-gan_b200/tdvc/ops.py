@@ -124,84 +124,138 @@ class _WeightNorm(torch.autograd.Function):
         return dv, dg
 
 
-class _StepCache:
-    """Inside `with ops.step_cache():` a weight that has not changed is normalised (and packed to bf16) once and
-    reused by every forward pass of the scope -- the generator runs 3-4 times per training iteration on the same
-    weights.  Reuse is through autograd (the cached tensor carries its grad_fn), so gradients from all passes
-    accumulate into one weight-norm backward.  Entries are keyed on the parameter versions and dropped at scope exit.
+class _Scope:
+    """State of one open step scope: what was normalised / packed inside it."""
 
-    Batching: the (v, g) pairs and the bf16 packs a scope asked for are remembered (the PLAN); from the next scope on,
-    entering the scope normalises every planned weight with ONE multi-tensor launch and packs every planned operand
-    with ONE more, instead of ~530 + ~380 small launches per step.  `_WeightNorm.forward` / `_pack_w` then pick their
-    result up from the flat buffers.  TDVC_NO_WN_BATCH=1 disables it."""
+    def __init__(self, tag):
+        self.tag = tag
+        self.wn = {}                # weight_norm() results of this scope
+        self.wp = {}                # packed operands / _step_cached() results of this scope
+        self.pre_w = {}             # (v ptr, g ptr) -> (w, inv, v version, g version) from the batched launch
+        self.pre_p = {}             # (w ptr, rows_p, cols_p, flip) -> packed operand from the batched launch
+        self.cur_w = {}             # w ptr -> weight index in this tag's plan
+
+
+class _StepCache:
+    """Inside `with ops.step_cache(tag):` a weight that has not changed is normalised (and packed to bf16) once and
+    reused by every pass of the scope.  Reuse is through autograd (the cached tensor carries its grad_fn), so gradients
+    from all passes accumulate into one weight-norm backward.  Entries are keyed on the parameter versions and dropped at
+    scope exit.
+
+    Scopes nest (a stack): lookups search from the innermost scope outwards, new entries go to the innermost one.  The
+    training iteration keeps a generator scope open from the generator passes to the end of the G backward and opens a
+    scope for the D step and one for the G step's discriminator passes inside it -- D's weights change between the two.
+
+    Batching: the (v, g) pairs and the bf16 packs a scope asked for are remembered per tag (the PLAN); from the next
+    scope of that tag on, entering it normalises every planned weight with ONE multi-tensor launch and packs every
+    planned operand with ONE more, instead of hundreds of small launches per step.  `_WeightNorm.forward` / `_pack_w`
+    then pick their result up from the flat buffers.  TDVC_NO_WN_BATCH=1 disables it."""
 
     def __init__(self):
-        self.depth = 0
-        self.wn = {}
-        self.wp = {}
-        self.plan_w = []            # [(weakref v, weakref g)]
-        self.plan_w_idx = {}        # (v ptr, g ptr) -> index into plan_w
-        self.plan_p = []            # [(weight index, rows_p, cols_p, flip)]
-        self.plan_p_idx = {}
-        self.tables = None
-        self.pre_w = {}             # this scope: (v ptr, g ptr) -> (w, inv, v version, g version)
-        self.pre_p = {}             # this scope: (w ptr, rows_p, cols_p, flip) -> packed operand
-        self.cur_w = {}             # this scope: w ptr -> weight index
+        self.stack = []
+        self.plans = {}             # tag -> dict(plan_w, plan_w_idx, plan_p, plan_p_idx, tables)
+        self._next_tag = "default"
+
+    @property
+    def depth(self):
+        return len(self.stack)
+
+    def __call__(self, tag="default"):
+        self._next_tag = tag
+        return self
+
+    def _plan(self, tag):
+        pl = self.plans.get(tag)
+        if pl is None:
+            # plan_w [(weakref v, weakref g)], plan_w_idx (v ptr, g ptr) -> index, plan_p [(weight index, rows_p, cols_p,
+            # flip)], plan_p_idx
+            pl = self.plans[tag] = dict(plan_w=[], plan_w_idx={}, plan_p=[], plan_p_idx={}, tables=None)
+        return pl
 
     def __enter__(self):
+        tag, self._next_tag = self._next_tag, "default"
         if os.environ.get("TDVC_NO_STEP_CACHE") != "1":
-            self.depth += 1
-            if self.depth == 1:
-                self._prelaunch()
+            sc = _Scope(tag)
+            self.stack.append(sc)
+            self._prelaunch(sc)
         return self
 
     def __exit__(self, *exc):
-        if os.environ.get("TDVC_NO_STEP_CACHE") != "1":
-            self.depth -= 1
-        if self.depth == 0:
-            self.wn.clear()
-            self.wp.clear()
-            self.pre_w.clear()
-            self.pre_p.clear()
-            self.cur_w.clear()
+        if os.environ.get("TDVC_NO_STEP_CACHE") != "1" and self.stack:
+            self.stack.pop()
         return False
+
+    # ---- scope-stack lookups
+    def get_wn(self, key):
+        for sc in reversed(self.stack):
+            hit = sc.wn.get(key)
+            if hit is not None:
+                return hit
+        return None
+
+    def put_wn(self, key, val):
+        self.stack[-1].wn[key] = val
+
+    def get_wp(self, key):
+        for sc in reversed(self.stack):
+            hit = sc.wp.get(key)
+            if hit is not None:
+                return hit
+        return None
+
+    def put_wp(self, key, val):
+        self.stack[-1].wp[key] = val
 
     # ---- plan bookkeeping
     def note_w(self, v, g, w):
-        if self.depth == 0 or not (v.is_leaf and g.is_leaf):
+        if not self.stack or not (v.is_leaf and g.is_leaf):
             return
+        sc = self.stack[-1]
+        pl = self._plan(sc.tag)
         key = (v.data_ptr(), g.data_ptr())
-        idx = self.plan_w_idx.get(key)
+        idx = pl["plan_w_idx"].get(key)
         if idx is None:
-            idx = len(self.plan_w)
-            self.plan_w.append((weakref.ref(v), weakref.ref(g)))
-            self.plan_w_idx[key] = idx
-            self.tables = None
-        self.cur_w[w.data_ptr()] = idx
+            idx = len(pl["plan_w"])
+            pl["plan_w"].append((weakref.ref(v), weakref.ref(g)))
+            pl["plan_w_idx"][key] = idx
+            pl["tables"] = None
+        sc.cur_w[w.data_ptr()] = idx
 
     def note_p(self, w, rows_p, cols_p, flip):
-        idx = self.cur_w.get(w.data_ptr()) if self.depth > 0 else None
-        if idx is None:
+        # the pack joins the plan of the scope that normalised w (the generator's weights are packed for their data
+        # gradients while the G-step scope is the innermost one)
+        for sc in reversed(self.stack):
+            idx = sc.cur_w.get(w.data_ptr())
+            if idx is None:
+                continue
+            pl = self._plan(sc.tag)
+            key = (idx, rows_p, cols_p, bool(flip))
+            if key not in pl["plan_p_idx"]:
+                pl["plan_p_idx"][key] = len(pl["plan_p"])
+                pl["plan_p"].append(key)
+                pl["tables"] = None
             return
-        key = (idx, rows_p, cols_p, bool(flip))
-        if key not in self.plan_p_idx:
-            self.plan_p_idx[key] = len(self.plan_p)
-            self.plan_p.append(key)
-            self.tables = None
 
     def lookup_w(self, v, g):
-        if self.depth == 0:
-            return None
-        hit = self.pre_w.get((v.data_ptr(), g.data_ptr()))
-        if hit is None or hit[2] != v._version or hit[3] != g._version:
-            return None
-        return hit[0], hit[1]
+        for sc in reversed(self.stack):
+            hit = sc.pre_w.get((v.data_ptr(), g.data_ptr()))
+            if hit is not None:
+                if hit[2] != v._version or hit[3] != g._version:
+                    return None
+                return hit[0], hit[1]
+        return None
 
     def lookup_p(self, w, rows_p, cols_p, flip):
-        return self.pre_p.get((w.data_ptr(), rows_p, cols_p, bool(flip))) if self.depth > 0 else None
+        key = (w.data_ptr(), rows_p, cols_p, bool(flip))
+        for sc in reversed(self.stack):
+            hit = sc.pre_p.get(key)
+            if hit is not None:
+                return hit
+        return None
 
     # ---- the batched launches
-    def _build_tables(self, live, dev):
+    @staticmethod
+    def _build_tables(pl, live, dev):
         al = lambda n, a: (n + a - 1) // a * a
         rows, tab, w_off, off, r = [0], [], [], 0, 0
         for v, g in live:
@@ -213,7 +267,7 @@ class _StepCache:
             r += nr
             rows.append(r)
         jobs, p_off, poff = [], [], 0
-        for (idx, rows_p, cols_p, flip) in self.plan_p:
+        for (idx, rows_p, cols_p, flip) in pl["plan_p"]:
             v = live[idx][0]
             Cout, Cin, K = v.shape
             jobs += [w_off[idx], poff, Cout, Cin, K, rows_p, cols_p, int(flip)]
@@ -227,22 +281,23 @@ class _StepCache:
                  jobs=torch.tensor(jobs, dtype=torch.int64).to(dev) if jobs else None)
         return t
 
-    def _prelaunch(self):
-        if not self.plan_w or os.environ.get("TDVC_NO_WN_BATCH") == "1" or branch_streams_enabled() or not torch.cuda.is_available():
+    def _prelaunch(self, sc):
+        pl = self._plan(sc.tag)
+        if not pl["plan_w"] or os.environ.get("TDVC_NO_WN_BATCH") == "1" or branch_streams_enabled() or not torch.cuda.is_available():
             return
-        live = [(rv(), rg()) for rv, rg in self.plan_w]
+        live = [(rv(), rg()) for rv, rg in pl["plan_w"]]
         if any(v is None or g is None for v, g in live):          # a module went away: start the plan over
-            self.plan_w, self.plan_w_idx, self.plan_p, self.plan_p_idx, self.tables = [], {}, [], {}, None
+            self.plans.pop(sc.tag, None)
             return
         dev = live[0][0].device
         if any(v.device != dev or not v.is_contiguous() or not g.is_contiguous() for v, g in live):
             return
         sig = tuple(v.data_ptr() for v, _ in live) + tuple(g.data_ptr() for _, g in live)
-        if self.tables is None or self.tables["sig"] != sig or self.tables["dev"] != dev:
+        if pl["tables"] is None or pl["tables"]["sig"] != sig or pl["tables"]["dev"] != dev:
             if torch.cuda.is_current_stream_capturing():
                 return                                           # host->device table upload is not capturable
-            self.tables = self._build_tables(live, dev)
-        t = self.tables
+            pl["tables"] = self._build_tables(pl, live, dev)
+        t = pl["tables"]
         lib = _lib.load()
         flat_w = torch.empty(t["w_elems"], device=dev, dtype=torch.float32)
         flat_inv = torch.empty(t["total_rows"], device=dev, dtype=torch.float32)
@@ -252,35 +307,35 @@ class _StepCache:
         for j, (v, g) in enumerate(live):
             w = flat_w[t["w_off"][j]:t["w_off"][j] + v.numel()].view_as(v)
             inv = flat_inv[t["row_start"][j]:t["row_start"][j + 1]]
-            self.pre_w[(v.data_ptr(), g.data_ptr())] = (w, inv, v._version, g._version)
-            self.cur_w[w.data_ptr()] = j
+            sc.pre_w[(v.data_ptr(), g.data_ptr())] = (w, inv, v._version, g._version)
+            sc.cur_w[w.data_ptr()] = j
             ws.append(w)
         if t["jobs"] is not None:
             flat_wp = torch.empty(t["p_elems"], device=dev, dtype=torch.bfloat16)
-            _lib.check(lib.tdvc_pack_weight_bf16_multi(_p(t["jobs"]), len(self.plan_p), t["blocks_per_job"], _p(flat_w),
+            _lib.check(lib.tdvc_pack_weight_bf16_multi(_p(t["jobs"]), len(pl["plan_p"]), t["blocks_per_job"], _p(flat_w),
                                                        _p(flat_wp), _st()),
                        "pack_weight_bf16_multi")
-            for i, (idx, rows_p, cols_p, flip) in enumerate(self.plan_p):
+            for i, (idx, rows_p, cols_p, flip) in enumerate(pl["plan_p"]):
                 K = live[idx][0].shape[2]
                 wp = flat_wp[t["p_off"][i]:t["p_off"][i] + K * rows_p * cols_p].view(K, rows_p, cols_p)
-                self.pre_p[(ws[idx].data_ptr(), rows_p, cols_p, flip)] = wp
+                sc.pre_p[(ws[idx].data_ptr(), rows_p, cols_p, flip)] = wp
 
 
 _step_cache = _StepCache()
 
 
-def step_cache() -> _StepCache:
-    return _step_cache
+def step_cache(tag: str = "default") -> _StepCache:
+    return _step_cache(tag)
 
 
 def weight_norm(v: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
     """w = g * v / ||v|| (norm over all dims but 0) -- torch.nn.utils.weight_norm's per-forward recompute."""
     if _step_cache.depth > 0:
         key = (v.data_ptr(), v._version, g.data_ptr(), g._version, torch.is_grad_enabled() and (v.requires_grad or g.requires_grad))
-        hit = _step_cache.wn.get(key)
+        hit = _step_cache.get_wn(key)
         if hit is None:
             hit = (_WeightNorm.apply(v, g), torch.cuda.current_stream().cuda_stream)
-            _step_cache.wn[key] = hit
+            _step_cache.put_wn(key, hit)
         elif os.environ.get("TDVC_DEBUG_STREAMS") == "1" and hit[1] != torch.cuda.current_stream().cuda_stream:
             print(f"[tdvc] weight {tuple(v.shape)} normalised on stream {hit[1]:#x}, reused on {torch.cuda.current_stream().cuda_stream:#x}",
                   flush=True)
@@ -851,6 +906,55 @@ def l1_mean_sum(sig: Sequence[torch.Tensor], ref: Sequence[torch.Tensor]) -> tor
     return _L1MeanSum.apply(len(sig), *sig, *ref)
 
 
+class _L1MeanSumRows(torch.autograd.Function):
+    """sum_i mean(|a_i[row0:row0+n] - b_i|) where a_i holds several signals stacked along the batch (the batched
+    discriminator call of the G step) and b_i is the detached reference of `n` rows.  The backward writes the gradient
+    of the whole stacked tensor (zeros outside the rows) instead of leaving a slice for autograd to pad."""
+
+    @staticmethod
+    def forward(ctx, n, row0, nrows, *tensors):
+        a, b = tensors[:n], tensors[n:]
+        _req(*a, *b)
+        a = [_c(t) for t in a]
+        b = [_c(t) for t in b]
+        out = torch.zeros(1, device=a[0].device, dtype=torch.float32)
+        lib = _lib.load()
+        for u, v in zip(a, b):
+            if row0 < 0 or row0 + nrows > u.shape[0] or tuple(v.shape) != (nrows,) + tuple(u.shape[1:]):
+                raise RuntimeError(f"l1 loss: rows [{row0}, {row0 + nrows}) of {tuple(u.shape)} vs {tuple(v.shape)}")
+            us = u[row0:row0 + nrows]
+            _lib.check(lib.tdvc_abs_diff_sum(_p(us), _p(v), 1.0 / v.numel(), _p(out), v.numel(), _st()), "abs_diff_sum")
+        ctx.cfg = (n, row0, nrows)
+        ctx.save_for_backward(*a, *b)
+        return out.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        n, row0, nrows = ctx.cfg
+        a, b = ctx.saved_tensors[:n], ctx.saved_tensors[n:]
+        g = g.reshape(1).contiguous().float()
+        lib = _lib.load()
+        grads = []
+        for i, (u, v) in enumerate(zip(a, b)):
+            if not ctx.needs_input_grad[3 + i]:
+                grads.append(None)
+                continue
+            d = torch.empty_like(u)
+            if row0 > 0:
+                d[:row0].zero_()
+            if row0 + nrows < u.shape[0]:
+                d[row0 + nrows:].zero_()
+            _lib.check(lib.tdvc_abs_diff_bwd(_p(u[row0:row0 + nrows]), _p(v), 1.0 / v.numel(), _p(g), _p(d[row0:row0 + nrows]),
+                                             v.numel(), _st()), "abs_diff_bwd")
+            grads.append(d)
+        return (None, None, None, *grads, *([None] * n))
+
+
+def l1_mean_sum_rows(sig: Sequence[torch.Tensor], row0: int, nrows: int, ref: Sequence[torch.Tensor]) -> torch.Tensor:
+    sig, ref = list(sig), [r.detach() for r in ref]
+    return _L1MeanSumRows.apply(len(sig), int(row0), int(nrows), *sig, *ref)
+
+
 # ----------------------------------------------------------------------------- bf16 tensor-core conv path
 
 def _ceil(a, m):
@@ -917,7 +1021,7 @@ def _pack_w(w, rows_p, cols_p, transpose_flip):
         if pre is not None:                        # packed by the scope's batched launch
             return pre
         key = (w.data_ptr(), w._version, tuple(w.shape), rows_p, cols_p, bool(transpose_flip))
-        hit = _step_cache.wp.get(key)
+        hit = _step_cache.get_wp(key)
         if hit is not None and hit[0]() is w:
             return hit[1]
         _step_cache.note_p(w, rows_p, cols_p, transpose_flip)
@@ -926,7 +1030,7 @@ def _pack_w(w, rows_p, cols_p, transpose_flip):
     _lib.check(_lib.load().tdvc_pack_weight_bf16(_p(w), _p(wp), Cout, Cin, K, coutp, cinp, int(transpose_flip), 0, 0, 0, 0,
                                                  _st()), "pack_weight_bf16")
     if key is not None:
-        _step_cache.wp[key] = (weakref.ref(w), wp)
+        _step_cache.put_wp(key, (weakref.ref(w), wp))
     return wp
 
 
@@ -1066,10 +1170,10 @@ def _step_cached(tag, tensors, make):
     if _step_cache.depth == 0:
         return make()
     key = (tag,) + tuple((t.data_ptr(), t._version) if t is not None else None for t in tensors)
-    hit = _step_cache.wp.get(key)
+    hit = _step_cache.get_wp(key)
     if hit is None:
         hit = (list(tensors), make())
-        _step_cache.wp[key] = hit
+        _step_cache.put_wp(key, hit)
     return hit[1]
 
 

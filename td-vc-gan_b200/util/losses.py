@@ -27,6 +27,20 @@ def multiscale_feat_loss(feat_sig_list, feat_ref_list, norm_p=1):
     return ops.l1_mean_sum(sig, ref)
 
 
+def multiscale_feat_loss_rows(feat_sig_list, row0, nrows, feat_ref_list):
+    """multiscale_feat_loss(f_sig, f_ref) where every map of `feat_sig_list` holds several signals stacked along the
+    batch and f_sig is its rows [row0, row0 + nrows)  (not in the reference: tdvc.train_step runs the discriminator once
+    on the stacked generator outputs)."""
+    sig, ref = [], []
+    for feat_sig, feat_ref in zip(feat_sig_list, feat_ref_list):
+        for map_sig, map_ref in zip(feat_sig, feat_ref):
+            sig.append(map_sig)
+            ref.append(map_ref)
+    if not sig:
+        return 0
+    return ops.l1_mean_sum_rows(sig, row0, nrows, ref)
+
+
 @functools.lru_cache(maxsize=None)
 def _mel_operands(sr, n_fft, n_mels, device):
     """Hann window and slaney-normalised HTK mel filterbank, as torchaudio.transforms.MelSpectrogram(sr, n_fft,

@@ -215,8 +215,9 @@ def test_step_scope_batch_tables():
     sc = ops._StepCache()
     shapes = [(16, 1, 7), (32, 16, 4), (136, 136, 3), (5, 3, 1)]
     live = [(nn.Parameter(torch.randn(*s)), nn.Parameter(torch.randn(s[0], 1, 1))) for s in shapes]
-    sc.plan_p = [(1, 32, 64, False), (2, 144, 144, False), (2, 144, 144, True)]
-    t = sc._build_tables(live, torch.device("cpu"))
+    pl = sc._plan("G")
+    pl["plan_p"] = [(1, 32, 64, False), (2, 144, 144, False), (2, 144, 144, True)]
+    t = sc._build_tables(pl, live, torch.device("cpu"))
     assert t["n"] == 4 and t["total_rows"] == sum(s[0] for s in shapes)
     assert t["row_start"] == [0, 16, 48, 184, 189]
     ends = [o + v.numel() for o, (v, _) in zip(t["w_off"], live)]
@@ -230,3 +231,25 @@ def test_step_scope_batch_tables():
     sizes = [4 * 32 * 64, 3 * 144 * 144, 3 * 144 * 144]
     assert all(o % 64 == 0 for o in t["p_off"]) and all(o + n <= o2 for o, n, o2 in zip(t["p_off"], sizes, t["p_off"][1:] + [t["p_elems"]]))
     assert 1 <= t["blocks_per_job"] <= 256
+
+
+def test_step_scopes_nest_and_keep_plans_per_tag():
+    """The scope stack of tdvc.ops._StepCache: lookups search outwards, inserts go to the innermost scope, a nested scope's
+    entries disappear when it closes, and every tag keeps its own plan."""
+    from tdvc import ops
+    sc = ops._StepCache()
+    with sc("G"):
+        assert sc.depth == 1 and sc.stack[-1].tag == "G"
+        sc.put_wn("kG", 1)
+        with sc("D"):
+            assert sc.depth == 2 and sc.stack[-1].tag == "D"
+            assert sc.get_wn("kG") == 1              # found in the enclosing scope
+            sc.put_wn("kD", 2)
+            sc.put_wp("pD", 3)
+            assert sc.get_wn("kD") == 2 and sc.get_wp("pD") == 3
+        assert sc.get_wn("kD") is None and sc.get_wp("pD") is None     # D's entries went with its scope
+        assert sc.get_wn("kG") == 1
+    assert sc.depth == 0
+    assert sc._plan("G") is not sc._plan("D")
+    with sc():
+        assert sc.stack[-1].tag == "default"

@@ -8,7 +8,7 @@ import torch.nn.functional as F
 
 from helpers import golden, golden_shapes, relerr, stats
 from oracle import tdvc_oracle as O
-from oracle.cases import CASES, HP_LATCLS, HP_STAGE1, HP_STAGE2_1, HP_STAGE2_2, rand_like
+from oracle.cases import CASES, HP_LATCLS, HP_STAGE1, HP_STAGE2_1, HP_STAGE2_2, HP_WAVE_CLIP, rand_like
 from oracle.params import make_batch, make_state_dict
 
 TOL = 1e-9
@@ -155,6 +155,7 @@ def test_losses():
                                           ("step_tiny_s21", HP_STAGE2_1, "step_tiny"),
                                           ("step_tiny_s22", HP_STAGE2_2, "step_tiny"),
                                           ("step_tiny_latcls", HP_LATCLS, "step_tiny"),
+                                          ("step_tiny_wave", HP_WAVE_CLIP, "step_tiny"),
                                           ("step_full_s1", HP_STAGE1, "step_full")])
 def test_train_step(name, hp, case):
     """One G+D iteration (train.py:259-491) against the reference's own modules driven by
