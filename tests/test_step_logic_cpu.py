@@ -114,4 +114,4 @@ def test_jitter_rolls_the_reference_signal():
             out = _run(cfg, hp)
     finally:
         torch.randint = real_randint
-    assert abs(float(out["g_loss"]) - float(np.asarray(g["g_loss"]).reshape(-1)[0])) <= 1e-9 * abs(float(out["g_loss"]))
+    assert abs(float(out["g_loss"]) - float(np.asarray(g["g_loss"]).reshape(-1)[0])) <= 1e-7 * abs(float(out["g_loss"]))
