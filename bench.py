@@ -23,8 +23,6 @@ for p in (PKG, REPO):
         sys.path.insert(0, p)
 
 METRIC = "train_audio_sec_per_sec"
-WORKLOAD = ("conv_enc-stage1.yaml as shipped: one D step + one G step (G fwd x3, D fwd x5, encoder(corrupted), LSGAN + "
-            "feature-matching + mel + contrastive losses, both backward passes, AdamW on G and D)")
 UNIT = "audio-s/s"
 SR = 16000
 # model + train sections of config/conv_enc-stage1.yaml (the reference's file does not travel to the GPU box)
@@ -33,8 +31,25 @@ MODEL = dict(ratios=(10, 8, 2, 2), channels=(256, 128, 64, 32, 16), content_dim=
 TRAIN = dict(no_conv=False, lambda_rec=0, lambda_idt=5, lambda_feat=2, lambda_spec=5, lambda_wave=0, lambda_latcls=0,
              lambda_cont_emb=10, lambda_corrupted=1, lambda_converted=0, lambda_f0=0, jitter_amp=0,
              batch_size=16, max_segment=8960, lr=1e-4, betas=(0.8, 0.99))
-# algorithmic FLOPs of one step at B=16 (fwd 1557 + bwd 2138 GF; analytic 2*MAC per conv)
-STEP_GFLOP_B16 = 3695.0
+# BASELINE.json configs: train sections of the shipped YAMLs (lambda_f0 forced to 0: torchcrepe is unavailable
+# offline) and the algorithmic FLOPs of one REFERENCE step at B=16 (analytic 2*MAC per conv,
+# every pass the reference runs -- the passes this implementation shares or skips still count as work delivered)
+CONFIGS = {
+    "stage1": dict(train=TRAIN, gflop=3695.0,
+                   workload="conv_enc-stage1.yaml as shipped: one D step + one G step (reference: G fwd x3, D fwd x5, "
+                            "encoder(corrupted), LSGAN + feature-matching + mel + contrastive losses, both backward passes, "
+                            "AdamW on G and D)"),
+    "stage2_1": dict(train=dict(TRAIN, no_conv=True, lambda_idt=20), gflop=2299.0,
+                     workload="conv_enc-stage2_1.yaml as shipped (no_conv: reconstruction; reference: G fwd x2, D fwd x4, "
+                              "encoder(corrupted))"),
+    "stage2_1_latcls": dict(train=dict(TRAIN, no_conv=True, lambda_idt=20, lambda_latcls=1), gflop=2299.0 + 15.0,
+                            workload="conv_enc-stage2_1.yaml with lambda_latcls=1: latent classifier step + gradient "
+                                     "reversal term (BASELINE config 2)"),
+    "stage2_2": dict(train=dict(TRAIN, lambda_rec=10, lambda_idt=1), gflop=5159.0,
+                     workload="conv_enc-stage2_2.yaml as shipped (conversion + reverse/cycle pass G(fake) -> rec, D(rec))"),
+}
+STEP_GFLOP_B16 = CONFIGS["stage1"]["gflop"]
+WORKLOAD = CONFIGS["stage1"]["workload"]
 
 
 def peaks():
@@ -160,13 +175,22 @@ def run_ours(args):
     lib = _lib.load()
     ops.set_precision(args.precision)
     ops.set_branch_streams(args.branch_streams)
+    conf = CONFIGS[args.config]
+    hp = conf["train"]
+    step_gflop = conf["gflop"]
     B, T, nspk = TRAIN["batch_size"], TRAIN["max_segment"], MODEL["nspk"]
     G, D = build_models(dev)
     broadcast_parameters(G); broadcast_parameters(D)
     oG = FusedAdamW(G.parameters(), TRAIN["lr"], TRAIN["betas"])
     oD = FusedAdamW(D.parameters(), TRAIN["lr"], TRAIN["betas"])
+    Cm = oC = None
+    if hp["lambda_latcls"] != 0:
+        from model.latent_classifier import LatentClassifier
+        Cm = LatentClassifier(nspk, MODEL["content_dim"]).to(dev)
+        broadcast_parameters(Cm)
+        oC = FusedAdamW(Cm.parameters(), TRAIN["lr"], (0.9, 0.999), weight_decay=0.0)     # torch.optim.Adam, train.py:192
     hook = GradAverager() if world > 1 else None
-    ts = TrainStep(G, D, TRAIN, oG, oD, nspk, grad_hook=hook)
+    ts = TrainStep(G, D, hp, oG, oD, nspk, grad_hook=hook, C=Cm, optimizer_C=oC)
     host = synth_batch(B, T, nspk, seed=1234 + rank)
     pinned = {k: v.pin_memory() for k, v in host.items()}
     resident, _ = to_device(host, dev)
@@ -197,9 +221,11 @@ def run_ours(args):
     if args.graph:
         # the whole step (both backward passes, all-reduce, optimisers) is one CUDA graph; eager warm-up inside
         n0 = lib.tdvc_launch_count()
+        f0 = [lib.tdvc_flop_count(i) for i in range(6)]
         graphed = GraphedTrainStep(ts, resident, warmup=2)
         n_cap = lib.tdvc_launch_count() - n0
         launches_per_step = n_cap / 3.0          # 2 eager warm-up steps + 1 captured step
+        fam_gflop = [(lib.tdvc_flop_count(i) - f0[i]) / 3.0 / 1e9 for i in range(6)]
 
         def step_resident():
             last.update(graphed.step())
@@ -212,6 +238,7 @@ def run_ours(args):
             last["host_losses"] = losses
     else:
         launches_per_step = None
+        fam_gflop = None
 
         def step_resident():
             last.update(ts.step(resident))
@@ -247,40 +274,126 @@ def run_ours(args):
     e2e = audio_s * args.steps / (ms_e2e / 1e3)
 
     out = None
+    fams = None
+    if rank == 0 and args.graph:
+        try:
+            fams = kernel_families(graphed.step, fam_gflop)
+        except Exception as e:          # never lose the headline line to the trace
+            fams = {"error": repr(e)[:200]}
     if rank == 0:
         pk = peaks()
-        roof = dominant_kernel_roofline(dev, B, T, pk, args)
+        flop_dom = dominant_kernel_roofline(dev, B, T, pk, args)
+        ms_step = ms / args.steps
+        roof = time_dominant_roofline(fams, pk, ms_step, step_gflop, flop_dom)
         out = {
             "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp32" if args.precision == "fp32" else "bf16",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD,
+            "config": {"workload": conf["workload"], "name": args.config,
                        "batch_per_gpu": B, "segment_samples": T, "sample_rate": SR, "speakers": nspk,
                        "lambda_f0": "0 (torchcrepe unavailable offline, SURVEY 8c)", "precision": args.precision,
                        "l2": "no explicit flush: one step streams >6 GB of activations, far larger than the 126 MB L2",
-                       "parallelism": f"dp{world}", "step_gflop_algorithmic": STEP_GFLOP_B16 * world,
+                       "parallelism": f"dp{world}", "step_gflop_algorithmic": step_gflop * world,
                        "cuda_graph": bool(args.graph)},
             "clocks": clocks,
             "e2e": {"value": round(e2e, 3), "unit": UNIT, "h2d_bytes_per_step": h2d[0], "d2h_bytes_per_step": d2h[0],
                     "ms_per_step": round(ms_e2e / args.steps, 3)},
             "gpu_launches": int(round(launches)),
-            "step_tflops_algorithmic": round(STEP_GFLOP_B16 * world / (ms / args.steps), 3),
+            "step_tflops_algorithmic": round(step_gflop * world / (ms / args.steps), 3),
+            "step_frac_of_sustained_tensor_peak": round(step_gflop / (ms / args.steps) / pk["tc_sustained"], 5),
             "roofline": roof,
+            "roofline_flop_dominant_kernel": flop_dom,
+            "kernel_families": fams,
             "losses": {k: float(v) for k, v in last.items() if k in ("d_loss", "g_loss")},
         }
-        if world == 1:
+        if world == 1 and not args.no_inference:
             try:
-                out["inference"] = inference_rtf(G, dev, args)
+                out["inference"] = inference_sweep(G, dev, args)
             except Exception as e:      # never lose the headline line to the auxiliary measurement
                 out["inference"] = {"error": repr(e)[:200]}
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(steps=1, warmup=0, budget_s=30.0)
+            out["cpu_baseline"] = cpu_baseline(steps=1, warmup=0, hp=hp)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if out is not None:
         print(json.dumps(out), flush=True)
+
+
+FAMILY_OF = (("conv_tc_wgrad_k", 3), ("conv_tc_wt_k", 2), ("conv_tc_ws_k", 1), ("conv_tc_fwd_k", 0), ("mrf_chain", 5),
+             ("conv_fwd_k", 4), ("conv_tr_k", 4), ("conv_wgrad_k", 4))
+FAMILY_NAME = {0: "conv_tc_fwd_k (tcgen05, one tile per CTA: fwd + dgrad of the small convs)",
+               1: "conv_tc_ws_k (tcgen05, weight-stationary persistent)", 2: "conv_tc_wt_k (tcgen05, stacked cond_var.0)",
+               3: "conv_tc_wgrad_k (tcgen05 weight gradients)", 4: "fp32 CUDA-core convs (grouped k41 s4 D layers, 1-channel stems, FIR)",
+               5: "fused MRF chain kernels (tcgen05)"}
+
+
+def kernel_families(replay, fam_gflop):
+    """Per-kernel-family busy time of ONE CUDA-graph replay of the step (CUPTI through torch.profiler, after the timed
+    region; kernels overlap slightly under programmatic dependent launch, so the sum can exceed the wall time), next to
+    the multiply-accumulate work the library handed to each conv family (tdvc_flop_count deltas of one step)."""
+    import collections
+    import re
+    import torch
+    from torch.profiler import ProfilerActivity, profile
+    replay()
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        replay()
+        torch.cuda.synchronize()
+    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    if not evs:
+        return {"error": "no CUDA activities in the trace"}
+    busy, cnt = collections.Counter(), collections.Counter()
+    for e in evs:
+        name = re.sub(r"\(.*", "", e.name)
+        name = re.sub(r"^void ", "", name)[:60]
+        busy[name] += (e.time_range.end - e.time_range.start) / 1e3
+        cnt[name] += 1
+    t0 = min(e.time_range.start for e in evs)
+    t1 = max(e.time_range.end for e in evs)
+    total = sum(busy.values())
+    top = [{"kernel": k, "launches": cnt[k], "ms": round(v, 3), "share_of_busy": round(v / total, 4)}
+           for k, v in sorted(busy.items(), key=lambda kv: -kv[1])[:24]]
+    conv = {}
+    for k, v in busy.items():
+        for pat, fam in FAMILY_OF:
+            if pat in k:
+                d = conv.setdefault(fam, {"family": FAMILY_NAME[fam], "launches": 0, "ms": 0.0})
+                d["launches"] += cnt[k]
+                d["ms"] += v
+                break
+    for fam, d in conv.items():
+        d["ms"] = round(d["ms"], 3)
+        if fam_gflop is not None:
+            d["gflop_per_step"] = round(fam_gflop[fam], 2)
+            d["tflops"] = round(fam_gflop[fam] / d["ms"], 2) if d["ms"] > 0 else None
+    return {"span_ms": round((t1 - t0) / 1e3, 3), "busy_ms": round(total, 3), "activities": len(evs), "top": top,
+            "conv_families": [conv[k] for k in sorted(conv, key=lambda k: -conv[k]["ms"])]}
+
+
+def time_dominant_roofline(fams, pk, ms_step, step_gflop, flop_dom):
+    """`roofline` describes what bounds the STEP: the conv kernel family with the largest share of the step's time, its
+    achieved rate = (2*MAC handed to it per step) / (its busy time in one replay) against the SUSTAINED dense bf16 peak
+    (it runs inside a long step); the whole-step fraction and the FLOP-dominant launch are reported beside it."""
+    peak = pk["tc_sustained"]
+    base = {"bound": "tensor", "peak": peak, "unit": "TFLOP/s", "traffic": None,
+            "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside the step), {pk['src']}",
+            "step": {"achieved": round(step_gflop / ms_step, 3), "frac": round(step_gflop / ms_step / peak, 5),
+                     "what": "algorithmic FLOPs of the whole reference step / step time"}}
+    try:
+        fam = fams["conv_families"][0]
+        ach = fam["tflops"]
+        base.update(achieved=ach, frac=round(ach / peak, 5), kernel=fam["family"], launches_per_step=fam["launches"],
+                    ms_per_step=fam["ms"], gflop_per_step=fam["gflop_per_step"],
+                    share_of_step_time=round(fam["ms"] / ms_step, 4),
+                    how="2*MAC handed to the family per step (tdvc_flop_count) / its busy time in one CUDA-graph replay "
+                        "(CUPTI, taken inside bench.py after the timed region)")
+    except Exception:
+        base.update(achieved=flop_dom["achieved"], frac=round(flop_dom["achieved"] / peak, 5), kernel=flop_dom["kernel"],
+                    how="family trace unavailable: the FLOP-dominant launch timed alone")
+    return base
 
 
 def dominant_kernel_roofline(dev, B, T, pk, args):
@@ -369,111 +482,113 @@ def dominant_kernel_roofline(dev, B, T, pk, args):
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone), {pk['src']}"}
 
 
-def inference_rtf(G, dev, args, B=16, seconds=4.0, reps=5):
-    """BASELINE config 5: batched `G(signal, c_tgt, c_var=excitation)` (generate_with_target.py:169) on synthetic
-    4 s utterances, forward only (no_grad), replayed from a CUDA graph.  RTF = wall time / audio seconds."""
+def inference_sweep(G, dev, args, seconds=4.0, batches=(1, 4, 16, 64, 128)):
+    """BASELINE config 5: batched `G(signal, c_tgt, c_var=excitation)` (generate_with_target.py:169) on synthetic 4 s
+    utterances, forward only (no_grad), weight norm + bf16 operand packing folded ONCE (ops.inference_cache), one CUDA
+    graph per batch size; RTF = wall time / audio seconds.  Batch sizes are bounded (no max-fit search on a shared box)."""
     import torch
+    from tdvc import ops
     T = int(seconds * SR)
-    host = synth_batch(B, T, MODEL["nspk"], seed=4321)
-    x, cv = host["signal_real"].to(dev), host["c_f0_conv"].to(dev)
-    c_tgt = torch.zeros(B, MODEL["nspk"], device=dev).scatter_(1, host["label_tgt"].to(dev).view(-1, 1), 1.0)
+    rows = []
     side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    g = torch.cuda.CUDAGraph()
-    with torch.no_grad():
-        with torch.cuda.stream(side):
-            for _ in range(2):
-                G(x, c_tgt, c_var=cv)
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        with torch.cuda.graph(g):
-            y = G(x, c_tgt, c_var=cv)
-    g.replay()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        g.replay()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
-    audio = B * seconds
-    return {"rtf": round(ms / 1e3 / audio, 7), "x_realtime": round(audio / (ms / 1e3), 1), "batch": B,
-            "utterance_s": seconds, "ms_per_batch": round(ms, 3), "finite": bool(torch.isfinite(y).all()),
-            "gflop_per_audio_s": 51.95, "tflops_algorithmic": round(51.95 * audio / ms, 2)}
+    with torch.no_grad(), ops.inference_cache():
+        for B in batches:
+            host = synth_batch(B, T, MODEL["nspk"], seed=4321)
+            x, cv = host["signal_real"].to(dev), host["c_f0_conv"].to(dev)
+            c_tgt = torch.zeros(B, MODEL["nspk"], device=dev).scatter_(1, host["label_tgt"].to(dev).view(-1, 1), 1.0)
+            try:
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for _ in range(2):
+                        G(x, c_tgt, c_var=cv)
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    y = G(x, c_tgt, c_var=cv)
+                g.replay()
+                torch.cuda.synchronize()
+                reps = 5 if B <= 16 else 3
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    g.replay()
+                e1.record()
+                torch.cuda.synchronize()
+            except torch.OutOfMemoryError:
+                rows.append({"batch": B, "error": "out of memory"})
+                break
+            ms = e0.elapsed_time(e1) / reps
+            audio = B * seconds
+            rows.append({"batch": B, "ms_per_batch": round(ms, 3), "rtf": round(ms / 1e3 / audio, 8),
+                         "x_realtime": round(audio / (ms / 1e3), 1), "tflops_algorithmic": round(51.95 * audio / ms, 2),
+                         "finite": bool(torch.isfinite(y).all())})
+            del g, y, x, cv
+            torch.cuda.empty_cache()
+    best = max((r for r in rows if "x_realtime" in r), key=lambda r: r["x_realtime"])
+    return {"utterance_s": seconds, "gflop_per_audio_s": 51.95, "weight_norm": "folded once (ops.inference_cache)",
+            "sweep": rows, "best": best, "rtf": best["rtf"], "x_realtime": best["x_realtime"], "batch": best["batch"]}
 
 
-def cpu_baseline(steps, warmup, budget_s=30.0):
-    """The reference algorithm (CPU oracle port, fp32, all host threads) on a bounded sample of the same
-    workload: full G+D steps (forward, both backward passes, torch AdamW updates) at the largest batch
-    B in {16, 8, 4, 2} whose estimated cost fits `budget_s` seconds per step; audio-s/s = B*0.56 s / step time."""
+def cpu_baseline(steps, warmup, hp=None, batch=None):
+    """The reference algorithm (CPU oracle port, fp32, all host threads) on the SAME workload as the CUDA arm: full G+D
+    steps (forward, both backward passes, torch AdamW updates) at B = 16, T = 8960; audio-s/s = B*0.56 s / step time.
+    About 7 s per step on 16 cores, so the bounded sample is simply `steps` whole steps."""
     import torch
     from oracle.step import make_models, oracle_step, step_batch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    hp = dict(TRAIN)
+    hp = dict(hp if hp is not None else TRAIN)
     hp["faithful_waste"] = True      # the reference back-propagates the sub-scale heads into G in the D step
+    Bs = int(batch or TRAIN["batch_size"])
+    cfg = dict(MODEL, B=Bs, T=TRAIN["max_segment"], seed=6)
+    sdG, sdD = make_models(cfg, torch.float32)
+    for v in list(sdG.values()) + list(sdD.values()):
+        v.requires_grad_(True)
+    oG = torch.optim.AdamW(list(sdG.values()), TRAIN["lr"], TRAIN["betas"])
+    oD = torch.optim.AdamW(list(sdD.values()), TRAIN["lr"], TRAIN["betas"])
+    data = step_batch(cfg, hp, torch.float32)
 
-    def setup(Bs):
-        cfg = dict(MODEL, B=Bs, T=TRAIN["max_segment"], seed=6)
-        sdG, sdD = make_models(cfg, torch.float32)
-        for v in list(sdG.values()) + list(sdD.values()):
-            v.requires_grad_(True)
-        oG = torch.optim.AdamW(list(sdG.values()), TRAIN["lr"], TRAIN["betas"])
-        oD = torch.optim.AdamW(list(sdD.values()), TRAIN["lr"], TRAIN["betas"])
-        return cfg, sdG, sdD, oG, oD, step_batch(cfg, hp, torch.float32)
-
-    def one(state):
-        cfg, sdG, sdD, oG, oD, batch = state
-        out = oracle_step(cfg, hp, torch.float32, sdG, sdD, batch)
+    def one():
+        out = oracle_step(cfg, hp, torch.float32, sdG, sdD, data)
         for k, v in sdD.items():
             v.grad = out["D_grad"][k]
         for k, v in sdG.items():
             v.grad = out["G_grad"][k]
         oD.step(); oG.step()
 
-    st = setup(2)
-    t0 = time.perf_counter()
-    one(st)                                   # probe (also warms the thread pool / allocator)
-    t2 = time.perf_counter() - t0
-    Bs = 2
-    for cand in (16, 8, 4):
-        if t2 * cand / 2 * 0.7 <= budget_s:   # larger batches amortise better than linearly
-            Bs = cand
-            break
-    if Bs != 2:
-        st = setup(Bs)
     for _ in range(warmup):
-        one(st)
+        one()
     t0 = time.perf_counter()
     for _ in range(steps):
-        one(st)
+        one()
     dt = (time.perf_counter() - t0) / steps
     v = Bs * TRAIN["max_segment"] / SR / dt
     return {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{steps} full G+D step(s) (fwd, both bwd, AdamW) at B={Bs} of 16, T=8960, fp32, "
-                      f"{warmup} warm-up after a B=2 probe; {dt:.2f} s/step",
+            "sample": f"{steps} full G+D step(s) (fwd, both bwd, AdamW) at B={Bs}, T=8960, fp32, {warmup} warm-up; "
+                      f"{dt:.2f} s/step",
             "s_per_step": round(dt, 3), "batch": Bs}
 
 
 def run_reference(args):
-    """`--impl reference`: the reference's CPU implementation of the path (oracle port; the reference itself is
-    pure Python/PyTorch and cannot travel to the GPU box) on the host cores, same metric and config."""
+    """`--impl reference`: the reference's CPU implementation of the path on the host cores -- the oracle port
+    (`kind: "port"`): the reference itself is pure Python/PyTorch and /root/reference does not exist on the GPU box -- at
+    the CUDA arm's own workload (same config, B = 16 per step, same metric)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    conf = CONFIGS[args.config]
     steps = max(1, args.steps)
     warm = min(args.warmup, 1)
-    cb = cpu_baseline(steps=steps, warmup=warm, budget_s=max(4.0, 150.0 / (steps + warm)))
-    sample_B = cb["batch"]
+    cb = cpu_baseline(steps=steps, warmup=warm, hp=conf["train"])
     out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-           "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": round(cb["s_per_step"] * 1e3, 1),
+           "steps": args.steps, "warmup": warm, "ms_per_step": round(cb["s_per_step"] * 1e3, 1),
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-           "config": {"workload": WORKLOAD, "batch_per_gpu": sample_B, "segment_samples": TRAIN["max_segment"],
-                      "sample_rate": SR, "speakers": MODEL["nspk"],
+           "config": {"workload": conf["workload"], "name": args.config, "batch_per_gpu": cb["batch"],
+                      "segment_samples": TRAIN["max_segment"], "sample_rate": SR, "speakers": MODEL["nspk"],
                       "lambda_f0": "0 (torchcrepe unavailable offline, SURVEY 8c)", "precision": "fp32",
                       "device": f"host CPU, {cb['cores']} threads (rank 0 only; the GPUs are not used by this arm)",
-                      "sample": f"each step is one full G+D iteration at B={sample_B} of 16"},
+                      "sample": f"each step is one full G+D iteration at B={cb['batch']} (the CUDA arm's batch per GPU)"},
            "cpu_baseline": cb,
            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
@@ -493,6 +608,10 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("TDVC_PRECISION", "bf16"), choices=["fp32", "bf16"],
                     help="bf16 = tcgen05 tensor-core path (2e-2 parity, the headline); fp32 = exact CUDA-core path (1e-5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-inference", action="store_true", help="skip the BASELINE config 5 inference sweep")
+    ap.add_argument("--config", default="stage1", choices=sorted(CONFIGS),
+                    help="which shipped train config the step follows (BASELINE.json configs 1, 2, 4; the wavlm configs "
+                         "need the WavLM front end, which is outside this path: unmeasured)")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="launch every kernel from Python each step instead of replaying one CUDA graph")
     ap.add_argument("--branch-streams", type=int, default=int(os.environ.get("TDVC_BRANCH_STREAMS", "0")),

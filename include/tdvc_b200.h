@@ -45,6 +45,11 @@ const char* tdvc_last_error(void);
 int tdvc_version(void);
 /* kernels launched by this library in this process so far (bench.py reports the per-step delta) */
 int64_t tdvc_launch_count(void);
+/* 2 * multiply-accumulates handed to one kernel family by this process so far (operand channel padding included):
+ * 0 conv_tc_fwd_k (tcgen05, one tile per CTA), 1 conv_tc_ws_k (weight-stationary), 2 conv_tc_wt_k (stacked weights),
+ * 3 conv_tc_wgrad_k, 4 the fp32 CUDA-core conv kernels, 5 the fused MRF chain kernels.  bench.py divides the per-step
+ * deltas by each family's measured time. */
+double tdvc_flop_count(int family);
 /* 1 if the current device is sm_100 (tcgen05/TMEM/TMA paths usable), 0 otherwise, <0 on error */
 int tdvc_device_is_sm100(void);
 

@@ -28,6 +28,10 @@ void set_error(const char* fmt, ...);
 
 // every kernel launch in the library is followed by this macro: it also feeds tdvc_launch_count()
 extern unsigned long long g_launches;
+// multiply-accumulate work handed to each kernel family (2 * MACs, channel padding of the packed operands included):
+// bench.py divides the per-step deltas by the families' measured time.  See tdvc_flop_count().
+enum FlopFamily { FLOP_TC_TILE = 0, FLOP_TC_WS = 1, FLOP_TC_WT = 2, FLOP_TC_WGRAD = 3, FLOP_FP32 = 4, FLOP_TC_CHAIN = 5, FLOP_FAMILIES = 8 };
+extern double g_flops[FLOP_FAMILIES];
 #define TDVC_LAUNCH_CHECK()            \
   do {                                 \
     ++tdvc::g_launches;                \

@@ -196,10 +196,9 @@ static int launch_fwd_t(FwdP p, const float* x, const float* w, const float* bia
     if (gpb > 1 && smem_b <= budget) { p.gpb = gpb; smem = smem_b; }
   }
   TDVC_CHECK_ARG(smem <= 200 * 1024);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  // the attribute is per device: set on every launch that needs it (cheap) rather than once per process
+  if (smem > 48 * 1024) {
     TDVC_CUDA(cudaFuncSetAttribute(conv_fwd_k<CO_T, TX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = 200 * 1024;
   }
   dim3 grid(cdiv(p.Tout, TT), p.gpb > 1 ? cdiv(p.groups, p.gpb) : p.groups * cdiv(p.cout_g, COB), p.B);
   TDVC_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535);
@@ -211,6 +210,7 @@ static int launch_fwd_t(FwdP p, const float* x, const float* w, const float* bia
 static int launch_fwd(FwdP p, const float* x, const float* w, const float* bias, const float* res, float* y,
                       cudaStream_t st) {
   if (p.B == 0 || p.Tout <= 0) return TDVC_OK;
+  g_flops[FLOP_FP32] += 2.0 * p.B * p.Tout * (double)p.Cout * p.cin_g * p.K;
   const bool small_t = p.Tout <= 48;
   const int ty = small_t ? 32 : 8;
   const int tt = small_t ? 32 : 128;
@@ -368,6 +368,7 @@ static int launch_tr_t(TrP p, const float* in, const float* w, const float* bias
 
 static int launch_tr(TrP p, const float* in, const float* w, const float* bias, float* out, cudaStream_t st) {
   if (p.B == 0 || p.Tout <= 0) return TDVC_OK;
+  g_flops[FLOP_FP32] += 2.0 * p.B * p.Tin * (double)p.Cout * p.in_g * p.K;
   int oc_t = p.out_g <= 2 ? 1 : (p.out_g <= 4 ? 2 : (p.out_g <= 8 ? 4 : 8));
   auto n_ctas = [&](int c) { return (long long)cdiv(p.Tout, 128) * p.groups * cdiv(p.out_g, 2 * c) * p.B; };
   while (oc_t > 1 && n_ctas(oc_t) < 2 * num_sms()) oc_t >>= 1;
@@ -496,10 +497,9 @@ static int launch_wgrad_t(WgP p, const float* A, const float* Bm, float* out, cu
   p.nchunk = cdiv(p.Ta, TTW);
   size_t smem = ((size_t)CAB * TTW + (size_t)p.rows * p.span) * sizeof(float);
   TDVC_CHECK_ARG(smem <= 200 * 1024);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  // the attribute is per device: set on every launch that needs it (cheap) rather than once per process
+  if (smem > 48 * 1024) {
     TDVC_CUDA(cudaFuncSetAttribute(conv_wgrad_k<RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = 200 * 1024;
   }
   int gx = cdiv(p.jtot, JB), gy = p.groups * cdiv(p.ca_g, CAB);
   long long total = (long long)p.B * p.nchunk;
@@ -518,6 +518,7 @@ static int launch_wgrad_t(WgP p, const float* A, const float* Bm, float* out, cu
 static int launch_wgrad(WgP p, const float* A, const float* Bm, float* out, cudaStream_t st) {
   TDVC_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)p.Ca * p.cb_g * p.K, st));
   if (p.B == 0) return TDVC_OK;
+  g_flops[FLOP_FP32] += 2.0 * p.B * p.Ta * (double)p.Ca * p.cb_g * p.K;
   if (p.ca_g <= 16) return launch_wgrad_t<1>(p, A, Bm, out, st);
   return launch_wgrad_t<4>(p, A, Bm, out, st);
 }

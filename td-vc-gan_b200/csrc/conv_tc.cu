@@ -1484,6 +1484,7 @@ extern "C" int tdvc_conv1d_tc_fwd_ex(const tdvc_tc_conv* c, void* stream) {
       TDVC_CHECK_ARG(grid.y <= 65535);
       tdvc::launch_k(kern, grid, TC_FWD_THREADS, smem_ws, (cudaStream_t)stream, map_a, map_b, map_an, map_bn, p, w);
       TDVC_LAUNCH_CHECK();
+      g_flops[FLOP_TC_WS] += 2.0 * c->B * c->Tout * (double)c->groups * c->Cout_g * c->Cinp_g * c->K;
       return TDVC_OK;
     }
   }
@@ -1513,6 +1514,7 @@ extern "C" int tdvc_conv1d_tc_fwd_ex(const tdvc_tc_conv* c, void* stream) {
   TDVC_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535);
   tdvc::launch_k(kern, grid, TC_FWD_THREADS, smem, (cudaStream_t)stream, map_a, map_b, p);
   TDVC_LAUNCH_CHECK();
+  g_flops[FLOP_TC_TILE] += 2.0 * c->B * c->Tout * (double)c->groups * c->Cout_g * c->Cinp_g * c->K;
   return TDVC_OK;
 }
 
@@ -1620,6 +1622,7 @@ extern "C" int tdvc_conv1d_tc_fwd_stacked(const void* xp, const void* wp, const 
   }
   tdvc::launch_k(kern, w.m_tiles * w.ctas_per_m, TC_FWD_THREADS, smem, (cudaStream_t)stream, map_x, map_w, map_xn, map_wn, p, w);
   TDVC_LAUNCH_CHECK();
+  g_flops[FLOP_TC_WT] += 2.0 * B * Tout * (double)w.rows_total * Cinp * K;
   return TDVC_OK;
 }
 
@@ -1685,11 +1688,8 @@ extern "C" int tdvc_conv1d_tc_wgrad(const void* dyp, const void* xp, float* dw, 
   splits = std::min(splits, p.units);
   p.splits = splits;
   size_t smem = (size_t)stages * stage_bytes + (p.bias ? 2 * WG_BOX_BYTES : 0) + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
-  static bool configured = false;
-  if (!configured) {
-    TDVC_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
+  // per-device attribute: set on every call (cheap), not once per process
+  TDVC_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CUtensorMap map_x, map_dy;
   int rc = make_map_3d(&map_x, xp, (uint64_t)Cp, (uint64_t)Tp, (uint64_t)B, 64, 64);
   if (rc) return rc;
@@ -1698,6 +1698,7 @@ extern "C" int tdvc_conv1d_tc_wgrad(const void* dyp, const void* xp, float* dw, 
   TDVC_CHECK_ARG(gy <= 65535);
   tdvc::launch_k(conv_tc_wgrad_k, dim3(splits, gy), TC_THREADS, smem, st, map_x, map_dy, p);
   TDVC_LAUNCH_CHECK();
+  g_flops[FLOP_TC_WGRAD] += 2.0 * B * Tout * (double)Cout * Cin * K;
   long long n = (long long)Cout * Cin * K;
   int blocks = (int)std::min<long long>((n + 255) / 256, 4LL * num_sms());
   if (ws_is_zero) tdvc::launch_k(wgrad_finalize_zero_k, blocks, 256, 0, st, ws, dw, Cout, Cin, K, p.Np, p.Mp, db, p.bias);

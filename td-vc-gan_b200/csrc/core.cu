@@ -7,6 +7,7 @@
 namespace tdvc {
 static thread_local char g_err[512] = "";
 unsigned long long g_launches = 0;
+double g_flops[FLOP_FAMILIES] = {0, 0, 0, 0, 0, 0, 0, 0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -40,6 +41,9 @@ bool pdl_enabled() {
 extern "C" const char* tdvc_last_error(void) { return tdvc::g_err; }
 extern "C" int tdvc_version(void) { return 100; }
 extern "C" int64_t tdvc_launch_count(void) { return (int64_t)tdvc::g_launches; }
+extern "C" double tdvc_flop_count(int family) {
+  return (family >= 0 && family < tdvc::FLOP_FAMILIES) ? tdvc::g_flops[family] : -1.0;
+}
 extern "C" int tdvc_device_is_sm100(void) {
   int dev = 0, major = 0;
   TDVC_CUDA(cudaGetDevice(&dev));

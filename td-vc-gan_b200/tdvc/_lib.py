@@ -45,6 +45,7 @@ SIGNATURES = {
     "tdvc_last_error": (C.c_char_p, []),
     "tdvc_version": (_I, []),
     "tdvc_launch_count": (_L, []),
+    "tdvc_flop_count": (C.c_double, [_I]),
     "tdvc_device_is_sm100": (_I, []),
     "tdvc_weight_norm_fwd": (_I, [_P, _P, _P, _P, _I, _I, _P]),
     "tdvc_weight_norm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P]),

@@ -328,6 +328,14 @@ def step_cache(tag: str = "default") -> _StepCache:
     return _step_cache(tag)
 
 
+def inference_cache() -> _StepCache:
+    """`with torch.no_grad(), ops.inference_cache():` -- weight norm folded and the bf16 operands packed ONCE for every
+    forward inside the block (generate_with_target.py:105-120 loads a checkpoint and then only runs G.forward): the first
+    call normalises and packs, later calls -- and a CUDA graph captured inside the block -- launch neither.  The weights
+    must not change while the block is open."""
+    return _step_cache("inference")
+
+
 def weight_norm(v: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
     """w = g * v / ||v|| (norm over all dims but 0) -- torch.nn.utils.weight_norm's per-forward recompute."""
     if _step_cache.depth > 0:

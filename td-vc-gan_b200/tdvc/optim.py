@@ -68,7 +68,11 @@ class FusedAdamW(torch.optim.Optimizer):
                 st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
 
     def _table(self, gi, params, grads):
-        key = tuple((p.data_ptr(), g.data_ptr()) for p, g in zip(params, grads))
+        # keyed on every address the kernel will dereference (parameters, gradients -- 0 where a parameter has none, which
+        # the kernel skips like torch.optim.AdamW does -- and both moments)
+        self._ensure_state(params)
+        key = tuple((p.data_ptr(), g.data_ptr() if g is not None else 0, self.state[p]["exp_avg"].data_ptr(),
+                     self.state[p]["exp_avg_sq"].data_ptr()) for p, g in zip(params, grads))
         cached = self._tables.get(gi)
         if cached is not None and cached["key"] == key:
             return cached
@@ -76,18 +80,34 @@ class FusedAdamW(torch.optim.Optimizer):
             raise RuntimeError("FusedAdamW: pointer tables must exist before CUDA-graph capture "
                                "(call use_grad_bank() and run one eager step first)")
         dev = params[0].device
-        self._ensure_state(params)
         mk = lambda vals: torch.tensor(vals, dtype=torch.int64).to(dev)
         tab = dict(key=key,
-                   p=mk([p.data_ptr() for p in params]), g=mk([g.data_ptr() for g in grads]),
+                   p=mk([p.data_ptr() for p in params]), g=mk([g.data_ptr() if g is not None else 0 for g in grads]),
                    m=mk([self.state[p]["exp_avg"].data_ptr() for p in params]),
                    v=mk([self.state[p]["exp_avg_sq"].data_ptr() for p in params]),
                    n=mk([p.numel() for p in params]), max_n=max(p.numel() for p in params), count=len(params),
                    step=torch.zeros(1, device=dev, dtype=torch.float32))
         if cached is not None:
             tab["step"] = cached["step"]
+        elif gi in getattr(self, "_restored_steps", {}):
+            tab["step"].fill_(self._restored_steps.pop(gi))
         self._tables[gi] = tab
         return tab
+
+    # ------------------------------------------------------------------ checkpointing
+    def state_dict(self):
+        """torch's layout plus the device-side step counters (one per parameter group), so that bias correction
+        continues where it stopped."""
+        sd = super().state_dict()
+        sd["tdvc_steps"] = {gi: float(t["step"].item()) for gi, t in self._tables.items()}
+        return sd
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        steps = state_dict.pop("tdvc_steps", {})
+        super().load_state_dict(state_dict)
+        self._tables = {}                       # the moments were replaced: cached pointer tables are stale
+        self._restored_steps = {int(k): float(v) for k, v in steps.items()}
 
     @torch.no_grad()
     def step(self, closure=None, grad_scale: float = 1.0):
@@ -101,14 +121,17 @@ class FusedAdamW(torch.optim.Optimizer):
         self._gathered = False
         for gi, group in enumerate(self.param_groups):
             if self._banks is not None:
-                params, grads = self._banks[gi]["params"], self._banks[gi]["views"]
+                bank = self._banks[gi]
+                params = bank["params"]
+                # a parameter that received no gradient is skipped (null gradient pointer), as torch.optim.AdamW skips it
+                grads = [v if p.grad is not None else None for p, v in zip(params, bank["views"])]
             else:
                 params = [p for p in group["params"] if p.grad is not None]
                 grads = [p.grad for p in params]
             if not params:
                 continue
             for p, g in zip(params, grads):
-                if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and g.is_contiguous()):
+                if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and (g is None or g.is_contiguous())):
                     raise RuntimeError("FusedAdamW needs contiguous fp32 CUDA parameters and gradients")
             tab = self._table(gi, params, grads)
             b1, b2 = group["betas"]
