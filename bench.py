@@ -345,14 +345,24 @@ def kernel_families(replay, fam_gflop):
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     if not evs:
         return {"error": "no CUDA activities in the trace"}
+    # kernels run back to back in one stream; with programmatic dependent launch a kernel is resident (waiting in
+    # griddepcontrol.wait) while its predecessor still runs, so its CUPTI duration overlaps the predecessor's.  A kernel is
+    # charged the part of its interval that follows the end of everything before it: the charges add up to the busy span.
+    evs.sort(key=lambda e: e.time_range.start)
     busy, cnt = collections.Counter(), collections.Counter()
+    frontier = evs[0].time_range.start
+    idle = 0.0
     for e in evs:
         name = re.sub(r"\(.*", "", e.name)
         name = re.sub(r"^void ", "", name)[:60]
-        busy[name] += (e.time_range.end - e.time_range.start) / 1e3
+        st, en = e.time_range.start, e.time_range.end
+        if st > frontier:
+            idle += (st - frontier) / 1e3
+        busy[name] += max(0.0, en - max(st, frontier)) / 1e3
+        frontier = max(frontier, en)
         cnt[name] += 1
-    t0 = min(e.time_range.start for e in evs)
-    t1 = max(e.time_range.end for e in evs)
+    t0 = evs[0].time_range.start
+    t1 = frontier
     total = sum(busy.values())
     top = [{"kernel": k, "launches": cnt[k], "ms": round(v, 3), "share_of_busy": round(v / total, 4)}
            for k, v in sorted(busy.items(), key=lambda kv: -kv[1])[:24]]
@@ -369,7 +379,8 @@ def kernel_families(replay, fam_gflop):
         if fam_gflop is not None:
             d["gflop_per_step"] = round(fam_gflop[fam], 2)
             d["tflops"] = round(fam_gflop[fam] / d["ms"], 2) if d["ms"] > 0 else None
-    return {"span_ms": round((t1 - t0) / 1e3, 3), "busy_ms": round(total, 3), "activities": len(evs), "top": top,
+    return {"span_ms": round((t1 - t0) / 1e3, 3), "busy_ms": round(total, 3), "idle_ms": round(idle, 3),
+            "activities": len(evs), "top": top,
             "conv_families": [conv[k] for k in sorted(conv, key=lambda k: -conv[k]["ms"])]}
 
 

@@ -220,6 +220,10 @@ typedef struct tdvc_tc_conv {
   int32_t out_act; float out_slope;
   int32_t out_packed, tp_out, cp_out, out_halo, out_ch_off, out_ch_stride;
   int32_t tm, cm, mask_halo, mask_ch_off, mask_ch_stride; float mask_slope;
+  /* fp32 output layout: element (group g, batch b, channel n, step t) at g*y_grp_stride + b*y_b_stride + n*Tout + t.
+   * Both 0 = group-major [groups][B][Cout_g][Tout]; y_grp_stride = Cout_g*Tout, y_b_stride = groups*Cout_g*Tout is the
+   * ordinary NCW tensor [B][groups*Cout_g][Tout] of a grouped nn.Conv1d (model/discriminator.py:26-30). */
+  int64_t y_grp_stride, y_b_stride;
 } tdvc_tc_conv;
 int tdvc_conv1d_tc_fwd_ex(const tdvc_tc_conv* c, void* stream);
 
@@ -249,6 +253,37 @@ int tdvc_conv1d_tc_wgrad(const void* dyp, const void* xp, float* dw, float* ws, 
                          int ws_is_zero /* != 0: ws holds zeros on entry and is left zeroed on return (a persistent
                                            workspace: no memset per call); 0: ws is scratch, cleared here */,
                          void* stream);
+
+/* Weight gradients of up to 65535 independent conv groups in one tcgen05 launch (conv_tc2.cu):
+ *   dW_g[co, ci, tap] = sum_{b,t} dyp[b, t, dy_ch_off + g*dy_ch_stride + co] * xp[b, t + tap*dilation + t_off_g, x_ch_off + g*x_ch_stride + ci]
+ * dyp[B,Tout,Cdp], xp[B,Tp,Cp] bf16 channels-last.  per_group != 0 (ngroups <= 4): group g has kg[g] <= K taps, row offset
+ * t_off[g] and its own output tensors dw[g] ([Cout][Cin][kg[g]], OVERWRITTEN) / db[g] -- the three kernel sizes of an MRF
+ * depth (model/generator.py:175-194).  per_group == 0: K taps and t_off[0] for every group, outputs dw[0] + g*dw_grp_stride,
+ * db[0] + g*db_grp_stride.  frame_s > 0 (per_group == 0): the groups are bundles of `sub` conv groups of a
+ * Conv1d(k = kreal, stride = frame_s, groups) seen as a stride-1 conv over frames (xp from tdvc_frame_pack_bf16: Cin = sub *
+ * cin_conv_g * frame_s frame channels per bundle, Cout = sub * cout_conv_g); dw[0] is then that conv's own gradient
+ * [ngroups*Cout][cin_conv_g][kreal] and db[0] its [ngroups*Cout] bias gradient (model/discriminator.py:26-30).
+ * want_bias: also produce the bias gradients (sum over (b,t) of dyp), through one more accumulator fed by a tile of ones.
+ * ws: tdvc_conv1d_tc_wgrad2_ws(c) floats; ws_is_zero != 0: it holds zeros on entry and is left zeroed (persistent). */
+typedef struct tdvc_tc_wgrad2 {
+  const void* dyp; const void* xp; float* ws;
+  float* dw[4]; float* db[4];
+  int64_t dw_grp_stride, db_grp_stride;
+  int32_t B, Cdp, Tout, Cp, Tp, Cout, Cin, K, dilation;
+  int32_t ngroups, per_group, x_ch_off, x_ch_stride, dy_ch_off, dy_ch_stride;
+  int32_t kg[4], t_off[4];
+  int32_t want_bias, ws_is_zero;
+  int32_t haloed;      /* -1 default; 1: one haloed x tile per time unit, taps = row-shifted views; 0: one copy per tap */
+  int32_t frame_s, kreal, cin_conv_g, sub;
+} tdvc_tc_wgrad2;
+int64_t tdvc_conv1d_tc_wgrad2_ws(const tdvc_tc_wgrad2* c);
+int tdvc_conv1d_tc_wgrad2(const tdvc_tc_wgrad2* c, void* stream);
+
+/* Channel-major frame view of a signal for the grouped strided convs (model/discriminator.py:26-30, k = 41, stride 4):
+ * xf[b, q, c*s + p] = x[b, c, s*q + p - pad] (bf16 channels-last, 0 outside the signal), q < Tq; and its inverse for the
+ * data gradient: dx[b, c, u] = dxf[b, c*s + p, q] with s*q + p = u + pad, dxf fp32 [B, C*s, Tq]. */
+int tdvc_frame_pack_bf16(const float* x, void* xf, int B, int C, int T, int s, int pad, int Tq, void* stream);
+int tdvc_frame_unpack(const float* dxf, float* dx, int B, int C, int T, int s, int pad, int Tq, void* stream);
 
 #ifdef __cplusplus
 }

@@ -18,119 +18,9 @@
 // the remaining warps (16 in the forward kernels, 4 in wgrad) = epilogue: tcgen05.ld -> bias / FiLM / residual /
 // activation / LeakyReLU mask -> NCW fp32 stores (a TMEM lane is a time step: for a fixed channel a warp writes 32
 // consecutive floats) or the next conv's packed bf16 operand.
-#include <cuda.h>
-#include <cuda_bf16.h>
-#include <algorithm>
-#include <cstdlib>
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace tdvc {
-
-// ------------------------------------------------------------------------------------------ PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t"
-      "}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
-      : "memory");
-}
-// same MMA with the descriptors given as (lo, hi) 32-bit halves: the issuing thread only does 32-bit adds on `lo`
-__device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                               uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      ".reg .b64 da, db;\n\t"
-      "mov.b64 da, {%1, %2};\n\t"
-      "mov.b64 db, {%3, %4};\n\t"
-      "setp.ne.b32 p, %6, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 128-byte rows,
-// 8-row (1024 B) swizzle atoms stacked along M/N -> SBO = 1024 B; LBO unused (1); version 1; layout 2.
-__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-
-// One lane of a converged warp (elect.sync).  Unlike `lane == 0`, the compiler knows the guarded region runs on exactly one
-// lane of a converged warp, so warp-uniform operands of tcgen05.mma / TMA go to uniform registers without the
-// elect-broadcast-retry loop it otherwise wraps around every such instruction (~100 cycles per MMA, measured).
-__device__ __forceinline__ uint32_t elect_one() {
-  uint32_t pred = 0;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred px;\n\t"
-      "elect.sync _|px, 0xffffffff;\n\t"
-      "@px mov.s32 %0, 1;\n\t"
-      "}"
-      : "+r"(pred));
-  return pred;
-}
 
 struct TcP {
   int B, Tout, Cout, K, dil, t_off;          // Cout = valid output channels per group
@@ -149,6 +39,7 @@ struct TcP {
   const __nv_bfloat16* maskp;                 // MASK == 1: packed activated tensor whose sign gates the result
   int tm, cm, mask_halo, mask_ch_off, mask_ch_stride;
   float mask_slope;
+  long long y_grp_stride, y_b_stride;         // fp32 output: g*y_grp_stride + b*y_b_stride + n*Tout + t
 };
 
 constexpr int TC_BM = 128;
@@ -198,7 +89,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcP& p, const float* bias
           }
         }
         if (OUT == 0) {
-          const long long base = (((long long)grp * p.B + b) * p.Cout + n0 + c0) * ct + t;
+          const long long base = (long long)grp * p.y_grp_stride + (long long)b * p.y_b_stride + (long long)(n0 + c0) * ct + t;
           float* yp = p.y + base;
           const float* rp = p.res + base;                                   // only dereferenced when EPI asks for it
           const float* gp = p.gb + ((long long)b * 2 * p.Cout + n0 + c0) * ct + t;
@@ -949,18 +840,6 @@ struct WgTcP {
 
 constexpr int WG_BOX_BYTES = 64 * 64 * 2;   // 64 time rows x 64 channels bf16
 
-// MN-major SWIZZLE_128B descriptor: 64-channel (128 B) rows, 8-row K atoms 1024 B apart (SBO), 64-channel MN
-// atoms `lbo` bytes apart (LBO).
-__device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-
 __global__ void __launch_bounds__(TC_THREADS) conv_tc_wgrad_k(const __grid_constant__ CUtensorMap map_x,
                                                               const __grid_constant__ CUtensorMap map_dy, WgTcP p) {
   pdl_prologue();
@@ -1261,38 +1140,6 @@ __global__ void pack_weight_multi_k(const long long* __restrict__ jobs, const fl
   }
 }
 
-// ------------------------------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)sym;
-  }
-  return fn;
-}
-
-static int make_map_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0, uint32_t box1,
-                       CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return TDVC_ERR_CUDA; }
-  cuuint64_t dims[3] = {d0, d1, d2};
-  cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
-  cuuint32_t box[3] = {box0, box1, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return TDVC_ERR_CUDA; }
-  return TDVC_OK;
-}
-
 }  // namespace tdvc
 using namespace tdvc;
 
@@ -1404,6 +1251,12 @@ extern "C" int tdvc_conv1d_tc_fwd_ex(const tdvc_tc_conv* c, void* stream) {
   p.out_ch_off = c->out_ch_off; p.out_ch_stride = c->out_ch_stride;
   p.maskp = (const __nv_bfloat16*)c->maskp; p.tm = c->tm; p.cm = c->cm; p.mask_halo = c->mask_halo;
   p.mask_ch_off = c->mask_ch_off; p.mask_ch_stride = c->mask_ch_stride; p.mask_slope = c->mask_slope;
+  if (c->y_grp_stride == 0 && c->y_b_stride == 0) {      // default: group-major [groups][B][Cout_g][Tout]
+    p.y_grp_stride = (long long)c->B * c->Cout_g * c->Tout;
+    p.y_b_stride = (long long)c->Cout_g * c->Tout;
+  } else {
+    p.y_grp_stride = c->y_grp_stride; p.y_b_stride = c->y_b_stride;
+  }
   {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("TDVC_TC_DEBUG"); dbg = e ? atoi(e) : 0; }

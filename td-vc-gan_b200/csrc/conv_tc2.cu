@@ -1,0 +1,448 @@
+// Second generation of the tcgen05 weight-gradient kernel, and the frame-view pack / unpack kernels of the
+// discriminators' grouped strided convolutions.
+//
+// conv_tc_wgrad2_k -- dW[g][tap][co][ci] = sum_{b,t} dy[b, t, dy_off_g + co] * x[b, t + tap*dil + t_off_g, x_off_g + ci]
+//   for up to thousands of independent groups in ONE launch (grid.z = group):
+//     * the 3 kernel-size branches of an MRF depth (k = 3 / 7 / 11 at the same dilation: per-group tap count and offset),
+//     * the 4 ... 256 conv groups of a discriminator layer in frame view (uniform groups),
+//     * a plain conv (one group).
+//   GEMM per (group, tap): M = ci (TMEM lanes), N = co (TMEM columns, one accumulator per tap), K = time.  Both operands are
+//   MN-major (channel-contiguous) SWIZZLE_128B views of the packed bf16 channels-last tensors the forward / data-gradient
+//   kernels already use.  What is new against conv_tc_wgrad_k:
+//     * the x tile of a 64-step time unit is loaded ONCE with its (KT-1)*dil halo rows and every tap is a row-shifted view
+//       of it (the 128-byte swizzle is a function of the absolute shared-memory address, so a start address moved by whole
+//       128-byte rows needs no descriptor fix-up) -- the first kernel loaded one shifted copy per tap: 11 x the bytes for
+//       k = 11, and a single-stage pipeline because 11 copies filled the shared memory;
+//     * only the 64-channel boxes that hold real channels are loaded (Cin <= 64: one box instead of two);
+//     * groups share a launch, so a 16-channel layer no longer costs one launch + one finalize per conv.
+//   Split-K over (batch, 64-step chunk) with lane-coalesced fp32 reductions into an always-zero workspace, as before;
+//   wgrad2_finalize_k moves the sums into the weight-gradient tensors (plain [Cout][Cin][K] per group, or the
+//   discriminator's [Cout][Cin/groups][41] through the frame mapping) and re-zeroes what it read.
+#include "tc_common.cuh"
+
+namespace tdvc {
+
+constexpr int W2_THREADS = 192;        // TMA warp, MMA warp, 4 epilogue warps
+constexpr int W2_TK = 64;              // time steps per unit
+constexpr int W2_BOX = 64 * 128;       // 64 rows x 64 channels bf16
+constexpr int W2_MAXG = 4;             // groups with individual tap counts / offsets / output tensors
+
+struct Wg2P {
+  int B, Tout, Cout, Cin, K, dil;
+  int ngroups, per_group;
+  int x_ch_off, x_ch_stride, dy_ch_off, dy_ch_stride;
+  int kg[W2_MAXG], toff[W2_MAXG];
+  int NT, n_ntiles, KT, ntap_groups, nb_dy, nb_x, rows_x, haloed;
+  int stages, tmem_cols, nchunk_t, units, splits;
+  int Mp, Np;
+  long long ws_grp_stride;
+  float* ws;
+  int bias;
+};
+
+__global__ void __launch_bounds__(W2_THREADS) conv_tc_wgrad2_k(const __grid_constant__ CUtensorMap map_x,
+                                                               const __grid_constant__ CUtensorMap map_dy, Wg2P p) {
+  pdl_prologue();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // stage = [x: two 64-channel boxes (haloed: rows_x rows each; per tap: KT pairs of 64 rows)] [dy: nb_dy boxes of 64 rows]
+  const int x_box = (p.haloed ? p.rows_x : W2_TK) * 128;
+  const int x_bytes = (p.haloed ? 1 : p.KT) * 2 * x_box;
+  const int dy_bytes = p.nb_dy * W2_BOX;
+  const int stage_bytes = x_bytes + dy_bytes;
+  uint8_t* ones = smem + (size_t)p.stages * stage_bytes;             // 2 x 64 x 64 bf16 of 1.0 (bias row), when p.bias
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ones + (p.bias ? 2 * W2_BOX : 0));
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tmem_full_bar = empty_bar + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.z;
+  int yy = blockIdx.y;
+  const int nt_i = yy % p.n_ntiles; yy /= p.n_ntiles;
+  const int tg = yy % p.ntap_groups;
+  const int mt = yy / p.ntap_groups;
+  const int ci0 = mt * 128, n0 = nt_i * p.NT, tap0 = tg * p.KT;
+  const int gi = p.per_group ? g : 0;
+  const int kgrp = p.per_group ? p.kg[gi] : p.K;
+  const int t_off = p.toff[gi];
+  const int ntaps = min(p.KT, kgrp - tap0);
+  const int split = blockIdx.x;
+  const int my_units = ntaps > 0 ? (p.units - split + p.splits - 1) / p.splits : 0;
+  const bool do_bias = p.bias && mt == 0 && tg == 0;
+  const int xc = p.x_ch_off + g * p.x_ch_stride + ci0;
+  const int dc = p.dy_ch_off + g * p.dy_ch_stride + n0;
+  // real 64-channel boxes of this CTA's 128-lane ci tile
+  const int nbx = min(p.nb_x, (p.Cin - ci0 + 63) / 64);
+  if (do_bias) {
+    uint32_t* o32 = reinterpret_cast<uint32_t*>(ones);
+    for (int i = threadIdx.x; i < 2 * W2_BOX / 4; i += W2_THREADS) o32[i] = 0x3F803F80u;      // bf16 1.0 pairs
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dy) : "memory");
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (my_units > 0) {
+    if (warp == 0) {
+      if (elect_one()) {
+        const uint32_t tx = (uint32_t)((p.haloed ? nbx : ntaps * nbx) * x_box + dy_bytes);
+        for (int it = 0; it < my_units; ++it) {
+          const int u = split + it * p.splits;
+          const int b = u / p.nchunk_t, tc = (u - b * p.nchunk_t) * W2_TK;
+          const int s = it % p.stages;
+          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* sx = smem + (size_t)s * stage_bytes;
+          mbar_expect_tx(&full_bar[s], tx);
+          if (p.haloed) {
+            const int row0 = tc + tap0 * p.dil + t_off;
+            for (int j = 0; j < nbx; ++j) tma_load_3d(sx + j * x_box, &map_x, &full_bar[s], xc + 64 * j, row0, b);
+          } else {
+            for (int tp = 0; tp < ntaps; ++tp)
+              for (int j = 0; j < nbx; ++j)
+                tma_load_3d(sx + (tp * 2 + j) * x_box, &map_x, &full_bar[s], xc + 64 * j, tc + (tap0 + tp) * p.dil + t_off, b);
+          }
+          for (int j = 0; j < p.nb_dy; ++j)
+            tma_load_3d(sx + x_bytes + j * W2_BOX, &map_dy, &full_bar[s], dc + 64 * j, tc, b);
+        }
+      }
+    } else if (warp == 1) {
+      // D = f32, A = B = bf16, both MN-major (bits 15, 16), N = NT, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      for (int it = 0; it < my_units; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t s_addr = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t b_addr = s_addr + x_bytes;
+          for (int tp = 0; tp < ntaps; ++tp) {
+            // haloed: tap tp = the tile moved down by tp*dil rows; per tap: its own pair of boxes
+            const uint32_t a_addr = p.haloed ? s_addr + (uint32_t)(tp * p.dil) * 128u : s_addr + (uint32_t)(tp * 2 * x_box);
+            for (int k = 0; k < W2_TK / 16; ++k) {      // 16 time rows = 2048 B per MMA
+              const uint64_t da = make_sw128_mnmajor_desc(a_addr + k * 2048, (uint32_t)x_box);
+              const uint64_t db = make_sw128_mnmajor_desc(b_addr + k * 2048, W2_BOX);
+              umma_bf16(tmem_base + (uint32_t)(tp * p.NT), da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+          if (do_bias) {
+            const uint32_t o_addr = smem_u32(ones);
+            for (int k = 0; k < W2_TK / 16; ++k) {
+              const uint64_t da = make_sw128_mnmajor_desc(o_addr + k * 2048, W2_BOX);
+              const uint64_t db = make_sw128_mnmajor_desc(b_addr + k * 2048, W2_BOX);
+              umma_bf16(tmem_base + (uint32_t)(p.KT * p.NT), da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[s]);
+          if (it == my_units - 1) umma_commit(tmem_full_bar);
+        }
+        __syncwarp();
+      }
+    } else {
+      const int q = warp & 3;
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+      const int ci = ci0 + q * 32 + lane;
+      const bool row_ok = ci < p.Cin;
+      const int nvalid = min(p.NT, p.Cout - n0);
+      float* wsg = p.ws + (long long)g * p.ws_grp_stride;
+      // lanes of warps whose 32 ci are all padding have nothing to add
+      if (ci0 + q * 32 < p.Cin) {
+        for (int tp = 0; tp < ntaps; ++tp) {
+          float* wrow = wsg + ((long long)(tap0 + tp) * p.Np + n0) * p.Mp + ci;
+          for (int c0 = 0; c0 < nvalid; c0 += 16) {
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tp * p.NT + c0), v);
+            if (row_ok) {
+              const int nj = min(16, nvalid - c0);
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < nj) atomicAdd(wrow + (long long)(c0 + j) * p.Mp, v[j]);
+            }
+          }
+        }
+      }
+      if (do_bias && q == 0) {
+        // every lane of accumulator KT holds the column sums; lane j of the warp adds column c0 + j
+        float* brow = wsg + (long long)p.K * p.Np * p.Mp + n0;
+        for (int c0 = 0; c0 < nvalid; c0 += 16) {
+          float v[16];
+          tmem_ld16(tmem_base + (uint32_t)(p.KT * p.NT + c0), v);
+          float mine = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) mine = (lane == j) ? v[j] : mine;
+          if (lane < min(16, nvalid - c0)) atomicAdd(brow + c0 + lane, mine);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ws[g][tap][co][ci] (+ bias row) -> the weight-gradient tensors; what is read is written back as zero, so a persistent
+// workspace needs no memset per call.
+struct Fin2P {
+  float* ws;
+  long long ws_grp_stride;
+  int ngroups, Np, Mp, Cout, Cin, K, bias, per_group;
+  float* dw[W2_MAXG];        // plain mode: dw of group g = [Cout][Cin][kg[g]]  (per_group) or dw[0] + g * dw_grp_stride
+  float* db[W2_MAXG];
+  int kg[W2_MAXG];
+  long long dw_grp_stride, db_grp_stride;
+  // frame mode (frame_s > 0): the groups are bundles of `sub` conv groups of a Conv1d(k = kreal, stride = frame_s) seen as a
+  // stride-1 conv over frames; ci = (local conv group, input channel c, phase p), tap = frame j, k = j * frame_s + p;
+  // dw[0] is the conv's own [Cout_total][cin_conv_g][kreal] gradient, db[0] its bias gradient
+  int frame_s, kreal, cin_conv_g, sub;
+};
+
+__global__ void wgrad2_finalize_k(Fin2P f) {
+  pdl_prologue();
+  const int g = blockIdx.y;
+  float* wsg = f.ws + (long long)g * f.ws_grp_stride;
+  const int gi = f.per_group ? g : 0;
+  const int kg = f.per_group ? f.kg[gi] : f.K;
+  const long long n = (long long)kg * f.Cout * f.Cin;
+  float* dwg = f.per_group ? f.dw[gi] : (f.dw[0] ? f.dw[0] + (long long)g * f.dw_grp_stride : nullptr);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % f.Cin);
+    const long long r = i / f.Cin;
+    const int co = (int)(r % f.Cout), tap = (int)(r / f.Cout);
+    float* src = wsg + ((long long)tap * f.Np + co) * f.Mp + ci;
+    const float v = *src;
+    *src = 0.f;
+    if (f.frame_s > 0) {
+      const int cin_b = f.Cin / f.sub, cout_b = f.Cout / f.sub;      // per conv group inside the bundle
+      if (co / cout_b != ci / cin_b) continue;                      // off-diagonal block of the bundle: not a weight
+      const int cl = ci % cin_b;
+      const int c = cl / f.frame_s, ph = cl % f.frame_s;
+      const int k = tap * f.frame_s + ph;
+      if (k < f.kreal && f.dw[0])
+        f.dw[0][(((long long)g * f.Cout + co) * f.cin_conv_g + c) * f.kreal + k] = v;
+    } else if (dwg) {
+      dwg[((long long)co * f.Cin + ci) * kg + tap] = v;
+    }
+  }
+  if (f.bias && blockIdx.x == 0) {
+    float* brow = wsg + (long long)f.K * f.Np * f.Mp;
+    float* dbg = f.frame_s > 0 ? (f.db[0] ? f.db[0] + (long long)g * f.Cout : nullptr)
+                               : (f.per_group ? f.db[gi] : (f.db[0] ? f.db[0] + (long long)g * f.db_grp_stride : nullptr));
+    for (int i = threadIdx.x; i < f.Cout; i += blockDim.x) {
+      if (dbg) dbg[i] = brow[i];
+      brow[i] = 0.f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ frame view (channel-major)
+// x[B, C, T] fp32 NCW -> xf[B, Tq, C*s] bf16 channels-last frames, xf[b, q, c*s + p] = x[b, c, s*q + p - pad] (0 outside the
+// signal): the operand of a Conv1d(k, stride = s, groups) run as a stride-1 grouped convolution over frames -- in this
+// order the s*cin_g frame channels of a conv group are contiguous.  A block moves 32 channels x 32 frames.
+template <int S>
+__global__ void __launch_bounds__(256) frame_pack_k(const float* __restrict__ x, __nv_bfloat16* __restrict__ xf, int C, int T,
+                                                    int pad, int Tq) {
+  pdl_prologue();
+  __shared__ float tile[32][32 * S + 1];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, q0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int u0 = q0 * S - pad;
+  for (int cy = wrp; cy < 32; cy += 8) {
+    const int c = c0 + cy;
+    const float* row = x + ((long long)b * C + c) * T;
+#pragma unroll
+    for (int l = 0; l < S; ++l) {
+      const int u = u0 + lane + 32 * l;
+      tile[cy][lane + 32 * l] = (c < C && u >= 0 && u < T) ? __ldg(row + u) : 0.f;
+    }
+  }
+  __syncthreads();
+  const int c = c0 + lane;
+  for (int qy = wrp; qy < 32; qy += 8) {
+    const int q = q0 + qy;
+    if (q >= Tq || c >= C) continue;
+    __nv_bfloat16* dst = xf + ((long long)b * Tq + q) * ((long long)C * S) + (long long)c * S;
+    if (S == 4) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(tile[lane][qy * 4], tile[lane][qy * 4 + 1]);
+      __nv_bfloat162 d = __floats2bfloat162_rn(tile[lane][qy * 4 + 2], tile[lane][qy * 4 + 3]);
+      uint2 w;
+      w.x = *reinterpret_cast<uint32_t*>(&a);
+      w.y = *reinterpret_cast<uint32_t*>(&d);
+      *reinterpret_cast<uint2*>(dst) = w;
+    } else if (S == 2) {
+      *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(tile[lane][qy * 2], tile[lane][qy * 2 + 1]);
+    } else {
+#pragma unroll
+      for (int pp = 0; pp < S; ++pp) dst[pp] = __float2bfloat16(tile[lane][qy * S + pp]);
+    }
+  }
+}
+
+// the inverse view for gradients: dx[b, c, u] = dxf[b, c*s + p, q] with s*q + p = u + pad; dxf is fp32 NCW over frames
+// [B, C*s, Tq] (what the data-gradient conv writes)
+__global__ void frame_unpack_k(const float* __restrict__ dxf, float* __restrict__ dx, int C, int T, int s, int pad, int Tq) {
+  pdl_prologue();
+  const int b = blockIdx.z, c = blockIdx.y;
+  const float* src = dxf + ((long long)b * C + c) * s * Tq;
+  float* dst = dx + ((long long)b * C + c) * T;
+  for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < T; u += gridDim.x * blockDim.x) {
+    const int v = u + pad;
+    const int q = v / s, ph = v - q * s;
+    dst[u] = q < Tq ? __ldg(src + (long long)ph * Tq + q) : 0.f;
+  }
+}
+
+}  // namespace tdvc
+using namespace tdvc;
+
+extern "C" int tdvc_frame_pack_bf16(const float* x, void* xf, int B, int C, int T, int s, int pad, int Tq, void* stream) {
+  TDVC_CHECK_ARG(x && xf && B >= 0 && C > 0 && T > 0 && pad >= 0 && Tq > 0 && (s == 1 || s == 2 || s == 4 || s == 8));
+  TDVC_CHECK_ARG(((long long)C * s) % 8 == 0 && ((uintptr_t)xf % 16) == 0);
+  if (B == 0) return TDVC_OK;
+  dim3 grid(cdiv(Tq, 32), cdiv(C, 32), B);
+  TDVC_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535);
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* o = (__nv_bfloat16*)xf;
+  switch (s) {
+    case 1: tdvc::launch_k(frame_pack_k<1>, grid, 256, 0, st, x, o, C, T, pad, Tq); break;
+    case 2: tdvc::launch_k(frame_pack_k<2>, grid, 256, 0, st, x, o, C, T, pad, Tq); break;
+    case 4: tdvc::launch_k(frame_pack_k<4>, grid, 256, 0, st, x, o, C, T, pad, Tq); break;
+    default: tdvc::launch_k(frame_pack_k<8>, grid, 256, 0, st, x, o, C, T, pad, Tq); break;
+  }
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_frame_unpack(const float* dxf, float* dx, int B, int C, int T, int s, int pad, int Tq, void* stream) {
+  TDVC_CHECK_ARG(dxf && dx && B >= 0 && C > 0 && T > 0 && s >= 1 && pad >= 0 && Tq > 0 && C <= 65535 && B <= 65535);
+  if (B == 0) return TDVC_OK;
+  tdvc::launch_k(frame_unpack_k, dim3(std::min(cdiv(T, 256), 64), C, B), 256, 0, (cudaStream_t)stream, dxf, dx, C, T, s, pad, Tq);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+extern "C" int64_t tdvc_conv1d_tc_wgrad2_ws(const tdvc_tc_wgrad2* c) {
+  if (!c) return 0;
+  const long long Mp = (long long)((c->Cin + 31) / 32) * 32, Np = (long long)((c->Cout + 15) / 16) * 16;
+  return (int64_t)c->ngroups * ((long long)c->K * Np * Mp + Np);
+}
+
+extern "C" int tdvc_conv1d_tc_wgrad2(const tdvc_tc_wgrad2* c, void* stream) {
+  TDVC_CHECK_ARG(c && c->dyp && c->xp && c->ws && c->B >= 0 && c->Tout > 0 && c->Tp > 0 && c->K > 0 && c->dilation > 0);
+  TDVC_CHECK_ARG(c->Cdp % 8 == 0 && c->Cp % 8 == 0 && c->ngroups >= 1 && c->ngroups <= 65535 && c->Cin > 0 && c->Cout > 0);
+  TDVC_CHECK_ARG(c->x_ch_off >= 0 && c->dy_ch_off >= 0 && c->x_ch_stride >= 0 && c->dy_ch_stride >= 0);
+  TDVC_CHECK_ARG(c->x_ch_off + (long long)(c->ngroups - 1) * c->x_ch_stride + c->Cin <= c->Cp);
+  TDVC_CHECK_ARG(c->dy_ch_off + (long long)(c->ngroups - 1) * c->dy_ch_stride + c->Cout <= c->Cdp);
+  TDVC_CHECK_ARG(((uintptr_t)c->xp % 16 == 0) && ((uintptr_t)c->dyp % 16 == 0));
+  const bool per_group = c->per_group != 0;
+  if (per_group) {
+    TDVC_CHECK_ARG(c->ngroups <= W2_MAXG);
+    for (int g = 0; g < c->ngroups; ++g) TDVC_CHECK_ARG(c->kg[g] >= 1 && c->kg[g] <= c->K);
+  }
+  if (c->frame_s > 0) {
+    TDVC_CHECK_ARG(!per_group && c->sub >= 1 && c->Cin % c->sub == 0 && c->Cout % c->sub == 0 && c->cin_conv_g >= 1 &&
+                   (c->Cin / c->sub) == c->cin_conv_g * c->frame_s && c->kreal >= 1 && c->kreal <= c->K * c->frame_s);
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  Wg2P p{};
+  p.B = c->B; p.Tout = c->Tout; p.Cout = c->Cout; p.Cin = c->Cin; p.K = c->K; p.dil = c->dilation;
+  p.ngroups = c->ngroups; p.per_group = per_group ? 1 : 0;
+  p.x_ch_off = c->x_ch_off; p.x_ch_stride = c->x_ch_stride; p.dy_ch_off = c->dy_ch_off; p.dy_ch_stride = c->dy_ch_stride;
+  for (int g = 0; g < W2_MAXG; ++g) { p.kg[g] = per_group ? c->kg[g] : c->K; p.toff[g] = per_group ? c->t_off[g] : c->t_off[0]; }
+  p.Mp = ((c->Cin + 31) / 32) * 32;
+  p.Np = ((c->Cout + 15) / 16) * 16;
+  p.ws = c->ws;
+  p.ws_grp_stride = (long long)c->K * p.Np * p.Mp + p.Np;
+  p.bias = c->want_bias ? 1 : 0;
+  const size_t ws_floats = (size_t)c->ngroups * (size_t)p.ws_grp_stride;
+  if (!c->ws_is_zero) TDVC_CUDA(cudaMemsetAsync(c->ws, 0, sizeof(float) * ws_floats, st));
+  {
+    static int h = -1;      // TDVC_WGRAD2_HALOED=0: one shifted copy of the x tile per tap (development / A-B switch)
+    if (h < 0) { const char* e = getenv("TDVC_WGRAD2_HALOED"); h = e ? atoi(e) : 1; }
+    p.haloed = c->haloed >= 0 ? c->haloed : h;
+  }
+  const int xt = p.bias;
+  p.nb_x = std::min(2, cdiv(c->Cin, 64));
+  // co tile / taps per CTA: as many taps as possible share the 512 TMEM columns (the x tile is then loaded once for all of them)
+  int best_nt = 16, best_kt = 1, best_cost = 1 << 30;
+  const long long budget = 200 * 1024;
+  for (int cand = std::min(p.Np, 256); cand >= 16; cand -= 16) {
+    int kt = std::min(c->K, 512 / cand - xt);
+    while (kt >= 1) {
+      const int rows_x = ((W2_TK + (kt - 1) * c->dilation + 7) / 8) * 8;
+      const long long xb = p.haloed ? 2LL * rows_x * 128 : (long long)kt * 2 * W2_BOX;
+      if (rows_x <= 256 && 2 * (xb + (long long)cdiv(cand, 64) * W2_BOX) <= budget) break;
+      --kt;
+    }
+    if (kt < 1) continue;
+    const int cost = cdiv(c->K, kt) * cdiv(p.Np, cand);
+    if (cost < best_cost) { best_cost = cost; best_nt = cand; best_kt = kt; }
+  }
+  TDVC_CHECK_ARG(best_cost < (1 << 30));
+  p.NT = best_nt; p.KT = best_kt;
+  p.ntap_groups = cdiv(c->K, p.KT);
+  p.n_ntiles = cdiv(p.Np, p.NT);
+  p.nb_dy = cdiv(p.NT, 64);
+  p.rows_x = ((W2_TK + (p.KT - 1) * c->dilation + 7) / 8) * 8;
+  int cols = 32;
+  while (cols < (p.KT + xt) * p.NT) cols <<= 1;
+  TDVC_CHECK_ARG(cols <= 512);
+  p.tmem_cols = cols;
+  const long long x_bytes = p.haloed ? 2LL * p.rows_x * 128 : (long long)p.KT * 2 * W2_BOX;
+  const long long stage_bytes = x_bytes + (long long)p.nb_dy * W2_BOX;
+  p.nchunk_t = cdiv(c->Tout, W2_TK);
+  p.units = c->B * p.nchunk_t;
+  int stages = (int)std::min<long long>(4, budget / stage_bytes);
+  TDVC_CHECK_ARG(stages >= 1);
+  stages = std::min(stages, std::max(1, p.units));
+  p.stages = stages;
+  const int m_tiles = cdiv(c->Cin, 128);
+  const int gy = m_tiles * p.ntap_groups * p.n_ntiles;
+  TDVC_CHECK_ARG(gy <= 65535);
+  if (c->B > 0) {
+    // split the time units so that the launch fills the machine about twice; one CTA reduces >= 4 units when it can
+    long long ctas_fixed = (long long)gy * c->ngroups;
+    int splits = (int)std::max<long long>(1, (2LL * num_sms() + ctas_fixed - 1) / ctas_fixed);
+    splits = std::min(splits, std::max(1, p.units / 4));
+    splits = std::min(splits, p.units);
+    p.splits = std::max(1, splits);
+    const size_t smem = (size_t)stages * stage_bytes + (p.bias ? 2 * W2_BOX : 0) + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
+    TDVC_CUDA(cudaFuncSetAttribute(conv_tc_wgrad2_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUtensorMap map_x, map_dy;
+    int rc = make_map_3d(&map_x, c->xp, (uint64_t)c->Cp, (uint64_t)c->Tp, (uint64_t)c->B, 64, (uint32_t)(p.haloed ? p.rows_x : W2_TK));
+    if (rc) return rc;
+    rc = make_map_3d(&map_dy, c->dyp, (uint64_t)c->Cdp, (uint64_t)c->Tout, (uint64_t)c->B, 64, W2_TK);
+    if (rc) return rc;
+    tdvc::launch_k(conv_tc_wgrad2_k, dim3(p.splits, gy, c->ngroups), W2_THREADS, smem, st, map_x, map_dy, p);
+    TDVC_LAUNCH_CHECK();
+    double taps = 0;
+    for (int g = 0; g < c->ngroups; ++g) taps += per_group ? c->kg[g] : c->K;
+    g_flops[FLOP_TC_WGRAD] += 2.0 * c->B * c->Tout * (double)c->Cout * c->Cin * taps;
+  }
+  Fin2P f{};
+  f.ws = c->ws; f.ws_grp_stride = p.ws_grp_stride; f.ngroups = c->ngroups; f.Np = p.Np; f.Mp = p.Mp;
+  f.Cout = c->Cout; f.Cin = c->Cin; f.K = c->K; f.bias = p.bias; f.per_group = p.per_group;
+  for (int g = 0; g < W2_MAXG; ++g) { f.dw[g] = c->dw[g]; f.db[g] = c->db[g]; f.kg[g] = p.kg[g]; }
+  f.dw_grp_stride = c->dw_grp_stride; f.db_grp_stride = c->db_grp_stride;
+  f.frame_s = c->frame_s; f.kreal = c->kreal; f.cin_conv_g = c->cin_conv_g; f.sub = c->sub > 0 ? c->sub : 1;
+  const long long n = (long long)c->K * c->Cout * c->Cin;
+  const int bx = (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, std::max(1, 4 * num_sms() / c->ngroups)));
+  tdvc::launch_k(wgrad2_finalize_k, dim3(bx, c->ngroups), 256, 0, st, f);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}

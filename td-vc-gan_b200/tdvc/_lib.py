@@ -31,7 +31,17 @@ class TcConv(C.Structure):
                [("out_slope", C.c_float)] + \
                [(n, C.c_int32) for n in ("out_packed", "tp_out", "cp_out", "out_halo", "out_ch_off", "out_ch_stride",
                                          "tm", "cm", "mask_halo", "mask_ch_off", "mask_ch_stride")] + \
-               [("mask_slope", C.c_float)]
+               [("mask_slope", C.c_float), ("y_grp_stride", C.c_int64), ("y_b_stride", C.c_int64)]
+
+
+class TcWgrad2(C.Structure):
+    """struct tdvc_tc_wgrad2"""
+    _fields_ = [("dyp", C.c_void_p), ("xp", C.c_void_p), ("ws", C.c_void_p), ("dw", C.c_void_p * 4), ("db", C.c_void_p * 4),
+                ("dw_grp_stride", C.c_int64), ("db_grp_stride", C.c_int64)] + \
+               [(n, C.c_int32) for n in ("B", "Cdp", "Tout", "Cp", "Tp", "Cout", "Cin", "K", "dilation", "ngroups", "per_group",
+                                         "x_ch_off", "x_ch_stride", "dy_ch_off", "dy_ch_stride")] + \
+               [("kg", C.c_int32 * 4), ("t_off", C.c_int32 * 4)] + \
+               [(n, C.c_int32) for n in ("want_bias", "ws_is_zero", "haloed", "frame_s", "kreal", "cin_conv_g", "sub")]
 
 
 PAD_ZEROS, PAD_REFLECT = 0, 1
@@ -89,6 +99,10 @@ SIGNATURES = {
     "tdvc_space_to_depth": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "tdvc_depth_to_space": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "tdvc_conv1d_tc_fwd_ex": (_I, [C.POINTER(TcConv), _P]),
+    "tdvc_conv1d_tc_wgrad2_ws": (_L, [C.POINTER(TcWgrad2)]),
+    "tdvc_conv1d_tc_wgrad2": (_I, [C.POINTER(TcWgrad2), _P]),
+    "tdvc_frame_pack_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "tdvc_frame_unpack": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "tdvc_conv1d_tc_fwd_stacked": (_I, [_P, _P, _P, _P] + [_I] * 12 + [_I, _F] + [_I] * 5 + [_P]),
     "tdvc_conv1d_tc_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P]),
 }

@@ -410,17 +410,22 @@ def conv1d(x, weight, bias=None, *, stride=1, padding=0, dilation=1, groups=1, r
            in_slope=1.0, out_act=None, out_slope=0.2, residual=None):
     """act(conv1d(leaky_relu(pad(x), in_slope), weight) + bias + residual); nn.Conv1d semantics
     (padding_mode 'zeros' or 'reflect')."""
-    if (_frame_conv_eligible(x.shape[1], weight.shape[0], weight.shape[2], int(stride), int(groups), int(dilation),
-                             bool(reflect and padding > 0))
-            and residual is None and tc_eligible(int(stride) * x.shape[1], weight.shape[0], 1, 1)
-            and x.shape[2] + 2 * int(padding) >= weight.shape[2]):
-        return _strided_conv_as_frames(x, weight, bias, int(stride), int(padding), in_slope, out_act, out_slope)
-    if _PRECISION == "bf16" and tc_eligible(x.shape[1], weight.shape[0], int(stride), int(groups)):
-        return _Conv1dTC.apply(x, weight, bias, residual, int(padding), int(dilation),
-                               PAD_REFLECT if (reflect and padding > 0) else PAD_ZEROS, float(in_slope), _ACT[out_act],
+    stride, padding, dilation, groups = int(stride), int(padding), int(dilation), int(groups)
+    is_reflect = bool(reflect and padding > 0)
+    if (_frame_conv_eligible(x.shape[1], weight.shape[0], weight.shape[2], stride, groups, dilation, is_reflect)
+            and residual is None and tc_eligible(stride * x.shape[1], weight.shape[0], 1, 1)
+            and x.shape[2] + 2 * padding >= weight.shape[2]):
+        return _strided_conv_as_frames(x, weight, bias, stride, padding, in_slope, out_act, out_slope)
+    if residual is None and in_slope == 1.0 and x.is_cuda:
+        plan = _grouped_frame_plan(x.shape[1], weight.shape[0], weight.shape[2], stride, groups, dilation, is_reflect)
+        if plan is not None and x.shape[2] + 2 * padding >= weight.shape[2]:
+            return _GroupedFrameConvTC.apply(x, weight, bias, stride, padding, groups, _ACT[out_act], float(out_slope), plan)
+    if _PRECISION == "bf16" and tc_eligible(x.shape[1], weight.shape[0], stride, groups):
+        return _Conv1dTC.apply(x, weight, bias, residual, padding, dilation,
+                               PAD_REFLECT if is_reflect else PAD_ZEROS, float(in_slope), _ACT[out_act],
                                float(out_slope))
-    return _Conv1d.apply(x, weight, bias, residual, int(stride), int(padding), int(dilation), int(groups),
-                         PAD_REFLECT if (reflect and padding > 0) else PAD_ZEROS, float(in_slope), _ACT[out_act],
+    return _Conv1d.apply(x, weight, bias, residual, stride, padding, dilation, groups,
+                         PAD_REFLECT if is_reflect else PAD_ZEROS, float(in_slope), _ACT[out_act],
                          float(out_slope))
 
 
@@ -1141,13 +1146,17 @@ class _Conv1dTC(torch.autograd.Function):
             # wgrad on tcgen05 from the two packed operands (time is the GEMM K dimension)
             halo = pad if pad_mode == PAD_REFLECT else 0
             dw = torch.empty_like(w)
-            ws, wz = _wgrad_ws(lib.tdvc_conv1d_tc_wgrad_ws(Cout, Cin, K), x.device)
             if db_from_wgrad:
                 db = torch.empty(Cout, device=x.device, dtype=torch.float32)
                 need_b = False
-            _lib.check(lib.tdvc_conv1d_tc_wgrad(_p(dyp), _p(xp), _p(dw), _p(ws), B, Cdp, Tout, xp.shape[2], xp.shape[1],
-                                                Cout, Cin, K, dilation, halo - pad, 0, 0, _p(db) if db_from_wgrad else None,
-                                                wz, _st()), "conv1d_tc_wgrad")
+            if _USE_WGRAD2:
+                wgrad2(dyp=dyp, xp=xp, B=B, Cdp=Cdp, Tout=Tout, Cp=xp.shape[2], Tp=xp.shape[1], Cout=Cout, Cin=Cin, K=K,
+                       dilation=dilation, t_off=[halo - pad], dw=[dw], db=[db if db_from_wgrad else None])
+            else:
+                ws, wz = _wgrad_ws(lib.tdvc_conv1d_tc_wgrad_ws(Cout, Cin, K), x.device)
+                _lib.check(lib.tdvc_conv1d_tc_wgrad(_p(dyp), _p(xp), _p(dw), _p(ws), B, Cdp, Tout, xp.shape[2], xp.shape[1],
+                                                    Cout, Cin, K, dilation, halo - pad, 0, 0, _p(db) if db_from_wgrad else None,
+                                                    wz, _st()), "conv1d_tc_wgrad")
         if need_b:
             db = torch.empty(Cout, device=x.device, dtype=torch.float32)
             _lib.check(lib.tdvc_bias_grad(_p(dy), _p(db), B, Cout, Tout, _st()), "bias_grad")
@@ -1233,8 +1242,10 @@ class _DepthToSpace(torch.autograd.Function):
 
 
 def _frame_conv_eligible(Cin, Cout, K, stride, groups, dilation, reflect) -> bool:
+    """dense Conv1d(k, stride = s) with k > s: a stride-1 conv with ceil(k / s) taps over frames of s samples (a kernel that
+    is not a whole number of strides -- the latent classifier's k = 21, s = 2 -- gets zero taps appended)"""
     return (_PRECISION == "bf16" and _FRAME_CONV and 1 < stride <= 16 and groups == 1 and dilation == 1 and not reflect
-            and K % stride == 0 and K > stride)
+            and K > stride)
 
 
 _FRAME_CONV = os.environ.get("TDVC_FRAME_CONV", "1") != "0"     # development switch: 0 = fp32 CUDA-core strided kernels
@@ -1245,11 +1256,16 @@ def _strided_conv_as_frames(x, weight, bias, stride, padding, in_slope, out_act,
     y[t] = sum_j sum_(p,ci) xs[(p,ci), t + j] * w[co, ci, s*j + p].  The frame view costs one pass over x; the
     convolution (forward, data and weight gradients) then runs on the tcgen05 path instead of the fp32 kernels."""
     Cout, Cin, K = weight.shape
-    s, m = stride, K // stride
-    Tq = (x.shape[2] + 2 * padding) // s
+    s, m = stride, -(-K // stride)
+    Tout = (x.shape[2] + 2 * padding - K) // s + 1
+    Tq = Tout + m - 1
     xs = _SpaceToDepth.apply(x, s, padding, Tq)
-    w2 = _step_cached(("frames_w", s, torch.is_grad_enabled()), [weight],
-                      lambda: weight.view(Cout, Cin, m, s).permute(0, 3, 1, 2).reshape(Cout, s * Cin, m))
+
+    def make():
+        wk = weight if m * s == K else torch.nn.functional.pad(weight, (0, m * s - K))
+        return wk.view(Cout, Cin, m, s).permute(0, 3, 1, 2).reshape(Cout, s * Cin, m)
+
+    w2 = _step_cached(("frames_w", s, torch.is_grad_enabled()), [weight], make)
     return _Conv1dTC.apply(xs, w2, bias, None, 0, 1, PAD_ZEROS, float(in_slope), _ACT[out_act], float(out_slope))
 
 
@@ -1270,6 +1286,145 @@ def _conv_transpose_as_frames(x, weight, bias, stride, padding):
     yq = _Conv1dTC.apply(x, w2, b2, None, m - 1, 1, PAD_ZEROS, 1.0, ACT_NONE, 1.0)
     return _DepthToSpace.apply(yq, s, padding, Tout)
 
+
+
+_USE_WGRAD2 = os.environ.get("TDVC_WGRAD2", "1") != "0"      # development switch: 0 = first-generation tcgen05 wgrad kernel
+_GROUPED_FRAMES = os.environ.get("TDVC_GROUPED_FRAMES", "1") != "0"    # development switch: 0 = fp32 CUDA-core grouped kernels
+
+
+def _grouped_frame_plan(Cin, Cout, K, stride, groups, dilation, reflect):
+    """Conv1d(k, stride = s, groups = G) -- the discriminators' k41 s4 layers, model/discriminator.py:26-30 -- as a stride-1
+    GROUPED tensor-core convolution over frames of s samples in channel-major order: a conv group's cin_g * s frame channels
+    are contiguous, so `sub` conv groups form one tensor-core group ("bundle") with a block-diagonal weight.  Returns
+    (sub, m taps, frame channels per bundle, outputs per bundle, bundles) or None when the layer is not of that form."""
+    if _PRECISION != "bf16" or not _GROUPED_FRAMES or groups <= 1 or dilation != 1 or reflect or stride not in (2, 4, 8):
+        return None
+    if Cin % groups or Cout % groups or K <= stride:
+        return None
+    cin_g, cout_g = Cin // groups, Cout // groups
+    fpg = cin_g * stride
+    for sub in (1, 2, 4, 8):
+        if groups % sub == 0 and (sub * fpg) % 16 == 0 and (sub * cout_g) % 16 == 0 and sub * fpg <= 128 and sub * cout_g <= 256:
+            return (sub, -(-K // stride), sub * fpg, sub * cout_g, groups // sub)
+    return None
+
+
+def _frame_weights(w, stride, plan):
+    """(forward, data-gradient) operands of the bundled frame convolution from the grouped conv weight w[Cout, cin_g, K]:
+    wp[j][bundle*Cout_b + co][ci] with ci = (local conv group, c, p) <- w[co, c, s*j + p] on the diagonal blocks, zero
+    elsewhere and for the appended taps; wtp[j'][bundle*Cin_b + ci][co] = wp[m-1-j'][...][ci] (taps reversed)."""
+    sub, m, cin_b, cout_b, nb = plan
+    Cout, cin_g, K = w.shape
+    fpg = cin_g * stride
+    wk = torch.nn.functional.pad(w, (0, m * stride - K)) if m * stride != K else w
+    src = wk.view(Cout, cin_g, m, stride).permute(2, 0, 1, 3).reshape(m, Cout, fpg)
+    if sub == 1:
+        wp32 = src
+    else:
+        cout_g = Cout // (nb * sub)
+        src5 = src.view(m, nb, sub, cout_g, fpg)
+        blk = torch.zeros(m, nb, sub, cout_g, sub, fpg, device=w.device, dtype=w.dtype)
+        for i in range(sub):
+            blk[:, :, i, :, i, :] = src5[:, :, i]
+        wp32 = blk.view(m, Cout, cin_b)
+    wp = wp32.to(torch.bfloat16).contiguous()
+    wtp = wp.view(m, nb, cout_b, cin_b).flip(0).transpose(2, 3).reshape(m, nb * cin_b, cout_b).contiguous()
+    return wp, wtp
+
+
+class _GroupedFrameConvTC(torch.autograd.Function):
+    """act(conv1d(x, w, groups) + bias) for Conv1d(k, stride = s, zero padding, groups) on tcgen05: one pass builds the bf16
+    frame view of x, the convolution is a grouped stride-1 launch of the tensor-core kernels writing the NCW fp32 feature
+    map (+ bias + LeakyReLU), the data gradient the same launch on dL/dy followed by the inverse frame view, and the weight
+    gradients of all groups one grouped launch of the weight-gradient kernel."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, stride, pad, groups, out_act, out_slope, plan):
+        _req(x, w, bias)
+        x, w, bias = _c(x), _c(w), _c(bias)
+        sub, m, cin_b, cout_b, nb = plan
+        B, Cin, T = x.shape
+        Cout, cin_g, K = w.shape
+        if cin_g * groups != Cin:
+            raise RuntimeError(f"conv1d: weight {tuple(w.shape)} does not match input {tuple(x.shape)} groups={groups}")
+        Tout = (T + 2 * pad - K) // stride + 1
+        Tq = Tout + m - 1
+        lib = _lib.load()
+        xf = torch.empty(B, Tq, Cin * stride, device=x.device, dtype=torch.bfloat16)
+        _lib.check(lib.tdvc_frame_pack_bf16(_p(x), _p(xf), B, Cin, T, stride, pad, Tq, _st()), "frame_pack")
+        wp, wtp = _step_cached(("gframes", stride, plan), [w], lambda: _frame_weights(w, stride, plan))
+        y = torch.empty(B, Cout, Tout, device=x.device, dtype=torch.float32)
+        _tc_conv(xp=xf, wp=wp, bias=bias, y=y, B=B, Tp=Tq, Tout=Tout, K=m, dilation=1, t_off=0, Cp_total=Cin * stride,
+                 groups=nb, a_ch_off=0, a_ch_stride=cin_b, Cinp_g=cin_b, Cout_g=cout_b, Coutp_g=cout_b,
+                 bias_stride=cout_b, out_act=out_act, out_slope=out_slope, out_packed=0,
+                 y_grp_stride=cout_b * Tout, y_b_stride=Cout * Tout)
+        ctx.cfg = (stride, pad, groups, out_act, out_slope, plan, T)
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(xf, w, wtp, y if out_act != ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xf, w, wtp, y = ctx.saved_tensors
+        stride, pad, groups, out_act, out_slope, plan, T = ctx.cfg
+        sub, m, cin_b, cout_b, nb = plan
+        lib = _lib.load()
+        dy = _c(dy)
+        B, Cout, Tout = dy.shape
+        Tq = xf.shape[1]
+        Cin = xf.shape[2] // stride
+        cin_g, K = w.shape[1], w.shape[2]
+        if out_act != ACT_NONE:
+            dz = torch.empty_like(dy)
+            _lib.check(lib.tdvc_act_bwd_from_output(_p(dy), _p(y), _p(dz), dy.numel(), out_act, out_slope, _st()), "act_bwd")
+            dy = dz
+        dx = dw = db = None
+        need_w = ctx.needs_input_grad[1]
+        need_b = ctx.has_bias and ctx.needs_input_grad[2]
+        if ctx.needs_input_grad[0] or need_w or need_b:
+            dyp = torch.empty(B, Tout, Cout, device=dy.device, dtype=torch.bfloat16)
+            _lib.check(lib.tdvc_pack_cl_bf16(_p(dy), _p(dyp), B, Cout, Tout, Cout, 0, PAD_ZEROS, 1.0, None, 0, 0, -1, None, _st()),
+                       "pack dy")
+        if ctx.needs_input_grad[0]:
+            dxf = torch.empty(B, Cin * stride, Tq, device=dy.device, dtype=torch.float32)
+            _tc_conv(xp=dyp, wp=wtp, y=dxf, B=B, Tp=Tout, Tout=Tq, K=m, dilation=1, t_off=-(m - 1), Cp_total=Cout, groups=nb,
+                     a_ch_off=0, a_ch_stride=cout_b, Cinp_g=cout_b, Cout_g=cin_b, Coutp_g=cin_b, bias_stride=0,
+                     out_act=ACT_NONE, out_slope=1.0, out_packed=0, y_grp_stride=cin_b * Tq, y_b_stride=Cin * stride * Tq)
+            dx = torch.empty(B, Cin, T, device=dy.device, dtype=torch.float32)
+            _lib.check(lib.tdvc_frame_unpack(_p(dxf), _p(dx), B, Cin, T, stride, pad, Tq, _st()), "frame_unpack")
+        if need_w or need_b:
+            dw = torch.empty_like(w)
+            db = torch.empty(Cout, device=dy.device, dtype=torch.float32) if need_b else None
+            wgrad2(dyp=dyp, xp=xf, B=B, Cdp=Cout, Tout=Tout, Cp=Cin * stride, Tp=Tq, Cout=cout_b, Cin=cin_b, K=m, dilation=1,
+                   ngroups=nb, x_ch_stride=cin_b, dy_ch_stride=cout_b, t_off=[0], dw=[dw], db=[db], frame_s=stride, kreal=K,
+                   cin_conv_g=cin_g, sub=sub)
+            if not need_w:
+                dw = None
+        return dx, dw, db, None, None, None, None, None, None
+
+
+def wgrad2(*, dyp, xp, B, Cdp, Tout, Cp, Tp, Cout, Cin, K, dilation, ngroups=1, per_group=False, x_ch_off=0, x_ch_stride=0,
+           dy_ch_off=0, dy_ch_stride=0, kg=None, t_off=(0,), dw=(None,), db=(None,), dw_grp_stride=0, db_grp_stride=0,
+           frame_s=0, kreal=0, cin_conv_g=0, sub=1, haloed=-1):
+    """tdvc_conv1d_tc_wgrad2 (include/tdvc_b200.h) on the persistent always-zero workspace."""
+    lib = _lib.load()
+    c = _lib.TcWgrad2()
+    c.dyp, c.xp = dyp.data_ptr(), xp.data_ptr()
+    for i in range(4):
+        c.dw[i] = dw[i].data_ptr() if i < len(dw) and dw[i] is not None else None
+        c.db[i] = db[i].data_ptr() if i < len(db) and db[i] is not None else None
+        c.kg[i] = int(kg[i]) if kg is not None and i < len(kg) else K
+        c.t_off[i] = int(t_off[i]) if i < len(t_off) else int(t_off[0])
+    c.dw_grp_stride, c.db_grp_stride = int(dw_grp_stride), int(db_grp_stride)
+    c.B, c.Cdp, c.Tout, c.Cp, c.Tp, c.Cout, c.Cin, c.K, c.dilation = B, Cdp, Tout, Cp, Tp, Cout, Cin, K, dilation
+    c.ngroups, c.per_group = ngroups, int(bool(per_group))
+    c.x_ch_off, c.x_ch_stride, c.dy_ch_off, c.dy_ch_stride = x_ch_off, x_ch_stride, dy_ch_off, dy_ch_stride
+    c.want_bias = int(any(b is not None for b in db))
+    c.haloed = haloed
+    c.frame_s, c.kreal, c.cin_conv_g, c.sub = frame_s, kreal, cin_conv_g, sub
+    ws, wz = _wgrad_ws(int(lib.tdvc_conv1d_tc_wgrad2_ws(C.byref(c))), dyp.device)
+    c.ws, c.ws_is_zero = ws.data_ptr(), wz
+    _lib.check(lib.tdvc_conv1d_tc_wgrad2(C.byref(c), _st()), "conv1d_tc_wgrad2")
 
 
 class _MRFCondPath(torch.autograd.Function):
@@ -1367,12 +1522,20 @@ class _MRFCondPath(torch.autograd.Function):
                                              -1, None, _st()), "pack dgb")
         # cond_var.2 weight gradients
         dw2 = []
-        ws, wz = _wgrad_ws(max(lib.tdvc_conv1d_tc_wgrad_ws(C2, Cc, K), lib.tdvc_conv1d_tc_wgrad_ws(n * Cg, Cc + 1, K)), dev)
-        for j in range(n):
-            g = torch.empty(C2, Cc, K, device=dev, dtype=torch.float32)
-            _lib.check(lib.tdvc_conv1d_tc_wgrad(_p(dgbp), _p(g1p), _p(g), _p(ws), B, n * C2p, T, n * Cg, T, C2, Cc, K, 1, -1,
-                                                j * Cg, j * C2p, _p(db2[j]), wz, _st()), "wgrad cond_var.2")
-            dw2.append(g)
+        if _USE_WGRAD2:
+            # the n blocks' cond_var.2 weight (+ bias) gradients: ONE grouped launch
+            dw2_all = torch.empty(n, C2, Cc, K, device=dev, dtype=torch.float32)
+            wgrad2(dyp=dgbp, xp=g1p, B=B, Cdp=n * C2p, Tout=T, Cp=n * Cg, Tp=T, Cout=C2, Cin=Cc, K=K, dilation=1, ngroups=n,
+                   x_ch_stride=Cg, dy_ch_stride=C2p, t_off=[-1], dw=[dw2_all], db=[db2], dw_grp_stride=C2 * Cc * K,
+                   db_grp_stride=C2)
+            dw2 = [dw2_all[j] for j in range(n)]
+        else:
+            ws, wz = _wgrad_ws(max(lib.tdvc_conv1d_tc_wgrad_ws(C2, Cc, K), lib.tdvc_conv1d_tc_wgrad_ws(n * Cg, Cc + 1, K)), dev)
+            for j in range(n):
+                g = torch.empty(C2, Cc, K, device=dev, dtype=torch.float32)
+                _lib.check(lib.tdvc_conv1d_tc_wgrad(_p(dgbp), _p(g1p), _p(g), _p(ws), B, n * C2p, T, n * Cg, T, C2, Cc, K, 1, -1,
+                                                    j * Cg, j * C2p, _p(db2[j]), wz, _st()), "wgrad cond_var.2")
+                dw2.append(g)
         # dL/dg1 (packed, LeakyReLU mask applied in the epilogue): grouped dgrad of cond_var.2
         def pack_bwd():
             w2tp = torch.empty(K, n * Cg, C2p, device=dev, dtype=torch.bfloat16)
@@ -1392,8 +1555,12 @@ class _MRFCondPath(torch.autograd.Function):
                  maskp=g1p, tm=T, cm=n * Cg, mask_halo=0, mask_ch_off=0, mask_ch_stride=Cg, mask_slope=slope)
         # cond_var.0 weight (+ bias, through the constant-one channel of cp) gradients: one GEMM for all blocks
         dw0_all = torch.empty(n * Cg, Cc + 1, K, device=dev, dtype=torch.float32)
-        _lib.check(lib.tdvc_conv1d_tc_wgrad(_p(dg1p), _p(cp), _p(dw0_all), _p(ws), B, n * Cg, T, Cg, T, n * Cg, Cc + 1, K, 1,
-                                            -1, 0, 0, None, wz, _st()), "wgrad cond_var.0")
+        if _USE_WGRAD2:
+            wgrad2(dyp=dg1p, xp=cp, B=B, Cdp=n * Cg, Tout=T, Cp=Cg, Tp=T, Cout=n * Cg, Cin=Cc + 1, K=K, dilation=1, t_off=[-1],
+                   dw=[dw0_all], db=[None])
+        else:
+            _lib.check(lib.tdvc_conv1d_tc_wgrad(_p(dg1p), _p(cp), _p(dw0_all), _p(ws), B, n * Cg, T, Cg, T, n * Cg, Cc + 1, K, 1,
+                                                -1, 0, 0, None, wz, _st()), "wgrad cond_var.0")
         # dL/dc: one conv over the n*Cg concatenated channels (sums the blocks' contributions in the GEMM)
         dc = None
         if ctx.needs_input_grad[0]:
@@ -1474,9 +1641,13 @@ class _FilmPosconvTC(torch.autograd.Function):
         dw = None
         if ctx.needs_input_grad[2]:
             dw = torch.empty_like(w)
-            ws, wz = _wgrad_ws(lib.tdvc_conv1d_tc_wgrad_ws(Cout, Cc, 1), dy.device)
-            _lib.check(lib.tdvc_conv1d_tc_wgrad(_p(dyp), _p(a1p), _p(dw), _p(ws), B, Cdp, T, Cp, T, Cout, Cc, 1, 1, 0, 0, 0,
-                                                _p(db) if db_from_wgrad else None, wz, _st()), "posconv_tc_wgrad")
+            if _USE_WGRAD2:
+                wgrad2(dyp=dyp, xp=a1p, B=B, Cdp=Cdp, Tout=T, Cp=Cp, Tp=T, Cout=Cout, Cin=Cc, K=1, dilation=1, t_off=[0],
+                       dw=[dw], db=[db if db_from_wgrad else None])
+            else:
+                ws, wz = _wgrad_ws(lib.tdvc_conv1d_tc_wgrad_ws(Cout, Cc, 1), dy.device)
+                _lib.check(lib.tdvc_conv1d_tc_wgrad(_p(dyp), _p(a1p), _p(dw), _p(ws), B, Cdp, T, Cp, T, Cout, Cc, 1, 1, 0, 0, 0,
+                                                    _p(db) if db_from_wgrad else None, wz, _st()), "posconv_tc_wgrad")
         dh0 = dgb = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             Cinp16 = _ceil(Cc, 16)
