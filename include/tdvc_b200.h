@@ -224,8 +224,32 @@ typedef struct tdvc_tc_conv {
    * Both 0 = group-major [groups][B][Cout_g][Tout]; y_grp_stride = Cout_g*Tout, y_b_stride = groups*Cout_g*Tout is the
    * ordinary NCW tensor [B][groups*Cout_g][Tout] of a grouped nn.Conv1d (model/discriminator.py:26-30). */
   int64_t y_grp_stride, y_b_stride;
+  /* Chain epilogues: an MRF stage (model/generator.py:69-111,175-194) kept in bf16 channels-last between its
+   * convolutions; group = kernel-size branch, channel counts multiples of 16, residual stream fp32 [branch][B][C][T].
+   *   chain_mode 3 (conv.1):     h0 = conv + bias -> yp2 (optional);  leaky_relu(h0 * (1 + gamma) + beta, out_slope) -> yp
+   *                              (gamma|beta = gb + g*gb_grp_stride, fp32 [B][2*Cout_g][Tout]; no FiLM when gb is NULL)
+   *   chain_mode 4 (posconv.1):  x' = conv + bias + residual[g*res_grp_stride ...] -> y (y_*_stride layout);
+   *                              leaky_relu(x', pk_slope) -> yp rows out_halo + t plus the reflect halo rows (yp optional)
+   *   chain_mode 5 (posconv^T):  d = conv * lrelu'(maskp);  dgamma = d * auxp, dbeta = d -> dgbp[b][t][dgb_ch_off +
+   *                              g*dgb_ch_stride + {n, Cout_g + n}];  d * (1 + gamma) -> yp   (gb NULL: d -> yp)
+   *   chain_mode 6 (conv.1^T):   rows = positions of the padded input (t_valid + 2*halo); d = conv * lrelu'(maskp);
+   *                              interior rows: d + residual -> y and yp (optional); halo rows -> halo_buf[g][B][Cout_g][2*halo]
+   *                              (folded onto the rows they mirror by tdvc_chain_fold)
+   * kg[g] > 0 (groups <= 4): group g uses the centred kg[g] of the K taps. */
+  int32_t chain_mode;
+  int32_t kg[4];
+  int64_t gb_grp_stride, res_grp_stride;
+  void* yp2; const void* auxp; void* dgbp;
+  int32_t dgb_cp, dgb_ch_off, dgb_ch_stride;
+  float* halo_buf;
+  int32_t halo, t_valid;
+  float pk_slope;
 } tdvc_tc_conv;
 int tdvc_conv1d_tc_fwd_ex(const tdvc_tc_conv* c, void* stream);
+/* after a chain_mode 6 launch: y[g][b][c][mirror(r)] += halo_buf[g][b][c][r] for the 2*halo reflect rows r of every
+ * (group, batch, channel) and, when yp is given, the packed bf16 copy of the touched samples is rewritten. */
+int tdvc_chain_fold(const float* halo_buf, float* y, void* yp, int groups, int B, int C, int T, int halo,
+                    int64_t y_grp_stride, int64_t y_b_stride, int cp_out, int out_ch_off, int out_ch_stride, void* stream);
 
 /* Stacked-block form for n convs that read the SAME input -- the FiLM cond_var[0] convs of the 9 blocks of an MRF stage
  * (generator.py:85-92,141-194).  The GEMM is turned round: the stacked weights are the M=128 tcgen05 operand (resident in

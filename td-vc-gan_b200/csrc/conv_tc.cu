@@ -40,6 +40,16 @@ struct TcP {
   int tm, cm, mask_halo, mask_ch_off, mask_ch_stride;
   float mask_slope;
   long long y_grp_stride, y_b_stride;         // fp32 output: g*y_grp_stride + b*y_b_stride + n*Tout + t
+  // chain epilogues (EPI >= 3): the MRF stage kept in bf16 channels-last between its convolutions
+  int kg[4];                                  // per-group kernel size, centred inside the K taps of the weight tensor
+  long long gb_grp_stride, res_grp_stride;    // FiLM gamma|beta and residual tensors: element offset of group g
+  __nv_bfloat16* yp2;                         // EPI 3: second packed output (the un-modulated conv result), geometry of yp
+  const __nv_bfloat16* auxp;                  // EPI 5: packed conv result saved by EPI 3, geometry of maskp
+  __nv_bfloat16* dgbp;                        // EPI 5: packed dL/d(gamma|beta) rows [B][Tout][dgb_cp]
+  int dgb_cp, dgb_ch_off, dgb_ch_stride;
+  float* halo_buf;                            // EPI 6: contributions that fall on reflect-halo rows [grp][B][Cout][2*halo]
+  int halo, t_valid;
+  float pk_slope;                             // EPI 4: LeakyReLU slope of the packed copy
 };
 
 constexpr int TC_BM = 128;
@@ -49,10 +59,151 @@ constexpr int TC_THREADS = 192;       // wgrad kernel: TMA warp, MMA warp, 4 epi
 constexpr int TC_EPI_WARPS = 16;      // forward kernels: epilogue warps (a multiple of 4: TC_EPI_WARPS / 4 per TMEM lane quadrant)
 constexpr int TC_FWD_THREADS = 64 + 32 * TC_EPI_WARPS;   // + TMA warp + MMA warp
 
+__device__ __forceinline__ void store16_bf16(__nv_bfloat16* dst, const float* v) {
+  uint32_t w[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    w[j] = *reinterpret_cast<uint32_t*>(&h2);
+  }
+  reinterpret_cast<uint4*>(dst)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+  reinterpret_cast<uint4*>(dst)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+__device__ __forceinline__ void load16_bf16(const __nv_bfloat16* src, float* v) {
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(src)), c = __ldg(reinterpret_cast<const uint4*>(src) + 1);
+  const uint32_t w[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    v[2 * j] = __uint_as_float(w[j] << 16);
+    v[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+  }
+}
+// v[j] *= slope where the packed activated value is <= 0 (bf16 sign / zero test on the raw bits)
+__device__ __forceinline__ void mask16_bf16(const __nv_bfloat16* mp, float* v, float slope) {
+  const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(mp)), m1 = __ldg(reinterpret_cast<const uint4*>(mp) + 1);
+  const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const uint32_t h = (j & 1) ? (mw[j >> 1] >> 16) : (mw[j >> 1] & 0xFFFFu);
+    if ((h & 0x8000u) || (h & 0x7FFFu) == 0) v[j] *= slope;
+  }
+}
+
+// Epilogues of the bf16-resident MRF stage (model/generator.py:69-111,175-194).  Every group is one kernel-size branch; all
+// tensors between the convolutions are bf16 channels-last with the branches side by side in the channel dimension, the
+// residual stream stays fp32 NCW [branch][B][C][T].  Channel counts are multiples of 16 (a thread's 16 columns are real).
+//   MODE 3  conv.1      h0 = acc + bias -> yp2 (kept for the backward);  a1 = leaky_relu(h0 * (1 + gamma) + beta) -> yp
+//   MODE 4  posconv.1   x' = acc + bias + x -> y fp32;  leaky_relu(x') -> yp with the reflect halo rows of the next conv.1
+//   MODE 5  posconv^T   d = acc * lrelu'(a1);  dgamma = d * h0, dbeta = d -> dgbp;  dh0 = d * (1 + gamma) -> yp
+//   MODE 6  conv.1^T    over the padded rows: d = acc * lrelu'(x);  interior rows: dx = d + dx' -> y fp32 and yp;
+//                       halo rows -> halo_buf (chain_fold_k adds them onto the rows they mirror)
+template <int MODE>
+__device__ __forceinline__ void tc_epilogue_chain(const TcP& p, const float* bias_s, uint32_t acc, int b, int t0, int grp,
+                                                  int n0, int q, int half, int lane) {
+  const int t = t0 + q * 32 + lane;
+  const bool t_ok = t < p.Tout;
+  const int nvalid = min(p.BN, p.Cout - n0);
+  for (int c0 = half * 16; c0 < nvalid; c0 += 16 * (TC_EPI_WARPS / 4)) {
+    float v[16];
+    tmem_ld16(acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+    if (!t_ok) continue;
+    {
+      const float4* b4 = reinterpret_cast<const float4*>(bias_s + c0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 bb = b4[j];
+        v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+      }
+    }
+    const int ch = n0 + c0;                              // first of this thread's 16 channels inside the group
+    if (MODE == 3) {
+      const long long prow = ((long long)b * p.tp_out + t + p.out_halo) * p.cp_out + p.out_ch_off + grp * p.out_ch_stride + ch;
+      if (p.yp2) store16_bf16(p.yp2 + prow, v);
+      if (p.gb) {
+        const long long ct = p.Tout;
+        const float* gp = p.gb + (long long)grp * p.gb_grp_stride + ((long long)b * 2 * p.Cout + ch) * ct + t;
+        const long long beta_off = (long long)p.Cout * ct;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], 1.f + __ldg(gp + j * ct), __ldg(gp + beta_off + j * ct));
+      }
+      const float sl = p.out_slope;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], v[j] * sl);
+      store16_bf16(p.yp + prow, v);
+    } else if (MODE == 4) {
+      const long long ct = p.Tout;
+      float* yo = p.y + (long long)grp * p.y_grp_stride + (long long)b * p.y_b_stride + (long long)ch * ct + t;
+      const float* rp = p.res + (long long)grp * p.res_grp_stride + ((long long)b * p.Cout + ch) * ct + t;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        v[j] += __ldg(rp + j * ct);
+        yo[j * ct] = v[j];
+      }
+      if (p.yp) {
+        const float sl = p.pk_slope;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], v[j] * sl);
+        __nv_bfloat16* col = p.yp + (long long)b * p.tp_out * p.cp_out + p.out_ch_off + grp * p.out_ch_stride + ch;
+        const int H = p.out_halo;
+        store16_bf16(col + (long long)(t + H) * p.cp_out, v);
+        // reflect halo of the consumer: padded row H - i (i = 1..H) mirrors x[i], padded row H + T - 1 + i mirrors x[T - 1 - i]
+        if (t >= 1 && t <= H) store16_bf16(col + (long long)(H - t) * p.cp_out, v);
+        if (t <= p.Tout - 2 && t >= p.Tout - 1 - H) store16_bf16(col + (long long)(H + 2 * (p.Tout - 1) - t) * p.cp_out, v);
+      }
+    } else if (MODE == 5) {
+      const long long mrow = ((long long)b * p.tm + t + p.mask_halo) * p.cm + p.mask_ch_off + grp * p.mask_ch_stride + ch;
+      mask16_bf16(p.maskp + mrow, v, p.mask_slope);
+      if (p.gb) {
+        float h0[16];
+        load16_bf16(p.auxp + mrow, h0);
+        float dg[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dg[j] = v[j] * h0[j];
+        __nv_bfloat16* dgp = p.dgbp + ((long long)b * p.Tout + t) * p.dgb_cp + p.dgb_ch_off + grp * p.dgb_ch_stride + ch;
+        store16_bf16(dgp, dg);                    // dL/dgamma
+        store16_bf16(dgp + p.Cout, v);            // dL/dbeta
+        const long long ct = p.Tout;
+        const float* gp = p.gb + (long long)grp * p.gb_grp_stride + ((long long)b * 2 * p.Cout + ch) * ct + t;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] *= 1.f + __ldg(gp + j * ct);
+      }
+      store16_bf16(p.yp + ((long long)b * p.tp_out + t + p.out_halo) * p.cp_out + p.out_ch_off + grp * p.out_ch_stride + ch, v);
+    } else if (MODE == 6) {
+      // rows are positions of the PADDED input (t_valid + 2 * halo of them); the packed activated input carries the same
+      // halo, so row t of it gates row t here -- for a halo row that is the sign of the sample it mirrors, which is the
+      // derivative the folded contribution needs
+      const long long mrow = ((long long)b * p.tm + t + p.mask_halo) * p.cm + p.mask_ch_off + grp * p.mask_ch_stride + ch;
+      mask16_bf16(p.maskp + mrow, v, p.mask_slope);
+      const int tt = t - p.halo;
+      if (tt >= 0 && tt < p.t_valid) {
+        const long long ct = p.t_valid;
+        float* yo = p.y + (long long)grp * p.y_grp_stride + (long long)b * p.y_b_stride + (long long)ch * ct + tt;
+        if (p.res) {
+          const float* rp = p.res + (long long)grp * p.res_grp_stride + ((long long)b * p.Cout + ch) * ct + tt;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += __ldg(rp + j * ct);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) yo[j * ct] = v[j];
+        if (p.yp) store16_bf16(p.yp + ((long long)b * p.tp_out + tt + p.out_halo) * p.cp_out + p.out_ch_off + grp * p.out_ch_stride + ch, v);
+      } else {
+        const int hr = t < p.halo ? t : t - p.t_valid;                 // 0 .. 2*halo - 1
+        float* hb = p.halo_buf + (((long long)grp * p.B + b) * p.Cout + ch) * (2 * p.halo) + hr;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) hb[(long long)j * 2 * p.halo] = v[j];
+      }
+    }
+  }
+}
+
 // Epilogue of one 128 x BN accumulator tile at TMEM address `acc` (lane quadrant q, column half `half`).
 template <int ACT, int EPI, int OUT, int MASK>
 __device__ __forceinline__ void tc_epilogue_tile(const TcP& p, const float* bias_s, uint32_t acc, int b, int t0, int grp,
                                                  int n0, int q, int half, int lane) {
+    if (EPI >= 3) {
+      tc_epilogue_chain<EPI>(p, bias_s, acc, b, t0, grp, n0, q, half, lane);
+      return;
+    }
     const int t = t0 + q * 32 + lane;
     const bool t_ok = t < p.Tout;
     const long long ct = p.Tout;
@@ -162,7 +313,10 @@ __global__ void __launch_bounds__(TC_FWD_THREADS) conv_tc_fwd_k(const __grid_con
   for (int i = threadIdx.x; i < p.BN; i += TC_FWD_THREADS)
     bias_s[i] = (p.bias && n0 + i < p.Cout) ? __ldg(p.bias + grp * p.bias_stride + n0 + i) : 0.f;
   const int b = blockIdx.z;
-  const int iters = (p.debug & 2) ? 0 : p.K * p.nchunk;
+  // a group may use fewer taps than the weight tensor holds (the k = 3 / 7 branches next to k = 11): the centred ones
+  const int kgrp = p.kg[grp & 3] > 0 ? p.kg[grp & 3] : p.K;
+  const int tap_lo = (p.K - kgrp) >> 1;
+  const int iters = (p.debug & 2) ? 0 : kgrp * p.nchunk;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -187,7 +341,8 @@ __global__ void __launch_bounds__(TC_FWD_THREADS) conv_tc_fwd_k(const __grid_con
         const int s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
         mbar_wait(&empty_bar[s], ph ^ 1u);
-        const int tap = it / p.nchunk, ck = it - tap * p.nchunk;
+        const int tl = it / p.nchunk, ck = it - tl * p.nchunk;
+        const int tap = tap_lo + tl;
         uint8_t* sa = smem + (size_t)s * stage_bytes;
         mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
         tma_load_3d(sa, &map_a, &full_bar[s], p.a_ch_off + grp * p.a_ch_stride + ck * TC_BK, t0 + tap * p.dil + p.t_off, b);
@@ -319,11 +474,13 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) conv_tc_ws_k(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int a_ch0 = p.a_ch_off + grp * p.a_ch_stride;
+  const int kgrp = p.kg[grp & 3] > 0 ? p.kg[grp & 3] : p.K;      // this group's taps: the centred kgrp of the K in the tensor
+  const int tap_lo = (p.K - kgrp) >> 1, tap_hi = tap_lo + kgrp;
 
   if (warp == 0) {
     if (elect_one()) {
-      mbar_expect_tx(w_full, (uint32_t)(p.K * nfull * w.w_tile_bytes + (w.narrow ? p.K * w.wn_tile_bytes : 0)));
-      for (int tap = 0; tap < p.K; ++tap) {
+      mbar_expect_tx(w_full, (uint32_t)(kgrp * nfull * w.w_tile_bytes + (w.narrow ? kgrp * w.wn_tile_bytes : 0)));
+      for (int tap = tap_lo; tap < tap_hi; ++tap) {
         for (int ck = 0; ck < nfull; ++ck)
           tma_load_3d(wsm + (size_t)(tap * nfull + ck) * w.w_tile_bytes, &map_b, w_full, ck * TC_BK, grp * p.coutp_g + n0, tap);
         if (w.narrow)
@@ -381,12 +538,12 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) conv_tc_ws_k(const __grid_c
           // the single issuing thread must spend < ~70 cycles per MMA (its execution time at N=144): descriptors are
           // advanced with 32-bit adds on their low words only
           const int nk = (!w.narrow && ck == nfull - 1) ? p.last_nk16 : (TC_BK / 16);
-          uint32_t a_lo = a_lo0 + (uint32_t)s * a_stage16;
-          uint32_t b_lo = b_lo0 + (uint32_t)ck * w_tile16;
-          for (int tap = 0; tap < p.K; ++tap) {
+          uint32_t a_lo = a_lo0 + (uint32_t)s * a_stage16 + (uint32_t)tap_lo * tap_step16;
+          uint32_t b_lo = b_lo0 + (uint32_t)ck * w_tile16 + (uint32_t)tap_lo * w_tap16;
+          for (int tap = tap_lo; tap < tap_hi; ++tap) {
             // row-shifted view of the haloed tile: the 128B swizzle is a function of the absolute shared-memory
             // address, so a start address moved by whole 128-byte rows needs no descriptor fix-up (verified on B200)
-            umma_bf16_lohi(d_addr, a_lo, hi128, b_lo, hi128, idesc, (ck > 0 || tap > 0) ? 1u : 0u);
+            umma_bf16_lohi(d_addr, a_lo, hi128, b_lo, hi128, idesc, (ck > 0 || tap > tap_lo) ? 1u : 0u);
             if (nk > 1) umma_bf16_lohi(d_addr, a_lo + 2, hi128, b_lo + 2, hi128, idesc, 1u);
             if (nk > 2) umma_bf16_lohi(d_addr, a_lo + 4, hi128, b_lo + 4, hi128, idesc, 1u);
             if (nk > 3) umma_bf16_lohi(d_addr, a_lo + 6, hi128, b_lo + 6, hi128, idesc, 1u);
@@ -404,9 +561,9 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) conv_tc_ws_k(const __grid_c
         mbar_wait(&fulln_bar[s], ph);
         tc_fence_after();
         if (elect_one()) {
-          uint32_t a_lo = an_lo0 + (uint32_t)s * an_stage16;
-          uint32_t b_lo = bn_lo0;
-          for (int tap = 0; tap < p.K; ++tap) {
+          uint32_t a_lo = an_lo0 + (uint32_t)s * an_stage16 + (uint32_t)tap_lo * tapn_step16;
+          uint32_t b_lo = bn_lo0 + (uint32_t)tap_lo * wn_tile16;
+          for (int tap = tap_lo; tap < tap_hi; ++tap) {
             umma_bf16_lohi(d_addr, a_lo, hi32, b_lo, hi32, idesc, 1u);
             a_lo += tapn_step16;
             b_lo += wn_tile16;
@@ -1199,6 +1356,53 @@ extern "C" int tdvc_pack_weight_bf16_multi(const void* jobs, int n_jobs, int blo
   return TDVC_OK;
 }
 
+// taps summed over the groups of a launch
+static double tc_taps(const tdvc_tc_conv* c) {
+  double n = 0;
+  for (int g = 0; g < c->groups; ++g) n += (c->groups <= 4 && c->kg[g] > 0) ? c->kg[g] : c->K;
+  return n;
+}
+
+// chain_mode 6 follow-up: fold the reflect-halo contributions onto the samples they mirror (one thread per (group, batch,
+// channel) row: the 2*halo updates of a row may hit the same sample when the signal is short)
+__global__ void chain_fold_k(const float* __restrict__ hb, float* __restrict__ y, __nv_bfloat16* __restrict__ yp, int groups,
+                             int B, int C, int T, int halo, long long y_grp_stride, long long y_b_stride, int cp_out,
+                             int out_ch_off, int out_ch_stride) {
+  tdvc::pdl_prologue();
+  const long long n = (long long)groups * B * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long r = i / C;
+    const int b = (int)(r % B), g = (int)(r / B);
+    const float* h = hb + i * (2 * halo);
+    float* row = y + (long long)g * y_grp_stride + (long long)b * y_b_stride + (long long)c * T;
+    for (int hr = 0; hr < 2 * halo; ++hr) {
+      const int tt = hr < halo ? halo - hr : T - 2 - (hr - halo);
+      row[tt] += h[hr];
+    }
+    if (yp) {
+      __nv_bfloat16* col = yp + (long long)b * T * cp_out + out_ch_off + g * out_ch_stride + c;
+      for (int hr = 0; hr < 2 * halo; ++hr) {
+        const int tt = hr < halo ? halo - hr : T - 2 - (hr - halo);
+        col[(long long)tt * cp_out] = __float2bfloat16(row[tt]);
+      }
+    }
+  }
+}
+
+extern "C" int tdvc_chain_fold(const float* halo_buf, float* y, void* yp, int groups, int B, int C, int T, int halo,
+                               int64_t y_grp_stride, int64_t y_b_stride, int cp_out, int out_ch_off, int out_ch_stride,
+                               void* stream) {
+  TDVC_CHECK_ARG(halo_buf && y && groups > 0 && B >= 0 && C > 0 && T > 0 && halo >= 0 && halo < T);
+  if (B == 0 || halo == 0) return TDVC_OK;
+  const long long n = (long long)groups * B * C;
+  const int blocks = (int)std::min<long long>((n + 127) / 128, 4LL * tdvc::num_sms());
+  tdvc::launch_k(chain_fold_k, blocks, 128, 0, (cudaStream_t)stream, halo_buf, y, (__nv_bfloat16*)yp, groups, B, C, T, halo,
+                 (long long)y_grp_stride, (long long)y_b_stride, cp_out, out_ch_off, out_ch_stride);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
 extern "C" int tdvc_conv1d_tc_fwd_ex(const tdvc_tc_conv* c, void* stream) {
   TDVC_CHECK_ARG(c && c->xp && c->wp && c->B >= 0 && c->Tp > 0 && c->Tout > 0 && c->K > 0 && c->dilation > 0);
   TDVC_CHECK_ARG(c->groups >= 1 && c->Cp_total % 8 == 0 && c->Cinp_g % 8 == 0 && c->Cinp_g > 0);
@@ -1208,17 +1412,44 @@ extern "C" int tdvc_conv1d_tc_fwd_ex(const tdvc_tc_conv* c, void* stream) {
   TDVC_CHECK_ARG(c->out_act >= 0 && c->out_act <= 2);
   if (c->out_packed) {
     TDVC_CHECK_ARG(c->yp && c->cp_out % 8 == 0 && c->out_ch_off % 16 == 0 && c->out_ch_stride % 16 == 0 &&
-                   ((uintptr_t)c->yp % 16 == 0) && c->out_act != TDVC_ACT_TANH && !c->gb && !c->residual);
+                   ((uintptr_t)c->yp % 16 == 0) && c->out_act != TDVC_ACT_TANH && (c->chain_mode || (!c->gb && !c->residual)));
     // every 16-channel chunk a thread stores must lie inside the row
     TDVC_CHECK_ARG(c->out_ch_off + (c->groups - 1) * c->out_ch_stride + c->Coutp_g <= c->cp_out);
   } else {
     TDVC_CHECK_ARG(c->y != nullptr);
-    if (c->groups > 1) TDVC_CHECK_ARG(!c->gb && !c->residual);
+    if (c->groups > 1 && !c->chain_mode) TDVC_CHECK_ARG(!c->gb && !c->residual);
   }
+  const int chain = c->chain_mode;
+  TDVC_CHECK_ARG(chain == 0 || (chain >= 3 && chain <= 6));
   if (c->maskp) {
     TDVC_CHECK_ARG(c->cm % 8 == 0 && c->mask_ch_off % 16 == 0 && c->mask_ch_stride % 16 == 0 && ((uintptr_t)c->maskp % 16 == 0));
     TDVC_CHECK_ARG(c->mask_ch_off + (c->groups - 1) * c->mask_ch_stride + c->Coutp_g <= c->cm);
-    TDVC_CHECK_ARG(!c->gb && !c->residual && c->out_act == TDVC_ACT_NONE);
+    if (!chain) TDVC_CHECK_ARG(!c->gb && !c->residual && c->out_act == TDVC_ACT_NONE);
+  }
+  if (chain) {
+    // a thread's 16 accumulator columns must all be real channels, rows of the packed tensors 16-byte aligned
+    TDVC_CHECK_ARG(c->Cout_g % 16 == 0 && c->Coutp_g == c->Cout_g);
+    if (chain == 3) TDVC_CHECK_ARG(c->out_packed && c->yp && (!c->yp2 || (uintptr_t)c->yp2 % 16 == 0));
+    if (chain == 4) {
+      TDVC_CHECK_ARG(!c->out_packed && c->y && c->residual);
+      if (c->yp) TDVC_CHECK_ARG(c->cp_out % 8 == 0 && c->out_ch_off % 8 == 0 && c->out_ch_stride % 8 == 0 && (uintptr_t)c->yp % 16 == 0 &&
+                                c->out_halo >= 0 && c->out_halo < c->Tout && c->tp_out >= c->Tout + 2 * c->out_halo);
+    }
+    if (chain == 5) {
+      TDVC_CHECK_ARG(c->out_packed && c->yp && c->maskp);
+      if (c->gb) TDVC_CHECK_ARG(c->auxp && c->dgbp && (uintptr_t)c->auxp % 16 == 0 && (uintptr_t)c->dgbp % 16 == 0 && c->dgb_cp % 8 == 0 &&
+                                c->dgb_ch_off % 8 == 0 && c->dgb_ch_stride % 8 == 0 &&
+                                c->dgb_ch_off + (c->groups - 1) * c->dgb_ch_stride + 2 * c->Cout_g <= c->dgb_cp);
+    }
+    if (chain == 6) {
+      TDVC_CHECK_ARG(!c->out_packed && c->y && c->maskp && c->halo >= 0 && c->t_valid > 0 && c->Tout == c->t_valid + 2 * c->halo);
+      TDVC_CHECK_ARG(c->halo == 0 || c->halo_buf != nullptr);
+      TDVC_CHECK_ARG(c->y_grp_stride != 0 || c->y_b_stride != 0);
+      if (c->yp) TDVC_CHECK_ARG(c->cp_out % 8 == 0 && c->out_ch_off % 8 == 0 && c->out_ch_stride % 8 == 0 && (uintptr_t)c->yp % 16 == 0);
+    }
+  }
+  for (int g = 0; g < 4; ++g) {
+    TDVC_CHECK_ARG(c->kg[g] >= 0 && c->kg[g] <= c->K && (c->kg[g] == 0 || ((c->K - c->kg[g]) % 2 == 0 && c->groups <= 4)));
   }
   if (c->B == 0) return TDVC_OK;
   TcP p{};
@@ -1251,6 +1482,11 @@ extern "C" int tdvc_conv1d_tc_fwd_ex(const tdvc_tc_conv* c, void* stream) {
   p.out_ch_off = c->out_ch_off; p.out_ch_stride = c->out_ch_stride;
   p.maskp = (const __nv_bfloat16*)c->maskp; p.tm = c->tm; p.cm = c->cm; p.mask_halo = c->mask_halo;
   p.mask_ch_off = c->mask_ch_off; p.mask_ch_stride = c->mask_ch_stride; p.mask_slope = c->mask_slope;
+  for (int g = 0; g < 4; ++g) p.kg[g] = c->kg[g];
+  p.gb_grp_stride = c->gb_grp_stride; p.res_grp_stride = c->res_grp_stride;
+  p.yp2 = (__nv_bfloat16*)c->yp2; p.auxp = (const __nv_bfloat16*)c->auxp; p.dgbp = (__nv_bfloat16*)c->dgbp;
+  p.dgb_cp = c->dgb_cp; p.dgb_ch_off = c->dgb_ch_off; p.dgb_ch_stride = c->dgb_ch_stride;
+  p.halo_buf = c->halo_buf; p.halo = c->halo; p.t_valid = c->t_valid; p.pk_slope = c->pk_slope;
   if (c->y_grp_stride == 0 && c->y_b_stride == 0) {      // default: group-major [groups][B][Cout_g][Tout]
     p.y_grp_stride = (long long)c->B * c->Cout_g * c->Tout;
     p.y_b_stride = (long long)c->Cout_g * c->Tout;
@@ -1304,7 +1540,11 @@ extern "C" int tdvc_conv1d_tc_fwd_ex(const tdvc_tc_conv* c, void* stream) {
       size_t smem_ws = (size_t)fixed + (size_t)st * a_stage + (2 * st + 2 * n_stages + 5) * sizeof(uint64_t) + 16 + 1024;
       typedef void (*WsFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, TcP, WsP);
       WsFn kern = nullptr;
-      if (!c->out_packed && !mask) {
+      if (chain == 3) kern = conv_tc_ws_k<1, 3, 1, 0>;
+      else if (chain == 4) kern = conv_tc_ws_k<0, 4, 0, 0>;
+      else if (chain == 5) kern = conv_tc_ws_k<0, 5, 1, 1>;
+      else if (chain == 6) kern = conv_tc_ws_k<0, 6, 0, 1>;
+      else if (!c->out_packed && !mask) {
         static const WsFn table[3][3] = {
             {conv_tc_ws_k<0, 0, 0, 0>, conv_tc_ws_k<0, 1, 0, 0>, conv_tc_ws_k<0, 2, 0, 0>},
             {conv_tc_ws_k<1, 0, 0, 0>, conv_tc_ws_k<1, 1, 0, 0>, conv_tc_ws_k<1, 2, 0, 0>},
@@ -1337,14 +1577,18 @@ extern "C" int tdvc_conv1d_tc_fwd_ex(const tdvc_tc_conv* c, void* stream) {
       TDVC_CHECK_ARG(grid.y <= 65535);
       tdvc::launch_k(kern, grid, TC_FWD_THREADS, smem_ws, (cudaStream_t)stream, map_a, map_b, map_an, map_bn, p, w);
       TDVC_LAUNCH_CHECK();
-      g_flops[FLOP_TC_WS] += 2.0 * c->B * c->Tout * (double)c->groups * c->Cout_g * c->Cinp_g * c->K;
+      g_flops[chain ? FLOP_TC_CHAIN : FLOP_TC_WS] += 2.0 * c->B * c->Tout * (double)c->Cout_g * c->Cinp_g * tc_taps(c);
       return TDVC_OK;
     }
   }
   size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, TcP);
   KernelFn kern = nullptr;
-  if (!c->out_packed && !mask) {
+  if (chain == 3) kern = conv_tc_fwd_k<1, 3, 1, 0>;
+  else if (chain == 4) kern = conv_tc_fwd_k<0, 4, 0, 0>;
+  else if (chain == 5) kern = conv_tc_fwd_k<0, 5, 1, 1>;
+  else if (chain == 6) kern = conv_tc_fwd_k<0, 6, 0, 1>;
+  else if (!c->out_packed && !mask) {
     static const KernelFn table[3][3] = {
         {conv_tc_fwd_k<0, 0, 0, 0>, conv_tc_fwd_k<0, 1, 0, 0>, conv_tc_fwd_k<0, 2, 0, 0>},
         {conv_tc_fwd_k<1, 0, 0, 0>, conv_tc_fwd_k<1, 1, 0, 0>, conv_tc_fwd_k<1, 2, 0, 0>},
@@ -1367,7 +1611,7 @@ extern "C" int tdvc_conv1d_tc_fwd_ex(const tdvc_tc_conv* c, void* stream) {
   TDVC_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535);
   tdvc::launch_k(kern, grid, TC_FWD_THREADS, smem, (cudaStream_t)stream, map_a, map_b, p);
   TDVC_LAUNCH_CHECK();
-  g_flops[FLOP_TC_TILE] += 2.0 * c->B * c->Tout * (double)c->groups * c->Cout_g * c->Cinp_g * c->K;
+  g_flops[chain ? FLOP_TC_CHAIN : FLOP_TC_TILE] += 2.0 * c->B * c->Tout * (double)c->Cout_g * c->Cinp_g * tc_taps(c);
   return TDVC_OK;
 }
 

@@ -38,6 +38,7 @@ struct Wg2P {
   long long ws_grp_stride;
   float* ws;
   int bias;
+  int k_inner;
 };
 
 __global__ void __launch_bounds__(W2_THREADS) conv_tc_wgrad2_k(const __grid_constant__ CUtensorMap map_x,
@@ -131,13 +132,27 @@ __global__ void __launch_bounds__(W2_THREADS) conv_tc_wgrad2_k(const __grid_cons
         if (elect_one()) {
           const uint32_t s_addr = smem_u32(smem + (size_t)s * stage_bytes);
           const uint32_t b_addr = s_addr + x_bytes;
-          for (int tp = 0; tp < ntaps; ++tp) {
-            // haloed: tap tp = the tile moved down by tp*dil rows; per tap: its own pair of boxes
-            const uint32_t a_addr = p.haloed ? s_addr + (uint32_t)(tp * p.dil) * 128u : s_addr + (uint32_t)(tp * 2 * x_box);
+          // k outermost: consecutive MMAs go to DIFFERENT accumulators (one per tap), so an instruction never waits for
+          // the one just issued -- MMAs that accumulate into the same TMEM tile are ~100 cycles apart at best
+          // (TDVC_WGRAD2_KINNER=1 restores the tap-outer order for A/B measurements)
+          if (!p.k_inner) {
             for (int k = 0; k < W2_TK / 16; ++k) {      // 16 time rows = 2048 B per MMA
-              const uint64_t da = make_sw128_mnmajor_desc(a_addr + k * 2048, (uint32_t)x_box);
               const uint64_t db = make_sw128_mnmajor_desc(b_addr + k * 2048, W2_BOX);
-              umma_bf16(tmem_base + (uint32_t)(tp * p.NT), da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+              for (int tp = 0; tp < ntaps; ++tp) {
+                // haloed: tap tp = the tile moved down by tp*dil rows; per tap: its own pair of boxes
+                const uint32_t a_addr = p.haloed ? s_addr + (uint32_t)(tp * p.dil) * 128u : s_addr + (uint32_t)(tp * 2 * x_box);
+                const uint64_t da = make_sw128_mnmajor_desc(a_addr + k * 2048, (uint32_t)x_box);
+                umma_bf16(tmem_base + (uint32_t)(tp * p.NT), da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+              }
+            }
+          } else {
+            for (int tp = 0; tp < ntaps; ++tp) {
+              const uint32_t a_addr = p.haloed ? s_addr + (uint32_t)(tp * p.dil) * 128u : s_addr + (uint32_t)(tp * 2 * x_box);
+              for (int k = 0; k < W2_TK / 16; ++k) {
+                const uint64_t da = make_sw128_mnmajor_desc(a_addr + k * 2048, (uint32_t)x_box);
+                const uint64_t db = make_sw128_mnmajor_desc(b_addr + k * 2048, W2_BOX);
+                umma_bf16(tmem_base + (uint32_t)(tp * p.NT), da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+              }
             }
           }
           if (do_bias) {
@@ -375,6 +390,9 @@ extern "C" int tdvc_conv1d_tc_wgrad2(const tdvc_tc_wgrad2* c, void* stream) {
     static int h = -1;      // TDVC_WGRAD2_HALOED=0: one shifted copy of the x tile per tap (development / A-B switch)
     if (h < 0) { const char* e = getenv("TDVC_WGRAD2_HALOED"); h = e ? atoi(e) : 1; }
     p.haloed = c->haloed >= 0 ? c->haloed : h;
+    static int ki = -1;
+    if (ki < 0) { const char* e = getenv("TDVC_WGRAD2_KINNER"); ki = e ? atoi(e) : 0; }
+    p.k_inner = ki;
   }
   const int xt = p.bias;
   p.nb_x = std::min(2, cdiv(c->Cin, 64));

@@ -264,6 +264,7 @@ class MRFBlock(nn.Module):
         super().__init__()
         self.blocks = nn.ModuleList([nn.ModuleList() for i in range(len(kernel_sizes))])
         self.has_cond = n_cond_const > 0 or n_cond_var > 0
+        self.kernel_sizes, self.dilations, self.n_channel = list(kernel_sizes), list(dilations), n_channel
         for i, kernel_size in enumerate(kernel_sizes):
             for dilation in dilations:
                 self.blocks[i].append(FiLMResnetBlock(n_channel, n_cond_const, n_cond_var, dilation, kernel_size,
@@ -322,7 +323,35 @@ class MRFBlock(nn.Module):
               for m in mods]
         return ops.mrf_cond_path(c, wb, slope=mods[0].cond_var[1].negative_slope)
 
+    def _fused_stage(self, x, c):
+        """bf16 mode: the whole stage as one autograd node whose intermediates stay bf16 channels-last (tdvc.ops._MRFStage),
+        or None when the stage is not of the form that path covers."""
+        if not x.is_cuda or (c is not None and (c.ndim != 3 or not self.has_cond)) or (c is None and self.has_cond):
+            return None
+        if not ops.mrf_stage_eligible(self.n_channel, x.shape[2], self.kernel_sizes, self.dilations, c is not None,
+                                      c.shape[1] if c is not None else 0):
+            return None
+        slopes = {m.conv[0].negative_slope for row in self.blocks for m in row} | \
+                 {m.posconv[0].negative_slope for row in self.blocks for m in row}
+        if len(slopes) != 1 or any(m.posconv[1].kernel_size != 1 for row in self.blocks for m in row):
+            return None
+        rows = []
+        for row in self.blocks:
+            r = []
+            for m in row:
+                t = (m.conv[1].effective_weight(), m.conv[1].bias, m.posconv[1].effective_weight(), m.posconv[1].bias)
+                if c is not None:
+                    t += (m.cond_var[0].effective_weight(), m.cond_var[0].bias, m.cond_var[2].effective_weight(),
+                          m.cond_var[2].bias)
+                r.append(t)
+            rows.append(r)
+        cond_slope = self.blocks[0][0].cond_var[1].negative_slope if c is not None else 0.2
+        return ops.mrf_stage(x, c, rows, self.kernel_sizes, self.dilations, slope=slopes.pop(), cond_slope=cond_slope)
+
     def forward(self, x, c=None):
+        y = self._fused_stage(x, c)
+        if y is not None:
+            return y
         gbs = self._fused_cond(c)
         if ops.branch_streams_enabled() and x.is_cuda and len(self.blocks) > 1:
             outs = self._forward_branches_concurrent(x, c, gbs)

@@ -31,7 +31,11 @@ class TcConv(C.Structure):
                [("out_slope", C.c_float)] + \
                [(n, C.c_int32) for n in ("out_packed", "tp_out", "cp_out", "out_halo", "out_ch_off", "out_ch_stride",
                                          "tm", "cm", "mask_halo", "mask_ch_off", "mask_ch_stride")] + \
-               [("mask_slope", C.c_float), ("y_grp_stride", C.c_int64), ("y_b_stride", C.c_int64)]
+               [("mask_slope", C.c_float), ("y_grp_stride", C.c_int64), ("y_b_stride", C.c_int64),
+                ("chain_mode", C.c_int32), ("kg", C.c_int32 * 4), ("gb_grp_stride", C.c_int64), ("res_grp_stride", C.c_int64),
+                ("yp2", C.c_void_p), ("auxp", C.c_void_p), ("dgbp", C.c_void_p), ("dgb_cp", C.c_int32),
+                ("dgb_ch_off", C.c_int32), ("dgb_ch_stride", C.c_int32), ("halo_buf", C.c_void_p), ("halo", C.c_int32),
+                ("t_valid", C.c_int32), ("pk_slope", C.c_float)]
 
 
 class TcWgrad2(C.Structure):
@@ -99,6 +103,7 @@ SIGNATURES = {
     "tdvc_space_to_depth": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "tdvc_depth_to_space": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "tdvc_conv1d_tc_fwd_ex": (_I, [C.POINTER(TcConv), _P]),
+    "tdvc_chain_fold": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _L, _L, _I, _I, _I, _P]),
     "tdvc_conv1d_tc_wgrad2_ws": (_L, [C.POINTER(TcWgrad2)]),
     "tdvc_conv1d_tc_wgrad2": (_I, [C.POINTER(TcWgrad2), _P]),
     "tdvc_frame_pack_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),

@@ -478,7 +478,7 @@ class _ConvTranspose1d(torch.autograd.Function):
 
 def conv_transpose1d(x, weight, bias=None, *, stride=1, padding=0, output_padding=0):
     if (_frame_conv_eligible(weight.shape[0], weight.shape[1], weight.shape[2], int(stride), 1, 1, False)
-            and int(output_padding) == 0 and tc_eligible(weight.shape[0], int(stride) * weight.shape[1], 1, 1)):
+            and weight.shape[2] % int(stride) == 0 and int(output_padding) == 0 and tc_eligible(weight.shape[0], int(stride) * weight.shape[1], 1, 1)):
         return _conv_transpose_as_frames(x, weight, bias, int(stride), int(padding))
     return _ConvTranspose1d.apply(x, weight, bias, int(stride), int(padding), int(output_padding))
 
@@ -1169,6 +1169,10 @@ class _Conv1dTC(torch.autograd.Function):
 def _tc_conv(**kw):
     c = _lib.TcConv()
     for k, v in kw.items():
+        if k == "kg":
+            for i, kk in enumerate(v):
+                c.kg[i] = int(kk)
+            continue
         setattr(c, k, v.data_ptr() if torch.is_tensor(v) else v)
     _lib.check(_lib.load().tdvc_conv1d_tc_fwd_ex(C.byref(c), _st()), "conv1d_tc_fwd_ex")
 
@@ -1427,6 +1431,131 @@ def wgrad2(*, dyp, xp, B, Cdp, Tout, Cp, Tp, Cout, Cin, K, dilation, ngroups=1, 
     _lib.check(lib.tdvc_conv1d_tc_wgrad2(C.byref(c), _st()), "conv1d_tc_wgrad2")
 
 
+def _cond_path_forward(c, slope, w0s, b0s, w2s, b2s):
+    """gamma|beta of all n FiLM blocks of a stage: gb[n, B, 2C, T] fp32 and what the backward needs (see _MRFCondPath)."""
+    n = len(w0s)
+    B, Cc, T = c.shape
+    K = w0s[0].shape[2]
+    C2 = w2s[0].shape[0]
+    if K != 3 or any(tuple(w.shape) != (Cc, Cc, 3) for w in w0s) or any(tuple(w.shape) != (C2, Cc, 3) for w in w2s):
+        raise RuntimeError("mrf_cond_path: unexpected cond_var geometry")
+    lib = _lib.load()
+    dev = c.device
+    Cg = _ceil(Cc + 1, 16)              # per-block channel pitch; channel Cc is the constant-one channel
+    C2p = _ceil(C2, 16)
+    # operands
+    cp = torch.empty(B, T, Cg, device=dev, dtype=torch.bfloat16)
+    _lib.check(lib.tdvc_pack_cl_bf16(_p(c), _p(cp), B, Cc, T, Cg, 0, PAD_ZEROS, 1.0, None, 0, Cg, Cc, None, _st()), "pack c")
+    # cond_var.0 weights: stacked densely (pitch Cc, kernel with the weights as the M operand) when they fit, else at
+    # the padded pitch Cg of the time-as-M kernels.  Blocks are packed in order: block j+1 overwrites the Cg - Cc
+    # zero rows block j's pack wrote past its end.
+    stacked = _STACKED_COND and Cg >= 64 and K * 128 * Cg * 2 + 2 * (256 + 8 * K) * 128 + 3 * 272 * 32 <= 220 * 1024
+    pitch0 = Cc if stacked else Cg
+    R0 = (n - 1) * pitch0 + Cg
+
+    def pack_fwd():
+        w0p = torch.empty(K, R0, Cg, device=dev, dtype=torch.bfloat16)
+        w2p = torch.empty(K, n * C2p, Cg, device=dev, dtype=torch.bfloat16)
+        b0p = torch.zeros(R0, device=dev, dtype=torch.float32)
+        b2p = torch.zeros(n * C2p, device=dev, dtype=torch.float32)
+        for j in range(n):
+            w0, w2 = _c(w0s[j]), _c(w2s[j])
+            _lib.check(lib.tdvc_pack_weight_bf16(_p(w0), _p(w0p), Cc, Cc, K, Cg, Cg, 0, R0, j * pitch0, Cg, 0, _st()), "pack w0")
+            _lib.check(lib.tdvc_pack_weight_bf16(_p(w2), _p(w2p), C2, Cc, K, C2p, Cg, 0, n * C2p, j * C2p, Cg, 0, _st()), "pack w2")
+            if b0s[j] is not None:
+                b0p[j * pitch0:j * pitch0 + Cc].copy_(b0s[j])
+            if b2s[j] is not None:
+                b2p[j * C2p:j * C2p + C2].copy_(b2s[j])
+        return w0p, w2p, b0p, b2p
+
+    # the generator runs several times per training iteration on the same weights: packed once per step scope
+    w0p, w2p, b0p, b2p = _step_cached(("cond_fwd", stacked), list(w0s) + list(w2s) + list(b0s) + list(b2s), pack_fwd)
+    # all cond_var.0 convs: packed bf16 output g1p[B, T, n*Cg] = leaky_relu(conv + bias)
+    g1p = torch.empty(B, T, n * Cg, device=dev, dtype=torch.bfloat16)
+    if stacked:
+        _lib.check(lib.tdvc_conv1d_tc_fwd_stacked(_p(cp), _p(w0p), _p(b0p), _p(g1p), B, Cg, 0, Cg, T, T, K, 1, -1, R0, n, Cc,
+                                                  ACT_LRELU, slope, T, n * Cg, 0, 0, Cg, _st()), "conv1d_tc_fwd_stacked")
+    else:
+        _tc_conv(xp=cp, wp=w0p, bias=b0p, B=B, Tp=T, Tout=T, K=K, dilation=1, t_off=-1, Cp_total=Cg, groups=1,
+                 a_ch_off=0, a_ch_stride=0, Cinp_g=Cg, Cout_g=n * Cg, Coutp_g=n * Cg, bias_stride=0,
+                 out_act=ACT_LRELU, out_slope=slope, out_packed=1, yp=g1p, tp_out=T, cp_out=n * Cg, out_halo=0,
+                 out_ch_off=0, out_ch_stride=0)
+    # all cond_var.2 convs, grouped: gb[n, B, 2C, T]
+    gb = torch.empty(n, B, C2, T, device=dev, dtype=torch.float32)
+    _tc_conv(xp=g1p, wp=w2p, bias=b2p, y=gb, B=B, Tp=T, Tout=T, K=K, dilation=1, t_off=-1, Cp_total=n * Cg, groups=n,
+             a_ch_off=0, a_ch_stride=Cg, Cinp_g=Cg, Cout_g=C2, Coutp_g=C2p, bias_stride=C2p, out_act=ACT_NONE,
+             out_slope=1.0, out_packed=0)
+    dims = (n, B, Cc, T, K, C2, Cg, C2p, slope)
+    return gb, dims, cp, g1p
+
+
+def _cond_path_backward(dims, cp, g1p, w0s, w2s, has_b0, has_b2, dgbp, need_dc):
+    """dgbp[B, T, n*C2p]: packed bf16 dL/d(gamma|beta) of every block.  Returns (dL/dc or None, flat per-block gradient
+    list [dw0, db0, dw2, db2] * n)."""
+    n, B, Cc, T, K, C2, Cg, C2p, slope = dims
+    lib = _lib.load()
+    dev = cp.device
+    db2 = torch.empty(n, C2, device=dev, dtype=torch.float32)
+    # cond_var.2 weight gradients (their bias gradients come out of the same GEMM through a tap of ones)
+    dw2 = []
+    if _USE_WGRAD2:
+        # the n blocks' cond_var.2 weight (+ bias) gradients: ONE grouped launch
+        dw2_all = torch.empty(n, C2, Cc, K, device=dev, dtype=torch.float32)
+        wgrad2(dyp=dgbp, xp=g1p, B=B, Cdp=n * C2p, Tout=T, Cp=n * Cg, Tp=T, Cout=C2, Cin=Cc, K=K, dilation=1, ngroups=n,
+               x_ch_stride=Cg, dy_ch_stride=C2p, t_off=[-1], dw=[dw2_all], db=[db2], dw_grp_stride=C2 * Cc * K,
+               db_grp_stride=C2)
+        dw2 = [dw2_all[j] for j in range(n)]
+    else:
+        ws, wz = _wgrad_ws(max(lib.tdvc_conv1d_tc_wgrad_ws(C2, Cc, K), lib.tdvc_conv1d_tc_wgrad_ws(n * Cg, Cc + 1, K)), dev)
+        for j in range(n):
+            g = torch.empty(C2, Cc, K, device=dev, dtype=torch.float32)
+            _lib.check(lib.tdvc_conv1d_tc_wgrad(_p(dgbp), _p(g1p), _p(g), _p(ws), B, n * C2p, T, n * Cg, T, C2, Cc, K, 1, -1,
+                                                j * Cg, j * C2p, _p(db2[j]), wz, _st()), "wgrad cond_var.2")
+            dw2.append(g)
+
+    # dL/dg1 (packed, LeakyReLU mask applied in the epilogue): grouped dgrad of cond_var.2
+    def pack_bwd():
+        w2tp = torch.empty(K, n * Cg, C2p, device=dev, dtype=torch.bfloat16)
+        w0tp = torch.empty(K, Cg, n * Cg, device=dev, dtype=torch.bfloat16)
+        for j in range(n):
+            _lib.check(lib.tdvc_pack_weight_bf16(_p(w2s[j]), _p(w2tp), C2, Cc, K, C2p, Cg, 1, n * Cg, j * Cg, C2p, 0, _st()),
+                       "pack w2^T")
+            _lib.check(lib.tdvc_pack_weight_bf16(_p(w0s[j]), _p(w0tp), Cc, Cc, K, Cg, Cg, 1, Cg, 0, n * Cg, j * Cg, _st()),
+                       "pack w0^T")
+        return w2tp, w0tp
+
+    w2tp, w0tp = _step_cached(("cond_bwd",), list(w0s) + list(w2s), pack_bwd)
+    dg1p = torch.empty(B, T, n * Cg, device=dev, dtype=torch.bfloat16)
+    _tc_conv(xp=dgbp, wp=w2tp, B=B, Tp=T, Tout=T, K=K, dilation=1, t_off=-1, Cp_total=n * C2p, groups=n, a_ch_off=0,
+             a_ch_stride=C2p, Cinp_g=C2p, Cout_g=Cg, Coutp_g=Cg, bias_stride=0, out_act=ACT_NONE, out_slope=1.0,
+             out_packed=1, yp=dg1p, tp_out=T, cp_out=n * Cg, out_halo=0, out_ch_off=0, out_ch_stride=Cg,
+             maskp=g1p, tm=T, cm=n * Cg, mask_halo=0, mask_ch_off=0, mask_ch_stride=Cg, mask_slope=slope)
+    # cond_var.0 weight (+ bias, through the constant-one channel of cp) gradients: one GEMM for all blocks
+    dw0_all = torch.empty(n * Cg, Cc + 1, K, device=dev, dtype=torch.float32)
+    if _USE_WGRAD2:
+        wgrad2(dyp=dg1p, xp=cp, B=B, Cdp=n * Cg, Tout=T, Cp=Cg, Tp=T, Cout=n * Cg, Cin=Cc + 1, K=K, dilation=1, t_off=[-1],
+               dw=[dw0_all], db=[None])
+    else:
+        ws, wz = _wgrad_ws(max(lib.tdvc_conv1d_tc_wgrad_ws(C2, Cc, K), lib.tdvc_conv1d_tc_wgrad_ws(n * Cg, Cc + 1, K)), dev)
+        _lib.check(lib.tdvc_conv1d_tc_wgrad(_p(dg1p), _p(cp), _p(dw0_all), _p(ws), B, n * Cg, T, Cg, T, n * Cg, Cc + 1, K, 1,
+                                            -1, 0, 0, None, wz, _st()), "wgrad cond_var.0")
+    # dL/dc: one conv over the n*Cg concatenated channels (sums the blocks' contributions in the GEMM)
+    dc = None
+    if need_dc:
+        dc = torch.empty(B, Cc, T, device=dev, dtype=torch.float32)
+        _tc_conv(xp=dg1p, wp=w0tp, y=dc, B=B, Tp=T, Tout=T, K=K, dilation=1, t_off=-1, Cp_total=n * Cg, groups=1,
+                 a_ch_off=0, a_ch_stride=0, Cinp_g=n * Cg, Cout_g=Cc, Coutp_g=Cg, bias_stride=0, out_act=ACT_NONE,
+                 out_slope=1.0, out_packed=0)
+    grads = []
+    for j in range(n):
+        blk = dw0_all[j * Cg:j * Cg + Cc]
+        grads.append(blk[:, :Cc, :].contiguous())
+        grads.append(blk[:, Cc, (K - 1) // 2].contiguous() if has_b0[j] else None)
+        grads.append(dw2[j])
+        grads.append(db2[j] if has_b2[j] else None)
+    return dc, grads
+
+
 class _MRFCondPath(torch.autograd.Function):
     """(gamma|beta)_j = cond_var_j[2](leaky_relu(cond_var_j[0](c)))  for all n FiLM blocks of one MRF stage
     (model/generator.py:85-92,102), which all read the same conditioning tensor c[B, Cc, T]:
@@ -1434,9 +1563,9 @@ class _MRFCondPath(torch.autograd.Function):
       forward   1 pack of c, ONE tcgen05 launch for the n `cond_var.0` convs (N = n*144) whose epilogue applies bias +
                 LeakyReLU and writes the next conv's bf16 channels-last operand directly, ONE grouped launch for the n
                 `cond_var.2` convs -> gb[n, B, 2C, T] fp32.
-      backward  n packs of dL/dgb (they also give cond_var.2's bias gradients), one grouped dgrad launch whose epilogue
-                applies the LeakyReLU mask and writes packed dL/dg1, n + 1 wgrad launches (the n `cond_var.0` weight
-                gradients are one GEMM; their bias gradients ride along through a constant-one input channel), and one
+      backward  n packs of dL/dgb, one grouped dgrad launch whose epilogue applies the LeakyReLU mask and writes packed
+                dL/dg1, the weight-gradient launches (cond_var.2: one grouped launch, bias gradients through a tap of ones;
+                cond_var.0: one GEMM for all blocks, bias gradients through a constant-one input channel), and one
                 dgrad launch over the concatenated 1296 channels, which also sums the n blocks' contributions to dL/dc.
     Intermediates never exist in fp32."""
 
@@ -1446,57 +1575,8 @@ class _MRFCondPath(torch.autograd.Function):
         w0s, b0s, w2s, b2s = wb[0::4], wb[1::4], wb[2::4], wb[3::4]
         _req(c, *wb)
         c = _c(c)
-        B, Cc, T = c.shape
-        K = w0s[0].shape[2]
-        C2 = w2s[0].shape[0]
-        if K != 3 or any(tuple(w.shape) != (Cc, Cc, 3) for w in w0s) or any(tuple(w.shape) != (C2, Cc, 3) for w in w2s):
-            raise RuntimeError("mrf_cond_path: unexpected cond_var geometry")
-        lib = _lib.load()
-        dev = c.device
-        Cg = _ceil(Cc + 1, 16)              # per-block channel pitch; channel Cc is the constant-one channel
-        C2p = _ceil(C2, 16)
-        # operands
-        cp = torch.empty(B, T, Cg, device=dev, dtype=torch.bfloat16)
-        _lib.check(lib.tdvc_pack_cl_bf16(_p(c), _p(cp), B, Cc, T, Cg, 0, PAD_ZEROS, 1.0, None, 0, Cg, Cc, None, _st()), "pack c")
-        # cond_var.0 weights: stacked densely (pitch Cc, kernel with the weights as the M operand) when they fit, else at
-        # the padded pitch Cg of the time-as-M kernels.  Blocks are packed in order: block j+1 overwrites the Cg - Cc
-        # zero rows block j's pack wrote past its end.
-        stacked = _STACKED_COND and Cg >= 64 and K * 128 * Cg * 2 + 2 * (256 + 8 * K) * 128 + 3 * 272 * 32 <= 220 * 1024
-        pitch0 = Cc if stacked else Cg
-        R0 = (n - 1) * pitch0 + Cg
-        def pack_fwd():
-            w0p = torch.empty(K, R0, Cg, device=dev, dtype=torch.bfloat16)
-            w2p = torch.empty(K, n * C2p, Cg, device=dev, dtype=torch.bfloat16)
-            b0p = torch.zeros(R0, device=dev, dtype=torch.float32)
-            b2p = torch.zeros(n * C2p, device=dev, dtype=torch.float32)
-            for j in range(n):
-                w0, w2 = _c(w0s[j]), _c(w2s[j])
-                _lib.check(lib.tdvc_pack_weight_bf16(_p(w0), _p(w0p), Cc, Cc, K, Cg, Cg, 0, R0, j * pitch0, Cg, 0, _st()), "pack w0")
-                _lib.check(lib.tdvc_pack_weight_bf16(_p(w2), _p(w2p), C2, Cc, K, C2p, Cg, 0, n * C2p, j * C2p, Cg, 0, _st()), "pack w2")
-                if b0s[j] is not None:
-                    b0p[j * pitch0:j * pitch0 + Cc].copy_(b0s[j])
-                if b2s[j] is not None:
-                    b2p[j * C2p:j * C2p + C2].copy_(b2s[j])
-            return w0p, w2p, b0p, b2p
-
-        # the generator runs several times per training iteration on the same weights: packed once per step scope
-        w0p, w2p, b0p, b2p = _step_cached(("cond_fwd", stacked), list(w0s) + list(w2s) + list(b0s) + list(b2s), pack_fwd)
-        # all cond_var.0 convs: packed bf16 output g1p[B, T, n*Cg] = leaky_relu(conv + bias)
-        g1p = torch.empty(B, T, n * Cg, device=dev, dtype=torch.bfloat16)
-        if stacked:
-            _lib.check(lib.tdvc_conv1d_tc_fwd_stacked(_p(cp), _p(w0p), _p(b0p), _p(g1p), B, Cg, 0, Cg, T, T, K, 1, -1, R0, n, Cc,
-                                                      ACT_LRELU, slope, T, n * Cg, 0, 0, Cg, _st()), "conv1d_tc_fwd_stacked")
-        else:
-            _tc_conv(xp=cp, wp=w0p, bias=b0p, B=B, Tp=T, Tout=T, K=K, dilation=1, t_off=-1, Cp_total=Cg, groups=1,
-                     a_ch_off=0, a_ch_stride=0, Cinp_g=Cg, Cout_g=n * Cg, Coutp_g=n * Cg, bias_stride=0,
-                     out_act=ACT_LRELU, out_slope=slope, out_packed=1, yp=g1p, tp_out=T, cp_out=n * Cg, out_halo=0,
-                     out_ch_off=0, out_ch_stride=0)
-        # all cond_var.2 convs, grouped: gb[n, B, 2C, T]
-        gb = torch.empty(n, B, C2, T, device=dev, dtype=torch.float32)
-        _tc_conv(xp=g1p, wp=w2p, bias=b2p, y=gb, B=B, Tp=T, Tout=T, K=K, dilation=1, t_off=-1, Cp_total=n * Cg, groups=n,
-                 a_ch_off=0, a_ch_stride=Cg, Cinp_g=Cg, Cout_g=C2, Coutp_g=C2p, bias_stride=C2p, out_act=ACT_NONE,
-                 out_slope=1.0, out_packed=0)
-        ctx.dims = (n, B, Cc, T, K, C2, Cg, C2p, slope)
+        gb, dims, cp, g1p = _cond_path_forward(c, slope, w0s, b0s, w2s, b2s)
+        ctx.dims = dims
         ctx.has_b0 = [b is not None for b in b0s]
         ctx.has_b2 = [b is not None for b in b2s]
         ctx.save_for_backward(cp, g1p, *[_c(w) for w in w0s], *[_c(w) for w in w2s])
@@ -1509,10 +1589,8 @@ class _MRFCondPath(torch.autograd.Function):
         cp, g1p = saved[0], saved[1]
         w0s, w2s = saved[2:2 + n], saved[2 + n:2 + 2 * n]
         lib = _lib.load()
-        dev = cp.device
-        # dL/dgb -> packed bf16 (cond_var.2's bias gradients come out of its wgrad GEMM below)
-        dgbp = torch.empty(B, T, n * C2p, device=dev, dtype=torch.bfloat16)
-        db2 = torch.empty(n, C2, device=dev, dtype=torch.float32)
+        # dL/dgb -> packed bf16
+        dgbp = torch.empty(B, T, n * C2p, device=cp.device, dtype=torch.bfloat16)
         for j in range(n):
             if dgb[j] is None:
                 dgbp[:, :, j * C2p:(j + 1) * C2p].zero_()
@@ -1520,61 +1598,7 @@ class _MRFCondPath(torch.autograd.Function):
             d = _c(dgb[j])
             _lib.check(lib.tdvc_pack_cl_bf16(_p(d), _p(dgbp), B, C2, T, n * C2p, 0, PAD_ZEROS, 1.0, None, j * C2p, C2p,
                                              -1, None, _st()), "pack dgb")
-        # cond_var.2 weight gradients
-        dw2 = []
-        if _USE_WGRAD2:
-            # the n blocks' cond_var.2 weight (+ bias) gradients: ONE grouped launch
-            dw2_all = torch.empty(n, C2, Cc, K, device=dev, dtype=torch.float32)
-            wgrad2(dyp=dgbp, xp=g1p, B=B, Cdp=n * C2p, Tout=T, Cp=n * Cg, Tp=T, Cout=C2, Cin=Cc, K=K, dilation=1, ngroups=n,
-                   x_ch_stride=Cg, dy_ch_stride=C2p, t_off=[-1], dw=[dw2_all], db=[db2], dw_grp_stride=C2 * Cc * K,
-                   db_grp_stride=C2)
-            dw2 = [dw2_all[j] for j in range(n)]
-        else:
-            ws, wz = _wgrad_ws(max(lib.tdvc_conv1d_tc_wgrad_ws(C2, Cc, K), lib.tdvc_conv1d_tc_wgrad_ws(n * Cg, Cc + 1, K)), dev)
-            for j in range(n):
-                g = torch.empty(C2, Cc, K, device=dev, dtype=torch.float32)
-                _lib.check(lib.tdvc_conv1d_tc_wgrad(_p(dgbp), _p(g1p), _p(g), _p(ws), B, n * C2p, T, n * Cg, T, C2, Cc, K, 1, -1,
-                                                    j * Cg, j * C2p, _p(db2[j]), wz, _st()), "wgrad cond_var.2")
-                dw2.append(g)
-        # dL/dg1 (packed, LeakyReLU mask applied in the epilogue): grouped dgrad of cond_var.2
-        def pack_bwd():
-            w2tp = torch.empty(K, n * Cg, C2p, device=dev, dtype=torch.bfloat16)
-            w0tp = torch.empty(K, Cg, n * Cg, device=dev, dtype=torch.bfloat16)
-            for j in range(n):
-                _lib.check(lib.tdvc_pack_weight_bf16(_p(w2s[j]), _p(w2tp), C2, Cc, K, C2p, Cg, 1, n * Cg, j * Cg, C2p, 0, _st()),
-                           "pack w2^T")
-                _lib.check(lib.tdvc_pack_weight_bf16(_p(w0s[j]), _p(w0tp), Cc, Cc, K, Cg, Cg, 1, Cg, 0, n * Cg, j * Cg, _st()),
-                           "pack w0^T")
-            return w2tp, w0tp
-
-        w2tp, w0tp = _step_cached(("cond_bwd",), list(w0s) + list(w2s), pack_bwd)
-        dg1p = torch.empty(B, T, n * Cg, device=dev, dtype=torch.bfloat16)
-        _tc_conv(xp=dgbp, wp=w2tp, B=B, Tp=T, Tout=T, K=K, dilation=1, t_off=-1, Cp_total=n * C2p, groups=n, a_ch_off=0,
-                 a_ch_stride=C2p, Cinp_g=C2p, Cout_g=Cg, Coutp_g=Cg, bias_stride=0, out_act=ACT_NONE, out_slope=1.0,
-                 out_packed=1, yp=dg1p, tp_out=T, cp_out=n * Cg, out_halo=0, out_ch_off=0, out_ch_stride=Cg,
-                 maskp=g1p, tm=T, cm=n * Cg, mask_halo=0, mask_ch_off=0, mask_ch_stride=Cg, mask_slope=slope)
-        # cond_var.0 weight (+ bias, through the constant-one channel of cp) gradients: one GEMM for all blocks
-        dw0_all = torch.empty(n * Cg, Cc + 1, K, device=dev, dtype=torch.float32)
-        if _USE_WGRAD2:
-            wgrad2(dyp=dg1p, xp=cp, B=B, Cdp=n * Cg, Tout=T, Cp=Cg, Tp=T, Cout=n * Cg, Cin=Cc + 1, K=K, dilation=1, t_off=[-1],
-                   dw=[dw0_all], db=[None])
-        else:
-            _lib.check(lib.tdvc_conv1d_tc_wgrad(_p(dg1p), _p(cp), _p(dw0_all), _p(ws), B, n * Cg, T, Cg, T, n * Cg, Cc + 1, K, 1,
-                                                -1, 0, 0, None, wz, _st()), "wgrad cond_var.0")
-        # dL/dc: one conv over the n*Cg concatenated channels (sums the blocks' contributions in the GEMM)
-        dc = None
-        if ctx.needs_input_grad[0]:
-            dc = torch.empty(B, Cc, T, device=dev, dtype=torch.float32)
-            _tc_conv(xp=dg1p, wp=w0tp, y=dc, B=B, Tp=T, Tout=T, K=K, dilation=1, t_off=-1, Cp_total=n * Cg, groups=1,
-                     a_ch_off=0, a_ch_stride=0, Cinp_g=n * Cg, Cout_g=Cc, Coutp_g=Cg, bias_stride=0, out_act=ACT_NONE,
-                     out_slope=1.0, out_packed=0)
-        grads = []
-        for j in range(n):
-            blk = dw0_all[j * Cg:j * Cg + Cc]
-            grads.append(blk[:, :Cc, :].contiguous())
-            grads.append(blk[:, Cc, (K - 1) // 2].contiguous() if ctx.has_b0[j] else None)
-            grads.append(dw2[j])
-            grads.append(db2[j] if ctx.has_b2[j] else None)
+        dc, grads = _cond_path_backward(ctx.dims, cp, g1p, w0s, w2s, ctx.has_b0, ctx.has_b2, dgbp, ctx.needs_input_grad[0])
         return (dc, None, *grads)
 
 
@@ -1589,6 +1613,253 @@ def mrf_cond_path(c, blocks_wb, slope=0.2):
 
 def mrf_cond_path_eligible(Cc, C2, T) -> bool:
     return _PRECISION == "bf16" and Cc >= 16 and C2 >= 16 and _ceil(C2, 16) <= 256
+
+
+# ----------------------------------------------------------------------------- the bf16-resident MRF stage
+
+_MRF_CHAIN = os.environ.get("TDVC_MRF_CHAIN", "1") != "0"       # development switch: 0 = block-by-block path
+
+
+def mrf_stage_eligible(C, T, kernel_sizes, dilations, has_cond, Cc=0) -> bool:
+    """The whole-stage path needs bf16 mode, channel counts that are multiples of 16 (a thread's 16 accumulator columns
+    are real channels), up to 4 kernel sizes of the same parity, and reflect halos shorter than the signal."""
+    if _PRECISION != "bf16" or not _MRF_CHAIN or C % 16 or C > 256 or not (1 <= len(kernel_sizes) <= 4):
+        return False
+    kmax = max(kernel_sizes)
+    if any(k % 2 == 0 or k < 1 for k in kernel_sizes) or any(d < 1 for d in dilations):
+        return False
+    if max(dilations) * (kmax - 1) // 2 >= T or 64 + (kmax - 1) * max(dilations) > 256:
+        return False
+    if has_cond and not mrf_cond_path_eligible(Cc, 2 * C, T):
+        return False
+    return True
+
+
+def _chain_weights(ws_f32, bs, G, Cx, Kmax, ks):
+    """Grouped operands of one depth: wp[Kmax][G*Cx][Cx] (forward; branch i's k_i taps centred, zeros around them),
+    wtp[Kmax][G*Cx][Cx] (data gradient: rows = input channels, taps reversed) and the concatenated bias [G*Cx]."""
+    lib = _lib.load()
+    dev = ws_f32[0].device
+    wp = torch.zeros(Kmax, G * Cx, Cx, device=dev, dtype=torch.bfloat16)
+    wtp = torch.zeros(Kmax, G * Cx, Cx, device=dev, dtype=torch.bfloat16)
+    bias = torch.zeros(G * Cx, device=dev, dtype=torch.float32)
+    for i in range(G):
+        w = _c(ws_f32[i])
+        off = (Kmax - ks[i]) // 2 * (G * Cx * Cx) * 2             # bytes: the first of the centred taps
+        _lib.check(lib.tdvc_pack_weight_bf16(_p(w), C.c_void_p(wp.data_ptr() + off), Cx, Cx, ks[i], Cx, Cx, 0, G * Cx, i * Cx, Cx, 0,
+                                             _st()), "pack chain w")
+        _lib.check(lib.tdvc_pack_weight_bf16(_p(w), C.c_void_p(wtp.data_ptr() + off), Cx, Cx, ks[i], Cx, Cx, 1, G * Cx, i * Cx, Cx, 0,
+                                             _st()), "pack chain w^T")
+        if bs[i] is not None:
+            bias[i * Cx:(i + 1) * Cx].copy_(bs[i])
+    return wp, wtp, bias
+
+
+class _MRFStage(torch.autograd.Function):
+    """One MRFBlock (model/generator.py:175-194): G kernel-size branches of D chained FiLM residual blocks
+    (model/generator.py:69-111), averaged -- as ONE autograd node whose tensors between the convolutions are bf16
+    channels-last, the G branches side by side in the channel dimension, each depth ONE launch per convolution for all
+    branches (group = branch, per-group tap count):
+
+      forward   pack(x) -> per depth: [conv.1 + bias, FiLM, LeakyReLU -> packed]  [posconv.1 + bias + residual -> fp32
+                residual stream + packed LeakyReLU copy with the next conv's reflect halo]  -> mean of the branches
+      backward  per depth, last to first: posconv weight gradients (grouped), [posconv^T with the LeakyReLU mask and the
+                FiLM backward in its epilogue -> packed dL/dh0, packed dL/d(gamma|beta)], conv.1 weight gradients (grouped),
+                [conv.1^T over the padded rows with the LeakyReLU mask and the residual gradient added -> fp32 + packed],
+                reflect fold; then the conditioning path's backward on the packed dL/d(gamma|beta).
+    The fp32 NCW activations h0 / FiLM output / LeakyReLU inputs of the block-by-block path, their pack passes and the
+    reflect-fold / mask passes do not exist here."""
+
+    @staticmethod
+    def forward(ctx, x, c, slope, cond_slope, ks, ds, *wb):
+        G, D = len(ks), len(ds)
+        has_cond = c is not None
+        per = 8 if has_cond else 4
+        assert len(wb) == per * G * D
+        _req(x, c, *wb)
+        x = _c(x)
+        B, Cc_x, T = x.shape
+        Cx = Cc_x
+        lib = _lib.load()
+        dev = x.device
+        Kmax = max(ks)
+        H = [(Kmax - 1) // 2 * d for d in ds]
+        blk = lambda i, j: wb[per * (i * D + j): per * (i * D + j + 1)]
+        # ---- conditioning path: gamma|beta of every block, block index i*D + j
+        gb = cdims = cp = g1p = None
+        if has_cond:
+            c = _c(c)
+            w0s = [blk(i, j)[4] for i in range(G) for j in range(D)]
+            b0s = [blk(i, j)[5] for i in range(G) for j in range(D)]
+            w2s = [blk(i, j)[6] for i in range(G) for j in range(D)]
+            b2s = [blk(i, j)[7] for i in range(G) for j in range(D)]
+            gb, cdims, cp, g1p = _cond_path_forward(c, cond_slope, w0s, b0s, w2s, b2s)
+        gb_blk = B * 2 * Cx * T                                      # elements of one block's gamma|beta
+        # ---- operands of the chain (once per step scope)
+        wconv, wpos = [], []
+        for j in range(D):
+            cw = [blk(i, j)[0] for i in range(G)]
+            cb = [blk(i, j)[1] for i in range(G)]
+            pw = [blk(i, j)[2] for i in range(G)]
+            pb = [blk(i, j)[3] for i in range(G)]
+            wconv.append(_step_cached(("chain_conv", Kmax, tuple(ks)), cw + cb, lambda: _chain_weights(cw, cb, G, Cx, Kmax, ks)))
+            wpos.append(_step_cached(("chain_pos",), pw + pb, lambda: _chain_weights(pw, pb, G, Cx, 1, [1] * G)))
+        # ---- depth 0 operand: LeakyReLU(x) with the reflect halo, C channels shared by the G branches
+        X = [torch.empty(B, T + 2 * H[0], Cx, device=dev, dtype=torch.bfloat16)]
+        _lib.check(lib.tdvc_pack_cl_bf16(_p(x), _p(X[0]), B, Cx, T, Cx, H[0], PAD_REFLECT if H[0] > 0 else PAD_ZEROS, slope, None,
+                                         0, 0, -1, None, _st()), "pack x")
+        a1, h0 = [], []
+        res, res_stride = x, 0
+        xs = None
+        for j in range(D):
+            a1j = torch.empty(B, T, G * Cx, device=dev, dtype=torch.bfloat16)
+            h0j = torch.empty(B, T, G * Cx, device=dev, dtype=torch.bfloat16) if has_cond else None
+            kw = dict(xp=X[j], wp=wconv[j][0], bias=wconv[j][2], B=B, Tp=T + 2 * H[j], Tout=T, K=Kmax, dilation=ds[j], t_off=0,
+                      Cp_total=X[j].shape[2], groups=G, a_ch_off=0, a_ch_stride=(0 if j == 0 else Cx), Cinp_g=Cx, Cout_g=Cx,
+                      Coutp_g=Cx, bias_stride=Cx, out_act=ACT_LRELU, out_slope=slope, out_packed=1, yp=a1j, tp_out=T,
+                      cp_out=G * Cx, out_halo=0, out_ch_off=0, out_ch_stride=Cx, chain_mode=3, kg=ks)
+            if has_cond:
+                kw.update(gb=gb.data_ptr() + 4 * j * gb_blk, gb_grp_stride=D * gb_blk, yp2=h0j)
+            _tc_conv(**kw)
+            xs = torch.empty(G, B, Cx, T, device=dev, dtype=torch.float32)
+            Hn = H[j + 1] if j + 1 < D else 0
+            Xn = torch.empty(B, T + 2 * Hn, G * Cx, device=dev, dtype=torch.bfloat16) if j + 1 < D else None
+            kw = dict(xp=a1j, wp=wpos[j][0], bias=wpos[j][2], residual=res, y=xs, B=B, Tp=T, Tout=T, K=1, dilation=1, t_off=0,
+                      Cp_total=G * Cx, groups=G, a_ch_off=0, a_ch_stride=Cx, Cinp_g=Cx, Cout_g=Cx, Coutp_g=Cx, bias_stride=Cx,
+                      out_act=ACT_NONE, out_slope=1.0, out_packed=0, chain_mode=4, res_grp_stride=res_stride,
+                      y_grp_stride=B * Cx * T, y_b_stride=Cx * T, pk_slope=slope)
+            if Xn is not None:
+                kw.update(yp=Xn, tp_out=T + 2 * Hn, cp_out=G * Cx, out_halo=Hn, out_ch_off=0, out_ch_stride=Cx)
+                X.append(Xn)
+            _tc_conv(**kw)
+            a1.append(a1j)
+            h0.append(h0j)
+            res, res_stride = xs, B * Cx * T
+        y = torch.empty(B, Cx, T, device=dev, dtype=torch.float32)
+        ptr = lambda i: C.c_void_p(xs.data_ptr() + 4 * i * B * Cx * T)
+        if G <= 3:
+            _lib.check(lib.tdvc_add3_scale(ptr(0), ptr(1) if G > 1 else None, ptr(2) if G > 2 else None, _p(y), y.numel(),
+                                           1.0 / G, _st()), "mrf mean")
+        else:
+            tmp = torch.empty_like(y)
+            _lib.check(lib.tdvc_add3_scale(ptr(0), ptr(1), ptr(2), _p(tmp), y.numel(), 1.0, _st()), "mrf sum")
+            _lib.check(lib.tdvc_add3_scale(_p(tmp), ptr(3), None, _p(y), y.numel(), 1.0 / G, _st()), "mrf mean")
+        ctx.cfg = (G, D, B, Cx, T, Kmax, tuple(ks), tuple(ds), tuple(H), slope, has_cond, per, cdims)
+        ctx.has_bias = [t is not None for t in wb]
+        saved = list(X) + a1 + ([t for t in h0] if has_cond else []) + ([gb, cp, g1p] if has_cond else [])
+        saved += [w for pair in wconv for w in (pair[1],)] + [w for pair in wpos for w in (pair[1],)]
+        if has_cond:
+            saved += [_c(blk(i, j)[4]) for i in range(G) for j in range(D)] + [_c(blk(i, j)[6]) for i in range(G) for j in range(D)]
+        ctx.save_for_backward(*saved)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        G, D, B, Cx, T, Kmax, ks, ds, H, slope, has_cond, per, cdims = ctx.cfg
+        sv = list(ctx.saved_tensors)
+        X, sv = sv[:D], sv[D:]
+        a1, sv = sv[:D], sv[D:]
+        h0 = [None] * D
+        gb = cp = g1p = None
+        if has_cond:
+            h0, sv = sv[:D], sv[D:]
+            (gb, cp, g1p), sv = sv[:3], sv[3:]
+        wconvT, sv = sv[:D], sv[D:]
+        wposT, sv = sv[:D], sv[D:]
+        n = G * D
+        w0s = w2s = None
+        if has_cond:
+            w0s, w2s = sv[:n], sv[n:2 * n]
+        lib = _lib.load()
+        dev = dy.device
+        dy = _c(dy)
+        need = ctx.needs_input_grad
+        gb_blk = B * 2 * Cx * T
+        C2p = 2 * Cx
+        dgbp = torch.empty(B, T, n * C2p, device=dev, dtype=torch.bfloat16) if has_cond else None
+        # gradient of the branch mean: the same dL/dy / G for every branch (group stride 0)
+        d_out = torch.empty_like(dy)
+        _lib.check(lib.tdvc_add3_scale(_p(dy), None, None, _p(d_out), dy.numel(), 1.0 / G, _st()), "mrf mean bwd")
+        dyp = torch.empty(B, T, Cx, device=dev, dtype=torch.bfloat16)
+        _lib.check(lib.tdvc_pack_cl_bf16(_p(d_out), _p(dyp), B, Cx, T, Cx, 0, PAD_ZEROS, 1.0, None, 0, 0, -1, None, _st()), "pack dy")
+        grads = [None] * (per * n)
+        gi = lambda i, j: per * (i * D + j)
+        d_in = None
+        for j in reversed(range(D)):
+            top = j == D - 1
+            # posconv.1 weight / bias gradients of the G branches
+            dwp = [torch.empty(Cx, Cx, 1, device=dev, dtype=torch.float32) for _ in range(G)]
+            dbp = [torch.empty(Cx, device=dev, dtype=torch.float32) if ctx.has_bias[gi(i, j) + 3] else None for i in range(G)]
+            wgrad2(dyp=dyp, xp=a1[j], B=B, Cdp=dyp.shape[2], Tout=T, Cp=G * Cx, Tp=T, Cout=Cx, Cin=Cx, K=1, dilation=1, ngroups=G,
+                   per_group=True, x_ch_stride=Cx, dy_ch_stride=(0 if top else Cx), kg=[1] * G, t_off=[0] * G, dw=dwp, db=dbp)
+            # posconv^T (+ LeakyReLU mask + FiLM backward) -> packed dL/dh0 and packed dL/d(gamma|beta)
+            dh0p = torch.empty(B, T, G * Cx, device=dev, dtype=torch.bfloat16)
+            kw = dict(xp=dyp, wp=wposT[j], B=B, Tp=T, Tout=T, K=1, dilation=1, t_off=0, Cp_total=dyp.shape[2], groups=G,
+                      a_ch_off=0, a_ch_stride=(0 if top else Cx), Cinp_g=Cx, Cout_g=Cx, Coutp_g=Cx, bias_stride=0,
+                      out_act=ACT_NONE, out_slope=1.0, out_packed=1, yp=dh0p, tp_out=T, cp_out=G * Cx, out_halo=0, out_ch_off=0,
+                      out_ch_stride=Cx, maskp=a1[j], tm=T, cm=G * Cx, mask_halo=0, mask_ch_off=0, mask_ch_stride=Cx,
+                      mask_slope=slope, chain_mode=5)
+            if has_cond:
+                kw.update(gb=gb.data_ptr() + 4 * j * gb_blk, gb_grp_stride=D * gb_blk, auxp=h0[j], dgbp=dgbp, dgb_cp=n * C2p,
+                          dgb_ch_off=j * C2p, dgb_ch_stride=D * C2p)
+            _tc_conv(**kw)
+            # conv.1 weight / bias gradients of the G branches (k_i taps each, one launch)
+            dwc = [torch.empty(Cx, Cx, ks[i], device=dev, dtype=torch.float32) for i in range(G)]
+            dbc = [torch.empty(Cx, device=dev, dtype=torch.float32) if ctx.has_bias[gi(i, j) + 1] else None for i in range(G)]
+            wgrad2(dyp=dh0p, xp=X[j], B=B, Cdp=G * Cx, Tout=T, Cp=X[j].shape[2], Tp=T + 2 * H[j], Cout=Cx, Cin=Cx, K=Kmax,
+                   dilation=ds[j], ngroups=G, per_group=True, x_ch_stride=(0 if j == 0 else Cx), dy_ch_stride=Cx, kg=list(ks),
+                   t_off=[H[j] - ds[j] * (k - 1) // 2 for k in ks], dw=dwc, db=dbc)
+            for i in range(G):
+                grads[gi(i, j) + 0], grads[gi(i, j) + 1] = dwc[i], dbc[i]
+                grads[gi(i, j) + 2], grads[gi(i, j) + 3] = dwp[i], dbp[i]
+            # conv.1^T over the padded rows (+ LeakyReLU mask + residual gradient) -> dL/dx of this depth, fp32 + packed
+            Lp = T + 2 * H[j]
+            d_in = torch.empty(G, B, Cx, T, device=dev, dtype=torch.float32)
+            dyp_prev = torch.empty(B, T, G * Cx, device=dev, dtype=torch.bfloat16) if j > 0 else None
+            hb = torch.empty(G, B, Cx, max(1, 2 * H[j]), device=dev, dtype=torch.float32)
+            kw = dict(xp=dh0p, wp=wconvT[j], B=B, Tp=T, Tout=Lp, K=Kmax, dilation=ds[j], t_off=-(Kmax - 1) * ds[j], Cp_total=G * Cx,
+                      groups=G, a_ch_off=0, a_ch_stride=Cx, Cinp_g=Cx, Cout_g=Cx, Coutp_g=Cx, bias_stride=0, out_act=ACT_NONE,
+                      out_slope=1.0, out_packed=0, y=d_in, y_grp_stride=B * Cx * T, y_b_stride=Cx * T, residual=d_out,
+                      res_grp_stride=(0 if top else B * Cx * T), maskp=X[j], tm=Lp, cm=X[j].shape[2], mask_halo=0, mask_ch_off=0,
+                      mask_ch_stride=(0 if j == 0 else Cx), mask_slope=slope, chain_mode=6, kg=ks, halo_buf=hb, halo=H[j],
+                      t_valid=T)
+            if dyp_prev is not None:
+                kw.update(yp=dyp_prev, tp_out=T, cp_out=G * Cx, out_halo=0, out_ch_off=0, out_ch_stride=Cx)
+            _tc_conv(**kw)
+            if H[j] > 0:
+                _lib.check(lib.tdvc_chain_fold(_p(hb), _p(d_in), _p(dyp_prev), G, B, Cx, T, H[j], B * Cx * T, Cx * T, G * Cx, 0, Cx,
+                                               _st()), "chain_fold")
+            d_out, dyp = d_in, dyp_prev
+        dx = None
+        if need[0]:
+            dx = torch.empty(B, Cx, T, device=dev, dtype=torch.float32)
+            ptr = lambda i: C.c_void_p(d_in.data_ptr() + 4 * i * B * Cx * T)
+            if G <= 3:
+                _lib.check(lib.tdvc_add3_scale(ptr(0), ptr(1) if G > 1 else None, ptr(2) if G > 2 else None, _p(dx), dx.numel(),
+                                               1.0, _st()), "mrf dx")
+            else:
+                tmp = torch.empty_like(dx)
+                _lib.check(lib.tdvc_add3_scale(ptr(0), ptr(1), ptr(2), _p(tmp), dx.numel(), 1.0, _st()), "mrf dx")
+                _lib.check(lib.tdvc_add3_scale(_p(tmp), ptr(3), None, _p(dx), dx.numel(), 1.0, _st()), "mrf dx")
+        dc = None
+        if has_cond:
+            has_b0 = [ctx.has_bias[gi(i, j) + 5] for i in range(G) for j in range(D)]
+            has_b2 = [ctx.has_bias[gi(i, j) + 7] for i in range(G) for j in range(D)]
+            dc, cg = _cond_path_backward(cdims, cp, g1p, w0s, w2s, has_b0, has_b2, dgbp, need[1])
+            for b_ in range(n):
+                grads[per * b_ + 4: per * b_ + 8] = cg[4 * b_: 4 * b_ + 4]
+        return (dx, dc, None, None, None, None, *grads)
+
+
+def mrf_stage(x, c, blocks, kernel_sizes, dilations, slope=0.2, cond_slope=0.2):
+    """blocks[i][j] = (conv_w, conv_b, pos_w, pos_b[, cv0_w, cv0_b, cv2_w, cv2_b]): effective (weight-normed) weights of the
+    FiLM block of kernel size i / dilation j."""
+    flat = []
+    for row in blocks:
+        for blk in row:
+            flat += list(blk)
+    return _MRFStage.apply(x, c, float(slope), float(cond_slope), tuple(int(k) for k in kernel_sizes),
+                           tuple(int(d) for d in dilations), *flat)
 
 
 # ----------------------------------------------------------------------------- fused FiLM + posconv

@@ -1,0 +1,159 @@
+"""The bf16-resident MRF stage (tdvc.ops._MRFStage: chain epilogues of the tcgen05 conv kernels, grouped weight
+gradients, reflect fold) against an fp64 PyTorch restatement of model/generator.py:69-111,175-194.
+
+bf16 operands, fp32 accumulation, bf16 storage of the tensors between the convolutions: outputs are asserted at 1e-2
+(max-abs-normalised, as everywhere).  Gradients pass through 2 LeakyReLUs per block whose branch flips where a
+pre-activation is below the bf16 rounding error, which shows as isolated outliers: they are asserted in relative L2
+(3e-2) and, elementwise, at 1e-1 of the tensor's largest entry."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g, dtype=torch.float64) * scale
+
+
+def dev(t):
+    return None if t is None else t.detach().float().cuda().requires_grad_(t.requires_grad)
+
+
+def l2err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@pytest.fixture(autouse=True)
+def bf16_mode():
+    from tdvc import ops
+    ops.set_precision("bf16")
+    yield
+    ops.set_precision("fp32")
+
+
+def mrf_ref(x, c, blocks, ks, ds, slope):
+    outs = []
+    for i, k in enumerate(ks):
+        h = x
+        for j, d in enumerate(ds):
+            blk = blocks[i][j]
+            cw, cb, pw, pb = blk[:4]
+            pad = d * (k - 1) // 2
+            hin = F.leaky_relu(h, slope)
+            if pad > 0:
+                hin = F.pad(hin, (pad, pad), mode="reflect")
+            h0 = F.conv1d(hin, cw, cb, dilation=d)
+            if c is not None:
+                w0, b0, w2, b2 = blk[4:]
+                g = F.conv1d(F.leaky_relu(F.conv1d(c, w0, b0, padding=1), slope), w2, b2, padding=1)
+                gamma, beta = g.chunk(2, dim=1)
+                h0 = h0 * (1 + gamma) + beta
+            h = F.conv1d(F.leaky_relu(h0, slope), pw, pb) + h
+        outs.append(h)
+    return sum(outs) / len(outs)
+
+
+def make_blocks(C, Cc, ks, ds, seed):
+    blocks = []
+    s = seed
+    for k in ks:
+        row = []
+        for _ in ds:
+            t = [rnd(C, C, k, seed=s + 1, scale=(C * k) ** -0.5), rnd(C, seed=s + 2, scale=0.1),
+                 rnd(C, C, 1, seed=s + 3, scale=C ** -0.5), rnd(C, seed=s + 4, scale=0.1)]
+            if Cc:
+                t += [rnd(Cc, Cc, 3, seed=s + 5, scale=(3 * Cc) ** -0.5), rnd(Cc, seed=s + 6, scale=0.1),
+                      rnd(2 * C, Cc, 3, seed=s + 7, scale=0.5 * (3 * Cc) ** -0.5), rnd(2 * C, seed=s + 8, scale=0.1)]
+            row.append([w.requires_grad_(True) for w in t])
+            s += 10
+        blocks.append(row)
+    return blocks
+
+
+CASES = [
+    # B, C, T, Cc (0 = encoder stage without conditioning), kernel sizes, dilations
+    (2, 16, 300, 24, (3, 7, 11), (1, 3, 5)),       # decoder full-rate stage shape class (C = 16), small cond
+    (2, 32, 260, 0, (3, 7, 11), (1, 3, 5)),        # encoder stage, C = 32
+    (1, 64, 200, 136, (3, 7, 11), (1, 3, 5)),      # decoder stage with the real 136-channel conditioning
+    (2, 128, 130, 0, (3, 7, 11), (1, 3, 5)),       # weights too large to stay resident: streaming kernel
+    (3, 16, 28, 0, (3, 7, 11), (1, 3, 5)),         # T = 28 with a 25-sample reflect halo: left and right folds overlap
+    (1, 256, 28, 0, (3, 7, 11), (1, 3, 5)),        # encoder's deepest stage
+    (2, 32, 515, 24, (3, 5), (1, 2)),              # two branches / two depths, ragged T over several tiles
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[str(i) for i in range(len(CASES))])
+def test_mrf_stage_chain(case):
+    from tdvc import ops
+    B, C, T, Cc, ks, ds = case
+    slope = 0.2
+    x = rnd(B, C, T, seed=1).requires_grad_(True)
+    c = rnd(B, Cc, T, seed=2).requires_grad_(True) if Cc else None
+    blocks = make_blocks(C, Cc, ks, ds, seed=100)
+    ref = mrf_ref(x, c, blocks, ks, ds, slope)
+    proj = rnd(B, C, T, seed=3)
+    (ref * proj).sum().backward()
+    assert ops.mrf_stage_eligible(C, T, ks, ds, bool(Cc), Cc)
+    xd, cd = dev(x), dev(c)
+    bd = [[[dev(w) for w in blk] for blk in row] for row in blocks]
+    n0 = ops._lib.load().tdvc_launch_count()
+    y = ops.mrf_stage(xd, cd, bd, ks, ds, slope=slope, cond_slope=slope)
+    torch.cuda.synchronize()
+    n_fwd = ops._lib.load().tdvc_launch_count() - n0
+    assert relerr(y, ref) < 1e-2, relerr(y, ref)
+    (y * proj.float().cuda()).sum().backward()
+    torch.cuda.synchronize()
+    n_all = ops._lib.load().tdvc_launch_count() - n0
+    worst = {}
+    worst["dx"] = (l2err(xd.grad, x.grad), relerr(xd.grad, x.grad))
+    if Cc:
+        worst["dc"] = (l2err(cd.grad, c.grad), relerr(cd.grad, c.grad))
+    names = ["conv_w", "conv_b", "pos_w", "pos_b", "cv0_w", "cv0_b", "cv2_w", "cv2_b"]
+    for i, row in enumerate(blocks):
+        for j, blk in enumerate(row):
+            for n, w, wd in zip(names, blk, bd[i][j]):
+                assert wd.grad is not None, (i, j, n)
+                worst[f"{i}.{j}.{n}"] = (l2err(wd.grad, w.grad), relerr(wd.grad, w.grad))
+    bad = {k: v for k, v in worst.items() if v[0] > 3e-2 or v[1] > 1e-1}
+    assert not bad, (bad, n_fwd, n_all)
+
+
+def test_mrf_stage_chain_matches_block_path_in_generator():
+    """The Generator with the whole-stage path switched on and off: same waveform and gradient norms within bf16 noise."""
+    import numpy as np
+    from oracle.cases import CASES as MC, rand_like
+    from oracle.params import make_batch, make_state_dict
+    from tdvc import ops
+    from test_host_cpu import build_G
+    cfg = MC["g_full"]
+    outs = []
+    for chain in (True, False):
+        ops._MRF_CHAIN = chain
+        try:
+            G = build_G(cfg)
+            shapes = {k: tuple(v.shape) for k, v in G.state_dict().items()}
+            G.load_state_dict(make_state_dict(shapes, seed=cfg["seed"], dtype=torch.float32), strict=True)
+            G.cuda()
+            b = make_batch(cfg["B"], cfg["T"], cfg["nspk"], seed=cfg["seed"] + 1, frames_div=320)
+            c_tgt = F.one_hot(b["label_tgt"], cfg["nspk"]).float().cuda()
+            n0 = ops._lib.load().tdvc_launch_count()
+            y, subs = G(b["signal_real"].float().cuda(), c_tgt, c_var=b["c_f0_conv"].float().cuda(), out_subsample=True)
+            loss = (y * rand_like(y, 11).float().cuda()).sum() + sum((s * rand_like(s, 12 + i).float().cuda()).sum()
+                                                                   for i, s in enumerate(subs))
+            loss.backward()
+            torch.cuda.synchronize()
+            n = ops._lib.load().tdvc_launch_count() - n0
+            outs.append((y.detach(), {k: p.grad.detach().clone() for k, p in G.named_parameters() if p.grad is not None}, n))
+        finally:
+            ops._MRF_CHAIN = True
+    (y_c, g_c, n_c), (y_b, g_b, n_b) = outs
+    assert n_c < 0.5 * n_b, (n_c, n_b)                     # the point of the exercise: far fewer launches
+    assert relerr(y_c, y_b) < 2e-2
+    assert set(g_c) == set(g_b)
+    errs = np.sort(np.array([abs(float(g_c[k].norm()) - float(g_b[k].norm())) / max(float(g_b[k].norm()), 1e-30) for k in g_b]))
+    assert errs[int(0.9 * len(errs))] < 3e-2 and errs[-1] < 2e-1, (errs[int(0.9 * len(errs))], errs[-1])

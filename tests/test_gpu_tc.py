@@ -355,9 +355,20 @@ FRAME_CASES = [
 ]
 
 
-@pytest.mark.parametrize("case", FRAME_CASES, ids=[str(i) for i in range(len(FRAME_CASES))])
+# kernels that are not a whole number of strides (zero taps appended): the latent classifier's k21 s2 layers
+# (model/latent_classifier.py:17-21) and a dense k41 s4 layer (the tiny discriminator's first strided layer has one group)
+FRAME_CASES_PADDED_K = [
+    (3, 16, 28, 32, 21, 2, 10),
+    (2, 128, 28, 256, 21, 2, 10),
+    (2, 512, 7, 1024, 21, 2, 10),
+    (2, 4, 2048, 16, 41, 4, 20),
+]
+
+
+@pytest.mark.parametrize("case", FRAME_CASES + FRAME_CASES_PADDED_K,
+                         ids=[str(i) for i in range(len(FRAME_CASES) + len(FRAME_CASES_PADDED_K))])
 def test_strided_conv_as_frames(case):
-    """Conv1d(k = m*stride) in bf16 mode = frame view + stride-1 tcgen05 conv; against fp64 PyTorch, 1e-2."""
+    """Conv1d(k, stride) in bf16 mode = frame view + stride-1 tcgen05 conv; against fp64 PyTorch, 1e-2."""
     from tdvc import ops
     B, Cin, T, Cout, K, s, p = case
     x = rnd(B, Cin, T, seed=1).requires_grad_(True)
