@@ -352,6 +352,7 @@ def kernel_families(replay, fam_gflop):
     busy, cnt = collections.Counter(), collections.Counter()
     frontier = evs[0].time_range.start
     idle = 0.0
+    inst = []
     for e in evs:
         name = re.sub(r"\(.*", "", e.name)
         name = re.sub(r"^void ", "", name)[:60]
@@ -359,6 +360,7 @@ def kernel_families(replay, fam_gflop):
         if st > frontier:
             idle += (st - frontier) / 1e3
         busy[name] += max(0.0, en - max(st, frontier)) / 1e3
+        inst.append((max(0.0, en - max(st, frontier)), name, len(inst)))
         frontier = max(frontier, en)
         cnt[name] += 1
     t0 = evs[0].time_range.start
@@ -379,8 +381,9 @@ def kernel_families(replay, fam_gflop):
         if fam_gflop is not None:
             d["gflop_per_step"] = round(fam_gflop[fam], 2)
             d["tflops"] = round(fam_gflop[fam] / d["ms"], 2) if d["ms"] > 0 else None
+    slowest = [{"kernel": n, "us": round(d, 1), "position": i} for d, n, i in sorted(inst, reverse=True)[:30]]
     return {"span_ms": round((t1 - t0) / 1e3, 3), "busy_ms": round(total, 3), "idle_ms": round(idle, 3),
-            "activities": len(evs), "top": top,
+            "activities": len(evs), "top": top, "slowest_launches": slowest,
             "conv_families": [conv[k] for k in sorted(conv, key=lambda k: -conv[k]["ms"])]}
 
 

@@ -1363,30 +1363,37 @@ static double tc_taps(const tdvc_tc_conv* c) {
   return n;
 }
 
-// chain_mode 6 follow-up: fold the reflect-halo contributions onto the samples they mirror (one thread per (group, batch,
-// channel) row: the 2*halo updates of a row may hit the same sample when the signal is short)
+// chain_mode 6 follow-up: fold the reflect-halo contributions onto the samples they mirror.  One thread per TARGET sample
+// (so no two threads touch the same element, also when the signal is so short that the left and the right fold overlap):
+// slot s < halo is sample tt = s + 1 (mirrored by padded row halo - tt and, when the signal is short, also by a right-halo
+// row), slot s >= halo is sample tt = T - 1 - halo + (s - halo) unless a left slot already owns it.
 __global__ void chain_fold_k(const float* __restrict__ hb, float* __restrict__ y, __nv_bfloat16* __restrict__ yp, int groups,
                              int B, int C, int T, int halo, long long y_grp_stride, long long y_b_stride, int cp_out,
                              int out_ch_off, int out_ch_stride) {
   tdvc::pdl_prologue();
-  const long long n = (long long)groups * B * C;
+  const long long n = (long long)groups * B * C * 2 * halo;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    const long long r = i / C;
+    const int s = (int)(i % (2 * halo));
+    const long long r0 = i / (2 * halo);
+    const int c = (int)(r0 % C);
+    const long long r = r0 / C;
     const int b = (int)(r % B), g = (int)(r / B);
-    const float* h = hb + i * (2 * halo);
+    int tt;
+    if (s < halo) {
+      tt = s + 1;
+    } else {
+      tt = T - 1 - halo + (s - halo);
+      if (tt <= halo) continue;                      // owned by a left slot
+    }
+    const float* h = hb + r0 * (2 * halo);
+    float add = 0.f;
+    if (tt >= 1 && tt <= halo) add += h[halo - tt];                            // padded row halo - tt mirrors sample tt
+    const int ir = T - 2 - tt;                                                // padded row halo + T + ir mirrors T - 2 - ir
+    if (ir >= 0 && ir < halo) add += h[halo + ir];
     float* row = y + (long long)g * y_grp_stride + (long long)b * y_b_stride + (long long)c * T;
-    for (int hr = 0; hr < 2 * halo; ++hr) {
-      const int tt = hr < halo ? halo - hr : T - 2 - (hr - halo);
-      row[tt] += h[hr];
-    }
-    if (yp) {
-      __nv_bfloat16* col = yp + (long long)b * T * cp_out + out_ch_off + g * out_ch_stride + c;
-      for (int hr = 0; hr < 2 * halo; ++hr) {
-        const int tt = hr < halo ? halo - hr : T - 2 - (hr - halo);
-        col[(long long)tt * cp_out] = __float2bfloat16(row[tt]);
-      }
-    }
+    const float v = row[tt] + add;
+    row[tt] = v;
+    if (yp) yp[((long long)b * T + tt) * cp_out + out_ch_off + g * out_ch_stride + c] = __float2bfloat16(v);
   }
 }
 
@@ -1395,9 +1402,9 @@ extern "C" int tdvc_chain_fold(const float* halo_buf, float* y, void* yp, int gr
                                void* stream) {
   TDVC_CHECK_ARG(halo_buf && y && groups > 0 && B >= 0 && C > 0 && T > 0 && halo >= 0 && halo < T);
   if (B == 0 || halo == 0) return TDVC_OK;
-  const long long n = (long long)groups * B * C;
-  const int blocks = (int)std::min<long long>((n + 127) / 128, 4LL * tdvc::num_sms());
-  tdvc::launch_k(chain_fold_k, blocks, 128, 0, (cudaStream_t)stream, halo_buf, y, (__nv_bfloat16*)yp, groups, B, C, T, halo,
+  const long long n = (long long)groups * B * C * 2 * halo;
+  const int blocks = (int)std::min<long long>((n + 255) / 256, 8LL * tdvc::num_sms());
+  tdvc::launch_k(chain_fold_k, blocks, 256, 0, (cudaStream_t)stream, halo_buf, y, (__nv_bfloat16*)yp, groups, B, C, T, halo,
                  (long long)y_grp_stride, (long long)y_b_stride, cp_out, out_ch_off, out_ch_stride);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;

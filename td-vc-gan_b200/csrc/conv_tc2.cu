@@ -14,7 +14,13 @@
 //       128-byte rows needs no descriptor fix-up) -- the first kernel loaded one shifted copy per tap: 11 x the bytes for
 //       k = 11, and a single-stage pipeline because 11 copies filled the shared memory;
 //     * only the 64-channel boxes that hold real channels are loaded (Cin <= 64: one box instead of two);
-//     * groups share a launch, so a 16-channel layer no longer costs one launch + one finalize per conv.
+//     * groups share a launch, so a 16-channel layer no longer costs one launch + one finalize per conv;
+//     * TAPS ON M (Cin = 16 / 32 / 64): a tcgen05.mma costs about the same whatever part of its 128 M lanes holds real
+//       channels (measured: ~128 cycles per instruction at N = 16), so a 16-channel layer used 1/8 of every instruction.
+//       The x tile is loaded as Cin-channel rows (SWIZZLE_32B / 64B / 128B box) and the A descriptor's leading-dimension
+//       offset -- the distance between consecutive Cin-channel atoms along M -- is set to dil rows: atom a of the operand is
+//       the tile moved down by a*dil rows, i.e. tap a.  One instruction then computes 128 / Cin taps: 8 instead of 44
+//       MMAs per time unit for a 16-channel k = 11 conv.
 //   Split-K over (batch, 64-step chunk) with lane-coalesced fp32 reductions into an always-zero workspace, as before;
 //   wgrad2_finalize_k moves the sums into the weight-gradient tensors (plain [Cout][Cin][K] per group, or the
 //   discriminator's [Cout][Cin/groups][41] through the frame mapping) and re-zeroes what it read.
@@ -39,7 +45,20 @@ struct Wg2P {
   float* ws;
   int bias;
   int k_inner;
+  int nacc_max;        // accumulator slots per CTA (the bias accumulator follows them)
+  int tm, sw;          // taps per MMA (1 = channels only on M) and swizzle / row bytes of the x tile (128 unless tm > 1)
 };
+
+// MN-major descriptor with explicit leading-dimension / stride byte offsets and layout code (2 = SWIZZLE_128B, 4 = 64B, 6 = 32B)
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
 
 __global__ void __launch_bounds__(W2_THREADS) conv_tc_wgrad2_k(const __grid_constant__ CUtensorMap map_x,
                                                                const __grid_constant__ CUtensorMap map_dy, Wg2P p) {
@@ -47,7 +66,7 @@ __global__ void __launch_bounds__(W2_THREADS) conv_tc_wgrad2_k(const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   // stage = [x: two 64-channel boxes (haloed: rows_x rows each; per tap: KT pairs of 64 rows)] [dy: nb_dy boxes of 64 rows]
-  const int x_box = (p.haloed ? p.rows_x : W2_TK) * 128;
+  const int x_box = (p.haloed ? p.rows_x : W2_TK) * p.sw;
   const int x_bytes = (p.haloed ? 1 : p.KT) * 2 * x_box;
   const int dy_bytes = p.nb_dy * W2_BOX;
   const int stage_bytes = x_bytes + dy_bytes;
@@ -68,13 +87,14 @@ __global__ void __launch_bounds__(W2_THREADS) conv_tc_wgrad2_k(const __grid_cons
   const int kgrp = p.per_group ? p.kg[gi] : p.K;
   const int t_off = p.toff[gi];
   const int ntaps = min(p.KT, kgrp - tap0);
+  const int nacc = (ntaps + p.tm - 1) / p.tm;            // accumulators in use: one per tap, or per block of tm taps
   const int split = blockIdx.x;
   const int my_units = ntaps > 0 ? (p.units - split + p.splits - 1) / p.splits : 0;
   const bool do_bias = p.bias && mt == 0 && tg == 0;
   const int xc = p.x_ch_off + g * p.x_ch_stride + ci0;
   const int dc = p.dy_ch_off + g * p.dy_ch_stride + n0;
   // real 64-channel boxes of this CTA's 128-lane ci tile
-  const int nbx = min(p.nb_x, (p.Cin - ci0 + 63) / 64);
+  const int nbx = p.tm > 1 ? 1 : min(p.nb_x, (p.Cin - ci0 + 63) / 64);
   if (do_bias) {
     uint32_t* o32 = reinterpret_cast<uint32_t*>(ones);
     for (int i = threadIdx.x; i < 2 * W2_BOX / 4; i += W2_THREADS) o32[i] = 0x3F803F80u;      // bf16 1.0 pairs
@@ -132,27 +152,17 @@ __global__ void __launch_bounds__(W2_THREADS) conv_tc_wgrad2_k(const __grid_cons
         if (elect_one()) {
           const uint32_t s_addr = smem_u32(smem + (size_t)s * stage_bytes);
           const uint32_t b_addr = s_addr + x_bytes;
-          // k outermost: consecutive MMAs go to DIFFERENT accumulators (one per tap), so an instruction never waits for
-          // the one just issued -- MMAs that accumulate into the same TMEM tile are ~100 cycles apart at best
-          // (TDVC_WGRAD2_KINNER=1 restores the tap-outer order for A/B measurements)
-          if (!p.k_inner) {
-            for (int k = 0; k < W2_TK / 16; ++k) {      // 16 time rows = 2048 B per MMA
+          // one accumulator per tap block (tm taps; tm = 1: per tap).  haloed: block tb = the tile moved down by tb*tm*dil
+          // rows and, inside the instruction, M atom a = the tile moved down by a further a*dil rows (LBO = dil rows).
+          const uint32_t row_b = (uint32_t)p.sw;                           // bytes per x row
+          const uint32_t layout = p.sw == 128 ? 2u : (p.sw == 64 ? 4u : 6u);
+          const uint32_t lbo = p.tm > 1 ? (uint32_t)p.dil * row_b : (uint32_t)x_box;
+          for (int tb = 0; tb < nacc; ++tb) {
+            const uint32_t a_addr = p.haloed ? s_addr + (uint32_t)(tb * p.tm * p.dil) * row_b : s_addr + (uint32_t)(tb * 2 * x_box);
+            for (int k = 0; k < W2_TK / 16; ++k) {      // 16 time rows per MMA
+              const uint64_t da = make_mnmajor_desc(a_addr + (uint32_t)k * 16u * row_b, lbo, 8u * row_b, layout);
               const uint64_t db = make_sw128_mnmajor_desc(b_addr + k * 2048, W2_BOX);
-              for (int tp = 0; tp < ntaps; ++tp) {
-                // haloed: tap tp = the tile moved down by tp*dil rows; per tap: its own pair of boxes
-                const uint32_t a_addr = p.haloed ? s_addr + (uint32_t)(tp * p.dil) * 128u : s_addr + (uint32_t)(tp * 2 * x_box);
-                const uint64_t da = make_sw128_mnmajor_desc(a_addr + k * 2048, (uint32_t)x_box);
-                umma_bf16(tmem_base + (uint32_t)(tp * p.NT), da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
-              }
-            }
-          } else {
-            for (int tp = 0; tp < ntaps; ++tp) {
-              const uint32_t a_addr = p.haloed ? s_addr + (uint32_t)(tp * p.dil) * 128u : s_addr + (uint32_t)(tp * 2 * x_box);
-              for (int k = 0; k < W2_TK / 16; ++k) {
-                const uint64_t da = make_sw128_mnmajor_desc(a_addr + k * 2048, (uint32_t)x_box);
-                const uint64_t db = make_sw128_mnmajor_desc(b_addr + k * 2048, W2_BOX);
-                umma_bf16(tmem_base + (uint32_t)(tp * p.NT), da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
-              }
+              umma_bf16(tmem_base + (uint32_t)(tb * p.NT), da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
             }
           }
           if (do_bias) {
@@ -160,7 +170,7 @@ __global__ void __launch_bounds__(W2_THREADS) conv_tc_wgrad2_k(const __grid_cons
             for (int k = 0; k < W2_TK / 16; ++k) {
               const uint64_t da = make_sw128_mnmajor_desc(o_addr + k * 2048, W2_BOX);
               const uint64_t db = make_sw128_mnmajor_desc(b_addr + k * 2048, W2_BOX);
-              umma_bf16(tmem_base + (uint32_t)(p.KT * p.NT), da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+              umma_bf16(tmem_base + (uint32_t)(p.nacc_max * p.NT), da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
             }
           }
           umma_commit(&empty_bar[s]);
@@ -172,12 +182,30 @@ __global__ void __launch_bounds__(W2_THREADS) conv_tc_wgrad2_k(const __grid_cons
       const int q = warp & 3;
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
-      const int ci = ci0 + q * 32 + lane;
-      const bool row_ok = ci < p.Cin;
       const int nvalid = min(p.NT, p.Cout - n0);
       float* wsg = p.ws + (long long)g * p.ws_grp_stride;
-      // lanes of warps whose 32 ci are all padding have nothing to add
-      if (ci0 + q * 32 < p.Cin) {
+      if (p.tm > 1) {
+        // lane = (tap within the block, input channel)
+        const int L = q * 32 + lane;
+        const int a = L / p.Cin, ci = L - a * p.Cin;
+        for (int tb = 0; tb < nacc; ++tb) {
+          const int tap = tap0 + tb * p.tm + a;
+          const bool row_ok = tap < tap0 + ntaps;
+          float* wrow = wsg + ((long long)tap * p.Np + n0) * p.Mp + ci;
+          for (int c0 = 0; c0 < nvalid; c0 += 16) {
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tb * p.NT + c0), v);
+            if (row_ok) {
+              const int nj = min(16, nvalid - c0);
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < nj) atomicAdd(wrow + (long long)(c0 + j) * p.Mp, v[j]);
+            }
+          }
+        }
+      } else if (ci0 + q * 32 < p.Cin) {         // lanes of warps whose 32 ci are all padding have nothing to add
+        const int ci = ci0 + q * 32 + lane;
+        const bool row_ok = ci < p.Cin;
         for (int tp = 0; tp < ntaps; ++tp) {
           float* wrow = wsg + ((long long)(tap0 + tp) * p.Np + n0) * p.Mp + ci;
           for (int c0 = 0; c0 < nvalid; c0 += 16) {
@@ -197,7 +225,7 @@ __global__ void __launch_bounds__(W2_THREADS) conv_tc_wgrad2_k(const __grid_cons
         float* brow = wsg + (long long)p.K * p.Np * p.Mp + n0;
         for (int c0 = 0; c0 < nvalid; c0 += 16) {
           float v[16];
-          tmem_ld16(tmem_base + (uint32_t)(p.KT * p.NT + c0), v);
+          tmem_ld16(tmem_base + (uint32_t)(p.nacc_max * p.NT + c0), v);
           float mine = 0.f;
 #pragma unroll
           for (int j = 0; j < 16; ++j) mine = (lane == j) ? v[j] : mine;
@@ -391,20 +419,33 @@ extern "C" int tdvc_conv1d_tc_wgrad2(const tdvc_tc_wgrad2* c, void* stream) {
     if (h < 0) { const char* e = getenv("TDVC_WGRAD2_HALOED"); h = e ? atoi(e) : 1; }
     p.haloed = c->haloed >= 0 ? c->haloed : h;
     static int ki = -1;
-    if (ki < 0) { const char* e = getenv("TDVC_WGRAD2_KINNER"); ki = e ? atoi(e) : 0; }
+    if (ki < 0) { const char* e = getenv("TDVC_WGRAD2_KINNER"); ki = e ? atoi(e) : 1; }
     p.k_inner = ki;
   }
   const int xt = p.bias;
   p.nb_x = std::min(2, cdiv(c->Cin, 64));
+  // taps on M: Cin = 16 / 32 / 64 channel rows (SWIZZLE_32B / 64B / 128B), 128 / Cin taps per instruction
+  {
+    static int tm_on = -1;     // TDVC_WGRAD2_TAPSM=0: channels only on M (development / A-B switch)
+    if (tm_on < 0) { const char* e = getenv("TDVC_WGRAD2_TAPSM"); tm_on = e ? atoi(e) : 1; }
+    const bool ok = tm_on && p.haloed && c->K > 1 && (c->Cin == 16 || c->Cin == 32 || c->Cin == 64) &&
+                    (c->tapsm < 0 || c->tapsm == 1);
+    p.tm = (ok && c->tapsm != 0) ? 128 / c->Cin : 1;
+    p.sw = p.tm > 1 ? 2 * c->Cin : 128;
+  }
   // co tile / taps per CTA: as many taps as possible share the 512 TMEM columns (the x tile is then loaded once for all of them)
   int best_nt = 16, best_kt = 1, best_cost = 1 << 30;
   const long long budget = 200 * 1024;
+  auto rows_for = [&](int kt) {     // haloed x rows of one time unit for kt taps (whole tap blocks when tm > 1)
+    const int taps = cdiv(kt, p.tm) * p.tm;
+    return ((W2_TK + (taps - 1) * c->dilation + 7) / 8) * 8;
+  };
   for (int cand = std::min(p.Np, 256); cand >= 16; cand -= 16) {
-    int kt = std::min(c->K, 512 / cand - xt);
+    int kt = c->K;
     while (kt >= 1) {
-      const int rows_x = ((W2_TK + (kt - 1) * c->dilation + 7) / 8) * 8;
-      const long long xb = p.haloed ? 2LL * rows_x * 128 : (long long)kt * 2 * W2_BOX;
-      if (rows_x <= 256 && 2 * (xb + (long long)cdiv(cand, 64) * W2_BOX) <= budget) break;
+      const int rows_x = rows_for(kt);
+      const long long xb = p.haloed ? 2LL * rows_x * p.sw : (long long)kt * 2 * W2_BOX;
+      if ((cdiv(kt, p.tm) + xt) * cand <= 512 && rows_x <= 256 && 2 * (xb + (long long)cdiv(cand, 64) * W2_BOX) <= budget) break;
       --kt;
     }
     if (kt < 1) continue;
@@ -413,15 +454,17 @@ extern "C" int tdvc_conv1d_tc_wgrad2(const tdvc_tc_wgrad2* c, void* stream) {
   }
   TDVC_CHECK_ARG(best_cost < (1 << 30));
   p.NT = best_nt; p.KT = best_kt;
+  if (p.tm > 1 && p.KT < c->K) p.KT = std::max(p.tm, p.KT / p.tm * p.tm);      // tap groups start at whole blocks
   p.ntap_groups = cdiv(c->K, p.KT);
   p.n_ntiles = cdiv(p.Np, p.NT);
   p.nb_dy = cdiv(p.NT, 64);
-  p.rows_x = ((W2_TK + (p.KT - 1) * c->dilation + 7) / 8) * 8;
+  p.rows_x = rows_for(p.KT);
+  p.nacc_max = cdiv(p.KT, p.tm);
   int cols = 32;
-  while (cols < (p.KT + xt) * p.NT) cols <<= 1;
+  while (cols < (p.nacc_max + xt) * p.NT) cols <<= 1;
   TDVC_CHECK_ARG(cols <= 512);
   p.tmem_cols = cols;
-  const long long x_bytes = p.haloed ? 2LL * p.rows_x * 128 : (long long)p.KT * 2 * W2_BOX;
+  const long long x_bytes = p.haloed ? 2LL * p.rows_x * p.sw : (long long)p.KT * 2 * W2_BOX;
   const long long stage_bytes = x_bytes + (long long)p.nb_dy * W2_BOX;
   p.nchunk_t = cdiv(c->Tout, W2_TK);
   p.units = c->B * p.nchunk_t;
@@ -442,7 +485,9 @@ extern "C" int tdvc_conv1d_tc_wgrad2(const tdvc_tc_wgrad2* c, void* stream) {
     const size_t smem = (size_t)stages * stage_bytes + (p.bias ? 2 * W2_BOX : 0) + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
     TDVC_CUDA(cudaFuncSetAttribute(conv_tc_wgrad2_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUtensorMap map_x, map_dy;
-    int rc = make_map_3d(&map_x, c->xp, (uint64_t)c->Cp, (uint64_t)c->Tp, (uint64_t)c->B, 64, (uint32_t)(p.haloed ? p.rows_x : W2_TK));
+    const CUtensorMapSwizzle xsw = p.sw == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.sw == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    int rc = make_map_3d(&map_x, c->xp, (uint64_t)c->Cp, (uint64_t)c->Tp, (uint64_t)c->B, (uint32_t)(p.sw / 2),
+                         (uint32_t)(p.haloed ? p.rows_x : W2_TK), xsw);
     if (rc) return rc;
     rc = make_map_3d(&map_dy, c->dyp, (uint64_t)c->Cdp, (uint64_t)c->Tout, (uint64_t)c->B, 64, W2_TK);
     if (rc) return rc;

@@ -87,17 +87,23 @@ def test_grouped_strided_conv_tc(case):
 
 
 WG2 = [
-    # B, T, Cin, Cout, [K per group], dil, haloed
-    (2, 300, 16, 16, [11], 5, 1),
-    (2, 300, 16, 16, [11], 5, 0),
-    (2, 520, 16, 16, [3, 7, 11], 3, 1),       # the three branches of an MRF depth, one launch
-    (2, 520, 32, 32, [3, 7, 11], 1, 1),
-    (3, 200, 64, 64, [3, 7, 11], 5, 1),       # 11 taps x 64 columns do not fit TMEM: two tap groups
-    (3, 200, 64, 64, [3, 7, 11], 5, 0),
-    (1, 130, 128, 128, [3, 7, 11], 3, 1),
-    (2, 28, 256, 256, [7], 1, 1),             # two ci tiles, T < one time unit
-    (2, 333, 136, 32, [3], 1, 1),             # Cin not a multiple of 64 (cond_var.2 shape)
-    (2, 333, 24, 16, [1], 1, 1),              # k = 1
+    # B, T, Cin, Cout, [K per group], dil, haloed, taps on M (-1 = default: on for Cin 16 / 32 / 64)
+    (2, 300, 16, 16, [11], 5, 1, -1),         # 8 taps per MMA (SWIZZLE_32B rows), 2 tap blocks
+    (2, 300, 16, 16, [11], 5, 1, 0),          # same conv, channels only on M
+    (2, 300, 16, 16, [11], 5, 0, -1),         # one copy of the x tile per tap
+    (2, 520, 16, 16, [3, 7, 11], 3, 1, -1),   # the three branches of an MRF depth, one launch
+    (2, 520, 16, 16, [3, 7, 11], 1, 1, -1),   # dilation 1: M atoms one row apart
+    (2, 520, 32, 32, [3, 7, 11], 1, 1, -1),   # 4 taps per MMA (SWIZZLE_64B rows)
+    (2, 520, 32, 32, [3, 7, 11], 5, 1, 0),
+    (3, 200, 64, 64, [3, 7, 11], 5, 1, -1),   # 2 taps per MMA (SWIZZLE_128B rows)
+    (3, 200, 64, 64, [3, 7, 11], 5, 1, 0),    # 11 taps x 64 columns do not fit TMEM: two tap groups
+    (3, 200, 64, 64, [3, 7, 11], 5, 0, -1),
+    (2, 2100, 16, 16, [11], 1, 1, -1),        # many time units per CTA (pipeline wrap-around)
+    (1, 130, 128, 128, [3, 7, 11], 3, 1, -1),
+    (2, 28, 256, 256, [7], 1, 1, -1),         # two ci tiles, T < one time unit
+    (2, 333, 136, 32, [3], 1, 1, -1),         # Cin not a multiple of 64 (cond_var.2 shape)
+    (2, 333, 24, 16, [1], 1, 1, -1),          # k = 1
+    (2, 333, 64, 16, [11], 1, 1, -1),         # the frame view of discriminator.4.0: 64 frame channels -> 16 outputs
 ]
 
 
@@ -106,7 +112,7 @@ def test_wgrad2_groups(case):
     """conv_tc_wgrad2_k on branch-concatenated operands: x[B, T + 2H, G*Cin] (reflect-free, zero halo H = max pad) and
     dy[B, T, G*Cout]; group g is a 'same' conv with kg[g] taps at dilation dil."""
     from tdvc import ops
-    B, T, Cin, Cout, ks, dil, haloed = case
+    B, T, Cin, Cout, ks, dil, haloed, tapsm = case
     G = len(ks)
     H = max(dil * (k - 1) // 2 for k in ks)
     x = rnd(B, G * Cin, T, seed=1)
@@ -119,7 +125,7 @@ def test_wgrad2_groups(case):
     dbs = [torch.full((Cout,), float("nan"), device="cuda") for _ in ks]
     ops.wgrad2(dyp=dyp, xp=xp, B=B, Cdp=G * Cout, Tout=T, Cp=G * Cin, Tp=T + 2 * H, Cout=Cout, Cin=Cin, K=max(ks), dilation=dil,
                ngroups=G, per_group=True, x_ch_stride=Cin, dy_ch_stride=Cout, kg=ks, t_off=[H - dil * (k - 1) // 2 for k in ks],
-               dw=dws, db=dbs, haloed=haloed)
+               dw=dws, db=dbs, haloed=haloed, tapsm=tapsm)
     torch.cuda.synchronize()
     xb = xp.double().cpu().transpose(1, 2)          # bf16-rounded operands, padded
     dyb = dyp.double().cpu().transpose(1, 2)
