@@ -100,6 +100,8 @@ WG2 = [
     (3, 200, 64, 64, [3, 7, 11], 5, 0, -1),
     (2, 2100, 16, 16, [11], 1, 1, -1),        # many time units per CTA (pipeline wrap-around)
     (1, 130, 128, 128, [3, 7, 11], 3, 1, -1),
+    (2, 130, 128, 128, [3, 7, 11], 5, 1, -1),  # four tap groups of 3 taps, dilation 5
+    (1, 28, 256, 256, [3, 7, 11], 5, 1, -1),   # encoder's deepest stage: one time unit, two ci tiles, four tap groups
     (2, 28, 256, 256, [7], 1, 1, -1),         # two ci tiles, T < one time unit
     (2, 333, 136, 32, [3], 1, 1, -1),         # Cin not a multiple of 64 (cond_var.2 shape)
     (2, 333, 24, 16, [1], 1, 1, -1),          # k = 1
