@@ -160,6 +160,12 @@ int tdvc_abs_diff_sum(const float* a, const float* b, float scale, float* out_su
 /* da = gscale[0] * scale * sign(a-b) */
 int tdvc_abs_diff_bwd(const float* a, const float* b, float scale, const float* gscale, float* da,
                       int64_t n, void* stream);
+/* the same for up to TDVC_L1_MAX_JOBS tensor pairs in one launch each (all 30 feature maps of util/losses.py:55-68):
+ * out_sum += sum_j scale_j * sum |a_j - b_j|;  da_j = scale_j * gscale[0] * sign(a_j - b_j).  Pointers 16-byte aligned. */
+#define TDVC_L1_MAX_JOBS 32
+typedef struct tdvc_l1_job { const float* a; const float* b; float* da; int64_t n; float scale; } tdvc_l1_job;
+int tdvc_abs_diff_sum_multi(const tdvc_l1_job* jobs, int n_jobs, float* out_sum, void* stream);
+int tdvc_abs_diff_bwd_multi(const tdvc_l1_job* jobs, int n_jobs, const float* gscale, void* stream);
 
 /* ---- contrastive (InfoNCE) loss over content-embedding frames, util/losses.py:70-116: gather of in-utterance
  *      negatives + cosine similarities + cross-entropy in one kernel.  One direction per call: anchors A, positives
@@ -309,6 +315,34 @@ int tdvc_conv1d_tc_wgrad2(const tdvc_tc_wgrad2* c, void* stream);
  * data gradient: dx[b, c, u] = dxf[b, c*s + p, q] with s*q + p = u + pad, dxf fp32 [B, C*s, Tq]. */
 int tdvc_frame_pack_bf16(const float* x, void* xf, int B, int C, int T, int s, int pad, int Tq, void* stream);
 int tdvc_frame_unpack(const float* dxf, float* dx, int B, int C, int T, int s, int pad, int Tq, void* stream);
+
+/* Operand packs in one launch each.  tdvc_chain_pack: the grouped bf16 operands of one MRF depth from the G <= 4 branches'
+ * fp32 weights w[g][C][C][k[g]] (model/generator.py:175-194): wp[Kmax][G*C][C] (forward, taps centred inside Kmax),
+ * wtp[Kmax][G*C][C] (data gradient: transposed, taps reversed) and bias_out[G*C] (bias[g] may be NULL).
+ * tdvc_frame_weights_pack: the bundled frame-view operands of a grouped strided conv w[Cout][cin_g][K], stride s, m =
+ * ceil(K/s) frame taps, bundles of `sub` conv groups (cin_b = sub*cin_g*s frame channels in, cout_b outputs):
+ * wp[m][Cout][cin_b] and wtp[m][(Cout/cout_b)*cin_b][cout_b] (model/discriminator.py:26-30). */
+int tdvc_chain_pack(const float* const* w, const float* const* bias, const int* k, int G, int C, int Kmax, void* wp,
+                    void* wtp, float* bias_out, void* stream);
+int tdvc_frame_weights_pack(const float* w, void* wp, void* wtp, int Cout, int cin_g, int K, int s, int m, int sub,
+                            int cin_b, int cout_b, void* stream);
+
+/* ---- log-mel spectrogram loss without cuFFT (util/losses.py:28-53; mel.cu).  The STFT of the 18 frames is a GEMM
+ *      against a (window x cos | -sin) basis run on the convolution kernels above; these are the pieces around it.
+ * frames: F[k][b*NF + n] = win[k] * x[b][reflect(n*hop + k - pad)] (fp32, [n_fft][B*NF]) and its adjoint dx[B][T];
+ *         split != 0: three row blocks [hi | lo | hi], hi = bf16(F), lo = bf16(F - hi), for a bf16 GEMM against the basis
+ *         blocks [B_hi | B_hi | B_lo] with fp32-class accuracy (the adjoint sums the gradients of blocks 0 and 2);
+ * power:  P[f][col] = S[f][col]^2 + S[im_off + f][col]^2 over the stacked (re | im) rows of the GEMM output S[rows][cols];
+ * log_clamp: y = log(max(x, floor)), gradient dy / x where x > floor else 0 (torch.clamp + torch.log). */
+int tdvc_stft_frames_fwd(const float* x, const float* win, float* F, int B, int T, int n_fft, int hop, int pad, int NF,
+                         int split, void* stream);
+int tdvc_stft_frames_bwd(const float* dF, const float* win, float* dx, int B, int T, int n_fft, int hop, int pad, int NF,
+                         int split, void* stream);
+int tdvc_power_fwd(const float* S, float* P, int nfreq, int im_off, int64_t cols, void* stream);
+int tdvc_power_bwd(const float* S, const float* dP, float* dS, int nfreq, int im_off, int rows_total, int64_t cols,
+                   void* stream);
+int tdvc_log_clamp_fwd(const float* x, float* y, int64_t n, float floor_, void* stream);
+int tdvc_log_clamp_bwd(const float* x, const float* dy, float* dx, int64_t n, float floor_, void* stream);
 
 #ifdef __cplusplus
 }

@@ -350,8 +350,102 @@ __global__ void frame_unpack_k(const float* __restrict__ dxf, float* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------ operand packs, one launch each
+// The grouped operands of one MRF depth (G kernel-size branches, model/generator.py:175-194) from the branches' fp32
+// weights w_g[C][C][k_g]: wp[Kmax][G*C][C] (forward: row = (branch, co), column = ci, branch g's taps centred inside Kmax,
+// zeros around them), wtp[Kmax][G*C][C] (data gradient: row = (branch, ci), column = co, taps reversed) and the
+// concatenated bias[G*C] -- instead of 3 fills + 6 per-weight pack launches + 3 bias copies.
+struct ChainPackP {
+  const float* w[4];
+  const float* bias[4];
+  int k[4];
+  int G, C, Kmax;
+  __nv_bfloat16* wp;
+  __nv_bfloat16* wtp;
+  float* bias_out;
+};
+
+__global__ void chain_pack_k(const __grid_constant__ ChainPackP p) {
+  pdl_prologue();
+  const long long n = (long long)p.Kmax * p.G * p.C * p.C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i % p.C);
+    long long r = i / p.C;
+    const int a = (int)(r % p.C); r /= p.C;
+    const int g = (int)(r % p.G);
+    const int tap = (int)(r / p.G);
+    const int kg = p.k[g], lo = (p.Kmax - kg) >> 1, t = tap - lo;
+    float f = 0.f, ft = 0.f;
+    if (t >= 0 && t < kg) {
+      f = p.w[g][((long long)a * p.C + b) * kg + t];                       // W[co = a][ci = b][t]
+      ft = p.w[g][((long long)b * p.C + a) * kg + (kg - 1 - t)];           // W[co = b][ci = a][k - 1 - t]
+    }
+    p.wp[i] = __float2bfloat16(f);
+    p.wtp[i] = __float2bfloat16(ft);
+  }
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < p.G * p.C; i += blockDim.x) {
+      const int g = i / p.C;
+      p.bias_out[i] = p.bias[g] ? p.bias[g][i - g * p.C] : 0.f;
+    }
+}
+
+// The bundled frame-view operands of a grouped strided conv (model/discriminator.py:26-30) from its weight
+// w[Cout][cin_g][K]: wp[m][Cout][cin_b] -- frame tap j, output channel co, bundle-local frame channel (local conv group,
+// c, phase p) <- w[co][c][s*j + p] on the diagonal blocks, zero elsewhere and for the appended taps -- and
+// wtp[m][nb*cin_b][cout_b] = the same transposed inside each bundle with the taps reversed (data gradient).
+__global__ void frame_weights_pack_k(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, __nv_bfloat16* __restrict__ wtp,
+                                     int Cout, int cin_g, int K, int s, int m, int sub, int cin_b, int cout_b) {
+  pdl_prologue();
+  const int fpg = cin_g * s, cout_g = cout_b / sub, nb = Cout / cout_b;
+  const long long n = (long long)m * Cout * cin_b;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int cib = (int)(i % cin_b);
+    long long r = i / cin_b;
+    const int co = (int)(r % Cout);
+    const int j = (int)(r / Cout);
+    const int sub_in = cib / fpg, local = cib - sub_in * fpg;
+    const int c = local / s, ph = local - c * s;
+    const int k = j * s + ph;
+    const int sub_out = (co / cout_g) % sub;
+    const float f = (sub_in == sub_out && k < K) ? w[((long long)co * cin_g + c) * K + k] : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16(f);
+    wp[i] = h;
+    const int bundle = co / cout_b, cob = co - bundle * cout_b;
+    wtp[((long long)(m - 1 - j) * nb * cin_b + (long long)bundle * cin_b + cib) * cout_b + cob] = h;
+  }
+}
+
 }  // namespace tdvc
 using namespace tdvc;
+
+extern "C" int tdvc_chain_pack(const float* const* w, const float* const* bias, const int* k, int G, int C, int Kmax, void* wp,
+                               void* wtp, float* bias_out, void* stream) {
+  TDVC_CHECK_ARG(w && k && G >= 1 && G <= 4 && C > 0 && Kmax >= 1 && wp && wtp && bias_out);
+  ChainPackP p{};
+  for (int g = 0; g < G; ++g) {
+    TDVC_CHECK_ARG(w[g] && k[g] >= 1 && k[g] <= Kmax && (Kmax - k[g]) % 2 == 0);
+    p.w[g] = w[g]; p.bias[g] = bias ? bias[g] : nullptr; p.k[g] = k[g];
+  }
+  p.G = G; p.C = C; p.Kmax = Kmax; p.wp = (__nv_bfloat16*)wp; p.wtp = (__nv_bfloat16*)wtp; p.bias_out = bias_out;
+  const long long n = (long long)Kmax * G * C * C;
+  const int blocks = (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, 4LL * num_sms()));
+  tdvc::launch_k(chain_pack_k, blocks, 256, 0, (cudaStream_t)stream, p);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_frame_weights_pack(const float* w, void* wp, void* wtp, int Cout, int cin_g, int K, int s, int m, int sub,
+                                       int cin_b, int cout_b, void* stream) {
+  TDVC_CHECK_ARG(w && wp && wtp && Cout > 0 && cin_g > 0 && K > 0 && s >= 1 && m >= 1 && m * s >= K && sub >= 1);
+  TDVC_CHECK_ARG(cin_b == sub * cin_g * s && cout_b % sub == 0 && Cout % cout_b == 0);
+  const long long n = (long long)m * Cout * cin_b;
+  const int blocks = (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, 4LL * num_sms()));
+  tdvc::launch_k(frame_weights_pack_k, blocks, 256, 0, (cudaStream_t)stream, w, (__nv_bfloat16*)wp, (__nv_bfloat16*)wtp, Cout, cin_g,
+                 K, s, m, sub, cin_b, cout_b);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
 
 extern "C" int tdvc_frame_pack_bf16(const float* x, void* xf, int B, int C, int T, int s, int pad, int Tq, void* stream) {
   TDVC_CHECK_ARG(x && xf && B >= 0 && C > 0 && T > 0 && pad >= 0 && Tq > 0 && (s == 1 || s == 2 || s == 4 || s == 8));

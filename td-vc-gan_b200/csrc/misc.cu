@@ -121,6 +121,62 @@ __global__ void abs_diff_bwd_k(const float* __restrict__ a, const float* __restr
   }
 }
 
+// sum_j scale_j * sum_i |a_j[i] - b_j[i]| for up to TDVC_L1_MAX_JOBS tensor pairs in ONE launch (the 30 feature maps of
+// util/losses.py:55-68), and its gradient.  The job table travels by value in the kernel parameters: the operands are
+// transient activations, so a device-resident pointer table would need a host-to-device copy per step, which a CUDA
+// graph cannot capture.  blockIdx.y = job; blockIdx.x strides over the job's elements.
+struct L1Jobs {
+  const float* a[TDVC_L1_MAX_JOBS];
+  const float* b[TDVC_L1_MAX_JOBS];
+  float* da[TDVC_L1_MAX_JOBS];
+  long long n[TDVC_L1_MAX_JOBS];
+  float scale[TDVC_L1_MAX_JOBS];
+};
+
+__global__ void abs_diff_sum_multi_k(const __grid_constant__ L1Jobs jobs, float* __restrict__ out) {
+  pdl_prologue();
+  __shared__ float sm[33];
+  const int j = blockIdx.y;
+  const float* a = jobs.a[j];
+  const float* b = jobs.b[j];
+  const long long n = jobs.n[j];
+  float s = 0.f;
+  const long long n4 = n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const float4* a4 = reinterpret_cast<const float4*>(a);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+  for (long long i = i0; i < n4; i += stride) {
+    const float4 u = a4[i], v = b4[i];
+    s += fabsf(u.x - v.x) + fabsf(u.y - v.y) + fabsf(u.z - v.z) + fabsf(u.w - v.w);
+  }
+  for (long long i = (n4 << 2) + i0; i < n; i += stride) s += fabsf(a[i] - b[i]);
+  s = block_sum(s, sm);
+  if (threadIdx.x == 0 && s != 0.f) atomicAdd(out, s * jobs.scale[j]);
+}
+
+__global__ void abs_diff_bwd_multi_k(const __grid_constant__ L1Jobs jobs, const float* __restrict__ gscale) {
+  pdl_prologue();
+  const int j = blockIdx.y;
+  const float* a = jobs.a[j];
+  const float* b = jobs.b[j];
+  float* da = jobs.da[j];
+  const long long n = jobs.n[j];
+  const float g = jobs.scale[j] * gscale[0];
+  const long long n4 = n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const float4* a4 = reinterpret_cast<const float4*>(a);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+  float4* d4 = reinterpret_cast<float4*>(da);
+  auto sg = [g](float d) { return d > 0.f ? g : (d < 0.f ? -g : 0.f); };
+  for (long long i = i0; i < n4; i += stride) {
+    const float4 u = a4[i], v = b4[i];
+    d4[i] = make_float4(sg(u.x - v.x), sg(u.y - v.y), sg(u.z - v.z), sg(u.w - v.w));
+  }
+  for (long long i = (n4 << 2) + i0; i < n; i += stride) da[i] = sg(a[i] - b[i]);
+}
+
 // AdamW exactly as torch.optim.AdamW (decoupled decay, bias correction, eps outside the sqrt of v_hat):
 //   p *= 1 - lr*wd ; m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
 __global__ void adamw_multi_k(float* const* __restrict__ params, const float* const* __restrict__ grads,
@@ -277,6 +333,45 @@ extern "C" int tdvc_abs_diff_bwd(const float* a, const float* b, float scale, co
   if (n == 0) return TDVC_OK;
   TDVC_CHECK_ARG(a && b && gscale && da);
   tdvc::launch_k(abs_diff_bwd_k, ew_blocks(n), 256, 0, (cudaStream_t)stream, a, b, scale, gscale, da, n);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+static int fill_l1_jobs(L1Jobs& J, const tdvc_l1_job* jobs, int n_jobs, bool bwd, long long* max_n) {
+  TDVC_CHECK_ARG(jobs && n_jobs >= 1 && n_jobs <= TDVC_L1_MAX_JOBS);
+  *max_n = 0;
+  for (int j = 0; j < n_jobs; ++j) {
+    TDVC_CHECK_ARG(jobs[j].n >= 0 && jobs[j].a && jobs[j].b && ((uintptr_t)jobs[j].a % 16 == 0) && ((uintptr_t)jobs[j].b % 16 == 0));
+    if (bwd) TDVC_CHECK_ARG(jobs[j].da && ((uintptr_t)jobs[j].da % 16 == 0));
+    J.a[j] = jobs[j].a; J.b[j] = jobs[j].b; J.da[j] = jobs[j].da; J.n[j] = jobs[j].n; J.scale[j] = jobs[j].scale;
+    *max_n = std::max<long long>(*max_n, jobs[j].n);
+  }
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_abs_diff_sum_multi(const tdvc_l1_job* jobs, int n_jobs, float* out_sum, void* stream) {
+  TDVC_CHECK_ARG(out_sum);
+  L1Jobs J{};
+  long long max_n = 0;
+  int rc = fill_l1_jobs(J, jobs, n_jobs, false, &max_n);
+  if (rc) return rc;
+  if (max_n == 0) return TDVC_OK;
+  // enough blocks for the largest map to stream at full rate; small maps leave most of their row of blocks idle
+  int bx = (int)std::max<long long>(1, std::min<long long>((max_n + 4095) / 4096, (4LL * num_sms() + n_jobs - 1) / n_jobs));
+  tdvc::launch_k(abs_diff_sum_multi_k, dim3(bx, n_jobs), 256, 0, (cudaStream_t)stream, J, out_sum);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_abs_diff_bwd_multi(const tdvc_l1_job* jobs, int n_jobs, const float* gscale, void* stream) {
+  TDVC_CHECK_ARG(gscale);
+  L1Jobs J{};
+  long long max_n = 0;
+  int rc = fill_l1_jobs(J, jobs, n_jobs, true, &max_n);
+  if (rc) return rc;
+  if (max_n == 0) return TDVC_OK;
+  int bx = (int)std::max<long long>(1, std::min<long long>((max_n + 4095) / 4096, (8LL * num_sms() + n_jobs - 1) / n_jobs));
+  tdvc::launch_k(abs_diff_bwd_multi_k, dim3(bx, n_jobs), 256, 0, (cudaStream_t)stream, J, gscale);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }

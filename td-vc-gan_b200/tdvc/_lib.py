@@ -38,6 +38,14 @@ class TcConv(C.Structure):
                 ("t_valid", C.c_int32), ("pk_slope", C.c_float)]
 
 
+class L1Job(C.Structure):
+    """struct tdvc_l1_job"""
+    _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("da", C.c_void_p), ("n", C.c_int64), ("scale", C.c_float)]
+
+
+L1_MAX_JOBS = 32
+
+
 class TcWgrad2(C.Structure):
     """struct tdvc_tc_wgrad2"""
     _fields_ = [("dyp", C.c_void_p), ("xp", C.c_void_p), ("ws", C.c_void_p), ("dw", C.c_void_p * 4), ("db", C.c_void_p * 4),
@@ -93,6 +101,8 @@ SIGNATURES = {
     "tdvc_sq_err_const_bwd": (_I, [_P, _F, _F, _P, _P, _L, _P]),
     "tdvc_abs_diff_sum": (_I, [_P, _P, _F, _P, _L, _P]),
     "tdvc_abs_diff_bwd": (_I, [_P, _P, _F, _P, _P, _L, _P]),
+    "tdvc_abs_diff_sum_multi": (_I, [C.POINTER(L1Job), _I, _P, _P]),
+    "tdvc_abs_diff_bwd_multi": (_I, [C.POINTER(L1Job), _I, _P, _P]),
     "tdvc_contrastive_dir": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
     "tdvc_adamw_multi": (_I, [_P, _P, _P, _P, _P, _I, _L, _F, _F, _F, _F, _F, _I, _F, _P, _P]),
     "tdvc_pack_cl_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _I, _I, _I, _P, _P]),
@@ -106,6 +116,14 @@ SIGNATURES = {
     "tdvc_chain_fold": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _L, _L, _I, _I, _I, _P]),
     "tdvc_conv1d_tc_wgrad2_ws": (_L, [C.POINTER(TcWgrad2)]),
     "tdvc_conv1d_tc_wgrad2": (_I, [C.POINTER(TcWgrad2), _P]),
+    "tdvc_stft_frames_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "tdvc_stft_frames_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "tdvc_power_fwd": (_I, [_P, _P, _I, _I, _L, _P]),
+    "tdvc_power_bwd": (_I, [_P, _P, _P, _I, _I, _I, _L, _P]),
+    "tdvc_log_clamp_fwd": (_I, [_P, _P, _L, _F, _P]),
+    "tdvc_log_clamp_bwd": (_I, [_P, _P, _P, _L, _F, _P]),
+    "tdvc_chain_pack": (_I, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int), _I, _I, _I, _P, _P, _P, _P]),
+    "tdvc_frame_weights_pack": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "tdvc_frame_pack_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "tdvc_frame_unpack": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "tdvc_conv1d_tc_fwd_stacked": (_I, [_P, _P, _P, _P] + [_I] * 12 + [_I, _F] + [_I] * 5 + [_P]),

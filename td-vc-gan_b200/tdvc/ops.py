@@ -832,7 +832,7 @@ def mse_to_const_sum(tensors: Sequence[torch.Tensor], target: float) -> torch.Te
 
 
 class _L1MeanSum(torch.autograd.Function):
-    """sum_i mean(|a_i - b_i|), b detached: util/losses.py:55-68 (all 30 feature maps, one scalar)."""
+    """sum_i mean(|a_i - b_i|), b detached: util/losses.py:55-68 (all 30 feature maps, one scalar, one launch)."""
 
     @staticmethod
     def forward(ctx, n, *tensors):
@@ -841,11 +841,10 @@ class _L1MeanSum(torch.autograd.Function):
         a = [_c(t) for t in a]
         b = [_c(t) for t in b]
         out = torch.zeros(1, device=a[0].device, dtype=torch.float32)
-        lib = _lib.load()
         for u, v in zip(a, b):
             if u.shape != v.shape:
                 raise RuntimeError(f"l1 loss: shape mismatch {tuple(u.shape)} vs {tuple(v.shape)}")
-            _lib.check(lib.tdvc_abs_diff_sum(_p(u), _p(v), 1.0 / u.numel(), _p(out), u.numel(), _st()), "abs_diff_sum")
+        _l1_multi([(u, v, None) for u, v in zip(a, b)], out=out)
         ctx.n = n
         ctx.save_for_backward(*a, *b)
         return out.reshape(())
@@ -855,15 +854,16 @@ class _L1MeanSum(torch.autograd.Function):
         n = ctx.n
         a, b = ctx.saved_tensors[:n], ctx.saved_tensors[n:]
         g = g.reshape(1).contiguous().float()
-        lib = _lib.load()
-        grads = []
+        grads, pairs = [], []
         for i, (u, v) in enumerate(zip(a, b)):
             if not ctx.needs_input_grad[1 + i]:
                 grads.append(None)
                 continue
             d = torch.empty_like(u)
-            _lib.check(lib.tdvc_abs_diff_bwd(_p(u), _p(v), 1.0 / u.numel(), _p(g), _p(d), u.numel(), _st()), "abs_diff_bwd")
+            pairs.append((u, v, d))
             grads.append(d)
+        if pairs:
+            _l1_multi(pairs, gscale=g)
         return (None, *grads, *([None] * n))
 
 
@@ -919,10 +919,28 @@ def l1_mean_sum(sig: Sequence[torch.Tensor], ref: Sequence[torch.Tensor]) -> tor
     return _L1MeanSum.apply(len(sig), *sig, *ref)
 
 
+def _l1_multi(pairs, out=None, gscale=None):
+    """pairs: [(a, b, da or None)] contiguous fp32 tensors of equal numel per pair; forward when `out` is given (adds
+    sum_j mean|a_j - b_j| into it), backward when `gscale` is given (da_j = gscale / numel_j * sign(a_j - b_j))."""
+    lib = _lib.load()
+    for i in range(0, len(pairs), _lib.L1_MAX_JOBS):
+        chunk = pairs[i:i + _lib.L1_MAX_JOBS]
+        jobs = (_lib.L1Job * len(chunk))()
+        for j, (a, b, da) in enumerate(chunk):
+            jobs[j].a, jobs[j].b = a.data_ptr(), b.data_ptr()
+            jobs[j].da = da.data_ptr() if da is not None else None
+            jobs[j].n, jobs[j].scale = b.numel(), 1.0 / b.numel()
+        if out is not None:
+            _lib.check(lib.tdvc_abs_diff_sum_multi(jobs, len(chunk), _p(out), _st()), "abs_diff_sum_multi")
+        else:
+            _lib.check(lib.tdvc_abs_diff_bwd_multi(jobs, len(chunk), _p(gscale), _st()), "abs_diff_bwd_multi")
+
+
 class _L1MeanSumRows(torch.autograd.Function):
     """sum_i mean(|a_i[row0:row0+n] - b_i|) where a_i holds several signals stacked along the batch (the batched
-    discriminator call of the G step) and b_i is the detached reference of `n` rows.  The backward writes the gradient
-    of the whole stacked tensor (zeros outside the rows) instead of leaving a slice for autograd to pad."""
+    discriminator call of the G step) and b_i is the detached reference of `n` rows: ONE reduction launch for all maps and
+    ONE gradient launch.  The backward writes the gradient of the whole stacked tensor (zeros outside the rows) instead of
+    leaving a slice for autograd to pad."""
 
     @staticmethod
     def forward(ctx, n, row0, nrows, *tensors):
@@ -931,12 +949,12 @@ class _L1MeanSumRows(torch.autograd.Function):
         a = [_c(t) for t in a]
         b = [_c(t) for t in b]
         out = torch.zeros(1, device=a[0].device, dtype=torch.float32)
-        lib = _lib.load()
+        pairs = []
         for u, v in zip(a, b):
             if row0 < 0 or row0 + nrows > u.shape[0] or tuple(v.shape) != (nrows,) + tuple(u.shape[1:]):
                 raise RuntimeError(f"l1 loss: rows [{row0}, {row0 + nrows}) of {tuple(u.shape)} vs {tuple(v.shape)}")
-            us = u[row0:row0 + nrows]
-            _lib.check(lib.tdvc_abs_diff_sum(_p(us), _p(v), 1.0 / v.numel(), _p(out), v.numel(), _st()), "abs_diff_sum")
+            pairs.append((u[row0:row0 + nrows], v, None))
+        _l1_multi(pairs, out=out)
         ctx.cfg = (n, row0, nrows)
         ctx.save_for_backward(*a, *b)
         return out.reshape(())
@@ -946,8 +964,7 @@ class _L1MeanSumRows(torch.autograd.Function):
         n, row0, nrows = ctx.cfg
         a, b = ctx.saved_tensors[:n], ctx.saved_tensors[n:]
         g = g.reshape(1).contiguous().float()
-        lib = _lib.load()
-        grads = []
+        grads, pairs = [], []
         for i, (u, v) in enumerate(zip(a, b)):
             if not ctx.needs_input_grad[3 + i]:
                 grads.append(None)
@@ -957,15 +974,103 @@ class _L1MeanSumRows(torch.autograd.Function):
                 d[:row0].zero_()
             if row0 + nrows < u.shape[0]:
                 d[row0 + nrows:].zero_()
-            _lib.check(lib.tdvc_abs_diff_bwd(_p(u[row0:row0 + nrows]), _p(v), 1.0 / v.numel(), _p(g), _p(d[row0:row0 + nrows]),
-                                             v.numel(), _st()), "abs_diff_bwd")
+            pairs.append((u[row0:row0 + nrows], v, d[row0:row0 + nrows]))
             grads.append(d)
+        if pairs:
+            _l1_multi(pairs, gscale=g)
         return (None, None, None, *grads, *([None] * n))
 
 
 def l1_mean_sum_rows(sig: Sequence[torch.Tensor], row0: int, nrows: int, ref: Sequence[torch.Tensor]) -> torch.Tensor:
     sig, ref = list(sig), [r.detach() for r in ref]
     return _L1MeanSumRows.apply(len(sig), int(row0), int(nrows), *sig, *ref)
+
+
+# ----------------------------------------------------------------------------- log-mel loss pieces (mel.cu)
+
+class _StftFrames(torch.autograd.Function):
+    """x[B, T] -> windowed frames F[(3*)n_fft, B*NF] with reflect padding n_fft/2 (torch.stft(center=True) framing)."""
+
+    @staticmethod
+    def forward(ctx, x, win, n_fft, hop, split):
+        _req(x, win)
+        x, win = _c(x), _c(win)
+        B, T = x.shape
+        pad = n_fft // 2
+        NF = (T + 2 * pad - n_fft) // hop + 1
+        if pad >= T:
+            raise RuntimeError(f"stft: reflect padding {pad} must be smaller than the signal length {T}")
+        F_ = torch.empty((3 if split else 1) * n_fft, B * NF, device=x.device, dtype=torch.float32)
+        _lib.check(_lib.load().tdvc_stft_frames_fwd(_p(x), _p(win), _p(F_), B, T, n_fft, hop, pad, NF, int(split), _st()), "stft_frames")
+        ctx.cfg = (B, T, n_fft, hop, pad, NF, int(split))
+        ctx.save_for_backward(win)
+        return F_
+
+    @staticmethod
+    def backward(ctx, dF):
+        (win,) = ctx.saved_tensors
+        B, T, n_fft, hop, pad, NF, split = ctx.cfg
+        dF = _c(dF)
+        dx = torch.empty(B, T, device=dF.device, dtype=torch.float32)
+        _lib.check(_lib.load().tdvc_stft_frames_bwd(_p(dF), _p(win), _p(dx), B, T, n_fft, hop, pad, NF, split, _st()), "stft_frames_bwd")
+        return dx, None, None, None, None
+
+
+def stft_frames(x, win, n_fft, hop, split=False):
+    return _StftFrames.apply(x, win, int(n_fft), int(hop), bool(split))
+
+
+class _Power(torch.autograd.Function):
+    """S[rows, cols] with real parts in rows [0, nfreq) and imaginary parts in rows [im_off, im_off + nfreq) -> |X|^2 [nfreq, cols]"""
+
+    @staticmethod
+    def forward(ctx, S, nfreq, im_off):
+        _req(S)
+        S = _c(S)
+        rows, cols = S.shape
+        P = torch.empty(nfreq, cols, device=S.device, dtype=torch.float32)
+        _lib.check(_lib.load().tdvc_power_fwd(_p(S), _p(P), nfreq, im_off, cols, _st()), "power")
+        ctx.cfg = (nfreq, im_off)
+        ctx.save_for_backward(S)
+        return P
+
+    @staticmethod
+    def backward(ctx, dP):
+        (S,) = ctx.saved_tensors
+        nfreq, im_off = ctx.cfg
+        dP = _c(dP)
+        dS = torch.empty_like(S)
+        _lib.check(_lib.load().tdvc_power_bwd(_p(S), _p(dP), _p(dS), nfreq, im_off, S.shape[0], S.shape[1], _st()), "power_bwd")
+        return dS, None, None
+
+
+def power_spectrum(S, nfreq, im_off):
+    return _Power.apply(S, int(nfreq), int(im_off))
+
+
+class _LogClamp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, floor_):
+        _req(x)
+        x = _c(x)
+        y = torch.empty_like(x)
+        _lib.check(_lib.load().tdvc_log_clamp_fwd(_p(x), _p(y), x.numel(), floor_, _st()), "log_clamp")
+        ctx.floor_ = floor_
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = _c(dy)
+        dx = torch.empty_like(x)
+        _lib.check(_lib.load().tdvc_log_clamp_bwd(_p(x), _p(dy), _p(dx), x.numel(), ctx.floor_, _st()), "log_clamp_bwd")
+        return dx, None
+
+
+def log_clamp(x, floor_=1e-5):
+    """torch.log(torch.clamp(x, min=floor_))"""
+    return _LogClamp.apply(x, float(floor_))
 
 
 # ----------------------------------------------------------------------------- bf16 tensor-core conv path
@@ -1314,25 +1419,16 @@ def _grouped_frame_plan(Cin, Cout, K, stride, groups, dilation, reflect):
 
 
 def _frame_weights(w, stride, plan):
-    """(forward, data-gradient) operands of the bundled frame convolution from the grouped conv weight w[Cout, cin_g, K]:
-    wp[j][bundle*Cout_b + co][ci] with ci = (local conv group, c, p) <- w[co, c, s*j + p] on the diagonal blocks, zero
-    elsewhere and for the appended taps; wtp[j'][bundle*Cin_b + ci][co] = wp[m-1-j'][...][ci] (taps reversed)."""
+    """(forward, data-gradient) operands of the bundled frame convolution from the grouped conv weight w[Cout, cin_g, K], one
+    launch: wp[j][bundle*Cout_b + co][ci] with ci = (local conv group, c, p) <- w[co, c, s*j + p] on the diagonal blocks,
+    zero elsewhere and for the appended taps; wtp[j'][bundle*Cin_b + ci][co] = wp[m-1-j'][...][ci] (taps reversed)."""
     sub, m, cin_b, cout_b, nb = plan
     Cout, cin_g, K = w.shape
-    fpg = cin_g * stride
-    wk = torch.nn.functional.pad(w, (0, m * stride - K)) if m * stride != K else w
-    src = wk.view(Cout, cin_g, m, stride).permute(2, 0, 1, 3).reshape(m, Cout, fpg)
-    if sub == 1:
-        wp32 = src
-    else:
-        cout_g = Cout // (nb * sub)
-        src5 = src.view(m, nb, sub, cout_g, fpg)
-        blk = torch.zeros(m, nb, sub, cout_g, sub, fpg, device=w.device, dtype=w.dtype)
-        for i in range(sub):
-            blk[:, :, i, :, i, :] = src5[:, :, i]
-        wp32 = blk.view(m, Cout, cin_b)
-    wp = wp32.to(torch.bfloat16).contiguous()
-    wtp = wp.view(m, nb, cout_b, cin_b).flip(0).transpose(2, 3).reshape(m, nb * cin_b, cout_b).contiguous()
+    w = _c(w)
+    wp = torch.empty(m, Cout, cin_b, device=w.device, dtype=torch.bfloat16)
+    wtp = torch.empty(m, nb * cin_b, cout_b, device=w.device, dtype=torch.bfloat16)
+    _lib.check(_lib.load().tdvc_frame_weights_pack(_p(w), _p(wp), _p(wtp), Cout, cin_g, K, stride, m, sub, cin_b, cout_b, _st()),
+               "frame_weights_pack")
     return wp, wtp
 
 
@@ -1636,22 +1732,18 @@ def mrf_stage_eligible(C, T, kernel_sizes, dilations, has_cond, Cc=0) -> bool:
 
 
 def _chain_weights(ws_f32, bs, G, Cx, Kmax, ks):
-    """Grouped operands of one depth: wp[Kmax][G*Cx][Cx] (forward; branch i's k_i taps centred, zeros around them),
-    wtp[Kmax][G*Cx][Cx] (data gradient: rows = input channels, taps reversed) and the concatenated bias [G*Cx]."""
+    """Grouped operands of one depth, one launch: wp[Kmax][G*Cx][Cx] (forward; branch i's k_i taps centred, zeros around
+    them), wtp[Kmax][G*Cx][Cx] (data gradient: rows = input channels, taps reversed) and the concatenated bias [G*Cx]."""
     lib = _lib.load()
     dev = ws_f32[0].device
-    wp = torch.zeros(Kmax, G * Cx, Cx, device=dev, dtype=torch.bfloat16)
-    wtp = torch.zeros(Kmax, G * Cx, Cx, device=dev, dtype=torch.bfloat16)
-    bias = torch.zeros(G * Cx, device=dev, dtype=torch.float32)
-    for i in range(G):
-        w = _c(ws_f32[i])
-        off = (Kmax - ks[i]) // 2 * (G * Cx * Cx) * 2             # bytes: the first of the centred taps
-        _lib.check(lib.tdvc_pack_weight_bf16(_p(w), C.c_void_p(wp.data_ptr() + off), Cx, Cx, ks[i], Cx, Cx, 0, G * Cx, i * Cx, Cx, 0,
-                                             _st()), "pack chain w")
-        _lib.check(lib.tdvc_pack_weight_bf16(_p(w), C.c_void_p(wtp.data_ptr() + off), Cx, Cx, ks[i], Cx, Cx, 1, G * Cx, i * Cx, Cx, 0,
-                                             _st()), "pack chain w^T")
-        if bs[i] is not None:
-            bias[i * Cx:(i + 1) * Cx].copy_(bs[i])
+    wp = torch.empty(Kmax, G * Cx, Cx, device=dev, dtype=torch.bfloat16)
+    wtp = torch.empty(Kmax, G * Cx, Cx, device=dev, dtype=torch.bfloat16)
+    bias = torch.empty(G * Cx, device=dev, dtype=torch.float32)
+    keep = [_c(w) for w in ws_f32] + [_c(b) for b in bs]
+    wptr = (C.c_void_p * G)(*[t.data_ptr() for t in keep[:G]])
+    bptr = (C.c_void_p * G)(*[(t.data_ptr() if t is not None else None) for t in keep[G:]])
+    karr = (C.c_int * G)(*[int(k) for k in ks])
+    _lib.check(lib.tdvc_chain_pack(wptr, bptr, karr, G, Cx, Kmax, _p(wp), _p(wtp), _p(bias), _st()), "chain_pack")
     return wp, wtp, bias
 
 

@@ -1,8 +1,10 @@
 """GAN training losses (reference: util/losses.py).  Same names and argument meaning.
 
-multiscale_feat_loss runs on the tdvc reduction kernels (one accumulation buffer for all 30 feature maps).
-multiscale_spec_loss and contrastive_loss are SURVEY.md 8(f) "next" rows: restated here on torch ops
-(cuFFT / matmul / gather), not yet on hand-written kernels."""
+multiscale_feat_loss runs on the tdvc reduction kernels (one launch for all 30 feature maps).  multiscale_spec_loss is
+the library's own as well: framing + window, the 2048-point real DFT of the 18 frames as a GEMM against a (cos | -sin)
+basis on the convolution kernels (tcgen05 in bf16 mode, with the operands split into bf16 high and low parts so that the
+spectrum keeps fp32-class accuracy), |X|^2, the mel projection as a second GEMM, log(clamp) and the L1 reduction -- no
+cuFFT / cuBLAS.  contrastive_loss is one fused gather + cosine + cross-entropy kernel per direction."""
 import functools
 import math
 
@@ -58,7 +60,55 @@ def _mel_operands(sr, n_fft, n_mels, device):
     return window.to(device), fb.to(device)
 
 
+@functools.lru_cache(maxsize=None)
+def _dft_basis(n_fft, device, split):
+    """[rows, n_fft, 1] conv weight of the real DFT: rows [0, nfreq) = cos(2 pi f k / N), rows [nfreq, 2 nfreq) = -sin(...),
+    zero rows up to a multiple of 128 (the tensor-core kernels' wide-N tiling).  split: three column blocks
+    [B_hi | B_hi | B_lo] (bf16 high / low parts, stored as fp32) matching ops.stft_frames(split=True)."""
+    nfreq = n_fft // 2 + 1
+    rows = (2 * nfreq + 127) // 128 * 128
+    k = torch.arange(n_fft, dtype=torch.float64)
+    f = torch.arange(nfreq, dtype=torch.float64).unsqueeze(1)
+    ang = 2.0 * math.pi * f * k / n_fft
+    B = torch.zeros(rows, n_fft, dtype=torch.float64)
+    B[:nfreq] = torch.cos(ang)
+    B[nfreq:2 * nfreq] = -torch.sin(ang)
+    B = B.float()
+    if split:
+        hi = B.to(torch.bfloat16).float()
+        lo = (B - hi).to(torch.bfloat16).float()
+        B = torch.cat([hi, hi, lo], dim=1)
+    return B.unsqueeze(2).contiguous().to(device), nfreq, nfreq
+
+
 def _log_mel(signal, n_fft):
+    """log(clamp(MelSpectrogram(signal), 1e-5)) -> [..., n_mels, frames] on the tdvc kernels (CUDA fp32 tensors)."""
+    window, fb = _mel_operands(16000, n_fft, 80, signal.device)
+    lead = signal.shape[:-1]
+    x = signal.reshape(-1, signal.shape[-1])
+    Bn = x.shape[0]
+    split = ops.get_precision() == "bf16"          # bf16 tensor-core GEMM: hi / lo operand split keeps fp32-class accuracy
+    basis, nfreq, im_off = _dft_basis(n_fft, signal.device, split)
+    frames = ops.stft_frames(x, window, n_fft, n_fft // 4, split=split)              # [(3*)n_fft, B*NF]
+    spec = ops.conv1d(frames.unsqueeze(0), basis)                                    # [1, rows, B*NF]: re | im
+    power = ops.power_spectrum(spec.squeeze(0), nfreq, im_off)                       # [nfreq, B*NF]
+    if split:
+        # mel projection on the fp32 kernels: |X|^2 spans 8 decades and 80 x 1025 x 288 MACs are not worth a rounding
+        prec = ops.get_precision()
+        ops.set_precision("fp32")
+        try:
+            mel = ops.conv1d(power.unsqueeze(0), fb.t().contiguous().unsqueeze(2))
+        finally:
+            ops.set_precision(prec)
+    else:
+        mel = ops.conv1d(power.unsqueeze(0), fb.t().contiguous().unsqueeze(2))       # [1, n_mels, B*NF]
+    logmel = ops.log_clamp(mel.squeeze(0), 1e-5)                                     # [n_mels, B*NF]
+    nf = logmel.shape[1] // Bn
+    return logmel.view(logmel.shape[0], Bn, nf).permute(1, 0, 2).reshape(lead + (logmel.shape[0], nf))
+
+
+def _log_mel_torch(signal, n_fft):
+    """The same on torch ops (torch.stft + matmul): what a CPU tensor gets -- tests of the host logic only."""
     window, fb = _mel_operands(16000, n_fft, 80, signal.device)
     window, fb = window.to(signal.dtype), fb.to(signal.dtype)
     lead = signal.shape[:-1]
@@ -78,7 +128,12 @@ def multiscale_spec_loss(signal, ref, fft_sizes, spectype='both', return_separat
     for fft_size in fft_sizes:
         if norm_p != 1:
             raise AttributeError("module 'torch.nn.functional' has no attribute 'rms_loss'")
-        loss = F.l1_loss(_log_mel(signal, fft_size), _log_mel(ref, fft_size).detach())
+        if signal.is_cuda and signal.dtype == torch.float32:
+            with torch.no_grad():
+                lm_ref = _log_mel(ref, fft_size)
+            loss = ops.l1_mean_sum([_log_mel(signal, fft_size)], [lm_ref])
+        else:
+            loss = F.l1_loss(_log_mel_torch(signal, fft_size), _log_mel_torch(ref, fft_size).detach())
         losses.append(loss)
         if return_separated:
             return sum(losses), losses

@@ -255,3 +255,80 @@ def test_pool_select_losses_adamw():
         o_ref.step(); o_my.step()
     for a, b in zip(ref_p, my_p):
         assert relerr(b, a) < 1e-5
+
+
+# ----------------------------------------------------------------------------- log-mel loss pieces (mel.cu)
+@pytest.mark.parametrize("B,T,n_fft,split", [(3, 8960, 2048, False), (2, 2600, 512, False), (3, 8960, 2048, True)])
+def test_stft_frames_power_logclamp(B, T, n_fft, split):
+    """Framing with reflect padding + window (and its adjoint), |X|^2 over stacked (re | im) rows, log(clamp): against
+    torch's unfold / autograd in fp64."""
+    from tdvc import ops
+    hop = n_fft // 4
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(B, T, generator=g, dtype=torch.float64) * 0.1).requires_grad_(True)
+    win = torch.hann_window(n_fft, periodic=True, dtype=torch.float64)
+    xp = F.pad(x.unsqueeze(1), (n_fft // 2, n_fft // 2), mode="reflect").squeeze(1)
+    fr = xp.unfold(1, n_fft, hop) * win                       # [B, NF, n_fft]
+    NF = fr.shape[1]
+    ref = fr.permute(2, 0, 1).reshape(n_fft, B * NF)
+    proj = torch.randn(ref.shape, generator=g, dtype=torch.float64)
+    (ref * proj).sum().backward()
+    xd = x.detach().float().cuda().requires_grad_(True)
+    Fd = ops.stft_frames(xd, win.float().cuda(), n_fft, hop, split=split)
+    if not split:
+        assert relerr(Fd, ref) < 1e-6
+        (Fd * proj.float().cuda()).sum().backward()
+        assert relerr(xd.grad, x.grad) < 1e-5
+    else:
+        assert Fd.shape == (3 * n_fft, B * NF)
+        hi, lo = Fd[:n_fft], Fd[n_fft:2 * n_fft]
+        assert torch.equal(hi, Fd[2 * n_fft:]) and torch.equal(hi, hi.to(torch.bfloat16).float())
+        assert relerr(hi.double() + lo.double(), ref) < 2e-5          # two bf16 parts: 2^-16 relative
+        p3 = torch.cat([proj, torch.randn(ref.shape, generator=g, dtype=torch.float64), proj * 0.5]).float().cuda()
+        (Fd * p3).sum().backward()
+        assert relerr(xd.grad, 1.5 * x.grad) < 1e-5                   # blocks 0 and 2 carry the derivative, block 1 none
+    # power over stacked rows with padding rows, log-clamp with entries below the floor
+    nfreq, rows, cols = 37, 96, 50
+    S = torch.randn(rows, cols, generator=g, dtype=torch.float64).requires_grad_(True)
+    Pref = S[:nfreq] ** 2 + S[40:40 + nfreq] ** 2
+    pj = torch.randn(nfreq, cols, generator=g, dtype=torch.float64)
+    (Pref * pj).sum().backward()
+    Sd = S.detach().float().cuda().requires_grad_(True)
+    Pd = ops.power_spectrum(Sd, nfreq, 40)
+    assert relerr(Pd, Pref) < 1e-6
+    (Pd * pj.float().cuda()).sum().backward()
+    assert relerr(Sd.grad, S.grad) < 1e-6
+    m = (torch.rand(80, 60, generator=g, dtype=torch.float64) * 1e-4).requires_grad_(True)     # a third below 1e-5... roughly
+    Lref = torch.log(torch.clamp(m, min=1e-5))
+    pj2 = torch.randn(80, 60, generator=g, dtype=torch.float64)
+    (Lref * pj2).sum().backward()
+    md = m.detach().float().cuda().requires_grad_(True)
+    Ld = ops.log_clamp(md, 1e-5)
+    assert relerr(Ld, Lref) < 1e-6
+    (Ld * pj2.float().cuda()).sum().backward()
+    assert relerr(md.grad, m.grad) < 1e-5
+
+
+def test_mel_loss_bf16_mode_keeps_fp32_class_accuracy():
+    """multiscale_spec_loss in bf16 mode: the DFT GEMM runs on tcgen05 with hi / lo split operands; value within 2e-4 and
+    gradient within 2e-3 (relative L2) of the fp64 reference (the fp32 path is held at 1e-5 / 1e-4 in test_gpu_models.py)."""
+    import numpy as np
+    import util.losses as L
+    from helpers import golden
+    from oracle.cases import rand_like
+    from tdvc import ops
+    g = golden("losses")
+    a = (rand_like(torch.empty(3, 1, 8960), 51) * 0.1).float().cuda().requires_grad_(True)
+    r = (rand_like(torch.empty(3, 1, 8960), 52) * 0.1).float().cuda()
+    ops.set_precision("bf16")
+    try:
+        n0 = ops._lib.load().tdvc_flop_count(0) + ops._lib.load().tdvc_flop_count(1)
+        mel = L.multiscale_spec_loss(a, r, [2048, 1024, 512])
+        mel.backward()
+        torch.cuda.synchronize()
+        assert ops._lib.load().tdvc_flop_count(0) + ops._lib.load().tdvc_flop_count(1) > n0      # the GEMM went to tcgen05
+    finally:
+        ops.set_precision("fp32")
+    assert abs(mel.item() - float(g["mel"])) < 2e-4 * abs(float(g["mel"])), (mel.item(), float(g["mel"]))
+    ref = torch.as_tensor(np.asarray(g["dmel"])).double()
+    assert float((a.grad.double().cpu() - ref).norm() / ref.norm()) < 2e-3
