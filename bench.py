@@ -191,6 +191,9 @@ def run_ours(args):
         oC = FusedAdamW(Cm.parameters(), TRAIN["lr"], (0.9, 0.999), weight_decay=0.0)     # torch.optim.Adam, train.py:192
     hook = GradAverager() if world > 1 else None
     ts = TrainStep(G, D, hp, oG, oD, nspk, grad_hook=hook, C=Cm, optimizer_C=oC)
+    if world > 1 and args.overlap:
+        # bucketed gradient all-reduce issued from autograd hooks, overlapped with the backward (captured into the graph)
+        ts.enable_overlap(bucket_mb=args.bucket_mb)
     host = synth_batch(B, T, nspk, seed=1234 + rank)
     pinned = {k: v.pin_memory() for k, v in host.items()}
     resident, _ = to_device(host, dev)
@@ -295,6 +298,9 @@ def run_ours(args):
                        "lambda_f0": "0 (torchcrepe unavailable offline, SURVEY 8c)", "precision": args.precision,
                        "l2": "no explicit flush: one step streams >6 GB of activations, far larger than the 126 MB L2",
                        "parallelism": f"dp{world}", "step_gflop_algorithmic": step_gflop * world,
+                       "grad_allreduce": ("none (1 GPU)" if world == 1 else
+                                          (f"bucketed ({args.bucket_mb} MB), overlapped with the backward, captured in the graph"
+                                           if args.overlap else "one flat all-reduce per network between graph segments")),
                        "cuda_graph": bool(args.graph)},
             "clocks": clocks,
             "e2e": {"value": round(e2e, 3), "unit": UNIT, "h2d_bytes_per_step": h2d[0], "d2h_bytes_per_step": d2h[0],
@@ -622,6 +628,10 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("TDVC_PRECISION", "bf16"), choices=["fp32", "bf16"],
                     help="bf16 = tcgen05 tensor-core path (2e-2 parity, the headline); fp32 = exact CUDA-core path (1e-5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--overlap", type=int, default=int(os.environ.get("TDVC_DP_OVERLAP", "1")),
+                    help="N > 1: 1 = bucketed gradient all-reduce overlapped with the backward (default), 0 = one flat "
+                         "all-reduce per network after its backward")
+    ap.add_argument("--bucket-mb", type=float, default=16.0)
     ap.add_argument("--no-inference", action="store_true", help="skip the BASELINE config 5 inference sweep")
     ap.add_argument("--config", default="stage1", choices=sorted(CONFIGS),
                     help="which shipped train config the step follows (BASELINE.json configs 1, 2, 4; the wavlm configs "

@@ -56,6 +56,99 @@ class GradAverager:
         torch._foreach_copy_(grads, views)
 
 
+class BucketedReducer:
+    """Gradient mean overlapped with the backward pass that produces the gradients: the optimiser's flat
+    gradient bank is cut into buckets of ~`bucket_mb` MB in REVERSE parameter order (backward reaches the last layers
+    first); a post-accumulate-grad hook per parameter counts arrivals, and the moment a bucket is complete its gradients are
+    copied into the bank and ONE asynchronous all-reduce of that slice is issued -- on the process group's communication
+    stream, so it runs while the rest of the backward still computes.  `finish()` flushes the buckets a backward did not
+    complete (parameters without gradient count as zeros) and waits for every outstanding collective.
+
+    Inside a CUDA-graph capture the collectives are captured with the compute (NCCL supports stream capture): the graph
+    then holds the all-reduce nodes on a parallel branch, and a replay overlaps them exactly as the eager run does."""
+
+    def __init__(self, opt, group: Optional[dist.ProcessGroup] = None, bucket_mb: float = 16.0):
+        if getattr(opt, "_banks", None) is None:
+            opt.use_grad_bank()
+        self.opt, self.group = opt, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.buckets = []          # dict(flat slice, params, views)
+        self.where = {}            # id(param) -> bucket index
+        cap = int(bucket_mb * (1 << 20) / 4)
+        for bank in opt._banks:
+            params, views, flat = bank["params"], bank["views"], bank["flat"]
+            offs, o = [], 0
+            for p in params:
+                offs.append(o)
+                o += p.numel()
+            hi = len(params)
+            while hi > 0:
+                lo = hi - 1
+                while lo > 0 and offs[hi - 1] + params[hi - 1].numel() - offs[lo - 1] <= cap:
+                    lo -= 1
+                end = offs[hi - 1] + params[hi - 1].numel()
+                self.buckets.append(dict(flat=flat[offs[lo]:end], params=params[lo:hi], views=views[lo:hi]))
+                for p in params[lo:hi]:
+                    self.where[id(p)] = len(self.buckets) - 1
+                hi = lo
+        self.pending = [0] * len(self.buckets)
+        self.done = [True] * len(self.buckets)
+        self.works = []
+        self.order = []            # bucket indices in the order they were reduced (tests / diagnostics)
+        self.armed = False
+        self._handles = [p.register_post_accumulate_grad_hook(self._on_grad) for b in self.buckets for p in b["params"]]
+
+    def arm(self):
+        """call before the backward pass whose gradients are to be averaged"""
+        self.pending = [len(b["params"]) for b in self.buckets]
+        self.done = [False] * len(self.buckets)
+        self.works, self.order, self.armed = [], [], True
+
+    def _on_grad(self, p):
+        if not self.armed:
+            return
+        bi = self.where[id(p)]
+        self.pending[bi] -= 1
+        if self.pending[bi] == 0 and not self.done[bi]:
+            self._reduce(bi)
+
+    @torch.no_grad()
+    def _reduce(self, bi):
+        b = self.buckets[bi]
+        src = [p.grad for p in b["params"] if p.grad is not None]
+        dst = [v for p, v in zip(b["params"], b["views"]) if p.grad is not None]
+        missing = [v for p, v in zip(b["params"], b["views"]) if p.grad is None]
+        if missing:
+            torch._foreach_zero_(missing)
+        if src:
+            torch._foreach_copy_(dst, src)
+        self.done[bi] = True
+        self.order.append(bi)
+        if self.world > 1:
+            flat = b["flat"]
+            if flat.is_cuda and dist.get_backend(self.group) == "nccl":
+                self.works.append((dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group, async_op=True), None))
+            else:
+                self.works.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True), flat))
+
+    def finish(self):
+        """flush what the backward left incomplete, wait for the collectives; the bank then holds the averaged gradients"""
+        for bi in range(len(self.buckets)):
+            if not self.done[bi]:
+                self._reduce(bi)
+        for w, flat in self.works:
+            w.wait()
+            if flat is not None:
+                flat.div_(self.world)
+        self.works, self.armed = [], False
+        self.opt._gathered = True
+
+    def remove(self):
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+
+
 def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None):
     """Make every rank start from rank `src`'s weights (replicas are built with the same seed, this is a guard)."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:

@@ -74,6 +74,8 @@ class TrainStep:
             pass
         self.num_spk = num_spk if num_spk is not None else G.embedding.weight.shape[1]
         self.grad_hook = grad_hook
+        # gradient all-reduce overlapped with the backward (tdvc.dp.BucketedReducer per optimiser), see enable_overlap()
+        self.reducers = {}
         self._gen = None          # generator passes of the current iteration (shared by the D and the G step)
         from model.generator import Encoder
         enc = getattr(G, "encoder", None)
@@ -98,11 +100,29 @@ class TrainStep:
         else:
             torch.nn.utils.clip_grad_norm_(module.parameters(), max_norm)
 
+    def enable_overlap(self, bucket_mb: float = 16.0, group=None):
+        """Data parallel: average the gradients of D, G (and C) bucket by bucket WHILE the backward that produces them still
+        runs (north_star: "gradient allreduce over NCCL overlapped with the discriminator and generator backward"), instead
+        of one all-reduce per network after its backward.  Needs FusedAdamW optimisers (the buckets are slices of their flat
+        gradient banks)."""
+        from tdvc.dp import BucketedReducer
+        for name, opt in (("D", self.opt_D), ("G", self.opt_G), ("C", self.opt_C)):
+            if opt is not None:
+                self.reducers[name] = BucketedReducer(opt, group=group, bucket_mb=bucket_mb)
+        return self
+
+    def _arm(self, name):
+        r = self.reducers.get(name)
+        if r is not None:
+            r.arm()
+
     def _reduce_and_step(self, name, module, opt, max_norm=None):
         """(data-parallel gradient mean) + (clip) + optimiser update.  With a FusedAdamW grad bank the all-reduce runs
         on the optimiser's flat bucket, otherwise on the parameters' .grad tensors."""
         banked = opt is not None and getattr(opt, "_banks", None) is not None
-        if banked:
+        if name in self.reducers:
+            self.reducers[name].finish()        # buckets were reduced during the backward; wait for the stragglers
+        elif banked:
             opt.gather_grads()
             if self.grad_hook is not None:
                 for gi in range(len(opt._banks)):
@@ -199,6 +219,7 @@ class TrainStep:
             c_loss = torch.nn.functional.cross_entropy(out_lat, batch["label_src"])
             if self.opt_C is not None:
                 self.opt_C.zero_grad(set_to_none=True)
+            self._arm("C")
             c_loss.backward()
         return {"c_loss": c_loss.detach()}
 
@@ -232,6 +253,7 @@ class TrainStep:
         d_loss = d_real + d_fake
         if self.opt_D is not None:
             self.opt_D.zero_grad(set_to_none=True)
+        self._arm("D")
         d_loss.backward()
         return {"d_loss_real": d_real.detach(), "d_loss_fake": d_fake.detach(), "d_loss": d_loss.detach(),
                 "fake": fake, "emb_real": gen["emb_real"]}
@@ -329,6 +351,7 @@ class TrainStep:
                 g_loss = g_loss + hp["lambda_latcls"] * g_lat
             if self.opt_G is not None:
                 self.opt_G.zero_grad(set_to_none=True)
+            self._arm("G")
             g_loss.backward()
         out.update(g_adv=g_adv.detach(), g_rec=g_rec.detach(), g_idt=g_idt.detach(), g_cont=g_cont.detach(),
                    g_loss=g_loss.detach(), fake=gen["fake"].detach())
@@ -360,7 +383,9 @@ class GraphedTrainStep:
                                    "lambda_latcls != 0, for C")
             opt.use_grad_bank()
         self.static = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in example_batch.items()}
-        self.split = ts.grad_hook is not None and getattr(ts.grad_hook, "world", 1) > 1
+        # gradient all-reduces issued eagerly BETWEEN graph segments (split) -- or, with ts.enable_overlap(), captured inside
+        # one graph on the communication stream, overlapped with the backward
+        self.split = ts.grad_hook is not None and getattr(ts.grad_hook, "world", 1) > 1 and not ts.reducers
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):

@@ -56,3 +56,61 @@ def test_grad_average_and_shard_two_ranks():
     assert s_a["x"] == full[:2].tolist() and s_b["x"] == full[2:].tolist()
     assert s_b["lab"] == [2, 3] and s_a["k"] == 3
     assert s_b["neg"][0] == torch.arange(12).view(4, 3)[2:].tolist()
+
+
+def _overlap_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tdvc.dp import BucketedReducer
+    from tdvc.optim import FusedAdamW
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 40), torch.nn.Tanh(), torch.nn.Linear(40, 40), torch.nn.Tanh(),
+                              torch.nn.Linear(40, 3))
+    unused = torch.nn.Parameter(torch.ones(7))                  # never receives a gradient
+    params = list(net.parameters()) + [unused]
+    opt = FusedAdamW(params, 1e-3)
+    red = BucketedReducer(opt, bucket_mb=40 * 40 * 4 / (1 << 20))   # ~one 40x40 weight per bucket: several buckets
+    torch.manual_seed(100 + rank)
+    x = torch.randn(5, 6)
+    fired_before_finish = []
+    for it in range(2):                                          # twice: re-arming works
+        for p in params:
+            p.grad = None
+        red.arm()
+        net(x).square().sum().backward()
+        fired_before_finish.append(list(red.order))
+        red.finish()
+    local = [p.grad.clone() if p.grad is not None else torch.zeros_like(p) for p in params]
+    bank = opt.bank(0).clone()
+    q.put((rank, [g.tolist() for g in local], bank.tolist(), len(red.buckets), fired_before_finish))
+    dist.destroy_process_group()
+
+
+def test_bucketed_reducer_overlaps_and_averages_two_ranks():
+    """tdvc.dp.BucketedReducer: buckets are cut in reverse parameter order, each is all-reduced from the gradient hook of
+    its last parameter (so before the backward has finished), parameters without gradient travel as zeros, and the bank
+    ends up holding the mean over ranks."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_overlap_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, g_a, bank_a, nb_a, fired_a), (_, g_b, bank_b, nb_b, fired_b) = res
+    assert nb_a == nb_b and nb_a >= 3
+    flat_a = torch.cat([torch.tensor(g).reshape(-1) for g in g_a])
+    flat_b = torch.cat([torch.tensor(g).reshape(-1) for g in g_b])
+    want = 0.5 * (flat_a + flat_b)
+    assert torch.allclose(torch.tensor(bank_a), want, rtol=1e-6, atol=1e-7)
+    assert bank_a == bank_b
+    assert torch.all(want[-7:] == 0)                             # the unused parameter
+    for fired in (fired_a, fired_b):
+        for order in fired:
+            # every bucket whose parameters all received gradients was reduced from a hook, during the backward, and in
+            # reverse layer order (bucket 0 holds the LAST parameters but also the unused one: it waits for finish())
+            assert order == sorted(order) and len(order) >= nb_a - 1 and 0 not in order

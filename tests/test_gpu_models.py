@@ -279,7 +279,9 @@ def test_graphed_step_equals_eager_step():
     (sd_e, gl_e, dl_e), (sd_g, gl_g, dl_g) = results
     assert abs(gl_e - gl_g) <= 1e-4 * abs(gl_e) and abs(dl_e - dl_g) <= 1e-4 * abs(dl_e)
     for k in sd_e:
-        assert relerr(sd_g[k], sd_e[k]) < 1e-4, k      # atomics in wgrad reorder fp32 sums run to run
+        # atomics in the weight-gradient / loss reductions reorder fp32 sums run to run, and Adam's m / sqrt(v) turns the
+        # sign of a noise-level gradient entry into a full lr-sized step: 5e-4 (measured 1e-5 .. 1.7e-4)
+        assert relerr(sd_g[k], sd_e[k]) < 5e-4, k
 
 
 def test_latent_classifier_vs_golden():
