@@ -338,9 +338,10 @@ int tdvc_stft_frames_fwd(const float* x, const float* win, float* F, int B, int 
                          int split, void* stream);
 int tdvc_stft_frames_bwd(const float* dF, const float* win, float* dx, int B, int T, int n_fft, int hop, int pad, int NF,
                          int split, void* stream);
-int tdvc_power_fwd(const float* S, float* P, int nfreq, int im_off, int64_t cols, void* stream);
-int tdvc_power_bwd(const float* S, const float* dP, float* dS, int nfreq, int im_off, int rows_total, int64_t cols,
+int tdvc_power_fwd(const float* S, float* P, int nfreq, int im_off, int64_t cols, int split /* P = [hi | lo | hi] */,
                    void* stream);
+int tdvc_power_bwd(const float* S, const float* dP, float* dS, int nfreq, int im_off, int rows_total, int64_t cols,
+                   int split, void* stream);
 int tdvc_log_clamp_fwd(const float* x, float* y, int64_t n, float floor_, void* stream);
 int tdvc_log_clamp_bwd(const float* x, const float* dy, float* dx, int64_t n, float floor_, void* stream);
 

@@ -79,25 +79,41 @@ __global__ void stft_frames_bwd_k(const float* __restrict__ dF, const float* __r
 }
 
 // S[2*nf_pad ...]: rows [0, nfreq) = real parts, rows [im_off, im_off + nfreq) = imaginary parts, `cols` columns each
-__global__ void power_fwd_k(const float* __restrict__ S, float* __restrict__ P, int nfreq, int im_off, long long cols) {
+// split != 0: P has three row blocks [hi | lo | hi] of the power (bf16 high / low parts) for the mel projection as a bf16 GEMM
+__global__ void power_fwd_k(const float* __restrict__ S, float* __restrict__ P, int nfreq, int im_off, long long cols, int split) {
   pdl_prologue();
   const long long n = (long long)nfreq * cols;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float re = S[i], im = S[i + (long long)im_off * cols];
-    P[i] = fmaf(re, re, im * im);
+    const float v = fmaf(re, re, im * im);
+    if (!split) {
+      P[i] = v;
+    } else {
+      const float hi = __bfloat162float(__float2bfloat16(v));
+      P[i] = hi;
+      P[i + n] = __bfloat162float(__float2bfloat16(v - hi));
+      P[i + 2 * n] = hi;
+    }
   }
 }
 
 __global__ void power_bwd_k(const float* __restrict__ S, const float* __restrict__ dP, float* __restrict__ dS, int nfreq,
-                            int im_off, int rows_total, long long cols) {
+                            int im_off, int rows_total, long long cols, int split) {
   pdl_prologue();
   const long long n = (long long)rows_total * cols;
+  const long long blk2 = 2LL * nfreq * cols;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / cols);
     const long long c = i - (long long)r * cols;
+    int f = -1;
+    if (r < nfreq) f = r;
+    else if (r >= im_off && r < im_off + nfreq) f = r - im_off;
     float g = 0.f;
-    if (r < nfreq) g = 2.f * S[i] * dP[(long long)r * cols + c];
-    else if (r >= im_off && r < im_off + nfreq) g = 2.f * S[i] * dP[(long long)(r - im_off) * cols + c];
+    if (f >= 0) {
+      float d = dP[(long long)f * cols + c];
+      if (split) d += dP[(long long)f * cols + c + blk2];      // hi blocks carry the derivative, lo = v - hi none
+      g = 2.f * S[i] * d;
+    }
     dS[i] = g;       // padding rows of the GEMM output carry no gradient
   }
 }
@@ -143,20 +159,20 @@ extern "C" int tdvc_stft_frames_bwd(const float* dF, const float* win, float* dx
   return TDVC_OK;
 }
 
-extern "C" int tdvc_power_fwd(const float* S, float* P, int nfreq, int im_off, int64_t cols, void* stream) {
+extern "C" int tdvc_power_fwd(const float* S, float* P, int nfreq, int im_off, int64_t cols, int split, void* stream) {
   TDVC_CHECK_ARG(S && P && nfreq > 0 && im_off >= nfreq && cols >= 0);
   if (cols == 0) return TDVC_OK;
-  tdvc::launch_k(power_fwd_k, blocks_for((long long)nfreq * cols), 256, 0, (cudaStream_t)stream, S, P, nfreq, im_off, (long long)cols);
+  tdvc::launch_k(power_fwd_k, blocks_for((long long)nfreq * cols), 256, 0, (cudaStream_t)stream, S, P, nfreq, im_off, (long long)cols, split);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
 
 extern "C" int tdvc_power_bwd(const float* S, const float* dP, float* dS, int nfreq, int im_off, int rows_total, int64_t cols,
-                              void* stream) {
+                              int split, void* stream) {
   TDVC_CHECK_ARG(S && dP && dS && nfreq > 0 && im_off >= nfreq && rows_total >= im_off + nfreq && cols >= 0);
   if (cols == 0) return TDVC_OK;
   tdvc::launch_k(power_bwd_k, blocks_for((long long)rows_total * cols), 256, 0, (cudaStream_t)stream, S, dP, dS, nfreq, im_off,
-                 rows_total, (long long)cols);
+                 rows_total, (long long)cols, split);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }

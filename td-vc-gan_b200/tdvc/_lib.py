@@ -118,8 +118,8 @@ SIGNATURES = {
     "tdvc_conv1d_tc_wgrad2": (_I, [C.POINTER(TcWgrad2), _P]),
     "tdvc_stft_frames_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "tdvc_stft_frames_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
-    "tdvc_power_fwd": (_I, [_P, _P, _I, _I, _L, _P]),
-    "tdvc_power_bwd": (_I, [_P, _P, _P, _I, _I, _I, _L, _P]),
+    "tdvc_power_fwd": (_I, [_P, _P, _I, _I, _L, _I, _P]),
+    "tdvc_power_bwd": (_I, [_P, _P, _P, _I, _I, _I, _L, _I, _P]),
     "tdvc_log_clamp_fwd": (_I, [_P, _P, _L, _F, _P]),
     "tdvc_log_clamp_bwd": (_I, [_P, _P, _P, _L, _F, _P]),
     "tdvc_chain_pack": (_I, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int), _I, _I, _I, _P, _P, _P, _P]),

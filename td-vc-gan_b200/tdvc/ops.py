@@ -1021,31 +1021,32 @@ def stft_frames(x, win, n_fft, hop, split=False):
 
 
 class _Power(torch.autograd.Function):
-    """S[rows, cols] with real parts in rows [0, nfreq) and imaginary parts in rows [im_off, im_off + nfreq) -> |X|^2 [nfreq, cols]"""
+    """S[rows, cols] with real parts in rows [0, nfreq) and imaginary parts in rows [im_off, im_off + nfreq) -> |X|^2
+    [nfreq, cols], or its bf16 high / low split [hi | lo | hi] as three row blocks (split)."""
 
     @staticmethod
-    def forward(ctx, S, nfreq, im_off):
+    def forward(ctx, S, nfreq, im_off, split):
         _req(S)
         S = _c(S)
         rows, cols = S.shape
-        P = torch.empty(nfreq, cols, device=S.device, dtype=torch.float32)
-        _lib.check(_lib.load().tdvc_power_fwd(_p(S), _p(P), nfreq, im_off, cols, _st()), "power")
-        ctx.cfg = (nfreq, im_off)
+        P = torch.empty((3 if split else 1) * nfreq, cols, device=S.device, dtype=torch.float32)
+        _lib.check(_lib.load().tdvc_power_fwd(_p(S), _p(P), nfreq, im_off, cols, int(split), _st()), "power")
+        ctx.cfg = (nfreq, im_off, int(split))
         ctx.save_for_backward(S)
         return P
 
     @staticmethod
     def backward(ctx, dP):
         (S,) = ctx.saved_tensors
-        nfreq, im_off = ctx.cfg
+        nfreq, im_off, split = ctx.cfg
         dP = _c(dP)
         dS = torch.empty_like(S)
-        _lib.check(_lib.load().tdvc_power_bwd(_p(S), _p(dP), _p(dS), nfreq, im_off, S.shape[0], S.shape[1], _st()), "power_bwd")
-        return dS, None, None
+        _lib.check(_lib.load().tdvc_power_bwd(_p(S), _p(dP), _p(dS), nfreq, im_off, S.shape[0], S.shape[1], split, _st()), "power_bwd")
+        return dS, None, None, None
 
 
-def power_spectrum(S, nfreq, im_off):
-    return _Power.apply(S, int(nfreq), int(im_off))
+def power_spectrum(S, nfreq, im_off, split=False):
+    return _Power.apply(S, int(nfreq), int(im_off), bool(split))
 
 
 class _LogClamp(torch.autograd.Function):

@@ -81,6 +81,19 @@ def _dft_basis(n_fft, device, split):
     return B.unsqueeze(2).contiguous().to(device), nfreq, nfreq
 
 
+@functools.lru_cache(maxsize=None)
+def _mel_weight(n_fft, device, split):
+    """the mel filterbank as a [n_mels, nfreq, 1] conv weight; split: column blocks [fb_hi | fb_hi | fb_lo] (power is
+    handed over as [hi | lo | hi]) so that the bf16 tensor-core GEMM keeps fp32-class accuracy over |X|^2's 8 decades"""
+    _, fb = _mel_operands(16000, n_fft, 80, device)
+    W = fb.t().contiguous().float()
+    if split:
+        hi = W.to(torch.bfloat16).float()
+        lo = (W - hi).to(torch.bfloat16).float()
+        W = torch.cat([hi, hi, lo], dim=1)
+    return W.unsqueeze(2).contiguous()
+
+
 def _log_mel(signal, n_fft):
     """log(clamp(MelSpectrogram(signal), 1e-5)) -> [..., n_mels, frames] on the tdvc kernels (CUDA fp32 tensors)."""
     window, fb = _mel_operands(16000, n_fft, 80, signal.device)
@@ -91,17 +104,8 @@ def _log_mel(signal, n_fft):
     basis, nfreq, im_off = _dft_basis(n_fft, signal.device, split)
     frames = ops.stft_frames(x, window, n_fft, n_fft // 4, split=split)              # [(3*)n_fft, B*NF]
     spec = ops.conv1d(frames.unsqueeze(0), basis)                                    # [1, rows, B*NF]: re | im
-    power = ops.power_spectrum(spec.squeeze(0), nfreq, im_off)                       # [nfreq, B*NF]
-    if split:
-        # mel projection on the fp32 kernels: |X|^2 spans 8 decades and 80 x 1025 x 288 MACs are not worth a rounding
-        prec = ops.get_precision()
-        ops.set_precision("fp32")
-        try:
-            mel = ops.conv1d(power.unsqueeze(0), fb.t().contiguous().unsqueeze(2))
-        finally:
-            ops.set_precision(prec)
-    else:
-        mel = ops.conv1d(power.unsqueeze(0), fb.t().contiguous().unsqueeze(2))       # [1, n_mels, B*NF]
+    power = ops.power_spectrum(spec.squeeze(0), nfreq, im_off, split=split)          # [(3*)nfreq, B*NF]
+    mel = ops.conv1d(power.unsqueeze(0), _mel_weight(n_fft, signal.device, split))   # [1, n_mels, B*NF]
     logmel = ops.log_clamp(mel.squeeze(0), 1e-5)                                     # [n_mels, B*NF]
     nf = logmel.shape[1] // Bn
     return logmel.view(logmel.shape[0], Bn, nf).permute(1, 0, 2).reshape(lead + (logmel.shape[0], nf))
