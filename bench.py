@@ -278,7 +278,9 @@ def run_ours(args):
 
     out = None
     fams = None
-    if rank == 0 and args.graph:
+    if args.graph:
+        # every rank replays (the step holds collectives when N > 1: a rank-0-only replay would wait for its peers
+        # forever); rank 0's trace is the one reported
         try:
             fams = kernel_families(graphed.step, fam_gflop)
         except Exception as e:          # never lose the headline line to the trace
