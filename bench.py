@@ -191,8 +191,10 @@ def run_ours(args):
         oC = FusedAdamW(Cm.parameters(), TRAIN["lr"], (0.9, 0.999), weight_decay=0.0)     # torch.optim.Adam, train.py:192
     hook = GradAverager() if world > 1 else None
     ts = TrainStep(G, D, hp, oG, oD, nspk, grad_hook=hook, C=Cm, optimizer_C=oC)
-    if world > 1 and args.overlap:
-        # bucketed gradient all-reduce issued from autograd hooks, overlapped with the backward (captured into the graph)
+    if world > 1 and args.overlap and not args.graph:
+        # eager launches: bucketed gradient all-reduce issued from autograd hooks, overlapped with the backward.  Under
+        # CUDA-graph replay (the default) the all-reduces run between graph segments instead: capturing the hook-driven
+        # NCCL calls into the step graph deadlocked on this stack (torch 2.11 / NCCL 2.28.9, 2 x B200, measured).
         ts.enable_overlap(bucket_mb=args.bucket_mb)
     host = synth_batch(B, T, nspk, seed=1234 + rank)
     pinned = {k: v.pin_memory() for k, v in host.items()}
@@ -301,8 +303,9 @@ def run_ours(args):
                        "l2": "no explicit flush: one step streams >6 GB of activations, far larger than the 126 MB L2",
                        "parallelism": f"dp{world}", "step_gflop_algorithmic": step_gflop * world,
                        "grad_allreduce": ("none (1 GPU)" if world == 1 else
-                                          (f"bucketed ({args.bucket_mb} MB), overlapped with the backward, captured in the graph"
-                                           if args.overlap else "one flat all-reduce per network between graph segments")),
+                                          (f"bucketed ({args.bucket_mb} MB), issued from autograd hooks, overlapped with the backward"
+                                           if (args.overlap and not args.graph) else
+                                           "one flat all-reduce per network between CUDA-graph segments")),
                        "cuda_graph": bool(args.graph)},
             "clocks": clocks,
             "e2e": {"value": round(e2e, 3), "unit": UNIT, "h2d_bytes_per_step": h2d[0], "d2h_bytes_per_step": d2h[0],
@@ -631,8 +634,8 @@ def main():
                     help="bf16 = tcgen05 tensor-core path (2e-2 parity, the headline); fp32 = exact CUDA-core path (1e-5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--overlap", type=int, default=int(os.environ.get("TDVC_DP_OVERLAP", "1")),
-                    help="N > 1: 1 = bucketed gradient all-reduce overlapped with the backward (default), 0 = one flat "
-                         "all-reduce per network after its backward")
+                    help="N > 1 with --no-graph: 1 = bucketed gradient all-reduce overlapped with the backward, 0 = one "
+                         "flat all-reduce per network after its backward (what the CUDA-graph path always does)")
     ap.add_argument("--bucket-mb", type=float, default=16.0)
     ap.add_argument("--no-inference", action="store_true", help="skip the BASELINE config 5 inference sweep")
     ap.add_argument("--config", default="stage1", choices=sorted(CONFIGS),

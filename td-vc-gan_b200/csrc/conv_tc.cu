@@ -50,6 +50,10 @@ struct TcP {
   float* halo_buf;                            // EPI 6: contributions that fall on reflect-halo rows [grp][B][Cout][2*halo]
   int halo, t_valid;
   float pk_slope;                             // EPI 4: LeakyReLU slope of the packed copy
+  // weight-stationary kernel, groups with different tap counts: CTAs are dealt out in proportion to the taps (the k = 11
+  // branch gets 11/21 of them instead of a third); group g owns CTAs [grp_cta0[g], grp_cta0[g+1]) of a 1-D grid
+  int balanced;
+  int grp_cta0[5];
 };
 
 constexpr int TC_BM = 128;
@@ -445,8 +449,19 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) conv_tc_ws_k(const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int grp = blockIdx.y / p.tiles_per_group;
-  const int n0 = (blockIdx.y - grp * p.tiles_per_group) * p.BN;
+  int grp, n0, cta_i, cta_n;          // this CTA's group / N tile, and its position among the CTAs that share them
+  if (p.balanced) {
+    grp = 0;
+    while (grp < 3 && (int)blockIdx.x >= p.grp_cta0[grp + 1]) ++grp;
+    n0 = 0;
+    cta_i = (int)blockIdx.x - p.grp_cta0[grp];
+    cta_n = p.grp_cta0[grp + 1] - p.grp_cta0[grp];
+  } else {
+    grp = blockIdx.y / p.tiles_per_group;
+    n0 = (blockIdx.y - grp * p.tiles_per_group) * p.BN;
+    cta_i = blockIdx.x;
+    cta_n = gridDim.x;
+  }
   for (int i = threadIdx.x; i < p.BN; i += TC_FWD_THREADS)
     bias_s[i] = (p.bias && n0 + i < p.Cout) ? __ldg(p.bias + grp * p.bias_stride + n0 + i) : 0.f;
 
@@ -487,7 +502,7 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) conv_tc_ws_k(const __grid_c
           tma_load_3d(wsn + (size_t)tap * w.wn_tile_bytes, &map_bn, w_full, nfull * TC_BK, grp * p.coutp_g + n0, tap);
       }
       int it = 0, itn = 0;
-      for (int m = blockIdx.x; m < w.n_mtiles; m += gridDim.x) {
+      for (int m = cta_i; m < w.n_mtiles; m += cta_n) {
         const int b = m / w.mtiles_per_b, t0 = (m - b * w.mtiles_per_b) * TC_BM;
         for (int ck = 0; ck < nfull; ++ck, ++it) {
           const int s = it % p.stages;
@@ -524,7 +539,7 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) conv_tc_ws_k(const __grid_c
     const uint32_t tap_step16 = (uint32_t)p.dil * 8u;                    // dil rows x 128 B
     const uint32_t tapn_step16 = (uint32_t)p.dil * 2u;                   // dil rows x 32 B
     int it = 0, itn = 0, i = 0;
-    for (int m = blockIdx.x; m < w.n_mtiles; m += gridDim.x, ++i) {
+    for (int m = cta_i; m < w.n_mtiles; m += cta_n, ++i) {
       const int acc = i & 1;
       const uint32_t d_addr = tmem_base + (uint32_t)(acc * p.BN);
       mbar_wait(&tmem_empty[acc], ((uint32_t)(i >> 1) & 1u) ^ 1u);
@@ -579,7 +594,7 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) conv_tc_ws_k(const __grid_c
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     int i = 0;
-    for (int m = blockIdx.x; m < w.n_mtiles; m += gridDim.x, ++i) {
+    for (int m = cta_i; m < w.n_mtiles; m += cta_n, ++i) {
       const int b = m / w.mtiles_per_b, t0 = (m - b * w.mtiles_per_b) * TC_BM;
       const int acc = i & 1;
       mbar_wait(&tmem_full[acc], (uint32_t)(i >> 1) & 1u);
@@ -1582,6 +1597,22 @@ extern "C" int tdvc_conv1d_tc_fwd_ex(const tdvc_tc_conv* c, void* stream) {
       }
       dim3 grid(ctas, n_tiles_total, 1);
       TDVC_CHECK_ARG(grid.y <= 65535);
+      bool any_kg = false;
+      for (int g = 0; g < 4; ++g) any_kg = any_kg || c->kg[g] > 0;
+      if (any_kg && p.tiles_per_group == 1 && c->groups >= 2 && c->groups <= 4) {
+        // CTAs per group in proportion to its taps (its share of the MMAs), at least one each
+        int taps[4], tot = 0, total_ctas = std::min(num_sms(), c->groups * n_mtiles), used = 0;
+        for (int g = 0; g < c->groups; ++g) { taps[g] = c->kg[g] > 0 ? c->kg[g] : c->K; tot += taps[g]; }
+        p.balanced = 1;
+        p.grp_cta0[0] = 0;
+        for (int g = 0; g < c->groups; ++g) {
+          int n = std::max(1, std::min(n_mtiles, (int)((long long)total_ctas * taps[g] / tot)));
+          used += n;
+          p.grp_cta0[g + 1] = used;
+        }
+        for (int g = c->groups; g < 4; ++g) p.grp_cta0[g + 1] = used;
+        grid = dim3(used, 1, 1);
+      }
       tdvc::launch_k(kern, grid, TC_FWD_THREADS, smem_ws, (cudaStream_t)stream, map_a, map_b, map_an, map_bn, p, w);
       TDVC_LAUNCH_CHECK();
       g_flops[chain ? FLOP_TC_CHAIN : FLOP_TC_WS] += 2.0 * c->B * c->Tout * (double)c->Cout_g * c->Cinp_g * tc_taps(c);

@@ -144,6 +144,17 @@ __global__ void __launch_bounds__(W2_THREADS) conv_tc_wgrad2_k(const __grid_cons
       // D = f32, A = B = bf16, both MN-major (bits 15, 16), N = NT, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                              ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      // descriptor constants (units of 16 bytes).  A: x tile, rows of p.sw bytes; LBO = next M atom (tm > 1: dil rows below,
+      // else the second 64-channel box), SBO = 8 rows.  B: dy tile, SWIZZLE_128B, LBO = next 64-channel box.
+      const uint32_t row_b = (uint32_t)p.sw;
+      const uint32_t layout = p.sw == 128 ? 2u : (p.sw == 64 ? 4u : 6u);
+      const uint32_t lbo = p.tm > 1 ? (uint32_t)p.dil * row_b : (uint32_t)x_box;
+      const uint32_t a_lo_flags = ((lbo >> 4) & 0x3FFFu) << 16;
+      const uint32_t a_hi = ((8u * row_b) >> 4) | (1u << 14) | (layout << 29);
+      const uint32_t b_lo_flags = (((uint32_t)W2_BOX >> 4) & 0x3FFFu) << 16;
+      const uint32_t b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t a_k16 = (16u * row_b) >> 4;                                   // 16 rows further down
+      const uint32_t a_tb16 = p.haloed ? ((uint32_t)(p.tm * p.dil) * row_b) >> 4 : (uint32_t)(2 * x_box) >> 4;
       for (int it = 0; it < my_units; ++it) {
         const int s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
@@ -151,27 +162,32 @@ __global__ void __launch_bounds__(W2_THREADS) conv_tc_wgrad2_k(const __grid_cons
         tc_fence_after();
         if (elect_one()) {
           const uint32_t s_addr = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint32_t b_addr = s_addr + x_bytes;
           // one accumulator per tap block (tm taps; tm = 1: per tap).  haloed: block tb = the tile moved down by tb*tm*dil
           // rows and, inside the instruction, M atom a = the tile moved down by a further a*dil rows (LBO = dil rows).
-          const uint32_t row_b = (uint32_t)p.sw;                           // bytes per x row
-          const uint32_t layout = p.sw == 128 ? 2u : (p.sw == 64 ? 4u : 6u);
-          const uint32_t lbo = p.tm > 1 ? (uint32_t)p.dil * row_b : (uint32_t)x_box;
+          // The single issuing thread is the bottleneck of these small MMAs (a descriptor built from scratch costs ~100
+          // cycles of dependent integer work per instruction): the high descriptor words are constants and the low
+          // words advance by 32-bit adds.
+          const uint32_t sa16 = (s_addr & 0x3FFFFu) >> 4;
+          const uint32_t sb16 = sa16 + (uint32_t)(x_bytes >> 4);
+          uint32_t a_blk = a_lo_flags + sa16;
           for (int tb = 0; tb < nacc; ++tb) {
-            const uint32_t a_addr = p.haloed ? s_addr + (uint32_t)(tb * p.tm * p.dil) * row_b : s_addr + (uint32_t)(tb * 2 * x_box);
+            const uint32_t d_addr = tmem_base + (uint32_t)(tb * p.NT);
+            uint32_t a_lo = a_blk, b_lo = b_lo_flags + sb16;
+#pragma unroll
             for (int k = 0; k < W2_TK / 16; ++k) {      // 16 time rows per MMA
-              const uint64_t da = make_mnmajor_desc(a_addr + (uint32_t)k * 16u * row_b, lbo, 8u * row_b, layout);
-              const uint64_t db = make_sw128_mnmajor_desc(b_addr + k * 2048, W2_BOX);
-              umma_bf16(tmem_base + (uint32_t)(tb * p.NT), da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+              umma_bf16_lohi(d_addr, a_lo, a_hi, b_lo, b_hi, idesc, (it > 0 || k > 0) ? 1u : 0u);
+              a_lo += a_k16;
+              b_lo += 2048u >> 4;
             }
+            a_blk += a_tb16;
           }
           if (do_bias) {
-            const uint32_t o_addr = smem_u32(ones);
-            for (int k = 0; k < W2_TK / 16; ++k) {
-              const uint64_t da = make_sw128_mnmajor_desc(o_addr + k * 2048, W2_BOX);
-              const uint64_t db = make_sw128_mnmajor_desc(b_addr + k * 2048, W2_BOX);
-              umma_bf16(tmem_base + (uint32_t)(p.nacc_max * p.NT), da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
-            }
+            const uint32_t o16 = (smem_u32(ones) & 0x3FFFFu) >> 4;
+            const uint32_t d_addr = tmem_base + (uint32_t)(p.nacc_max * p.NT);
+#pragma unroll
+            for (int k = 0; k < W2_TK / 16; ++k)
+              umma_bf16_lohi(d_addr, b_lo_flags + o16 + (uint32_t)k * 128u, b_hi, b_lo_flags + sb16 + (uint32_t)k * 128u, b_hi, idesc,
+                             (it > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);
           if (it == my_units - 1) umma_commit(tmem_full_bar);

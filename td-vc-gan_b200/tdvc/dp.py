@@ -64,8 +64,9 @@ class BucketedReducer:
     stream, so it runs while the rest of the backward still computes.  `finish()` flushes the buckets a backward did not
     complete (parameters without gradient count as zeros) and waits for every outstanding collective.
 
-    Inside a CUDA-graph capture the collectives are captured with the compute (NCCL supports stream capture): the graph
-    then holds the all-reduce nodes on a parallel branch, and a replay overlaps them exactly as the eager run does."""
+    For eager steps.  Capturing these hook-driven collectives into the CUDA graph of the whole step was tried and never
+    returned on 2 x B200 (torch 2.11 / NCCL 2.28.9); GraphedTrainStep therefore keeps the all-reduces between graph
+    segments (tdvc/train_step.py)."""
 
     def __init__(self, opt, group: Optional[dist.ProcessGroup] = None, bucket_mb: float = 16.0):
         if getattr(opt, "_banks", None) is None:

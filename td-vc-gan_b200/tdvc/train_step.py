@@ -375,6 +375,11 @@ class GraphedTrainStep:
 
     def __init__(self, ts: TrainStep, example_batch: dict, warmup: int = 3):
         self.ts = ts
+        if ts.reducers and getattr(ts.grad_hook, "world", 1) > 1:
+            # measured on 2 x B200 (torch 2.11, NCCL 2.28.9): capturing the hook-driven asynchronous all-reduces into the
+            # step graph never returns.  The graph path cuts the iteration at the all-reduces instead (below).
+            raise RuntimeError("GraphedTrainStep: the hook-driven gradient all-reduce (TrainStep.enable_overlap) is for eager "
+                               "steps; under CUDA graphs the all-reduces run between graph segments")
         self.with_c = ts.C is not None and ts.hp.get("lambda_latcls", 0) != 0
         opts = [ts.opt_G, ts.opt_D] + ([ts.opt_C] if self.with_c else [])
         for opt in opts:
@@ -383,9 +388,8 @@ class GraphedTrainStep:
                                    "lambda_latcls != 0, for C")
             opt.use_grad_bank()
         self.static = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in example_batch.items()}
-        # gradient all-reduces issued eagerly BETWEEN graph segments (split) -- or, with ts.enable_overlap(), captured inside
-        # one graph on the communication stream, overlapped with the backward
-        self.split = ts.grad_hook is not None and getattr(ts.grad_hook, "world", 1) > 1 and not ts.reducers
+        # data parallel: the iteration is cut at the gradient all-reduces, which are issued eagerly between the segments
+        self.split = ts.grad_hook is not None and getattr(ts.grad_hook, "world", 1) > 1
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
