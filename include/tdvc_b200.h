@@ -305,6 +305,8 @@ typedef struct tdvc_tc_wgrad2 {
   int32_t want_bias, ws_is_zero;
   int32_t haloed;      /* -1 default; 1: one haloed x tile per time unit, taps = row-shifted views; 0: one copy per tap */
   int32_t tapsm;       /* -1 default (on when Cin is 16, 32 or 64); 0: channels only on the M lanes; 1: 128 / Cin taps per MMA */
+  int32_t swap;        /* -1 default (operand roles swapped, M = co / N = ci, when 128 < Cin <= 256 and all taps fit TMEM:
+                          the FiLM conditioning convs); 0: never */
   int32_t frame_s, kreal, cin_conv_g, sub;
 } tdvc_tc_wgrad2;
 int64_t tdvc_conv1d_tc_wgrad2_ws(const tdvc_tc_wgrad2* c);

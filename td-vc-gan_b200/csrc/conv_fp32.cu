@@ -537,6 +537,62 @@ __global__ void channel_sum_k(const float* __restrict__ dy, float* __restrict__ 
   if (threadIdx.x == 0) atomicAdd(db + c, s);
 }
 
+// Weight (and bias) gradient of a 1-input-channel stride-1 conv -- the waveform stems: discriminator.0.0 (1 -> 16, k15,
+// reflect), encoder.0 and excite_downsample.4 (1 -> 16 / 8, k7, reflect).  dw[co][k] = sum_{b,t} dy[b,co,t] * xpad[b, t + k*dil - pad].
+// A CTA takes one (batch, 1024-step chunk): the padded input chunk and 256-step tiles of dy are staged in shared memory,
+// thread p owns the pair (co, k) = (p / K, p % K) -- the 15 taps of a channel read consecutive shared-memory words, the dy
+// value is a broadcast -- and adds its partial sum with one atomic.  The general kernel above spends 160 us on the
+// discriminator stem at B = 32 (a few CTAs walk the whole tensor); this one reads dy once at full rate.
+constexpr int STEM_TT = 1024, STEM_SUB = 256;
+
+__global__ void __launch_bounds__(256) stem_wgrad_k(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dw,
+                                                     float* __restrict__ db, int Cout, int T, int K, int dil, int pad, int pad_mode,
+                                                     float in_slope) {
+  pdl_prologue();
+  extern __shared__ float sm[];
+  const int span = STEM_TT + (K - 1) * dil;
+  float* xs = sm;                              // [span]
+  float* dys = sm + ((span + 3) & ~3);         // [Cout][STEM_SUB + 1]
+  const int b = blockIdx.y, t0 = blockIdx.x * STEM_TT;
+  const float* xrow = x + (long long)b * T;
+  for (int i = threadIdx.x; i < span; i += 256) xs[i] = fetch_padded(xrow, t0 + i - pad, T, pad_mode, in_slope);
+  const int npairs = Cout * K;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};         // pairs p, p + 256, ... (Cout * K <= 1024)
+  float bsum = 0.f;                            // threads < Cout: bias gradient of channel threadIdx.x
+  const int tend = min(STEM_TT, T - t0);
+  for (int s0 = 0; s0 < tend; s0 += STEM_SUB) {
+    const int ns = min(STEM_SUB, tend - s0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < Cout * STEM_SUB; i += 256) {
+      const int co = i / STEM_SUB, t = i - co * STEM_SUB;
+      dys[co * (STEM_SUB + 1) + t] = t < ns ? __ldg(dy + ((long long)b * Cout + co) * T + t0 + s0 + t) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int pidx = threadIdx.x + 256 * q;
+      if (pidx < npairs) {
+        const int co = pidx / K, k = pidx - co * K;
+        const float* dr = dys + co * (STEM_SUB + 1);
+        const float* xr = xs + s0 + k * dil;
+        float a = acc[q];
+        for (int t = 0; t < ns; ++t) a = fmaf(dr[t], xr[t], a);
+        acc[q] = a;
+      }
+    }
+    if (db && threadIdx.x < Cout) {
+      const float* dr = dys + threadIdx.x * (STEM_SUB + 1);
+      for (int t = 0; t < ns; ++t) bsum += dr[t];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int pidx = threadIdx.x + 256 * q;
+    if (pidx < npairs) atomicAdd(dw + pidx, acc[q]);
+  }
+  if (db && threadIdx.x < Cout) atomicAdd(db + threadIdx.x, bsum);
+}
+
 static int launch_channel_sum(const float* dy, float* db, int B, int C, int T, cudaStream_t st) {
   TDVC_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * C, st));
   if (B == 0) return TDVC_OK;
@@ -634,6 +690,22 @@ extern "C" int tdvc_conv1d_bwd_weight(const tdvc_conv_geom* g, const float* dy, 
   if (rc) return rc;
   TDVC_CHECK_ARG(dy && x && dw);
   cudaStream_t st = (cudaStream_t)stream;
+  if (g->Cin == 1 && g->groups == 1 && g->stride == 1 && g->Cout * g->K <= 1024 && g->Cout <= 256 && g->Tout == g->Tin) {
+    // the waveform stems
+    TDVC_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)g->Cout * g->K, st));
+    if (dbias) TDVC_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * (size_t)g->Cout, st));
+    if (g->B == 0) return TDVC_OK;
+    const int span = STEM_TT + (g->K - 1) * g->dilation;
+    const size_t smem = (size_t)(((span + 3) & ~3) + g->Cout * (STEM_SUB + 1)) * sizeof(float);
+    if (smem <= 200 * 1024) {
+      if (smem > 48 * 1024) TDVC_CUDA(cudaFuncSetAttribute(stem_wgrad_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      tdvc::launch_k(stem_wgrad_k, dim3(cdiv(g->Tout, STEM_TT), g->B), 256, smem, st, dy, x, dw, dbias, g->Cout, g->Tin, g->K,
+                     g->dilation, g->pad, g->pad_mode, g->in_slope);
+      TDVC_LAUNCH_CHECK();
+      g_flops[FLOP_FP32] += 2.0 * g->B * g->Tout * (double)g->Cout * g->K;
+      return TDVC_OK;
+    }
+  }
   WgP p{};
   p.B = g->B; p.Ca = g->Cout; p.Ta = g->Tout; p.Cb = g->Cin; p.Tb = g->Tin; p.K = g->K;
   p.stride = g->stride; p.pad = g->pad; p.dil = g->dilation; p.groups = g->groups;

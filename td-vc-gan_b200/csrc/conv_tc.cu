@@ -1599,7 +1599,10 @@ extern "C" int tdvc_conv1d_tc_fwd_ex(const tdvc_tc_conv* c, void* stream) {
       TDVC_CHECK_ARG(grid.y <= 65535);
       bool any_kg = false;
       for (int g = 0; g < 4; ++g) any_kg = any_kg || c->kg[g] > 0;
-      if (any_kg && p.tiles_per_group == 1 && c->groups >= 2 && c->groups <= 4) {
+      static int balance = -1;     // TDVC_TC_BALANCE=1 (off by default: measured 2x SLOWER on the MRF chain launches -- a tile's
+                                   // cost there is its epilogue, the same for every branch, not its 3 / 7 / 11 MMAs)
+      if (balance < 0) { const char* e = getenv("TDVC_TC_BALANCE"); balance = e ? atoi(e) : 0; }
+      if (balance && any_kg && p.tiles_per_group == 1 && c->groups >= 2 && c->groups <= 4) {
         // CTAs per group in proportion to its taps (its share of the MMAs), at least one each
         int taps[4], tot = 0, total_ctas = std::min(num_sms(), c->groups * n_mtiles), used = 0;
         for (int g = 0; g < c->groups; ++g) { taps[g] = c->kg[g] > 0 ? c->kg[g] : c->K; tot += taps[g]; }

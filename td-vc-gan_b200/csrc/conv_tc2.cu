@@ -255,6 +255,183 @@ __global__ void __launch_bounds__(W2_THREADS) conv_tc_wgrad2_k(const __grid_cons
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+// The same GEMM with the operand roles swapped, for convolutions whose INPUT width is just over one 128-lane M tile
+// (the FiLM conditioning convs: 136 / 137 channels -- a second M tile would carry 8 or 9 real channels and double the
+// MMAs): M = co (dy tile, plain), N = ci <= 256 (haloed x tile; the taps are row-shifted views of the B operand), one
+// accumulator of N columns per tap, bias gradient = one more 16-column accumulator against a tile of ones on the B side.
+// Workspace layout [g][tap][ci][co] (a TMEM lane is a co: a warp's reduction covers 32 consecutive floats).
+struct Wg2sP {
+  int B, Tout, Cout, Cin, K, dil, t_off;
+  int ngroups, x_ch_off, x_ch_stride, dy_ch_off, dy_ch_stride;
+  int NT, nb_x, rows_x, stages, tmem_cols, nchunk_t, units, splits;
+  int CinP, CoutP;
+  long long ws_grp_stride;
+  float* ws;
+  int bias;
+};
+
+__global__ void __launch_bounds__(W2_THREADS) conv_tc_wgrad2s_k(const __grid_constant__ CUtensorMap map_x,
+                                                                const __grid_constant__ CUtensorMap map_dy, Wg2sP p) {
+  pdl_prologue();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int x_box = p.rows_x * 128;
+  const int x_bytes = p.nb_x * x_box;
+  const int dy_bytes = 2 * W2_BOX;                                   // 128 co = two 64-channel boxes of 64 rows
+  const int stage_bytes = dy_bytes + x_bytes;
+  uint8_t* ones = smem + (size_t)p.stages * stage_bytes;             // 64 rows x 64 channels of 1.0, when p.bias
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ones + (p.bias ? W2_BOX : 0));
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tmem_full_bar = empty_bar + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.z;
+  const int co0 = blockIdx.y * 128;
+  const int split = blockIdx.x;
+  const int my_units = (p.units - split + p.splits - 1) / p.splits;
+  const int xc = p.x_ch_off + g * p.x_ch_stride;
+  const int dc = p.dy_ch_off + g * p.dy_ch_stride + co0;
+  const int nba = min(2, (p.Cout - co0 + 63) / 64);
+  if (p.bias) {
+    uint32_t* o32 = reinterpret_cast<uint32_t*>(ones);
+    for (int i = threadIdx.x; i < W2_BOX / 4; i += W2_THREADS) o32[i] = 0x3F803F80u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dy) : "memory");
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (my_units > 0) {
+    if (warp == 0) {
+      if (elect_one()) {
+        const uint32_t tx = (uint32_t)(nba * W2_BOX + x_bytes);
+        for (int it = 0; it < my_units; ++it) {
+          const int u = split + it * p.splits;
+          const int b = u / p.nchunk_t, tc = (u - b * p.nchunk_t) * W2_TK;
+          const int s = it % p.stages;
+          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* sa = smem + (size_t)s * stage_bytes;
+          mbar_expect_tx(&full_bar[s], tx);
+          for (int j = 0; j < nba; ++j) tma_load_3d(sa + j * W2_BOX, &map_dy, &full_bar[s], dc + 64 * j, tc, b);
+          for (int j = 0; j < p.nb_x; ++j) tma_load_3d(sa + dy_bytes + j * x_box, &map_x, &full_bar[s], xc + 64 * j, tc + p.t_off, b);
+        }
+      }
+    } else if (warp == 1) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t idesc_b = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                               ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);                      // SBO = 8 rows, SWIZZLE_128B
+      const uint32_t a_flags = (((uint32_t)W2_BOX >> 4) & 0x3FFFu) << 16;             // LBO: next 64 co
+      const uint32_t b_flags = (((uint32_t)x_box >> 4) & 0x3FFFu) << 16;              // LBO: next 64 ci
+      const uint32_t tap16 = ((uint32_t)p.dil * 128u) >> 4;
+      for (int it = 0; it < my_units; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa16 = (smem_u32(smem + (size_t)s * stage_bytes) & 0x3FFFFu) >> 4;
+          const uint32_t sb16 = sa16 + (uint32_t)(dy_bytes >> 4);
+          uint32_t b_tap = b_flags + sb16;
+          for (int tap = 0; tap < p.K; ++tap) {
+            const uint32_t d_addr = tmem_base + (uint32_t)(tap * p.NT);
+            uint32_t a_lo = a_flags + sa16, b_lo = b_tap;
+#pragma unroll
+            for (int k = 0; k < W2_TK / 16; ++k) {
+              umma_bf16_lohi(d_addr, a_lo, hi, b_lo, hi, idesc, (it > 0 || k > 0) ? 1u : 0u);
+              a_lo += 128u;
+              b_lo += 128u;
+            }
+            b_tap += tap16;
+          }
+          if (p.bias) {
+            const uint32_t o16 = (smem_u32(ones) & 0x3FFFFu) >> 4;
+            const uint32_t d_addr = tmem_base + (uint32_t)(p.K * p.NT);
+#pragma unroll
+            for (int k = 0; k < W2_TK / 16; ++k)
+              umma_bf16_lohi(d_addr, a_flags + sa16 + (uint32_t)k * 128u, hi, a_flags + o16 + (uint32_t)k * 128u, hi, idesc_b,
+                             (it > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+          if (it == my_units - 1) umma_commit(tmem_full_bar);
+        }
+        __syncwarp();
+      }
+    } else {
+      const int q = warp & 3;
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+      const int co = co0 + q * 32 + lane;
+      const bool row_ok = co < p.Cout;
+      float* wsg = p.ws + (long long)g * p.ws_grp_stride;
+      if (co0 + q * 32 < p.Cout) {
+        for (int tap = 0; tap < p.K; ++tap) {
+          float* wrow = wsg + (long long)tap * p.CinP * p.CoutP + co;
+          for (int c0 = 0; c0 < p.Cin; c0 += 16) {
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tap * p.NT + c0), v);
+            if (row_ok) {
+              const int nj = min(16, p.Cin - c0);
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < nj) atomicAdd(wrow + (long long)(c0 + j) * p.CoutP, v[j]);
+            }
+          }
+        }
+        if (p.bias) {
+          float v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.K * p.NT), v);
+          if (row_ok) atomicAdd(wsg + (long long)p.K * p.CinP * p.CoutP + co, v[0]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// swapped workspace [g][tap][ci][co] (+ bias row [co]) -> dw[g][co][ci][tap]; re-zeroes what it read
+__global__ void wgrad2s_finalize_k(float* __restrict__ ws, long long ws_grp_stride, int Cout, int Cin, int K, int CinP, int CoutP,
+                                   float* __restrict__ dw, long long dw_grp_stride, float* __restrict__ db, long long db_grp_stride,
+                                   int bias) {
+  pdl_prologue();
+  const int g = blockIdx.y;
+  float* wsg = ws + (long long)g * ws_grp_stride;
+  const long long n = (long long)K * Cin * Cout;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cout);
+    const long long r = i / Cout;
+    const int ci = (int)(r % Cin), tap = (int)(r / Cin);
+    float* src = wsg + ((long long)tap * CinP + ci) * CoutP + co;
+    const float v = *src;
+    *src = 0.f;
+    if (dw) dw[(long long)g * dw_grp_stride + ((long long)co * Cin + ci) * K + tap] = v;
+  }
+  if (bias && blockIdx.x == 0) {
+    float* brow = wsg + (long long)K * CinP * CoutP;
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) {
+      if (db) db[(long long)g * db_grp_stride + i] = brow[i];
+      brow[i] = 0.f;
+    }
+  }
+}
+
 // ws[g][tap][co][ci] (+ bias row) -> the weight-gradient tensors; what is read is written back as zero, so a persistent
 // workspace needs no memset per call.
 struct Fin2P {
@@ -489,10 +666,70 @@ extern "C" int tdvc_frame_unpack(const float* dxf, float* dx, int B, int C, int 
   return TDVC_OK;
 }
 
+// operand roles swapped (M = co, N = ci): the input width is just over one 128-lane tile and fits one N tile with all taps
+static bool wgrad2_swapped(const tdvc_tc_wgrad2* c) {
+  static int on = -1;        // TDVC_WGRAD2_SWAP=0: never (development / A-B switch)
+  if (on < 0) { const char* e = getenv("TDVC_WGRAD2_SWAP"); on = e ? atoi(e) : 1; }
+  const int nt = ((c->Cin + 15) / 16) * 16;
+  return on && c->swap != 0 && !c->per_group && c->frame_s == 0 && c->Cin > 128 && c->Cin <= 256 && c->K * nt + 16 <= 512 &&
+         64 + (c->K - 1) * c->dilation <= 256;
+}
+
 extern "C" int64_t tdvc_conv1d_tc_wgrad2_ws(const tdvc_tc_wgrad2* c) {
   if (!c) return 0;
+  if (wgrad2_swapped(c)) {
+    const long long CinP = ((c->Cin + 15) / 16) * 16, CoutP = (long long)((c->Cout + 31) / 32) * 32;
+    return (int64_t)c->ngroups * ((long long)c->K * CinP * CoutP + CoutP);
+  }
   const long long Mp = (long long)((c->Cin + 31) / 32) * 32, Np = (long long)((c->Cout + 15) / 16) * 16;
   return (int64_t)c->ngroups * ((long long)c->K * Np * Mp + Np);
+}
+
+static int wgrad2_launch_swapped(const tdvc_tc_wgrad2* c, cudaStream_t st) {
+  Wg2sP p{};
+  p.B = c->B; p.Tout = c->Tout; p.Cout = c->Cout; p.Cin = c->Cin; p.K = c->K; p.dil = c->dilation; p.t_off = c->t_off[0];
+  p.ngroups = c->ngroups; p.x_ch_off = c->x_ch_off; p.x_ch_stride = c->x_ch_stride; p.dy_ch_off = c->dy_ch_off;
+  p.dy_ch_stride = c->dy_ch_stride;
+  p.NT = ((c->Cin + 15) / 16) * 16;
+  p.nb_x = cdiv(p.NT, 64);
+  p.rows_x = ((W2_TK + (c->K - 1) * c->dilation + 7) / 8) * 8;
+  p.CinP = p.NT; p.CoutP = ((c->Cout + 31) / 32) * 32;
+  p.ws = c->ws; p.ws_grp_stride = (long long)c->K * p.CinP * p.CoutP + p.CoutP;
+  p.bias = c->want_bias ? 1 : 0;
+  if (!c->ws_is_zero) TDVC_CUDA(cudaMemsetAsync(c->ws, 0, sizeof(float) * (size_t)c->ngroups * (size_t)p.ws_grp_stride, st));
+  int cols = 32;
+  while (cols < c->K * p.NT + (p.bias ? 16 : 0)) cols <<= 1;
+  p.tmem_cols = cols;
+  const long long stage_bytes = 2LL * W2_BOX + (long long)p.nb_x * p.rows_x * 128;
+  p.nchunk_t = cdiv(c->Tout, W2_TK);
+  p.units = c->B * p.nchunk_t;
+  int stages = (int)std::min<long long>(4, (200LL * 1024) / stage_bytes);
+  TDVC_CHECK_ARG(stages >= 1);
+  p.stages = std::min(stages, std::max(1, p.units));
+  const int m_tiles = cdiv(c->Cout, 128);
+  if (c->B > 0) {
+    const long long ctas_fixed = (long long)m_tiles * c->ngroups;
+    int splits = (int)std::max<long long>(1, (2LL * num_sms() + ctas_fixed - 1) / ctas_fixed);
+    splits = std::min(splits, std::max(1, p.units / 4));
+    p.splits = std::max(1, std::min(splits, p.units));
+    const size_t smem = (size_t)p.stages * stage_bytes + (p.bias ? W2_BOX : 0) + (2 * p.stages + 1) * sizeof(uint64_t) + 16 + 1024;
+    TDVC_CUDA(cudaFuncSetAttribute(conv_tc_wgrad2s_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUtensorMap map_x, map_dy;
+    int rc = make_map_3d(&map_x, c->xp, (uint64_t)c->Cp, (uint64_t)c->Tp, (uint64_t)c->B, 64, (uint32_t)p.rows_x);
+    if (rc) return rc;
+    rc = make_map_3d(&map_dy, c->dyp, (uint64_t)c->Cdp, (uint64_t)c->Tout, (uint64_t)c->B, 64, W2_TK);
+    if (rc) return rc;
+    TDVC_CHECK_ARG(m_tiles <= 65535);
+    tdvc::launch_k(conv_tc_wgrad2s_k, dim3(p.splits, m_tiles, c->ngroups), W2_THREADS, smem, st, map_x, map_dy, p);
+    TDVC_LAUNCH_CHECK();
+    g_flops[FLOP_TC_WGRAD] += 2.0 * c->B * c->Tout * (double)c->Cout * c->Cin * c->K * c->ngroups;
+  }
+  const long long n = (long long)c->K * c->Cout * c->Cin;
+  const int bx = (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, std::max(1, 4 * num_sms() / c->ngroups)));
+  tdvc::launch_k(wgrad2s_finalize_k, dim3(bx, c->ngroups), 256, 0, st, c->ws, p.ws_grp_stride, c->Cout, c->Cin, c->K, p.CinP, p.CoutP,
+                 c->dw[0], (long long)c->dw_grp_stride, c->db[0], (long long)c->db_grp_stride, p.bias);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
 }
 
 extern "C" int tdvc_conv1d_tc_wgrad2(const tdvc_tc_wgrad2* c, void* stream) {
@@ -512,6 +749,7 @@ extern "C" int tdvc_conv1d_tc_wgrad2(const tdvc_tc_wgrad2* c, void* stream) {
                    (c->Cin / c->sub) == c->cin_conv_g * c->frame_s && c->kreal >= 1 && c->kreal <= c->K * c->frame_s);
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (wgrad2_swapped(c)) return wgrad2_launch_swapped(c, st);
   Wg2P p{};
   p.B = c->B; p.Tout = c->Tout; p.Cout = c->Cout; p.Cin = c->Cin; p.K = c->K; p.dil = c->dilation;
   p.ngroups = c->ngroups; p.per_group = per_group ? 1 : 0;

@@ -53,7 +53,7 @@ class TcWgrad2(C.Structure):
                [(n, C.c_int32) for n in ("B", "Cdp", "Tout", "Cp", "Tp", "Cout", "Cin", "K", "dilation", "ngroups", "per_group",
                                          "x_ch_off", "x_ch_stride", "dy_ch_off", "dy_ch_stride")] + \
                [("kg", C.c_int32 * 4), ("t_off", C.c_int32 * 4)] + \
-               [(n, C.c_int32) for n in ("want_bias", "ws_is_zero", "haloed", "tapsm", "frame_s", "kreal", "cin_conv_g", "sub")]
+               [(n, C.c_int32) for n in ("want_bias", "ws_is_zero", "haloed", "tapsm", "swap", "frame_s", "kreal", "cin_conv_g", "sub")]
 
 
 PAD_ZEROS, PAD_REFLECT = 0, 1

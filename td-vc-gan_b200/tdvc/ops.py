@@ -1506,7 +1506,7 @@ class _GroupedFrameConvTC(torch.autograd.Function):
 
 def wgrad2(*, dyp, xp, B, Cdp, Tout, Cp, Tp, Cout, Cin, K, dilation, ngroups=1, per_group=False, x_ch_off=0, x_ch_stride=0,
            dy_ch_off=0, dy_ch_stride=0, kg=None, t_off=(0,), dw=(None,), db=(None,), dw_grp_stride=0, db_grp_stride=0,
-           frame_s=0, kreal=0, cin_conv_g=0, sub=1, haloed=-1, tapsm=-1):
+           frame_s=0, kreal=0, cin_conv_g=0, sub=1, haloed=-1, tapsm=-1, swap=-1):
     """tdvc_conv1d_tc_wgrad2 (include/tdvc_b200.h) on the persistent always-zero workspace."""
     lib = _lib.load()
     c = _lib.TcWgrad2()
@@ -1521,7 +1521,7 @@ def wgrad2(*, dyp, xp, B, Cdp, Tout, Cp, Tp, Cout, Cin, K, dilation, ngroups=1, 
     c.ngroups, c.per_group = ngroups, int(bool(per_group))
     c.x_ch_off, c.x_ch_stride, c.dy_ch_off, c.dy_ch_stride = x_ch_off, x_ch_stride, dy_ch_off, dy_ch_stride
     c.want_bias = int(any(b is not None for b in db))
-    c.haloed, c.tapsm = haloed, tapsm
+    c.haloed, c.tapsm, c.swap = haloed, tapsm, swap
     c.frame_s, c.kreal, c.cin_conv_g, c.sub = frame_s, kreal, cin_conv_g, sub
     ws, wz = _wgrad_ws(int(lib.tdvc_conv1d_tc_wgrad2_ws(C.byref(c))), dyp.device)
     c.ws, c.ws_is_zero = ws.data_ptr(), wz

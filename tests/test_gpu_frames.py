@@ -165,3 +165,40 @@ def test_latent_classifier_bf16_vs_golden():
     # held at 1e-2 without an activation in test_gpu_tc.py::test_strided_conv_as_frames): relative L2 of dL/dx within 1e-1
     ref = torch.as_tensor(np.asarray(g["dx"])).double()
     assert float((x.grad.double().cpu() - ref).norm() / ref.norm()) < 1e-1
+
+
+WG2U = [
+    # B, T, groups, Cin, x pitch, Cout, dy pitch, K, dil, swap
+    (2, 333, 9, 136, 144, 32, 32, 3, 1, -1),      # the 9 cond_var.2 blocks of a stage: operand roles swapped (M = co)
+    (2, 333, 9, 136, 144, 32, 32, 3, 1, 0),       # the same through the channels-on-M form (two M tiles, 8 real lanes in the second)
+    (1, 700, 1, 137, 144, 1296, 1296, 3, 1, -1),  # the stacked cond_var.0 gradient (+ the constant-one channel): 11 M tiles of co
+    (2, 70, 3, 200, 208, 48, 64, 5, 2, -1),       # another width / dilation, T barely over one time unit
+]
+
+
+@pytest.mark.parametrize("case", WG2U, ids=[str(i) for i in range(len(WG2U))])
+def test_wgrad2_uniform_groups_and_swapped_operands(case):
+    """conv_tc_wgrad2(s)_k on uniform groups with zero 'same' padding through TMA out-of-bounds fill (t_off = -pad), incl. the
+    operand-swapped form used when the input width is just over one 128-lane tile."""
+    from tdvc import ops
+    B, T, G, Cin, xpitch, Cout, dpitch, K, dil, swap = case
+    pad = dil * (K - 1) // 2
+    x = rnd(B, G * xpitch, T, seed=1)
+    dy = rnd(B, G * dpitch, T, seed=2)
+    xp = x.float().cuda().transpose(1, 2).contiguous().to(torch.bfloat16)
+    dyp = dy.float().cuda().transpose(1, 2).contiguous().to(torch.bfloat16)
+    dw = torch.full((G, Cout, Cin, K), float("nan"), device="cuda")
+    db = torch.full((G, Cout), float("nan"), device="cuda")
+    ops.wgrad2(dyp=dyp, xp=xp, B=B, Cdp=G * dpitch, Tout=T, Cp=G * xpitch, Tp=T, Cout=Cout, Cin=Cin, K=K, dilation=dil, ngroups=G,
+               x_ch_stride=xpitch, dy_ch_stride=dpitch, t_off=[-pad], dw=[dw], db=[db], dw_grp_stride=Cout * Cin * K,
+               db_grp_stride=Cout, swap=swap)
+    torch.cuda.synchronize()
+    xb = F.pad(xp.double().cpu().transpose(1, 2), (pad, pad))
+    dyb = dyp.double().cpu().transpose(1, 2)
+    for g in range(G):
+        xg = xb[:, g * xpitch:g * xpitch + Cin]
+        dg = dyb[:, g * dpitch:g * dpitch + Cout]
+        ref = torch.stack([torch.einsum("bot,bit->oi", dg, xg[:, :, tap * dil: tap * dil + T]) for tap in range(K)], 2)
+        assert relerr(dw[g], ref) < 2e-3, g
+        assert relerr(db[g], dg.sum(dim=(0, 2))) < 2e-3, g
+    assert float(ops._WGRAD_WS[dyp.device].abs().max()) == 0.0
