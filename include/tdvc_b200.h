@@ -64,6 +64,10 @@ int tdvc_weight_norm_bwd(const float* dw, const float* v, const float* g, const 
  * row_start = device int32[n_weights + 1], first global row of each weight; inv norms go to flat_inv[global row]. */
 int tdvc_weight_norm_fwd_multi(const void* table, const void* row_start, int n_weights, int total_rows,
                                float* flat_w, float* flat_inv, void* stream);
+/* the backward for MANY weights in one launch: table = device int64[n_weights][6] {v pointer, g pointer, offset of dw_j in
+ * flat_dw, offset of dv_j in flat_dv, first row of dg_j in flat_dg, cols}; 1/||v|| is recomputed from v. */
+int tdvc_weight_norm_bwd_multi(const void* table, const void* row_start, int n_weights, int total_rows,
+                               const float* flat_dw, float* flat_dv, float* flat_dg, void* stream);
 
 /* ---- Conv1d (model/generator.py:75-92,146-156,214-249,299-347; model/discriminator.py:17-38;
  *      depthwise Kaiser FIR F.conv1d at model/generator.py:165-168, model/discriminator.py:100-102).

@@ -79,6 +79,43 @@ __global__ void wn_bwd_k(const float* __restrict__ dw, const float* __restrict__
   if (threadIdx.x == 0) dg[r] = s * inv;
 }
 
+// The backward for MANY weights in one launch: table[j] = {v, g, offset of dw_j in flat_dw, offset of dv_j in flat_dv, first
+// row of dg_j in flat_dg, cols}; row_start as in wn_fwd_multi_k; one block per global row.  1 / ||v|| is recomputed from v
+// (the forward's value may belong to a scope that is gone), so the kernel needs nothing from the forward.
+__global__ void wn_bwd_multi_k(const long long* __restrict__ table, const int* __restrict__ row_start, int n,
+                               const float* __restrict__ flat_dw, float* __restrict__ flat_dv, float* __restrict__ flat_dg) {
+  pdl_prologue();
+  __shared__ float sm[33];
+  const int gr = blockIdx.x;
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(row_start + mid) <= gr) lo = mid; else hi = mid - 1;
+  }
+  const long long* e = table + 6LL * lo;
+  const float* v = reinterpret_cast<const float*>(e[0]);
+  const float* g = reinterpret_cast<const float*>(e[1]);
+  const int cols = (int)e[5];
+  const int r = gr - __ldg(row_start + lo);
+  const float* vr = v + (long long)r * cols;
+  const float* dr = flat_dw + e[2] + (long long)r * cols;
+  float sv = 0.f, sd = 0.f;
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) {
+    const float a = vr[i];
+    sv = fmaf(a, a, sv);
+    sd = fmaf(dr[i], a, sd);
+  }
+  sv = block_sum(sv, sm);
+  sd = block_sum(sd, sm);
+  float inv = rsqrtf(sv);
+  inv = inv * (1.5f - 0.5f * sv * inv * inv);
+  const float gi = g[r] * inv;
+  const float c = sd * inv * inv;
+  float* o = flat_dv + e[3] + (long long)r * cols;
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) o[i] = gi * (dr[i] - vr[i] * c);
+  if (threadIdx.x == 0) flat_dg[e[4] + r] = sd * inv;
+}
+
 // per-(b,c) mean and 1/sqrt(var+eps) over T (biased variance, two-pass for fp32 accuracy)
 __global__ void instnorm_stats_k(const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ rstd, int T,
                                  float eps) {
@@ -185,6 +222,15 @@ extern "C" int tdvc_weight_norm_fwd_multi(const void* table, const void* row_sta
   TDVC_CHECK_ARG(table && row_start && n_weights > 0 && total_rows > 0 && flat_w && flat_inv);
   tdvc::launch_k(wn_fwd_multi_k, total_rows, 256, 0, (cudaStream_t)stream, (const long long*)table, (const int*)row_start,
                  n_weights, flat_w, flat_inv);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_weight_norm_bwd_multi(const void* table, const void* row_start, int n_weights, int total_rows,
+                                          const float* flat_dw, float* flat_dv, float* flat_dg, void* stream) {
+  TDVC_CHECK_ARG(table && row_start && n_weights > 0 && total_rows > 0 && flat_dw && flat_dv && flat_dg);
+  tdvc::launch_k(wn_bwd_multi_k, total_rows, 128, 0, (cudaStream_t)stream, (const long long*)table, (const int*)row_start,
+                 n_weights, flat_dw, flat_dv, flat_dg);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }

@@ -72,6 +72,7 @@ SIGNATURES = {
     "tdvc_weight_norm_fwd": (_I, [_P, _P, _P, _P, _I, _I, _P]),
     "tdvc_weight_norm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "tdvc_weight_norm_fwd_multi": (_I, [_P, _P, _I, _I, _P, _P, _P]),
+    "tdvc_weight_norm_bwd_multi": (_I, [_P, _P, _I, _I, _P, _P, _P, _P]),
     "tdvc_conv1d_fwd": (_I, [_G, _P, _P, _P, _P, _P, _P]),
     "tdvc_conv1d_bwd_data_ws": (_L, [_G]),
     "tdvc_conv1d_bwd_data": (_I, [_G, _P, _P, _P, _P, _P, _P]),

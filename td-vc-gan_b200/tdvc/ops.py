@@ -98,7 +98,7 @@ class _WeightNorm(torch.autograd.Function):
     def forward(ctx, v, g):
         _req(v, g)
         pre = _step_cache.lookup_w(v, g)
-        if pre is not None:                      # normalised by the scope's batched launch
+        if pre is not None and pre[1] is not None:
             w, inv = pre
         else:
             v, g = _c(v), _c(g)
@@ -122,6 +122,70 @@ class _WeightNorm(torch.autograd.Function):
         _lib.check(_lib.load().tdvc_weight_norm_bwd(_p(dw), _p(v), _p(g), _p(inv), _p(dv), _p(dg), rows, cols, _st()),
                    "weight_norm_bwd")
         return dv, dg
+
+
+def _wn_multi_forward(t):
+    lib = _lib.load()
+    flat_w = torch.empty(t["w_elems"], device=t["dev"], dtype=torch.float32)
+    flat_inv = torch.empty(t["total_rows"], device=t["dev"], dtype=torch.float32)
+    _lib.check(lib.tdvc_weight_norm_fwd_multi(_p(t["table"]), _p(t["rows_dev"]), t["n"], t["total_rows"], _p(flat_w),
+                                              _p(flat_inv), _st()), "weight_norm_fwd_multi")
+    return flat_w, flat_inv
+
+
+class _WeightNormMulti(torch.autograd.Function):
+    """w_j = g_j * v_j / ||v_j|| for every weight of a step scope: one launch forward (all w_j are views of one flat
+    buffer), one launch backward (tdvc_weight_norm_bwd_multi) once every dL/dw_j has arrived."""
+
+    @staticmethod
+    def forward(ctx, t, *vg):
+        n = t["n"]
+        vs, gs = vg[:n], vg[n:]
+        flat_w, _ = _wn_multi_forward(t)
+        ws = [flat_w[t["w_off"][j]:t["w_off"][j] + vs[j].numel()].view_as(vs[j]) for j in range(n)]
+        ctx.t = t
+        ctx.shapes = [tuple(v.shape) for v in vs]
+        return tuple(ws)
+
+    @staticmethod
+    def backward(ctx, *dws):
+        t = ctx.t
+        n = t["n"]
+        lib = _lib.load()
+        dev = t["dev"]
+        flat_dw = torch.empty(t["w_elems"], device=dev, dtype=torch.float32)
+        flat_dv = torch.empty(t["w_elems"], device=dev, dtype=torch.float32)
+        flat_dg = torch.empty(t["total_rows"], device=dev, dtype=torch.float32)
+        src, dst, missing = [], [], []
+        for j in range(n):
+            numel = 1
+            for d in ctx.shapes[j]:
+                numel *= d
+            view = flat_dw[t["w_off"][j]:t["w_off"][j] + numel].view(ctx.shapes[j])
+            if dws[j] is None:
+                missing.append(view)
+            else:
+                src.append(dws[j])
+                dst.append(view)
+        if missing:
+            torch._foreach_zero_(missing)
+        if src:
+            torch._foreach_copy_(dst, src)
+        _lib.check(lib.tdvc_weight_norm_bwd_multi(_p(t["btable"]), _p(t["rows_dev"]), n, t["total_rows"], _p(flat_dw), _p(flat_dv),
+                                                  _p(flat_dg), _st()), "weight_norm_bwd_multi")
+        dvs, dgs = [], []
+        for j in range(n):
+            numel = 1
+            for d in ctx.shapes[j]:
+                numel *= d
+            if dws[j] is None:
+                dvs.append(None)
+                dgs.append(None)
+                continue
+            dvs.append(flat_dv[t["w_off"][j]:t["w_off"][j] + numel].view(ctx.shapes[j]))
+            rows = ctx.shapes[j][0]
+            dgs.append(flat_dg[t["row_start"][j]:t["row_start"][j] + rows].view(rows, *([1] * (len(ctx.shapes[j]) - 1))))
+        return (None, *dvs, *dgs)
 
 
 class _Scope:
@@ -274,7 +338,13 @@ class _StepCache:
             p_off.append(poff)
             poff += al(K * rows_p * cols_p, 64)
         max_job = max([jobs[8 * i + 4] * jobs[8 * i + 5] * jobs[8 * i + 6] for i in range(len(jobs) // 8)] or [1])
+        # backward table (tdvc_weight_norm_bwd_multi): dw_j and dv_j sit at w_j's offset of their own flat buffers, dg_j at
+        # its first global row
+        btab = []
+        for j, (v, g) in enumerate(live):
+            btab += [v.data_ptr(), g.data_ptr(), w_off[j], w_off[j], rows[j], v.numel() // v.shape[0]]
         t = dict(sig=tuple(tab[0::4]) + tuple(tab[1::4]), dev=dev, n=len(live), total_rows=r, w_elems=off, p_elems=poff,
+                 btable=torch.tensor(btab, dtype=torch.int64).to(dev),
                  blocks_per_job=max(1, min(256, -(-max_job // (256 * 16)))),      # <= 16 outputs per thread in the largest job
                  w_off=w_off, row_start=rows, p_off=p_off,
                  table=torch.tensor(tab, dtype=torch.int64).to(dev), rows_dev=torch.tensor(rows, dtype=torch.int32).to(dev),
@@ -299,17 +369,18 @@ class _StepCache:
             pl["tables"] = self._build_tables(pl, live, dev)
         t = pl["tables"]
         lib = _lib.load()
-        flat_w = torch.empty(t["w_elems"], device=dev, dtype=torch.float32)
-        flat_inv = torch.empty(t["total_rows"], device=dev, dtype=torch.float32)
-        _lib.check(lib.tdvc_weight_norm_fwd_multi(_p(t["table"]), _p(t["rows_dev"]), t["n"], t["total_rows"], _p(flat_w),
-                                                  _p(flat_inv), _st()), "weight_norm_fwd_multi")
-        ws = []
+        need_grad = torch.is_grad_enabled() and any(v.requires_grad or g.requires_grad for v, g in live)
+        if need_grad:
+            # ONE autograd node for every weight of the scope: its backward gathers the weight gradients and runs a single
+            # multi-tensor launch instead of one wn_bwd_k per weight
+            ws = list(_WeightNormMulti.apply(t, *[v for v, _ in live], *[g for _, g in live]))
+            flat_w = ws[0]               # the first weight sits at offset 0 of the flat buffer: its address is the buffer's
+        else:
+            flat_w, _ = _wn_multi_forward(t)
+            ws = [flat_w[t["w_off"][j]:t["w_off"][j] + v.numel()].view_as(v) for j, (v, g) in enumerate(live)]
         for j, (v, g) in enumerate(live):
-            w = flat_w[t["w_off"][j]:t["w_off"][j] + v.numel()].view_as(v)
-            inv = flat_inv[t["row_start"][j]:t["row_start"][j + 1]]
-            sc.pre_w[(v.data_ptr(), g.data_ptr())] = (w, inv, v._version, g._version)
-            sc.cur_w[w.data_ptr()] = j
-            ws.append(w)
+            sc.pre_w[(v.data_ptr(), g.data_ptr())] = (ws[j], None, v._version, g._version)
+            sc.cur_w[ws[j].data_ptr()] = j
         if t["jobs"] is not None:
             flat_wp = torch.empty(t["p_elems"], device=dev, dtype=torch.bfloat16)
             _lib.check(lib.tdvc_pack_weight_bf16_multi(_p(t["jobs"]), len(pl["plan_p"]), t["blocks_per_job"], _p(flat_w),
@@ -339,6 +410,9 @@ def inference_cache() -> _StepCache:
 def weight_norm(v: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
     """w = g * v / ||v|| (norm over all dims but 0) -- torch.nn.utils.weight_norm's per-forward recompute."""
     if _step_cache.depth > 0:
+        pre = _step_cache.lookup_w(v, g)
+        if pre is not None and pre[1] is None:        # normalised by the scope's batched launch (carries the scope's grad_fn)
+            return pre[0]
         key = (v.data_ptr(), v._version, g.data_ptr(), g._version, torch.is_grad_enabled() and (v.requires_grad or g.requires_grad))
         hit = _step_cache.get_wn(key)
         if hit is None:

@@ -267,7 +267,13 @@ class TrainStep:
     def g_forward_backward(self, batch, raw_draws=None) -> dict:
         gen = self._gen_for(batch)
         try:
-            with ops.step_cache("Gstep"):
+            # D (and C) are frozen BEFORE their scope opens: the scope's batched weight norm then builds no autograd node
+            # for them, and their convolutions compute no weight gradients in this step
+            with contextlib.ExitStack() as stack:
+                stack.enter_context(frozen(self.D))
+                if self.C is not None:
+                    stack.enter_context(frozen(self.C))
+                stack.enter_context(ops.step_cache("Gstep"))
                 return self._g_forward_backward(batch, gen, raw_draws)
         finally:
             self._close_gen()                 # the graph is consumed by this backward
