@@ -135,22 +135,30 @@ def _wn_multi_forward(t):
 
 class _WeightNormMulti(torch.autograd.Function):
     """w_j = g_j * v_j / ||v_j|| for every weight of a step scope: one launch forward (all w_j are views of one flat
-    buffer), one launch backward (tdvc_weight_norm_bwd_multi) once every dL/dw_j has arrived."""
+    buffer), one launch backward (tdvc_weight_norm_bwd_multi) once every dL/dw_j has arrived.
+
+    The parameters enter as plain tensors next to a per-scope `anchor` that carries the autograd edge, and the backward
+    deposits dL/dv_j, dL/dg_j into the parameters' .grad itself (set, or added in place when a gradient is already there --
+    what AccumulateGrad does).  Routing ~500 parameter gradients of one node through the engine's AccumulateGrad nodes
+    made the engine synchronise the legacy default stream with the capturing stream under CUDA-graph capture (fp32 mode,
+    measured: cudaErrorStreamCaptureImplicit); the per-parameter post-accumulate hooks do not fire for these parameters
+    (tdvc.dp.BucketedReducer.finish() flushes their buckets)."""
 
     @staticmethod
-    def forward(ctx, t, *vg):
+    def forward(ctx, t, live, anchor):
         n = t["n"]
-        vs, gs = vg[:n], vg[n:]
+        vs, gs = [v for v, _ in live], [g for _, g in live]
         flat_w, _ = _wn_multi_forward(t)
         ws = [flat_w[t["w_off"][j]:t["w_off"][j] + vs[j].numel()].view_as(vs[j]) for j in range(n)]
         ctx.t = t
-        ctx.shapes = [tuple(v.shape) for v in vs]
+        ctx.params = (vs, gs)
         return tuple(ws)
 
     @staticmethod
     def backward(ctx, *dws):
         t = ctx.t
         n = t["n"]
+        vs, gs = ctx.params
         lib = _lib.load()
         dev = t["dev"]
         flat_dw = torch.empty(t["w_elems"], device=dev, dtype=torch.float32)
@@ -158,10 +166,7 @@ class _WeightNormMulti(torch.autograd.Function):
         flat_dg = torch.empty(t["total_rows"], device=dev, dtype=torch.float32)
         src, dst, missing = [], [], []
         for j in range(n):
-            numel = 1
-            for d in ctx.shapes[j]:
-                numel *= d
-            view = flat_dw[t["w_off"][j]:t["w_off"][j] + numel].view(ctx.shapes[j])
+            view = flat_dw[t["w_off"][j]:t["w_off"][j] + vs[j].numel()].view_as(vs[j])
             if dws[j] is None:
                 missing.append(view)
             else:
@@ -173,19 +178,24 @@ class _WeightNormMulti(torch.autograd.Function):
             torch._foreach_copy_(dst, src)
         _lib.check(lib.tdvc_weight_norm_bwd_multi(_p(t["btable"]), _p(t["rows_dev"]), n, t["total_rows"], _p(flat_dw), _p(flat_dv),
                                                   _p(flat_dg), _st()), "weight_norm_bwd_multi")
-        dvs, dgs = [], []
-        for j in range(n):
-            numel = 1
-            for d in ctx.shapes[j]:
-                numel *= d
-            if dws[j] is None:
-                dvs.append(None)
-                dgs.append(None)
-                continue
-            dvs.append(flat_dv[t["w_off"][j]:t["w_off"][j] + numel].view(ctx.shapes[j]))
-            rows = ctx.shapes[j][0]
-            dgs.append(flat_dg[t["row_start"][j]:t["row_start"][j] + rows].view(rows, *([1] * (len(ctx.shapes[j]) - 1))))
-        return (None, *dvs, *dgs)
+        with torch.no_grad():
+            for j in range(n):
+                if dws[j] is None:
+                    continue
+                v, g = vs[j], gs[j]
+                if v.requires_grad:
+                    dv = flat_dv[t["w_off"][j]:t["w_off"][j] + v.numel()].view_as(v)
+                    if v.grad is None:
+                        v.grad = dv
+                    else:
+                        v.grad.add_(dv)
+                if g.requires_grad:
+                    dg = flat_dg[t["row_start"][j]:t["row_start"][j] + g.numel()].view_as(g)
+                    if g.grad is None:
+                        g.grad = dg
+                    else:
+                        g.grad.add_(dg)
+        return None, None, None
 
 
 class _Scope:
@@ -373,7 +383,8 @@ class _StepCache:
         if need_grad:
             # ONE autograd node for every weight of the scope: its backward gathers the weight gradients and runs a single
             # multi-tensor launch instead of one wn_bwd_k per weight
-            ws = list(_WeightNormMulti.apply(t, *[v for v, _ in live], *[g for _, g in live]))
+            anchor = torch.zeros(1, device=dev, dtype=torch.float32, requires_grad=True)
+            ws = list(_WeightNormMulti.apply(t, list(live), anchor))
             flat_w = ws[0]               # the first weight sits at offset 0 of the flat buffer: its address is the buffer's
         else:
             flat_w, _ = _wn_multi_forward(t)
