@@ -198,6 +198,15 @@ int tdvc_pack_cl_bf16(const float* x, void* xp, int B, int C, int T, int Cp /* r
                       the wgrad GEMM); -1: none */,
                       const float* film_gb /* optional [B,2C,T]: x*(1+gamma)+beta is applied before the LeakyReLU
                       (FiLM + activation + pack in one pass, generator.py:104-108) */, void* stream);
+/*      the same pass on dL/dy of a layer that ends in LeakyReLU(slope) (model/discriminator.py:15-37: every layer of D):
+ *      dyp = bf16 channels-last of dy * (y > 0 ? 1 : slope) -- the activation's backward applied while packing, chan_sum =
+ *      the bias gradient.  Replaces torch's leaky_relu_backward + the pack. */
+/*      the decoder's conditioning cat([c.unsqueeze(2).repeat(1, 1, T), e], dim=1) (model/generator.py:387-399; c[B,Cc] the
+ *      speaker code, e[B,Ce,T] the excitation level) as the packed operand of the cond_var convs, without the fp32 tensor:
+ *      cp[B, T, Cg] bf16, channel Cc+Ce = 1 (bias-gradient channel), zeros up to Cg. */
+int tdvc_cond_pack_cl(const float* c, const float* e, void* cp, int B, int Cc, int Ce, int T, int Cg, void* stream);
+int tdvc_pack_cl_bf16_masked(const float* dy, const float* y /* the layer's output, same shape */, float slope, void* dyp,
+                             int B, int C, int T, int Cp, float* chan_sum /* optional [C], OVERWRITTEN */, void* stream);
 /* w[Cout,Cin,K] fp32 -> wp[K, Coutp, Cinp] bf16 (zero padded); transpose_flip!=0 produces the
  * dgrad operand wp[K, Cinp, Coutp] with taps reversed. */
 int tdvc_pack_weight_bf16(const float* w, void* wp, int Cout, int Cin, int K, int Coutp, int Cinp,

@@ -1,9 +1,9 @@
 """Each kernel family of the training step launched in isolation at its benchmark shape, twice (the second launch of
-every kernel is the one to read: warm instruction cache, cold data like inside the step) -- the program `ncu --set full`
+every kernel is the one profiled: warm instruction cache, cold data like inside the step) -- the program `ncu --set full`
 is pointed at (profiles/tools/gpu_run_ncu.sh).  Shapes: conv_enc-stage1, B = 16 per pass, two passes stacked (B = 32),
 T = 8960, 136 conditioning channels.
 
-    python profiles/tools/ncu_targets.py [mrf|disc|hbm|all]
+    python profiles/tools/ncu_targets.py [mini|mrf|disc|hbm|all]
 """
 import os
 import sys
@@ -29,39 +29,50 @@ def rnd(*shape, scale=1.0, grad=False):
 
 
 def twice(fn):
-    for _ in range(2):
-        fn()
-        torch.cuda.synchronize()
+    """first call outside the profiler range (ncu --profile-from-start off), second one inside"""
+    fn()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    fn()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
 
 
-if what in ("mrf", "all"):
-    # the full-rate decoder stage: C = 16, 9 FiLM blocks, 136-channel conditioning (model/generator.py:175-194)
-    C, Cc, ks, ds = 16, 136, (3, 7, 11), (1, 3, 5)
-    x, c = rnd(B, C, T, grad=True), rnd(B, Cc, T, grad=True)
-    blocks = [[[rnd(C, C, k, scale=(C * k) ** -0.5, grad=True), rnd(C, scale=0.1, grad=True),
-                rnd(C, C, 1, scale=C ** -0.5, grad=True), rnd(C, scale=0.1, grad=True),
-                rnd(Cc, Cc, 3, scale=(3 * Cc) ** -0.5, grad=True), rnd(Cc, scale=0.1, grad=True),
-                rnd(2 * C, Cc, 3, scale=0.5 * (3 * Cc) ** -0.5, grad=True), rnd(2 * C, scale=0.1, grad=True)]
-               for _ in ds] for k in ks]
-    proj = rnd(B, C, T)
+def mrf_blocks(C, Cc, ks, ds):
+    def blk(k):
+        t = [rnd(C, C, k, scale=(C * k) ** -0.5, grad=True), rnd(C, scale=0.1, grad=True),
+             rnd(C, C, 1, scale=C ** -0.5, grad=True), rnd(C, scale=0.1, grad=True)]
+        if Cc:
+            t += [rnd(Cc, Cc, 3, scale=(3 * Cc) ** -0.5, grad=True), rnd(Cc, scale=0.1, grad=True),
+                  rnd(2 * C, Cc, 3, scale=0.5 * (3 * Cc) ** -0.5, grad=True), rnd(2 * C, scale=0.1, grad=True)]
+        return t
+    return [[blk(k) for _ in ds] for k in ks]
+
+
+def run_stage(C, Cc, Tq, ks, ds):
+    x = rnd(B, C, Tq, grad=True)
+    c = rnd(B, Cc, Tq, grad=True) if Cc else None
+    blocks, proj = mrf_blocks(C, Cc, ks, ds), rnd(B, C, Tq)
 
     def stage():
         y = ops.mrf_stage(x, c, blocks, ks, ds)
         (y * proj).sum().backward()
     twice(stage)
-    # an encoder stage without conditioning: C = 64, T / 4
-    C2 = 64
-    x2 = rnd(B, C2, T // 4, grad=True)
-    blocks2 = [[[rnd(C2, C2, k, scale=(C2 * k) ** -0.5, grad=True), rnd(C2, scale=0.1, grad=True),
-                 rnd(C2, C2, 1, scale=C2 ** -0.5, grad=True), rnd(C2, scale=0.1, grad=True)] for _ in ds] for k in ks]
-    proj2 = rnd(B, C2, T // 4)
 
-    def stage2():
-        y = ops.mrf_stage(x2, None, blocks2, ks, ds)
-        (y * proj2).sum().backward()
-    twice(stage2)
 
-if what in ("disc", "all"):
+if what in ("mini", "all"):
+    # ONE FiLM block (k = 7, d = 3) of the full-rate decoder stage (C = 16, 136-channel conditioning) and of an encoder stage
+    # (C = 64, T / 4): every kernel of the bf16-resident stage at its benchmark shape, ~30 launches instead of ~300
+    run_stage(16, 136, T, (7,), (3,))
+    run_stage(64, 0, T // 4, (7,), (3,))
+    run_stage(256, 0, 28, (11,), (5,))
+
+if what in ("mrf",):
+    # the full 9-block stages: the stacked cond_var.0 launch (9 x 136 output rows) and the 3-branch chain kernels
+    run_stage(16, 136, T, (3, 7, 11), (1, 3, 5))
+    run_stage(64, 0, T // 4, (3, 7, 11), (1, 3, 5))
+
+if what in ("disc", "mini", "all"):
     # discriminator.1.0 (16 -> 64, k41 s4, 4 groups) on the full-rate branch and the dense 1024 -> 1024 k5 layer
     x = rnd(B, 16, T, grad=True)
     w, b = rnd(64, 4, 41, scale=164 ** -0.5, grad=True), rnd(64, scale=0.1, grad=True)
@@ -78,7 +89,7 @@ if what in ("disc", "all"):
         y.sum().backward()
     twice(dense)
 
-if what in ("hbm", "all"):
+if what in ("hbm", "mini", "all"):
     # bandwidth-bound kernels: feature-matching L1 over one full-rate map, LSGAN term, CIN, AdamW, batched weight norm
     a, r = rnd(B, 16, T, grad=True), rnd(B // 2, 16, T)
 
@@ -104,7 +115,8 @@ if what in ("hbm", "all"):
     def gfwd():
         with torch.no_grad(), ops.step_cache("G"):
             G(xg, ct, c_var=cv)
-    for _ in range(3):       # third scope: the batched weight-norm / pack launches of the recorded plan
+    for _ in range(2):       # the third scope runs the batched weight-norm / pack launches of the recorded plan
         gfwd()
         torch.cuda.synchronize()
+    twice(gfwd)
 print("ncu targets done:", what)

@@ -593,6 +593,84 @@ __global__ void __launch_bounds__(256) stem_wgrad_k(const float* __restrict__ dy
   if (db && threadIdx.x < Cout) atomicAdd(db + threadIdx.x, bsum);
 }
 
+
+// Weight (and bias) gradient of the narrow convs -- the excitation pyramid (8 -> 8 channels: k = 2r stride r, k5, 1x1) and
+// the 1-channel output heads (C -> 1, k7): Cout <= 16 and Cout * Cin * K <= 2048.  The general kernel gives such a conv a
+// few CTAs that each walk the whole tensor (59 us per call on average in the step, 15 calls); here a CTA takes one (batch,
+// TT-step chunk), stages the padded input span of all Cin channels and 128-step tiles of dy in shared memory, thread p owns
+// the triples (co, ci, k) = p, p + 256, ... and adds its partial sums with one atomic each.
+constexpr int NARROW_SUB = 128, NARROW_ACC = 8;
+
+__global__ void __launch_bounds__(256) narrow_wgrad_k(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dw,
+                                                       float* __restrict__ db, int Cin, int Cout, int Tin, int Tout, int K, int stride,
+                                                       int dil, int pad, int pad_mode, float in_slope, int TT) {
+  pdl_prologue();
+  extern __shared__ float sm[];
+  const int span = (TT - 1) * stride + (K - 1) * dil + 1;
+  const int spanp = span | 1;                  // odd pitch: channels start in different banks
+  float* xs = sm;                              // [Cin][spanp]
+  float* dys = sm + ((Cin * spanp + 3) & ~3);  // [Cout][NARROW_SUB + 1]
+  const int b = blockIdx.y, t0 = blockIdx.x * TT;
+  const float* xb = x + (long long)b * Cin * Tin;
+  const int g0 = t0 * stride - pad;
+  for (int i = threadIdx.x; i < Cin * span; i += 256) {
+    const int ci = i / span, j = i - ci * span;
+    xs[ci * spanp + j] = fetch_padded(xb + (long long)ci * Tin, g0 + j, Tin, pad_mode, in_slope);
+  }
+  const int npairs = Cout * Cin * K, cik = Cin * K;
+  float acc[NARROW_ACC];
+  int xoff[NARROW_ACC], doff[NARROW_ACC];
+#pragma unroll
+  for (int q = 0; q < NARROW_ACC; ++q) {
+    acc[q] = 0.f;
+    const int pidx = min(threadIdx.x + 256 * q, npairs - 1);
+    const int co = pidx / cik, rem = pidx - co * cik, ci = rem / K, k = rem - ci * K;
+    xoff[q] = ci * spanp + k * dil;
+    doff[q] = co * (NARROW_SUB + 1);
+  }
+  float bsum = 0.f;
+  const int tend = min(TT, Tout - t0);
+  for (int s0 = 0; s0 < tend; s0 += NARROW_SUB) {
+    const int ns = min(NARROW_SUB, tend - s0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < Cout * NARROW_SUB; i += 256) {
+      const int co = i / NARROW_SUB, t = i - co * NARROW_SUB;
+      dys[co * (NARROW_SUB + 1) + t] = t < ns ? __ldg(dy + ((long long)b * Cout + co) * Tout + t0 + s0 + t) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NARROW_ACC; ++q) {
+      if (threadIdx.x + 256 * q < npairs) {
+        const float* dr = dys + doff[q];
+        const float* xr = xs + xoff[q] + s0 * stride;
+        float a = acc[q];
+        for (int t = 0; t < ns; ++t) a = fmaf(dr[t], xr[t * stride], a);
+        acc[q] = a;
+      }
+    }
+    if (db && threadIdx.x < Cout) {
+      const float* dr = dys + threadIdx.x * (NARROW_SUB + 1);
+      for (int t = 0; t < ns; ++t) bsum += dr[t];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < NARROW_ACC; ++q) {
+    const int pidx = threadIdx.x + 256 * q;
+    if (pidx < npairs) atomicAdd(dw + pidx, acc[q]);
+  }
+  if (db && threadIdx.x < Cout) atomicAdd(db + threadIdx.x, bsum);
+}
+
+// chunk length of narrow_wgrad_k: the largest of 1024 .. 128 whose shared-memory tiles fit 160 KB; 0 = none does
+static int narrow_wgrad_tt(int Cin, int Cout, int K, int stride, int dil, size_t* smem) {
+  for (int TT = 1024; TT >= 128; TT >>= 1) {
+    const int span = (TT - 1) * stride + (K - 1) * dil + 1;
+    const size_t need = ((size_t)((Cin * (span | 1) + 3) & ~3) + (size_t)Cout * (NARROW_SUB + 1)) * sizeof(float);
+    if (need <= 160 * 1024) { *smem = need; return TT; }
+  }
+  return 0;
+}
+
 static int launch_channel_sum(const float* dy, float* db, int B, int C, int T, cudaStream_t st) {
   TDVC_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * C, st));
   if (B == 0) return TDVC_OK;
@@ -703,6 +781,21 @@ extern "C" int tdvc_conv1d_bwd_weight(const tdvc_conv_geom* g, const float* dy, 
                      g->dilation, g->pad, g->pad_mode, g->in_slope);
       TDVC_LAUNCH_CHECK();
       g_flops[FLOP_FP32] += 2.0 * g->B * g->Tout * (double)g->Cout * g->K;
+      return TDVC_OK;
+    }
+  }
+  if (g->groups == 1 && g->Cin > 1 && g->Cout <= 16 && (long long)g->Cout * g->Cin * g->K <= 256 * NARROW_ACC && g->B > 0) {
+    // the excitation pyramid and the 1-channel heads
+    size_t smem = 0;
+    const int TT = narrow_wgrad_tt(g->Cin, g->Cout, g->K, g->stride, g->dilation, &smem);
+    if (TT > 0) {
+      TDVC_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)g->Cout * g->Cin * g->K, st));
+      if (dbias) TDVC_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * (size_t)g->Cout, st));
+      if (smem > 48 * 1024) TDVC_CUDA(cudaFuncSetAttribute(narrow_wgrad_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      tdvc::launch_k(narrow_wgrad_k, dim3(cdiv(g->Tout, TT), g->B), 256, smem, st, dy, x, dw, dbias, g->Cin, g->Cout, g->Tin,
+                     g->Tout, g->K, g->stride, g->dilation, g->pad, g->pad_mode, g->in_slope, TT);
+      TDVC_LAUNCH_CHECK();
+      g_flops[FLOP_FP32] += 2.0 * g->B * g->Tout * (double)g->Cout * g->Cin * g->K;
       return TDVC_OK;
     }
   }

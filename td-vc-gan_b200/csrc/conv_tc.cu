@@ -1201,7 +1201,8 @@ template <int CH>
 __global__ void __launch_bounds__(256) pack_cl_bf16_k(const float* __restrict__ x, __nv_bfloat16* __restrict__ xp, int C,
                                                      int T, int Cp, int Tp, int halo, int pad_mode, float slope,
                                                      float* __restrict__ chan_sum, int c_off, int Cw, int ones_ch,
-                                                     const float* __restrict__ film_gb) {
+                                                     const float* __restrict__ film_gb, const float* __restrict__ mask_y,
+                                                     float mask_slope) {
   pdl_prologue();
   constexpr int TL = 4096 / CH;             // time steps per tile: 64 / 128 / 256
   constexpr int RPW = CH / 8;               // channel rows per warp
@@ -1233,6 +1234,8 @@ __global__ void __launch_bounds__(256) pack_cl_bf16_k(const float* __restrict__ 
             const float* gp = film_gb + ((long long)b * 2 * C + c) * T + u;
             v = fmaf(v, 1.f + __ldg(gp), __ldg(gp + (long long)C * T));
           }
+          // x = dL/dy of a LeakyReLU layer, mask_y its output: the derivative of the activation applied on the way in
+          if (mask_y && !(__ldg(mask_y + ((long long)b * C + c) * T + u) > 0.f)) v *= mask_slope;
         }
       }
       vals[r][l] = v;
@@ -1268,6 +1271,38 @@ __global__ void __launch_bounds__(256) pack_cl_bf16_k(const float* __restrict__ 
     __nv_bfloat16* dst = xp + ((long long)b * Tp + tp) * Cp + c_off + c;
     if (c + 1 < Cw) *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(o0, o1);
     else *dst = __float2bfloat16(o0);
+  }
+}
+
+
+// The decoder's conditioning tensor cat([speaker code repeated over time, excitation pyramid level]) (model/generator.py:
+// 387-399) written straight into the bf16 channels-last operand of the cond_var convs: cp[b, t, 0..Cc) = c[b, :] (constant
+// over time), cp[b, t, Cc..Cc+Ce) = e[b, :, t], cp[b, t, Cc+Ce] = 1 (the bias-gradient channel), zero up to Cg.  The fp32
+// [B, Cc+Ce, T] tensor the reference builds (156 MB at the full-rate stage) is never materialised.
+__global__ void __launch_bounds__(256) cond_pack_cl_k(const float* __restrict__ c, const float* __restrict__ e,
+                                                      __nv_bfloat16* __restrict__ cp, int Cc, int Ce, int T, int Cg) {
+  pdl_prologue();
+  extern __shared__ float sm[];               // [Cc] speaker code | [Ce][64 + 1] excitation tile
+  float* cs = sm;
+  float* es = sm + Cc;
+  const int b = blockIdx.y, t0 = blockIdx.x * 64;
+  for (int i = threadIdx.x; i < Cc; i += 256) cs[i] = __ldg(c + (long long)b * Cc + i);
+  for (int i = threadIdx.x; i < Ce * 64; i += 256) {
+    const int ch = i >> 6, t = i & 63;
+    es[ch * 65 + t] = (t0 + t < T) ? __ldg(e + ((long long)b * Ce + ch) * T + t0 + t) : 0.f;
+  }
+  __syncthreads();
+  const int pairs = Cg / 2;
+  const int nt = min(64, T - t0);
+  for (int i = threadIdx.x; i < nt * pairs; i += 256) {
+    const int t = i / pairs, ch = 2 * (i - t * pairs);
+    float v[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int cc = ch + q;
+      v[q] = cc < Cc ? cs[cc] : (cc < Cc + Ce ? es[(cc - Cc) * 65 + t] : (cc == Cc + Ce ? 1.f : 0.f));
+    }
+    *reinterpret_cast<__nv_bfloat162*>(cp + ((long long)b * T + t0 + t) * Cg + ch) = __floats2bfloat162_rn(v[0], v[1]);
   }
 }
 
@@ -1315,9 +1350,9 @@ __global__ void pack_weight_multi_k(const long long* __restrict__ jobs, const fl
 }  // namespace tdvc
 using namespace tdvc;
 
-extern "C" int tdvc_pack_cl_bf16(const float* x, void* xp, int B, int C, int T, int Cp, int halo, int pad_mode,
-                                 float in_slope, float* chan_sum, int c_off, int Cw, int ones_ch, const float* film_gb,
-                                 void* stream) {
+static int pack_cl_bf16_launch(const float* x, void* xp, int B, int C, int T, int Cp, int halo, int pad_mode, float in_slope,
+                               float* chan_sum, int c_off, int Cw, int ones_ch, const float* film_gb, const float* mask_y,
+                               float mask_slope, void* stream) {
   if (Cw <= 0) Cw = Cp - c_off;
   TDVC_CHECK_ARG(B >= 0 && C > 0 && T > 0 && Cw >= C && c_off >= 0 && c_off + Cw <= Cp && Cp % 8 == 0 && halo >= 0 && x && xp);
   TDVC_CHECK_ARG(ones_ch < 0 || (ones_ch >= C && ones_ch < Cw));
@@ -1332,17 +1367,40 @@ extern "C" int tdvc_pack_cl_bf16(const float* x, void* xp, int B, int C, int T, 
   if (C <= 16 && Cw <= 64) {
     dim3 grid(cdiv(Tp, 256), 1, B);
     tdvc::launch_k(pack_cl_bf16_k<16>, grid, 256, 0, st, x, o, C, T, Cp, Tp, halo, pad_mode, in_slope, chan_sum, c_off, Cw, ones_ch,
-                                             film_gb);
+                                             film_gb, mask_y, mask_slope);
   } else if (C <= 32 && Cw <= 64) {
     dim3 grid(cdiv(Tp, 128), 1, B);
     tdvc::launch_k(pack_cl_bf16_k<32>, grid, 256, 0, st, x, o, C, T, Cp, Tp, halo, pad_mode, in_slope, chan_sum, c_off, Cw, ones_ch,
-                                             film_gb);
+                                             film_gb, mask_y, mask_slope);
   } else {
     dim3 grid(cdiv(Tp, 64), cdiv(Cw, 64), B);
     TDVC_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535);
     tdvc::launch_k(pack_cl_bf16_k<64>, grid, 256, 0, st, x, o, C, T, Cp, Tp, halo, pad_mode, in_slope, chan_sum, c_off, Cw, ones_ch,
-                                             film_gb);
+                                             film_gb, mask_y, mask_slope);
   }
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_pack_cl_bf16(const float* x, void* xp, int B, int C, int T, int Cp, int halo, int pad_mode,
+                                 float in_slope, float* chan_sum, int c_off, int Cw, int ones_ch, const float* film_gb,
+                                 void* stream) {
+  return pack_cl_bf16_launch(x, xp, B, C, T, Cp, halo, pad_mode, in_slope, chan_sum, c_off, Cw, ones_ch, film_gb, nullptr, 1.f,
+                             stream);
+}
+
+extern "C" int tdvc_pack_cl_bf16_masked(const float* dy, const float* y, float slope, void* dyp, int B, int C, int T, int Cp,
+                                        float* chan_sum, void* stream) {
+  TDVC_CHECK_ARG(y != nullptr);
+  return pack_cl_bf16_launch(dy, dyp, B, C, T, Cp, 0, TDVC_PAD_ZEROS, 1.f, chan_sum, 0, 0, -1, nullptr, y, slope, stream);
+}
+
+extern "C" int tdvc_cond_pack_cl(const float* c, const float* e, void* cp, int B, int Cc, int Ce, int T, int Cg, void* stream) {
+  TDVC_CHECK_ARG(c && e && cp && B >= 0 && Cc > 0 && Ce > 0 && T > 0 && Cg % 2 == 0 && Cg > Cc + Ce && B <= 65535);
+  if (B == 0) return TDVC_OK;
+  const size_t smem = ((size_t)Cc + (size_t)Ce * 65) * sizeof(float);
+  TDVC_CHECK_ARG(smem <= 48 * 1024);
+  tdvc::launch_k(cond_pack_cl_k, dim3(cdiv(T, 64), B), 256, smem, (cudaStream_t)stream, c, e, (__nv_bfloat16*)cp, Cc, Ce, T, Cg);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }

@@ -58,6 +58,8 @@ def _run_chain(mods, x, c=None):
             else:
                 x = m(x)
         elif isinstance(m, ConditionalInstanceNorm):
+            if isinstance(c, ops.CondParts):
+                c = c.tensor()
             if slope != 1.0:
                 x = ops.leaky_relu(x, slope)
                 slope = 1.0
@@ -70,6 +72,8 @@ def _run_chain(mods, x, c=None):
             if slope != 1.0:
                 x = ops.leaky_relu(x, slope)
                 slope = 1.0
+            if isinstance(c, ops.CondParts) and not isinstance(m, MRFBlock):
+                c = c.tensor()
             x = m(x, c)
         else:
             if slope != 1.0:
@@ -352,6 +356,8 @@ class MRFBlock(nn.Module):
         y = self._fused_stage(x, c)
         if y is not None:
             return y
+        if isinstance(c, ops.CondParts):
+            c = c.tensor()
         gbs = self._fused_cond(c)
         if ops.branch_streams_enabled() and x.is_cuda and len(self.blocks) > 1:
             outs = self._forward_branches_concurrent(x, c, gbs)
@@ -486,7 +492,7 @@ class Decoder(nn.Module):
             curr_scale = 0
             c_var_scales = self.get_scaled_conditioning(c_var)
             # c is time-constant: cat([c.repeat(time), excitation_scale]) is built by one kernel per scale
-            cc = ops.cond_concat(c, c_var_scales[-1])
+            cc = ops.cond_parts(c, c_var_scales[-1])
             mods = list(self.decoder)
             seg_start = 0
             bounds = [i for i in self.upsample_idxs if i < len(mods)]
@@ -496,7 +502,7 @@ class Decoder(nn.Module):
                 if head is not None:
                     subsample_out.append(_run_chain(head, x))
                 curr_scale += 1
-                cc = ops.cond_concat(c, c_var_scales[-1 - curr_scale])
+                cc = ops.cond_parts(c, c_var_scales[-1 - curr_scale])
                 seg_start = b
             x = _run_chain(mods[seg_start:], x, cc)
         if out_subsample:

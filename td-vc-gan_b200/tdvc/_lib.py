@@ -107,6 +107,8 @@ SIGNATURES = {
     "tdvc_contrastive_dir": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
     "tdvc_adamw_multi": (_I, [_P, _P, _P, _P, _P, _I, _L, _F, _F, _F, _F, _F, _I, _F, _P, _P]),
     "tdvc_pack_cl_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _I, _I, _I, _P, _P]),
+    "tdvc_cond_pack_cl": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "tdvc_pack_cl_bf16_masked": (_I, [_P, _P, _F, _P, _I, _I, _I, _I, _P, _P]),
     "tdvc_pack_weight_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "tdvc_conv1d_tc_wgrad_ws": (_L, [_I, _I, _I]),
     "tdvc_conv1d_tc_wgrad": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P]),

@@ -98,6 +98,10 @@ class BucketedReducer:
         self.order = []            # bucket indices in the order they were reduced (tests / diagnostics)
         self.armed = False
         self._handles = [p.register_post_accumulate_grad_hook(self._on_grad) for b in self.buckets for p in b["params"]]
+        import weakref
+        from tdvc import ops
+        self._listener = weakref.WeakMethod(self._on_grad)     # gradients the batched weight-norm backward writes itself
+        ops.grad_deposit_listeners.append(self._listener)
 
     def arm(self):
         """call before the backward pass whose gradients are to be averaged"""
@@ -106,7 +110,7 @@ class BucketedReducer:
         self.works, self.order, self.armed = [], [], True
 
     def _on_grad(self, p):
-        if not self.armed:
+        if not self.armed or id(p) not in self.where:
             return
         bi = self.where[id(p)]
         self.pending[bi] -= 1
@@ -148,6 +152,9 @@ class BucketedReducer:
         for h in self._handles:
             h.remove()
         self._handles = []
+        from tdvc import ops
+        if self._listener in ops.grad_deposit_listeners:
+            ops.grad_deposit_listeners.remove(self._listener)
 
 
 def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None):

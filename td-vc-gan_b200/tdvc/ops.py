@@ -133,6 +133,11 @@ def _wn_multi_forward(t):
     return flat_w, flat_inv
 
 
+# called with every parameter whose .grad _WeightNormMulti.backward has just written (the engine's post-accumulate-grad hooks
+# do not see those deposits); weakref.WeakMethod entries, tdvc.dp.BucketedReducer listens here
+grad_deposit_listeners = []
+
+
 class _WeightNormMulti(torch.autograd.Function):
     """w_j = g_j * v_j / ||v_j|| for every weight of a step scope: one launch forward (all w_j are views of one flat
     buffer), one launch backward (tdvc_weight_norm_bwd_multi) once every dL/dw_j has arrived.
@@ -141,8 +146,8 @@ class _WeightNormMulti(torch.autograd.Function):
     deposits dL/dv_j, dL/dg_j into the parameters' .grad itself (set, or added in place when a gradient is already there --
     what AccumulateGrad does).  Routing ~500 parameter gradients of one node through the engine's AccumulateGrad nodes
     made the engine synchronise the legacy default stream with the capturing stream under CUDA-graph capture (fp32 mode,
-    measured: cudaErrorStreamCaptureImplicit); the per-parameter post-accumulate hooks do not fire for these parameters
-    (tdvc.dp.BucketedReducer.finish() flushes their buckets)."""
+    measured: cudaErrorStreamCaptureImplicit).  The engine's post-accumulate-grad hooks do not fire for these parameters;
+    `grad_deposit_listeners` are called instead."""
 
     @staticmethod
     def forward(ctx, t, live, anchor):
@@ -195,6 +200,16 @@ class _WeightNormMulti(torch.autograd.Function):
                         g.grad = dg
                     else:
                         g.grad.add_(dg)
+            for ref in list(grad_deposit_listeners):
+                fn = ref()
+                if fn is None:                 # its reducer is gone
+                    grad_deposit_listeners.remove(ref)
+                    continue
+                for j in range(n):
+                    if dws[j] is not None:
+                        for p in (vs[j], gs[j]):
+                            if p.requires_grad:
+                                fn(p)
         return None, None, None
 
 
@@ -1217,9 +1232,30 @@ def _pack_act(x, Cp, halo, pad_mode, slope, cache=True, chan_sum=None):
     return xp
 
 
+# bf16 packs of weights that never change (the DFT basis and the mel filterbank of the spectral loss, 13 M elements):
+# packed once per process instead of once per step.  The entry keeps the source alive, so its address stays unique.
+_CONST_PACKS = {}
+
+
+def mark_constant(w):
+    """Declare a conv weight immutable for the life of the process: its tensor-core operand forms are cached."""
+    w._tdvc_const = True
+    return w
+
+
 def _pack_w(w, rows_p, cols_p, transpose_flip):
     Cout, Cin, K = w.shape
     key = None
+    if getattr(w, "_tdvc_const", False):
+        ckey = (w.data_ptr(), tuple(w.shape), rows_p, cols_p, bool(transpose_flip))
+        hit = _CONST_PACKS.get(ckey)
+        if hit is None:
+            wp = torch.empty(K, rows_p, cols_p, device=w.device, dtype=torch.bfloat16)
+            coutp, cinp = (cols_p, rows_p) if transpose_flip else (rows_p, cols_p)
+            _lib.check(_lib.load().tdvc_pack_weight_bf16(_p(w), _p(wp), Cout, Cin, K, coutp, cinp, int(transpose_flip), 0, 0, 0, 0,
+                                                         _st()), "pack_weight_bf16")
+            hit = _CONST_PACKS[ckey] = (w, wp)
+        return hit[1]
     if _step_cache.depth > 0:
         pre = _step_cache.lookup_p(w, rows_p, cols_p, transpose_flip)
         if pre is not None:                        # packed by the scope's batched launch
@@ -1300,22 +1336,31 @@ class _Conv1dTC(torch.autograd.Function):
         B, Cin, Tin = x.shape
         Cout, _, K = w.shape
         Tout = dy.shape[2]
-        if out_act != ACT_NONE:
-            dz = torch.empty_like(dy)
-            _lib.check(lib.tdvc_act_bwd_from_output(_p(dy), _p(y), _p(dz), dy.numel(), out_act, out_slope, _st()), "act_bwd")
-            dy = dz
         dx = dw = db = None
         need_b = ctx.has_bias and ctx.needs_input_grad[2]
         Cdp = _cp(Cout)
         dyp = None
         db_from_wgrad = need_b and ctx.needs_input_grad[1]      # the wgrad GEMM yields it through a tap of ones
-        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+        packs = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        want_dres = ctx.has_res and ctx.needs_input_grad[3]
+        # LeakyReLU layers (every layer of D): the activation's backward is applied inside the pack of dL/dy below
+        mask_in_pack = out_act == ACT_LRELU and packs and not want_dres and not (need_b and not packs)
+        if out_act != ACT_NONE and not mask_in_pack:
+            dz = torch.empty_like(dy)
+            _lib.check(lib.tdvc_act_bwd_from_output(_p(dy), _p(y), _p(dz), dy.numel(), out_act, out_slope, _st()), "act_bwd")
+            dy = dz
+        if packs:
             # one pass over dL/dy: bf16 channels-last copy shared by dgrad and wgrad (+ the bias gradient as column
             # sums when no wgrad follows)
             if need_b and not db_from_wgrad:
                 db = torch.empty(Cout, device=x.device, dtype=torch.float32)
                 need_b = False
-            dyp = _pack_act(dy, Cdp, 0, PAD_ZEROS, 1.0, cache=False, chan_sum=db)
+            if mask_in_pack:
+                dyp = torch.empty(B, Tout, Cdp, device=x.device, dtype=torch.bfloat16)
+                _lib.check(lib.tdvc_pack_cl_bf16_masked(_p(dy), _p(y), out_slope, _p(dyp), B, Cout, Tout, Cdp, _p(db), _st()),
+                           "pack_cl_bf16_masked")
+            else:
+                dyp = _pack_act(dy, Cdp, 0, PAD_ZEROS, 1.0, cache=False, chan_sum=db)
         if ctx.needs_input_grad[0]:
             # dgrad = the same implicit GEMM on dy with channel-swapped, tap-flipped weights
             ph = pad if pad_mode == PAD_REFLECT else 0            # reflect halo kept in the staging buffer
@@ -1560,17 +1605,21 @@ class _GroupedFrameConvTC(torch.autograd.Function):
         Tq = xf.shape[1]
         Cin = xf.shape[2] // stride
         cin_g, K = w.shape[1], w.shape[2]
-        if out_act != ACT_NONE:
-            dz = torch.empty_like(dy)
-            _lib.check(lib.tdvc_act_bwd_from_output(_p(dy), _p(y), _p(dz), dy.numel(), out_act, out_slope, _st()), "act_bwd")
-            dy = dz
         dx = dw = db = None
         need_w = ctx.needs_input_grad[1]
         need_b = ctx.has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[0] or need_w or need_b:
             dyp = torch.empty(B, Tout, Cout, device=dy.device, dtype=torch.bfloat16)
-            _lib.check(lib.tdvc_pack_cl_bf16(_p(dy), _p(dyp), B, Cout, Tout, Cout, 0, PAD_ZEROS, 1.0, None, 0, 0, -1, None, _st()),
-                       "pack dy")
+            if out_act == ACT_LRELU:      # the activation's backward applied inside the pack
+                _lib.check(lib.tdvc_pack_cl_bf16_masked(_p(dy), _p(y), out_slope, _p(dyp), B, Cout, Tout, Cout, None, _st()),
+                           "pack_cl_bf16_masked")
+            else:
+                if out_act != ACT_NONE:
+                    dz = torch.empty_like(dy)
+                    _lib.check(lib.tdvc_act_bwd_from_output(_p(dy), _p(y), _p(dz), dy.numel(), out_act, out_slope, _st()), "act_bwd")
+                    dy = dz
+                _lib.check(lib.tdvc_pack_cl_bf16(_p(dy), _p(dyp), B, Cout, Tout, Cout, 0, PAD_ZEROS, 1.0, None, 0, 0, -1, None,
+                                                 _st()), "pack dy")
         if ctx.needs_input_grad[0]:
             dxf = torch.empty(B, Cin * stride, Tq, device=dy.device, dtype=torch.float32)
             _tc_conv(xp=dyp, wp=wtp, y=dxf, B=B, Tp=Tout, Tout=Tq, K=m, dilation=1, t_off=-(m - 1), Cp_total=Cout, groups=nb,
@@ -1613,10 +1662,17 @@ def wgrad2(*, dyp, xp, B, Cdp, Tout, Cp, Tp, Cout, Cin, K, dilation, ngroups=1, 
     _lib.check(lib.tdvc_conv1d_tc_wgrad2(C.byref(c), _st()), "conv1d_tc_wgrad2")
 
 
-def _cond_path_forward(c, slope, w0s, b0s, w2s, b2s):
-    """gamma|beta of all n FiLM blocks of a stage: gb[n, B, 2C, T] fp32 and what the backward needs (see _MRFCondPath)."""
+def _cond_path_forward(c, slope, w0s, b0s, w2s, b2s, parts=None):
+    """gamma|beta of all n FiLM blocks of a stage: gb[n, B, 2C, T] fp32 and what the backward needs (see _MRFCondPath).
+    parts = (speaker code [B, Cs], excitation [B, Ce, T]): the conditioning cat([code over time, excitation]) given as its
+    two sources (c is None); the packed operand is then written from them directly."""
     n = len(w0s)
-    B, Cc, T = c.shape
+    if parts is not None:
+        B, T = parts[1].shape[0], parts[1].shape[2]
+        Cc = parts[0].shape[1] + parts[1].shape[1]
+        c = parts[1]
+    else:
+        B, Cc, T = c.shape
     K = w0s[0].shape[2]
     C2 = w2s[0].shape[0]
     if K != 3 or any(tuple(w.shape) != (Cc, Cc, 3) for w in w0s) or any(tuple(w.shape) != (C2, Cc, 3) for w in w2s):
@@ -1627,7 +1683,11 @@ def _cond_path_forward(c, slope, w0s, b0s, w2s, b2s):
     C2p = _ceil(C2, 16)
     # operands
     cp = torch.empty(B, T, Cg, device=dev, dtype=torch.bfloat16)
-    _lib.check(lib.tdvc_pack_cl_bf16(_p(c), _p(cp), B, Cc, T, Cg, 0, PAD_ZEROS, 1.0, None, 0, Cg, Cc, None, _st()), "pack c")
+    if parts is not None:
+        _lib.check(lib.tdvc_cond_pack_cl(_p(parts[0]), _p(parts[1]), _p(cp), B, parts[0].shape[1], parts[1].shape[1], T, Cg, _st()),
+                   "cond_pack_cl")
+    else:
+        _lib.check(lib.tdvc_pack_cl_bf16(_p(c), _p(cp), B, Cc, T, Cg, 0, PAD_ZEROS, 1.0, None, 0, Cg, Cc, None, _st()), "pack c")
     # cond_var.0 weights: stacked densely (pitch Cc, kernel with the weights as the M operand) when they fit, else at
     # the padded pitch Cg of the time-as-M kernels.  Blocks are packed in order: block j+1 overwrites the Cg - Cc
     # zero rows block j's pack wrote past its end.
@@ -1849,12 +1909,12 @@ class _MRFStage(torch.autograd.Function):
     reflect-fold / mask passes do not exist here."""
 
     @staticmethod
-    def forward(ctx, x, c, slope, cond_slope, ks, ds, *wb):
+    def forward(ctx, x, c, e, slope, cond_slope, ks, ds, *wb):
         G, D = len(ks), len(ds)
         has_cond = c is not None
         per = 8 if has_cond else 4
         assert len(wb) == per * G * D
-        _req(x, c, *wb)
+        _req(x, c, e, *wb)
         x = _c(x)
         B, Cc_x, T = x.shape
         Cx = Cc_x
@@ -1865,13 +1925,22 @@ class _MRFStage(torch.autograd.Function):
         blk = lambda i, j: wb[per * (i * D + j): per * (i * D + j + 1)]
         # ---- conditioning path: gamma|beta of every block, block index i*D + j
         gb = cdims = cp = g1p = None
+        ctx.cond_parts = None
         if has_cond:
             c = _c(c)
             w0s = [blk(i, j)[4] for i in range(G) for j in range(D)]
             b0s = [blk(i, j)[5] for i in range(G) for j in range(D)]
             w2s = [blk(i, j)[6] for i in range(G) for j in range(D)]
             b2s = [blk(i, j)[7] for i in range(G) for j in range(D)]
-            gb, cdims, cp, g1p = _cond_path_forward(c, cond_slope, w0s, b0s, w2s, b2s)
+            if e is not None:
+                # c = speaker code [B, Cs], e = excitation level [B, Ce, T]: the conditioning tensor is never built in fp32
+                e = _c(e)
+                if c.dim() != 2 or e.dim() != 3 or c.shape[0] != e.shape[0] or e.shape[2] != T:
+                    raise RuntimeError(f"mrf_stage: conditioning parts {tuple(c.shape)}, {tuple(e.shape)} do not match x {tuple(x.shape)}")
+                ctx.cond_parts = (c.shape[1], e.shape[1])
+                gb, cdims, cp, g1p = _cond_path_forward(None, cond_slope, w0s, b0s, w2s, b2s, parts=(c, e))
+            else:
+                gb, cdims, cp, g1p = _cond_path_forward(c, cond_slope, w0s, b0s, w2s, b2s)
         gb_blk = B * 2 * Cx * T                                      # elements of one block's gamma|beta
         # ---- operands of the chain (once per step scope)
         wconv, wpos = [], []
@@ -2023,20 +2092,55 @@ class _MRFStage(torch.autograd.Function):
         if has_cond:
             has_b0 = [ctx.has_bias[gi(i, j) + 5] for i in range(G) for j in range(D)]
             has_b2 = [ctx.has_bias[gi(i, j) + 7] for i in range(G) for j in range(D)]
-            dc, cg = _cond_path_backward(cdims, cp, g1p, w0s, w2s, has_b0, has_b2, dgbp, need[1])
+            dc, cg = _cond_path_backward(cdims, cp, g1p, w0s, w2s, has_b0, has_b2, dgbp, need[1] or need[2])
             for b_ in range(n):
                 grads[per * b_ + 4: per * b_ + 8] = cg[4 * b_: 4 * b_ + 4]
-        return (dx, dc, None, None, None, None, *grads)
+        de = None
+        if ctx.cond_parts is not None and dc is not None:
+            # conditioning given as (speaker code, excitation): time-sum / split of dL/dc (what cond_concat's backward does)
+            Cs, Ce = ctx.cond_parts
+            dfull = dc
+            dc = torch.empty(B, Cs, device=dev, dtype=torch.float32)
+            de = torch.empty(B, Ce, T, device=dev, dtype=torch.float32) if need[2] else None
+            _lib.check(lib.tdvc_cond_concat_bwd(_p(dfull), _p(dc), _p(de), B, Cs, Ce, T, 1, _st()), "cond_concat_bwd")
+        return (dx, dc, de, None, None, None, None, *grads)
+
+
+class CondParts:
+    """The decoder's conditioning cat([c.unsqueeze(2).repeat(1, 1, T), e], dim=1) (model/generator.py:387-399) kept as its two
+    sources -- speaker code c[B, Cs], excitation level e[B, Ce, T] -- so that the bf16 whole-stage path can write its packed
+    operand from them directly; .tensor() builds (once) the fp32 tensor every other consumer gets."""
+
+    def __init__(self, c, e):
+        self.c, self.e = c, e
+        self._full = None
+        self.shape = (e.shape[0], c.shape[1] + e.shape[1], e.shape[2])
+        self.ndim = 3
+
+    def tensor(self):
+        if self._full is None:
+            self._full = cond_concat(self.c, self.e)
+        return self._full
+
+
+def cond_parts(c, e):
+    """cond_concat(c, e), lazily: a CondParts where the whole-stage path can consume the parts, else the tensor."""
+    if _PRECISION == "bf16" and _MRF_CHAIN and e.is_cuda and c.dim() == 2 and e.dim() == 3:
+        return CondParts(c, e)
+    return cond_concat(c, e)
 
 
 def mrf_stage(x, c, blocks, kernel_sizes, dilations, slope=0.2, cond_slope=0.2):
     """blocks[i][j] = (conv_w, conv_b, pos_w, pos_b[, cv0_w, cv0_b, cv2_w, cv2_b]): effective (weight-normed) weights of the
-    FiLM block of kernel size i / dilation j."""
+    FiLM block of kernel size i / dilation j.  c: the conditioning tensor [B, Cc, T], a CondParts, or None."""
     flat = []
     for row in blocks:
         for blk in row:
             flat += list(blk)
-    return _MRFStage.apply(x, c, float(slope), float(cond_slope), tuple(int(k) for k in kernel_sizes),
+    e = None
+    if isinstance(c, CondParts):
+        c, e = c.c, c.e
+    return _MRFStage.apply(x, c, e, float(slope), float(cond_slope), tuple(int(k) for k in kernel_sizes),
                            tuple(int(d) for d in dilations), *flat)
 
 

@@ -78,7 +78,7 @@ def _dft_basis(n_fft, device, split):
         hi = B.to(torch.bfloat16).float()
         lo = (B - hi).to(torch.bfloat16).float()
         B = torch.cat([hi, hi, lo], dim=1)
-    return B.unsqueeze(2).contiguous().to(device), nfreq, nfreq
+    return ops.mark_constant(B.unsqueeze(2).contiguous().to(device)), nfreq, nfreq
 
 
 @functools.lru_cache(maxsize=None)
@@ -91,7 +91,7 @@ def _mel_weight(n_fft, device, split):
         hi = W.to(torch.bfloat16).float()
         lo = (W - hi).to(torch.bfloat16).float()
         W = torch.cat([hi, hi, lo], dim=1)
-    return W.unsqueeze(2).contiguous()
+    return ops.mark_constant(W.unsqueeze(2).contiguous())
 
 
 def _log_mel(signal, n_fft):

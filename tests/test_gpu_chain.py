@@ -167,6 +167,37 @@ def test_mrf_stage_chain(case):
     assert not bad, bad
 
 
+def test_mrf_stage_conditioning_parts():
+    """Conditioning handed over as (speaker code, excitation) -- tdvc_cond_pack_cl writes the packed operand, the fp32
+    cat([code over time, excitation]) tensor is never built -- against the same stage fed the concatenated tensor: identical
+    output (the packed operands are the same bits), gradients of the parts = time-sum / slice of the tensor's gradient."""
+    from tdvc import ops
+    B, C, T, Cs, Ce, ks, ds = 2, 16, 300, 16, 8, (3, 7, 11), (1, 3, 5)
+    x = rnd(B, C, T, seed=1)
+    code, exc = rnd(B, Cs, seed=2), rnd(B, Ce, T, seed=3)
+    blocks = make_blocks(C, Cs + Ce, ks, ds, seed=100)
+    proj = rnd(B, C, T, seed=4).float().cuda()
+    res = []
+    for parts in (False, True):
+        xd = x.float().cuda().requires_grad_(True)
+        cd, ed = code.float().cuda().requires_grad_(True), exc.float().cuda().requires_grad_(True)
+        bd = [[[dev(w) for w in blk] for blk in row] for row in blocks]
+        if parts:
+            cond = ops.CondParts(cd, ed)
+        else:
+            cond = torch.cat([cd.unsqueeze(2).repeat(1, 1, T), ed], dim=1)
+        y = ops.mrf_stage(xd, cond, bd, ks, ds, slope=0.2, cond_slope=0.2)
+        (y * proj).sum().backward()
+        torch.cuda.synchronize()
+        res.append((y.detach(), xd.grad, cd.grad, ed.grad, [w.grad for row in bd for blk in row for w in blk]))
+    (y0, dx0, dc0, de0, g0), (y1, dx1, dc1, de1, g1) = res
+    assert torch.equal(y0, y1)
+    assert relerr(dx1, dx0) < 1e-6
+    assert relerr(de1, de0) < 1e-6 and relerr(dc1, dc0) < 1e-5, (relerr(de1, de0), relerr(dc1, dc0))
+    for a, b in zip(g0, g1):
+        assert relerr(b, a) < 1e-5          # split-K atomics: summation order differs from run to run
+
+
 def test_mrf_stage_chain_matches_block_path_in_generator():
     """The Generator with the whole-stage path switched on and off: same waveform and gradient norms within bf16 noise."""
     import numpy as np

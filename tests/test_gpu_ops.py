@@ -48,6 +48,13 @@ CONV_CASES = [
     (1, 3, 31, 5, 5, 1, 2, 1, 1, True, 0.2, None, True, False),           # ragged tiny
     (2, 256, 28, 256, 7, 1, 3, 1, 1, False, 0.2, None, True, False),      # encoder.18 (T/320)
     (2, 16, 1000, 16, 11, 1, 25, 5, 1, True, 0.2, None, True, False),     # multi-tile reflect both ends
+    # the excitation pyramid (narrow_wgrad_k): 8 -> 8 channels
+    (2, 8, 2600, 8, 4, 2, 1, 1, 1, False, 1.0, None, True, False),        # block.0, r = 2, two chunks
+    (3, 8, 1300, 8, 5, 1, 2, 1, 1, False, 0.2, None, True, True),         # block.2/4, k5 'same' + shortcut residual
+    (2, 8, 2400, 8, 16, 8, 4, 1, 1, False, 1.0, None, True, False),       # block.0, r = 8, 256-step chunks
+    (2, 8, 2000, 8, 20, 10, 5, 1, 1, False, 1.0, None, True, False),      # block.0, r = 10
+    (2, 8, 2500, 8, 1, 1, 0, 1, 1, False, 1.0, None, True, False),        # shortcut 1x1
+    (2, 64, 1100, 1, 7, 1, 3, 1, 1, True, 0.2, "tanh", True, False),      # sub-scale head from 64 channels
 ]
 
 
