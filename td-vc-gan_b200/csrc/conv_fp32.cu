@@ -555,7 +555,13 @@ __global__ void __launch_bounds__(256) stem_wgrad_k(const float* __restrict__ dy
   float* dys = sm + ((span + 3) & ~3);         // [Cout][STEM_SUB + 1]
   const int b = blockIdx.y, t0 = blockIdx.x * STEM_TT;
   const float* xrow = x + (long long)b * T;
-  for (int i = threadIdx.x; i < span; i += 256) xs[i] = fetch_padded(xrow, t0 + i - pad, T, pad_mode, in_slope);
+  for (int base = threadIdx.x; base < span; base += 256 * 4) {      // 4 loads in flight per thread
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = base + 256 * u < span ? fetch_padded(xrow, t0 + base + 256 * u - pad, T, pad_mode, in_slope) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) if (base + 256 * u < span) xs[base + 256 * u] = v[u];
+  }
   const int npairs = Cout * K;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};         // pairs p, p + 256, ... (Cout * K <= 1024)
   float bsum = 0.f;                            // threads < Cout: bias gradient of channel threadIdx.x
@@ -563,9 +569,20 @@ __global__ void __launch_bounds__(256) stem_wgrad_k(const float* __restrict__ dy
   for (int s0 = 0; s0 < tend; s0 += STEM_SUB) {
     const int ns = min(STEM_SUB, tend - s0);
     __syncthreads();
-    for (int i = threadIdx.x; i < Cout * STEM_SUB; i += 256) {
-      const int co = i / STEM_SUB, t = i - co * STEM_SUB;
-      dys[co * (STEM_SUB + 1) + t] = t < ns ? __ldg(dy + ((long long)b * Cout + co) * T + t0 + s0 + t) : 0.f;
+    for (int base = threadIdx.x; base < Cout * STEM_SUB; base += 256 * 8) {      // 8 loads in flight per thread
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = base + 256 * u;
+        const int co = i / STEM_SUB, t = i - co * STEM_SUB;
+        v[u] = (i < Cout * STEM_SUB && t < ns) ? __ldg(dy + ((long long)b * Cout + co) * T + t0 + s0 + t) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = base + 256 * u;
+        const int co = i / STEM_SUB, t = i - co * STEM_SUB;
+        if (i < Cout * STEM_SUB) dys[co * (STEM_SUB + 1) + t] = v[u];
+      }
     }
     __syncthreads();
 #pragma unroll
@@ -613,9 +630,21 @@ __global__ void __launch_bounds__(256) narrow_wgrad_k(const float* __restrict__ 
   const int b = blockIdx.y, t0 = blockIdx.x * TT;
   const float* xb = x + (long long)b * Cin * Tin;
   const int g0 = t0 * stride - pad;
-  for (int i = threadIdx.x; i < Cin * span; i += 256) {
-    const int ci = i / span, j = i - ci * span;
-    xs[ci * spanp + j] = fetch_padded(xb + (long long)ci * Tin, g0 + j, Tin, pad_mode, in_slope);
+  // 8 independent loads in flight per thread: with a handful of warps per SM a load-then-store loop is latency bound
+  for (int base = threadIdx.x; base < Cin * span; base += 256 * 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = base + 256 * u;
+      const int ci = i / span, j = i - ci * span;
+      v[u] = i < Cin * span ? fetch_padded(xb + (long long)ci * Tin, g0 + j, Tin, pad_mode, in_slope) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = base + 256 * u;
+      const int ci = i / span, j = i - ci * span;
+      if (i < Cin * span) xs[ci * spanp + j] = v[u];
+    }
   }
   const int npairs = Cout * Cin * K, cik = Cin * K;
   float acc[NARROW_ACC];
@@ -633,9 +662,20 @@ __global__ void __launch_bounds__(256) narrow_wgrad_k(const float* __restrict__ 
   for (int s0 = 0; s0 < tend; s0 += NARROW_SUB) {
     const int ns = min(NARROW_SUB, tend - s0);
     __syncthreads();
-    for (int i = threadIdx.x; i < Cout * NARROW_SUB; i += 256) {
-      const int co = i / NARROW_SUB, t = i - co * NARROW_SUB;
-      dys[co * (NARROW_SUB + 1) + t] = t < ns ? __ldg(dy + ((long long)b * Cout + co) * Tout + t0 + s0 + t) : 0.f;
+    for (int base = threadIdx.x; base < Cout * NARROW_SUB; base += 256 * 4) {
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + 256 * u;
+        const int co = i / NARROW_SUB, t = i - co * NARROW_SUB;
+        v[u] = (i < Cout * NARROW_SUB && t < ns) ? __ldg(dy + ((long long)b * Cout + co) * Tout + t0 + s0 + t) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + 256 * u;
+        const int co = i / NARROW_SUB, t = i - co * NARROW_SUB;
+        if (i < Cout * NARROW_SUB) dys[co * (NARROW_SUB + 1) + t] = v[u];
+      }
     }
     __syncthreads();
 #pragma unroll
@@ -643,9 +683,16 @@ __global__ void __launch_bounds__(256) narrow_wgrad_k(const float* __restrict__ 
       if (threadIdx.x + 256 * q < npairs) {
         const float* dr = dys + doff[q];
         const float* xr = xs + xoff[q] + s0 * stride;
-        float a = acc[q];
-        for (int t = 0; t < ns; ++t) a = fmaf(dr[t], xr[t * stride], a);
-        acc[q] = a;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;      // four chains: the sum is not bound by the FMA latency
+        int t = 0;
+        for (; t + 4 <= ns; t += 4) {
+          a0 = fmaf(dr[t], xr[t * stride], a0);
+          a1 = fmaf(dr[t + 1], xr[(t + 1) * stride], a1);
+          a2 = fmaf(dr[t + 2], xr[(t + 2) * stride], a2);
+          a3 = fmaf(dr[t + 3], xr[(t + 3) * stride], a3);
+        }
+        for (; t < ns; ++t) a0 = fmaf(dr[t], xr[t * stride], a0);
+        acc[q] += (a0 + a1) + (a2 + a3);
       }
     }
     if (db && threadIdx.x < Cout) {
@@ -661,13 +708,15 @@ __global__ void __launch_bounds__(256) narrow_wgrad_k(const float* __restrict__ 
   if (db && threadIdx.x < Cout) atomicAdd(db + threadIdx.x, bsum);
 }
 
-// chunk length of narrow_wgrad_k: the largest of 1024 .. 128 whose shared-memory tiles fit 160 KB; 0 = none does
+// chunk length of narrow_wgrad_k (512 .. 128 time steps); 0 = no chunk fits
 static int narrow_wgrad_tt(int Cin, int Cout, int K, int stride, int dil, size_t* smem) {
-  for (int TT = 1024; TT >= 128; TT >>= 1) {
-    const int span = (TT - 1) * stride + (K - 1) * dil + 1;
-    const size_t need = ((size_t)((Cin * (span | 1) + 3) & ~3) + (size_t)Cout * (NARROW_SUB + 1)) * sizeof(float);
-    if (need <= 160 * 1024) { *smem = need; return TT; }
-  }
+  // first choice: tiles of <= 40 KB (several CTAs per SM hide the staging latency); else whatever fits 160 KB
+  for (size_t budget : {(size_t)40 * 1024, (size_t)160 * 1024})
+    for (int TT = 512; TT >= 128; TT >>= 1) {
+      const int span = (TT - 1) * stride + (K - 1) * dil + 1;
+      const size_t need = ((size_t)((Cin * (span | 1) + 3) & ~3) + (size_t)Cout * (NARROW_SUB + 1)) * sizeof(float);
+      if (need <= budget) { *smem = need; return TT; }
+    }
   return 0;
 }
 

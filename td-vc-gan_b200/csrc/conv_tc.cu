@@ -25,6 +25,9 @@ namespace tdvc {
 struct TcP {
   int B, Tout, Cout, K, dil, t_off;          // Cout = valid output channels per group
   int nchunk, last_nk16, BN, stages, tmem_cols;
+  // weight-stationary kernel, narrow tiles: the 16 epilogue warps form 4 / epi_spt teams of epi_spt column sets; team k takes
+  // the CTA's tiles k, k + teams, ... and nacc = 2 * teams accumulators are in flight (0 = one team of 4 sets, 2 accumulators)
+  int epi_spt, nacc;
   int out_act;
   float out_slope;
   const float* bias;
@@ -93,6 +96,8 @@ __device__ __forceinline__ void mask16_bf16(const __nv_bfloat16* mp, float* v, f
   }
 }
 
+__device__ __forceinline__ int epi_spt_of(const TcP& p) { return p.epi_spt > 0 ? p.epi_spt : TC_EPI_WARPS / 4; }
+
 // Epilogues of the bf16-resident MRF stage (model/generator.py:69-111,175-194).  Every group is one kernel-size branch; all
 // tensors between the convolutions are bf16 channels-last with the branches side by side in the channel dimension, the
 // residual stream stays fp32 NCW [branch][B][C][T].  Channel counts are multiples of 16 (a thread's 16 columns are real).
@@ -107,7 +112,7 @@ __device__ __forceinline__ void tc_epilogue_chain(const TcP& p, const float* bia
   const int t = t0 + q * 32 + lane;
   const bool t_ok = t < p.Tout;
   const int nvalid = min(p.BN, p.Cout - n0);
-  for (int c0 = half * 16; c0 < nvalid; c0 += 16 * (TC_EPI_WARPS / 4)) {
+  for (int c0 = (half % epi_spt_of(p)) * 16; c0 < nvalid; c0 += 16 * epi_spt_of(p)) {
     float v[16];
     tmem_ld16(acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
     if (!t_ok) continue;
@@ -212,7 +217,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcP& p, const float* bias
     const bool t_ok = t < p.Tout;
     const long long ct = p.Tout;
     const int nvalid = min(p.BN, p.Cout - n0);          // columns of this tile that are real channels
-    for (int c0 = half * 16; c0 < nvalid; c0 += 16 * (TC_EPI_WARPS / 4)) {
+    for (int c0 = (half % epi_spt_of(p)) * 16; c0 < nvalid; c0 += 16 * epi_spt_of(p)) {
       float v[16];
       if (p.debug & 4) {
 #pragma unroll
@@ -444,9 +449,10 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) conv_tc_ws_k(const __grid_c
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* fulln_bar = empty_bar + p.stages;
   uint64_t* emptyn_bar = fulln_bar + w.n_stages;
-  uint64_t* tmem_full = emptyn_bar + w.n_stages;   // [2]
-  uint64_t* tmem_empty = tmem_full + 2;            // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  const int spt = epi_spt_of(p), nteams = (TC_EPI_WARPS / 4) / spt, nacc = p.nacc > 0 ? p.nacc : 2;
+  uint64_t* tmem_full = emptyn_bar + w.n_stages;   // [nacc]
+  uint64_t* tmem_empty = tmem_full + nacc;         // [nacc]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + nacc);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int grp, n0, cta_i, cta_n;          // this CTA's group / N tile, and its position among the CTAs that share them
@@ -477,9 +483,9 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) conv_tc_ws_k(const __grid_c
       mbar_init(&fulln_bar[s], 1);
       mbar_init(&emptyn_bar[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < nacc; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], TC_EPI_WARPS);          // one arrival per epilogue warp
+      mbar_init(&tmem_empty[a], 4 * spt);               // one arrival per epilogue warp of the team that drains it
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -540,9 +546,9 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) conv_tc_ws_k(const __grid_c
     const uint32_t tapn_step16 = (uint32_t)p.dil * 2u;                   // dil rows x 32 B
     int it = 0, itn = 0, i = 0;
     for (int m = cta_i; m < w.n_mtiles; m += cta_n, ++i) {
-      const int acc = i & 1;
+      const int acc = i % nacc;
       const uint32_t d_addr = tmem_base + (uint32_t)(acc * p.BN);
-      mbar_wait(&tmem_empty[acc], ((uint32_t)(i >> 1) & 1u) ^ 1u);
+      mbar_wait(&tmem_empty[acc], ((uint32_t)(i / nacc) & 1u) ^ 1u);
       tc_fence_after();
       for (int ck = 0; ck < nfull; ++ck, ++it) {
         const int s = it % p.stages;
@@ -593,11 +599,13 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) conv_tc_ws_k(const __grid_c
   } else {
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
+    const int team = half / spt;
     int i = 0;
     for (int m = cta_i; m < w.n_mtiles; m += cta_n, ++i) {
+      if (i % nteams != team) continue;               // another team's tile
       const int b = m / w.mtiles_per_b, t0 = (m - b * w.mtiles_per_b) * TC_BM;
-      const int acc = i & 1;
-      mbar_wait(&tmem_full[acc], (uint32_t)(i >> 1) & 1u);
+      const int acc = i % nacc;
+      mbar_wait(&tmem_full[acc], (uint32_t)(i / nacc) & 1u);
       tc_fence_after();
       if (!(p.debug & 32))
         tc_epilogue_tile<ACT, EPI, OUT, MASK>(p, bias_s, tmem_base + (uint32_t)(acc * p.BN), b, t0, grp, n0, q, half, lane);
@@ -1614,10 +1622,16 @@ extern "C" int tdvc_conv1d_tc_fwd_ex(const tdvc_tc_conv* c, void* stream) {
         if (cap >= 2) st = std::min(st, cap);
       }
       p.stages = st;
+      // narrow tiles (the 16 / 32-channel MRF stages): one tile's epilogue occupies 4 / 8 of the 16 epilogue warps and is a
+      // chain of dependent memory round trips (~2.5 us measured), so several tiles are drained at once by separate warp teams
+      static int teams_on = -1;     // TDVC_TC_EPI_TEAMS=0: development switch, one team as before
+      if (teams_on < 0) { const char* e = getenv("TDVC_TC_EPI_TEAMS"); teams_on = e ? atoi(e) : 1; }
+      p.epi_spt = !teams_on ? 4 : (p.BN <= 16 ? 1 : (p.BN <= 32 ? 2 : 4));
+      p.nacc = 2 * (4 / p.epi_spt);
       int cols2 = 32;
-      while (cols2 < 2 * p.BN) cols2 <<= 1;
+      while (cols2 < p.nacc * p.BN) cols2 <<= 1;
       p.tmem_cols = cols2;
-      size_t smem_ws = (size_t)fixed + (size_t)st * a_stage + (2 * st + 2 * n_stages + 5) * sizeof(uint64_t) + 16 + 1024;
+      size_t smem_ws = (size_t)fixed + (size_t)st * a_stage + (2 * st + 2 * n_stages + 2 * p.nacc + 1) * sizeof(uint64_t) + 16 + 1024;
       typedef void (*WsFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, TcP, WsP);
       WsFn kern = nullptr;
       if (chain == 3) kern = conv_tc_ws_k<1, 3, 1, 0>;
