@@ -206,7 +206,8 @@ int tdvc_pack_cl_bf16(const float* x, void* xp, int B, int C, int T, int Cp /* r
  *      cp[B, T, Cg] bf16, channel Cc+Ce = 1 (bias-gradient channel), zeros up to Cg. */
 int tdvc_cond_pack_cl(const float* c, const float* e, void* cp, int B, int Cc, int Ce, int T, int Cg, void* stream);
 int tdvc_pack_cl_bf16_masked(const float* dy, const float* y /* the layer's output, same shape */, float slope, void* dyp,
-                             int B, int C, int T, int Cp, float* chan_sum /* optional [C], OVERWRITTEN */, void* stream);
+                             int B, int C, int T, int Cp, int halo /* zero rows on both sides: dyp[B, T + 2*halo, Cp] */,
+                             float* chan_sum /* optional [C], OVERWRITTEN */, void* stream);
 /* w[Cout,Cin,K] fp32 -> wp[K, Coutp, Cinp] bf16 (zero padded); transpose_flip!=0 produces the
  * dgrad operand wp[K, Cinp, Coutp] with taps reversed. */
 int tdvc_pack_weight_bf16(const float* w, void* wp, int Cout, int Cin, int K, int Coutp, int Cinp,
@@ -263,6 +264,17 @@ typedef struct tdvc_tc_conv {
   float* halo_buf;
   int32_t halo, t_valid;
   float pk_slope;
+  /* unframe_s > 0 (fp32 output, no chain mode): the launch is the data gradient of a Conv1d(k, stride = s, padding = pad)
+   * run over frames (tdvc_frame_pack_bf16): output channel f of row q is sample u = s*q + f % s - unframe_pad of channel f / s,
+   * written to y[b, f / s, u] of a [B, unframe_C, unframe_T] tensor (rows outside [0, unframe_T) are dropped) -- the
+   * inverse frame view in the epilogue instead of tdvc_frame_unpack.  s must divide 16. */
+  int32_t unframe_s, unframe_pad, unframe_T, unframe_C;
+  /* flat_tp > 0 (fp32 output, groups = 1, no chain / mask / residual): short sequences run batch-flattened -- the packed input
+   * [B_real, flat_tp, Cp] with flat_halo zero rows on both sides of every sample is handed over as ONE sequence (B = 1,
+   * Tp = Tout = B_real * flat_tp), so a 128-row tile holds several samples instead of one sample's 9 .. 35 time steps (the
+   * discriminator's 1024-channel tail, model/discriminator.py:31-38, and the T/320 convs of the generator); output row r is
+   * time step r % flat_tp - flat_halo of sample r / flat_tp and is stored to y[B_real, Cout_g, flat_T] when inside [0, flat_T). */
+  int32_t flat_tp, flat_halo, flat_T;
 } tdvc_tc_conv;
 int tdvc_conv1d_tc_fwd_ex(const tdvc_tc_conv* c, void* stream);
 /* after a chain_mode 6 launch: y[g][b][c][mirror(r)] += halo_buf[g][b][c][r] for the 2*halo reflect rows r of every

@@ -53,6 +53,8 @@ struct TcP {
   float* halo_buf;                            // EPI 6: contributions that fall on reflect-halo rows [grp][B][Cout][2*halo]
   int halo, t_valid;
   float pk_slope;                             // EPI 4: LeakyReLU slope of the packed copy
+  int unframe_s, unframe_pad, unframe_T, unframe_C;   // fp32 output through the inverse frame view (see tdvc_tc_conv)
+  int flat_tp, flat_halo, flat_T;                     // batch-flattened short sequences (see tdvc_tc_conv)
   // weight-stationary kernel, groups with different tap counts: CTAs are dealt out in proportion to the taps (the k = 11
   // branch gets 11/21 of them instead of a third); group g owns CTAs [grp_cta0[g], grp_cta0[g+1]) of a 1-D grid
   int balanced;
@@ -248,7 +250,48 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcP& p, const float* bias
             if ((h & 0x8000u) || (h & 0x7FFFu) == 0) v[j] *= p.mask_slope;
           }
         }
-        if (OUT == 0) {
+        if (OUT == 0 && p.flat_tp > 0) {
+          // batch-flattened rows: t is a row of the concatenated padded samples
+          const int bb = t / p.flat_tp, tt = t - bb * p.flat_tp - p.flat_halo;
+          if (tt >= 0 && tt < p.flat_T) {
+            float* yp = p.y + ((long long)bb * p.Cout + n0 + c0) * p.flat_T + tt;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (j < nj) {
+                float o = v[j];
+                if (ACT == TDVC_ACT_LRELU) o = o > 0.f ? o : o * p.out_slope;
+                else if (ACT == TDVC_ACT_TANH) o = tanhf(o);
+                *yp = o;
+              }
+              yp += p.flat_T;
+            }
+          }
+        } else if (OUT == 0 && p.unframe_s > 0) {
+          // data gradient of a strided conv run over frames: this thread's 16 frame channels are 16 / s conv channels x s
+          // consecutive samples
+          const int s = p.unframe_s;
+          const int f0 = grp * p.Cout + n0 + c0;
+          const int u0 = s * t - p.unframe_pad;
+          // whole frames inside the signal and 16-byte aligned rows: vector stores (a warp writes 32 consecutive frames of
+          // one channel = one contiguous run); scalar stores at the edges
+          const bool vec = (s % 4 == 0) && (p.unframe_T % 4 == 0) && (p.unframe_pad % 4 == 0) && u0 >= 0 && u0 + s <= p.unframe_T;
+#pragma unroll
+          for (int j0 = 0; j0 < 16; j0 += 4) {
+            if (j0 >= nj) break;
+            float* dst = p.y + ((long long)b * p.unframe_C + (f0 + j0) / s) * p.unframe_T + u0 + (j0 % s);
+            if (vec) {
+              *reinterpret_cast<float4*>(dst) = make_float4(v[j0], v[j0 + 1], v[j0 + 2], v[j0 + 3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int jj = j0 + e;                                     // frame channel f0 + jj: conv channel, phase
+                const int u = u0 + jj % s;
+                if (jj < nj && u >= 0 && u < p.unframe_T)
+                  p.y[((long long)b * p.unframe_C + (f0 + jj) / s) * p.unframe_T + u] = v[jj];
+              }
+            }
+          }
+        } else if (OUT == 0) {
           const long long base = (long long)grp * p.y_grp_stride + (long long)b * p.y_b_stride + (long long)(n0 + c0) * ct + t;
           float* yp = p.y + base;
           const float* rp = p.res + base;                                   // only dereferenced when EPI asks for it
@@ -1398,9 +1441,9 @@ extern "C" int tdvc_pack_cl_bf16(const float* x, void* xp, int B, int C, int T, 
 }
 
 extern "C" int tdvc_pack_cl_bf16_masked(const float* dy, const float* y, float slope, void* dyp, int B, int C, int T, int Cp,
-                                        float* chan_sum, void* stream) {
+                                        int halo, float* chan_sum, void* stream) {
   TDVC_CHECK_ARG(y != nullptr);
-  return pack_cl_bf16_launch(dy, dyp, B, C, T, Cp, 0, TDVC_PAD_ZEROS, 1.f, chan_sum, 0, 0, -1, nullptr, y, slope, stream);
+  return pack_cl_bf16_launch(dy, dyp, B, C, T, Cp, halo, TDVC_PAD_ZEROS, 1.f, chan_sum, 0, 0, -1, nullptr, y, slope, stream);
 }
 
 extern "C" int tdvc_cond_pack_cl(const float* c, const float* e, void* cp, int B, int Cc, int Ce, int T, int Cg, void* stream) {
@@ -1589,6 +1632,17 @@ extern "C" int tdvc_conv1d_tc_fwd_ex(const tdvc_tc_conv* c, void* stream) {
   const int epi = c->gb ? 2 : (c->residual ? 1 : 0);
   const int act = c->out_act;
   const bool mask = c->maskp != nullptr;
+  if (c->unframe_s > 0) {
+    TDVC_CHECK_ARG(!chain && !c->out_packed && !mask && epi == 0 && act == TDVC_ACT_NONE && 16 % c->unframe_s == 0 &&
+                   c->Cout_g % 16 == 0 && c->unframe_T > 0 && c->unframe_C > 0 &&
+                   (long long)c->groups * c->Cout_g == (long long)c->unframe_C * c->unframe_s);
+    p.unframe_s = c->unframe_s; p.unframe_pad = c->unframe_pad; p.unframe_T = c->unframe_T; p.unframe_C = c->unframe_C;
+  }
+  if (c->flat_tp > 0) {
+    TDVC_CHECK_ARG(!chain && !c->out_packed && !mask && epi == 0 && c->groups == 1 && c->B == 1 && c->unframe_s == 0 &&
+                   c->flat_halo >= 0 && c->flat_T > 0 && c->flat_T + c->flat_halo <= c->flat_tp && c->Tout % c->flat_tp == 0);
+    p.flat_tp = c->flat_tp; p.flat_halo = c->flat_halo; p.flat_T = c->flat_T;
+  }
   // ---- weight-stationary persistent variant when the whole weight tile set fits next to an activation ring
   {
     static int ws_on = -1;

@@ -35,7 +35,9 @@ class TcConv(C.Structure):
                 ("chain_mode", C.c_int32), ("kg", C.c_int32 * 4), ("gb_grp_stride", C.c_int64), ("res_grp_stride", C.c_int64),
                 ("yp2", C.c_void_p), ("auxp", C.c_void_p), ("dgbp", C.c_void_p), ("dgb_cp", C.c_int32),
                 ("dgb_ch_off", C.c_int32), ("dgb_ch_stride", C.c_int32), ("halo_buf", C.c_void_p), ("halo", C.c_int32),
-                ("t_valid", C.c_int32), ("pk_slope", C.c_float)]
+                ("t_valid", C.c_int32), ("pk_slope", C.c_float), ("unframe_s", C.c_int32), ("unframe_pad", C.c_int32),
+                ("unframe_T", C.c_int32), ("unframe_C", C.c_int32), ("flat_tp", C.c_int32), ("flat_halo", C.c_int32),
+                ("flat_T", C.c_int32)]
 
 
 class L1Job(C.Structure):
@@ -108,7 +110,7 @@ SIGNATURES = {
     "tdvc_adamw_multi": (_I, [_P, _P, _P, _P, _P, _I, _L, _F, _F, _F, _F, _F, _I, _F, _P, _P]),
     "tdvc_pack_cl_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _I, _I, _I, _P, _P]),
     "tdvc_cond_pack_cl": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
-    "tdvc_pack_cl_bf16_masked": (_I, [_P, _P, _F, _P, _I, _I, _I, _I, _P, _P]),
+    "tdvc_pack_cl_bf16_masked": (_I, [_P, _P, _F, _P, _I, _I, _I, _I, _I, _P, _P]),
     "tdvc_pack_weight_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "tdvc_conv1d_tc_wgrad_ws": (_L, [_I, _I, _I]),
     "tdvc_conv1d_tc_wgrad": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P]),

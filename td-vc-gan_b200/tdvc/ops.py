@@ -1314,14 +1314,25 @@ class _Conv1dTC(torch.autograd.Function):
             raise RuntimeError(f"conv1d: reflect padding {pad} must be smaller than the input length {Tin}")
         lib = _lib.load()
         Cp, Coutp = _cp(Cin), _ceil(Cout, 16)
-        halo = pad if pad_mode == PAD_REFLECT else 0          # zero padding is TMA out-of-bounds fill
+        # short 'same' convs (the discriminator's 1024-channel tail at T = 9 .. 35, the generator's T/320 convs): the batch is
+        # run as ONE sequence of zero-separated samples, so a 128-row tile holds several samples instead of one
+        flat = (_FLAT_SHORT and pad_mode == PAD_ZEROS and residual is None and B >= 2 and Tout == Tin and pad > 0
+                and 2 * (Tin + 2 * pad) <= 128)
+        halo = pad if (pad_mode == PAD_REFLECT or flat) else 0   # zero padding is otherwise TMA out-of-bounds fill
         xp = _pack_act(x, Cp, halo, pad_mode, in_slope)
         wp = _pack_w(w, Coutp, Cp, False)
         y = torch.empty(B, Cout, Tout, device=x.device, dtype=torch.float32)
         if residual is not None and residual.shape != y.shape:
             raise RuntimeError("conv1d: residual shape mismatch")
-        _lib.check(lib.tdvc_conv1d_tc_fwd(_p(xp), _p(wp), _p(bias), None, _p(residual), _p(y), B, Cp, Tin + 2 * halo, Cout,
-                                          Coutp, Tout, K, dilation, halo - pad, out_act, out_slope, _st()), "conv1d_tc_fwd")
+        if flat:
+            Tp = Tin + 2 * pad
+            _tc_conv(xp=xp, wp=wp, bias=bias, y=y, B=1, Tp=B * Tp, Tout=B * Tp, K=K, dilation=dilation, t_off=-pad, Cp_total=Cp,
+                     groups=1, a_ch_off=0, a_ch_stride=0, Cinp_g=Cp, Cout_g=Cout, Coutp_g=Coutp, bias_stride=0, out_act=out_act,
+                     out_slope=out_slope, out_packed=0, flat_tp=Tp, flat_halo=pad, flat_T=Tout)
+        else:
+            _lib.check(lib.tdvc_conv1d_tc_fwd(_p(xp), _p(wp), _p(bias), None, _p(residual), _p(y), B, Cp, Tin + 2 * halo, Cout,
+                                              Coutp, Tout, K, dilation, halo - pad, out_act, out_slope, _st()), "conv1d_tc_fwd")
+        ctx.flat = flat
         ctx.cfg = (pad, dilation, pad_mode, in_slope, out_act, out_slope)
         ctx.has_bias, ctx.has_res = bias is not None, residual is not None
         ctx.save_for_backward(x, w, y if out_act != ACT_NONE else None, xp)
@@ -1355,12 +1366,13 @@ class _Conv1dTC(torch.autograd.Function):
             if need_b and not db_from_wgrad:
                 db = torch.empty(Cout, device=x.device, dtype=torch.float32)
                 need_b = False
+            dyh = pad if ctx.flat else 0                        # flat: dL/dy laid out like the packed input (same zero rows)
             if mask_in_pack:
-                dyp = torch.empty(B, Tout, Cdp, device=x.device, dtype=torch.bfloat16)
-                _lib.check(lib.tdvc_pack_cl_bf16_masked(_p(dy), _p(y), out_slope, _p(dyp), B, Cout, Tout, Cdp, _p(db), _st()),
+                dyp = torch.empty(B, Tout + 2 * dyh, Cdp, device=x.device, dtype=torch.bfloat16)
+                _lib.check(lib.tdvc_pack_cl_bf16_masked(_p(dy), _p(y), out_slope, _p(dyp), B, Cout, Tout, Cdp, dyh, _p(db), _st()),
                            "pack_cl_bf16_masked")
             else:
-                dyp = _pack_act(dy, Cdp, 0, PAD_ZEROS, 1.0, cache=False, chan_sum=db)
+                dyp = _pack_act(dy, Cdp, dyh, PAD_ZEROS, 1.0, cache=False, chan_sum=db)
         if ctx.needs_input_grad[0]:
             # dgrad = the same implicit GEMM on dy with channel-swapped, tap-flipped weights
             ph = pad if pad_mode == PAD_REFLECT else 0            # reflect halo kept in the staging buffer
@@ -1370,8 +1382,15 @@ class _Conv1dTC(torch.autograd.Function):
             wtp = _pack_w(w, Cinp16, Cdp, True)
             need_stage = ph > 0 or in_slope != 1.0
             stage = torch.empty(B, Cin, Lout, device=x.device, dtype=torch.float32)
-            _lib.check(lib.tdvc_conv1d_tc_fwd(_p(dyp), _p(wtp), None, None, None, _p(stage), B, Cdp, Tout, Cin, Cinp16, Lout,
-                                              K, dilation, -zpad, ACT_NONE, 1.0, _st()), "conv1d_tc_dgrad")
+            if ctx.flat:
+                # 'same' conv: the data gradient is the same flattened conv on dL/dy (zpad == pad, Lout == Tin == Tout)
+                Tp = Tout + 2 * pad
+                _tc_conv(xp=dyp, wp=wtp, y=stage, B=1, Tp=B * Tp, Tout=B * Tp, K=K, dilation=dilation, t_off=-zpad, Cp_total=Cdp,
+                         groups=1, a_ch_off=0, a_ch_stride=0, Cinp_g=Cdp, Cout_g=Cin, Coutp_g=Cinp16, bias_stride=0,
+                         out_act=ACT_NONE, out_slope=1.0, out_packed=0, flat_tp=Tp, flat_halo=pad, flat_T=Lout)
+            else:
+                _lib.check(lib.tdvc_conv1d_tc_fwd(_p(dyp), _p(wtp), None, None, None, _p(stage), B, Cdp, Tout, Cin, Cinp16, Lout,
+                                                  K, dilation, -zpad, ACT_NONE, 1.0, _st()), "conv1d_tc_dgrad")
             if need_stage:
                 dx = torch.empty_like(x)
                 _lib.check(lib.tdvc_pad_act_bwd(_p(stage), _p(x), _p(dx), B * Cin, Tin, ph, int(pad_mode == PAD_REFLECT),
@@ -1385,7 +1404,12 @@ class _Conv1dTC(torch.autograd.Function):
             if db_from_wgrad:
                 db = torch.empty(Cout, device=x.device, dtype=torch.float32)
                 need_b = False
-            if _USE_WGRAD2:
+            if ctx.flat:
+                # both operands are [B, T + 2*pad, C] with the same zero rows: one sequence of B * (T + 2*pad) steps
+                Tp = Tout + 2 * pad
+                wgrad2(dyp=dyp, xp=xp, B=1, Cdp=Cdp, Tout=B * Tp, Cp=xp.shape[2], Tp=B * Tp, Cout=Cout, Cin=Cin, K=K,
+                       dilation=dilation, t_off=[-pad], dw=[dw], db=[db if db_from_wgrad else None])
+            elif _USE_WGRAD2:
                 wgrad2(dyp=dyp, xp=xp, B=B, Cdp=Cdp, Tout=Tout, Cp=xp.shape[2], Tp=xp.shape[1], Cout=Cout, Cin=Cin, K=K,
                        dilation=dilation, t_off=[halo - pad], dw=[dw], db=[db if db_from_wgrad else None])
             else:
@@ -1530,6 +1554,8 @@ def _conv_transpose_as_frames(x, weight, bias, stride, padding):
 
 _USE_WGRAD2 = os.environ.get("TDVC_WGRAD2", "1") != "0"      # development switch: 0 = first-generation tcgen05 wgrad kernel
 _GROUPED_FRAMES = os.environ.get("TDVC_GROUPED_FRAMES", "1") != "0"    # development switch: 0 = fp32 CUDA-core grouped kernels
+_FLAT_SHORT = os.environ.get("TDVC_FLAT_SHORT", "1") != "0"    # development switch: 0 = one tile per sample for short sequences
+_UNFRAME_EPILOGUE = os.environ.get("TDVC_UNFRAME_EPILOGUE", "1") != "0"   # development switch: 0 = separate frame_unpack pass
 
 
 def _grouped_frame_plan(Cin, Cout, K, stride, groups, dilation, reflect):
@@ -1611,7 +1637,7 @@ class _GroupedFrameConvTC(torch.autograd.Function):
         if ctx.needs_input_grad[0] or need_w or need_b:
             dyp = torch.empty(B, Tout, Cout, device=dy.device, dtype=torch.bfloat16)
             if out_act == ACT_LRELU:      # the activation's backward applied inside the pack
-                _lib.check(lib.tdvc_pack_cl_bf16_masked(_p(dy), _p(y), out_slope, _p(dyp), B, Cout, Tout, Cout, None, _st()),
+                _lib.check(lib.tdvc_pack_cl_bf16_masked(_p(dy), _p(y), out_slope, _p(dyp), B, Cout, Tout, Cout, 0, None, _st()),
                            "pack_cl_bf16_masked")
             else:
                 if out_act != ACT_NONE:
@@ -1621,12 +1647,17 @@ class _GroupedFrameConvTC(torch.autograd.Function):
                 _lib.check(lib.tdvc_pack_cl_bf16(_p(dy), _p(dyp), B, Cout, Tout, Cout, 0, PAD_ZEROS, 1.0, None, 0, 0, -1, None,
                                                  _st()), "pack dy")
         if ctx.needs_input_grad[0]:
-            dxf = torch.empty(B, Cin * stride, Tq, device=dy.device, dtype=torch.float32)
-            _tc_conv(xp=dyp, wp=wtp, y=dxf, B=B, Tp=Tout, Tout=Tq, K=m, dilation=1, t_off=-(m - 1), Cp_total=Cout, groups=nb,
-                     a_ch_off=0, a_ch_stride=cout_b, Cinp_g=cout_b, Cout_g=cin_b, Coutp_g=cin_b, bias_stride=0,
-                     out_act=ACT_NONE, out_slope=1.0, out_packed=0, y_grp_stride=cin_b * Tq, y_b_stride=Cin * stride * Tq)
             dx = torch.empty(B, Cin, T, device=dy.device, dtype=torch.float32)
-            _lib.check(lib.tdvc_frame_unpack(_p(dxf), _p(dx), B, Cin, T, stride, pad, Tq, _st()), "frame_unpack")
+            kw = dict(xp=dyp, wp=wtp, B=B, Tp=Tout, Tout=Tq, K=m, dilation=1, t_off=-(m - 1), Cp_total=Cout, groups=nb,
+                      a_ch_off=0, a_ch_stride=cout_b, Cinp_g=cout_b, Cout_g=cin_b, Coutp_g=cin_b, bias_stride=0,
+                      out_act=ACT_NONE, out_slope=1.0, out_packed=0)
+            if _UNFRAME_EPILOGUE and 16 % stride == 0 and cin_b % 16 == 0 and stride * Tq - pad >= T:
+                # the inverse frame view in the conv's epilogue: every sample of dx is one (frame, phase) of the Tq rows
+                _tc_conv(y=dx, unframe_s=stride, unframe_pad=pad, unframe_T=T, unframe_C=Cin, **kw)
+            else:
+                dxf = torch.empty(B, Cin * stride, Tq, device=dy.device, dtype=torch.float32)
+                _tc_conv(y=dxf, y_grp_stride=cin_b * Tq, y_b_stride=Cin * stride * Tq, **kw)
+                _lib.check(lib.tdvc_frame_unpack(_p(dxf), _p(dx), B, Cin, T, stride, pad, Tq, _st()), "frame_unpack")
         if need_w or need_b:
             dw = torch.empty_like(w)
             db = torch.empty(Cout, device=dy.device, dtype=torch.float32) if need_b else None

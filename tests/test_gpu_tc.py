@@ -39,6 +39,11 @@ TC_CASES = [
     (2, 256, 28, 256, 7, 3, 1, False, 0.2, None, False),       # T/320 stage: T < tile
     (2, 256, 35, 512, 5, 2, 1, False, 1.0, "lrelu", False),    # wide N: two 256-wide tiles, D-style epilogue
     (1, 1024, 35, 1024, 5, 2, 1, False, 1.0, "lrelu", False),  # the discriminator's big layer
+    # batch-flattened short sequences (B >= 2, T + 2*pad <= 64): several samples per 128-row tile
+    (5, 64, 9, 100, 3, 1, 1, False, 1.0, None, False),         # discriminator output conv at T = 9, Cout = 100
+    (7, 128, 18, 128, 5, 2, 1, False, 1.0, "lrelu", False),    # dense k5 at T = 18
+    (33, 64, 35, 64, 5, 2, 1, False, 1.0, "lrelu", False),     # 33 x 39 = 1287 rows: 11 tiles, samples straddle tile borders
+    (6, 128, 28, 256, 7, 3, 1, False, 0.2, None, False),       # decoder.1 at T/320 with the input LeakyReLU
 ]
 
 
