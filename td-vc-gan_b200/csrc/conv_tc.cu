@@ -1593,6 +1593,19 @@ extern "C" int tdvc_conv1d_tc_fwd_ex(const tdvc_tc_conv* c, void* stream) {
   for (int cand = std::min(c->Coutp_g, 256); cand >= 16; cand -= 16)
     if (c->Coutp_g % cand == 0) { bn = cand; break; }
   TDVC_CHECK_ARG(bn >= 16);
+  {
+    // Few, fat tiles (short sequences x wide layers: the discriminator's 1024 x 1024 x 5 conv at T <= 35 is 10 x 4 tiles of
+    // N = 256) leave most SMs idle while every CTA streams its 2.6 MB weight slice through one SM's L2 port (measured: 53 us
+    // against an 8 us tensor roofline).  Narrower N tiles put the same traffic on more SMs.
+    const long long m_tiles = (long long)cdiv(c->Tout, TC_BM) * c->B * c->groups;
+    while (bn > 64 && m_tiles * (c->Coutp_g / bn) * 2 <= num_sms()) {
+      int next = 0;
+      for (int cand = bn - 16; cand >= 64; cand -= 16)
+        if (c->Coutp_g % cand == 0) { next = cand; break; }
+      if (!next) break;
+      bn = next;
+    }
+  }
   p.BN = bn;
   p.tiles_per_group = c->Coutp_g / bn;
   p.coutp_g = c->Coutp_g;
