@@ -110,6 +110,28 @@ def test_pack_kernels_exact():
     assert torch.equal(wt, ref)
 
 
+@pytest.mark.parametrize("B,C,T,Cp", [(2, 16, 520, 16), (3, 20, 260, 32), (2, 64, 132, 64), (2, 100, 68, 112), (1, 8, 1024, 16)])
+def test_pack_vectorized_and_masked_exact(B, C, T, Cp):
+    """The un-haloed pack with 16-byte loads (T % 4 == 0) and its masked form (LeakyReLU backward applied while packing dL/dy,
+    per-channel sums = bias gradient): bit-exact layout, sums to fp32 accuracy."""
+    from tdvc import ops
+    lib = ops._lib.load()
+    x = rnd(B, C, T, seed=1).float()
+    y = rnd(B, C, T, seed=2).float()
+    y[0, 0, :5] = 0.0                                     # y == 0 takes the slope branch, like leaky_relu_backward on the output
+    xd, yd = x.cuda(), y.cuda()
+    xp = ops._pack_act(xd, Cp, 0, 0, 0.2, cache=False)
+    ref = F.pad(F.leaky_relu(x, 0.2).to(torch.bfloat16).permute(0, 2, 1), (0, Cp - C))
+    assert torch.equal(xp.cpu(), ref)
+    dyp = torch.empty(B, T, Cp, device="cuda", dtype=torch.bfloat16)
+    db = torch.empty(C, device="cuda", dtype=torch.float32)
+    ops._lib.check(lib.tdvc_pack_cl_bf16_masked(xd.data_ptr(), yd.data_ptr(), 0.2, dyp.data_ptr(), B, C, T, Cp, 0, db.data_ptr(),
+                                                torch.cuda.current_stream().cuda_stream), "masked pack")
+    masked = x * torch.where(y > 0, 1.0, 0.2)
+    assert torch.equal(dyp.cpu(), F.pad(masked.to(torch.bfloat16).permute(0, 2, 1), (0, Cp - C)))
+    assert relerr(db, masked.double().sum(dim=(0, 2))) < 1e-5
+
+
 def _build_and_load(cfg):
     from oracle.params import make_state_dict
     from test_host_cpu import build_D, build_G
