@@ -1332,7 +1332,8 @@ __global__ void __launch_bounds__(256) pack_cl_bf16_k(const float* __restrict__ 
 template <int CH>
 __global__ void __launch_bounds__(256) pack_cl_bf16_v4_k(const float* __restrict__ x, __nv_bfloat16* __restrict__ xp, int C, int T,
                                                         int Cp, float slope, float* __restrict__ chan_sum, int c_off, int Cw,
-                                                        const float* __restrict__ mask_y, float mask_slope) {
+                                                        const float* __restrict__ mask_y, float mask_slope, int halo,
+                                                        int pad_mode) {
   pdl_prologue();
   constexpr int TL = 4096 / CH;              // time steps per tile: 64 / 128 / 256 (CH * TL = 4096 elements, as above)
   constexpr int LPR = TL / 4;                // lanes per channel row: 16 / 32 / 64
@@ -1374,14 +1375,42 @@ __global__ void __launch_bounds__(256) pack_cl_bf16_v4_k(const float* __restrict
   __syncthreads();
   const int c = c0 + 2 * lane;
   if (c >= Cw) return;
+  // tiles are cut in SOURCE time steps (so the 16-byte loads stay aligned whatever the halo); sample t is row halo + t, and a
+  // sample that a reflect halo row mirrors (1 <= t <= halo on the left, T-1-halo <= t <= T-2 on the right) is written there too
+  const int Tp = T + 2 * halo;
+  const bool reflect = pad_mode == TDVC_PAD_REFLECT && halo > 0;
   for (int ty = wrp; ty < TL; ty += 8) {
     const int t = t0 + ty;
     if (t >= T) break;
-    __nv_bfloat16* dst = xp + ((long long)b * T + t) * Cp + c_off + c;
     const float o0 = (2 * lane < CH) ? tile[2 * lane < CH ? 2 * lane : 0][ty] : 0.f;
     const float o1 = (2 * lane + 1 < CH) ? tile[2 * lane + 1 < CH ? 2 * lane + 1 : 0][ty] : 0.f;
-    if (c + 1 < Cw) *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(o0, o1);
-    else *dst = __float2bfloat16(o0);
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(o0, o1);
+    int rows[3] = {halo + t, -1, -1};
+    if (reflect) {
+      if (t >= 1 && t <= halo) rows[1] = halo - t;
+      if (t >= T - 1 - halo && t <= T - 2) rows[2] = halo + 2 * T - 2 - t;
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      if (rows[r] < 0) continue;
+      __nv_bfloat16* dst = xp + ((long long)b * Tp + rows[r]) * Cp + c_off + c;
+      if (c + 1 < Cw) *reinterpret_cast<__nv_bfloat162*>(dst) = h2;
+      else *dst = __low2bfloat16(h2);
+    }
+  }
+  if (halo > 0 && !reflect) {
+    // zero halo rows: the first tile writes the left ones, the last tile the right ones
+    const __nv_bfloat162 z2 = __floats2bfloat162_rn(0.f, 0.f);
+    const bool first = blockIdx.x == 0, last = blockIdx.x == gridDim.x - 1;
+    for (int j = wrp; j < halo; j += 8) {
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        if (side == 0 ? !first : !last) continue;
+        __nv_bfloat16* dst = xp + ((long long)b * Tp + (side == 0 ? j : halo + T + j)) * Cp + c_off + c;
+        if (c + 1 < Cw) *reinterpret_cast<__nv_bfloat162*>(dst) = z2;
+        else *dst = __low2bfloat16(z2);
+      }
+    }
   }
 }
 
@@ -1444,16 +1473,19 @@ __global__ void pack_weight_multi_k(const long long* __restrict__ jobs, const fl
   const float* w = flat_w + e[0];
   __nv_bfloat16* wp = flat_wp + e[1];
   const int Cout = (int)e[2], Cin = (int)e[3], K = (int)e[4], Rp = (int)e[5], Qp = (int)e[6], flip = (int)e[7];
-  const long long n = (long long)K * Rp * Qp;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int qq = (int)(i % Qp);
-    const long long r2 = i / Qp;
-    const int rr = (int)(r2 % Rp);
-    const int k = (int)(r2 / Rp);
+  // a thread owns one (row, column) of the operand and walks its K taps: the K source floats are contiguous (neighbouring
+  // threads read neighbouring runs), each tap's store is coalesced, and the index arithmetic is 32-bit and once per K outputs
+  // (one output per thread with 64-bit div/mod ran the discriminator's 36 M outputs at 0.95 TB/s)
+  const int nrq = Rp * Qp;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nrq; i += gridDim.x * blockDim.x) {
+    const int rr = i / Qp, qq = i - rr * Qp;
     const int co = flip ? qq : rr, ci = flip ? rr : qq;
-    const int ks = flip ? K - 1 - k : k;
-    const float v = (co < Cout && ci < Cin) ? w[((long long)co * Cin + ci) * K + ks] : 0.f;
-    wp[i] = __float2bfloat16(v);
+    const bool ok = co < Cout && ci < Cin;
+    const float* src = w + ((long long)co * Cin + ci) * K;
+    for (int k = 0; k < K; ++k) {
+      const float v = ok ? __ldg(src + (flip ? K - 1 - k : k)) : 0.f;
+      wp[(long long)k * nrq + i] = __float2bfloat16(v);
+    }
   }
 }
 
@@ -1474,21 +1506,24 @@ static int pack_cl_bf16_launch(const float* x, void* xp, int B, int C, int T, in
   cudaStream_t st = (cudaStream_t)stream;
   __nv_bfloat16* o = (__nv_bfloat16*)xp;
   // thin tensors: fewer channel rows, longer time tiles (same bytes in flight per CTA)
-  const bool v4 = halo == 0 && T % 4 == 0 && !film_gb && ones_ch < 0 && (uintptr_t)x % 16 == 0 && (!mask_y || (uintptr_t)mask_y % 16 == 0);
+  const bool v4 = T % 4 == 0 && !film_gb && ones_ch < 0 && (uintptr_t)x % 16 == 0 && (!mask_y || (uintptr_t)mask_y % 16 == 0);
   if (C <= 16 && Cw <= 64) {
-    dim3 grid(cdiv(Tp, 256), 1, B);
-    if (v4) tdvc::launch_k(pack_cl_bf16_v4_k<16>, grid, 256, 0, st, x, o, C, T, Cp, in_slope, chan_sum, c_off, Cw, mask_y, mask_slope);
+    dim3 grid(cdiv(v4 ? T : Tp, 256), 1, B);
+    if (v4) tdvc::launch_k(pack_cl_bf16_v4_k<16>, grid, 256, 0, st, x, o, C, T, Cp, in_slope, chan_sum, c_off, Cw, mask_y, mask_slope, halo,
+                           pad_mode);
     else tdvc::launch_k(pack_cl_bf16_k<16>, grid, 256, 0, st, x, o, C, T, Cp, Tp, halo, pad_mode, in_slope, chan_sum, c_off, Cw, ones_ch,
                                              film_gb, mask_y, mask_slope);
   } else if (C <= 32 && Cw <= 64) {
-    dim3 grid(cdiv(Tp, 128), 1, B);
-    if (v4) tdvc::launch_k(pack_cl_bf16_v4_k<32>, grid, 256, 0, st, x, o, C, T, Cp, in_slope, chan_sum, c_off, Cw, mask_y, mask_slope);
+    dim3 grid(cdiv(v4 ? T : Tp, 128), 1, B);
+    if (v4) tdvc::launch_k(pack_cl_bf16_v4_k<32>, grid, 256, 0, st, x, o, C, T, Cp, in_slope, chan_sum, c_off, Cw, mask_y, mask_slope, halo,
+                           pad_mode);
     else tdvc::launch_k(pack_cl_bf16_k<32>, grid, 256, 0, st, x, o, C, T, Cp, Tp, halo, pad_mode, in_slope, chan_sum, c_off, Cw, ones_ch,
                                              film_gb, mask_y, mask_slope);
   } else {
-    dim3 grid(cdiv(Tp, 64), cdiv(Cw, 64), B);
+    dim3 grid(cdiv(v4 ? T : Tp, 64), cdiv(Cw, 64), B);
     TDVC_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535);
-    if (v4) tdvc::launch_k(pack_cl_bf16_v4_k<64>, grid, 256, 0, st, x, o, C, T, Cp, in_slope, chan_sum, c_off, Cw, mask_y, mask_slope);
+    if (v4) tdvc::launch_k(pack_cl_bf16_v4_k<64>, grid, 256, 0, st, x, o, C, T, Cp, in_slope, chan_sum, c_off, Cw, mask_y, mask_slope, halo,
+                           pad_mode);
     else tdvc::launch_k(pack_cl_bf16_k<64>, grid, 256, 0, st, x, o, C, T, Cp, Tp, halo, pad_mode, in_slope, chan_sum, c_off, Cw, ones_ch,
                                              film_gb, mask_y, mask_slope);
   }
