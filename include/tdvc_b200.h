@@ -102,6 +102,23 @@ int tdvc_conv_transpose1d_bwd_weight(const tdvc_conv_geom* g, const float* dy, c
 /* ---- elementwise pieces of FiLMResnetBlock / MRFBlock / Discriminator
  *      (model/generator.py:96-111,186-194; model/discriminator.py:20,31,38) */
 int tdvc_leaky_relu_fwd(const float* x, float* y, int64_t n, float slope, void* stream);
+/* F0 track -> sine + noise excitation, the decoder's c_var conditioning (util/__init__.py:22-50 f0_to_excitation):
+ * f0[rows, F] Hz (0 = unvoiced; the last frame is dropped), out[rows, (F-1)*step].  Per-sample angular frequency = the
+ * reference's nearest / linear F.interpolate mix, phase = its cumulative sum (formed in fp64), voiced samples
+ * 0.1 sin(phase + *phase0) + 0.003 noise_v, unvoiced samples noise_u * 0.003 * (0.1 / 0.009).  The random numbers are inputs
+ * drawn by the caller in the reference's order: noise_v[rows, N]; noise_u full [rows, N] (u_offset = NULL) or compact, the
+ * k-th unvoiced sample in row-major order taking noise_u[k], with u_offset[row] = unvoiced samples in the rows before
+ * (tdvc_f0_unvoiced_count gives counts[rows]). */
+int tdvc_f0_unvoiced_count(const float* f0, int* counts, int rows, int F, int step, float sampling_rate, int linear,
+                           void* stream);
+int tdvc_f0_excitation(const float* f0, const float* noise_v, const float* noise_u, const int64_t* u_offset,
+                       const float* phase0 /* device scalar */, float* out, int rows, int F, int step, float sampling_rate,
+                       int linear, void* stream);
+/* WaveNet gate of the SSL content encoder (model/ssl_encoder.py:7-14 fused_add_tanh_sigmoid_multiply):
+ * y[B,H,T] = tanh(a[:, :H] + g[:, :H]) * sigmoid(a[:, H:] + g[:, H:]) for a, g [B,2H,T] (g optional);
+ * backward: da[B,2H,T] from dy and the recomputed activations (the gradient of g is the same tensor). */
+int tdvc_gate_fwd(const float* a, const float* g, float* y, int B, int H, int T, void* stream);
+int tdvc_gate_bwd(const float* dy, const float* a, const float* g, float* da, int B, int H, int T, void* stream);
 /* dz = dy * act'(.) evaluated from the activation OUTPUT y (lrelu: sign(y); tanh: 1-y^2) */
 int tdvc_act_bwd_from_output(const float* dy, const float* y, float* dz, int64_t n, int act,
                              float slope, void* stream);

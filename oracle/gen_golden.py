@@ -228,6 +228,33 @@ def case_latent_classifier(name):
          shapes=np.array([str(tuple(v.shape)) for v in m.state_dict().values()]))
 
 
+def case_ssl_wn(name):
+    """The WaveNet-style stack behind WavLM (model/ssl_encoder.py:16-116: WN + Encoder): m, logs and every gradient for a
+    small geometry (64 SSL dims -> 32 hidden / 32 out, 4 layers k5) and a conditioned WN (gin_channels, dilation rate 2)."""
+    from model.ssl_encoder import Encoder as SSLWNEncoder, WN
+    B, T = 3, 28
+    m = SSLWNEncoder(64, 32, 32, 5, 1, 4)
+    load(m, 31)
+    x = rand_like(torch.empty(B, 64, T), 91).requires_grad_(True)
+    torch.manual_seed(5)
+    z, mean, logs, _ = m(x)
+    loss = (mean * rand_like(mean, 92)).sum() + (logs * rand_like(logs, 93)).sum()
+    loss.backward()
+    full, st = grads_of(m, 1 << 30)
+    w = WN(16, 3, 2, 3, gin_channels=8)
+    load(w, 32)
+    xw = rand_like(torch.empty(2, 16, 40), 94).requires_grad_(True)
+    gw = rand_like(torch.empty(2, 8, 40), 95).requires_grad_(True)
+    yw = w(xw, 1, g=gw)
+    (yw * rand_like(yw, 96)).sum().backward()
+    wfull, wst = grads_of(w, 1 << 30)
+    save(name, m=mean, logs=logs, dx=x.grad, grad=full, gstat=st,
+         keys=np.array(list(m.state_dict().keys())),
+         shapes=np.array([str(tuple(v.shape)) for v in m.state_dict().values()]),
+         wn_y=yw, wn_dx=xw.grad, wn_dg=gw.grad, wn_grad=wfull,
+         wn_keys=np.array(list(w.state_dict().keys())))
+
+
 def ref_step(G, D, b, hp, nspk, C=None):
     """train.py:259-491 driven through the reference's own modules (lambda_f0 term = 0)."""
     x = b["signal_real"]
@@ -350,6 +377,7 @@ if __name__ == "__main__":
     if want("cin"): case_cin("cin")
     if want("losses"): case_losses("losses")
     if want("latcls"): case_latent_classifier("latcls")
+    if want("ssl_wn"): case_ssl_wn("ssl_wn")
     if want("legacy"): case_legacy_blocks("legacy")
     if want("g_full"): case_generator("g_full", CASES["g_full"], full_limit=4096)
     if want("d_full"): case_discriminator("d_full", CASES["d_full"], full_limit=4096)

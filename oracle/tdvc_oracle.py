@@ -316,6 +316,38 @@ def latent_classifier(sd: SD, x: torch.Tensor, *, num_layers: int = 3, down: int
     return x.mean(dim=2)
 
 
+def ssl_wn(sd: SD, prefix: str, x: torch.Tensor, g=None, *, hidden: int, kernel_size: int, dilation_rate: int,
+           n_layers: int) -> torch.Tensor:
+    """WN.forward, model/ssl_encoder.py:53-81 (x_mask = 1, dropout 0): per layer a dilated wn conv to 2H channels, the
+    tanh * sigmoid gate (fused_add_tanh_sigmoid_multiply, :7-14) with the optional conditioning slice added first, a 1x1 wn
+    conv whose first H outputs are the residual and the rest the skip sum (the last layer has skip outputs only)."""
+    out = torch.zeros_like(x)
+    if g is not None:
+        g = conv(sd, prefix + "cond_layer", g)
+    for i in range(n_layers):
+        d = dilation_rate ** i
+        a = conv(sd, f"{prefix}in_layers.{i}", x, padding=int((kernel_size * d - d) / 2), dilation=d)
+        if g is not None:
+            a = a + g[:, i * 2 * hidden:(i + 1) * 2 * hidden]
+        acts = torch.tanh(a[:, :hidden]) * torch.sigmoid(a[:, hidden:])
+        rs = conv(sd, f"{prefix}res_skip_layers.{i}", acts)
+        if i < n_layers - 1:
+            x = x + rs[:, :hidden]
+            out = out + rs[:, hidden:]
+        else:
+            out = out + rs
+    return out
+
+
+def ssl_wn_encoder(sd: SD, x: torch.Tensor, *, out_channels: int, hidden: int, kernel_size: int, dilation_rate: int,
+                   n_layers: int):
+    """Encoder.forward of model/ssl_encoder.py:105-116 without the sampled z: (m, logs)."""
+    h = conv(sd, "pre", x)
+    h = ssl_wn(sd, "enc.", h, hidden=hidden, kernel_size=kernel_size, dilation_rate=dilation_rate, n_layers=n_layers)
+    stats = conv(sd, "proj", h)
+    return stats[:, :out_channels], stats[:, out_channels:]
+
+
 class GradRev(torch.autograd.Function):
     """model/grad_rev.py:3-10: identity forward, negated gradient."""
 

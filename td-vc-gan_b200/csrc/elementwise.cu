@@ -154,6 +154,37 @@ __global__ void cond_concat_bwd_k(const float* __restrict__ dout, float* __restr
   }
 }
 
+// WaveNet gate of the SSL content encoder (model/ssl_encoder.py:7-14, fused_add_tanh_sigmoid_multiply):
+//   acts[b, c, t] = tanh(a[b, c, t] + g[b, c, t]) * sigmoid(a[b, H + c, t] + g[b, H + c, t]),  a, g: [B, 2H, T], g optional.
+// The backward recomputes the two activations from a (+ g): d(a_tanh) = d * s * (1 - th^2), d(a_sig) = d * th * s * (1 - s);
+// the gradient of g is the same tensor.
+__global__ void gate_fwd_k(const float* __restrict__ a, const float* __restrict__ g, float* __restrict__ y, int B, int H, int T) {
+  pdl_prologue();
+  const long long n = (long long)B * H * T, ht = (long long)H * T;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / ht, r = i - b * ht;
+    const long long ia = b * 2 * ht + r;
+    float u = a[ia], v = a[ia + ht];
+    if (g) { u += g[ia]; v += g[ia + ht]; }
+    y[i] = tanhf(u) * (1.f / (1.f + expf(-v)));
+  }
+}
+
+__global__ void gate_bwd_k(const float* __restrict__ dy, const float* __restrict__ a, const float* __restrict__ g,
+                           float* __restrict__ da, int B, int H, int T) {
+  pdl_prologue();
+  const long long n = (long long)B * H * T, ht = (long long)H * T;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / ht, r = i - b * ht;
+    const long long ia = b * 2 * ht + r;
+    float u = a[ia], v = a[ia + ht];
+    if (g) { u += g[ia]; v += g[ia + ht]; }
+    const float th = tanhf(u), sg = 1.f / (1.f + expf(-v)), d = dy[i];
+    da[ia] = d * sg * (1.f - th * th);
+    da[ia + ht] = d * th * sg * (1.f - sg);
+  }
+}
+
 }  // namespace tdvc
 using namespace tdvc;
 
@@ -236,6 +267,22 @@ extern "C" int tdvc_cond_concat_bwd(const float* dout, float* dc, float* de, int
   TDVC_CHECK_ARG(Cc == 0 || dc);
   if (B == 0) return TDVC_OK;
   tdvc::launch_k(cond_concat_bwd_k, B * (Cc + Ce), 256, 0, (cudaStream_t)stream, dout, dc, de, B, Cc, Ce, T, c_first);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_gate_fwd(const float* a, const float* g, float* y, int B, int H, int T, void* stream) {
+  TDVC_CHECK_ARG(a && y && B >= 0 && H > 0 && T > 0);
+  if (B == 0) return TDVC_OK;
+  tdvc::launch_k(gate_fwd_k, ew_blocks((long long)B * H * T), 256, 0, (cudaStream_t)stream, a, g, y, B, H, T);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_gate_bwd(const float* dy, const float* a, const float* g, float* da, int B, int H, int T, void* stream) {
+  TDVC_CHECK_ARG(dy && a && da && B >= 0 && H > 0 && T > 0);
+  if (B == 0) return TDVC_OK;
+  tdvc::launch_k(gate_bwd_k, ew_blocks((long long)B * H * T), 256, 0, (cudaStream_t)stream, dy, a, g, da, B, H, T);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }

@@ -541,7 +541,7 @@ class Generator(nn.Module):
         self.decoder = Decoder(decoder_ratios, decoder_channels[:], num_res_blocks, dec_cond_dim, content_dim,
                                dec_norm_layer, dec_weight_norm)
         if encoder_model in ['wavlm']:
-            from model.ssl_encoder import SSLEncoder   # reference's own file (frozen WavLM front end; out of scope)
+            from model.ssl_encoder import SSLEncoder   # WN stack on the tdvc kernels; WavLM itself comes from a reference checkout
             self.encoder = SSLEncoder(encoder_model, num_enc_layers, content_dim, weight_norm=_as_torch_wn(enc_weight_norm))
         else:
             self.encoder = Encoder(decoder_ratios[::-1], decoder_channels[::-1], num_res_blocks, enc_cond_dim,

@@ -85,6 +85,10 @@ SIGNATURES = {
     "tdvc_conv_transpose1d_bwd_data": (_I, [_G, _P, _P, _P, _P]),
     "tdvc_conv_transpose1d_bwd_weight": (_I, [_G, _P, _P, _P, _P, _P]),
     "tdvc_leaky_relu_fwd": (_I, [_P, _P, _L, _F, _P]),
+    "tdvc_f0_unvoiced_count": (_I, [_P, _P, _I, _I, _I, _F, _I, _P]),
+    "tdvc_f0_excitation": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P]),
+    "tdvc_gate_fwd": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "tdvc_gate_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "tdvc_act_bwd_from_output": (_I, [_P, _P, _P, _L, _I, _F, _P]),
     "tdvc_film_fwd": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "tdvc_film_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),

@@ -610,6 +610,35 @@ def leaky_relu(x, slope=0.2):
     return _LeakyReLU.apply(x, float(slope))
 
 
+class _Gate(torch.autograd.Function):
+    """tanh(a[:, :H] + g[:, :H]) * sigmoid(a[:, H:] + g[:, H:])  (model/ssl_encoder.py:7-14)."""
+
+    @staticmethod
+    def forward(ctx, a, g):
+        _req(a, g)
+        a, g = _c(a), _c(g)
+        B, C2, T = a.shape
+        if C2 % 2 or (g is not None and g.shape != a.shape):
+            raise RuntimeError(f"gate: inputs {tuple(a.shape)}, {None if g is None else tuple(g.shape)} must be [B, 2H, T]")
+        y = torch.empty(B, C2 // 2, T, device=a.device, dtype=torch.float32)
+        _lib.check(_lib.load().tdvc_gate_fwd(_p(a), _p(g), _p(y), B, C2 // 2, T, _st()), "gate_fwd")
+        ctx.save_for_backward(a, g)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, g = ctx.saved_tensors
+        dy = _c(dy)
+        B, C2, T = a.shape
+        da = torch.empty_like(a)
+        _lib.check(_lib.load().tdvc_gate_bwd(_p(dy), _p(a), _p(g), _p(da), B, C2 // 2, T, _st()), "gate_bwd")
+        return da, (da.clone() if (g is not None and ctx.needs_input_grad[1]) else None)
+
+
+def gated_tanh_sigmoid(a, g=None):
+    return _Gate.apply(a, g)
+
+
 class _Film(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h, gb):

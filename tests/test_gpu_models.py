@@ -301,6 +301,54 @@ def test_latent_classifier_vs_golden():
     check_grads(m, g, 1e-4, 2e-5)
 
 
+def test_ssl_wn_encoder_vs_golden():
+    """The WaveNet-style stack of the SSL content encoder (model/ssl_encoder.py:16-116) on the tdvc kernels
+    against the reference's own module: posterior mean / log-scale, input and parameter gradients (fp32 path, 1e-5 / 1e-4),
+    plus a conditioned, dilated WN (gin_channels = 8, dilation rate 2)."""
+    from model.ssl_encoder import Encoder as SSLWNEncoder, WN
+    g = golden("ssl_wn")
+    m = SSLWNEncoder(64, 32, 32, 5, 1, 4)
+    assert list(m.state_dict().keys()) == [str(k) for k in g["keys"]]
+    m = load_det(m, 31)
+    x = cu(rand_like(torch.empty(3, 64, 28), 91)).requires_grad_(True)
+    z, mean, logs, _ = m(x)
+    assert relerr(mean, g["m"]) < TOL and relerr(logs, g["logs"]) < TOL
+    assert z.shape == mean.shape
+    ((mean * cu(rand_like(mean, 92))).sum() + (logs * cu(rand_like(logs, 93))).sum()).backward()
+    assert relerr(x.grad, g["dx"]) < 2e-5
+    check_grads(m, g, 1e-4, 2e-5)
+    w = WN(16, 3, 2, 3, gin_channels=8)
+    assert list(w.state_dict().keys()) == [str(k) for k in g["wn_keys"]]
+    w = load_det(w, 32)
+    xw = cu(rand_like(torch.empty(2, 16, 40), 94)).requires_grad_(True)
+    gw = cu(rand_like(torch.empty(2, 8, 40), 95)).requires_grad_(True)
+    yw = w(xw, 1, g=gw)
+    assert relerr(yw, g["wn_y"]) < TOL
+    (yw * cu(rand_like(yw, 96))).sum().backward()
+    assert relerr(xw.grad, g["wn_dx"]) < 2e-5 and relerr(gw.grad, g["wn_dg"]) < 2e-5
+    for k, p in w.named_parameters():
+        assert relerr(p.grad, g["wn_grad/" + k]) < 1e-4, k
+
+
+def test_ssl_wn_encoder_bf16():
+    """The same stack in bf16 mode (tcgen05 convs; the T = 28 convs take the batch-flattened path): 2e-2."""
+    from model.ssl_encoder import Encoder as SSLWNEncoder
+    from tdvc import ops
+    g = golden("ssl_wn")
+    m = load_det(SSLWNEncoder(64, 32, 32, 5, 1, 4), 31)
+    x = cu(rand_like(torch.empty(3, 64, 28), 91)).requires_grad_(True)
+    ops.set_precision("bf16")
+    try:
+        z, mean, logs, _ = m(x)
+        ((mean * cu(rand_like(mean, 92))).sum() + (logs * cu(rand_like(logs, 93))).sum()).backward()
+    finally:
+        ops.set_precision("fp32")
+    assert relerr(mean, g["m"]) < 2e-2 and relerr(logs, g["logs"]) < 2e-2
+    assert relerr(x.grad, g["dx"]) < 3e-2
+    for k, p in m.named_parameters():
+        assert relerr(p.grad, g["grad/" + k]) < 5e-2, (k, relerr(p.grad, g["grad/" + k]))
+
+
 def test_legacy_blocks_vs_golden():
     """The constructible-but-unused residual blocks of model/generator.py:11-67 on the tdvc kernels."""
     import torch.nn as nn

@@ -339,3 +339,42 @@ def test_mel_loss_bf16_mode_keeps_fp32_class_accuracy():
     assert abs(mel.item() - float(g["mel"])) < 2e-4 * abs(float(g["mel"])), (mel.item(), float(g["mel"]))
     ref = torch.as_tensor(np.asarray(g["dmel"])).double()
     assert float((a.grad.double().cpu() - ref).norm() / ref.norm()) < 2e-3
+
+
+@pytest.mark.parametrize("linear", [True, False])
+def test_f0_to_excitation_device(linear):
+    """util.f0_to_excitation on CUDA tracks (csrc/excitation.cu; reference util/__init__.py:22-50).  The generator is consumed
+    in the reference's order, so the numbers can be re-drawn: unvoiced samples must equal noise * 0.003 * gain bit for bit,
+    voiced samples 0.1 sin(phase + phase0) + 0.003 noise with the phase summed in fp64 from the reference's own fp32
+    per-sample frequencies (torch's F.interpolate on the device): 1e-5 absolute = 1e-4 of the sine's amplitude.  The kernel's
+    interpolated frequencies may differ from torch's in the last bit (fused multiply-add contraction), which adds up to a few
+    1e-5 rad over 8960 samples (measured 3e-6 in the output); the reference's own fp32 cumsum is ~1e-4 rad off at the end of a
+    segment, so it cannot be the yardstick."""
+    import util
+    B, F_, step, sr = 3, 141, 64, 16000
+    g = torch.Generator().manual_seed(3)
+    f0 = 100 + 200 * torch.rand(B, 1, F_, generator=g)
+    f0[0, 0, 10:30] = 0
+    f0[1, 0, :5] = 0          # unvoiced start: the clamped source index of the linear interpolation
+    f0[1, 0, 70] = 0          # one isolated unvoiced frame
+    f0[2, 0, -8:] = 0         # unvoiced end (the last frame is dropped)
+    f0d = f0.cuda()
+    torch.manual_seed(11)
+    out = util.f0_to_excitation(f0d, step, sr, linear=linear)
+    assert out.shape == (B, 1, (F_ - 1) * step) and out.is_cuda
+    torch.manual_seed(11)
+    phase0 = torch.rand(1, device="cuda") * 2 * torch.pi
+    nv = torch.randn(B, 1, (F_ - 1) * step, device="cuda")
+    omega = util._upsampled_frequency(2 * torch.pi * f0d[:, :, :-1] / sr, step, linear)      # the reference's fp32 arithmetic
+    silent = omega == 0
+    assert 0 < int(silent.sum()) < silent.numel()
+    nu = torch.randn(int(silent.sum()), device="cuda")
+    phase = torch.cumsum(omega.double(), -1)
+    ref = 0.1 * torch.sin(phase + phase0.double()) + nv.double() * 0.003
+    ref[silent] = (nu * 0.003 * (0.1 / (3 * 0.003))).double()
+    assert torch.equal(out[silent], (nu * 0.003 * (0.1 / (3 * 0.003))))
+    err = (out.double() - ref).abs().max().item()
+    assert err < 1e-5, err
+    # the fp32 path of the reference (torch ops, CPU) on the same track: same statistics, phase within its own rounding
+    rms_v = out[~silent].pow(2).mean().sqrt().item()
+    assert abs(rms_v - (0.1 ** 2 / 2 + 0.003 ** 2) ** 0.5) < 2e-3

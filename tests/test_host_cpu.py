@@ -66,6 +66,17 @@ def test_cin_state_dict():
     assert list(CINResnetBlock(12, 7, dilation=3, kernel_size=7).state_dict().keys()) == [str(k) for k in g["blk_keys"]]
 
 
+def test_ssl_wn_state_dict():
+    """checkpoint layout of the SSL content encoder's WaveNet stack (model/ssl_encoder.py:16-116) = the reference module's"""
+    import ast
+    from model.ssl_encoder import Encoder as SSLWNEncoder, WN
+    g = golden("ssl_wn")
+    m = SSLWNEncoder(64, 32, 32, 5, 1, 4)
+    assert list(m.state_dict().keys()) == [str(k) for k in g["keys"]]
+    assert [tuple(v.shape) for v in m.state_dict().values()] == [ast.literal_eval(str(x)) for x in g["shapes"]]
+    assert list(WN(16, 3, 2, 3, gin_channels=8).state_dict().keys()) == [str(k) for k in g["wn_keys"]]
+
+
 def test_strict_round_trip_and_no_caller_mutation():
     cfg = CASES["g_tiny"]
     chans = list(cfg["channels"])

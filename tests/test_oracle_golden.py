@@ -211,6 +211,31 @@ def test_latent_classifier():
     _check_grads(g, sd)
 
 
+def test_ssl_wn_encoder():
+    """the WaveNet-style stack of model/ssl_encoder.py (Encoder + WN), and a conditioned dilated WN."""
+    g = golden("ssl_wn")
+    sd = _sd(g, 31)
+    x = rand_like(torch.empty(3, 64, 28), 91).requires_grad_(True)
+    m, logs = O.ssl_wn_encoder(sd, x, out_channels=32, hidden=32, kernel_size=5, dilation_rate=1, n_layers=4)
+    assert relerr(m, g["m"]) < TOL and relerr(logs, g["logs"]) < TOL
+    ((m * rand_like(m, 92)).sum() + (logs * rand_like(logs, 93)).sum()).backward()
+    assert relerr(x.grad, g["dx"]) < TOL
+    _check_grads(g, sd)
+    keys = [str(k) for k in g["wn_keys"]]
+    shapes = {k: tuple(g["wn_grad/" + k].shape) for k in keys}
+    wsd = make_state_dict(shapes, seed=32, dtype=torch.float64)
+    for v in wsd.values():
+        v.requires_grad_(True)
+    xw = rand_like(torch.empty(2, 16, 40), 94).requires_grad_(True)
+    gw = rand_like(torch.empty(2, 8, 40), 95).requires_grad_(True)
+    yw = O.ssl_wn(wsd, "", xw, gw, hidden=16, kernel_size=3, dilation_rate=2, n_layers=3)
+    assert relerr(yw, g["wn_y"]) < TOL
+    (yw * rand_like(yw, 96)).sum().backward()
+    assert relerr(xw.grad, g["wn_dx"]) < TOL and relerr(gw.grad, g["wn_dg"]) < TOL
+    for k, v in wsd.items():
+        assert relerr(v.grad, g["wn_grad/" + k]) < TOL, k
+
+
 def test_legacy_blocks():
     """DecoderResnetBlock / TranformResnetBlock / ResnetBlock."""
     import ast
