@@ -114,6 +114,11 @@ int tdvc_f0_unvoiced_count(const float* f0, int* counts, int rows, int F, int st
 int tdvc_f0_excitation(const float* f0, const float* noise_v, const float* noise_u, const int64_t* u_offset,
                        const float* phase0 /* device scalar */, float* out, int rows, int F, int step, float sampling_rate,
                        int linear, void* stream);
+/* YIN pitch estimation, util/yin.py:24-140 (`estimate`, hard search): signal[B, T] -> f0[B, n_frames] Hz (0 = no period below the
+ * threshold).  Windows of frame_length = 2 * tau_max samples centred on multiples of frame_stride (zero padding),
+ * n_frames = (max(T, frame_length) - 1) / frame_stride + 1; lags tau_min + 1 .. tau_max - 1 are searched. */
+int tdvc_yin_estimate(const float* signal, float* f0, int B, int T, int n_frames, int frame_length, int frame_stride,
+                      int tau_min, int tau_max, float threshold, float sample_rate, void* stream);
 /* WaveNet gate of the SSL content encoder (model/ssl_encoder.py:7-14 fused_add_tanh_sigmoid_multiply):
  * y[B,H,T] = tanh(a[:, :H] + g[:, :H]) * sigmoid(a[:, H:] + g[:, H:]) for a, g [B,2H,T] (g optional);
  * backward: da[B,2H,T] from dy and the recomputed activations (the gradient of g is the same tensor). */

@@ -255,6 +255,25 @@ def case_ssl_wn(name):
          wn_keys=np.array(list(w.state_dict().keys())))
 
 
+def case_yin(name):
+    """util/yin.py `estimate` as train.py:238 would call it (pitch 50..550 Hz, one frame per 64 samples) on four 0.56 s
+    signals: sines with noise (one with a silent stretch, one with a glide), a two-tone mixture, and white noise."""
+    import util.yin as ref_yin
+    g = torch.Generator().manual_seed(77)
+    T, sr = 8960, 16000
+    t = torch.arange(T, dtype=torch.float32) / sr
+    x = torch.zeros(4, T)
+    x[0] = 0.05 * torch.sin(2 * np.pi * 140.0 * t) + 0.01 * torch.randn(T, generator=g)
+    x[0, 3000:4500] = 0.002 * torch.randn(1500, generator=g)
+    x[1] = 0.05 * torch.sin(2 * np.pi * (110.0 * t + 150.0 * t * t)) + 0.005 * torch.randn(T, generator=g)
+    x[2] = 0.04 * torch.sin(2 * np.pi * 220.0 * t) + 0.02 * torch.sin(2 * np.pi * 331.0 * t + 0.3) + 0.004 * torch.randn(T, generator=g)
+    x[3] = 0.02 * torch.randn(T, generator=g)
+    f0 = ref_yin.estimate(x, sr, pitch_min=50, pitch_max=550, frame_stride=64 / sr)
+    f0_soft = ref_yin.estimate(x, sr, pitch_min=50, pitch_max=550, frame_stride=64 / sr, soft=True)
+    short = ref_yin.estimate(x[:2, :500], sr, pitch_min=50, pitch_max=550, frame_stride=64 / sr)
+    save(name, x=x, f0=f0, f0_soft=f0_soft, f0_short=short)
+
+
 def ref_step(G, D, b, hp, nspk, C=None):
     """train.py:259-491 driven through the reference's own modules (lambda_f0 term = 0)."""
     x = b["signal_real"]
@@ -378,6 +397,7 @@ if __name__ == "__main__":
     if want("losses"): case_losses("losses")
     if want("latcls"): case_latent_classifier("latcls")
     if want("ssl_wn"): case_ssl_wn("ssl_wn")
+    if want("yin"): case_yin("yin")
     if want("legacy"): case_legacy_blocks("legacy")
     if want("g_full"): case_generator("g_full", CASES["g_full"], full_limit=4096)
     if want("d_full"): case_discriminator("d_full", CASES["d_full"], full_limit=4096)

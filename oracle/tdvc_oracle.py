@@ -348,6 +348,32 @@ def ssl_wn_encoder(sd: SD, x: torch.Tensor, *, out_channels: int, hidden: int, k
     return stats[:, :out_channels], stats[:, out_channels:]
 
 
+def yin_estimate(signal: torch.Tensor, sample_rate: float, pitch_min: float = 20, pitch_max: float = 20000,
+                 frame_stride: float = 0.01, threshold: float = 0.1) -> torch.Tensor:
+    """util/yin.py:24-84 + :87-133 (`estimate`, hard search) with the difference function in its defining form (equation 6 of
+    the YIN paper, d(tau) = sum_j (x_j - x_{j+tau})^2 over the part of the window where both samples exist) in fp64 instead of
+    the reference's fp32 FFT; the cumulative-mean normalisation (equation 8) is rounded to fp32 before the threshold / slope
+    comparisons because that is where the reference decides."""
+    x = signal.double()
+    tau_min, tau_max = int(sample_rate / pitch_max), int(sample_rate / pitch_min)
+    W, hop = 2 * tau_max, int(frame_stride * sample_rate)
+    if x.shape[-1] < W:
+        x = F.pad(x, [0, W - x.shape[-1]])
+    fr = F.pad(x, [W // 2, W // 2 - 1]).unfold(-1, W, hop)                      # [..., frames, W]
+    d = torch.stack([((fr[..., :W - tau] - fr[..., tau:]) ** 2).sum(-1) for tau in range(1, tau_max)], dim=-1)
+    lag = torch.arange(1, tau_max, dtype=torch.float64)
+    c = (d * lag / d.cumsum(-1).clamp_min(1e-5)).float()[..., tau_min:]
+    thr = torch.tensor(threshold, dtype=torch.float32)
+    n = c.shape[-1]
+    below = (c < thr).int().argmax(-1)
+    rising = F.pad(c.diff() >= 0.0, [0, 1], value=True)
+    idx = torch.arange(n)
+    ok = (idx >= below.unsqueeze(-1)) & rising & (below.unsqueeze(-1) > 0)
+    tau = ok.int().argmax(-1)
+    # `sample_rate / tensor` is Tensor.__rtruediv__ = reciprocal(tensor) * sample_rate: two fp32 roundings, reproduced here
+    return torch.where(tau > 0, (tau + tau_min + 1).float().reciprocal() * sample_rate, torch.zeros((), dtype=torch.float32))
+
+
 class GradRev(torch.autograd.Function):
     """model/grad_rev.py:3-10: identity forward, negated gradient."""
 

@@ -87,6 +87,7 @@ SIGNATURES = {
     "tdvc_leaky_relu_fwd": (_I, [_P, _P, _L, _F, _P]),
     "tdvc_f0_unvoiced_count": (_I, [_P, _P, _I, _I, _I, _F, _I, _P]),
     "tdvc_f0_excitation": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P]),
+    "tdvc_yin_estimate": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P]),
     "tdvc_gate_fwd": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "tdvc_gate_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "tdvc_act_bwd_from_output": (_I, [_P, _P, _P, _L, _I, _F, _P]),

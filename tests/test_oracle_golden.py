@@ -236,6 +236,27 @@ def test_ssl_wn_encoder():
         assert relerr(v.grad, g["wn_grad/" + k]) < TOL, k
 
 
+def test_yin():
+    """util/yin.py.  The package's torch formulation (CPU path of util.yin.estimate) must reproduce the
+    reference's output exactly (same fp32 FFT arithmetic); the fp64 direct-form oracle -- what the CUDA kernel is held against --
+    must choose the same period: measured 560 of 560 frames on this fixture; 99.5 % is asserted because the reference's fp32
+    FFT carries ~1e-6-relative noise in the difference function, so a frame whose normalised difference touches the threshold,
+    or whose first minimum is flat to that level, could land on a neighbouring candidate there."""
+    import util.yin as yin
+    g = golden("yin")
+    x = torch.from_numpy(g["x"]).float()          # the fixtures are stored as fp64 copies of the reference's fp32 tensors
+    ref, ref_short = torch.from_numpy(g["f0"]).float(), torch.from_numpy(g["f0_short"]).float()
+    kw = dict(pitch_min=50, pitch_max=550, frame_stride=64 / 16000)
+    assert torch.equal(yin.estimate(x, 16000, **kw), ref)
+    assert torch.equal(yin.estimate(x[:2, :500], 16000, **kw), ref_short)
+    assert relerr(yin.estimate(x, 16000, soft=True, **kw), g["f0_soft"]) < 1e-5
+    f0 = O.yin_estimate(x, 16000, **kw)
+    same = (f0 == ref).float().mean().item()
+    assert same >= 0.995, same
+    assert ((ref > 0) == (f0 > 0)).float().mean().item() >= 0.99
+    assert torch.equal(O.yin_estimate(x[:2, :500], 16000, **kw) > 0, ref_short > 0)
+
+
 def test_legacy_blocks():
     """DecoderResnetBlock / TranformResnetBlock / ResnetBlock."""
     import ast
