@@ -336,7 +336,7 @@ FAMILY_OF = (("conv_tc_wgrad_k", 3), ("conv_tc_wt_k", 2), ("conv_tc_ws_k", 1), (
              ("conv_fwd_k", 4), ("conv_tr_k", 4), ("conv_wgrad_k", 4))
 FAMILY_NAME = {0: "conv_tc_fwd_k (tcgen05, one tile per CTA: fwd + dgrad of the small convs)",
                1: "conv_tc_ws_k (tcgen05, weight-stationary persistent)", 2: "conv_tc_wt_k (tcgen05, stacked cond_var.0)",
-               3: "conv_tc_wgrad_k (tcgen05 weight gradients)", 4: "fp32 CUDA-core convs (grouped k41 s4 D layers, 1-channel stems, FIR)",
+               3: "conv_tc_wgrad_k (tcgen05 weight gradients)", 4: "fp32 CUDA-core convs (1-channel stems, 8-channel excitation pyramid, FIR filters)",
                5: "fused MRF chain kernels (tcgen05)"}
 
 

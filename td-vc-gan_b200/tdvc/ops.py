@@ -2018,15 +2018,19 @@ class _MRFStage(torch.autograd.Function):
         a1, h0 = [], []
         res, res_stride = x, 0
         xs = None
+        needs_bwd = any(ctx.needs_input_grad)
         for j in range(D):
             a1j = torch.empty(B, T, G * Cx, device=dev, dtype=torch.bfloat16)
-            h0j = torch.empty(B, T, G * Cx, device=dev, dtype=torch.bfloat16) if has_cond else None
+            # the un-modulated conv result is only read by the FiLM backward: not written for a forward-only call
+            h0j = torch.empty(B, T, G * Cx, device=dev, dtype=torch.bfloat16) if (has_cond and needs_bwd) else None
             kw = dict(xp=X[j], wp=wconv[j][0], bias=wconv[j][2], B=B, Tp=T + 2 * H[j], Tout=T, K=Kmax, dilation=ds[j], t_off=0,
                       Cp_total=X[j].shape[2], groups=G, a_ch_off=0, a_ch_stride=(0 if j == 0 else Cx), Cinp_g=Cx, Cout_g=Cx,
                       Coutp_g=Cx, bias_stride=Cx, out_act=ACT_LRELU, out_slope=slope, out_packed=1, yp=a1j, tp_out=T,
                       cp_out=G * Cx, out_halo=0, out_ch_off=0, out_ch_stride=Cx, chain_mode=3, kg=ks)
             if has_cond:
-                kw.update(gb=gb.data_ptr() + 4 * j * gb_blk, gb_grp_stride=D * gb_blk, yp2=h0j)
+                kw.update(gb=gb.data_ptr() + 4 * j * gb_blk, gb_grp_stride=D * gb_blk)
+                if h0j is not None:
+                    kw.update(yp2=h0j)
             _tc_conv(**kw)
             xs = torch.empty(G, B, Cx, T, device=dev, dtype=torch.float32)
             Hn = H[j + 1] if j + 1 < D else 0
