@@ -65,6 +65,7 @@ def _st():
 
 
 def _req(*ts):
+    cur = None
     for t in ts:
         if t is None:
             continue
@@ -73,6 +74,12 @@ def _req(*ts):
                                f"{t.device} tensor")
         if t.dtype != torch.float32:
             raise RuntimeError(f"tdvc ops are fp32 at the boundary; got {t.dtype}")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            # kernels are launched on the current device's current stream
+            raise RuntimeError(f"tdvc ops run on the current CUDA device (cuda:{cur}); got a {t.device} tensor -- wrap the call "
+                               "in torch.cuda.device(...)")
 
 
 def _c(t: Optional[torch.Tensor]):
