@@ -207,6 +207,12 @@ int tdvc_adamw_multi(float* const* params, const float* const* grads, float* con
                      float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                      float grad_scale, float* step_dev /* optional device step counter: incremented, then used
                      for the bias corrections instead of `step` (CUDA-graph replay) */, void* stream);
+/*      the same update with the work cut into equal blocks by the caller: blocks[n_blocks][2] = (tensor index, first element),
+ *      a device array of int32 pairs, one CTA per block of 4096 elements (the form FusedAdamW uses: a 5 M-element layer next
+ *      to 700 small tensors is spread over 1280 CTAs instead of 64). */
+int tdvc_adamw_blocks(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                      const int64_t* sizes, const int32_t* blocks, int n_blocks, float lr, float beta1, float beta2, float eps,
+                      float weight_decay, int step, float grad_scale, float* step_dev, void* stream);
 
 /* ---- bf16 tensor-core path (tcgen05 / TMEM / TMA), dense stride-1 Conv1d as implicit GEMM.
  *      pack: x[B,C,T] fp32 NCW -> xp[B, Tp, Cp] bf16 channels-last with LeakyReLU(in_slope) and

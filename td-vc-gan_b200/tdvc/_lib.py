@@ -113,6 +113,7 @@ SIGNATURES = {
     "tdvc_abs_diff_bwd_multi": (_I, [C.POINTER(L1Job), _I, _P, _P]),
     "tdvc_contrastive_dir": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
     "tdvc_adamw_multi": (_I, [_P, _P, _P, _P, _P, _I, _L, _F, _F, _F, _F, _F, _I, _F, _P, _P]),
+    "tdvc_adamw_blocks": (_I, [_P, _P, _P, _P, _P, _P, _I, _F, _F, _F, _F, _F, _I, _F, _P, _P]),
     "tdvc_pack_cl_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _I, _I, _I, _P, _P]),
     "tdvc_cond_pack_cl": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "tdvc_pack_cl_bf16_masked": (_I, [_P, _P, _F, _P, _I, _I, _I, _I, _I, _P, _P]),

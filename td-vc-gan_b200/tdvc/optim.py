@@ -15,6 +15,8 @@ import torch
 
 from . import _lib
 
+_BLOCK = 4096          # elements per CTA of tdvc_adamw_blocks (ADAMW_BLOCK in csrc/misc.cu)
+
 
 class FusedAdamW(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
@@ -87,6 +89,10 @@ class FusedAdamW(torch.optim.Optimizer):
                    v=mk([self.state[p]["exp_avg_sq"].data_ptr() for p in params]),
                    n=mk([p.numel() for p in params]), max_n=max(p.numel() for p in params), count=len(params),
                    step=torch.zeros(1, device=dev, dtype=torch.float32))
+        # equal blocks of _BLOCK elements over all tensors: (tensor index, first element) per CTA of tdvc_adamw_blocks
+        blocks = [(ti, s) for ti, p in enumerate(params) for s in range(0, p.numel(), _BLOCK)]
+        tab["blk"] = torch.tensor(blocks, dtype=torch.int32).reshape(-1, 2).to(dev)
+        tab["n_blk"] = len(blocks)
         if cached is not None:
             tab["step"] = cached["step"]
         elif gi in getattr(self, "_restored_steps", {}):
@@ -137,7 +143,7 @@ class FusedAdamW(torch.optim.Optimizer):
             b1, b2 = group["betas"]
             st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
             vp = lambda t: C.c_void_p(t.data_ptr())
-            _lib.check(lib.tdvc_adamw_multi(vp(tab["p"]), vp(tab["g"]), vp(tab["m"]), vp(tab["v"]), vp(tab["n"]),
-                                            tab["count"], tab["max_n"], group["lr"], b1, b2, group["eps"],
-                                            group["weight_decay"], 0, float(grad_scale), vp(tab["step"]), st), "adamw_multi")
+            _lib.check(lib.tdvc_adamw_blocks(vp(tab["p"]), vp(tab["g"]), vp(tab["m"]), vp(tab["v"]), vp(tab["n"]), vp(tab["blk"]),
+                                             tab["n_blk"], group["lr"], b1, b2, group["eps"], group["weight_decay"], 0,
+                                             float(grad_scale), vp(tab["step"]), st), "adamw_blocks")
         return loss
