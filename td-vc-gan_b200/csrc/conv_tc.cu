@@ -28,6 +28,9 @@ struct TcP {
   // weight-stationary kernel, narrow tiles: the 16 epilogue warps form 4 / epi_spt teams of epi_spt column sets; team k takes
   // the CTA's tiles k, k + teams, ... and nacc = 2 * teams accumulators are in flight (0 = one team of 4 sets, 2 accumulators)
   int epi_spt, nacc;
+  // conv_tc_fwdh_k: the activation tile is loaded ONCE per 64-channel chunk with its (K-1)*dil halo rows (a_rows rows, two
+  // stages) and the weight tiles stream through their own ring of b_stages
+  int a_rows, b_stages;
   int out_act;
   float out_slope;
   const float* bias;
@@ -656,6 +659,118 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) conv_tc_ws_k(const __grid_c
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------ streamed weights, haloed tile
+// conv_tc_fwd_k for K > 1 with the activation side of conv_tc_ws_k: per 64-channel chunk the 128-step tile is loaded once
+// with its (K-1)*dil halo rows and the K taps are row-shifted descriptor views of it, while the weight tiles (too large to be
+// resident: the 1024-channel discriminator layers, the 1296-channel data gradient of cond_var.0, the C >= 128 MRF stages)
+// stream through their own ring.  conv_tc_fwd_k re-loads the activation tile for every tap: (16 KB + BN x 128 B) per 4 MMAs
+// is 66 B/cycle at BN = 144 -- the L2 -> SM port, not the tensor core, set its pace (428 us for the cond_var.0 data gradient
+// against 230 us of MMA issue).
+template <int ACT, int EPI, int OUT, int MASK>
+__global__ void __launch_bounds__(TC_FWD_THREADS) conv_tc_fwdh_k(const __grid_constant__ CUtensorMap map_a,
+                                                                 const __grid_constant__ CUtensorMap map_b, TcP p) {
+  pdl_prologue();
+  __shared__ __align__(16) float bias_s[256];
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr int A_ST = 2;
+  const int a_bytes = p.a_rows * 128, b_bytes = p.BN * TC_BK * 2;
+  uint8_t* ring_a = smem;
+  uint8_t* ring_b = smem + (size_t)A_ST * a_bytes;
+  uint64_t* full_a = reinterpret_cast<uint64_t*>(ring_b + (size_t)p.b_stages * b_bytes);
+  uint64_t* empty_a = full_a + A_ST;
+  uint64_t* full_b = empty_a + A_ST;
+  uint64_t* empty_b = full_b + p.b_stages;
+  uint64_t* tmem_full_bar = empty_b + p.b_stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t0 = blockIdx.x * TC_BM;
+  const int grp = blockIdx.y / p.tiles_per_group;
+  const int n0 = (blockIdx.y - grp * p.tiles_per_group) * p.BN;
+  for (int i = threadIdx.x; i < p.BN; i += TC_FWD_THREADS)
+    bias_s[i] = (p.bias && n0 + i < p.Cout) ? __ldg(p.bias + grp * p.bias_stride + n0 + i) : 0.f;
+  const int b = blockIdx.z;
+  const int kgrp = p.kg[grp & 3] > 0 ? p.kg[grp & 3] : p.K;
+  const int tap_lo = (p.K - kgrp) >> 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    for (int s = 0; s < A_ST; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
+    for (int s = 0; s < p.b_stages; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int itb = 0;
+      for (int ck = 0; ck < p.nchunk; ++ck) {
+        const int sa = ck % A_ST;
+        mbar_wait(&empty_a[sa], ((uint32_t)(ck / A_ST) & 1u) ^ 1u);
+        mbar_expect_tx(&full_a[sa], (uint32_t)a_bytes);
+        tma_load_3d(ring_a + (size_t)sa * a_bytes, &map_a, &full_a[sa], p.a_ch_off + grp * p.a_ch_stride + ck * TC_BK, t0 + p.t_off, b);
+        for (int tl = 0; tl < kgrp; ++tl, ++itb) {
+          const int sb = itb % p.b_stages;
+          mbar_wait(&empty_b[sb], ((uint32_t)(itb / p.b_stages) & 1u) ^ 1u);
+          mbar_expect_tx(&full_b[sb], (uint32_t)b_bytes);
+          tma_load_3d(ring_b + (size_t)sb * b_bytes, &map_b, &full_b[sb], ck * TC_BK, grp * p.coutp_g + n0, tap_lo + tl);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    const uint64_t d128 = make_sw128_kmajor_desc(0);
+    const uint32_t hi128 = (uint32_t)(d128 >> 32), lo_flags = (uint32_t)d128;
+    const uint32_t a_lo0 = lo_flags | ((smem_u32(ring_a) & 0x3FFFF) >> 4);
+    const uint32_t b_lo0 = lo_flags | ((smem_u32(ring_b) & 0x3FFFF) >> 4);
+    const uint32_t a_stage16 = (uint32_t)a_bytes >> 4, b_stage16 = (uint32_t)b_bytes >> 4;
+    const uint32_t tap_step16 = (uint32_t)p.dil * 8u;                    // dil rows x 128 B
+    int itb = 0;
+    for (int ck = 0; ck < p.nchunk; ++ck) {
+      const int sa = ck % A_ST;
+      mbar_wait(&full_a[sa], (uint32_t)(ck / A_ST) & 1u);
+      tc_fence_after();
+      const int nk = (ck == p.nchunk - 1) ? p.last_nk16 : (TC_BK / 16);
+      for (int tl = 0; tl < kgrp; ++tl, ++itb) {
+        const int sb = itb % p.b_stages;
+        mbar_wait(&full_b[sb], (uint32_t)(itb / p.b_stages) & 1u);
+        tc_fence_after();
+        if (elect_one()) {
+          // row-shifted view of the haloed tile (the 128B swizzle is a function of the absolute shared-memory address)
+          const uint32_t a_lo = a_lo0 + (uint32_t)sa * a_stage16 + (uint32_t)(tap_lo + tl) * tap_step16;
+          const uint32_t b_lo = b_lo0 + (uint32_t)sb * b_stage16;
+          umma_bf16_lohi(tmem_base, a_lo, hi128, b_lo, hi128, idesc, (ck > 0 || tl > 0) ? 1u : 0u);
+          if (nk > 1) umma_bf16_lohi(tmem_base, a_lo + 2, hi128, b_lo + 2, hi128, idesc, 1u);
+          if (nk > 2) umma_bf16_lohi(tmem_base, a_lo + 4, hi128, b_lo + 4, hi128, idesc, 1u);
+          if (nk > 3) umma_bf16_lohi(tmem_base, a_lo + 6, hi128, b_lo + 6, hi128, idesc, 1u);
+          umma_commit(&empty_b[sb]);
+          if (tl == kgrp - 1) {
+            umma_commit(&empty_a[sa]);
+            if (ck == p.nchunk - 1) umma_commit(tmem_full_bar);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    tc_epilogue_tile<ACT, EPI, OUT, MASK>(p, bias_s, tmem_base, b, t0, grp, n0, q, half, lane);
   }
   tc_fence_before();
   __syncthreads();
@@ -1862,6 +1977,48 @@ extern "C" int tdvc_conv1d_tc_fwd_ex(const tdvc_tc_conv* c, void* stream) {
   size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, TcP);
   KernelFn kern = nullptr;
+  {
+    // K > 1: the haloed-tile form (conv_tc_fwdh_k) when tile + halo fit one TMA box (256 rows)
+    static int halo_on = -1;     // TDVC_TC_FWD_HALO=0: development switch, per-tap activation tiles (conv_tc_fwd_k)
+    if (halo_on < 0) { const char* e = getenv("TDVC_TC_FWD_HALO"); halo_on = e ? atoi(e) : 1; }
+    const int a_rows = (TC_BM + (c->K - 1) * c->dilation + 7) / 8 * 8;
+    const long long a_bytes = (long long)a_rows * 128, b_bytes = (long long)p.BN * TC_BK * 2;
+    const int b_st = (int)std::min<long long>(6, (196LL * 1024 - 2 * a_bytes) / b_bytes);
+    if (halo_on && c->K > 1 && a_rows <= 256 && b_st >= 2) {
+      p.a_rows = a_rows; p.b_stages = b_st;
+      const size_t smem_h = (size_t)(2 * a_bytes + b_st * b_bytes) + (2 * 2 + 2 * b_st + 1) * sizeof(uint64_t) + 16 + 1024;
+      KernelFn kh = nullptr;
+      if (chain == 3) kh = conv_tc_fwdh_k<1, 3, 1, 0>;
+      else if (chain == 4) kh = conv_tc_fwdh_k<0, 4, 0, 0>;
+      else if (chain == 5) kh = conv_tc_fwdh_k<0, 5, 1, 1>;
+      else if (chain == 6) kh = conv_tc_fwdh_k<0, 6, 0, 1>;
+      else if (!c->out_packed && !mask) {
+        static const KernelFn table[3][3] = {
+            {conv_tc_fwdh_k<0, 0, 0, 0>, conv_tc_fwdh_k<0, 1, 0, 0>, conv_tc_fwdh_k<0, 2, 0, 0>},
+            {conv_tc_fwdh_k<1, 0, 0, 0>, conv_tc_fwdh_k<1, 1, 0, 0>, conv_tc_fwdh_k<1, 2, 0, 0>},
+            {conv_tc_fwdh_k<2, 0, 0, 0>, conv_tc_fwdh_k<2, 1, 0, 0>, conv_tc_fwdh_k<2, 2, 0, 0>}};
+        kh = table[act][epi];
+      } else if (!c->out_packed && mask) {
+        kh = conv_tc_fwdh_k<0, 0, 0, 1>;
+      } else if (c->out_packed && !mask) {
+        kh = act == TDVC_ACT_LRELU ? conv_tc_fwdh_k<1, 0, 1, 0> : conv_tc_fwdh_k<0, 0, 1, 0>;
+      } else {
+        kh = conv_tc_fwdh_k<0, 0, 1, 1>;
+      }
+      TDVC_CUDA(cudaFuncSetAttribute(kh, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      CUtensorMap map_a, map_b;
+      int rc = make_map_3d(&map_a, c->xp, (uint64_t)c->Cp_total, (uint64_t)c->Tp, (uint64_t)c->B, TC_BK, (uint32_t)a_rows);
+      if (rc) return rc;
+      rc = make_map_3d(&map_b, c->wp, (uint64_t)c->Cinp_g, (uint64_t)c->groups * c->Coutp_g, (uint64_t)c->K, TC_BK, (uint32_t)p.BN);
+      if (rc) return rc;
+      dim3 grid(cdiv(c->Tout, TC_BM), c->groups * p.tiles_per_group, c->B);
+      TDVC_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535);
+      tdvc::launch_k(kh, grid, TC_FWD_THREADS, smem_h, (cudaStream_t)stream, map_a, map_b, p);
+      TDVC_LAUNCH_CHECK();
+      g_flops[chain ? FLOP_TC_CHAIN : FLOP_TC_TILE] += 2.0 * c->B * c->Tout * (double)c->Cout_g * c->Cinp_g * tc_taps(c);
+      return TDVC_OK;
+    }
+  }
   if (chain == 3) kern = conv_tc_fwd_k<1, 3, 1, 0>;
   else if (chain == 4) kern = conv_tc_fwd_k<0, 4, 0, 0>;
   else if (chain == 5) kern = conv_tc_fwd_k<0, 5, 1, 1>;
