@@ -1529,6 +1529,65 @@ __global__ void __launch_bounds__(256) pack_cl_bf16_v4_k(const float* __restrict
   }
 }
 
+// The pack for short sequences (T <= 64: the discriminators' 1024-channel tail at T = 9 .. 35, the T/320 stage): the
+// 64-channel x T block of one sample is CONTIGUOUS in the NCW source, so it is read as one linear run (full sectors whatever
+// T % 4 is) and transposed through shared memory; halo rows (zero or reflect) and the LeakyReLU-backward mask as above.
+// pack_cl_bf16_k reads such tensors as 64-step rows of which half the lanes are idle (10 us per 4.6 MB tensor, 76 launches).
+__global__ void __launch_bounds__(256) pack_cl_bf16_short_k(const float* __restrict__ x, __nv_bfloat16* __restrict__ xp, int C, int T,
+                                                           int Cp, float slope, float* __restrict__ chan_sum, int c_off, int Cw,
+                                                           const float* __restrict__ mask_y, float mask_slope, int halo,
+                                                           int pad_mode) {
+  pdl_prologue();
+  __shared__ float tile[64][65];
+  const int b = blockIdx.y, c0 = blockIdx.x * 64;
+  const int nch = min(64, C - c0);                       // source channels of this block (<= 0: padding channels only)
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const long long base = ((long long)b * C + c0) * T;
+  const int n = max(nch, 0) * T;
+  for (int i0 = threadIdx.x; i0 < n; i0 += 256 * 4) {
+    float v[4], m[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + 256 * u;
+      v[u] = i < n ? __ldg(x + base + i) : 0.f;
+      m[u] = (mask_y && i < n) ? __ldg(mask_y + base + i) : 1.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + 256 * u;
+      if (i < n) {
+        const int c = i / T, t = i - c * T;
+        tile[c][t] = (m[u] > 0.f) ? v[u] : v[u] * mask_slope;
+      }
+    }
+  }
+  __syncthreads();
+  if (chan_sum && (int)threadIdx.x < nch) {              // bias gradient: per-channel sum of the (masked) source
+    float sum = 0.f;
+    for (int t = 0; t < T; ++t) sum += tile[threadIdx.x][t];
+    atomicAdd(chan_sum + c0 + threadIdx.x, sum);
+  }
+  const int c = c0 + 2 * lane;
+  if (c >= Cw) return;
+  const int Tp = T + 2 * halo;
+  for (int tp = wrp; tp < Tp; tp += 8) {
+    int u = tp - halo;
+    bool ok = true;
+    if (u < 0) { if (pad_mode == TDVC_PAD_REFLECT) { u = -u; ok = u < T; } else ok = false; }
+    else if (u >= T) { if (pad_mode == TDVC_PAD_REFLECT) { u = 2 * (T - 1) - u; ok = u >= 0; } else ok = false; }
+    float o0 = 0.f, o1 = 0.f;
+    if (ok) {
+      if (2 * lane < nch) o0 = tile[2 * lane][u];
+      if (2 * lane + 1 < nch) o1 = tile[2 * lane + 1][u];
+      o0 = o0 > 0.f ? o0 : o0 * slope;
+      o1 = o1 > 0.f ? o1 : o1 * slope;
+    }
+    __nv_bfloat16* dst = xp + ((long long)b * Tp + tp) * Cp + c_off + c;
+    if (c + 1 < Cw) *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(o0, o1);
+    else *dst = __float2bfloat16(o0);
+  }
+}
+
 // The decoder's conditioning tensor cat([speaker code repeated over time, excitation pyramid level]) (model/generator.py:
 // 387-399) written straight into the bf16 channels-last operand of the cond_var convs: cp[b, t, 0..Cc) = c[b, :] (constant
 // over time), cp[b, t, Cc..Cc+Ce) = e[b, :, t], cp[b, t, Cc+Ce] = 1 (the bias-gradient channel), zero up to Cg.  The fp32
@@ -1622,7 +1681,10 @@ static int pack_cl_bf16_launch(const float* x, void* xp, int B, int C, int T, in
   __nv_bfloat16* o = (__nv_bfloat16*)xp;
   // thin tensors: fewer channel rows, longer time tiles (same bytes in flight per CTA)
   const bool v4 = T % 4 == 0 && !film_gb && ones_ch < 0 && (uintptr_t)x % 16 == 0 && (!mask_y || (uintptr_t)mask_y % 16 == 0);
-  if (C <= 16 && Cw <= 64) {
+  if (T <= 64 && !film_gb && ones_ch < 0 && B <= 65535) {
+    tdvc::launch_k(pack_cl_bf16_short_k, dim3(cdiv(Cw, 64), B), 256, 0, st, x, o, C, T, Cp, in_slope, chan_sum, c_off, Cw, mask_y,
+                   mask_slope, halo, pad_mode);
+  } else if (C <= 16 && Cw <= 64) {
     dim3 grid(cdiv(v4 ? T : Tp, 256), 1, B);
     if (v4) tdvc::launch_k(pack_cl_bf16_v4_k<16>, grid, 256, 0, st, x, o, C, T, Cp, in_slope, chan_sum, c_off, Cw, mask_y, mask_slope, halo,
                            pad_mode);

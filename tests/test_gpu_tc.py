@@ -110,7 +110,8 @@ def test_pack_kernels_exact():
     assert torch.equal(wt, ref)
 
 
-@pytest.mark.parametrize("B,C,T,Cp", [(2, 16, 520, 16), (3, 20, 260, 32), (2, 64, 132, 64), (2, 100, 68, 112), (1, 8, 1024, 16)])
+@pytest.mark.parametrize("B,C,T,Cp", [(2, 16, 520, 16), (3, 20, 260, 32), (2, 64, 132, 64), (2, 100, 68, 112), (1, 8, 1024, 16),
+                                      (4, 70, 35, 80), (2, 1024, 9, 1024), (3, 130, 64, 144), (2, 16, 18, 16)])
 def test_pack_vectorized_and_masked_exact(B, C, T, Cp):
     """The un-haloed pack with 16-byte loads (T % 4 == 0) and its masked form (LeakyReLU backward applied while packing dL/dy,
     per-channel sums = bias gradient): bit-exact layout, sums to fp32 accuracy."""
@@ -129,6 +130,16 @@ def test_pack_vectorized_and_masked_exact(B, C, T, Cp):
                                                 torch.cuda.current_stream().cuda_stream), "masked pack")
     masked = x * torch.where(y > 0, 1.0, 0.2)
     assert torch.equal(dyp.cpu(), F.pad(masked.to(torch.bfloat16).permute(0, 2, 1), (0, Cp - C)))
+    assert relerr(db, masked.double().sum(dim=(0, 2))) < 1e-5
+    # zero and reflect halos (the short-sequence kernel for T <= 64, the vectorised one for T % 4 == 0, else the scalar one)
+    for halo, mode, name in ((2, 0, "constant"), (3, 1, "reflect")):
+        xh = ops._pack_act(xd, Cp, halo, mode, 0.2, cache=False)
+        ref = F.pad(F.leaky_relu(x, 0.2), (halo, halo), mode=name).to(torch.bfloat16)
+        assert torch.equal(xh.cpu(), F.pad(ref.permute(0, 2, 1), (0, Cp - C))), (halo, name)
+    dyh = torch.empty(B, T + 4, Cp, device="cuda", dtype=torch.bfloat16)
+    ops._lib.check(lib.tdvc_pack_cl_bf16_masked(xd.data_ptr(), yd.data_ptr(), 0.2, dyh.data_ptr(), B, C, T, Cp, 2, db.data_ptr(),
+                                                torch.cuda.current_stream().cuda_stream), "masked pack, halo")
+    assert torch.equal(dyh.cpu(), F.pad(F.pad(masked, (2, 2)).to(torch.bfloat16).permute(0, 2, 1), (0, Cp - C)))
     assert relerr(db, masked.double().sum(dim=(0, 2))) < 1e-5
 
 
