@@ -242,6 +242,16 @@ int tdvc_pack_weight_bf16(const float* w, void* wp, int Cout, int Cin, int K, in
                           int transpose_flip, int R_total, int r_off, int Q_total, int q_off, void* stream);
 /* (R_total, r_off, Q_total, q_off): write the packed block at row r_off / column q_off of a larger
  * wp[K][R_total][Q_total] holding several convs' weights (grouped launches); <= 0 totals mean "the block is all". */
+/* a list of small packs in one launch (job table by value): kind 0 = the weight block of tdvc_pack_weight_bf16 (src fp32
+ * [Cout][Cin][K] -> rows [r_off, r_off+Rp) x columns [q_off, q_off+Qp) of dst bf16 [K][R_total][Q_total]; flip = transposed
+ * with reversed taps), kind 1 = Rp floats of a bias vector at dst: the first Cout from src (may be NULL), zeros after. */
+#define TDVC_PACK_MAX_JOBS 40
+typedef struct tdvc_pack_job {
+  const void* src;
+  void* dst;
+  int32_t kind, Cout, Cin, K, Rp, Qp, flip, R_total, r_off, Q_total, q_off, pad_;
+} tdvc_pack_job;
+int tdvc_pack_jobs(const tdvc_pack_job* jobs, int n_jobs, void* stream);
 /* MANY weights in one launch: jobs = device int64[n_jobs][8] {offset of w inside flat_w (floats), offset of wp inside
  * flat_wp (bf16 elements), Cout, Cin, K, Rp, Qp, transpose_flip}; job output layout [K][Rp][Qp] as above. */
 int tdvc_pack_weight_bf16_multi(const void* jobs, int n_jobs, int blocks_per_job, const float* flat_w, void* flat_wp,

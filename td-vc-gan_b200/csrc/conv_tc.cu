@@ -1637,6 +1637,38 @@ __global__ void pack_weight_bf16_k(const float* __restrict__ w, __nv_bfloat16* _
   }
 }
 
+// A list of small packs in ONE launch, the job table passed by value (the sources are this step's weight-norm outputs: a
+// device-resident table would need an uncapturable host-to-device copy per step).  kind 0: the block of pack_weight_bf16_k
+// (rows [r_off, r_off + Rp) x columns [q_off, q_off + Qp) of wp[K][R_total][Q_total]); kind 1: Rp floats of a bias vector,
+// the first Cout from src, zeros after.  The conditioning path of an MRF stage packed its 2 x 9 weights and biases with 36 + 36
+// launches per stage and direction (144 of the step's 161 pack_weight_bf16_k launches).
+struct PackJobs { tdvc_pack_job j[TDVC_PACK_MAX_JOBS]; };
+
+__global__ void __launch_bounds__(256) pack_jobs_k(const __grid_constant__ PackJobs J) {
+  pdl_prologue();
+  const tdvc_pack_job& e = J.j[blockIdx.y];
+  if (e.kind == 1) {
+    float* dst = reinterpret_cast<float*>(e.dst);
+    const float* src = reinterpret_cast<const float*>(e.src);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < e.Rp; i += gridDim.x * blockDim.x)
+      dst[i] = (src && i < e.Cout) ? __ldg(src + i) : 0.f;
+    return;
+  }
+  const float* w = reinterpret_cast<const float*>(e.src);
+  __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(e.dst);
+  const int nrq = e.Rp * e.Qp;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nrq; i += gridDim.x * blockDim.x) {
+    const int rr = i / e.Qp, qq = i - rr * e.Qp;
+    const int co = e.flip ? qq : rr, ci = e.flip ? rr : qq;
+    const bool ok = co < e.Cout && ci < e.Cin;
+    const float* src = w + ((long long)co * e.Cin + ci) * e.K;
+    for (int k = 0; k < e.K; ++k) {
+      const float v = ok ? __ldg(src + (e.flip ? e.K - 1 - k : k)) : 0.f;
+      wp[((long long)k * e.R_total + e.r_off + rr) * e.Q_total + e.q_off + qq] = __float2bfloat16(v);
+    }
+  }
+}
+
 // Many weights in one launch: job[j] = {src offset in flat_w (floats), dst offset in flat_wp (bf16), Cout, Cin, K, Rp, Qp,
 // transpose_flip}; blockIdx.y = job, blockIdx.x strides over the job's K*Rp*Qp outputs (layout of pack_weight_bf16_k
 // with R_total = Rp, Q_total = Qp).
@@ -1742,6 +1774,29 @@ extern "C" int tdvc_pack_weight_bf16(const float* w, void* wp, int Cout, int Cin
   int blocks = (int)std::min<long long>((n + 255) / 256, 8LL * num_sms());
   tdvc::launch_k(pack_weight_bf16_k, blocks, 256, 0, (cudaStream_t)stream, w, (__nv_bfloat16*)wp, Cout, Cin, K, Rp, Qp, transpose_flip, R_total,
                                                                        r_off, Q_total, q_off);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_pack_jobs(const tdvc_pack_job* jobs, int n_jobs, void* stream) {
+  TDVC_CHECK_ARG(jobs && n_jobs >= 0 && n_jobs <= TDVC_PACK_MAX_JOBS);
+  if (n_jobs == 0) return TDVC_OK;
+  PackJobs J{};
+  long long max_n = 1;
+  for (int i = 0; i < n_jobs; ++i) {
+    const tdvc_pack_job& e = jobs[i];
+    TDVC_CHECK_ARG(e.dst && (e.kind == 0 || e.kind == 1) && e.Rp >= 0);
+    if (e.kind == 0) {
+      TDVC_CHECK_ARG(e.src && e.Cout > 0 && e.Cin > 0 && e.K > 0 && e.Qp > 0 && e.r_off >= 0 && e.q_off >= 0 &&
+                     e.r_off + e.Rp <= e.R_total && e.q_off + e.Qp <= e.Q_total);
+      max_n = std::max(max_n, (long long)e.Rp * e.Qp);
+    } else {
+      max_n = std::max(max_n, (long long)e.Rp);
+    }
+    J.j[i] = e;
+  }
+  const int bx = (int)std::min<long long>(cdiv(max_n, 256), 64);
+  tdvc::launch_k(pack_jobs_k, dim3(bx, n_jobs), 256, 0, (cudaStream_t)stream, J);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }

@@ -40,6 +40,15 @@ class TcConv(C.Structure):
                 ("flat_T", C.c_int32)]
 
 
+class PackJob(C.Structure):
+    """struct tdvc_pack_job"""
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p)] + \
+               [(n, C.c_int32) for n in ("kind", "Cout", "Cin", "K", "Rp", "Qp", "flip", "R_total", "r_off", "Q_total", "q_off", "pad_")]
+
+
+PACK_MAX_JOBS = 40
+
+
 class L1Job(C.Structure):
     """struct tdvc_l1_job"""
     _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("da", C.c_void_p), ("n", C.c_int64), ("scale", C.c_float)]
@@ -116,6 +125,7 @@ SIGNATURES = {
     "tdvc_adamw_blocks": (_I, [_P, _P, _P, _P, _P, _P, _I, _F, _F, _F, _F, _F, _I, _F, _P, _P]),
     "tdvc_pack_cl_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _I, _I, _I, _P, _P]),
     "tdvc_cond_pack_cl": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "tdvc_pack_jobs": (_I, [_P, _I, _P]),
     "tdvc_pack_cl_bf16_masked": (_I, [_P, _P, _F, _P, _I, _I, _I, _I, _I, _P, _P]),
     "tdvc_pack_weight_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "tdvc_conv1d_tc_wgrad_ws": (_L, [_I, _I, _I]),

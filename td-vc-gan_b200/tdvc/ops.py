@@ -1729,6 +1729,20 @@ def wgrad2(*, dyp, xp, B, Cdp, Tout, Cp, Tp, Cout, Cin, K, dilation, ngroups=1, 
     _lib.check(lib.tdvc_conv1d_tc_wgrad2(C.byref(c), _st()), "conv1d_tc_wgrad2")
 
 
+def _pack_jobs(jobs):
+    """tdvc_pack_jobs: jobs = list of dicts (src tensor or None, dst tensor, dst element offset, kind, geometry)."""
+    lib = _lib.load()
+    for lo in range(0, len(jobs), _lib.PACK_MAX_JOBS):
+        part = jobs[lo:lo + _lib.PACK_MAX_JOBS]
+        arr = (_lib.PackJob * len(part))()
+        for a, j in zip(arr, part):
+            a.src = j["src"].data_ptr() if j.get("src") is not None else None
+            a.dst = j["dst"].data_ptr() + j.get("dst_off", 0) * j["dst"].element_size()
+            for k in ("kind", "Cout", "Cin", "K", "Rp", "Qp", "flip", "R_total", "r_off", "Q_total", "q_off"):
+                setattr(a, k, int(j.get(k, 0)))
+        _lib.check(lib.tdvc_pack_jobs(arr, len(part), _st()), "pack_jobs")
+
+
 def _cond_path_forward(c, slope, w0s, b0s, w2s, b2s, parts=None):
     """gamma|beta of all n FiLM blocks of a stage: gb[n, B, 2C, T] fp32 and what the backward needs (see _MRFCondPath).
     parts = (speaker code [B, Cs], excitation [B, Ce, T]): the conditioning cat([code over time, excitation]) given as its
@@ -1765,16 +1779,22 @@ def _cond_path_forward(c, slope, w0s, b0s, w2s, b2s, parts=None):
     def pack_fwd():
         w0p = torch.empty(K, R0, Cg, device=dev, dtype=torch.bfloat16)
         w2p = torch.empty(K, n * C2p, Cg, device=dev, dtype=torch.bfloat16)
-        b0p = torch.zeros(R0, device=dev, dtype=torch.float32)
-        b2p = torch.zeros(n * C2p, device=dev, dtype=torch.float32)
+        b0p = torch.empty(R0, device=dev, dtype=torch.float32)
+        b2p = torch.empty(n * C2p, device=dev, dtype=torch.float32)
+        # ONE launch for the 2n weight blocks and 2n bias slices.  Stacked form (pitch0 = Cc < Cg): block j owns rows
+        # [j*Cc, (j+1)*Cc); only the last block also writes the Cg - Cc zero rows behind it (no two jobs touch the same row)
+        keep, jobs = [], []
         for j in range(n):
             w0, w2 = _c(w0s[j]), _c(w2s[j])
-            _lib.check(lib.tdvc_pack_weight_bf16(_p(w0), _p(w0p), Cc, Cc, K, Cg, Cg, 0, R0, j * pitch0, Cg, 0, _st()), "pack w0")
-            _lib.check(lib.tdvc_pack_weight_bf16(_p(w2), _p(w2p), C2, Cc, K, C2p, Cg, 0, n * C2p, j * C2p, Cg, 0, _st()), "pack w2")
-            if b0s[j] is not None:
-                b0p[j * pitch0:j * pitch0 + Cc].copy_(b0s[j])
-            if b2s[j] is not None:
-                b2p[j * C2p:j * C2p + C2].copy_(b2s[j])
+            keep += [w0, w2]
+            rows0 = Cg if j == n - 1 else pitch0
+            jobs.append(dict(src=w0, dst=w0p, kind=0, Cout=Cc, Cin=Cc, K=K, Rp=rows0, Qp=Cg, flip=0, R_total=R0, r_off=j * pitch0,
+                             Q_total=Cg, q_off=0))
+            jobs.append(dict(src=w2, dst=w2p, kind=0, Cout=C2, Cin=Cc, K=K, Rp=C2p, Qp=Cg, flip=0, R_total=n * C2p, r_off=j * C2p,
+                             Q_total=Cg, q_off=0))
+            jobs.append(dict(src=_c(b0s[j]), dst=b0p, dst_off=j * pitch0, kind=1, Cout=Cc, Rp=rows0))
+            jobs.append(dict(src=_c(b2s[j]), dst=b2p, dst_off=j * C2p, kind=1, Cout=C2, Rp=C2p))
+        _pack_jobs(jobs)
         return w0p, w2p, b0p, b2p
 
     # the generator runs several times per training iteration on the same weights: packed once per step scope
@@ -1826,11 +1846,14 @@ def _cond_path_backward(dims, cp, g1p, w0s, w2s, has_b0, has_b2, dgbp, need_dc):
     def pack_bwd():
         w2tp = torch.empty(K, n * Cg, C2p, device=dev, dtype=torch.bfloat16)
         w0tp = torch.empty(K, Cg, n * Cg, device=dev, dtype=torch.bfloat16)
+        jobs = []
         for j in range(n):
-            _lib.check(lib.tdvc_pack_weight_bf16(_p(w2s[j]), _p(w2tp), C2, Cc, K, C2p, Cg, 1, n * Cg, j * Cg, C2p, 0, _st()),
-                       "pack w2^T")
-            _lib.check(lib.tdvc_pack_weight_bf16(_p(w0s[j]), _p(w0tp), Cc, Cc, K, Cg, Cg, 1, Cg, 0, n * Cg, j * Cg, _st()),
-                       "pack w0^T")
+            # transposed, tap-reversed operands of the two data-gradient convs (one launch for all 2n blocks)
+            jobs.append(dict(src=w2s[j], dst=w2tp, kind=0, Cout=C2, Cin=Cc, K=K, Rp=Cg, Qp=C2p, flip=1, R_total=n * Cg, r_off=j * Cg,
+                             Q_total=C2p, q_off=0))
+            jobs.append(dict(src=w0s[j], dst=w0tp, kind=0, Cout=Cc, Cin=Cc, K=K, Rp=Cg, Qp=Cg, flip=1, R_total=Cg, r_off=0,
+                             Q_total=n * Cg, q_off=j * Cg))
+        _pack_jobs(jobs)
         return w2tp, w0tp
 
     w2tp, w0tp = _step_cached(("cond_bwd",), list(w0s) + list(w2s), pack_bwd)
