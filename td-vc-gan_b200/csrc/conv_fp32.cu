@@ -543,7 +543,10 @@ __global__ void channel_sum_k(const float* __restrict__ dy, float* __restrict__ 
 // thread p owns the pair (co, k) = (p / K, p % K) -- the 15 taps of a channel read consecutive shared-memory words, the dy
 // value is a broadcast -- and adds its partial sum with one atomic.  The general kernel above spends 160 us on the
 // discriminator stem at B = 32 (a few CTAs walk the whole tensor); this one reads dy once at full rate.
-constexpr int STEM_TT = 1024, STEM_SUB = 256;
+// 256-step chunks: a CTA's work is a chain of dependent global-load rounds (tile, then each dy sub-tile); ncu showed the kernel
+// waiting on that chain (long-scoreboard stalls 13-15 per issue, 288 CTAs of 5 rounds each: 35-50 us) -- short chains in many
+// CTAs overlap instead
+constexpr int STEM_TT = 256, STEM_SUB = 256;
 
 __global__ void __launch_bounds__(256) stem_wgrad_k(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dw,
                                                      float* __restrict__ db, int Cout, int T, int K, int dil, int pad, int pad_mode,
@@ -708,11 +711,11 @@ __global__ void __launch_bounds__(256) narrow_wgrad_k(const float* __restrict__ 
   if (db && threadIdx.x < Cout) atomicAdd(db + threadIdx.x, bsum);
 }
 
-// chunk length of narrow_wgrad_k (512 .. 128 time steps); 0 = no chunk fits
+// chunk length of narrow_wgrad_k (256 or 128 time steps: short load chains in many CTAs, see STEM_TT); 0 = no chunk fits
 static int narrow_wgrad_tt(int Cin, int Cout, int K, int stride, int dil, size_t* smem) {
   // first choice: tiles of <= 40 KB (several CTAs per SM hide the staging latency); else whatever fits 160 KB
   for (size_t budget : {(size_t)40 * 1024, (size_t)160 * 1024})
-    for (int TT = 512; TT >= 128; TT >>= 1) {
+    for (int TT = 256; TT >= 128; TT >>= 1) {
       const int span = (TT - 1) * stride + (K - 1) * dil + 1;
       const size_t need = ((size_t)((Cin * (span | 1) + 3) & ~3) + (size_t)Cout * (NARROW_SUB + 1)) * sizeof(float);
       if (need <= budget) { *smem = need; return TT; }
