@@ -48,10 +48,10 @@ inf.append(f"Best: B = {best['batch']}, **{best['x_realtime']:.0f}× real time**
 ws = next(f for f in kf["conv_families"] if "conv_tc_ws_k" in f["family"])
 dp_text = (f"Batch-sharded, full replicas, weak scaling (B = 16 per GPU). 2 GPUs: **{dp['ms_per_step']:.2f} ms/step, {dp['value']:.1f} audio-s/s = "
            f"{dp['value'] / d['value']:.3f}× the 1-GPU value of the same build** (`r2/final_dp2.json`): the iteration is three CUDA-graph segments with "
-           f"the flat all-reduces of D's (71 MB) and G's (59 MB) gradient banks between them; 4 GPUs on the previous build (22.6 ms on one GPU): 23.14 ms/step, "
+           f"the flat all-reduces of D's (71 MB) and G's (59 MB) gradient banks between them; 4 GPUs on an earlier build of the day (22.6 ms on one GPU): 23.14 ms/step, "
            f"1549 audio-s/s = 3.91× its 1-GPU value (`r2/dp4_23p1ms_build_u.json`). Hook-driven bucketed all-reduces overlapped with the "
            f"backward exist for eager steps (`tdvc/dp.py:BucketedReducer`); captured into the step graph they never returned on this stack "
-           f"(DESIGN.md §7), and with 0.3 ms of collectives against 22 ms of compute there is nothing measurable to win at this step time. "
+           f"(DESIGN.md §7), and with 0.3 ms of collectives against 21 ms of compute there is nothing measurable to win at this step time. "
            f"The 1 → 8 GPU run is the driver's (`SCALE_r02.json`).")
 rep = {
     "@FINAL_FILE@": "final_stage1.json", "@FINAL_MS@": f"{d['ms_per_step']:.2f}", "@FINAL_VALUE@": f"{d['value']:.1f}",
