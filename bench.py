@@ -261,7 +261,11 @@ def run_ours(args):
     n0 = lib.tdvc_launch_count()
     if sampler:
         sampler.start()
+    if args.profile:
+        torch.cuda.profiler.start()      # ncu --profile-from-start off: the profiled range is exactly the timed steps
     ms = timed(step_resident, args.steps)
+    if args.profile:
+        torch.cuda.profiler.stop()
     clocks = sampler.stop() if sampler else None
     launches = launches_per_step if launches_per_step is not None else (lib.tdvc_launch_count() - n0) / max(1, args.steps)
     if args.profile:
@@ -415,6 +419,16 @@ def time_dominant_roofline(fams, pk, ms_step, step_gflop, flop_dom):
                     share_of_step_time=round(fam["ms"] / ms_step, 4),
                     how="2*MAC handed to the family per step (tdvc_flop_count) / its busy time in one CUDA-graph replay "
                         "(CUPTI, taken inside bench.py after the timed region)")
+        try:   # DRAM bytes per launch of this family, averaged over its launches inside one step (committed ncu capture)
+            with open(os.path.join(REPO, "profiles", "r2", "final_ncu_conv_metrics.json")) as f:
+                m = json.load(f)
+            k = m["families"][fam["family"].split(" ")[0]]
+            base.update(traffic=k["dram_bytes_per_launch"],
+                        traffic_source="profiles/r2/final_ncu_conv_metrics.json: dram__bytes_read.sum + dram__bytes_write.sum, mean "
+                                       f"over the family's {k['launches']} launches of one step (ncu, 21.3 ms/step build)",
+                        tensor_pipe_pct_of_active_ncu=k["tensor_pipe_pct_of_active"])
+        except Exception:
+            pass
     except Exception:
         base.update(achieved=flop_dom["achieved"], frac=round(flop_dom["achieved"] / peak, 5), kernel=flop_dom["kernel"],
                     how="family trace unavailable: the FLOP-dominant launch timed alone")

@@ -176,6 +176,17 @@ int tdvc_select_channel_fwd(const float* x, const int64_t* label, float* y, int 
 int tdvc_select_channel_bwd(const float* dy, const int64_t* label, float* dx /*zero-filled here*/,
                             int B, int C, int T, void* stream);
 
+/* ---- the discriminator's output layer with the label gather folded in (model/discriminator.py:36 `self.output`, a
+ *      weight-normed Conv1d(width, num_classes, 3, padding=1, bias=False), followed by :49-51 `x.gather(1, label)`):
+ *      only the selected speaker's row is computed,
+ *        y[b,0,t] = sum_{c,k} w[label[b], c, k] * x[b, c, t + k - pad]      (stride 1, zero padding, 2*pad = K-1 <= 7);
+ *      a label outside [0, NC) yields zeros.  bwd: dx[B,C,T] (may be NULL) and dw[NC,C,K] (may be NULL; ACCUMULATED into,
+ *      the caller zero-fills it: samples that share a label add into the same row). */
+int tdvc_conv1d_select_fwd(const float* x, const float* w, const int64_t* label, float* y, int B, int C, int T, int NC,
+                           int K, int pad, void* stream);
+int tdvc_conv1d_select_bwd(const float* dy, const float* x, const float* w, const int64_t* label, float* dx, float* dw,
+                           int B, int C, int T, int NC, int K, int pad, void* stream);
+
 /* ---- losses (train.py:273-281,327-331 LSGAN F.mse_loss; util/losses.py:55-68 F.l1_loss).
  *      out_sum += scale * sum(...) (caller zeroes out_sum; scale carries 1/N and any lambda). */
 int tdvc_sq_err_const_sum(const float* a, float target, float scale, float* out_sum, int64_t n, void* stream);

@@ -81,8 +81,12 @@ __device__ __forceinline__ void store16_bf16(__nv_bfloat16* dst, const float* v)
   reinterpret_cast<uint4*>(dst)[0] = make_uint4(w[0], w[1], w[2], w[3]);
   reinterpret_cast<uint4*>(dst)[1] = make_uint4(w[4], w[5], w[6], w[7]);
 }
-__device__ __forceinline__ void load16_bf16(const __nv_bfloat16* src, float* v) {
-  const uint4 a = __ldg(reinterpret_cast<const uint4*>(src)), c = __ldg(reinterpret_cast<const uint4*>(src) + 1);
+// 16 packed bf16 (32 bytes) of one row: loaded as two 16-byte words, decoded later (the load can be issued long before its use)
+__device__ __forceinline__ void ld32B_bf16(const __nv_bfloat16* src, uint4& a, uint4& c) {
+  a = __ldg(reinterpret_cast<const uint4*>(src));
+  c = __ldg(reinterpret_cast<const uint4*>(src) + 1);
+}
+__device__ __forceinline__ void unpack16_bf16(const uint4& a, const uint4& c, float* v) {
   const uint32_t w[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -91,8 +95,7 @@ __device__ __forceinline__ void load16_bf16(const __nv_bfloat16* src, float* v) 
   }
 }
 // v[j] *= slope where the packed activated value is <= 0 (bf16 sign / zero test on the raw bits)
-__device__ __forceinline__ void mask16_bf16(const __nv_bfloat16* mp, float* v, float slope) {
-  const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(mp)), m1 = __ldg(reinterpret_cast<const uint4*>(mp) + 1);
+__device__ __forceinline__ void mask16_words(const uint4& m0, const uint4& m1, float* v, float slope) {
   const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
@@ -103,6 +106,71 @@ __device__ __forceinline__ void mask16_bf16(const __nv_bfloat16* mp, float* v, f
 
 __device__ __forceinline__ int epi_spt_of(const TcP& p) { return p.epi_spt > 0 ? p.epi_spt : TC_EPI_WARPS / 4; }
 
+// Operands-first epilogues.  Everything an epilogue reads from global memory besides the accumulator (LeakyReLU masks, FiLM
+// gamma | beta, residuals, the saved conv result) has an address that is known before the tile's MMAs retire, so those loads
+// are issued BEFORE the wait on the accumulator barrier and their memory round trip overlaps the MMAs instead of following
+// them: a narrow tile's epilogue was a chain of dependent round trips (TMEM load -> operand loads -> store, 2.8 us per tile
+// under ncu) and the cond_var.2 data gradient ran at 3.2 TB/s on algorithmic traffic (profiles/r2/final_ncu_conv_metrics.txt).
+// Same arithmetic in the same order: results are bit-identical.  TDVC_EPI_HOIST=0 compiles the loads back behind the wait.
+#ifndef TDVC_EPI_HOIST
+#define TDVC_EPI_HOIST 1
+#endif
+// plain mask path: column chunks per thread whose mask words are loaded ahead (packed output: 3, covers N <= 192 -- the
+// 136-channel cond_var.2 data gradient; fp32 output: 2, which keeps conv_tc_fwdh_k<0,0,0,1> inside the 56 registers ptxas
+// gives it for two resident CTAs)
+template <int OUT> struct EpiPf { static constexpr int n = OUT == 1 ? 3 : 2; };
+
+struct ChainOps {
+  uint4 m0, m1;        // modes 5, 6: packed activated tensor whose sign gates the result
+  uint4 a0, a1;        // mode 5: the packed un-modulated conv result h0
+  float g[16];         // mode 3 / 5: gamma;  mode 4 / 6: residual
+  float bt[16];        // mode 3: beta
+};
+
+template <int MODE>
+__device__ __forceinline__ void tc_chain_load(const TcP& p, int b, int t, int grp, int ch, ChainOps& o) {
+  if (MODE == 3) {
+    if (p.gb) {
+      const long long ct = p.Tout;
+      const float* gp = p.gb + (long long)grp * p.gb_grp_stride + ((long long)b * 2 * p.Cout + ch) * ct + t;
+      const long long beta_off = (long long)p.Cout * ct;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        o.g[j] = __ldg(gp + j * ct);
+        o.bt[j] = __ldg(gp + beta_off + j * ct);
+      }
+    }
+  } else if (MODE == 4) {
+    const long long ct = p.Tout;
+    const float* rp = p.res + (long long)grp * p.res_grp_stride + ((long long)b * p.Cout + ch) * ct + t;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o.g[j] = __ldg(rp + j * ct);
+  } else if (MODE == 5) {
+    const long long mrow = ((long long)b * p.tm + t + p.mask_halo) * p.cm + p.mask_ch_off + grp * p.mask_ch_stride + ch;
+    ld32B_bf16(p.maskp + mrow, o.m0, o.m1);
+    if (p.gb) {
+      ld32B_bf16(p.auxp + mrow, o.a0, o.a1);
+      const long long ct = p.Tout;
+      const float* gp = p.gb + (long long)grp * p.gb_grp_stride + ((long long)b * 2 * p.Cout + ch) * ct + t;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o.g[j] = __ldg(gp + j * ct);
+    }
+  } else if (MODE == 6) {
+    // rows are positions of the PADDED input (t_valid + 2 * halo of them); the packed activated input carries the same
+    // halo, so row t of it gates row t here -- for a halo row that is the sign of the sample it mirrors, which is the
+    // derivative the folded contribution needs
+    const long long mrow = ((long long)b * p.tm + t + p.mask_halo) * p.cm + p.mask_ch_off + grp * p.mask_ch_stride + ch;
+    ld32B_bf16(p.maskp + mrow, o.m0, o.m1);
+    const int tt = t - p.halo;
+    if (p.res && tt >= 0 && tt < p.t_valid) {
+      const long long ct = p.t_valid;
+      const float* rp = p.res + (long long)grp * p.res_grp_stride + ((long long)b * p.Cout + ch) * ct + tt;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o.g[j] = __ldg(rp + j * ct);
+    }
+  }
+}
+
 // Epilogues of the bf16-resident MRF stage (model/generator.py:69-111,175-194).  Every group is one kernel-size branch; all
 // tensors between the convolutions are bf16 channels-last with the branches side by side in the channel dimension, the
 // residual stream stays fp32 NCW [branch][B][C][T].  Channel counts are multiples of 16 (a thread's 16 columns are real).
@@ -111,13 +179,18 @@ __device__ __forceinline__ int epi_spt_of(const TcP& p) { return p.epi_spt > 0 ?
 //   MODE 5  posconv^T   d = acc * lrelu'(a1);  dgamma = d * h0, dbeta = d -> dgbp;  dh0 = d * (1 + gamma) -> yp
 //   MODE 6  conv.1^T    over the padded rows: d = acc * lrelu'(x);  interior rows: dx = d + dx' -> y fp32 and yp;
 //                       halo rows -> halo_buf (chain_fold_k adds them onto the rows they mirror)
-template <int MODE>
+// wait_acc() blocks until the accumulator is complete; the first chunk's operands are in flight by then.
+template <int MODE, typename Wait>
 __device__ __forceinline__ void tc_epilogue_chain(const TcP& p, const float* bias_s, uint32_t acc, int b, int t0, int grp,
-                                                  int n0, int q, int half, int lane) {
+                                                  int n0, int q, int half, int lane, Wait wait_acc) {
   const int t = t0 + q * 32 + lane;
   const bool t_ok = t < p.Tout;
   const int nvalid = min(p.BN, p.Cout - n0);
-  for (int c0 = (half % epi_spt_of(p)) * 16; c0 < nvalid; c0 += 16 * epi_spt_of(p)) {
+  const int step = 16 * epi_spt_of(p), first = (half % epi_spt_of(p)) * 16;
+  ChainOps o;
+  if (TDVC_EPI_HOIST && t_ok && first < nvalid) tc_chain_load<MODE>(p, b, t, grp, n0 + first, o);
+  wait_acc();
+  for (int c0 = first; c0 < nvalid; c0 += step) {
     float v[16];
     tmem_ld16(acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
     if (!t_ok) continue;
@@ -130,15 +203,13 @@ __device__ __forceinline__ void tc_epilogue_chain(const TcP& p, const float* bia
       }
     }
     const int ch = n0 + c0;                              // first of this thread's 16 channels inside the group
+    if (!TDVC_EPI_HOIST || c0 != first) tc_chain_load<MODE>(p, b, t, grp, ch, o);
     if (MODE == 3) {
       const long long prow = ((long long)b * p.tp_out + t + p.out_halo) * p.cp_out + p.out_ch_off + grp * p.out_ch_stride + ch;
       if (p.yp2) store16_bf16(p.yp2 + prow, v);
       if (p.gb) {
-        const long long ct = p.Tout;
-        const float* gp = p.gb + (long long)grp * p.gb_grp_stride + ((long long)b * 2 * p.Cout + ch) * ct + t;
-        const long long beta_off = (long long)p.Cout * ct;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], 1.f + __ldg(gp + j * ct), __ldg(gp + beta_off + j * ct));
+        for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], 1.f + o.g[j], o.bt[j]);
       }
       const float sl = p.out_slope;
 #pragma unroll
@@ -147,10 +218,9 @@ __device__ __forceinline__ void tc_epilogue_chain(const TcP& p, const float* bia
     } else if (MODE == 4) {
       const long long ct = p.Tout;
       float* yo = p.y + (long long)grp * p.y_grp_stride + (long long)b * p.y_b_stride + (long long)ch * ct + t;
-      const float* rp = p.res + (long long)grp * p.res_grp_stride + ((long long)b * p.Cout + ch) * ct + t;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        v[j] += __ldg(rp + j * ct);
+        v[j] += o.g[j];
         yo[j * ct] = v[j];
       }
       if (p.yp) {
@@ -165,37 +235,29 @@ __device__ __forceinline__ void tc_epilogue_chain(const TcP& p, const float* bia
         if (t <= p.Tout - 2 && t >= p.Tout - 1 - H) store16_bf16(col + (long long)(H + 2 * (p.Tout - 1) - t) * p.cp_out, v);
       }
     } else if (MODE == 5) {
-      const long long mrow = ((long long)b * p.tm + t + p.mask_halo) * p.cm + p.mask_ch_off + grp * p.mask_ch_stride + ch;
-      mask16_bf16(p.maskp + mrow, v, p.mask_slope);
+      mask16_words(o.m0, o.m1, v, p.mask_slope);
       if (p.gb) {
         float h0[16];
-        load16_bf16(p.auxp + mrow, h0);
+        unpack16_bf16(o.a0, o.a1, h0);
         float dg[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) dg[j] = v[j] * h0[j];
         __nv_bfloat16* dgp = p.dgbp + ((long long)b * p.Tout + t) * p.dgb_cp + p.dgb_ch_off + grp * p.dgb_ch_stride + ch;
         store16_bf16(dgp, dg);                    // dL/dgamma
         store16_bf16(dgp + p.Cout, v);            // dL/dbeta
-        const long long ct = p.Tout;
-        const float* gp = p.gb + (long long)grp * p.gb_grp_stride + ((long long)b * 2 * p.Cout + ch) * ct + t;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] *= 1.f + __ldg(gp + j * ct);
+        for (int j = 0; j < 16; ++j) v[j] *= 1.f + o.g[j];
       }
       store16_bf16(p.yp + ((long long)b * p.tp_out + t + p.out_halo) * p.cp_out + p.out_ch_off + grp * p.out_ch_stride + ch, v);
     } else if (MODE == 6) {
-      // rows are positions of the PADDED input (t_valid + 2 * halo of them); the packed activated input carries the same
-      // halo, so row t of it gates row t here -- for a halo row that is the sign of the sample it mirrors, which is the
-      // derivative the folded contribution needs
-      const long long mrow = ((long long)b * p.tm + t + p.mask_halo) * p.cm + p.mask_ch_off + grp * p.mask_ch_stride + ch;
-      mask16_bf16(p.maskp + mrow, v, p.mask_slope);
+      mask16_words(o.m0, o.m1, v, p.mask_slope);
       const int tt = t - p.halo;
       if (tt >= 0 && tt < p.t_valid) {
         const long long ct = p.t_valid;
         float* yo = p.y + (long long)grp * p.y_grp_stride + (long long)b * p.y_b_stride + (long long)ch * ct + tt;
         if (p.res) {
-          const float* rp = p.res + (long long)grp * p.res_grp_stride + ((long long)b * p.Cout + ch) * ct + tt;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] += __ldg(rp + j * ct);
+          for (int j = 0; j < 16; ++j) v[j] += o.g[j];
         }
 #pragma unroll
         for (int j = 0; j < 16; ++j) yo[j * ct] = v[j];
@@ -210,138 +272,158 @@ __device__ __forceinline__ void tc_epilogue_chain(const TcP& p, const float* bia
   }
 }
 
-// Epilogue of one 128 x BN accumulator tile at TMEM address `acc` (lane quadrant q, column half `half`).
+// One 16-column chunk (columns c0 .. c0+15 of the tile, TMEM lane quadrant q) of the plain epilogues; m0 | m1 are the
+// chunk's mask words (MASK == 1), loaded by the caller.
 template <int ACT, int EPI, int OUT, int MASK>
-__device__ __forceinline__ void tc_epilogue_tile(const TcP& p, const float* bias_s, uint32_t acc, int b, int t0, int grp,
-                                                 int n0, int q, int half, int lane) {
-    if (EPI >= 3) {
-      tc_epilogue_chain<EPI>(p, bias_s, acc, b, t0, grp, n0, q, half, lane);
-      return;
-    }
-    const int t = t0 + q * 32 + lane;
-    const bool t_ok = t < p.Tout;
-    const long long ct = p.Tout;
-    const int nvalid = min(p.BN, p.Cout - n0);          // columns of this tile that are real channels
-    for (int c0 = (half % epi_spt_of(p)) * 16; c0 < nvalid; c0 += 16 * epi_spt_of(p)) {
-      float v[16];
-      if (p.debug & 4) {
+__device__ __forceinline__ void tc_epilogue_chunk(const TcP& p, const float* bias_s, uint32_t acc, int b, int t, bool t_ok,
+                                                  int grp, int n0, int c0, int nvalid, int q, const uint4& m0, const uint4& m1) {
+  const long long ct = p.Tout;
+  float v[16];
+  if (p.debug & 4) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = (float)(c0 + j);
+    for (int j = 0; j < 16; ++j) v[j] = (float)(c0 + j);
+  } else {
+    tmem_ld16(acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+  }
+  if (!t_ok) return;
+  const int nj = min(16, nvalid - c0);
+  {
+    const float4* b4 = reinterpret_cast<const float4*>(bias_s + c0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 bb = b4[j];
+      v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+    }
+  }
+  if (MASK) mask16_words(m0, m1, v, p.mask_slope);
+  if (OUT == 0 && p.flat_tp > 0) {
+    // batch-flattened rows: t is a row of the concatenated padded samples
+    const int bb = t / p.flat_tp, tt = t - bb * p.flat_tp - p.flat_halo;
+    if (tt >= 0 && tt < p.flat_T) {
+      float* yp = p.y + ((long long)bb * p.Cout + n0 + c0) * p.flat_T + tt;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (j < nj) {
+          float o = v[j];
+          if (ACT == TDVC_ACT_LRELU) o = o > 0.f ? o : o * p.out_slope;
+          else if (ACT == TDVC_ACT_TANH) o = tanhf(o);
+          *yp = o;
+        }
+        yp += p.flat_T;
+      }
+    }
+  } else if (OUT == 0 && p.unframe_s > 0) {
+    // data gradient of a strided conv run over frames: this thread's 16 frame channels are 16 / s conv channels x s
+    // consecutive samples
+    const int s = p.unframe_s;
+    const int f0 = grp * p.Cout + n0 + c0;
+    const int u0 = s * t - p.unframe_pad;
+    // whole frames inside the signal and 16-byte aligned rows: vector stores (a warp writes 32 consecutive frames of
+    // one channel = one contiguous run); scalar stores at the edges
+    const bool vec = (s % 4 == 0) && (p.unframe_T % 4 == 0) && (p.unframe_pad % 4 == 0) && u0 >= 0 && u0 + s <= p.unframe_T;
+#pragma unroll
+    for (int j0 = 0; j0 < 16; j0 += 4) {
+      if (j0 >= nj) break;
+      float* dst = p.y + ((long long)b * p.unframe_C + (f0 + j0) / s) * p.unframe_T + u0 + (j0 % s);
+      if (vec) {
+        *reinterpret_cast<float4*>(dst) = make_float4(v[j0], v[j0 + 1], v[j0 + 2], v[j0 + 3]);
       } else {
-        tmem_ld16(acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      }
-      if (t_ok) {
-        const int nj = min(16, nvalid - c0);
-        {
-          const float4* b4 = reinterpret_cast<const float4*>(bias_s + c0);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 bb = b4[j];
-            v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
-          }
-        }
-        if (MASK) {
-          const __nv_bfloat16* mp = p.maskp + ((long long)b * p.tm + t + p.mask_halo) * p.cm + p.mask_ch_off +
-                                    grp * p.mask_ch_stride + n0 + c0;
-          uint4 m0 = __ldg(reinterpret_cast<const uint4*>(mp));
-          uint4 m1 = __ldg(reinterpret_cast<const uint4*>(mp) + 1);
-          const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            // bf16 sign/zero test on the raw bits: value <= 0  <=>  sign bit set or magnitude zero
-            const uint32_t h = (j & 1) ? (mw[j >> 1] >> 16) : (mw[j >> 1] & 0xFFFFu);
-            if ((h & 0x8000u) || (h & 0x7FFFu) == 0) v[j] *= p.mask_slope;
-          }
-        }
-        if (OUT == 0 && p.flat_tp > 0) {
-          // batch-flattened rows: t is a row of the concatenated padded samples
-          const int bb = t / p.flat_tp, tt = t - bb * p.flat_tp - p.flat_halo;
-          if (tt >= 0 && tt < p.flat_T) {
-            float* yp = p.y + ((long long)bb * p.Cout + n0 + c0) * p.flat_T + tt;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (j < nj) {
-                float o = v[j];
-                if (ACT == TDVC_ACT_LRELU) o = o > 0.f ? o : o * p.out_slope;
-                else if (ACT == TDVC_ACT_TANH) o = tanhf(o);
-                *yp = o;
-              }
-              yp += p.flat_T;
-            }
-          }
-        } else if (OUT == 0 && p.unframe_s > 0) {
-          // data gradient of a strided conv run over frames: this thread's 16 frame channels are 16 / s conv channels x s
-          // consecutive samples
-          const int s = p.unframe_s;
-          const int f0 = grp * p.Cout + n0 + c0;
-          const int u0 = s * t - p.unframe_pad;
-          // whole frames inside the signal and 16-byte aligned rows: vector stores (a warp writes 32 consecutive frames of
-          // one channel = one contiguous run); scalar stores at the edges
-          const bool vec = (s % 4 == 0) && (p.unframe_T % 4 == 0) && (p.unframe_pad % 4 == 0) && u0 >= 0 && u0 + s <= p.unframe_T;
-#pragma unroll
-          for (int j0 = 0; j0 < 16; j0 += 4) {
-            if (j0 >= nj) break;
-            float* dst = p.y + ((long long)b * p.unframe_C + (f0 + j0) / s) * p.unframe_T + u0 + (j0 % s);
-            if (vec) {
-              *reinterpret_cast<float4*>(dst) = make_float4(v[j0], v[j0 + 1], v[j0 + 2], v[j0 + 3]);
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int jj = j0 + e;                                     // frame channel f0 + jj: conv channel, phase
-                const int u = u0 + jj % s;
-                if (jj < nj && u >= 0 && u < p.unframe_T)
-                  p.y[((long long)b * p.unframe_C + (f0 + jj) / s) * p.unframe_T + u] = v[jj];
-              }
-            }
-          }
-        } else if (OUT == 0) {
-          const long long base = (long long)grp * p.y_grp_stride + (long long)b * p.y_b_stride + (long long)(n0 + c0) * ct + t;
-          float* yp = p.y + base;
-          const float* rp = p.res + base;                                   // only dereferenced when EPI asks for it
-          const float* gp = p.gb + ((long long)b * 2 * p.Cout + n0 + c0) * ct + t;
-          const long long beta_off = (long long)p.Cout * ct;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (j < nj) {
-              float o = v[j];
-              if (EPI == 2) {
-                o = fmaf(o, 1.f + __ldg(gp), __ldg(gp + beta_off));
-                if (p.res) o += __ldg(rp);
-              } else if (EPI == 1) {
-                o += __ldg(rp);
-              }
-              if (ACT == TDVC_ACT_LRELU) o = o > 0.f ? o : o * p.out_slope;
-              else if (ACT == TDVC_ACT_TANH) o = tanhf(o);
-              if (!(p.debug & 1)) *yp = o;
-            }
-            yp += ct; rp += ct; gp += ct;
-          }
-        } else {
-          // packed output: this thread owns 16 consecutive channels of one time step = 32 contiguous bytes
-          if (ACT == TDVC_ACT_LRELU) {
-            const float sl = p.out_slope;       // 0 < slope < 1: leaky_relu(o) = max(o, slope * o)
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], v[j] * sl);
-          }
-          if (nj < 16) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = (j < nj) ? v[j] : 0.f;
-          }
-          __nv_bfloat16* op = p.yp + ((long long)b * p.tp_out + t + p.out_halo) * p.cp_out + p.out_ch_off +
-                              grp * p.out_ch_stride + n0 + c0;
-          uint32_t w[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-            w[j] = *reinterpret_cast<uint32_t*>(&h2);
-          }
-          if (!(p.debug & 1)) {
-            reinterpret_cast<uint4*>(op)[0] = make_uint4(w[0], w[1], w[2], w[3]);
-            reinterpret_cast<uint4*>(op)[1] = make_uint4(w[4], w[5], w[6], w[7]);
-          }
+        for (int e = 0; e < 4; ++e) {
+          const int jj = j0 + e;                                     // frame channel f0 + jj: conv channel, phase
+          const int u = u0 + jj % s;
+          if (jj < nj && u >= 0 && u < p.unframe_T)
+            p.y[((long long)b * p.unframe_C + (f0 + jj) / s) * p.unframe_T + u] = v[jj];
         }
       }
     }
+  } else if (OUT == 0) {
+    const long long base = (long long)grp * p.y_grp_stride + (long long)b * p.y_b_stride + (long long)(n0 + c0) * ct + t;
+    float* yp = p.y + base;
+    const float* rp = p.res + base;                                   // only dereferenced when EPI asks for it
+    const float* gp = p.gb + ((long long)b * 2 * p.Cout + n0 + c0) * ct + t;
+    const long long beta_off = (long long)p.Cout * ct;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (j < nj) {
+        float o = v[j];
+        if (EPI == 2) {
+          o = fmaf(o, 1.f + __ldg(gp), __ldg(gp + beta_off));
+          if (p.res) o += __ldg(rp);
+        } else if (EPI == 1) {
+          o += __ldg(rp);
+        }
+        if (ACT == TDVC_ACT_LRELU) o = o > 0.f ? o : o * p.out_slope;
+        else if (ACT == TDVC_ACT_TANH) o = tanhf(o);
+        if (!(p.debug & 1)) *yp = o;
+      }
+      yp += ct; rp += ct; gp += ct;
+    }
+  } else {
+    // packed output: this thread owns 16 consecutive channels of one time step = 32 contiguous bytes
+    if (ACT == TDVC_ACT_LRELU) {
+      const float sl = p.out_slope;       // 0 < slope < 1: leaky_relu(o) = max(o, slope * o)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], v[j] * sl);
+    }
+    if (nj < 16) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = (j < nj) ? v[j] : 0.f;
+    }
+    __nv_bfloat16* op = p.yp + ((long long)b * p.tp_out + t + p.out_halo) * p.cp_out + p.out_ch_off +
+                        grp * p.out_ch_stride + n0 + c0;
+    if (!(p.debug & 1)) store16_bf16(op, v);
+  }
+}
+
+// Epilogue of one 128 x BN accumulator tile at TMEM address `acc` (lane quadrant q, column half `half`); wait_acc() blocks
+// until the accumulator is complete and is called once, by every thread, after the operand loads that can run ahead.
+template <int ACT, int EPI, int OUT, int MASK, typename Wait>
+__device__ __forceinline__ void tc_epilogue_tile(const TcP& p, const float* bias_s, uint32_t acc, int b, int t0, int grp,
+                                                 int n0, int q, int half, int lane, Wait wait_acc) {
+  if (EPI >= 3) {
+    tc_epilogue_chain<EPI>(p, bias_s, acc, b, t0, grp, n0, q, half, lane, wait_acc);
+    return;
+  }
+  const int t = t0 + q * 32 + lane;
+  const bool t_ok = t < p.Tout;
+  const int nvalid = min(p.BN, p.Cout - n0);          // columns of this tile that are real channels
+  const int step = 16 * epi_spt_of(p), first = (half % epi_spt_of(p)) * 16;
+  const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+  if (MASK && TDVC_EPI_HOIST) {
+    const __nv_bfloat16* mrow = p.maskp + ((long long)b * p.tm + t + p.mask_halo) * p.cm + p.mask_ch_off +
+                                grp * p.mask_ch_stride + n0;
+    constexpr int PF = EpiPf<OUT>::n;
+    uint4 mk[PF][2];
+#pragma unroll
+    for (int i = 0; i < PF; ++i) {
+      mk[i][0] = z4; mk[i][1] = z4;
+      const int c0 = first + i * step;
+      if (t_ok && c0 < nvalid) ld32B_bf16(mrow + c0, mk[i][0], mk[i][1]);
+    }
+    wait_acc();
+#pragma unroll
+    for (int i = 0; i < PF; ++i) {
+      const int c0 = first + i * step;
+      if (c0 < nvalid) tc_epilogue_chunk<ACT, EPI, OUT, MASK>(p, bias_s, acc, b, t, t_ok, grp, n0, c0, nvalid, q, mk[i][0], mk[i][1]);
+    }
+    for (int c0 = first + PF * step; c0 < nvalid; c0 += step) {
+      uint4 m0 = z4, m1 = z4;
+      if (t_ok) ld32B_bf16(mrow + c0, m0, m1);
+      tc_epilogue_chunk<ACT, EPI, OUT, MASK>(p, bias_s, acc, b, t, t_ok, grp, n0, c0, nvalid, q, m0, m1);
+    }
+  } else {
+    wait_acc();
+    for (int c0 = first; c0 < nvalid; c0 += step) {
+      uint4 m0 = z4, m1 = z4;
+      if (MASK && t_ok) {
+        const __nv_bfloat16* mp = p.maskp + ((long long)b * p.tm + t + p.mask_halo) * p.cm + p.mask_ch_off +
+                                  grp * p.mask_ch_stride + n0 + c0;
+        ld32B_bf16(mp, m0, m1);
+      }
+      tc_epilogue_chunk<ACT, EPI, OUT, MASK>(p, bias_s, acc, b, t, t_ok, grp, n0, c0, nvalid, q, m0, m1);
+    }
+  }
 }
 
 // ACT: tdvc_act of the epilogue; EPI: 0 = bias only, 1 = + residual, 2 = FiLM (+ residual when p.res);
@@ -434,9 +516,11 @@ __global__ void __launch_bounds__(TC_FWD_THREADS) conv_tc_fwd_k(const __grid_con
     // consecutive floats (one 128-byte line).
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    if (iters > 0) mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    tc_epilogue_tile<ACT, EPI, OUT, MASK>(p, bias_s, tmem_base, b, t0, grp, n0, q, half, lane);
+    auto wait_acc = [&]() {
+      if (iters > 0) mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+    };
+    tc_epilogue_tile<ACT, EPI, OUT, MASK>(p, bias_s, tmem_base, b, t0, grp, n0, q, half, lane, wait_acc);
   }
   tc_fence_before();
   __syncthreads();
@@ -651,10 +735,15 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) conv_tc_ws_k(const __grid_c
       if (i % nteams != team) continue;               // another team's tile
       const int b = m / w.mtiles_per_b, t0 = (m - b * w.mtiles_per_b) * TC_BM;
       const int acc = i % nacc;
-      mbar_wait(&tmem_full[acc], (uint32_t)(i / nacc) & 1u);
-      tc_fence_after();
+      const uint32_t acc_phase = (uint32_t)(i / nacc) & 1u;
+      auto wait_acc = [&]() {
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+      };
       if (!(p.debug & 32))
-        tc_epilogue_tile<ACT, EPI, OUT, MASK>(p, bias_s, tmem_base + (uint32_t)(acc * p.BN), b, t0, grp, n0, q, half, lane);
+        tc_epilogue_tile<ACT, EPI, OUT, MASK>(p, bias_s, tmem_base + (uint32_t)(acc * p.BN), b, t0, grp, n0, q, half, lane, wait_acc);
+      else
+        wait_acc();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -768,9 +857,11 @@ __global__ void __launch_bounds__(TC_FWD_THREADS) conv_tc_fwdh_k(const __grid_co
   } else {
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    tc_epilogue_tile<ACT, EPI, OUT, MASK>(p, bias_s, tmem_base, b, t0, grp, n0, q, half, lane);
+    auto wait_acc = [&]() {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+    };
+    tc_epilogue_tile<ACT, EPI, OUT, MASK>(p, bias_s, tmem_base, b, t0, grp, n0, q, half, lane, wait_acc);
   }
   tc_fence_before();
   __syncthreads();

@@ -71,6 +71,101 @@ __global__ void select_bwd_k(const float* __restrict__ dy, const int64_t* __rest
   }
 }
 
+// The discriminator's output layer with the label gather folded in (model/discriminator.py:36,49-51: a k3 conv to one
+// logit track per speaker, of which only the target speaker's row is kept).  Only that row is computed:
+//   y[b, t] = sum_{c, k} w[label[b], c, k] * x[b, c, t + k - pad]          (stride 1, zero padding, no bias)
+// one CTA per (sample, 32 time steps); warp = channel slice, lane = time step; the 32 partial sums meet in shared memory.
+constexpr int SELCONV_MAX_K = 8;
+
+__global__ void __launch_bounds__(1024) select_conv_fwd_k(const float* __restrict__ x, const float* __restrict__ w,
+                                                          const int64_t* __restrict__ label, float* __restrict__ y, int C, int T,
+                                                          int NC, int K, int pad) {
+  pdl_prologue();
+  __shared__ float sm[32][33];
+  const int b = blockIdx.y, lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int t = blockIdx.x * 32 + lane;
+  const long long l = label[b];
+  float acc = 0.f;
+  if (l >= 0 && l < NC && t < T) {
+    const float* xb = x + (long long)b * C * T;
+    const float* wl = w + l * (long long)C * K;
+    for (int c = slice; c < C; c += 32) {
+      const float* xr = xb + (long long)c * T;
+      const float* wr = wl + (long long)c * K;
+      for (int k = 0; k < K; ++k) {
+        const int u = t + k - pad;
+        if (u >= 0 && u < T) acc = fmaf(__ldg(wr + k), __ldg(xr + u), acc);
+      }
+    }
+  }
+  sm[slice][lane] = acc;
+  __syncthreads();
+  if (slice == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s += sm[i][lane];
+    if (t < T) y[(long long)b * T + t] = s;
+  }
+}
+
+// Backward of the above.  One warp per (sample, channel) row, lanes over time:
+//   dx[b, c, t]          = sum_k w[label[b], c, k] * dy[b, t - k + pad]                       (dx != nullptr)
+//   dw[label[b], c, k]  += sum_t dy[b, t] * x[b, c, t + k - pad]                              (dw != nullptr, zero-filled by
+//                                                                                             the caller; samples may share a label)
+__global__ void __launch_bounds__(256) select_conv_bwd_k(const float* __restrict__ dy, const float* __restrict__ x,
+                                                         const float* __restrict__ w, const int64_t* __restrict__ label,
+                                                         float* __restrict__ dx, float* __restrict__ dw, int B, int C, int T,
+                                                         int NC, int K, int pad) {
+  pdl_prologue();
+  const int lane = threadIdx.x & 31;
+  const long long rows = (long long)B * C;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < rows; row += warps) {
+    const int b = (int)(row / C), c = (int)(row - (long long)b * C);
+    const long long l = label[b];
+    const bool ok = l >= 0 && l < NC;
+    const float* dyb = dy + (long long)b * T;
+    const float* xr = x + row * T;
+    float wk[SELCONV_MAX_K];
+#pragma unroll
+    for (int k = 0; k < SELCONV_MAX_K; ++k) wk[k] = (ok && k < K) ? __ldg(w + (l * C + c) * K + k) : 0.f;
+    float dwk[SELCONV_MAX_K];
+#pragma unroll
+    for (int k = 0; k < SELCONV_MAX_K; ++k) dwk[k] = 0.f;
+    for (int t0 = 0; t0 < T; t0 += 32) {
+      const int t = t0 + lane;
+      if (t < T) {
+        if (dx) {
+          float s = 0.f;
+#pragma unroll
+          for (int k = 0; k < SELCONV_MAX_K; ++k) {
+            const int u = t - k + pad;
+            if (k < K && u >= 0 && u < T) s = fmaf(wk[k], __ldg(dyb + u), s);
+          }
+          dx[row * T + t] = s;
+        }
+        if (dw && ok) {
+          const float g = __ldg(dyb + t);
+#pragma unroll
+          for (int k = 0; k < SELCONV_MAX_K; ++k) {
+            const int u = t + k - pad;
+            if (k < K && u >= 0 && u < T) dwk[k] = fmaf(g, __ldg(xr + u), dwk[k]);
+          }
+        }
+      }
+    }
+    if (dw && ok) {
+#pragma unroll
+      for (int k = 0; k < SELCONV_MAX_K; ++k) {
+        if (k < K) {
+          const float s = warp_sum(dwk[k]);
+          if (lane == 0) atomicAdd(dw + (l * C + c) * K + k, s);
+        }
+      }
+    }
+  }
+}
+
 __global__ void sq_err_const_sum_k(const float* __restrict__ a, float target, float scale, float* __restrict__ out,
                                    long long n) {
   pdl_prologue();
@@ -345,6 +440,29 @@ extern "C" int tdvc_select_channel_bwd(const float* dy, const int64_t* label, fl
   TDVC_CHECK_ARG(B >= 0 && C > 0 && T > 0 && dy && label && dx);
   if (B == 0) return TDVC_OK;
   tdvc::launch_k(select_bwd_k, ew_blocks((long long)B * C * T), 256, 0, (cudaStream_t)stream, dy, label, dx, B, C, T);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_conv1d_select_fwd(const float* x, const float* w, const int64_t* label, float* y, int B, int C, int T,
+                                      int NC, int K, int pad, void* stream) {
+  TDVC_CHECK_ARG(B >= 0 && C > 0 && T > 0 && NC > 0 && K > 0 && K <= SELCONV_MAX_K && pad >= 0 && 2 * pad == K - 1);
+  TDVC_CHECK_ARG(x && w && label && y);
+  if (B == 0) return TDVC_OK;
+  tdvc::launch_k(select_conv_fwd_k, dim3((unsigned)cdiv(T, 32), (unsigned)B), 1024, 0, (cudaStream_t)stream, x, w, label, y, C, T,
+                 NC, K, pad);
+  TDVC_LAUNCH_CHECK();
+  return TDVC_OK;
+}
+
+extern "C" int tdvc_conv1d_select_bwd(const float* dy, const float* x, const float* w, const int64_t* label, float* dx,
+                                      float* dw, int B, int C, int T, int NC, int K, int pad, void* stream) {
+  TDVC_CHECK_ARG(B >= 0 && C > 0 && T > 0 && NC > 0 && K > 0 && K <= SELCONV_MAX_K && pad >= 0 && 2 * pad == K - 1);
+  TDVC_CHECK_ARG(dy && x && w && label && (dx || dw));
+  if (B == 0) return TDVC_OK;
+  const long long rows = (long long)B * C;
+  const int blocks = (int)std::max<long long>(1, std::min<long long>((rows + 7) / 8, 16LL * num_sms()));
+  tdvc::launch_k(select_conv_bwd_k, blocks, 256, 0, (cudaStream_t)stream, dy, x, w, label, dx, dw, B, C, T, NC, K, pad);
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }

@@ -49,8 +49,9 @@ class Discriminator(nn.Module):
         for conv, act in self.discriminator:
             x = conv(x, out_act="lrelu", out_slope=act.negative_slope)      # conv + bias + LeakyReLU: one launch
             features.append(x)
-        logits = self.output(x)
-        return ops.select_channel(logits, label_tgt.view(-1)), features     # x.gather(1, label), discriminator.py:49-51
+        # output conv + x.gather(1, label) (discriminator.py:36,49-51): only the target speaker's logit track is computed
+        out = self.output
+        return ops.conv1d_select(x, out.effective_weight(), label_tgt.view(-1)), features
 
 
 class _DiscriminatorBank(nn.Module):

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtdvc_b200.so")
+# TDVC_LIB: another build of the same library (A/B measurements of compile-time variants); default: the in-tree build
+LIB_PATH = os.environ.get("TDVC_LIB") or os.path.join(_HERE, "libtdvc_b200.so")
 
 c_float_p = C.c_void_p  # device pointers travel as void*
 
@@ -114,6 +115,8 @@ SIGNATURES = {
     "tdvc_avgpool4s2_bwd": (_I, [_P, _P, _I, _I, _I, _P]),
     "tdvc_select_channel_fwd": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "tdvc_select_channel_bwd": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "tdvc_conv1d_select_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "tdvc_conv1d_select_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "tdvc_sq_err_const_sum": (_I, [_P, _F, _F, _P, _L, _P]),
     "tdvc_sq_err_const_bwd": (_I, [_P, _F, _F, _P, _P, _L, _P]),
     "tdvc_abs_diff_sum": (_I, [_P, _P, _F, _P, _L, _P]),

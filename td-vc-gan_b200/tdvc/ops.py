@@ -927,6 +927,53 @@ def select_channel(x, label):
     return _SelectChannel.apply(x, label)
 
 
+class _Conv1dSelect(torch.autograd.Function):
+    """conv1d(x, w, padding=(K-1)/2).gather(1, label) computing only the gathered row (tdvc_conv1d_select_*)."""
+
+    @staticmethod
+    def forward(ctx, x, w, label):
+        _req(x, w)
+        x, w = _c(x), _c(w)
+        if not label.is_cuda or label.dtype != torch.int64:
+            raise RuntimeError("conv1d_select: label must be a CUDA int64 tensor")
+        label = label.contiguous()
+        B, Cc, T = x.shape
+        NC, Cw, K = w.shape
+        if Cw != Cc or K % 2 != 1 or K > 7 or label.numel() != B:
+            raise RuntimeError(f"conv1d_select: weight {tuple(w.shape)} / label {tuple(label.shape)} do not match input "
+                               f"{tuple(x.shape)} (odd K <= 7)")
+        y = torch.empty(B, 1, T, device=x.device, dtype=torch.float32)
+        _lib.check(_lib.load().tdvc_conv1d_select_fwd(_p(x), _p(w), _p(label), _p(y), B, Cc, T, NC, K, (K - 1) // 2, _st()),
+                   "conv1d_select_fwd")
+        ctx.save_for_backward(x, w, label)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, label = ctx.saved_tensors
+        B, Cc, T = x.shape
+        NC, _, K = w.shape
+        dy = _c(dy)
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = torch.zeros_like(w) if ctx.needs_input_grad[1] else None       # accumulated into: samples may share a label
+        if dx is not None or dw is not None:
+            _lib.check(_lib.load().tdvc_conv1d_select_bwd(_p(dy), _p(x), _p(w), _p(label), _p(dx), _p(dw), B, Cc, T, NC, K,
+                                                          (K - 1) // 2, _st()), "conv1d_select_bwd")
+        return dx, dw, None
+
+
+_FUSED_SELECT = os.environ.get("TDVC_FUSED_SELECT", "1") != "0"   # development switch: 0 = full output conv, then the gather
+
+
+def conv1d_select(x, weight, label):
+    """The discriminator's output layer and label gather (model/discriminator.py:36,49-51) as one op:
+    conv1d(x, weight, padding=(K-1)//2) restricted to output row label[b] of sample b -> [B, 1, T].  Only the selected
+    rows are computed (1 / num_classes of the layer's multiply-adds), in fp32 in every precision mode."""
+    if not _FUSED_SELECT:
+        return select_channel(conv1d(x, weight, None, padding=(weight.shape[2] - 1) // 2), label)
+    return _Conv1dSelect.apply(x, weight, label)
+
+
 # ----------------------------------------------------------------------------- losses
 
 class _SqErrConstMean(torch.autograd.Function):

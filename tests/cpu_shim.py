@@ -92,6 +92,10 @@ def select_channel(x, label):
     return x.gather(1, label.view(-1, 1, 1).expand(-1, 1, x.shape[2]))
 
 
+def conv1d_select(x, weight, label):
+    return select_channel(F.conv1d(x, weight, None, padding=(weight.shape[2] - 1) // 2), label)
+
+
 def mse_to_const_sum(tensors, target):
     return sum(((t - target) ** 2).mean() for t in tensors)
 
@@ -122,7 +126,7 @@ def installed():
                  grad_reverse=_GradReverse.apply, l2_normalize=lambda x: F.normalize(x, dim=1), cond_concat=cond_concat,
                  cond_concat_front=cond_concat_front, instance_norm=instance_norm, cond_instance_norm=cond_instance_norm,
                  time_mean=lambda x: x.mean(dim=2), avg_pool_4_2_1=lambda x: F.avg_pool1d(x, 4, 2, 1, count_include_pad=False),
-                 select_channel=select_channel, mse_to_const_sum=mse_to_const_sum, l1_mean_sum=l1_mean_sum,
+                 select_channel=select_channel, conv1d_select=conv1d_select, mse_to_const_sum=mse_to_const_sum, l1_mean_sum=l1_mean_sum,
                  l1_mean_sum_rows=l1_mean_sum_rows, contrastive_loss=contrastive_loss, mrf_cond_path_eligible=_false,
                  film_posconv_eligible=_false)
     saved = {k: getattr(ops, k) for k in table}

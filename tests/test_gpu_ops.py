@@ -265,6 +265,44 @@ def test_pool_select_losses_adamw():
 
 
 # ----------------------------------------------------------------------------- log-mel loss pieces (mel.cu)
+@pytest.mark.parametrize("B,C,T,NC,K,labels", [
+    (4, 1024, 35, 100, 3, [7, 99, 7, 0]),        # D tail at the full rate; two samples share a label (rows of dw add up)
+    (3, 64, 9, 10, 3, [9, 9, 9]),                # shortest scale
+    (2, 48, 70, 5, 5, [4, 1]),                   # more than one 32-step tile, k5
+    (1, 16, 1, 3, 3, [2]),                       # a single time step: only the centre tap sees data
+])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_conv1d_select(B, C, T, NC, K, labels, mode):
+    """Output conv + label gather as one op (model/discriminator.py:36,49-51) against conv1d(...).gather(1, label) in fp64:
+    forward, dL/dx and dL/dw (fp32 arithmetic in both precision modes), and the unfused path as a cross-check."""
+    from tdvc import ops
+    x = rnd(B, C, T, seed=1).requires_grad_(True)
+    w = rnd(NC, C, K, seed=2, scale=(C * K) ** -0.5).requires_grad_(True)
+    lab = torch.tensor(labels)
+    ref = F.conv1d(x, w, None, padding=(K - 1) // 2).gather(1, lab.view(-1, 1, 1).expand(-1, 1, T))
+    proj = rnd(B, 1, T, seed=3)
+    (ref * proj).sum().backward()
+    ops.set_precision(mode)
+    try:
+        xd, wd = dev(x), dev(w)
+        y = ops.conv1d_select(xd, wd, lab.cuda())
+        (y * proj.float().cuda()).sum().backward()
+        torch.cuda.synchronize()
+    finally:
+        ops.set_precision("fp32")
+    assert y.shape == (B, 1, T)
+    assert relerr(y, ref) < TOL
+    assert relerr(xd.grad, x.grad) < TOL
+    assert relerr(wd.grad, w.grad) < TOL_W
+    # rows of speakers that are not in the batch receive exactly zero
+    unused = [c for c in range(NC) if c not in labels]
+    assert float(wd.grad[unused].abs().max()) == 0.0 if unused else True
+    # frozen weights (the G step): only dL/dx is produced
+    xd2, wd2 = dev(x), w.detach().float().cuda()
+    (ops.conv1d_select(xd2, wd2, lab.cuda()) * proj.float().cuda()).sum().backward()
+    assert relerr(xd2.grad, x.grad) < TOL
+
+
 @pytest.mark.parametrize("B,T,n_fft,split", [(3, 8960, 2048, False), (2, 2600, 512, False), (3, 8960, 2048, True)])
 def test_stft_frames_power_logclamp(B, T, n_fft, split):
     """Framing with reflect padding + window (and its adjoint), |X|^2 over stacked (re | im) rows, log(clamp): against
