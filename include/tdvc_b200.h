@@ -179,7 +179,7 @@ int tdvc_select_channel_bwd(const float* dy, const int64_t* label, float* dx /*z
 /* ---- the discriminator's output layer with the label gather folded in (model/discriminator.py:36 `self.output`, a
  *      weight-normed Conv1d(width, num_classes, 3, padding=1, bias=False), followed by :49-51 `x.gather(1, label)`):
  *      only the selected speaker's row is computed,
- *        y[b,0,t] = sum_{c,k} w[label[b], c, k] * x[b, c, t + k - pad]      (stride 1, zero padding, 2*pad = K-1 <= 7);
+ *        y[b,0,t] = sum_{c,k} w[label[b], c, k] * x[b, c, t + k - pad]      (stride 1, zero padding, K in {1,3,5,7}, pad = (K-1)/2);
  *      a label outside [0, NC) yields zeros.  bwd: dx[B,C,T] (may be NULL) and dw[NC,C,K] (may be NULL; ACCUMULATED into,
  *      the caller zero-fills it: samples that share a label add into the same row). */
 int tdvc_conv1d_select_fwd(const float* x, const float* w, const int64_t* label, float* y, int B, int C, int T, int NC,

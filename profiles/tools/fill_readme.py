@@ -21,6 +21,7 @@ def load(name):
 
 d = load("final_stage1.json")
 dp = load("final_dp2.json")
+dp_base = load("build_21p3ms_stage1.json")      # the 1-GPU line of the build the 2-GPU run was taken on
 kf = d["kernel_families"]
 rows = ["| kernel | launches | ms | share of busy time |", "|---|---|---|---|"]
 for t in kf["top"][:16]:
@@ -47,7 +48,8 @@ inf.append(f"Best: B = {best['batch']}, **{best['x_realtime']:.0f}× real time**
            f"per call; round 2 before the bf16-resident stages: 2 390×).")
 ws = next(f for f in kf["conv_families"] if "conv_tc_ws_k" in f["family"])
 dp_text = (f"Batch-sharded, full replicas, weak scaling (B = 16 per GPU). 2 GPUs: **{dp['ms_per_step']:.2f} ms/step, {dp['value']:.1f} audio-s/s = "
-           f"{dp['value'] / d['value']:.3f}× the 1-GPU value of the same build** (`r2/final_dp2.json`): the iteration is three CUDA-graph segments with "
+           f"{dp['value'] / dp_base['value']:.3f}× the 1-GPU value of the same build** (`r2/final_dp2.json`, `r2/build_21p3ms_stage1.json`: the build before the "
+           f"last two changes, {dp_base['ms_per_step']:.1f} ms/step on one GPU): the iteration is three CUDA-graph segments with "
            f"the flat all-reduces of D's (71 MB) and G's (59 MB) gradient banks between them; 4 GPUs on an earlier build of the day (22.6 ms on one GPU): 23.14 ms/step, "
            f"1549 audio-s/s = 3.91× its 1-GPU value (`r2/dp4_23p1ms_build_u.json`). Hook-driven bucketed all-reduces overlapped with the "
            f"backward exist for eager steps (`tdvc/dp.py:BucketedReducer`); captured into the step graph they never returned on this stack "

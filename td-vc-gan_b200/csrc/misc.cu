@@ -75,26 +75,44 @@ __global__ void select_bwd_k(const float* __restrict__ dy, const int64_t* __rest
 // logit track per speaker, of which only the target speaker's row is kept).  Only that row is computed:
 //   y[b, t] = sum_{c, k} w[label[b], c, k] * x[b, c, t + k - pad]          (stride 1, zero padding, no bias)
 // one CTA per (sample, 32 time steps); warp = channel slice, lane = time step; the 32 partial sums meet in shared memory.
-constexpr int SELCONV_MAX_K = 8;
-
+template <int K>
 __global__ void __launch_bounds__(1024) select_conv_fwd_k(const float* __restrict__ x, const float* __restrict__ w,
                                                           const int64_t* __restrict__ label, float* __restrict__ y, int C, int T,
-                                                          int NC, int K, int pad) {
+                                                          int NC) {
   pdl_prologue();
+  constexpr int pad = (K - 1) / 2;
   __shared__ float sm[32][33];
   const int b = blockIdx.y, lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int t = blockIdx.x * 32 + lane;
   const long long l = label[b];
   float acc = 0.f;
   if (l >= 0 && l < NC && t < T) {
-    const float* xb = x + (long long)b * C * T;
+    const float* xt = x + (long long)b * C * T + t - pad;
     const float* wl = w + l * (long long)C * K;
-    for (int c = slice; c < C; c += 32) {
-      const float* xr = xb + (long long)c * T;
-      const float* wr = wl + (long long)c * K;
-      for (int k = 0; k < K; ++k) {
-        const int u = t + k - pad;
-        if (u >= 0 && u < T) acc = fmaf(__ldg(wr + k), __ldg(xr + u), acc);
+    bool in[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) in[k] = (t + k - pad >= 0) && (t + k - pad < T);
+    // every load of U channels is issued before the first multiply-add (a branch per tap serialised them: 96 dependent L2
+    // round trips per thread; now C / (32 U) batches of 2 K U independent loads)
+    constexpr int U = K <= 3 ? 8 : 4;
+    for (int c0 = slice; c0 < C; c0 += 32 * U) {
+      float xv[U][K], wv[U][K];
+#pragma unroll
+      for (int i = 0; i < U; ++i) {
+        const int c = c0 + 32 * i;
+        const bool c_ok = c < C;
+        const float* xr = xt + (long long)c * T;
+        const float* wr = wl + (long long)c * K;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          xv[i][k] = (c_ok && in[k]) ? __ldg(xr + k) : 0.f;
+          wv[i][k] = c_ok ? __ldg(wr + k) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < U; ++i) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc = fmaf(wv[i][k], xv[i][k], acc);
       }
     }
   }
@@ -112,11 +130,13 @@ __global__ void __launch_bounds__(1024) select_conv_fwd_k(const float* __restric
 //   dx[b, c, t]          = sum_k w[label[b], c, k] * dy[b, t - k + pad]                       (dx != nullptr)
 //   dw[label[b], c, k]  += sum_t dy[b, t] * x[b, c, t + k - pad]                              (dw != nullptr, zero-filled by
 //                                                                                             the caller; samples may share a label)
+template <int K>
 __global__ void __launch_bounds__(256) select_conv_bwd_k(const float* __restrict__ dy, const float* __restrict__ x,
                                                          const float* __restrict__ w, const int64_t* __restrict__ label,
                                                          float* __restrict__ dx, float* __restrict__ dw, int B, int C, int T,
-                                                         int NC, int K, int pad) {
+                                                         int NC) {
   pdl_prologue();
+  constexpr int pad = (K - 1) / 2;
   const int lane = threadIdx.x & 31;
   const long long rows = (long long)B * C;
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -126,41 +146,39 @@ __global__ void __launch_bounds__(256) select_conv_bwd_k(const float* __restrict
     const bool ok = l >= 0 && l < NC;
     const float* dyb = dy + (long long)b * T;
     const float* xr = x + row * T;
-    float wk[SELCONV_MAX_K];
+    float wk[K], dwk[K];
 #pragma unroll
-    for (int k = 0; k < SELCONV_MAX_K; ++k) wk[k] = (ok && k < K) ? __ldg(w + (l * C + c) * K + k) : 0.f;
-    float dwk[SELCONV_MAX_K];
-#pragma unroll
-    for (int k = 0; k < SELCONV_MAX_K; ++k) dwk[k] = 0.f;
+    for (int k = 0; k < K; ++k) {
+      wk[k] = ok ? __ldg(w + (l * C + c) * K + k) : 0.f;
+      dwk[k] = 0.f;
+    }
     for (int t0 = 0; t0 < T; t0 += 32) {
       const int t = t0 + lane;
       if (t < T) {
+        // dy taps t - pad .. t + pad serve both sums: dx uses dy[t - k + pad], dw uses dy[t] and x[t + k - pad]
+        float dyv[K], xv[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const int u = t + k - pad;
+          const bool in = u >= 0 && u < T;
+          dyv[k] = in ? __ldg(dyb + u) : 0.f;
+          xv[k] = (in && dw) ? __ldg(xr + u) : 0.f;
+        }
         if (dx) {
           float s = 0.f;
 #pragma unroll
-          for (int k = 0; k < SELCONV_MAX_K; ++k) {
-            const int u = t - k + pad;
-            if (k < K && u >= 0 && u < T) s = fmaf(wk[k], __ldg(dyb + u), s);
-          }
+          for (int k = 0; k < K; ++k) s = fmaf(wk[k], dyv[K - 1 - k], s);      // dy[t - k + pad] = tap K-1-k of the window
           dx[row * T + t] = s;
         }
-        if (dw && ok) {
-          const float g = __ldg(dyb + t);
 #pragma unroll
-          for (int k = 0; k < SELCONV_MAX_K; ++k) {
-            const int u = t + k - pad;
-            if (k < K && u >= 0 && u < T) dwk[k] = fmaf(g, __ldg(xr + u), dwk[k]);
-          }
-        }
+        for (int k = 0; k < K; ++k) dwk[k] = fmaf(dyv[pad], xv[k], dwk[k]);
       }
     }
     if (dw && ok) {
 #pragma unroll
-      for (int k = 0; k < SELCONV_MAX_K; ++k) {
-        if (k < K) {
-          const float s = warp_sum(dwk[k]);
-          if (lane == 0) atomicAdd(dw + (l * C + c) * K + k, s);
-        }
+      for (int k = 0; k < K; ++k) {
+        const float s = warp_sum(dwk[k]);
+        if (lane == 0) atomicAdd(dw + (l * C + c) * K + k, s);
       }
     }
   }
@@ -446,23 +464,35 @@ extern "C" int tdvc_select_channel_bwd(const float* dy, const int64_t* label, fl
 
 extern "C" int tdvc_conv1d_select_fwd(const float* x, const float* w, const int64_t* label, float* y, int B, int C, int T,
                                       int NC, int K, int pad, void* stream) {
-  TDVC_CHECK_ARG(B >= 0 && C > 0 && T > 0 && NC > 0 && K > 0 && K <= SELCONV_MAX_K && pad >= 0 && 2 * pad == K - 1);
+  TDVC_CHECK_ARG(B >= 0 && C > 0 && T > 0 && NC > 0 && (K == 1 || K == 3 || K == 5 || K == 7) && 2 * pad == K - 1);
   TDVC_CHECK_ARG(x && w && label && y);
   if (B == 0) return TDVC_OK;
-  tdvc::launch_k(select_conv_fwd_k, dim3((unsigned)cdiv(T, 32), (unsigned)B), 1024, 0, (cudaStream_t)stream, x, w, label, y, C, T,
-                 NC, K, pad);
+  const dim3 grid((unsigned)cdiv(T, 32), (unsigned)B);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (K) {
+    case 1: tdvc::launch_k(select_conv_fwd_k<1>, grid, 1024, 0, st, x, w, label, y, C, T, NC); break;
+    case 3: tdvc::launch_k(select_conv_fwd_k<3>, grid, 1024, 0, st, x, w, label, y, C, T, NC); break;
+    case 5: tdvc::launch_k(select_conv_fwd_k<5>, grid, 1024, 0, st, x, w, label, y, C, T, NC); break;
+    default: tdvc::launch_k(select_conv_fwd_k<7>, grid, 1024, 0, st, x, w, label, y, C, T, NC); break;
+  }
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
 
 extern "C" int tdvc_conv1d_select_bwd(const float* dy, const float* x, const float* w, const int64_t* label, float* dx,
                                       float* dw, int B, int C, int T, int NC, int K, int pad, void* stream) {
-  TDVC_CHECK_ARG(B >= 0 && C > 0 && T > 0 && NC > 0 && K > 0 && K <= SELCONV_MAX_K && pad >= 0 && 2 * pad == K - 1);
+  TDVC_CHECK_ARG(B >= 0 && C > 0 && T > 0 && NC > 0 && (K == 1 || K == 3 || K == 5 || K == 7) && 2 * pad == K - 1);
   TDVC_CHECK_ARG(dy && x && w && label && (dx || dw));
   if (B == 0) return TDVC_OK;
   const long long rows = (long long)B * C;
   const int blocks = (int)std::max<long long>(1, std::min<long long>((rows + 7) / 8, 16LL * num_sms()));
-  tdvc::launch_k(select_conv_bwd_k, blocks, 256, 0, (cudaStream_t)stream, dy, x, w, label, dx, dw, B, C, T, NC, K, pad);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (K) {
+    case 1: tdvc::launch_k(select_conv_bwd_k<1>, blocks, 256, 0, st, dy, x, w, label, dx, dw, B, C, T, NC); break;
+    case 3: tdvc::launch_k(select_conv_bwd_k<3>, blocks, 256, 0, st, dy, x, w, label, dx, dw, B, C, T, NC); break;
+    case 5: tdvc::launch_k(select_conv_bwd_k<5>, blocks, 256, 0, st, dy, x, w, label, dx, dw, B, C, T, NC); break;
+    default: tdvc::launch_k(select_conv_bwd_k<7>, blocks, 256, 0, st, dy, x, w, label, dx, dw, B, C, T, NC); break;
+  }
   TDVC_LAUNCH_CHECK();
   return TDVC_OK;
 }
