@@ -49,7 +49,7 @@ inf.append(f"Best: B = {best['batch']}, **{best['x_realtime']:.0f}× real time**
 ws = next(f for f in kf["conv_families"] if "conv_tc_ws_k" in f["family"])
 dp_text = (f"Batch-sharded, full replicas, weak scaling (B = 16 per GPU). 2 GPUs: **{dp['ms_per_step']:.2f} ms/step, {dp['value']:.1f} audio-s/s = "
            f"{dp['value'] / dp_base['value']:.3f}× the 1-GPU value of the same build** (`r2/final_dp2.json`, `r2/build_21p3ms_stage1.json`: the build before the "
-           f"last two changes, {dp_base['ms_per_step']:.1f} ms/step on one GPU): the iteration is three CUDA-graph segments with "
+           f"last three changes, {dp_base['ms_per_step']:.1f} ms/step on one GPU): the iteration is three CUDA-graph segments with "
            f"the flat all-reduces of D's (71 MB) and G's (59 MB) gradient banks between them; 4 GPUs on an earlier build of the day (22.6 ms on one GPU): 23.14 ms/step, "
            f"1549 audio-s/s = 3.91× its 1-GPU value (`r2/dp4_23p1ms_build_u.json`). Hook-driven bucketed all-reduces overlapped with the "
            f"backward exist for eager steps (`tdvc/dp.py:BucketedReducer`); captured into the step graph they never returned on this stack "

@@ -49,6 +49,21 @@ __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 bool pdl_enabled();
+// The tensor-core kernels run the part of their prologue that touches no global memory -- mbarrier initialisation, tensor-map
+// prefetch, TMEM allocation, shared-memory constants -- BEFORE griddepcontrol.wait, so it overlaps the tail of the preceding
+// kernel instead of following it; everything that reads global memory (bias, TMA loads, epilogue operands) stays behind the
+// wait.  launch_dependents is issued together with the wait as before: a dependent grid starts only when every CTA of this
+// one is resident, so blocks that sit in the wait (holding shared memory / TMEM columns) cannot starve their predecessor.
+// -DTDVC_PDL_LATE_WAIT=0 puts the wait back at the top of the kernel.
+#ifndef TDVC_PDL_LATE_WAIT
+#define TDVC_PDL_LATE_WAIT 1
+#endif
+__device__ __forceinline__ void pdl_prologue_top() {
+  if (!TDVC_PDL_LATE_WAIT) pdl_prologue();
+}
+__device__ __forceinline__ void pdl_prologue_late() {
+  if (TDVC_PDL_LATE_WAIT) pdl_prologue();
+}
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

@@ -432,7 +432,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcP& p, const float* bias
 template <int ACT, int EPI, int OUT, int MASK>
 __global__ void __launch_bounds__(TC_FWD_THREADS) conv_tc_fwd_k(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_b, TcP p) {
-  pdl_prologue();
+  pdl_prologue_top();
   __shared__ __align__(16) float bias_s[256];      // bias of this N tile (zeros when absent)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B atoms need 1024-B alignment
@@ -447,8 +447,6 @@ __global__ void __launch_bounds__(TC_FWD_THREADS) conv_tc_fwd_k(const __grid_con
   const int t0 = blockIdx.x * TC_BM;
   const int grp = blockIdx.y / p.tiles_per_group;
   const int n0 = (blockIdx.y - grp * p.tiles_per_group) * p.BN;       // channel offset inside the group
-  for (int i = threadIdx.x; i < p.BN; i += TC_FWD_THREADS)
-    bias_s[i] = (p.bias && n0 + i < p.Cout) ? __ldg(p.bias + grp * p.bias_stride + n0 + i) : 0.f;
   const int b = blockIdx.z;
   // a group may use fewer taps than the weight tensor holds (the k = 3 / 7 branches next to k = 11): the centred ones
   const int kgrp = p.kg[grp & 3] > 0 ? p.kg[grp & 3] : p.K;
@@ -466,6 +464,9 @@ __global__ void __launch_bounds__(TC_FWD_THREADS) conv_tc_fwd_k(const __grid_con
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1 && !(p.debug & 16)) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  pdl_prologue_late();
+  for (int i = threadIdx.x; i < p.BN; i += TC_FWD_THREADS)
+    bias_s[i] = (p.bias && n0 + i < p.Cout) ? __ldg(p.bias + grp * p.bias_stride + n0 + i) : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -564,7 +565,7 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) conv_tc_ws_k(const __grid_c
                                                                   const __grid_constant__ CUtensorMap map_b,
                                                                   const __grid_constant__ CUtensorMap map_an,
                                                                   const __grid_constant__ CUtensorMap map_bn, TcP p, WsP w) {
-  pdl_prologue();
+  pdl_prologue_top();
   __shared__ __align__(16) float bias_s[256];
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -598,8 +599,6 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) conv_tc_ws_k(const __grid_c
     cta_i = blockIdx.x;
     cta_n = gridDim.x;
   }
-  for (int i = threadIdx.x; i < p.BN; i += TC_FWD_THREADS)
-    bias_s[i] = (p.bias && n0 + i < p.Cout) ? __ldg(p.bias + grp * p.bias_stride + n0 + i) : 0.f;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -620,6 +619,9 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) conv_tc_ws_k(const __grid_c
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  pdl_prologue_late();
+  for (int i = threadIdx.x; i < p.BN; i += TC_FWD_THREADS)
+    bias_s[i] = (p.bias && n0 + i < p.Cout) ? __ldg(p.bias + grp * p.bias_stride + n0 + i) : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -764,7 +766,7 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 1) conv_tc_ws_k(const __grid_c
 template <int ACT, int EPI, int OUT, int MASK>
 __global__ void __launch_bounds__(TC_FWD_THREADS) conv_tc_fwdh_k(const __grid_constant__ CUtensorMap map_a,
                                                                  const __grid_constant__ CUtensorMap map_b, TcP p) {
-  pdl_prologue();
+  pdl_prologue_top();
   __shared__ __align__(16) float bias_s[256];
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -783,8 +785,6 @@ __global__ void __launch_bounds__(TC_FWD_THREADS) conv_tc_fwdh_k(const __grid_co
   const int t0 = blockIdx.x * TC_BM;
   const int grp = blockIdx.y / p.tiles_per_group;
   const int n0 = (blockIdx.y - grp * p.tiles_per_group) * p.BN;
-  for (int i = threadIdx.x; i < p.BN; i += TC_FWD_THREADS)
-    bias_s[i] = (p.bias && n0 + i < p.Cout) ? __ldg(p.bias + grp * p.bias_stride + n0 + i) : 0.f;
   const int b = blockIdx.z;
   const int kgrp = p.kg[grp & 3] > 0 ? p.kg[grp & 3] : p.K;
   const int tap_lo = (p.K - kgrp) >> 1;
@@ -798,6 +798,9 @@ __global__ void __launch_bounds__(TC_FWD_THREADS) conv_tc_fwdh_k(const __grid_co
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  pdl_prologue_late();
+  for (int i = threadIdx.x; i < p.BN; i += TC_FWD_THREADS)
+    bias_s[i] = (p.bias && n0 + i < p.Cout) ? __ldg(p.bias + grp * p.bias_stride + n0 + i) : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();

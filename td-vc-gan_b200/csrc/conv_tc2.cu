@@ -62,7 +62,7 @@ __device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32
 
 __global__ void __launch_bounds__(W2_THREADS) conv_tc_wgrad2_k(const __grid_constant__ CUtensorMap map_x,
                                                                const __grid_constant__ CUtensorMap map_dy, Wg2P p) {
-  pdl_prologue();
+  pdl_prologue_top();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   // stage = [x: two 64-channel boxes (haloed: rows_x rows each; per tap: KT pairs of 64 rows)] [dy: nb_dy boxes of 64 rows]
@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(W2_THREADS) conv_tc_wgrad2_k(const __grid_cons
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  pdl_prologue_late();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
