@@ -336,12 +336,31 @@ def run_ours(args):
         print(json.dumps(out), flush=True)
 
 
-FAMILY_OF = (("conv_tc_wgrad_k", 3), ("conv_tc_wt_k", 2), ("conv_tc_ws_k", 1), ("conv_tc_fwd_k", 0), ("mrf_chain", 5),
-             ("conv_fwd_k", 4), ("conv_tr_k", 4), ("conv_wgrad_k", 4))
-FAMILY_NAME = {0: "conv_tc_fwd_k (tcgen05, one tile per CTA: fwd + dgrad of the small convs)",
+# conv kernel families = the counters of tdvc_flop_count(): a kernel name (CUPTI, template arguments kept) -> the family whose
+# 2*MAC counter its launches feed (csrc: g_flops[...]).  The chain epilogues (second template argument >= 3) are instances of
+# the ws / fwdh / fwd kernels but count as their own family; the finalize passes of the weight gradients belong to them.
+FAMILY_NAME = {0: "conv_tc_fwd_k + conv_tc_fwdh_k (tcgen05, one tile per CTA, streamed weights: C >= 128 layers, short sequences, their data gradients)",
                1: "conv_tc_ws_k (tcgen05, weight-stationary persistent)", 2: "conv_tc_wt_k (tcgen05, stacked cond_var.0)",
-               3: "conv_tc_wgrad_k (tcgen05 weight gradients)", 4: "fp32 CUDA-core convs (1-channel stems, 8-channel excitation pyramid, FIR filters)",
-               5: "fused MRF chain kernels (tcgen05)"}
+               3: "conv_tc_wgrad2_k + conv_tc_wgrad2s_k + finalize (tcgen05 weight gradients)",
+               4: "fp32 CUDA-core convs (1-channel stems, 8-channel excitation pyramid, FIR filters, their gradients)",
+               5: "MRF chain epilogues of conv_tc_ws_k / conv_tc_fwdh_k (EPI 3-6, tcgen05)"}
+
+
+def family_of(name):
+    """Family index (FAMILY_NAME) of a kernel name, or None for kernels that are not convolutions."""
+    import re
+    m = re.search(r"conv_tc_(ws|fwdh|fwd)_k<\s*\d+,\s*(\d+)", name)
+    if m:
+        if int(m.group(2)) >= 3:
+            return 5
+        return 1 if m.group(1) == "ws" else 0
+    if "conv_tc_wt_k" in name:
+        return 2
+    if re.search(r"conv_tc_wgrad\w*_k|wgrad2s?_finalize\w*_k|wgrad_finalize\w*_k", name):
+        return 3
+    if re.search(r"(^|:)(conv_fwd_k|conv_tr_k|conv_wgrad_k|narrow_wgrad_k|stem_wgrad_k)", name):
+        return 4
+    return None
 
 
 def kernel_families(replay, fam_gflop):
@@ -385,12 +404,11 @@ def kernel_families(replay, fam_gflop):
            for k, v in sorted(busy.items(), key=lambda kv: -kv[1])[:24]]
     conv = {}
     for k, v in busy.items():
-        for pat, fam in FAMILY_OF:
-            if pat in k:
-                d = conv.setdefault(fam, {"family": FAMILY_NAME[fam], "launches": 0, "ms": 0.0})
-                d["launches"] += cnt[k]
-                d["ms"] += v
-                break
+        fam = family_of(k)
+        if fam is not None:
+            d = conv.setdefault(fam, {"family": FAMILY_NAME[fam], "id": fam, "launches": 0, "ms": 0.0})
+            d["launches"] += cnt[k]
+            d["ms"] += v
     for fam, d in conv.items():
         d["ms"] = round(d["ms"], 3)
         if fam_gflop is not None:
@@ -400,6 +418,37 @@ def kernel_families(replay, fam_gflop):
     return {"span_ms": round((t1 - t0) / 1e3, 3), "busy_ms": round(total, 3), "idle_ms": round(idle, 3),
             "activities": len(evs), "top": top, "slowest_launches": slowest,
             "conv_families": [conv[k] for k in sorted(conv, key=lambda k: -conv[k]["ms"])]}
+
+
+# families whose tensor-core launches were ALL captured by the final-build ncu metric pass (profiles/r2/final_ncu_conv_metrics.json:
+# -k regex:conv_tc_ws_k|conv_tc_fwdh_k|conv_tc_wgrad2s_k|conv_tc_wt_k); the others hold conv_tc_fwd_k / conv_tc_wgrad2_k launches too
+NCU_COMPLETE = (1, 2)
+
+
+def ncu_family_traffic(fam_id):
+    """`traffic` of a conv family: dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the family's launches
+    inside one step, from the committed ncu capture; None (with a note on what was captured) when the capture does not
+    hold every launch of the family."""
+    try:
+        with open(os.path.join(REPO, "profiles", "r2", "final_ncu_conv_metrics.json")) as f:
+            inst = json.load(f)["instances"]
+    except Exception:
+        return {"traffic": None}
+    n = nbytes = tens = us = 0.0
+    for name, k in inst.items():
+        if family_of(name) == fam_id:
+            n += k["launches"]
+            nbytes += k["launches"] * k["dram_bytes_per_launch"]
+            us += k["launches"] * k["us_per_launch"]
+            tens += k["launches"] * k["us_per_launch"] * k["tensor_pipe_pct_of_active"]
+    src = "profiles/r2/final_ncu_conv_metrics.json (ncu, one eager step of the 21.3 ms/step build)"
+    if n == 0:
+        return {"traffic": None, "traffic_note": f"no launch of this family in {src}"}
+    got = {"launches": int(n), "dram_bytes_per_launch": round(nbytes / n), "tensor_pipe_pct_of_active": round(tens / us, 2)}
+    if fam_id in NCU_COMPLETE:
+        return {"traffic": got["dram_bytes_per_launch"], "tensor_pipe_pct_of_active_ncu": got["tensor_pipe_pct_of_active"],
+                "traffic_source": f"{src}: dram__bytes_read.sum + dram__bytes_write.sum, mean over the family's {int(n)} launches"}
+    return {"traffic": None, "traffic_note": f"{src} holds only part of this family's launches: {got}"}
 
 
 def time_dominant_roofline(fams, pk, ms_step, step_gflop, flop_dom):
@@ -419,16 +468,7 @@ def time_dominant_roofline(fams, pk, ms_step, step_gflop, flop_dom):
                     share_of_step_time=round(fam["ms"] / ms_step, 4),
                     how="2*MAC handed to the family per step (tdvc_flop_count) / its busy time in one CUDA-graph replay "
                         "(CUPTI, taken inside bench.py after the timed region)")
-        try:   # DRAM bytes per launch of this family, averaged over its launches inside one step (committed ncu capture)
-            with open(os.path.join(REPO, "profiles", "r2", "final_ncu_conv_metrics.json")) as f:
-                m = json.load(f)
-            k = m["families"][fam["family"].split(" ")[0]]
-            base.update(traffic=k["dram_bytes_per_launch"],
-                        traffic_source="profiles/r2/final_ncu_conv_metrics.json: dram__bytes_read.sum + dram__bytes_write.sum, mean "
-                                       f"over the family's {k['launches']} launches of one step (ncu, 21.3 ms/step build)",
-                        tensor_pipe_pct_of_active_ncu=k["tensor_pipe_pct_of_active"])
-        except Exception:
-            pass
+        base.update(ncu_family_traffic(fam.get("id")))
     except Exception:
         base.update(achieved=flop_dom["achieved"], frac=round(flop_dom["achieved"] / peak, 5), kernel=flop_dom["kernel"],
                     how="family trace unavailable: the FLOP-dominant launch timed alone")

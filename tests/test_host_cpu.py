@@ -264,3 +264,30 @@ def test_step_scopes_nest_and_keep_plans_per_tag():
     assert sc._plan("G") is not sc._plan("D")
     with sc():
         assert sc.stack[-1].tag == "default"
+
+
+def test_bench_kernel_families_follow_the_flop_counters():
+    """bench.py attributes a kernel's time to the family whose tdvc_flop_count() counter its launches feed: chain
+    instances (second template argument 3..6) of the ws / fwdh / fwd kernels are their own family, fwdh belongs with fwd,
+    the finalize passes with the weight gradients -- a family's TFLOP/s divides like by like."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    cases = {
+        "tdvc::conv_tc_ws_k<0, 0, 0, 0>": 1, "tdvc::conv_tc_ws_k<1, 0, 1, 0>": 1, "tdvc::conv_tc_ws_k<0, 0, 1, 1>": 1,
+        "tdvc::conv_tc_ws_k<1, 3, 1, 0>": 5, "tdvc::conv_tc_ws_k<0, 6, 0, 1>": 5, "tdvc::conv_tc_fwdh_k<0, 5, 1, 1>": 5,
+        "tdvc::conv_tc_fwd_k<0, 4, 0, 0>": 5, "tdvc::conv_tc_fwdh_k<0, 0, 0, 0>": 0, "tdvc::conv_tc_fwd_k<1, 0, 0, 0>": 0,
+        "tdvc::conv_tc_wt_k<1, 0>": 2, "tdvc::conv_tc_wgrad2_k": 3, "tdvc::conv_tc_wgrad2s_k": 3, "tdvc::conv_tc_wgrad_k": 3,
+        "tdvc::wgrad2_finalize_wide_k": 3, "tdvc::wgrad2_finalize_k": 3, "tdvc::wgrad2s_finalize_k": 3,
+        "tdvc::conv_fwd_k<1, 32>": 4, "tdvc::conv_tr_k<1>": 4, "tdvc::conv_wgrad_k<1>": 4, "tdvc::narrow_wgrad_k": 4,
+        "tdvc::stem_wgrad_k": 4,
+        "tdvc::pack_cl_bf16_short_k": None, "tdvc::frame_pack_k<4>": None, "tdvc::adamw_blocks_k": None,
+        "at::native::vectorized_elementwise_kernel<4, at::native::CUD": None, "tdvc::select_conv_fwd_k<3>": None,
+    }
+    for name, fam in cases.items():
+        assert bench.family_of(name) == fam, name
+    assert set(bench.FAMILY_NAME) == {0, 1, 2, 3, 4, 5}
+    # traffic is quoted only for families whose launches the committed ncu capture holds completely
+    ws = bench.ncu_family_traffic(1)
+    assert ws["traffic"] and ws["traffic"] > 1e6 and "traffic_source" in ws
+    wg = bench.ncu_family_traffic(3)
+    assert wg["traffic"] is None and "part of this family" in wg["traffic_note"]
