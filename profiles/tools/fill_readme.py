@@ -27,10 +27,13 @@ rows = ["| kernel | launches | ms | share of busy time |", "|---|---|---|---|"]
 for t in kf["top"][:16]:
     rows.append(f"| `{t['kernel'].replace('tdvc::', '')}` | {t['launches']} | {t['ms']:.3f} | {100 * t['share_of_busy']:.1f} % |")
 rows.append(f"| all kernels of one replay | {kf['activities']} activities | busy {kf['busy_ms']:.2f}, idle {kf['idle_ms']:.2f} | |")
-fam = ["", "Conv families (2·MAC handed to the family per step ÷ its busy time):", "",
-       "| family | launches | ms | GF / step | TFLOP/s |", "|---|---|---|---|---|"]
-for f in kf["conv_families"]:
-    fam.append(f"| {f['family']} | {f['launches']} | {f['ms']:.2f} | {f['gflop_per_step']:.0f} | {f['tflops']:.0f} |")
+fam = ["", "Conv families (2·MAC handed to the family per step ÷ its busy time; `r2/final_stage1_families_corrected.json`, "
+       f"{load('final_stage1_families_corrected.json')['ms_per_step']:.2f} ms/step in that run):", "",
+       "| family | launches | ms | GF / step | TFLOP/s | of the sustained bf16 peak |", "|---|---|---|---|---|---|"]
+dc = load("final_stage1_families_corrected.json")     # same build, bench.py with the corrected kernel -> family map
+for f in dc["kernel_families"]["conv_families"]:
+    fam.append(f"| {f['family']} | {f['launches']} | {f['ms']:.2f} | {f['gflop_per_step']:.0f} | {f['tflops']:.0f} | "
+               f"{100 * f['tflops'] / 1382.4:.1f} % |")
 cfg_rows = ["| config | file | GF / step (reference) | ms/step | audio-s/s | TFLOP/s algorithmic | round-2 first measurement |", "|---|---|---|---|---|---|---|"]
 first = {"stage1": "47.0 ms", "stage2_1": "37.2 ms", "stage2_1_latcls": "48.7 ms", "stage2_2": "68.6 ms"}
 for n in ("stage1", "stage2_1", "stage2_1_latcls", "stage2_2"):
@@ -46,7 +49,7 @@ inf.append("")
 inf.append(f"Best: B = {best['batch']}, **{best['x_realtime']:.0f}× real time** = {best['tflops_algorithmic']:.0f} TFLOP/s = "
            f"{100 * best['tflops_algorithmic'] / 1382.4:.0f} % of the sustained peak (round 1: 2 142×, one batch size, weight norm recomputed "
            f"per call; round 2 before the bf16-resident stages: 2 390×).")
-ws = next(f for f in kf["conv_families"] if "conv_tc_ws_k" in f["family"])
+dom = dc["roofline"]
 dp_text = (f"Batch-sharded, full replicas, weak scaling (B = 16 per GPU). 2 GPUs: **{dp['ms_per_step']:.2f} ms/step, {dp['value']:.1f} audio-s/s = "
            f"{dp['value'] / dp_base['value']:.3f}× the 1-GPU value of the same build** (`r2/final_dp2.json`, `r2/build_21p3ms_stage1.json`: the build before the "
            f"last three changes, {dp_base['ms_per_step']:.1f} ms/step on one GPU): the iteration is three CUDA-graph segments with "
@@ -63,7 +66,8 @@ rep = {
     "@FAMILY_TABLE@": "\n".join(rows + fam), "@CONFIG_TABLE@": "\n".join(cfg_rows), "@INFER_TABLE@": "\n".join(inf),
     "@DP_TEXT@": dp_text, "@PARITY_FILE@": "final_parity_bf16.json",
     "@CPU_MS@": f"{1e3 * d['cpu_baseline']['s_per_step']:,.0f}".replace(",", " "), "@CPU_VALUE@": f"{d['cpu_baseline']['value']:.2f}",
-    "@WS_MS@": f"{ws['ms']:.2f}", "@WS_TF@": f"{ws['tflops']:.0f}", "@WS_FRAC@": f"{100 * ws['tflops'] / 1382.4:.1f}",
+    "@DOM_MS@": f"{dom['ms_per_step']:.2f}", "@DOM_TF@": f"{dom['achieved']:.0f}", "@DOM_FRAC@": f"{100 * dom['frac']:.1f}",
+    "@DOM_GF@": f"{dom['gflop_per_step']:.0f}", "@DOM_N@": f"{dom['launches_per_step']}", "@DOM_SHARE@": f"{100 * dom['share_of_step_time']:.0f}",
 }
 s = open(SRC).read()
 for k, v in rep.items():
